@@ -1,0 +1,187 @@
+/* lrr_gpu.h — C ABI of the B200-native CDCL robust-ICP backend (liblrr_b200.so).
+ *
+ * Drop-in boundary for the LRR hot path.  Every entry point cites the reference
+ * interface (file:line under the upstream msofka/LRR tree) it replaces.  Plain C: opaque handles,
+ * plain pointers and sizes, `int` status returns (0 = ok), no exceptions, no global state.
+ * One lrr_ctx per CUDA device; calls on one ctx are serialised by the caller — the reference
+ * estimators are single-threaded too (rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760).
+ *
+ * All feature arrays are HOST pointers in structure-of-arrays order (component-major):
+ *   xyz      : 3*n doubles  x[0..n) y[0..n) z[0..n)                       cdcl_feature::location_
+ *   P6       : 6*n doubles  Pxx Pxy Pxz Pyy Pyz Pzz (symmetric projector)  ::error_projector_
+ *   C6       : 6*n doubles  Cxx Cxy Cxz Cyy Cyz Czz, NULL for rrl          cdcl_feature::covariance_
+ *   strength : n doubles                                                   ::strength_
+ *   shape    : n bytes  0=CORNER 1=TUBE 2=SHEET                            ::shape_
+ *   dirs     : 9*n doubles d0x d0y d0z d1x d1y d1z d2x d2y d2z, NULL ok    ::directions_
+ * (cdcl/cdcl_feature.h:17-64, cdcl/cdcl_feature_with_shape.h:23-89, cdcl/cdcl_feature_ICP.h:23-96).
+ *
+ * The CPU oracle (oracle/liblrr_oracle.so, test infrastructure only) exports the same functions
+ * with the prefix `lrro_`, so parity tests run one script against both libraries.
+ */
+#ifndef LRR_GPU_H_
+#define LRR_GPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lrr_ctx  lrr_ctx;   /* one CUDA device + stream + scratch                          */
+typedef struct lrr_fset lrr_fset;  /* one uploaded feature set: SoA stream copy + NN grid records  */
+typedef struct lrr_est  lrr_est;   /* one estimator object (forward or symmetric)                  */
+
+/* status codes */
+enum {
+  LRR_OK = 0,
+  LRR_ERR_INVALID = 1,      /* bad argument                                                       */
+  LRR_ERR_UNSUPPORTED = 2,  /* (dim,dof,kind) the reference does not instantiate, see Q6           */
+  LRR_ERR_CUDA = 3,         /* CUDA runtime failure; lrr_ctx_last_error has the text               */
+  LRR_ERR_NO_DEVICE = 4,    /* no CUDA device: the product path has NO CPU fallback                */
+  LRR_ERR_STATE = 5         /* call order violated (e.g. metric before any match exists)           */
+};
+
+/* estimator kinds = the four reference classes on the path */
+enum {
+  LRR_CDCL_FWD = 0, /* cdcl_estimation_ICP_matching_all<dim,dof>            cdcl/cdcl_estimation_ICP_matching_all.h:34  */
+  LRR_CDCL_SYM = 1, /* cdcl_estimation_symmetric_ICP_matching_all<dim,dof>  cdcl/cdcl_estimation_symmetric_ICP_matching_all.h */
+  LRR_RRL_FWD  = 2, /* rrl_estimation_ICP_matching_all<dim,dof>             rrl/rrl_estimation_ICP_matching_all.h       */
+  LRR_RRL_SYM  = 3  /* rrl_estimation_symmetric_ICP_matching_all<dim,dof>   rrl/rrl_estimation_symmetric_ICP_matching_all.h */
+};
+
+/* transform kinds (cdcl/cdcl_trans_affine.h, cdcl/cdcl_trans_rigid3d.h) */
+enum { LRR_TRANS_AFFINE = 0, LRR_TRANS_RIGID3D = 1 };
+
+/* direction selector for symmetric estimators (forward_ / backward_ members) */
+enum { LRR_DIR_FORWARD = 0, LRR_DIR_BACKWARD = 1 };
+
+/* moving-set order policy: the reference calls vcl_random_shuffle(moving_) in every
+ * find_closest_euclidean (cdcl/...ICP_matching_all.txx:557, rrl/...ICP_matching_all.txx:508; Q4),
+ * unseeded libstdc++ rand().  The permutation is therefore an injectable input here. */
+enum {
+  LRR_ORDER_FIXED = 0,     /* keep the order given by lrr_est_set_order (identity by default)      */
+  LRR_ORDER_RESHUFFLE = 1  /* Fisher-Yates with SplitMix64(seed) applied cumulatively per call     */
+};
+
+/* scalar metrics (lrr_est_metric) */
+enum {
+  LRR_METRIC_RMS = 0,            /* RMS_error()      cdcl :196-230 ; rrl :211-241 (returns sum r^2, Q1) */
+  LRR_METRIC_WEIGHTED = 1,       /* weighted_error() cdcl :236-268 ; rrl :247-276                     */
+  LRR_METRIC_MEDIAN = 2,         /* median_error()   cdcl :159-190 ; rrl :177-205                     */
+  LRR_METRIC_SHEET_ANGLES = 3,   /* sheet_angles()   cdcl :273-323 ; rrl :281-323                     */
+  LRR_METRIC_TUBE_ANGLES = 4     /* tube_angles()    cdcl :328-382 ; rrl :328-375                     */
+};
+
+/* iteration-control state of a symmetric estimator (cdcl sym .h / rrl sym .h:203-224) */
+typedef struct lrr_est_state {
+  int64_t number_points[2];   /* number_points_ of forward_/backward_                             */
+  int64_t number_matches;     /* number_matches_ (ramp 1000, x2 ...)                               */
+  int32_t finest_level;       /* finest_level_                                                     */
+  int32_t oscillation_count;  /* oscillation_count_                                                */
+  double  error_difference;   /* error_difference_                                                 */
+  double  weighted_error;     /* weighted_error_                                                   */
+  double  scale[2];           /* last robust scale returned by estimate_scale_and_assign_weight    */
+  int32_t scale_estimated[2]; /* scale_estimated_                                                  */
+  int32_t iterations_done;    /* one_iteration calls since set_transform                           */
+  double  norm_center_moving[3], norm_center_fixed[3];  /* last normalisation (A9)                 */
+  double  norm_radius_moving, norm_radius_fixed;
+} lrr_est_state;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int  lrr_ctx_create(int device, lrr_ctx** out);
+void lrr_ctx_destroy(lrr_ctx* ctx);
+/* optional cudaStream_t; NULL = the context's own non-blocking stream */
+int  lrr_ctx_set_stream(lrr_ctx* ctx, void* cuda_stream);
+int  lrr_ctx_synchronize(lrr_ctx* ctx);
+const char* lrr_ctx_last_error(lrr_ctx* ctx);
+/* number of kernel launches issued by this context so far (bench `gpu_launches`) */
+int64_t lrr_ctx_launch_count(lrr_ctx* ctx);
+
+/* ---- feature sets ----------------------------------------------------------------------------
+ * Replaces the vector<feature_sptr> arguments of the estimator constructors and build_kd_trees()
+ * (cdcl/cdcl_estimation_ICP_matching_all.txx:113-135) / the Voronoi map of
+ * rrl/examples/compute_distance_map.cxx:55-151: the upload also builds the exact-NN uniform grid. */
+int  lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6,
+                         const double* strength, const uint8_t* shape, const double* dirs, lrr_fset** out);
+void lrr_features_destroy(lrr_fset* fs);
+int64_t lrr_features_size(const lrr_fset* fs);
+/* exact Euclidean 1-NN of n_query host points (SoA xyz) among the set; lowest index wins ties.
+ * Replaces rsdl_kd_tree::n_nearest(n=1) (cdcl :572) and the Voronoi lookup (rrl :530-543, Q5). */
+int  lrr_features_nearest(lrr_fset* fs, int64_t n_query, const double* q_xyz, int32_t* idx_out);
+
+/* ---- estimators ------------------------------------------------------------------------------ */
+/* ctor #3 semantics (cdcl sym .txx:144-164, rrl sym .txx:198-220): forward_ = (moving_inside -> fixed_all),
+ * backward_ = (fixed_inside -> moving_all).  Until lrr_est_set_subsets is called the inside sets are
+ * the whole sets.  Forward kinds ignore the backward half.  dim must be 3; dof 12 (affine) or 6
+ * (rigid3d, cdcl kinds only — Q6). */
+int  lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset* moving_all, lrr_fset* fixed_all, lrr_est** out);
+void lrr_est_destroy(lrr_est* est);
+/* set_features(moving_inside, fixed_inside)  (cdcl sym :206-226, rrl sym :269-289; forward: set_moving_data).
+ * Index lists into the *_all sets (the driver's deep clones, rrl/itkLocationRegistration.cxx:1346,1357). */
+int  lrr_est_set_subsets(lrr_est* est, const int32_t* moving_inside, int64_t nm, const int32_t* fixed_inside, int64_t nf);
+/* set_transform(trans): forward <- trans, backward <- trans->inverse(), scale_estimated_=false,
+ * number_points_=1000, ramp/oscillation state reset (cdcl :141-153, sym :231-242).  cov may be NULL (zeros). */
+int  lrr_est_set_transform(lrr_est* est, int trans_kind, const double* A9, const double* t3, const double* c3, const double* cov);
+/* normalize_matches() / weight_by_strength(bool)  (cdcl .h:92,117) */
+int  lrr_est_set_flags(lrr_est* est, int normalize_matches, int weight_by_strength);
+/* injection points for the unpinned third-party pieces */
+int  lrr_est_set_order(lrr_est* est, int dir, const int32_t* perm, int64_t n);      /* Q4 */
+int  lrr_est_set_shuffle(lrr_est* est, int mode, uint64_t seed);                    /* Q4 */
+int  lrr_est_set_initial_scale(lrr_est* est, int dir, double scale /* NaN => MUSE */);
+/* set_number_points (cdcl :95-108; protected in the reference, reached through the symmetric friend) */
+int  lrr_est_set_number_points(lrr_est* est, int dir, int64_t number_points, int* at_max);
+/* find_closest_euclidean()  (cdcl :541-654, rrl :494-571, sym wrappers) */
+int  lrr_est_find_closest(lrr_est* est);
+/* one_iteration(caller=0, display=0, iteration)  (cdcl :434-509, cdcl sym :268-363, rrl :427-462, rrl sym :341-438) */
+int  lrr_est_one_iteration(lrr_est* est, unsigned iteration, int* converged);
+/* run(): while(!converged && it<max_iter) one_iteration  (cdcl :413-428; driver loop rrl/itkLocationRegistration.cxx:2418) */
+int  lrr_est_run(lrr_est* est, int max_iter, int* converged, int* iterations);
+/* get_transform() / get_transform_backward(): A, t, center_moving_, covariance (dof x dof row-major) */
+int  lrr_est_get_transform(lrr_est* est, int dir, int* trans_kind, double* A9, double* t3, double* c3, double* cov);
+/* current matches_ of a direction: from = index into the inside set's parent (*_all), to = index into the
+ * other *_all set, w = weight.  n receives the match count; arrays may be NULL to query n only. */
+int  lrr_est_get_matches(lrr_est* est, int dir, int64_t cap, int64_t* n, int32_t* from_idx, int32_t* to_idx, double* w);
+int  lrr_est_metric(lrr_est* est, int which, int dir, double* out);
+/* estimate_LS_backward(estimate_parameters)  (cdcl sym :705-863, rrl sym :922-934) */
+int  lrr_est_estimate_ls_backward(lrr_est* est, int estimate_parameters);
+/* compute_transfer_error_covariance(): covarJ = mean_i J_i Sigma J_i^T  (cdcl :388-404, rrl :381-397) */
+int  lrr_est_transfer_cov(lrr_est* est, int dir, double* S9);
+int  lrr_est_get_state(lrr_est* est, lrr_est_state* out);
+/* oscillated()  (rrl sym .h:156) */
+int  lrr_est_oscillated(lrr_est* est, int* out);
+
+/* ---- covariance objective (cdcl_obj_fun_cov<3,dof>::compute, cdcl/cdcl_obj_fun_cov.txx:44-134) --------
+ * x = vec(upper Cholesky factor of Sigma_theta), length dof(dof+1)/2; f and g (same length) may be NULL.
+ * Evaluated over the current matches/weights of `dir` in the current (unnormalised) coordinates. */
+int  lrr_objcov_eval(lrr_est* est, int dir, const double* x, double* f, double* g);
+/* estimate_covariance(): normalise, x0 = chol(Sigma), L-BFGS (<= max_evals evaluations, stop once f dropped
+ * by more than 5 %: cdcl/cdcl_lbfgs.h:30-36), Sigma <- U^T U, unnormalise (cdcl/cdcl_estimation.txx:264-337). */
+int  lrr_objcov_refine(lrr_est* est, int dir, int max_evals, double* f_start, double* f_end, int* n_evals);
+
+/* ---- batched location registration (outer loops of LocationRegistration::Run,
+ * rrl/itkLocationRegistration.cxx:2138,2230,2332) ------------------------------------- */
+typedef struct lrr_job {
+  double  A[9], t[3], c[3];      /* initial transform (affine) of this candidate                    */
+  double  roi_center_moving[3];  /* ROI cube centre in the moving volume                            */
+  double  roi_center_fixed[3];   /* ROI cube centre in the fixed volume                             */
+  double  roi_half_size;         /* half edge of the cube (25 mm = the driver's 50 mm ROI, :2275)   */
+} lrr_job;
+
+typedef struct lrr_result {
+  int32_t status;        /* 0 ok, 1 rejected (<1000 features in an ROI, :1632), 2 invalid transform  */
+  int32_t converged, oscillated, iterations;
+  int32_t n_moving_inside, n_fixed_inside;
+  double  A[9], t[3], c[3];
+  double  cov[144];
+  double  rms, weighted_error;
+} lrr_result;
+
+/* Run njobs independent rrl symmetric <3,12> registrations (set_features + set_transform + <=max_iter
+ * one_iteration calls each) over one resident volume pair. */
+int  lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs,
+                   int max_iter, uint64_t shuffle_seed, lrr_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRR_GPU_H_ */

@@ -1,0 +1,346 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see lrr_oracle_core.hpp header).  C API of the CPU restatement.
+// Exports the same functions as include/lrr_gpu.h with the prefix `lrro_`, so one parity script drives
+// both libraries.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load this library.
+#include <cstring>
+#include <string>
+#include <thread>
+#include <atomic>
+#include "../include/lrr_gpu.h"
+#include "lrr_oracle_core.hpp"
+
+using namespace lrro;
+
+struct lrro_ctx { std::string err; };
+struct lrro_fset {
+  lrro_ctx* ctx;
+  std::vector<Feature> base;   // pristine copies
+  std::shared_ptr<KdTree> kd;
+  bool has_cov = false, has_dirs = false;
+};
+struct lrro_est {
+  lrro_ctx* ctx; int kind, dof; lrro_fset *moving_all, *fixed_all;
+  std::vector<FeatureP> moving_all_f, fixed_all_f;       // the estimator's own *_all objects
+  std::vector<int32_t> moving_inside_idx, fixed_inside_idx;
+  std::shared_ptr<FwdEst> fwd; std::shared_ptr<SymEst> sym;
+  int shuffle_mode = 0; uint64_t seed = 0;
+  int flavor() const { return (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM) ? FLAVOR_RRL : FLAVOR_CDCL; }
+  bool is_sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
+  FwdEst* dir(int d) { if (is_sym()) return d == 0 ? sym->forward_.get() : sym->backward_.get(); return d == 0 ? fwd.get() : nullptr; }
+};
+
+static std::vector<FeatureP> clone_set(const std::vector<Feature>& base) {
+  std::vector<FeatureP> v; v.reserve(base.size());
+  for (auto& f : base) v.push_back(std::make_shared<Feature>(f));
+  return v;
+}
+static std::vector<FeatureP> clone_subset(const std::vector<Feature>& base, const std::vector<int32_t>& idx) {
+  std::vector<FeatureP> v; v.reserve(idx.size());
+  for (int32_t i : idx) v.push_back(std::make_shared<Feature>(base[i]));
+  return v;
+}
+static void apply_policy(lrro_est* e) {
+  for (int d = 0; d < 2; ++d) if (FwdEst* f = e->dir(d)) {
+    f->shuffle_mode = e->shuffle_mode;
+    f->rng = SplitMix64(e->seed + (uint64_t)d * 0x632BE59BD9B4E019ULL);
+  }
+}
+
+extern "C" {
+
+int lrro_ctx_create(int, lrro_ctx** out) { *out = new lrro_ctx(); return LRR_OK; }
+void lrro_ctx_destroy(lrro_ctx* c) { delete c; }
+int lrro_ctx_set_stream(lrro_ctx*, void*) { return LRR_OK; }
+int lrro_ctx_synchronize(lrro_ctx*) { return LRR_OK; }
+const char* lrro_ctx_last_error(lrro_ctx* c) { return c->err.c_str(); }
+int64_t lrro_ctx_launch_count(lrro_ctx*) { return 0; }
+
+int lrro_features_upload(lrro_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6,
+                         const double* strength, const uint8_t* shape, const double* dirs, lrro_fset** out) {
+  if (!ctx || n < 0 || !xyz || !P6 || !out) return LRR_ERR_INVALID;
+  auto* fs = new lrro_fset(); fs->ctx = ctx; fs->base.resize(n);
+  fs->has_cov = C6 != nullptr; fs->has_dirs = dirs != nullptr;
+  static const int sym6[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+  std::vector<double> pts(3 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    Feature& f = fs->base[i];
+    for (int d = 0; d < 3; ++d) { f.loc[d] = xyz[d * n + i]; pts[3 * i + d] = f.loc[d]; }
+    f.strength = strength ? strength[i] : 0.0; f.strength_f = (float)f.strength;
+    for (int k = 0; k < 9; ++k) { f.P[k] = P6[sym6[k] * n + i]; f.cov[k] = C6 ? C6[sym6[k] * n + i] : 0.0; }
+    f.shape = shape ? shape[i] : CORNER;
+    f.ndirs = (f.shape == SHEET) ? 1 : (f.shape == TUBE ? 2 : 3);
+    for (int a = 0; a < 3; ++a) for (int d = 0; d < 3; ++d) f.dirs[a][d] = dirs ? dirs[(3 * a + d) * n + i] : 0.0;
+    f.id = (int)i;
+  }
+  fs->kd = std::make_shared<KdTree>(); fs->kd->build(pts);
+  *out = fs; return LRR_OK;
+}
+void lrro_features_destroy(lrro_fset* fs) { delete fs; }
+int64_t lrro_features_size(const lrro_fset* fs) { return (int64_t)fs->base.size(); }
+int lrro_features_nearest(lrro_fset* fs, int64_t nq, const double* q, int32_t* idx) {
+  for (int64_t i = 0; i < nq; ++i) { double p[3] = {q[i], q[nq + i], q[2 * nq + i]}; idx[i] = fs->kd->nearest(p); }
+  return LRR_OK;
+}
+// test hook: brute-force NN (cross-check of the kd-tree, K-f)
+int lrro_features_nearest_brute(lrro_fset* fs, int64_t nq, const double* q, int32_t* idx) {
+  for (int64_t i = 0; i < nq; ++i) { double p[3] = {q[i], q[nq + i], q[2 * nq + i]}; idx[i] = fs->kd->nearest_brute(p); }
+  return LRR_OK;
+}
+
+static void rebuild(lrro_est* e, TransP trans) {
+  auto mi = e->moving_inside_idx.empty() ? clone_set(e->moving_all->base) : clone_subset(e->moving_all->base, e->moving_inside_idx);
+  if (!e->is_sym()) {
+    e->fwd = std::make_shared<FwdEst>(e->flavor(), mi, e->fixed_all_f, trans, e->fixed_all->kd);
+  } else {
+    auto fi = e->fixed_inside_idx.empty() ? clone_set(e->fixed_all->base) : clone_subset(e->fixed_all->base, e->fixed_inside_idx);
+    e->sym = std::make_shared<SymEst>(e->flavor(), e->moving_all_f, e->fixed_all_f, trans, trans->inverse(), mi, fi, e->fixed_all->kd, e->moving_all->kd);
+  }
+  apply_policy(e);
+}
+
+int lrro_est_create(lrro_ctx* ctx, int kind, int dim, int dof, lrro_fset* moving_all, lrro_fset* fixed_all, lrro_est** out) {
+  if (!ctx || !moving_all || !fixed_all || !out) return LRR_ERR_INVALID;
+  if (dim != 3 || (dof != 12 && dof != 6)) return LRR_ERR_UNSUPPORTED;
+  if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;  // Q6
+  if (kind < 0 || kind > 3) return LRR_ERR_INVALID;
+  auto* e = new lrro_est(); e->ctx = ctx; e->kind = kind; e->dof = dof; e->moving_all = moving_all; e->fixed_all = fixed_all;
+  e->moving_all_f = clone_set(moving_all->base); e->fixed_all_f = clone_set(fixed_all->base);
+  rebuild(e, std::make_shared<Trans>(dof == 12 ? TRANS_AFFINE : TRANS_RIGID3D));
+  *out = e; return LRR_OK;
+}
+void lrro_est_destroy(lrro_est* e) { delete e; }
+
+int lrro_est_set_subsets(lrro_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
+  e->moving_inside_idx.assign(mi, mi + nm);
+  if (fi) e->fixed_inside_idx.assign(fi, fi + nf); else e->fixed_inside_idx.clear();
+  auto mv = clone_subset(e->moving_all->base, e->moving_inside_idx);
+  if (!e->is_sym()) { e->fwd->set_moving_data(mv); }
+  else {
+    auto fv = e->fixed_inside_idx.empty() ? clone_set(e->fixed_all->base) : clone_subset(e->fixed_all->base, e->fixed_inside_idx);
+    e->sym->set_features(mv, fv);
+  }
+  return LRR_OK;
+}
+int lrro_est_set_transform(lrro_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
+  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12)) return LRR_ERR_INVALID;
+  auto t = std::make_shared<Trans>(tk == LRR_TRANS_AFFINE ? TRANS_AFFINE : TRANS_RIGID3D);
+  std::memcpy(t->A, A9, sizeof(double) * 9); std::memcpy(t->t, t3, sizeof(double) * 3);
+  if (c3) std::memcpy(t->c, c3, sizeof(double) * 3);
+  if (cov) t->covar.assign(cov, cov + e->dof * e->dof);
+  if (e->is_sym()) e->sym->set_transform(t); else e->fwd->set_transform(t);
+  return LRR_OK;
+}
+int lrro_est_set_flags(lrro_est* e, int normalize, int wbs) {
+  for (int d = 0; d < 2; ++d) if (FwdEst* f = e->dir(d)) { f->normalize_matches_ = normalize != 0; f->weight_by_strength_ = wbs != 0; }
+  if (e->is_sym()) e->sym->normalize_matches_ = normalize != 0;
+  return LRR_OK;
+}
+int lrro_est_set_order(lrro_est* e, int d, const int32_t* perm, int64_t n) {
+  FwdEst* f = e->dir(d); if (!f || (size_t)n != f->moving_base_.size()) return LRR_ERR_INVALID;
+  f->set_order(perm, (size_t)n); return LRR_OK;
+}
+int lrro_est_set_shuffle(lrro_est* e, int mode, uint64_t seed) { e->shuffle_mode = mode; e->seed = seed; apply_policy(e); return LRR_OK; }
+int lrro_est_set_initial_scale(lrro_est* e, int d, double s) { FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID; f->initial_scale = s; return LRR_OK; }
+int lrro_est_set_number_points(lrro_est* e, int d, int64_t m, int* at_max) {
+  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  bool r = f->set_number_points((size_t)m); if (at_max) *at_max = r; return LRR_OK;
+}
+int lrro_est_find_closest(lrro_est* e) { if (e->is_sym()) e->sym->find_closest_euclidean(); else e->fwd->find_closest_euclidean(); return LRR_OK; }
+int lrro_est_one_iteration(lrro_est* e, unsigned it, int* conv) {
+  bool c = e->is_sym() ? e->sym->one_iteration(it) : e->fwd->one_iteration();
+  if (conv) *conv = c; return LRR_OK;
+}
+int lrro_est_run(lrro_est* e, int max_iter, int* conv, int* iters) {
+  bool c = e->is_sym() ? e->sym->run(max_iter, iters) : e->fwd->run(max_iter, iters);
+  if (conv) *conv = c; return LRR_OK;
+}
+int lrro_est_get_transform(lrro_est* e, int d, int* tk, double* A9, double* t3, double* c3, double* cov) {
+  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  const Trans& t = *f->trans_;
+  if (tk) *tk = t.kind == TRANS_AFFINE ? LRR_TRANS_AFFINE : LRR_TRANS_RIGID3D;
+  if (A9) std::memcpy(A9, t.A, 72); if (t3) std::memcpy(t3, t.t, 24); if (c3) std::memcpy(c3, t.c, 24);
+  if (cov) std::memcpy(cov, t.covar.data(), sizeof(double) * t.covar.size());
+  return LRR_OK;
+}
+int lrro_est_get_matches(lrro_est* e, int d, int64_t cap, int64_t* n, int32_t* from_idx, int32_t* to_idx, double* w) {
+  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  int64_t m = (int64_t)f->matches_.size(); if (n) *n = m;
+  for (int64_t i = 0; i < m && i < cap; ++i) {
+    if (from_idx) from_idx[i] = f->matches_[i].from->id;
+    if (to_idx) to_idx[i] = f->matches_[i].to->id;
+    if (w) w[i] = f->matches_[i].w;
+  }
+  return LRR_OK;
+}
+int lrro_est_metric(lrro_est* e, int which, int d, double* out) {
+  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  switch (which) {
+    case LRR_METRIC_RMS: *out = f->RMS_error(); break;
+    case LRR_METRIC_WEIGHTED: *out = f->weighted_error(); break;
+    case LRR_METRIC_MEDIAN: *out = f->median_error(); break;
+    case LRR_METRIC_SHEET_ANGLES: *out = f->sheet_angles(); break;
+    case LRR_METRIC_TUBE_ANGLES: *out = f->tube_angles(); break;
+    default: return LRR_ERR_INVALID;
+  }
+  return LRR_OK;
+}
+int lrro_est_estimate_ls_backward(lrro_est* e, int ep) { if (!e->is_sym()) return LRR_ERR_INVALID; e->sym->estimate_LS_backward(ep != 0); return LRR_OK; }
+int lrro_est_transfer_cov(lrro_est* e, int d, double* S9) {
+  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  f->compute_transfer_error_covariance(); std::memcpy(S9, f->trans_->covarJ, 72); return LRR_OK;
+}
+int lrro_est_get_state(lrro_est* e, lrr_est_state* s) {
+  std::memset(s, 0, sizeof(*s));
+  for (int d = 0; d < 2; ++d) if (FwdEst* f = e->dir(d)) {
+    s->number_points[d] = (int64_t)f->number_points_; s->scale[d] = f->last_scale; s->scale_estimated[d] = f->scale_estimated_;
+  }
+  FwdEst* f0 = e->dir(0);
+  for (int k = 0; k < 3; ++k) { s->norm_center_moving[k] = f0->last_norm[k]; s->norm_center_fixed[k] = f0->last_norm[4 + k]; }
+  s->norm_radius_moving = f0->last_norm[3]; s->norm_radius_fixed = f0->last_norm[7];
+  if (e->is_sym()) {
+    s->number_matches = e->sym->number_matches_; s->finest_level = e->sym->finest_level_;
+    s->oscillation_count = (int)e->sym->oscillation_count_; s->error_difference = e->sym->error_difference_;
+    s->weighted_error = e->sym->weighted_error_; s->iterations_done = e->sym->iterations_done;
+  }
+  return LRR_OK;
+}
+int lrro_est_oscillated(lrro_est* e, int* out) { *out = e->is_sym() ? e->sym->oscillated() : 0; return LRR_OK; }
+
+int lrro_objcov_eval(lrro_est* e, int d, const double* x, double* f, double* g) {
+  FwdEst* fe = e->dir(d); if (!fe) return LRR_ERR_INVALID;
+  std::vector<double> saved = fe->trans_->covar;
+  ObjFunCov obj(fe->matches_, *fe->trans_);
+  obj.compute(x, f, g);
+  fe->trans_->covar = saved;
+  return LRR_OK;
+}
+// estimate_covariance (cdcl/cdcl_estimation.txx:264-337) on the ICP matches of direction d.
+int lrro_objcov_refine(lrro_est* e, int d, int max_evals, double* f_start, double* f_end, int* n_evals) {
+  FwdEst* fe = e->dir(d); if (!fe) return LRR_ERR_INVALID;
+  Trans& tr = *fe->trans_; const int dof = tr.dof;
+  double cm[3] = {0, 0, 0}, cf[3] = {0, 0, 0}, rm = 0, rf = 0;
+  if (fe->normalize_matches_) { fe->normalize_matches_fn(cm, rm, cf, rf); tr.normalize(rm, rf, cm, cf); }
+  ObjFunCov obj(fe->matches_, tr);
+  std::vector<double> U((size_t)dof * dof);
+  if (!cholesky_upper(dof, tr.covar.data(), U.data())) {
+    if (fe->normalize_matches_) { tr.unnormalize(rm, rf, cm, cf); fe->unnormalize_matches_fn(cm, rm, cf, rf); }
+    return LRR_ERR_STATE;
+  }
+  std::vector<double> x(dof * (dof + 1) / 2); int ind = 0;
+  for (int d1 = 0; d1 < dof; ++d1) for (int d2 = d1; d2 < dof; ++d2) x[ind++] = U[d1 * dof + d2];
+  double fs = 0, fe_ = 0;
+  int ev = lbfgs_minimize([&](const double* xx, double* f, double* g) { obj.compute(xx, f, g); }, x, max_evals, &fs, &fe_);
+  std::vector<double> up((size_t)dof * dof, 0.0); ind = 0;
+  for (int d1 = 0; d1 < dof; ++d1) for (int d2 = d1; d2 < dof; ++d2) up[d1 * dof + d2] = x[ind++];
+  for (int i = 0; i < dof; ++i) for (int j = 0; j < dof; ++j) { double s = 0; for (int k = 0; k < dof; ++k) s += up[k * dof + i] * up[k * dof + j]; tr.covar[i * dof + j] = s; }
+  if (fe->normalize_matches_) { tr.unnormalize(rm, rf, cm, cf); fe->unnormalize_matches_fn(cm, rm, cf, rf); }
+  if (f_start) *f_start = fs; if (f_end) *f_end = fe_; if (n_evals) *n_evals = ev;
+  return LRR_OK;
+}
+
+// validTransform (rrl/itkLocationRegistration.cxx:2914-2926)
+static bool valid_transform(const Trans& t) {
+  double w[3]; svd_singular_values(3, t.A, w);
+  for (int d = 0; d < 3; ++d) if (w[d] > 10.0 || w[d] < 0.1) return false;
+  return true;
+}
+
+static void run_one_job(const lrro_fset* moving_all, const lrro_fset* fixed_all, const std::vector<FeatureP>& mall,
+                        const std::vector<FeatureP>& fall, std::shared_ptr<const KdTree> kd_fixed, std::shared_ptr<const KdTree> kd_moving,
+                        const lrr_job& job, int max_iter, uint64_t seed, lrr_result& r) {
+  std::memset(&r, 0, sizeof(r));
+  auto in_cube = [&](const Feature& f, const double* c) {
+    for (int d = 0; d < 3; ++d) if (c[d] - job.roi_half_size > f.loc[d] || f.loc[d] > c[d] + job.roi_half_size) return false;
+    return true;
+  };
+  std::vector<FeatureP> mi, fi;   // FeaturesInROIs (rrl/itkLocationRegistration.cxx:1324-1360)
+  for (auto& f : fixed_all->base) if (in_cube(f, job.roi_center_fixed)) fi.push_back(std::make_shared<Feature>(f));
+  for (auto& f : moving_all->base) if (in_cube(f, job.roi_center_moving)) mi.push_back(std::make_shared<Feature>(f));
+  r.n_moving_inside = (int)mi.size(); r.n_fixed_inside = (int)fi.size();
+  if (mi.size() < 1000 || fi.size() < 1000) { r.status = 1; return; }   // :1632
+  auto t = std::make_shared<Trans>(TRANS_AFFINE);
+  std::memcpy(t->A, job.A, 72); std::memcpy(t->t, job.t, 24); std::memcpy(t->c, job.c, 24);
+  // prebuilt kd-trees are shared: the driver keeps one estimator alive across locations (:1635-1638)
+  SymEst est(FLAVOR_RRL, mall, fall, t, t->inverse(), mi, fi, kd_fixed, kd_moving);
+  est.forward_->shuffle_mode = est.backward_->shuffle_mode = 1;
+  est.forward_->rng = SplitMix64(seed); est.backward_->rng = SplitMix64(seed + 0x632BE59BD9B4E019ULL);
+  est.set_transform(t);
+  bool converged = false; int it = 0;
+  while (!converged && it < max_iter) {                               // :2418
+    converged = est.one_iteration((unsigned)it); ++it;
+    if (!valid_transform(*est.forward_->trans_)) { r.status = 2; break; }   // :2482
+  }
+  const Trans& T = *est.forward_->trans_;
+  r.converged = converged; r.oscillated = est.oscillated(); r.iterations = it;
+  std::memcpy(r.A, T.A, 72); std::memcpy(r.t, T.t, 24); std::memcpy(r.c, T.c, 24);
+  std::memcpy(r.cov, T.covar.data(), sizeof(double) * 144);
+  r.rms = est.forward_->RMS_error(); r.weighted_error = est.forward_->weighted_error();
+}
+
+// Batched location registration on the CPU.  nthreads <= 0 -> 1 (the reference's execution model).
+int lrro_batch_run_mt(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, const lrr_job* jobs, int64_t njobs,
+                      int max_iter, uint64_t shuffle_seed, lrr_result* out, int nthreads) {
+  if (nthreads <= 0) nthreads = 1;
+  std::atomic<int64_t> next{0};
+  auto worker = [&]() {
+    // per-thread *_all clones: features are mutated in place during normalisation (Q10)
+    auto mall = clone_set(moving_all->base); auto fall = clone_set(fixed_all->base);
+    for (;;) {
+      int64_t j = next.fetch_add(1); if (j >= njobs) break;
+      run_one_job(moving_all, fixed_all, mall, fall, fixed_all->kd, moving_all->kd, jobs[j], max_iter, shuffle_seed + (uint64_t)j, out[j]);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; ++i) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+  return LRR_OK;
+}
+int lrro_batch_run(lrro_ctx* c, lrro_fset* m, lrro_fset* f, const lrr_job* jobs, int64_t njobs, int max_iter, uint64_t seed, lrr_result* out) {
+  return lrro_batch_run_mt(c, m, f, jobs, njobs, max_iter, seed, out, 1);
+}
+
+// ---- test hooks -------------------------------------------------------------------------------
+double lrro_test_muse_scale(const double* r, int64_t n) { return muse_scale(std::vector<double>(r, r + n)); }
+double lrro_test_mad_scale(const double* r, int64_t n) { std::vector<double> v(r, r + n); return median_abs_dev_scale(v); }
+double lrro_test_weight_BT(double u) { return weight_BT(u); }
+double lrro_test_rho(double u) { return rho(u); }
+double lrro_test_rho_p(double u) { return rho_p(u); }
+double lrro_test_weight(double u) { return weight_rho(u); }
+void lrro_test_svd_inverse(int n, const double* M, double* inv) { svd_inverse(n, M, inv); }
+double lrro_test_gauss_inv_cdf(double p) { return gauss_inv_cdf(p); }
+// normalize followed by unnormalize of (A,t,c,cov) — K-d
+void lrro_test_trans_roundtrip(int kind, double* A9, double* t3, double* c3, double* cov, double rm, double rf,
+                               const double* cm, const double* cf, int do_unnormalize) {
+  Trans t(kind == LRR_TRANS_AFFINE ? TRANS_AFFINE : TRANS_RIGID3D);
+  std::memcpy(t.A, A9, 72); std::memcpy(t.t, t3, 24); std::memcpy(t.c, c3, 24);
+  if (cov) t.covar.assign(cov, cov + t.dof * t.dof);
+  t.normalize(rm, rf, cm, cf);
+  if (do_unnormalize) t.unnormalize(rm, rf, cm, cf);
+  std::memcpy(A9, t.A, 72); std::memcpy(t3, t.t, 24); std::memcpy(c3, t.c, 24);
+  if (cov) std::memcpy(cov, t.covar.data(), sizeof(double) * t.dof * t.dof);
+}
+void lrro_test_trans_inverse(int kind, double* A9, double* t3, double* c3) {
+  Trans t(kind == LRR_TRANS_AFFINE ? TRANS_AFFINE : TRANS_RIGID3D);
+  std::memcpy(t.A, A9, 72); std::memcpy(t.t, t3, 24); std::memcpy(t.c, c3, 24);
+  auto r = t.inverse();
+  std::memcpy(A9, r->A, 72); std::memcpy(t3, r->t, 24); std::memcpy(c3, r->c, 24);
+}
+void lrro_test_recompose(double* R9, double* t3, const double* dR9, const double* dt3) {
+  Trans g(TRANS_RIGID3D), inc(TRANS_RIGID3D);
+  std::memcpy(g.A, R9, 72); std::memcpy(g.t, t3, 24); std::memcpy(inc.A, dR9, 72); std::memcpy(inc.t, dt3, 24);
+  g.recompose_increment(inc);
+  std::memcpy(R9, g.A, 72); std::memcpy(t3, g.t, 24);
+}
+// dense AtA/Atb over the current forward matches of a forward estimator, no weighting changes (K-e)
+int lrro_test_dense_normal_equations(lrro_est* e, int d, double* AtA, double* Atb) {
+  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  const int dof = f->trans_->dof;
+  std::vector<double> A((size_t)dof * dof, 0.0), b(dof, 0.0);
+  for (auto& m : f->matches_) FwdEst::accumulate_dense(*f->trans_, m.from->loc, m.to->P, m.to->loc, m.w, A, b);
+  std::memcpy(AtA, A.data(), sizeof(double) * dof * dof); std::memcpy(Atb, b.data(), sizeof(double) * dof);
+  return LRR_OK;
+}
+int lrro_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,1137 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path
+// (lrr_b200/), only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference.
+//
+// CPU restatement (C++17, fp64, no FMA contraction) of the LRR hot path: the robust ICP loop of
+//   cdcl/cdcl_estimation_ICP_matching_all.txx, cdcl/cdcl_estimation_symmetric_ICP_matching_all.txx,
+//   rrl/rrl_estimation_ICP_matching_all.txx, rrl/rrl_estimation_symmetric_ICP_matching_all.txx,
+//   cdcl/cdcl_trans_affine.txx, cdcl/cdcl_trans_rigid3d.cxx, cdcl/cdcl_utils.h:123-248,
+//   cdcl/cdcl_obj_fun_cov.txx, cdcl/cdcl_lbfgs.h, cdcl/cdcl_estimation.txx:264-337.
+// Each function cites the reference file:line it follows.  The data model deliberately mirrors the
+// reference's (one heap object per feature behind a ref-counted pointer, matches holding pointers,
+// in-place normalisation of shared feature objects — Q10), because it doubles as the faithful
+// single-thread CPU baseline.
+//
+// PARITY STATUS: the reference ships NO tests, golden vectors or fixtures and cannot be
+// compiled here (VXL/ITK/VTK absent), so this oracle is pinned only by known-answer
+// tests authored in tests/ (K-a..K-i) — "parity unpinned" by reference-owned vectors.  Third-party
+// arithmetic restated from published algorithms, all UNPINNED upstream (FIND_PACKAGE(VXL), no version):
+//   * rrel_muset_obj::scale (VXL contrib/rpl/rrel) — MUSE, Miller & Stewart CVPR'96; table constants
+//     recalled from upstream rrel_muse_table; the initial scale is therefore also an injectable input.
+//   * rsdl_kd_tree::n_nearest (VXL contrib/rpl/rsdl) — exact Euclidean 1-NN; ties: lowest index.
+//   * vnl_svd::inverse, vnl_inverse, vnl_determinant, vnl_symmetric_eigensystem — see lrr_oracle_linalg.hpp.
+//   * vnl_lbfgs (v3p netlib) — Nocedal L-BFGS; iterate trajectory unpinned, f/g pinned by formula.
+//   * vcl_random_shuffle — permutation is an injectable input (Q4).
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <limits>
+#include <memory>
+#include <set>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#include "lrr_oracle_linalg.hpp"
+
+namespace lrro {
+
+enum { CORNER = 0, TUBE = 1, SHEET = 2 };           // cdcl_feature_with_shape.h:32
+enum { TRANS_AFFINE = 0, TRANS_RIGID3D = 1 };
+enum { FLAVOR_CDCL = 0, FLAVOR_RRL = 1 };
+
+// ----------------------------------------------------------------------------------------------
+// A1: cdcl_feature_with_shape<3> / cdcl_feature_ICP<3>  (cdcl/cdcl_feature_with_shape.h:23-89,
+// cdcl/cdcl_feature_ICP.h:23-96).  strength_f is the fp32 copy cdcl_feature_ICP stores (.h:83).
+struct Feature {
+  double loc[3];
+  double strength;
+  float  strength_f;
+  double cov[9];
+  double P[9];
+  int    shape;
+  int    ndirs;
+  double dirs[3][3];
+  int    id;  // index in the parent *_all set (clones keep it) — bookkeeping only
+};
+using FeatureP = std::shared_ptr<Feature>;
+
+// cdcl_match with exactly one `to` (n = 1 everywhere on this path, cdcl :551, rrl :503).
+struct Match { FeatureP from, to; double w; };
+
+// ----------------------------------------------------------------------------------------------
+// SplitMix64 + Fisher-Yates: the injectable stand-in for vcl_random_shuffle (Q4).
+struct SplitMix64 {
+  uint64_t s;
+  explicit SplitMix64(uint64_t seed = 0) : s(seed) {}
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  }
+};
+template <class T> inline void fisher_yates(std::vector<T>& a, SplitMix64& rng) {
+  for (size_t i = a.size(); i > 1; --i) {
+    size_t j = (size_t)(rng.next() % (uint64_t)i);
+    std::swap(a[i - 1], a[j]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// A7/A8 helper: the reference's private copy of rrel_util_median_abs_dev_scale
+// (cdcl/cdcl_estimation_ICP_matching_all.txx:520-536, dof = 1).  Q12.
+inline double median_abs_dev_scale(std::vector<double>& v) {
+  long count = (long)v.size();
+  const int dof = 1;
+  if (count <= dof) return 0;
+  for (auto& x : v) x = std::fabs(x);
+  auto loc = v.begin() + ((count - dof) / 2 + dof);
+  std::nth_element(v.begin(), loc, v.end());
+  return 1.4826 * (1 + 5.0 / (count - dof)) * *loc;
+}
+
+// cdcl/cdcl_utils.h:142-152
+inline double weight_BT(double residual) {
+  if (residual <= 16.0) { double temp = 1 - residual * 0.0625; return temp * temp; }
+  return 0;
+}
+// cdcl/cdcl_utils.h:158-178
+inline double rho(double residual) {
+  const double b = 4.0, b_2 = b * b, f = 2.9872, c = b_2 / 6.0;
+  if (residual > b_2) return f * c;
+  return f * c * (1 - std::pow(1 - residual / b_2, 3.0));
+}
+// cdcl/cdcl_utils.h:184-204
+inline double rho_p(double residual) {
+  const double b = 4.0, b_2 = b * b, f = 2.9872;
+  if (residual > b_2) return 0.0;
+  double temp = 1 - residual / b_2;
+  return f * 0.5 * temp * temp;
+}
+// cdcl/cdcl_utils.h:209-227
+inline double weight_rho(double residual) {
+  const double b = 4.0, b_2 = b * b, f = 2.9872;
+  if (residual <= b_2) return f * (1 - residual / b_2) * (1 - residual / b_2);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// MUSE (rrel_muset_obj(0,false)::scale; call sites cdcl :721-725, rrl :630-634).  UNPINNED upstream.
+// Restated from Miller & Stewart, "MUSE: Robust surface fitting using unbiased scale estimates",
+// CVPR'96, trimmed variant: over inlier fractions 0.25..0.95 step 0.05 minimise
+//   s_k * stddev(k-th order stat) / E(k-th order stat),  s_k = sum of k smallest |r| / divisor(k,n)
+// for half-normal order statistics; return the minimising s_k (no sk refinement).
+inline double gauss_inv_cdf(double p) {
+  // Acklam's rational approximation + one Halley step on erfc: |rel err| < 1e-15.
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                             1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                             6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                             -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                             3.754408661907416e+00};
+  double x;
+  if (p < 0.02425) {
+    double q = std::sqrt(-2 * std::log(p));
+    x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+        ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  } else if (p <= 1 - 0.02425) {
+    double q = p - 0.5, r = q * q;
+    x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+        (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+  } else {
+    double q = std::sqrt(-2 * std::log(1 - p));
+    x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+        ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  }
+  double e = 0.5 * std::erfc(-x / std::sqrt(2.0)) - p;
+  double u = e * std::sqrt(2 * M_PI) * std::exp(x * x / 2);
+  x = x - u / (1 + x * u / 2);
+  return x;
+}
+inline double muse_expected_kth(unsigned k, unsigned n) {
+  return gauss_inv_cdf(0.5 * (1.0 + double(k) / double(n + 1)));
+}
+inline double muse_stddev_kth(unsigned k, unsigned n) {
+  double pk = double(k) / double(n + 1), qk = 1.0 - pk;
+  double Qk = gauss_inv_cdf(0.5 * (1.0 + pk));
+  double pQk = std::sqrt(2 / M_PI) * std::exp(-0.5 * Qk * Qk);  // half-normal density at Qk
+  double Qk_prime = 1.0 / pQk;
+  double Qk_dprime = Qk / (pQk * pQk);
+  double Qk_tprime = (1.0 + 2.0 * Qk * Qk) / (pQk * pQk * pQk);
+  double vrk = (pk * qk / double(n + 2)) * Qk_prime * Qk_prime +
+               (pk * qk / (double(n + 2) * double(n + 2))) *
+                   (2.0 * (qk - pk) * Qk_prime * Qk_dprime + pk * qk * (Qk_prime * Qk_tprime + 0.5 * Qk_dprime * Qk_dprime));
+  return std::sqrt(vrk);
+}
+inline double muse_divisor(unsigned k, unsigned n) {
+  double r = double(k) / double(n);
+  double mean = gauss_inv_cdf(0.5 * (1.0 + r));
+  return double(n) * std::sqrt(2 / M_PI) * (1.0 - std::exp(-0.5 * mean * mean));
+}
+// Given |r| sorted ascending.  Shared driver so that the objective loop is stated once.
+inline double muse_scale_sorted(const std::vector<double>& abs_sorted) {
+  const unsigned n = (unsigned)abs_sorted.size();
+  if (n == 0) return 0.0;
+  const double min_frac = 0.25, max_frac = 0.95, frac_inc = 0.05, min_ratio = 3.0;
+  bool at_start = true;
+  double best_sk = 0, best_obj = 0, sum = 0;
+  unsigned prev_k = 0;
+  for (double frac = min_frac; frac <= max_frac + 0.00001; frac += frac_inc) {
+    long kk = std::lround(frac * n);
+    unsigned k = (kk <= 0) ? 1u : (unsigned)kk;
+    if (k > n) k = n;
+    double ek = muse_expected_kth(k, n), sd = muse_stddev_kth(k, n);
+    if (ek / sd < min_ratio) continue;
+    for (unsigned i = prev_k; i < k; ++i) sum += abs_sorted[i];
+    double sk = sum / muse_divisor(k, n);
+    double obj = sk * sd / ek;
+    if (at_start || obj < best_obj) { at_start = false; best_sk = sk; best_obj = obj; }
+    prev_k = k;
+  }
+  return best_sk;
+}
+inline double muse_scale(std::vector<double> r) {
+  for (auto& x : r) x = std::fabs(x);
+  std::sort(r.begin(), r.end());
+  return muse_scale_sorted(r);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Exact Euclidean 1-NN (stands in for rsdl_kd_tree::n_nearest(n=1), cdcl :572).  d2 = dx*dx+dy*dy+dz*dz
+// evaluated left to right without FMA; ties -> lowest index.  kd-tree + brute force for cross-checks.
+inline double dist2(const double* a, const double* b) {
+  double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+struct KdTree {
+  struct Node { int lo, hi, axis, left, right; double split; double bmin[3], bmax[3]; };
+  std::vector<double> pts;   // 3*n, copied at build like rsdl_kd_tree copies its rsdl_points
+  std::vector<int> perm;
+  std::vector<Node> nodes;
+  int n = 0;
+  void build(const std::vector<double>& xyz_aos) {
+    pts = xyz_aos; n = (int)(pts.size() / 3);
+    perm.resize(n); std::iota(perm.begin(), perm.end(), 0);
+    nodes.clear(); nodes.reserve(n / 4 + 16);
+    if (n > 0) build_rec(0, n);
+  }
+  int build_rec(int lo, int hi) {
+    Node nd; nd.lo = lo; nd.hi = hi; nd.left = nd.right = -1; nd.axis = 0; nd.split = 0;
+    for (int d = 0; d < 3; ++d) { nd.bmin[d] = 1e300; nd.bmax[d] = -1e300; }
+    for (int i = lo; i < hi; ++i) for (int d = 0; d < 3; ++d) {
+      double v = pts[3 * perm[i] + d];
+      nd.bmin[d] = std::min(nd.bmin[d], v); nd.bmax[d] = std::max(nd.bmax[d], v);
+    }
+    int me = (int)nodes.size(); nodes.push_back(nd);
+    if (hi - lo > 8) {
+      int ax = 0; double ext = -1;
+      for (int d = 0; d < 3; ++d) if (nd.bmax[d] - nd.bmin[d] > ext) { ext = nd.bmax[d] - nd.bmin[d]; ax = d; }
+      int mid = (lo + hi) / 2;
+      std::nth_element(perm.begin() + lo, perm.begin() + mid, perm.begin() + hi,
+                       [&](int a, int b) { return pts[3 * a + ax] < pts[3 * b + ax]; });
+      nodes[me].axis = ax; nodes[me].split = pts[3 * perm[mid] + ax];
+      int l = build_rec(lo, mid); int r = build_rec(mid, hi);
+      nodes[me].left = l; nodes[me].right = r;
+    }
+    return me;
+  }
+  static double box_d2(const Node& nd, const double* q) {
+    double s = 0;
+    for (int d = 0; d < 3; ++d) {
+      double e = 0;
+      if (q[d] < nd.bmin[d]) e = nd.bmin[d] - q[d]; else if (q[d] > nd.bmax[d]) e = q[d] - nd.bmax[d];
+      s += e * e;
+    }
+    return s;
+  }
+  void search(int ni, const double* q, double& best, int& bi) const {
+    const Node& nd = nodes[ni];
+    // conservative prune: box distance uses a different rounding path than dist2, allow equality
+    if (box_d2(nd, q) * (1.0 - 1e-12) > best) return;
+    if (nd.left < 0) {
+      for (int i = nd.lo; i < nd.hi; ++i) {
+        int j = perm[i]; double d = dist2(q, &pts[3 * j]);
+        if (d < best || (d == best && j < bi)) { best = d; bi = j; }
+      }
+      return;
+    }
+    int first = nd.left, second = nd.right;
+    if (q[nd.axis] >= nd.split) std::swap(first, second);
+    search(first, q, best, bi); search(second, q, best, bi);
+  }
+  int nearest(const double* q) const {
+    double best = std::numeric_limits<double>::infinity(); int bi = -1;
+    if (n > 0) search(0, q, best, bi);
+    return bi;
+  }
+  int nearest_brute(const double* q) const {
+    double best = std::numeric_limits<double>::infinity(); int bi = -1;
+    for (int j = 0; j < n; ++j) { double d = dist2(q, &pts[3 * j]); if (d < best) { best = d; bi = j; } }
+    return bi;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// A2/A3/A9: cdcl_trans_affine<3,12> and cdcl_trans_rigid3d (<3,6>).
+struct Trans {
+  int kind = TRANS_AFFINE;
+  int dof = 12;
+  double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // A_ / R_
+  double t[3] = {0, 0, 0};
+  double c[3] = {0, 0, 0};                     // center_moving_ (cdcl_trans.h:147)
+  std::vector<double> covar;                   // covar_ dof x dof
+  double covarJ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double alpha = 0, beta = 0, gamma = 0;       // rigid only
+
+  explicit Trans(int k = TRANS_AFFINE) : kind(k), dof(k == TRANS_AFFINE ? 12 : 6), covar((size_t)dof * dof, 0.0) {}
+  // create_new(): identity of the same kind, zero covariance, zero centre.
+  std::shared_ptr<Trans> create_new() const { return std::make_shared<Trans>(kind); }
+
+  // map_loc: A_ * ( from - center_moving_ ) + t_   (affine.txx:112-115, rigid3d.cxx:171-174).
+  // vnl evaluates the row dot product left to right, then adds t.
+  void map_loc(const double* x, double* y) const {
+    double v0 = x[0] - c[0], v1 = x[1] - c[1], v2 = x[2] - c[2];
+    for (int r = 0; r < 3; ++r) {
+      double acc = A[3 * r] * v0;
+      acc += A[3 * r + 1] * v1;
+      acc += A[3 * r + 2] * v2;
+      y[r] = acc + t[r];
+    }
+  }
+  // jacobian_wrt_par_thread (affine.txx:141-161, rigid3d.cxx:197-225): J is 3 x dof row-major.
+  void jacobian_wrt_par(const double* x, double* J) const {
+    double lc[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
+    std::fill(J, J + 3 * dof, 0.0);
+    if (kind == TRANS_AFFINE) {
+      int p = 0;
+      for (int d1 = 0; d1 < 3; ++d1) for (int d2 = 0; d2 < 3; ++d2) { J[d1 * dof + p] = lc[d2]; ++p; }
+      for (int d = 0; d < 3; ++d, ++p) J[d * dof + p] = 1.0;
+    } else {
+      J[1 * dof + 0] = -lc[2]; J[2 * dof + 0] = lc[1];
+      J[0 * dof + 1] = lc[2];  J[2 * dof + 1] = -lc[0];
+      J[0 * dof + 2] = -lc[1]; J[1 * dof + 2] = lc[0];
+      J[0 * dof + 3] = 1.0; J[1 * dof + 4] = 1.0; J[2 * dof + 5] = 1.0;
+    }
+  }
+  // get_parameterization (affine.txx:65-83 row-major A then t; rigid3d.cxx:123-135).
+  std::vector<double> get_parameterization() const {
+    std::vector<double> p(dof, 0.0);
+    if (kind == TRANS_AFFINE) { for (int i = 0; i < 9; ++i) p[i] = A[i]; for (int d = 0; d < 3; ++d) p[9 + d] = t[d]; }
+    else { p[0] = alpha; p[1] = beta; p[2] = gamma; for (int d = 0; d < 3; ++d) p[3 + d] = t[d]; }
+    return p;
+  }
+  // set_parameterization (affine.txx:89-106; rigid3d.cxx:140-166: small-angle R, Q7).
+  void set_parameterization(const double* p) {
+    if (kind == TRANS_AFFINE) { for (int i = 0; i < 9; ++i) A[i] = p[i]; for (int d = 0; d < 3; ++d) t[d] = p[9 + d]; }
+    else {
+      alpha = p[0]; beta = p[1]; gamma = p[2];
+      double da = p[0], db = p[1], dg = p[2];
+      A[0] = 1.0; A[1] = -dg; A[2] = db;
+      A[3] = dg;  A[4] = 1.0; A[5] = -da;
+      A[6] = -db; A[7] = da;  A[8] = 1.0;
+      t[0] = p[3]; t[1] = p[4]; t[2] = p[5];
+    }
+  }
+  // inverse() (affine.txx:54-59, rigid3d.cxx:113-118): (invA, -invA*t + c, centre 0), fresh covariance (zeros).
+  std::shared_ptr<Trans> inverse() const {
+    auto r = std::make_shared<Trans>(kind);
+    double invA[9]; svd_inverse(3, A, invA);
+    for (int i = 0; i < 9; ++i) r->A[i] = invA[i];
+    for (int i = 0; i < 3; ++i) {
+      double acc = (-invA[3 * i]) * t[0];
+      acc += (-invA[3 * i + 1]) * t[1];
+      acc += (-invA[3 * i + 2]) * t[2];
+      r->t[i] = acc + c[i];
+    }
+    if (kind == TRANS_RIGID3D) {  // ctor #4 recovers Euler angles (rigid3d.cxx:83-108)
+      r->beta = std::asin(r->A[2]);
+      double C = std::cos(r->beta);
+      if (std::fabs(C) > 1e-6) {
+        r->alpha = std::atan2(-r->A[5] / C, r->A[8] / C);
+        r->gamma = std::atan2(-r->A[1] / C, r->A[0] / C);
+      } else { r->alpha = 0; r->gamma = std::atan2(r->A[3], r->A[4]); }
+    }
+    return r;
+  }
+  // normalize (affine.txx:220-253; rigid3d.cxx:260-281: no covariance update, centre NOT reset).
+  void normalize(double rm, double rf, const double* cm, const double* cf) {
+    double s = rm / rf;
+    for (int i = 0; i < 9; ++i) A[i] = s * A[i];
+    double dc[3] = {cm[0] - c[0], cm[1] - c[1], cm[2] - c[2]};
+    for (int r = 0; r < 3; ++r) {
+      double acc = A[3 * r] * dc[0]; acc += A[3 * r + 1] * dc[1]; acc += A[3 * r + 2] * dc[2];
+      t[r] = t[r] / rf + acc / rm - cf[r] / rf;
+    }
+    if (kind == TRANS_AFFINE) {
+      const int df = 12, dm = 3, dm2 = 9;
+      std::vector<double> B((size_t)df * df, 0.0);
+      double temp = rm / rf;
+      for (int d = 0; d < dm2; ++d) B[d * df + d] = temp;
+      double factor[3] = {dc[0] / rf, dc[1] / rf, dc[2] / rf};
+      for (int d1 = 0; d1 < dm; ++d1) for (int d2 = 0; d2 < dm; ++d2) B[(dm2 + d1) * df + d1 * dm + d2] = factor[d2];
+      temp = 1.0 / rf;
+      for (int d = dm2; d < df; ++d) B[d * df + d] = temp;
+      covar = mat_BCBt(B, covar, df);
+      c[0] = c[1] = c[2] = 0.0;
+    }
+  }
+  // unnormalize (affine.txx:259-286; rigid3d.cxx:285-305).
+  void unnormalize(double rm, double rf, const double* cm, const double* cf) {
+    double s = rf / rm;
+    for (int i = 0; i < 9; ++i) A[i] = s * A[i];
+    if (kind == TRANS_AFFINE) {
+      for (int r = 0; r < 3; ++r) t[r] = rf * t[r] + cf[r];
+      const int df = 12, dm2 = 9;
+      std::vector<double> B((size_t)df * df, 0.0);
+      for (int d = 0; d < dm2; ++d) B[d * df + d] = rf / rm;
+      for (int d = dm2; d < df; ++d) B[d * df + d] = rf;
+      covar = mat_BCBt(B, covar, df);
+    } else {
+      for (int r = 0; r < 3; ++r) {
+        double acc = (-A[3 * r]) * cm[0]; acc += (-A[3 * r + 1]) * cm[1]; acc += (-A[3 * r + 2]) * cm[2];
+        t[r] = acc + rf * t[r] + cf[r];
+      }
+    }
+    c[0] = cm[0]; c[1] = cm[1]; c[2] = cm[2];
+  }
+  // recompose_increment (rigid3d.cxx:309-326): dR = U V^T, R <- R * dR, t <- dR * t + dt   (Q7).
+  void recompose_increment(const Trans& inc) {
+    double dR[9]; svd_orthogonalize3(inc.A, dR);
+    double Rn[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+      double acc = A[3 * i] * dR[j]; acc += A[3 * i + 1] * dR[3 + j]; acc += A[3 * i + 2] * dR[6 + j];
+      Rn[3 * i + j] = acc;
+    }
+    double tn[3];
+    for (int i = 0; i < 3; ++i) {
+      double acc = dR[3 * i] * t[0]; acc += dR[3 * i + 1] * t[1]; acc += dR[3 * i + 2] * t[2];
+      tn[i] = acc + inc.t[i];
+    }
+    for (int i = 0; i < 9; ++i) A[i] = Rn[i];
+    for (int i = 0; i < 3; ++i) t[i] = tn[i];
+  }
+  static std::vector<double> mat_BCBt(const std::vector<double>& B, const std::vector<double>& C, int n) {
+    std::vector<double> T((size_t)n * n, 0.0), R((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k < n; ++k) s += B[i * n + k] * C[k * n + j]; T[i * n + j] = s; }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k < n; ++k) s += T[i * n + k] * B[j * n + k]; R[i * n + j] = s; }
+    return R;
+  }
+};
+using TransP = std::shared_ptr<Trans>;
+
+// residual2 = e^T P e, vnl order: (e^T P) then dot e; clamped at 0 (cdcl :219-220).
+inline double proj_residual2(const double* e, const double* P) {
+  double r = 0;
+  for (int j = 0; j < 3; ++j) {
+    double col = e[0] * P[j]; col += e[1] * P[3 + j]; col += e[2] * P[6 + j];
+    r += col * e[j];
+  }
+  if (r < 0.0) r = 0.0;
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Forward estimator: cdcl_estimation_ICP_matching_all<3,dof> (FLAVOR_CDCL) and
+// rrl_estimation_ICP_matching_all<3,12> (FLAVOR_RRL; exact-NN branch rrl :523-526, see Q5).
+struct FwdEst {
+  int flavor;
+  std::vector<FeatureP> moving_base_;  // moving_ as handed in (order of set_moving_data)
+  std::vector<FeatureP> moving_;       // moving_[res_], shuffled in place per policy
+  std::vector<FeatureP> fixed_;
+  std::vector<Match> matches_;
+  TransP trans_;
+  std::shared_ptr<const KdTree> kd_;   // kd_tree_[res_]; may be shared between estimators over one fixed set
+  size_t number_points_ = 1000;
+  bool normalize_matches_ = false, weight_by_strength_ = false, scale_estimated_ = false;
+  // injection points
+  int shuffle_mode = 0; SplitMix64 rng{0};
+  double initial_scale = std::numeric_limits<double>::quiet_NaN();
+  double last_scale = 0;
+  double last_norm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cm[3], rm, cf[3], rf
+
+  // ctor #2 (cdcl :73-91, rrl :89-113)
+  FwdEst(int flavor_, const std::vector<FeatureP>& moving, const std::vector<FeatureP>& fixed, TransP trans,
+         std::shared_ptr<const KdTree> prebuilt = nullptr)
+      : flavor(flavor_), moving_base_(moving), moving_(moving), fixed_(fixed), trans_(trans), kd_(prebuilt) {
+    if (!kd_) build_kd_trees();
+    if (number_points_ > moving_.size()) number_points_ = moving_.size();
+  }
+  // build_kd_trees (cdcl :113-135)
+  void build_kd_trees() {
+    std::vector<double> pts; pts.reserve(fixed_.size() * 3);
+    for (auto& f : fixed_) { pts.push_back(f->loc[0]); pts.push_back(f->loc[1]); pts.push_back(f->loc[2]); }
+    auto kd = std::make_shared<KdTree>(); kd->build(pts); kd_ = kd;
+  }
+  // set_number_points (cdcl :95-108)
+  bool set_number_points(size_t n) {
+    if (n >= moving_.size()) { number_points_ = moving_.size(); return true; }
+    number_points_ = n; return false;
+  }
+  // set_transform (cdcl :141-153)
+  void set_transform(TransP t) {
+    trans_ = t; scale_estimated_ = false; number_points_ = 1000;
+    if (number_points_ > moving_.size()) number_points_ = moving_.size();
+  }
+  // set_moving_data (cdcl .h:96)
+  void set_moving_data(const std::vector<FeatureP>& m) { matches_.clear(); moving_base_ = m; moving_ = m; }
+  void set_order(const int32_t* perm, size_t n) {
+    std::vector<FeatureP> m(n);
+    for (size_t i = 0; i < n; ++i) m[i] = moving_base_[perm[i]];
+    moving_ = m;
+  }
+
+  // RMS_error (cdcl :196-230; rrl :211-241 never increments count -> returns the plain sum, Q1)
+  double RMS_error() const {
+    double error = 0.0; unsigned count = 0;
+    for (auto& m : matches_) {
+      double y[3]; trans_->map_loc(m.from->loc, y);
+      double e[3] = {y[0] - m.to->loc[0], y[1] - m.to->loc[1], y[2] - m.to->loc[2]};
+      error += proj_residual2(e, m.to->P);
+      if (flavor == FLAVOR_CDCL) count += 1;
+    }
+    if (count != 0) error = std::sqrt(error / double(count));
+    return error;
+  }
+  // weighted_error (cdcl :236-268, rrl :247-276)
+  double weighted_error() const {
+    double error = 0.0, sum_weight = 0.0;
+    for (auto& m : matches_) {
+      double y[3]; trans_->map_loc(m.from->loc, y);
+      double e[3] = {y[0] - m.to->loc[0], y[1] - m.to->loc[1], y[2] - m.to->loc[2]};
+      double r2 = proj_residual2(e, m.to->P);
+      error += std::sqrt(r2) * m.w; sum_weight += m.w;
+    }
+    if (sum_weight != 0) error /= sum_weight;
+    return error;
+  }
+  // median_error (cdcl :159-190)
+  double median_error() const {
+    std::vector<double> errors;
+    for (auto& m : matches_) {
+      double y[3]; trans_->map_loc(m.from->loc, y);
+      double e[3] = {y[0] - m.to->loc[0], y[1] - m.to->loc[1], y[2] - m.to->loc[2]};
+      errors.push_back(std::sqrt(proj_residual2(e, m.to->P)));
+    }
+    if (errors.empty()) return 0.0;
+    auto loc = errors.begin() + (errors.size() - 1) / 2 + 1;
+    if (loc == errors.end()) --loc;  // reference would read past the end for size 1
+    std::nth_element(errors.begin(), loc, errors.end());
+    return *loc;
+  }
+  static double fold_angle(double dot) {
+    double a = std::acos(dot);
+    if (a > M_PI / 2) a = M_PI - a;
+    return a;
+  }
+  // sheet_angles (cdcl :273-323 via eigenvectors of the covariances; rrl :281-323 via mapped directions_)
+  double sheet_angles() const {
+    double avg = 0.0, sw = 0.0;
+    for (auto& m : matches_) {
+      const Feature& p = *m.from; const Feature& q = *m.to;
+      if (p.shape != SHEET || q.shape != SHEET) continue;
+      double ang;
+      if (flavor == FLAVOR_CDCL) {
+        double Vp[9], Vq[9], D[3];
+        sym_eig3(p.cov, Vp, D); sym_eig3(q.cov, Vq, D);
+        ang = fold_angle(Vp[0] * Vq[0] + Vp[3] * Vq[3] + Vp[6] * Vq[6]);
+      } else {
+        double y[3]; trans_->map_loc(p.loc, y);
+        double pn[3] = {p.loc[0] + p.dirs[0][0], p.loc[1] + p.dirs[0][1], p.loc[2] + p.dirs[0][2]}, yn[3];
+        trans_->map_loc(pn, yn);
+        double d[3] = {yn[0] - y[0], yn[1] - y[1], yn[2] - y[2]};
+        double nrm = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int k = 0; k < 3; ++k) d[k] /= nrm;
+        ang = fold_angle(d[0] * q.dirs[0][0] + d[1] * q.dirs[0][1] + d[2] * q.dirs[0][2]);
+      }
+      avg += m.w * ang; sw += m.w;
+    }
+    return avg / sw;
+  }
+  // tube_angles (cdcl :328-382: column 2 = largest-eigenvalue eigenvector; rrl :328-375: tangent = d0 x d1)
+  double tube_angles() const {
+    double avg = 0.0, sw = 0.0;
+    for (auto& m : matches_) {
+      const Feature& p = *m.from; const Feature& q = *m.to;
+      if (p.shape != TUBE || q.shape != TUBE) continue;
+      double ang;
+      if (flavor == FLAVOR_CDCL) {
+        double Vp[9], Vq[9], D[3];
+        sym_eig3(p.cov, Vp, D); sym_eig3(q.cov, Vq, D);
+        ang = fold_angle(Vp[2] * Vq[2] + Vp[5] * Vq[5] + Vp[8] * Vq[8]);
+      } else {
+        auto cross = [](const double* a, const double* b, double* o) {
+          o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+        };
+        double pt[3], qt[3]; cross(p.dirs[0], p.dirs[1], pt); cross(q.dirs[0], q.dirs[1], qt);
+        double y[3]; trans_->map_loc(p.loc, y);
+        double pl[3] = {p.loc[0] + pt[0], p.loc[1] + pt[1], p.loc[2] + pt[2]}, yl[3];
+        trans_->map_loc(pl, yl);
+        double d[3] = {yl[0] - y[0], yl[1] - y[1], yl[2] - y[2]};
+        double nrm = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int k = 0; k < 3; ++k) d[k] /= nrm;
+        ang = fold_angle(d[0] * qt[0] + d[1] * qt[1] + d[2] * qt[2]);
+      }
+      avg += m.w * ang; sw += m.w;
+    }
+    return avg / sw;
+  }
+  // compute_transfer_error_covariance (cdcl :388-404, rrl :381-397)
+  void compute_transfer_error_covariance() {
+    const int dof = trans_->dof;
+    double covJ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> J(3 * dof), T(3 * dof);
+    for (auto& m : matches_) {
+      trans_->jacobian_wrt_par(m.from->loc, J.data());
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < dof; ++j) { double s = 0; for (int k = 0; k < dof; ++k) s += J[i * dof + k] * trans_->covar[k * dof + j]; T[i * dof + j] = s; }
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < dof; ++k) s += T[i * dof + k] * J[j * dof + k]; covJ[i * 3 + j] += s; }
+    }
+    for (int i = 0; i < 9; ++i) trans_->covarJ[i] = covJ[i] * (1.0 / double(matches_.size()));
+  }
+
+  // find_closest_euclidean (cdcl :541-654; rrl :494-571 with the exact-NN branch, Q5)
+  void find_closest_euclidean() {
+    if (shuffle_mode == 1) fisher_yates(moving_, rng);  // vcl_random_shuffle( moving_[res_] )  :557
+    matches_.clear();
+    for (size_t i = 0; i < number_points_; ++i) {
+      FeatureP p = moving_[i];
+      double y[3]; trans_->map_loc(p->loc, y);
+      int idx = kd_->nearest(y);
+      if (idx < 0) continue;
+      matches_.push_back(Match{p, fixed_[idx], 1.0});
+    }
+  }
+
+  // estimate_scale_and_assign_weight (cdcl :660-822, rrl :577-718)
+  double estimate_scale_and_assign_weight() {
+    std::vector<double> distances; distances.reserve(matches_.size());
+    double sum_weighted_error = 0.0, sum_weights = 0.0;
+    for (auto& m : matches_) {
+      double y[3]; trans_->map_loc(m.from->loc, y);
+      double e[3] = {y[0] - m.to->loc[0], y[1] - m.to->loc[1], y[2] - m.to->loc[2]};
+      double residual2 = proj_residual2(e, m.to->P);
+      if (scale_estimated_) { sum_weighted_error += m.w * residual2; sum_weights += m.w; }
+      m.w = residual2;  // temporarily store squared residual
+      distances.push_back(std::sqrt(residual2));
+    }
+    double scale = 0.0;
+    if (!scale_estimated_) {
+      if (std::isnan(initial_scale)) scale = muse_scale(distances);
+      else scale = initial_scale;
+      scale_estimated_ = true;
+    } else {
+      scale = std::sqrt(sum_weighted_error / sum_weights);
+    }
+    const double constant = 1.0;
+    scale = constant * scale;
+    for (auto& m : matches_) {
+      double scale2 = scale * scale;
+      m.w = weight_BT(m.w / scale2) / scale2;
+    }
+    last_scale = scale;
+    return scale;
+  }
+
+  // weight_by_strength (cdcl :826-862; rrl :722-752 with fp32 strengths)  Q13
+  void weight_by_strength_fn() {
+    std::vector<double> gw; gw.reserve(matches_.size());
+    for (auto& m : matches_) {
+      if (m.w != 0) {
+        double grad_w;
+        if (flavor == FLAVOR_RRL) { float g = m.from->strength_f * m.to->strength_f; grad_w = g; }
+        else grad_w = m.from->strength * m.to->strength;
+        if (grad_w > 90000.0) grad_w = 90000.0;
+        m.w *= grad_w; gw.push_back(grad_w);
+      }
+    }
+    double grad_scale = median_abs_dev_scale(gw);
+    for (auto& m : matches_) m.w *= (1.0 / grad_scale);
+  }
+  // weight_spatially (cdcl :973-1004, rrl :756-778)
+  void weight_spatially() {
+    std::vector<double> sw; sw.reserve(matches_.size());
+    for (auto& m : matches_) {
+      const double* q = m.to->loc;
+      double dist = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);   // vnl magnitude()
+      double spatial_weight = 1.0 / (1.0 + 5.0 * dist * dist);
+      m.w *= spatial_weight; sw.push_back(spatial_weight);
+    }
+    double spatial_scale = median_abs_dev_scale(sw);
+    for (auto& m : matches_) m.w *= (1.0 / spatial_scale);
+  }
+
+  // cdcl_normalize_matches (cdcl :1159-1240; rrl :864-943 skips the covariances).
+  // The std::set of smart pointers makes each matched fixed feature count once.
+  void normalize_matches_fn(double* cm, double& rm, double* cf, double& rf) {
+    cm[0] = cm[1] = cm[2] = 0; cf[0] = cf[1] = cf[2] = 0; rm = 0; rf = 0;
+    std::set<Feature*> fixed_matched;
+    for (auto& m : matches_) {
+      for (int d = 0; d < 3; ++d) cm[d] += m.from->loc[d];
+      if (fixed_matched.insert(m.to.get()).second) for (int d = 0; d < 3; ++d) cf[d] += m.to->loc[d];
+    }
+    for (int d = 0; d < 3; ++d) { cm[d] /= double(matches_.size()); cf[d] /= double(fixed_matched.size()); }
+    auto mag = [](const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    for (auto& m : matches_) {
+      for (int d = 0; d < 3; ++d) m.from->loc[d] -= cm[d];
+      rm += mag(m.from->loc);
+    }
+    rm /= double(matches_.size());
+    for (Feature* q : fixed_matched) { for (int d = 0; d < 3; ++d) q->loc[d] -= cf[d]; rf += mag(q->loc); }
+    rf /= double(fixed_matched.size());
+    for (auto& m : matches_) {
+      for (int d = 0; d < 3; ++d) m.from->loc[d] /= rm;
+      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.from->cov[k] /= (rm * rm);
+    }
+    for (Feature* q : fixed_matched) {
+      for (int d = 0; d < 3; ++d) q->loc[d] /= rf;
+      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) q->cov[k] /= (rf * rf);
+    }
+    for (int d = 0; d < 3; ++d) { last_norm[d] = cm[d]; last_norm[4 + d] = cf[d]; }
+    last_norm[3] = rm; last_norm[7] = rf;
+  }
+  // cdcl_unnormalize_matches (cdcl :1245-1286, rrl :948-986)
+  void unnormalize_matches_fn(const double* cm, double rm, const double* cf, double rf) {
+    std::set<Feature*> fixed_matched;
+    for (auto& m : matches_) {
+      for (int d = 0; d < 3; ++d) { m.from->loc[d] *= rm; m.from->loc[d] += cm[d]; }
+      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.from->cov[k] *= (rm * rm);
+      if (fixed_matched.insert(m.to.get()).second) {
+        for (int d = 0; d < 3; ++d) { m.to->loc[d] *= rf; m.to->loc[d] += cf[d]; }
+        if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.to->cov[k] *= (rf * rf);
+      }
+    }
+  }
+
+  // AtA += J^T P J w ; Atb += J^T P q_loc w   (cdcl :1061-1062), dense like the vnl products.
+  static void accumulate_dense(const Trans& tr, const double* Jloc, const double* P, const double* qloc, double w,
+                               std::vector<double>& AtA, std::vector<double>& Atb) {
+    const int dof = tr.dof;
+    std::vector<double> J(3 * dof), JtP(dof * 3);
+    tr.jacobian_wrt_par(Jloc, J.data());
+    for (int i = 0; i < dof; ++i) for (int j = 0; j < 3; ++j) {
+      double s = 0; for (int k = 0; k < 3; ++k) s += J[k * dof + i] * P[k * 3 + j];
+      JtP[i * 3 + j] = s;
+    }
+    for (int i = 0; i < dof; ++i) {
+      for (int j = 0; j < dof; ++j) {
+        double s = 0; for (int k = 0; k < 3; ++k) s += JtP[i * 3 + k] * J[k * dof + j];
+        AtA[i * dof + j] += s * w;
+      }
+      double s = 0; for (int k = 0; k < 3; ++k) s += JtP[i * 3 + k] * qloc[k];
+      Atb[i] += s * w;
+    }
+  }
+
+  // estimate_LS (cdcl :1009-1093, rrl :783-859)
+  void estimate_LS(bool estimate_parameters) {
+    double cm[3] = {0, 0, 0}, cf[3] = {0, 0, 0}, rm = 0, rf = 0;
+    if (normalize_matches_) { normalize_matches_fn(cm, rm, cf, rf); trans_->normalize(rm, rf, cm, cf); }
+    double scale = estimate_scale_and_assign_weight();
+    if (scale < 0.005) scale = 0.005;
+    if (weight_by_strength_) weight_by_strength_fn();
+    const int dof = trans_->dof;
+    std::vector<double> AtA((size_t)dof * dof, 0.0), Atb(dof, 0.0);
+    for (auto& m : matches_) {
+      double qloc[3];
+      if (trans_->kind == TRANS_RIGID3D && flavor == FLAVOR_CDCL)
+        for (int d = 0; d < 3; ++d) qloc[d] = m.to->loc[d] - m.from->loc[d];
+      else for (int d = 0; d < 3; ++d) qloc[d] = m.to->loc[d];
+      accumulate_dense(*trans_, m.from->loc, m.to->P, qloc, m.w, AtA, Atb);
+    }
+    std::vector<double> invAA((size_t)dof * dof);
+    svd_inverse(dof, AtA.data(), invAA.data());
+    trans_->covar = invAA;
+    if (estimate_parameters) {
+      std::vector<double> np(dof, 0.0);
+      for (int i = 0; i < dof; ++i) { double s = 0; for (int k = 0; k < dof; ++k) s += invAA[i * dof + k] * Atb[k]; np[i] = s; }
+      trans_->set_parameterization(np.data());
+    }
+    if (normalize_matches_) { trans_->unnormalize(rm, rf, cm, cf); unnormalize_matches_fn(cm, rm, cf, rf); }
+  }
+
+  // For rigid: replace every match's from_ by a transformed clone (cdcl :455-484).
+  static void make_incremental(FwdEst& e, TransP& global) {
+    global = e.trans_;
+    e.trans_ = global->create_new();
+    e.trans_->covar = global->covar;
+    const double* Jp = global->A;
+    for (auto& m : e.matches_) {
+      auto cl = std::make_shared<Feature>(*m.from);
+      global->map_loc(m.from->loc, cl->loc);
+      double T[9];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += Jp[i * 3 + k] * m.from->cov[k * 3 + j]; T[i * 3 + j] = s; }
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += T[i * 3 + k] * Jp[j * 3 + k]; cl->cov[i * 3 + j] = s; }
+      m.from = cl;
+    }
+    double zero[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    e.trans_->set_parameterization(zero);
+  }
+
+  // one_iteration (cdcl :434-509, rrl :427-462)
+  bool one_iteration() {
+    find_closest_euclidean();
+    double RMS_before = RMS_error();
+    TransP global;
+    bool rigid = (trans_->kind == TRANS_RIGID3D && flavor == FLAVOR_CDCL);
+    if (rigid) make_incremental(*this, global);
+    estimate_LS(true);
+    if (rigid) {
+      global->recompose_increment(*trans_);
+      global->covar = trans_->covar;
+      trans_ = global;
+    }
+    double RMS_after = RMS_error();
+    return std::fabs(RMS_before - RMS_after) < 1e-4;
+  }
+  // run (cdcl :413-428)
+  bool run(int max_iterations, int* iters) {
+    bool converged = false; int it = 0;
+    while (!converged && it < max_iterations) { converged = one_iteration(); ++it; }
+    if (iters) *iters = it;
+    return converged;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Symmetric estimator: cdcl_estimation_symmetric_ICP_matching_all (FLAVOR_CDCL) and
+// rrl_estimation_symmetric_ICP_matching_all (FLAVOR_RRL).
+struct SymEst {
+  int flavor;
+  std::shared_ptr<FwdEst> forward_, backward_;
+  bool normalize_matches_ = true;
+  unsigned oscillation_count_ = 0;
+  double error_difference_ = 0.0, weighted_error_ = 0.0;
+  unsigned number_matches_ = 1000;
+  bool finest_level_ = false;
+  int iterations_done = 0;
+
+  // ctor #3 (cdcl sym :144-164, rrl sym :198-220)
+  SymEst(int flavor_, const std::vector<FeatureP>& moving, const std::vector<FeatureP>& fixed, TransP trans, TransP trans_inverse,
+         const std::vector<FeatureP>& moving_inside, const std::vector<FeatureP>& fixed_inside,
+         std::shared_ptr<const KdTree> kd_fixed = nullptr, std::shared_ptr<const KdTree> kd_moving = nullptr)
+      : flavor(flavor_) {
+    forward_ = std::make_shared<FwdEst>(flavor, moving_inside, fixed, trans, kd_fixed);
+    backward_ = std::make_shared<FwdEst>(flavor, fixed_inside, moving, trans_inverse, kd_moving);
+    forward_->weight_by_strength_ = true; forward_->normalize_matches_ = true;
+    backward_->weight_by_strength_ = true; backward_->normalize_matches_ = true;
+  }
+  void reset_control() { oscillation_count_ = 0; error_difference_ = 0.0; number_matches_ = 1000; finest_level_ = false; }
+  // set_features (cdcl sym :206-226)
+  void set_features(const std::vector<FeatureP>& mi, const std::vector<FeatureP>& fi) {
+    forward_->set_moving_data(mi); backward_->set_moving_data(fi); reset_control();
+  }
+  // set_transform (cdcl sym :231-242)
+  void set_transform(TransP t) { forward_->set_transform(t); backward_->set_transform(t->inverse()); reset_control(); iterations_done = 0; }
+  void find_closest_euclidean() { forward_->find_closest_euclidean(); backward_->find_closest_euclidean(); }
+  bool oscillated() const { return oscillation_count_ > 10; }   // sym .h:156
+
+  // cdcl_normalize_matches_known (cdcl sym :869-908, rrl sym :1093-1129)
+  void normalize_matches_known(std::vector<Match>& matches, const double* cm, double rm, const double* cf, double rf) {
+    std::set<Feature*> fixed_matched;
+    for (auto& m : matches) {
+      for (int d = 0; d < 3; ++d) { m.from->loc[d] -= cm[d]; m.from->loc[d] /= rm; }
+      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.from->cov[k] /= (rm * rm);
+      if (fixed_matched.insert(m.to.get()).second) {
+        for (int d = 0; d < 3; ++d) { m.to->loc[d] -= cf[d]; m.to->loc[d] /= rf; }
+        if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.to->cov[k] /= (rf * rf);
+      }
+    }
+  }
+  // add_constraints (cdcl sym :368-393): clones with from/to reversed, weight kept (Q11)
+  static void add_constraints(const std::vector<Match>& from_matches, std::vector<Match>& to_matches) {
+    for (auto& m : from_matches) {
+      auto p_clone = std::make_shared<Feature>(*m.from);
+      auto q_clone = std::make_shared<Feature>(*m.to);
+      to_matches.push_back(Match{q_clone, p_clone, m.w});
+    }
+  }
+
+  // rrl: ThreadedGenerateDataForward/Backward (rrl sym :441-655): hand-unrolled affine accumulation of the
+  // upper triangle, projector pre-multiplied by the weight, matches with w < 1e-4 skipped.
+  static void rrl_accumulate(const Trans& tr, const double* Jloc, const double* Pmat, const double* bloc, double weight,
+                             double* AtA /*12x12*/, double* Atb /*12*/) {
+    const int dof = 12;
+    if (weight < 1e-4) return;
+    double Jth[3 * 12]; tr.jacobian_wrt_par(Jloc, Jth);
+    double ep[9]; for (int k = 0; k < 9; ++k) ep[k] = Pmat[k] * weight;
+    double JP[12 * 3];
+    for (int r = 0; r < 3; ++r) for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k)
+      JP[(3 * r + a) * 3 + k] = Jth[r * dof + 3 * r + a] * ep[r * 3 + k];
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) JP[(9 + r) * 3 + k] = ep[r * 3 + k];
+    for (int i = 0; i < dof; ++i) for (int j = i; j < dof; ++j) {
+      double accum = JP[i * 3 + 0] * Jth[0 * dof + j];
+      for (int k = 1; k < 3; ++k) accum += JP[i * 3 + k] * Jth[k * dof + j];
+      AtA[i * dof + j] += accum;
+    }
+    for (int i = 0; i < dof; ++i) {
+      double accum = JP[i * 3 + 0] * bloc[0];
+      for (int k = 1; k < 3; ++k) accum += JP[i * 3 + k] * bloc[k];
+      Atb[i] += accum;
+    }
+  }
+
+  // estimate_LS (cdcl sym :398-701; rrl sym :699-918)
+  void estimate_LS(bool estimate_parameters) {
+    FwdEst& F = *forward_; FwdEst& B = *backward_;
+    TransP fglobal, bglobal;
+    if (flavor == FLAVOR_CDCL) {
+      if (F.trans_->kind == TRANS_RIGID3D) FwdEst::make_incremental(F, fglobal);   // :401-428
+      if (B.trans_->kind == TRANS_RIGID3D) FwdEst::make_incremental(B, bglobal);   // :431-456
+    }
+    double fs = F.estimate_scale_and_assign_weight(); if (fs < 0.005) fs = 0.005;   // before normalisation, Q3
+    double bs = B.estimate_scale_and_assign_weight(); if (bs < 0.005) bs = 0.005;
+    double cm[3] = {0, 0, 0}, cf[3] = {0, 0, 0}, rm = 0, rf = 0;
+    if (normalize_matches_) {
+      F.normalize_matches_fn(cm, rm, cf, rf);
+      F.trans_->normalize(rm, rf, cm, cf);
+      normalize_matches_known(B.matches_, cf, rf, cm, rm);
+      B.trans_->normalize(rf, rm, cf, cm);
+    }
+    const int dof = F.trans_->dof;
+    std::vector<double> AtA((size_t)dof * dof, 0.0), Atb(dof, 0.0);
+    size_t end_of_forward = F.matches_.size();
+    if (flavor == FLAVOR_CDCL) {
+      add_constraints(B.matches_, F.matches_);                 // :541-542
+      if (F.weight_by_strength_) F.weight_by_strength_fn();    // :544
+      F.weight_spatially();                                    // :546
+      for (auto& m : F.matches_) {                             // :575-628
+        double qloc[3];
+        if (F.trans_->kind == TRANS_RIGID3D) for (int d = 0; d < 3; ++d) qloc[d] = m.to->loc[d] - m.from->loc[d];
+        else for (int d = 0; d < 3; ++d) qloc[d] = m.to->loc[d];
+        FwdEst::accumulate_dense(*F.trans_, m.from->loc, m.to->P, qloc, m.w, AtA, Atb);
+      }
+    } else {
+      if (F.weight_by_strength_) F.weight_by_strength_fn();    // rrl sym :724-725
+      if (B.weight_by_strength_) B.weight_by_strength_fn();
+      F.weight_spatially(); B.weight_spatially();              // :727-728
+      for (auto& m : F.matches_) rrl_accumulate(*F.trans_, m.from->loc, m.to->P, m.to->loc, m.w, AtA.data(), Atb.data());
+      // backward list: J at the target q (moving-image feature), projector and b of the source p (:557-646)
+      for (auto& m : B.matches_) rrl_accumulate(*F.trans_, m.to->loc, m.from->P, m.from->loc, m.w, AtA.data(), Atb.data());
+      for (int i = 0; i < dof; ++i) for (int j = i + 1; j < dof; ++j) AtA[j * dof + i] = AtA[i * dof + j];   // :874-876
+    }
+    std::vector<double> invAA((size_t)dof * dof);
+    svd_inverse(dof, AtA.data(), invAA.data());
+    F.trans_->covar = invAA;
+    if (estimate_parameters) {
+      std::vector<double> np(dof, 0.0);
+      for (int i = 0; i < dof; ++i) { double s = 0; for (int k = 0; k < dof; ++k) s += invAA[i * dof + k] * Atb[k]; np[i] = s; }
+      F.trans_->set_parameterization(np.data());
+    }
+    if (flavor == FLAVOR_CDCL) F.matches_.erase(F.matches_.begin() + end_of_forward, F.matches_.end());   // :665
+    if (normalize_matches_) {
+      F.trans_->unnormalize(rm, rf, cm, cf);
+      F.unnormalize_matches_fn(cm, rm, cf, rf);
+      B.trans_->unnormalize(rf, rm, cf, cm);
+      B.unnormalize_matches_fn(cf, rf, cm, rm);
+    }
+    if (flavor == FLAVOR_CDCL && fglobal) {                    // :677-683
+      fglobal->recompose_increment(*F.trans_);
+      fglobal->covar = F.trans_->covar;
+      F.trans_ = fglobal;
+    }
+    if (estimate_parameters) B.trans_ = F.trans_->inverse();   // :693-695 / rrl :910-912
+    (void)bglobal;
+  }
+
+  // estimate_LS_backward: rrl swaps the two estimators and reuses estimate_LS (rrl sym :922-934);
+  // cdcl has its own body (cdcl sym :705-863).
+  void estimate_LS_backward(bool estimate_parameters) {
+    if (flavor == FLAVOR_RRL) {
+      std::swap(forward_, backward_);
+      estimate_LS(estimate_parameters);
+      std::swap(forward_, backward_);
+      return;
+    }
+    FwdEst& F = *forward_; FwdEst& B = *backward_;
+    TransP bglobal;
+    if (B.trans_->kind == TRANS_RIGID3D) FwdEst::make_incremental(B, bglobal);
+    double fs = F.estimate_scale_and_assign_weight(); if (fs < 0.005) fs = 0.005;
+    double bs = B.estimate_scale_and_assign_weight(); if (bs < 0.005) bs = 0.005;
+    size_t end_of_backward = B.matches_.size();
+    add_constraints(F.matches_, B.matches_);                   // :744
+    double cm[3] = {0, 0, 0}, cf[3] = {0, 0, 0}, rm = 0, rf = 0;
+    if (normalize_matches_) { B.normalize_matches_fn(cm, rm, cf, rf); B.trans_->normalize(rm, rf, cm, cf); }
+    if (B.weight_by_strength_) B.weight_by_strength_fn();      // :763
+    const int dof = B.trans_->dof;
+    std::vector<double> AtA((size_t)dof * dof, 0.0), Atb(dof, 0.0);
+    for (auto& m : B.matches_) {
+      double qloc[3];
+      if (B.trans_->kind == TRANS_RIGID3D) for (int d = 0; d < 3; ++d) qloc[d] = m.to->loc[d] - m.from->loc[d];
+      else for (int d = 0; d < 3; ++d) qloc[d] = m.to->loc[d];
+      FwdEst::accumulate_dense(*B.trans_, m.from->loc, m.to->P, qloc, m.w, AtA, Atb);
+    }
+    std::vector<double> invAA((size_t)dof * dof);
+    svd_inverse(dof, AtA.data(), invAA.data());
+    B.trans_->covar = invAA;
+    if (estimate_parameters) {
+      std::vector<double> np(dof, 0.0);
+      for (int i = 0; i < dof; ++i) { double s = 0; for (int k = 0; k < dof; ++k) s += invAA[i * dof + k] * Atb[k]; np[i] = s; }
+      B.trans_->set_parameterization(np.data());
+    }
+    B.matches_.erase(B.matches_.begin() + end_of_backward, B.matches_.end());
+    if (normalize_matches_) { B.trans_->unnormalize(rm, rf, cm, cf); B.unnormalize_matches_fn(cm, rm, cf, rf); }
+    if (estimate_parameters) F.trans_ = B.trans_->inverse();
+    if (bglobal) { bglobal->recompose_increment(*B.trans_); bglobal->covar = B.trans_->covar; B.trans_ = bglobal; }
+  }
+
+  // one_iteration (cdcl sym :268-363; rrl sym :341-438: oscillation logic only when iteration > 0)
+  bool one_iteration(unsigned iteration) {
+    double weighted_error_before = forward_->weighted_error();
+    find_closest_euclidean();
+    estimate_LS(true);
+    double weighted_error_after = forward_->weighted_error();
+    double curr_error_difference = weighted_error_after - weighted_error_before;
+    double diff = (weighted_error_after - weighted_error_before) / weighted_error_after;
+    bool converged = std::fabs(diff) < 1e-4;
+    weighted_error_ = weighted_error_after;
+    if (flavor == FLAVOR_CDCL || iteration > 0) {
+      if (!finest_level_ && (oscillation_count_ > 1 || (std::fabs(diff) < 0.01))) converged = true;
+      else if (!converged) {
+        if (weighted_error_after > 1.5) {
+          if (curr_error_difference * error_difference_ < 0.0) ++oscillation_count_;
+          else if (oscillation_count_ > 0) --oscillation_count_;
+          if (oscillated()) converged = true;
+        } else {
+          if (curr_error_difference > 0.0) ++oscillation_count_;
+          if (oscillation_count_ > 3) converged = true;
+        }
+      }
+    }
+    error_difference_ = curr_error_difference;
+    if (converged) {
+      if (!finest_level_) {
+        converged = false;
+        number_matches_ *= 2;
+        bool fmax = forward_->set_number_points(number_matches_);
+        bool bmax = backward_->set_number_points(number_matches_);
+        finest_level_ = fmax && bmax;
+        oscillation_count_ = 0; error_difference_ = 0.0;
+      }
+    }
+    ++iterations_done;
+    return converged && finest_level_;
+  }
+  // driver loop (rrl/itkLocationRegistration.cxx:2418)
+  bool run(int max_iterations, int* iters) {
+    bool converged = false; int it = 0;
+    while (!converged && it < max_iterations) { converged = one_iteration((unsigned)it); ++it; }
+    if (iters) *iters = it;
+    return converged;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// A13: cdcl_obj_fun_cov<3,dof>::compute (cdcl/cdcl_obj_fun_cov.txx:18-134).
+struct ObjFunCov {
+  const std::vector<Match>& matches_;
+  Trans& trans_;
+  std::vector<double> JCpJ_;   // 9 per match
+  ObjFunCov(const std::vector<Match>& matches, Trans& trans) : matches_(matches), trans_(trans) {
+    const double* Jp = trans_.A;
+    JCpJ_.resize(matches_.size() * 9);
+    for (size_t i = 0; i < matches_.size(); ++i) {
+      const double* C = matches_[i].from->cov; double T[9];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += Jp[a * 3 + k] * C[k * 3 + b]; T[a * 3 + b] = s; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += T[a * 3 + k] * Jp[b * 3 + k]; JCpJ_[i * 9 + a * 3 + b] = s; }
+    }
+  }
+  int nx() const { return trans_.dof * (trans_.dof + 1) / 2; }
+  void compute(const double* x, double* f, double* g) {
+    const int dof = trans_.dof;
+    std::vector<double> upper((size_t)dof * dof, 0.0);
+    int ind = 0;
+    for (int d1 = 0; d1 < dof; ++d1) for (int d2 = d1; d2 < dof; ++d2) upper[d1 * dof + d2] = x[ind++];
+    // trans_->set_covariance( upper^T * upper )   :58
+    for (int i = 0; i < dof; ++i) for (int j = 0; j < dof; ++j) { double s = 0; for (int k = 0; k < dof; ++k) s += upper[k * dof + i] * upper[k * dof + j]; trans_.covar[i * dof + j] = s; }
+    double num_of_all_matches = 0.0;
+    std::vector<double> kl((size_t)dof * dof, 0.0), J(3 * dof), T(3 * dof), JtCi(dof * 3), temp(dof);
+    double fv = 0.0;
+    for (size_t i = 0; i < matches_.size(); ++i) {
+      const Feature& p = *matches_[i].from; const Feature& q = *matches_[i].to;
+      trans_.jacobian_wrt_par(p.loc, J.data());
+      double Cij[9];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < dof; ++b) { double s = 0; for (int k = 0; k < dof; ++k) s += J[a * dof + k] * trans_.covar[k * dof + b]; T[a * dof + b] = s; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < dof; ++k) s += T[a * dof + k] * J[b * dof + k]; Cij[a * 3 + b] = JCpJ_[i * 9 + a * 3 + b] + s; }
+      num_of_all_matches += 1.0;
+      for (int k = 0; k < 9; ++k) Cij[k] += q.cov[k];
+      double Ci[9]; inv3(Cij, Ci);
+      double y[3]; trans_.map_loc(p.loc, y);
+      double err[3] = {q.loc[0] - y[0], q.loc[1] - y[1], q.loc[2] - y[2]};
+      double Cie[3]; for (int a = 0; a < 3; ++a) Cie[a] = Ci[a * 3] * err[0] + Ci[a * 3 + 1] * err[1] + Ci[a * 3 + 2] * err[2];
+      double residual = err[0] * Cie[0] + err[1] * Cie[1] + err[2] * Cie[2];
+      double w = matches_[i].w;
+      if (f) fv += w * (rho(residual) + std::log(det3(Cij)));
+      if (g) {
+        for (int a = 0; a < dof; ++a) { temp[a] = J[0 * dof + a] * Cie[0] + J[1 * dof + a] * Cie[1] + J[2 * dof + a] * Cie[2]; }
+        for (int a = 0; a < dof; ++a) for (int b = 0; b < 3; ++b) JtCi[a * 3 + b] = J[0 * dof + a] * Ci[0 * 3 + b] + J[1 * dof + a] * Ci[1 * 3 + b] + J[2 * dof + a] * Ci[2 * 3 + b];
+        double rp = rho_p(residual);
+        for (int a = 0; a < dof; ++a) for (int b = 0; b < dof; ++b) {
+          double jcj = JtCi[a * 3] * J[0 * dof + b] + JtCi[a * 3 + 1] * J[1 * dof + b] + JtCi[a * 3 + 2] * J[2 * dof + b];
+          kl[a * dof + b] += w * (-rp * temp[a] * temp[b] + jcj);
+        }
+      }
+    }
+    if (g) {
+      // g[ind] = < kl , upper^T se + se^T upper >   :106-120
+      ind = 0;
+      for (int d1 = 0; d1 < dof; ++d1) for (int d2 = d1; d2 < dof; ++d2) {
+        double s = 0;
+        // (upper^T se)[i][j] = upper[d1][i] * delta(j,d2) ; (se^T upper)[i][j] = delta(i,d2) * upper[d1][j]
+        for (int i = 0; i < dof; ++i) s += kl[i * dof + d2] * upper[d1 * dof + i];
+        for (int j = 0; j < dof; ++j) s += kl[d2 * dof + j] * upper[d1 * dof + j];
+        g[ind++] = s * (1.0 / num_of_all_matches);
+      }
+    }
+    if (f) *f = fv / num_of_all_matches;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// L-BFGS (stands in for vnl_lbfgs = v3p netlib lbfgs, Nocedal; m = 5, backtracking Armijo/Wolfe line
+// search) with cdcl_lbfgs::report_iter's early stop: finish as soon as |f_start - f| > 5 % |f_start|
+// (cdcl/cdcl_lbfgs.h:30-36) and at most max_evals evaluations (cdcl/cdcl_estimation.txx:299).
+// Trajectory is UNPINNED upstream; the product's host L-BFGS follows this same written spec.
+template <class FG>
+inline int lbfgs_minimize(FG&& fg, std::vector<double>& x, int max_evals, double* f_start, double* f_end) {
+  const int n = (int)x.size(), mem = 5;
+  std::vector<double> g(n), gn(n), xn(n), d(n);
+  std::vector<std::vector<double>> S, Y; std::vector<double> RHO;
+  double f = 0; int evals = 0;
+  fg(x.data(), &f, g.data()); ++evals;
+  *f_start = f; *f_end = f;
+  auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double s = 0; for (int i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  int iter = 0;
+  while (evals < max_evals) {
+    // two-loop recursion
+    d = g;
+    std::vector<double> al(S.size());
+    for (int i = (int)S.size() - 1; i >= 0; --i) { al[i] = RHO[i] * dot(S[i], d); for (int k = 0; k < n; ++k) d[k] -= al[i] * Y[i][k]; }
+    if (!S.empty()) { double gam = dot(S.back(), Y.back()) / dot(Y.back(), Y.back()); for (int k = 0; k < n; ++k) d[k] *= gam; }
+    for (size_t i = 0; i < S.size(); ++i) { double be = RHO[i] * dot(Y[i], d); for (int k = 0; k < n; ++k) d[k] += S[i][k] * (al[i] - be); }
+    for (int k = 0; k < n; ++k) d[k] = -d[k];
+    double gd = dot(g, d);
+    if (!(gd < 0)) break;
+    double gnorm = std::sqrt(dot(g, g));
+    double step = (iter == 0) ? 1.0 / (gnorm > 0 ? gnorm : 1.0) : 1.0;
+    bool accepted = false; double fn = f;
+    while (evals < max_evals) {
+      for (int k = 0; k < n; ++k) xn[k] = x[k] + step * d[k];
+      fg(xn.data(), &fn, gn.data()); ++evals;
+      if (std::isfinite(fn) && fn <= f + 1e-4 * step * gd) { accepted = true; break; }
+      step *= 0.5;
+    }
+    if (!accepted) break;
+    std::vector<double> s(n), yv(n);
+    for (int k = 0; k < n; ++k) { s[k] = xn[k] - x[k]; yv[k] = gn[k] - g[k]; }
+    double sy = dot(s, yv);
+    if (sy > 1e-300) { S.push_back(s); Y.push_back(yv); RHO.push_back(1.0 / sy); if ((int)S.size() > mem) { S.erase(S.begin()); Y.erase(Y.begin()); RHO.erase(RHO.begin()); } }
+    x = xn; g = gn; f = fn; *f_end = f; ++iter;
+    if (std::fabs(*f_start - *f_end) > 0.05 * std::fabs(*f_start)) break;   // report_iter()
+    if (std::sqrt(dot(g, g)) < 1e-12) break;
+  }
+  return evals;
+}
+
+}  // namespace lrro
