@@ -1,0 +1,752 @@
+// C ABI of liblrr_b200.so (include/lrr_gpu.h): contexts, feature sets, estimators and the host-side
+// iteration control (ramp / oscillation state machine of the symmetric estimators), driving the sm_100a
+// kernels of lrr_grid.cu, lrr_icp.cu, lrr_select.cu, lrr_metrics.cu and lrr_batch.cu.
+// There is NO CPU fallback: every entry point that computes needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/lrr_gpu.h"
+#include "lrr_internal.h"
+#include "lrr_host.h"
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return LRR_ERR_CUDA; } \
+  } while (0)
+
+template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
+
+// ---- context -------------------------------------------------------------------------------------------
+extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
+  if (!out) return LRR_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return LRR_ERR_NO_DEVICE; }
+  lrr_ctx* ctx = new lrr_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LRR_ERR_CUDA; }
+  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->stream = ctx->own_stream;
+  ok = ok && dmalloc(&ctx->partials, (size_t)2 * LRR_MAX_BLOCKS * LRR_NRED) == cudaSuccess;
+  ok = ok && dmalloc(&ctx->ticket, 8) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->ticket, 0, 8 * sizeof(unsigned int)) == cudaSuccess;
+  // four selectors (G and S for two groups)
+  const size_t sel_uints = (size_t)LRR_SEL_FINE + LRR_SEL_COARSE;
+  ok = ok && dmalloc(&ctx->sel_hist, 4 * sel_uints) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->sel_hist, 0, 4 * sel_uints * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && dmalloc(&ctx->sel_cand, (size_t)4 * LRR_SEL_CAP) == cudaSuccess;
+  ok = ok && dmalloc(&ctx->sel_misc, (size_t)4 * 8) == cudaSuccess;   // 8 x 8 bytes per selector
+  ok = ok && cudaMemset(ctx->sel_misc, 0, 4 * 8 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && dmalloc(&ctx->muse_table, 4 * 32) == cudaSuccess;
+  ok = ok && dmalloc(&ctx->scratch_d, 1024) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&ctx->pinned, 2 * sizeof(Scal) + 4096) == cudaSuccess;
+  ctx->sort.keys2 = nullptr; ctx->sort.hist = nullptr; ctx->sort.cap = 0; ctx->sort_keys = nullptr;
+  if (!ok) { cudaGetLastError(); lrr_ctx_destroy(ctx); return LRR_ERR_CUDA; }
+  for (int i = 0; i < 4; ++i) {
+    SelDev& s = ctx->sel[i];
+    s.fine = ctx->sel_hist + (size_t)i * sel_uints; s.coarse = s.fine + LRR_SEL_FINE;
+    s.cand = ctx->sel_cand + (size_t)i * LRR_SEL_CAP;
+    unsigned long long* m = ctx->sel_misc + (size_t)i * 8;
+    s.cand_minmax = m; s.cand_count = (unsigned int*)(m + 2); s.bin = (int*)(m + 3); s.rank = (unsigned int*)(m + 4);
+    s.count = (double*)(m + 5); s.result = (double*)(m + 6);
+    s.inv_width = (i < 2) ? (double)LRR_SEL_FINE / LRR_STRENGTH_CAP : (double)LRR_SEL_FINE;   // G keys in [0,9e4], S keys in (0,1]
+  }
+  *out = ctx;
+  return LRR_OK;
+}
+extern "C" void lrr_ctx_destroy(lrr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->sel_hist); cudaFree(ctx->sel_cand); cudaFree(ctx->sel_misc);
+  cudaFree(ctx->muse_table); cudaFree(ctx->scratch_d); cudaFree(ctx->sort_keys);
+  if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+extern "C" int lrr_ctx_set_stream(lrr_ctx* ctx, void* s) { if (!ctx) return LRR_ERR_INVALID; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return LRR_OK; }
+extern "C" int lrr_ctx_synchronize(lrr_ctx* ctx) { if (!ctx) return LRR_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return LRR_OK; }
+extern "C" const char* lrr_ctx_last_error(lrr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t lrr_ctx_launch_count(lrr_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
+
+int lrr_ctx_need_sort(lrr_ctx* ctx, size_t n) {
+  if (ctx->sort.cap >= n && ctx->sort_keys) return LRR_OK;
+  if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
+  cudaFree(ctx->sort_keys); ctx->sort_keys = nullptr;
+  CK(lrr_sort_alloc(&ctx->sort, n));
+  CK(dmalloc(&ctx->sort_keys, n));
+  return LRR_OK;
+}
+
+// ---- feature sets ----------------------------------------------------------------------------------------
+extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6, const double* strength,
+                                   const uint8_t* shape, const double* dirs, lrr_fset** out) {
+  if (!ctx || n < 0 || n > 0x7fffff00LL || !out || (n > 0 && (!xyz || !P6))) return LRR_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  lrr_fset* fs = new lrr_fset(); fs->ctx = ctx; fs->n = n;
+  std::vector<double> zeros; std::vector<uint8_t> zshape;
+  if (!strength) { zeros.assign((size_t)n, 0.0); strength = zeros.data(); }
+  if (!shape) { zshape.assign((size_t)n, 0); shape = zshape.data(); }
+  cudaStream_t st = ctx->stream;
+#define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); lrr_features_destroy(fs); return LRR_ERR_CUDA; } } while (0)
+  FCK(dmalloc(&fs->xyz, (size_t)3 * n)); FCK(dmalloc(&fs->s, (size_t)n)); FCK(dmalloc(&fs->P6, (size_t)6 * n));
+  FCK(dmalloc(&fs->shape, (size_t)n));
+  FCK(cudaMemcpyAsync(fs->xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  FCK(cudaMemcpyAsync(fs->P6, P6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st));
+  FCK(cudaMemcpyAsync(fs->s, strength, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  FCK(cudaMemcpyAsync(fs->shape, shape, (size_t)n, cudaMemcpyHostToDevice, st));
+  if (C6) { FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(cudaMemcpyAsync(fs->C6, C6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st)); }
+  if (dirs) { FCK(dmalloc(&fs->dirs, (size_t)9 * n)); FCK(cudaMemcpyAsync(fs->dirs, dirs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, st)); }
+  FCK(dmalloc(&fs->pos4, (size_t)n)); FCK(dmalloc(&fs->rec, (size_t)8 * n)); FCK(dmalloc(&fs->sorted_of_orig, (size_t)n));
+  FsetBuild fb; memset(&fb, 0, sizeof(fb));
+  fb.n = n; fb.x = fs->xyz; fb.y = fs->xyz + n; fb.z = fs->xyz + 2 * n; fb.pos4 = fs->pos4; fb.sorted_of_orig = fs->sorted_of_orig;
+  FCK(lrr_grid_build(&fb, st, &ctx->launches));
+  fs->cell_start = fb.cell_start;
+  FsetDev& d = fs->dev;
+  d.n = (int)n; d.x = fs->xyz; d.y = fs->xyz + n; d.z = fs->xyz + 2 * n; d.s = fs->s; d.P6 = fs->P6; d.C6 = fs->C6; d.dirs = fs->dirs;
+  d.shape = fs->shape; d.grid = fb.grid; d.rec = fs->rec; d.sorted_of_orig = fs->sorted_of_orig;
+  lrr_k_fill_records(d, fs->rec, st, &ctx->launches);
+  FCK(cudaStreamSynchronize(st));
+  FCK(cudaGetLastError());
+#undef FCK
+  *out = fs;
+  return LRR_OK;
+}
+extern "C" void lrr_features_destroy(lrr_fset* fs) {
+  if (!fs) return;
+  cudaSetDevice(fs->ctx->device);
+  cudaFree(fs->xyz); cudaFree(fs->s); cudaFree(fs->P6); cudaFree(fs->C6); cudaFree(fs->dirs); cudaFree(fs->shape);
+  cudaFree(fs->pos4); cudaFree(fs->rec); cudaFree(fs->sorted_of_orig); cudaFree(fs->cell_start);
+  delete fs;
+}
+extern "C" int64_t lrr_features_size(const lrr_fset* fs) { return fs ? fs->n : 0; }
+extern "C" int lrr_features_nearest(lrr_fset* fs, int64_t nq, const double* q, int32_t* idx) {
+  if (!fs || nq < 0 || (nq > 0 && (!q || !idx))) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = fs->ctx;
+  cudaSetDevice(ctx->device);
+  if (nq == 0) return LRR_OK;
+  double* dq = nullptr; int* di = nullptr;
+  CK(dmalloc(&dq, (size_t)3 * nq)); CK(dmalloc(&di, (size_t)nq));
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dq, q, sizeof(double) * 3 * nq, cudaMemcpyHostToDevice, st));
+  CK(lrr_nn_query(fs->dev.grid, nq, dq, dq + nq, dq + 2 * nq, di, st, &ctx->launches));
+  CK(cudaMemcpyAsync(idx, di, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(dq); cudaFree(di);
+  return LRR_OK;
+}
+
+// ---- estimator helpers -----------------------------------------------------------------------------------
+static void identity_scal(Scal& s, int dof) {
+  memset(&s, 0, sizeof(s));
+  s.A[0] = s.A[4] = s.A[8] = 1.0; s.Ag[0] = s.Ag[4] = s.Ag[8] = 1.0;
+  s.rfrom = s.rto = 1.0; s.G = s.S = 1.0;
+  (void)dof;
+}
+
+static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_all) {
+  d.from_all = from_all; d.to_all = to_all;
+  const size_t cap = (size_t)from_all->n, nto = (size_t)to_all->n;
+  d.cap = cap;
+  CK(dmalloc(&d.fx, 4 * cap)); d.fy = d.fx + cap; d.fz = d.fx + 2 * cap; d.fs = d.fx + 3 * cap;
+  CK(dmalloc(&d.fP6, 6 * cap)); CK(dmalloc(&d.forig, cap)); CK(dmalloc(&d.order, cap));
+  CK(dmalloc(&d.sidx, cap)); CK(dmalloc(&d.w, 4 * cap)); d.r2 = d.w + cap; d.gkey = d.w + 2 * cap; d.skey = d.w + 3 * cap;
+  CK(dmalloc(&d.stamp, nto)); CK(cudaMemsetAsync(d.stamp, 0xFF, nto * sizeof(unsigned long long), ctx->stream));
+  CK(dmalloc(&d.sc, 1));
+  d.epoch = 0; d.has_order = false; d.matches = 0; d.weights_fresh = false;
+  d.initial_scale = std::numeric_limits<double>::quiet_NaN();
+  return LRR_OK;
+}
+static void dir_free(lrr_dir& d) {
+  cudaFree(d.fx); cudaFree(d.fP6); cudaFree(d.forig); cudaFree(d.order); cudaFree(d.sidx); cudaFree(d.w); cudaFree(d.stamp); cudaFree(d.sc);
+}
+static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
+  if (n < 0 || (size_t)n > d.cap) return LRR_ERR_INVALID;
+  cudaStream_t st = ctx->stream;
+  if (idx) {
+    for (int64_t i = 0; i < n; ++i) if (idx[i] < 0 || idx[i] >= d.from_all->n) return LRR_ERR_INVALID;
+    CK(cudaMemcpyAsync(d.forig, idx, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // idx is caller memory
+    lrr_k_gather_from(d.from_all->dev, d.forig, (int)n, d.fx, d.fy, d.fz, d.fs, d.fP6, st, &ctx->launches);
+    d.subset = true;
+  } else {
+    n = d.from_all->n;
+    lrr_k_gather_from(d.from_all->dev, nullptr, (int)n, d.fx, d.fy, d.fz, d.fs, d.fP6, st, &ctx->launches);
+    d.subset = false;
+  }
+  d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false;
+  d.host_order.clear();
+  return LRR_OK;
+}
+
+static DirArgs dir_args(const lrr_dir& d) {
+  DirArgs a; memset(&a, 0, sizeof(a));
+  const size_t n = (size_t)d.n_in;
+  a.fx = d.fx; a.fy = d.fx + n; a.fz = d.fx + 2 * n; a.fs = d.fx + 3 * n;   // compact arrays are packed at stride n_in
+  a.fP6 = d.fP6; a.forig = d.subset ? d.forig : nullptr; a.n_in = (int)d.n_in;
+  a.order = d.has_order ? d.order : nullptr;
+  a.M = (int)std::min<int64_t>(d.number_points, d.n_in);
+  a.to = d.to_all->dev; a.from_all = d.from_all->dev;
+  a.sidx = d.sidx; a.w = d.w; a.r2 = d.r2; a.gkey = d.gkey; a.skey = d.skey;
+  a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
+  a.sc = d.sc;
+  return a;
+}
+
+static EstArgs est_args(lrr_est* e, int src = 0) {
+  EstArgs a; memset(&a, 0, sizeof(a));
+  lrr_ctx* ctx = e->ctx;
+  a.ndir = e->sym() ? 2 : 1;
+  for (int d = 0; d < a.ndir; ++d) a.d[d] = dir_args(e->d[d]);
+  int f = 0;
+  if (e->rrl()) f |= LRR_F_RRL;
+  if (e->dof == 6) f |= LRR_F_RIGID;
+  if (e->normalize) f |= LRR_F_NORMALIZE;
+  if (e->sym()) f |= LRR_F_SYM;
+  if (e->strength) f |= LRR_F_STRENGTH;
+  if (e->kind == LRR_CDCL_SYM) f |= LRR_F_MERGED;
+  a.flags = f; a.dof = e->dof; a.src = src; a.estimate_parameters = 1;
+  a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
+  a.partials = ctx->partials; a.ticket = ctx->ticket;
+  return a;
+}
+
+// upload / download the head of a direction's scalars (everything before the moments)
+static const size_t kScalHead = offsetof(Scal, mom);
+static int push_scal(lrr_est* e, int d) {
+  lrr_ctx* ctx = e->ctx;
+  CK(cudaMemcpyAsync(e->d[d].sc, &e->h[d], kScalHead, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LRR_OK;
+}
+static int pull_scal(lrr_est* e, int mask) {
+  lrr_ctx* ctx = e->ctx;
+  char* pin = (char*)ctx->pinned;
+  for (int d = 0; d < 2; ++d) if (mask & (1 << d))
+    CK(cudaMemcpyAsync(pin + d * sizeof(Scal), e->d[d].sc, kScalHead, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  for (int d = 0; d < 2; ++d) if (mask & (1 << d)) memcpy(&e->h[d], pin + d * sizeof(Scal), kScalHead);
+  return LRR_OK;
+}
+static int dmask(const lrr_est* e) { return e->sym() ? 3 : 1; }
+
+static void inverse_trans(const Scal& f, Scal& b) {   // cdcl_trans_affine::inverse / rigid3d::inverse
+  double invA[9]; lrr_inv3(f.A, invA);
+  for (int i = 0; i < 9; ++i) b.A[i] = invA[i];
+  for (int i = 0; i < 3; ++i) {
+    double acc = (-invA[3 * i]) * f.t[0]; acc += (-invA[3 * i + 1]) * f.t[1]; acc += (-invA[3 * i + 2]) * f.t[2];
+    b.t[i] = acc + f.c[i]; b.c[i] = 0.0;
+  }
+  memset(b.cov, 0, sizeof(b.cov));
+}
+
+static void reset_control(lrr_est* e) { e->oscillation_count = 0; e->error_difference = 0.0; e->number_matches = 1000; e->finest_level = 0; }
+
+extern "C" int lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset* moving_all, lrr_fset* fixed_all, lrr_est** out) {
+  if (!ctx || !moving_all || !fixed_all || !out) return LRR_ERR_INVALID;
+  if (moving_all->ctx != ctx || fixed_all->ctx != ctx) return LRR_ERR_INVALID;
+  if (dim != 3 || (dof != 12 && dof != 6)) return LRR_ERR_UNSUPPORTED;
+  if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;   // Q6
+  if (kind < 0 || kind > 3) return LRR_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  lrr_est* e = new lrr_est();
+  e->ctx = ctx; e->kind = kind; e->dof = dof; e->moving_all = moving_all; e->fixed_all = fixed_all;
+  e->normalize = e->sym(); e->strength = e->sym();   // the symmetric ctor switches both on (cdcl sym :151-156)
+  reset_control(e);
+  int rc = dir_alloc(ctx, e->d[0], moving_all, fixed_all);
+  if (rc == LRR_OK && e->sym()) rc = dir_alloc(ctx, e->d[1], fixed_all, moving_all);
+  if (rc == LRR_OK) rc = dir_set_subset(ctx, e->d[0], nullptr, 0);
+  if (rc == LRR_OK && e->sym()) rc = dir_set_subset(ctx, e->d[1], nullptr, 0);
+  if (rc != LRR_OK) { lrr_est_destroy(e); return rc; }
+  for (int d = 0; d < 2; ++d) {
+    identity_scal(e->h[d], dof);
+    e->d[d].number_points = std::min<int64_t>(1000, e->d[d].n_in);
+    e->d[d].scale_estimated = false;
+  }
+  for (int d = 0; d < (e->sym() ? 2 : 1); ++d) {
+    cudaMemsetAsync(e->d[d].sc, 0, sizeof(Scal), ctx->stream);
+    if ((rc = push_scal(e, d)) != LRR_OK) { lrr_est_destroy(e); return rc; }
+  }
+  *out = e;
+  return LRR_OK;
+}
+extern "C" void lrr_est_destroy(lrr_est* e) {
+  if (!e) return;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  dir_free(e->d[0]); if (e->sym()) dir_free(e->d[1]);
+  delete e;
+}
+
+extern "C" int lrr_est_set_subsets(lrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
+  if (!e || !mi || nm < 0) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  int rc = dir_set_subset(ctx, e->d[0], mi, nm);
+  if (rc != LRR_OK) return rc;
+  if (e->sym()) {
+    rc = (fi && nf > 0) ? dir_set_subset(ctx, e->d[1], fi, nf) : dir_set_subset(ctx, e->d[1], nullptr, 0);
+    if (rc != LRR_OK) return rc;
+    reset_control(e);   // set_features (cdcl sym :206-226)
+  }
+  e->werr_cache_valid = false;
+  return LRR_OK;
+}
+
+static void set_identity_norm(Scal& s) {
+  for (int d = 0; d < 3; ++d) { s.cfrom[d] = 0; s.cto[d] = 0; }
+  s.rfrom = 1; s.rto = 1;
+}
+
+extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
+  if (!e || !A9 || !t3) return LRR_ERR_INVALID;
+  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
+  Scal& f = e->h[0];
+  memcpy(f.A, A9, 72); memcpy(f.t, t3, 24);
+  if (c3) memcpy(f.c, c3, 24); else memset(f.c, 0, 24);
+  memset(f.cov, 0, sizeof(f.cov));
+  if (cov) for (int i = 0; i < e->dof * e->dof; ++i) f.cov[i] = cov[i];
+  f.from_mapped = 0; f.status = 0; f.scale_estimated = 0;
+  if (!e->normalize) set_identity_norm(f);
+  for (int d = 0; d < 2; ++d) {   // set_transform (cdcl :141-153): scale_estimated_ = false, number_points_ = 1000
+    e->d[d].scale_estimated = false;
+    e->d[d].number_points = std::min<int64_t>(1000, e->d[d].n_in);
+  }
+  if ((rc = push_scal(e, 0)) != LRR_OK) return rc;
+  if (e->sym()) {
+    Scal& b = e->h[1];
+    inverse_trans(f, b); b.from_mapped = 0; b.status = 0; b.scale_estimated = 0;
+    if (!e->normalize) set_identity_norm(b);
+    if ((rc = push_scal(e, 1)) != LRR_OK) return rc;
+    reset_control(e);
+  }
+  e->iterations_done = 0;
+  e->werr_cache_valid = false;
+  return LRR_OK;
+}
+
+extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
+  if (!e) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  e->normalize = normalize != 0; e->strength = wbs != 0;
+  if (!e->normalize) {
+    int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
+    for (int d = 0; d < (e->sym() ? 2 : 1); ++d) { set_identity_norm(e->h[d]); if ((rc = push_scal(e, d)) != LRR_OK) return rc; }
+  }
+  return LRR_OK;
+}
+
+extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64_t n) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_dir& d = e->d[dir];
+  if (!perm) { d.has_order = false; return LRR_OK; }
+  if (n != d.n_in) return LRR_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) if (perm[i] < 0 || perm[i] >= n) return LRR_ERR_INVALID;
+  CK(cudaMemcpyAsync(d.order, perm, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d.has_order = true;
+  return LRR_OK;
+}
+extern "C" int lrr_est_set_shuffle(lrr_est* e, int mode, uint64_t seed) {
+  if (!e || (mode != LRR_ORDER_FIXED && mode != LRR_ORDER_RESHUFFLE)) return LRR_ERR_INVALID;
+  e->shuffle_mode = mode; e->seed = seed;
+  for (int d = 0; d < 2; ++d) e->d[d].shuffle_calls = 0;
+  return LRR_OK;
+}
+extern "C" int lrr_est_set_initial_scale(lrr_est* e, int dir, double s) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  e->d[dir].initial_scale = s; return LRR_OK;
+}
+extern "C" int lrr_est_set_number_points(lrr_est* e, int dir, int64_t m, int* at_max) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0) || m < 0) return LRR_ERR_INVALID;
+  lrr_dir& d = e->d[dir];
+  bool r;
+  if (m >= d.n_in) { d.number_points = d.n_in; r = true; } else { d.number_points = m; r = false; }   // cdcl :95-108
+  if (at_max) *at_max = r;
+  return LRR_OK;
+}
+
+// ---- MUSE table (rrel_muset_obj(0,false); Miller & Stewart, CVPR'96; trimmed statistics of the half-normal) ----
+static double gauss_inv_cdf(double p) {   // Acklam's rational approximation + one Halley step
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+  double x;
+  if (p < 0.02425) { double q = std::sqrt(-2 * std::log(p)); x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1); }
+  else if (p <= 1 - 0.02425) { double q = p - 0.5, r = q * q; x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q / (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1); }
+  else { double q = std::sqrt(-2 * std::log(1 - p)); x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1); }
+  const double e = 0.5 * std::erfc(-x / std::sqrt(2.0)) - p;
+  const double u = e * std::sqrt(2 * M_PI) * std::exp(x * x / 2);
+  return x - u / (1 + x * u / 2);
+}
+static int build_muse_table(unsigned n, double* table /* 4 x 32 */) {
+  int rows = 0;
+  for (double frac = 0.25; frac <= 0.95 + 0.00001; frac += 0.05) {
+    long kk = std::lround(frac * n);
+    unsigned k = (kk <= 0) ? 1u : (unsigned)kk; if (k > n) k = n;
+    const double ek = gauss_inv_cdf(0.5 * (1.0 + double(k) / double(n + 1)));
+    const double pk = double(k) / double(n + 1), qk = 1.0 - pk;
+    const double Qk = ek, pQk = std::sqrt(2 / M_PI) * std::exp(-0.5 * Qk * Qk);
+    const double Q1 = 1.0 / pQk, Q2 = Qk / (pQk * pQk), Q3 = (1.0 + 2.0 * Qk * Qk) / (pQk * pQk * pQk);
+    const double vrk = (pk * qk / double(n + 2)) * Q1 * Q1 +
+                       (pk * qk / (double(n + 2) * double(n + 2))) * (2.0 * (qk - pk) * Q1 * Q2 + pk * qk * (Q1 * Q3 + 0.5 * Q2 * Q2));
+    const double sd = std::sqrt(vrk);
+    if (ek / sd < 3.0) continue;
+    const double mean = gauss_inv_cdf(0.5 * (1.0 + double(k) / double(n)));
+    const double div = double(n) * std::sqrt(2 / M_PI) * (1.0 - std::exp(-0.5 * mean * mean));
+    table[4 * rows] = (double)k; table[4 * rows + 1] = ek; table[4 * rows + 2] = sd; table[4 * rows + 3] = div;
+    if (++rows == 32) break;
+  }
+  return rows;
+}
+
+// ---- Feistel cycle-walking permutation: the RESHUFFLE policy (stand-in for vcl_random_shuffle, Q4) --------
+static inline uint64_t splitmix64(uint64_t& s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+static int apply_shuffle(lrr_est* e, int dir) {
+  lrr_ctx* ctx = e->ctx; lrr_dir& d = e->d[dir];
+  if (e->shuffle_mode != LRR_ORDER_RESHUFFLE) return LRR_OK;
+  // Fisher-Yates with SplitMix64, applied cumulatively to the order vector — same spec as the oracle
+  if ((int64_t)d.host_order.size() != d.n_in) { d.host_order.resize((size_t)d.n_in); for (int64_t i = 0; i < d.n_in; ++i) d.host_order[(size_t)i] = (int32_t)i; d.shuffle_calls = 0; d.rng_state = e->seed + (uint64_t)dir * 0x632BE59BD9B4E019ULL; }
+  for (size_t i = d.host_order.size(); i > 1; --i) { size_t j = (size_t)(splitmix64(d.rng_state) % (uint64_t)i); std::swap(d.host_order[i - 1], d.host_order[j]); }
+  CK(cudaMemcpyAsync(d.order, d.host_order.data(), sizeof(int) * d.n_in, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d.has_order = true;
+  return LRR_OK;
+}
+
+// find_closest_euclidean of every direction (cdcl :541-654, sym wrappers)
+static int do_find_closest(lrr_est* e) {
+  lrr_ctx* ctx = e->ctx;
+  const int nd = e->sym() ? 2 : 1;
+  for (int d = 0; d < nd; ++d) {
+    int rc = apply_shuffle(e, d); if (rc != LRR_OK) return rc;
+    e->d[d].epoch += 1;
+    if (e->d[d].epoch == 0xFFFFFFFFu) {   // stamp epochs exhausted: start over
+      CK(cudaMemsetAsync(e->d[d].stamp, 0xFF, (size_t)e->d[d].to_all->n * sizeof(unsigned long long), ctx->stream));
+      e->d[d].epoch = 1;
+    }
+  }
+  EstArgs a = est_args(e);
+  lrr_k_match(a, ctx->stream, &ctx->launches);
+  for (int d = 0; d < nd; ++d) { e->d[d].matches = a.d[d].M; e->d[d].weights_fresh = true; }
+  e->werr_cache_valid = false;
+  return LRR_OK;
+}
+
+static int muse_for_dir(lrr_est* e, const EstArgs& a, int d) {
+  lrr_ctx* ctx = e->ctx;
+  const int M = a.d[d].M;
+  int rc = lrr_ctx_need_sort(ctx, (size_t)std::max(M, 1)); if (rc != LRR_OK) return rc;
+  lrr_k_resid_keys(a.d[d], ctx->sort_keys, ctx->stream, &ctx->launches);
+  lrr_sort_doubles(&ctx->sort, ctx->sort_keys, M, ctx->stream, &ctx->launches);
+  double table[4 * 32];
+  const int rows = build_muse_table((unsigned)M, table);
+  CK(cudaMemcpyAsync(ctx->muse_table, table, sizeof(double) * 4 * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // `table` is a stack buffer
+  lrr_muse_from_sorted(ctx->sort_keys, M, ctx->muse_table, rows, &e->d[d].sc->scale, ctx->stream, &ctx->launches);
+  return LRR_OK;
+}
+
+// estimate_LS (cdcl :1009-1093, cdcl sym :398-701, rrl :783-859, rrl sym :699-918) on the device
+static int do_estimate(lrr_est* e, int src, int estimate_parameters) {
+  lrr_ctx* ctx = e->ctx;
+  const int nd = e->sym() ? 2 : 1;
+  EstArgs a = est_args(e, src);
+  a.estimate_parameters = estimate_parameters;
+  for (int d = 0; d < nd; ++d) if (e->d[d].matches <= 0 || a.d[d].M <= 0) { ctx->err = "estimate_LS without matches"; return LRR_ERR_STATE; }
+  // stale weights (not straight after find_closest): residuals under the current transform first (cdcl :698-701)
+  int stale = 0;
+  for (int d = 0; d < nd; ++d) if (!e->d[d].weights_fresh) stale |= 1 << d;
+  if (stale) { lrr_k_resid(a, stale, ctx->stream, &ctx->launches); a.flags |= LRR_F_USE_OLD_W; }
+  int mode[2] = {0, 0}; double sin[2] = {0, 0};
+  for (int d = 0; d < nd; ++d) {
+    lrr_dir& D = e->d[d];
+    if (!D.scale_estimated) {
+      if (std::isnan(D.initial_scale)) { int rc = muse_for_dir(e, a, d); if (rc != LRR_OK) return rc; mode[d] = 1; }
+      else { mode[d] = 2; sin[d] = D.initial_scale; }
+      D.scale_estimated = true;
+    }
+  }
+  if (e->normalize) { lrr_k_norm1(a, ctx->stream, &ctx->launches); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
+  lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches);
+  if (e->strength || e->sym()) lrr_k_collect(a, ctx->stream, &ctx->launches);
+  lrr_k_accumulate(a, ctx->stream, &ctx->launches);
+  for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
+  e->werr_cache_valid = false;
+  return LRR_OK;
+}
+
+static int check_status(lrr_est* e) {
+  const int nd = e->sym() ? 2 : 1;
+  for (int d = 0; d < nd; ++d) if (e->h[d].status & LRR_ST_SELECT_OVERFLOW) {
+    e->ctx->err = "order-statistic selector overflow (more than LRR_SEL_CAP distinct keys in one histogram bin)";
+    return LRR_ERR_STATE;
+  }
+  return LRR_OK;
+}
+
+static double rms_of(const lrr_est* e, const Scal& s, bool after) {   // RMS_error (cdcl :196-230; rrl :211-241, Q1)
+  const double sum = after ? s.res_sum_r2 : s.sum_r2;
+  if (e->rrl()) return sum;
+  const double cnt = s.res_count;
+  return cnt != 0 ? std::sqrt(sum / cnt) : sum;
+}
+static double werr_of(const Scal& s) { return s.res_sum_w != 0 ? s.res_sum_wr / s.res_sum_w : s.res_sum_wr; }
+
+extern "C" int lrr_est_find_closest(lrr_est* e) {
+  if (!e) return LRR_ERR_INVALID;
+  cudaSetDevice(e->ctx->device);
+  return do_find_closest(e);
+}
+
+static int one_iteration_fwd(lrr_est* e, int* converged) {
+  lrr_ctx* ctx = e->ctx;
+  int rc = do_find_closest(e); if (rc != LRR_OK) return rc;
+  if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
+  EstArgs a = est_args(e);
+  lrr_k_resid(a, 1, ctx->stream, &ctx->launches);
+  if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
+  if ((rc = check_status(e)) != LRR_OK) return rc;
+  const double before = rms_of(e, e->h[0], false), after = rms_of(e, e->h[0], true);
+  *converged = std::fabs(before - after) < 1e-4;   // cdcl :506
+  e->iterations_done += 1;
+  return LRR_OK;
+}
+
+static int weighted_error_now(lrr_est* e, int dir, double* out) {
+  lrr_ctx* ctx = e->ctx;
+  if (e->d[dir].matches <= 0) { *out = 0.0; return LRR_OK; }
+  EstArgs a = est_args(e);
+  lrr_k_resid(a, 1 << dir, ctx->stream, &ctx->launches);
+  int rc = pull_scal(e, 1 << dir); if (rc != LRR_OK) return rc;
+  *out = werr_of(e->h[dir]);
+  return LRR_OK;
+}
+
+// one_iteration of the symmetric estimators (cdcl sym :268-363, rrl sym :341-438)
+static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out) {
+  lrr_ctx* ctx = e->ctx;
+  int rc;
+  double before;
+  if (e->werr_cache_valid) before = e->werr_cache;
+  else if ((rc = weighted_error_now(e, 0, &before)) != LRR_OK) return rc;
+  if ((rc = do_find_closest(e)) != LRR_OK) return rc;
+  if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
+  EstArgs a = est_args(e);
+  lrr_k_resid(a, 1, ctx->stream, &ctx->launches);
+  if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
+  if ((rc = check_status(e)) != LRR_OK) return rc;
+  const double after = werr_of(e->h[0]);
+  e->werr_cache = after; e->werr_cache_valid = true;
+  const double curr = after - before;
+  const double diff = (after - before) / after;
+  bool converged = std::fabs(diff) < 1e-4;
+  e->weighted_error = after;
+  if (!e->rrl() || iteration > 0) {
+    if (!e->finest_level && (e->oscillation_count > 1 || std::fabs(diff) < 0.01)) converged = true;
+    else if (!converged) {
+      if (after > 1.5) {
+        if (curr * e->error_difference < 0.0) ++e->oscillation_count;
+        else if (e->oscillation_count > 0) --e->oscillation_count;
+        if (e->oscillation_count > 10) converged = true;
+      } else {
+        if (curr > 0.0) ++e->oscillation_count;
+        if (e->oscillation_count > 3) converged = true;
+      }
+    }
+  }
+  e->error_difference = curr;
+  if (converged && !e->finest_level) {
+    converged = false;
+    e->number_matches *= 2;
+    int fmax = 0, bmax = 0;
+    lrr_est_set_number_points(e, 0, e->number_matches, &fmax);
+    lrr_est_set_number_points(e, 1, e->number_matches, &bmax);
+    e->finest_level = fmax && bmax;
+    e->oscillation_count = 0; e->error_difference = 0.0;
+  }
+  e->iterations_done += 1;
+  *converged_out = converged && e->finest_level;
+  return LRR_OK;
+}
+
+extern "C" int lrr_est_one_iteration(lrr_est* e, unsigned iteration, int* converged) {
+  if (!e) return LRR_ERR_INVALID;
+  cudaSetDevice(e->ctx->device);
+  int c = 0;
+  int rc = e->sym() ? one_iteration_sym(e, iteration, &c) : one_iteration_fwd(e, &c);
+  if (converged) *converged = c;
+  return rc;
+}
+extern "C" int lrr_est_run(lrr_est* e, int max_iter, int* converged, int* iterations) {
+  if (!e) return LRR_ERR_INVALID;
+  int c = 0, it = 0, rc = LRR_OK;
+  while (!c && it < max_iter) { rc = lrr_est_one_iteration(e, (unsigned)it, &c); if (rc != LRR_OK) break; ++it; }
+  if (converged) *converged = c;
+  if (iterations) *iterations = it;
+  return rc;
+}
+
+extern "C" int lrr_est_get_transform(lrr_est* e, int dir, int* tk, double* A9, double* t3, double* c3, double* cov) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  cudaSetDevice(e->ctx->device);
+  int rc = pull_scal(e, 1 << dir); if (rc != LRR_OK) return rc;
+  const Scal& s = e->h[dir];
+  if (tk) *tk = e->dof == 12 ? LRR_TRANS_AFFINE : LRR_TRANS_RIGID3D;
+  if (A9) memcpy(A9, s.A, 72); if (t3) memcpy(t3, s.t, 24); if (c3) memcpy(c3, s.c, 24);
+  if (cov) memcpy(cov, s.cov, sizeof(double) * e->dof * e->dof);
+  return LRR_OK;
+}
+
+extern "C" int lrr_est_get_matches(lrr_est* e, int dir, int64_t cap, int64_t* n, int32_t* from_idx, int32_t* to_idx, double* w) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_dir& d = e->d[dir];
+  const int64_t m = d.matches;
+  if (n) *n = m;
+  const int64_t c = std::min(m, cap);
+  if (c <= 0 || (!from_idx && !to_idx && !w)) return LRR_OK;
+  EstArgs a = est_args(e);
+  a.d[dir].M = (int)m;
+  int* tmp = nullptr;
+  CK(dmalloc(&tmp, (size_t)2 * m));
+  lrr_k_export_matches(a.d[dir], tmp, tmp + m, ctx->stream, &ctx->launches);
+  if (from_idx) CK(cudaMemcpyAsync(from_idx, tmp, sizeof(int) * c, cudaMemcpyDeviceToHost, ctx->stream));
+  if (to_idx) CK(cudaMemcpyAsync(to_idx, tmp + m, sizeof(int) * c, cudaMemcpyDeviceToHost, ctx->stream));
+  if (w) CK(cudaMemcpyAsync(w, d.w, sizeof(double) * c, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(tmp);
+  return LRR_OK;
+}
+
+extern "C" int lrr_est_metric(lrr_est* e, int which, int dir, double* out) {
+  if (!e || !out || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_dir& d = e->d[dir];
+  EstArgs a = est_args(e);
+  a.d[dir].M = (int)d.matches;   // metrics run over the existing matches
+  int rc;
+  switch (which) {
+    case LRR_METRIC_RMS:
+    case LRR_METRIC_WEIGHTED: {
+      if (d.matches <= 0) { *out = 0.0; return LRR_OK; }
+      lrr_k_resid(a, 1 << dir, ctx->stream, &ctx->launches);
+      if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;
+      *out = which == LRR_METRIC_RMS ? rms_of(e, e->h[dir], true) : werr_of(e->h[dir]);
+      return LRR_OK;
+    }
+    case LRR_METRIC_MEDIAN: {
+      if (d.matches <= 0) { *out = 0.0; return LRR_OK; }
+      const int M = (int)d.matches;
+      lrr_k_resid(a, 1 << dir, ctx->stream, &ctx->launches);
+      if ((rc = lrr_ctx_need_sort(ctx, (size_t)M)) != LRR_OK) return rc;
+      lrr_k_resid_keys(a.d[dir], ctx->sort_keys, ctx->stream, &ctx->launches);
+      lrr_sort_doubles(&ctx->sort, ctx->sort_keys, M, ctx->stream, &ctx->launches);
+      int loc = (M - 1) / 2 + 1; if (loc >= M) loc = M - 1;   // cdcl :186-188
+      CK(cudaMemcpyAsync(ctx->pinned, ctx->sort_keys + loc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      *out = *(double*)ctx->pinned;
+      return LRR_OK;
+    }
+    case LRR_METRIC_SHEET_ANGLES:
+    case LRR_METRIC_TUBE_ANGLES: {
+      if (d.matches <= 0) { ctx->err = "angles without matches"; return LRR_ERR_STATE; }
+      lrr_k_angles(a.d[dir], a.flags, which == LRR_METRIC_SHEET_ANGLES ? 0 : 1, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches);
+      CK(cudaMemcpyAsync(ctx->pinned, &d.sc->ang_num, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      const double* p = (const double*)ctx->pinned;
+      *out = p[0] / p[1];
+      return LRR_OK;
+    }
+    default: return LRR_ERR_INVALID;
+  }
+}
+
+extern "C" int lrr_est_estimate_ls_backward(lrr_est* e, int estimate_parameters) {
+  if (!e || !e->sym()) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  if (e->kind == LRR_CDCL_SYM) { ctx->err = "estimate_LS_backward: cdcl symmetric variant not built yet (rrl only)"; return LRR_ERR_UNSUPPORTED; }
+  // rrl: swap forward_/backward_, estimate_LS, swap back (rrl sym :922-934)
+  int rc = do_estimate(e, 1, estimate_parameters); if (rc != LRR_OK) return rc;
+  if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
+  return check_status(e);
+}
+
+// compute_transfer_error_covariance: covarJ = mean_i J_i Sigma J_i^T  (cdcl :388-404, rrl :381-397)
+extern "C" int lrr_est_transfer_cov(lrr_est* e, int dir, double* S9) {
+  if (!e || !S9 || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_dir& d = e->d[dir];
+  if (d.matches <= 0) { ctx->err = "transfer covariance without matches"; return LRR_ERR_STATE; }
+  EstArgs a = est_args(e);
+  a.d[dir].M = (int)d.matches;
+  lrr_k_transfer_cov(a.d[dir], e->dof, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches);
+  int rc = pull_scal(e, 1 << dir); if (rc != LRR_OK) return rc;
+  double m10[10];
+  CK(cudaMemcpyAsync(ctx->pinned, d.sc->covJ, 10 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(m10, ctx->pinned, sizeof(m10));
+  // M[a][b] = sum x~_a x~_b
+  double Mm[4][4];
+  Mm[0][0] = m10[0]; Mm[0][1] = Mm[1][0] = m10[1]; Mm[0][2] = Mm[2][0] = m10[2]; Mm[0][3] = Mm[3][0] = m10[3];
+  Mm[1][1] = m10[4]; Mm[1][2] = Mm[2][1] = m10[5]; Mm[1][3] = Mm[3][1] = m10[6]; Mm[2][2] = m10[7]; Mm[2][3] = Mm[3][2] = m10[8]; Mm[3][3] = m10[9];
+  const int dof = e->dof; const double* Sg = e->h[dir].cov;
+  // J[dd][i] = sum_a x~_a E[a][dd][i]
+  auto E = [&](int a_, int dd, int i) -> double {
+    if (dof == 12) { const int di = i < 9 ? i / 3 : i - 9, ai = i < 9 ? i % 3 : 3; return (di == dd && ai == a_) ? 1.0 : 0.0; }
+    if (i >= 3) return (a_ == 3 && dd == i - 3) ? 1.0 : 0.0;
+    if (a_ == 3 || dd == i || a_ != 3 - dd - i) return 0.0;
+    return ((dd == 2 && i == 0) || (dd == 0 && i == 1) || (dd == 1 && i == 2)) ? 1.0 : -1.0;
+  };
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    double s = 0;
+    for (int a_ = 0; a_ < 4; ++a_) for (int i = 0; i < dof; ++i) { const double ea = E(a_, r, i); if (ea == 0) continue;
+      for (int b_ = 0; b_ < 4; ++b_) for (int j = 0; j < dof; ++j) { const double eb = E(b_, c, j); if (eb == 0) continue; s += Mm[a_][b_] * ea * eb * Sg[i * dof + j]; } }
+    S9[r * 3 + c] = s * (1.0 / (double)d.matches);
+  }
+  return LRR_OK;
+}
+
+extern "C" int lrr_est_get_state(lrr_est* e, lrr_est_state* s) {
+  if (!e || !s) return LRR_ERR_INVALID;
+  cudaSetDevice(e->ctx->device);
+  int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
+  memset(s, 0, sizeof(*s));
+  const int nd = e->sym() ? 2 : 1;
+  for (int d = 0; d < nd; ++d) {
+    s->number_points[d] = std::min<int64_t>(e->d[d].number_points, e->d[d].n_in);
+    s->scale[d] = e->h[d].scale; s->scale_estimated[d] = e->d[d].scale_estimated;
+  }
+  for (int k = 0; k < 3; ++k) { s->norm_center_moving[k] = e->h[0].cfrom[k]; s->norm_center_fixed[k] = e->h[0].cto[k]; }
+  s->norm_radius_moving = e->h[0].rfrom; s->norm_radius_fixed = e->h[0].rto;
+  if (e->sym()) {
+    s->number_matches = e->number_matches; s->finest_level = e->finest_level; s->oscillation_count = (int)e->oscillation_count;
+    s->error_difference = e->error_difference; s->weighted_error = e->weighted_error;
+  }
+  s->iterations_done = e->iterations_done;
+  return LRR_OK;
+}
+extern "C" int lrr_est_oscillated(lrr_est* e, int* out) {
+  if (!e || !out) return LRR_ERR_INVALID;
+  *out = e->sym() ? (e->oscillation_count > 10) : 0;   // sym .h:156
+  return LRR_OK;
+}
+
+extern "C" int lrr_objcov_eval(lrr_est* e, int, const double*, double*, double*) { if (e) e->ctx->err = "objcov not built yet"; return LRR_ERR_UNSUPPORTED; }
+extern "C" int lrr_objcov_refine(lrr_est* e, int, int, double*, double*, int*) { if (e) e->ctx->err = "objcov not built yet"; return LRR_ERR_UNSUPPORTED; }
+extern "C" int lrr_batch_run(lrr_ctx* ctx, lrr_fset*, lrr_fset*, const lrr_job*, int64_t, int, uint64_t, lrr_result*) {
+  if (ctx) ctx->err = "batch not built yet"; return LRR_ERR_UNSUPPORTED;
+}

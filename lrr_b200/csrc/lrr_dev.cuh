@@ -33,15 +33,36 @@ __device__ __forceinline__ double lrr_weight_BT(double u) {
   if (u <= 16.0) { double t = 1 - u * 0.0625; return t * t; }
   return 0.0;
 }
+// cdcl/cdcl_utils.h:158-178 and :184-204
+__device__ __forceinline__ double lrr_rho(double r) {
+  const double b_2 = 16.0, f = 2.9872, c = b_2 / 6.0;
+  if (r > b_2) return f * c;
+  double t = 1 - r / b_2;
+  return f * c * (1 - t * t * t);
+}
+__device__ __forceinline__ double lrr_rho_p(double r) {
+  const double b_2 = 16.0, f = 2.9872;
+  if (r > b_2) return 0.0;
+  double t = 1 - r / b_2;
+  return f * 0.5 * t * t;
+}
+
+__device__ __forceinline__ double4 lrr_ld_pos4(const double4* __restrict__ p) {
+  // two 16-byte read-only loads of one 32-byte sector
+  const double2* q = reinterpret_cast<const double2*>(p);
+  double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ int lrr_pos4_orig(const double4& p) { return (int)__double_as_longlong(p.w); }
 
 // scan points [lo,hi) of the cell-sorted position array
-__device__ __forceinline__ void lrr_nn_scan(const GridDev& g, int lo, int hi, double qx, double qy, double qz, double& best,
-                                            int& best_s, int& best_o) {
+__device__ __forceinline__ void lrr_nn_scan(const double4* __restrict__ pos4, int lo, int hi, double qx, double qy, double qz,
+                                            double& best, int& best_s, int& best_o) {
   for (int j = lo; j < hi; ++j) {
-    const double* p = g.gpos + 3 * (size_t)j;
-    double d = lrr_dist2_exact(qx, qy, qz, p[0], p[1], p[2]);
-    if (d < best) { best = d; best_s = j; best_o = g.gorig[j]; }
-    else if (d == best) { int o = g.gorig[j]; if (o < best_o) { best_s = j; best_o = o; } }
+    double4 p = lrr_ld_pos4(pos4 + j);
+    double d = lrr_dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+    if (d < best) { best = d; best_s = j; best_o = lrr_pos4_orig(p); }
+    else if (d == best) { int o = lrr_pos4_orig(p); if (o < best_o) { best_s = j; best_o = o; } }
   }
 }
 
@@ -71,10 +92,10 @@ __device__ __forceinline__ int lrr_nn_search(const GridDev& g, double qx, double
         const int row = (z * g.ny + y) * g.nx;
         if (face || r == 0) {
           // whole x-run [x0,x1] is new: x-adjacent cells are contiguous in the sorted order
-          lrr_nn_scan(g, g.cell_start[row + x0], g.cell_start[row + x1 + 1], qx, qy, qz, best, best_s, best_o);
+          lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + x0), __ldg(g.cell_start + row + x1 + 1), qx, qy, qz, best, best_s, best_o);
         } else {
-          if (cx - r >= 0) lrr_nn_scan(g, g.cell_start[row + cx - r], g.cell_start[row + cx - r + 1], qx, qy, qz, best, best_s, best_o);
-          if (cx + r < g.nx) lrr_nn_scan(g, g.cell_start[row + cx + r], g.cell_start[row + cx + r + 1], qx, qy, qz, best, best_s, best_o);
+          if (cx - r >= 0) lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + cx - r), __ldg(g.cell_start + row + cx - r + 1), qx, qy, qz, best, best_s, best_o);
+          if (cx + r < g.nx) lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + cx + r), __ldg(g.cell_start + row + cx + r + 1), qx, qy, qz, best, best_s, best_o);
         }
       }
     }
@@ -93,44 +114,97 @@ __device__ __forceinline__ int lrr_nn_search(const GridDev& g, double qx, double
   return best_s;
 }
 
-// ---- deterministic two-level reduction -------------------------------------------------------------
-// Each thread contributes K doubles; warp shuffles, then shared memory across warps, then one row of
-// `partials` per block.  The last block to finish (atomic ticket) adds the rows in fixed order, so the
-// result is reproducible run to run.  Returns true in every thread of the last block; out[K] is then
-// valid in shared memory `sh_out` (K <= LRR_NRED).
-template <int K>
-__device__ __forceinline__ bool lrr_block_reduce(double (&v)[K], double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                                 double* sh_out /* >= K */, double* sh_tmp /* >= K*nwarps */) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// ---- reduction scopes ------------------------------------------------------------------------------
+// A phase body is written once against a Scope: `first()/stride()` drive the element loop, `reduce<K>`
+// sums K doubles per thread over the scope.  It returns true in every thread of the FINALIZER block with
+// the totals in shared memory; the finalizer then writes the derived scalars to Scal.
+//   GridScope : one kernel over the whole GPU.  Warp shuffles, shared memory across warps, one row of
+//               `partials` per block; the last block to finish (atomic ticket) adds the rows in fixed
+//               order, so results are reproducible run to run.
+//   BlockScope: one thread block owns the whole registration (batched mode): block reduction only.
+struct GridScope {
+  double* partials; unsigned int* ticket;
+  __device__ __forceinline__ int first() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+  __device__ __forceinline__ int stride() const { return gridDim.x * blockDim.x; }
+  // G = lanes per item: lanes with equal (lane % G) are summed; outputs are K*G values, index g*K + k.
+  template <int K, int G = 1>
+  __device__ __forceinline__ bool reduce(double (&v)[K], double* sh_out /* >= K*G */, double* sh_tmp /* >= K*G*nwarps */) const {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int KG = K * G;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double x = v[k];
+    for (int k = 0; k < K; ++k) {
+      double x = v[k];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) sh_tmp[wid * K + k] = x;
+      for (int o = 16; o >= G; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane < G) sh_tmp[wid * KG + lane * K + k] = x;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < KG; k += blockDim.x) {
+      double s = 0;
+      for (int w = 0; w < nw; ++w) s += sh_tmp[w * KG + k];
+      partials[(size_t)blockIdx.x * LRR_NRED + k] = s;
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int t = atomicAdd(ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+      if (is_last) *ticket = 0;   // re-arm for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    for (int k = threadIdx.x; k < KG; k += blockDim.x) {
+      double s = 0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
+      sh_out[k] = s;
+    }
+    __syncthreads();
+    return true;
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    double s = 0;
-    for (int w = 0; w < nw; ++w) s += sh_tmp[w * K + k];
-    partials[(size_t)blockIdx.x * LRR_NRED + k] = s;
+  // ticket only (no sums): true in every thread of the last block
+  __device__ __forceinline__ bool last_block() const {
+    __shared__ bool is_last2;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int t = atomicAdd(ticket, 1u);
+      is_last2 = (t == gridDim.x - 1);
+      if (is_last2) *ticket = 0;
+    }
+    __syncthreads();
+    if (is_last2) __threadfence();
+    return is_last2;
   }
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-    if (is_last) *ticket = 0;   // re-arm for the next launch
+  __device__ __forceinline__ void phase_end() const {}
+};
+
+struct BlockScope {
+  __device__ __forceinline__ int first() const { return threadIdx.x; }
+  __device__ __forceinline__ int stride() const { return blockDim.x; }
+  template <int K, int G = 1>
+  __device__ __forceinline__ bool reduce(double (&v)[K], double* sh_out, double* sh_tmp) const {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int KG = K * G;
+    __syncthreads();   // sh_tmp / sh_out may still be read by the previous phase
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = v[k];
+#pragma unroll
+      for (int o = 16; o >= G; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane < G) sh_tmp[wid * KG + lane * K + k] = x;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < KG; k += blockDim.x) {
+      double s = 0;
+      for (int w = 0; w < nw; ++w) s += sh_tmp[w * KG + k];
+      sh_out[k] = s;
+    }
+    __syncthreads();
+    return true;
   }
-  __syncthreads();
-  if (!is_last) return false;
-  __threadfence();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    double s = 0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
-    sh_out[k] = s;
-  }
-  __syncthreads();
-  return true;
-}
+  __device__ __forceinline__ bool last_block() const { __syncthreads(); return true; }
+  // make the finalizer's global writes visible to the whole block before the next phase
+  __device__ __forceinline__ void phase_end() const { __threadfence_block(); __syncthreads(); }
+};

@@ -103,11 +103,11 @@ __global__ void k_cell_sort(const int* __restrict__ cell_start, int ncell, int* 
 }
 
 __global__ void k_fill_pos(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int n,
-                           const int* __restrict__ gorig, double* __restrict__ gpos, int* __restrict__ sorted_of_orig) {
+                           const int* __restrict__ gorig, double4* __restrict__ pos4, int* __restrict__ sorted_of_orig) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   int o = gorig[j];
-  gpos[3 * j] = x[o]; gpos[3 * j + 1] = y[o]; gpos[3 * j + 2] = z[o];
+  pos4[j] = make_double4(x[o], y[o], z[o], __longlong_as_double((long long)o));
   sorted_of_orig[o] = j;
 }
 
@@ -121,7 +121,7 @@ cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches) 
     g.ox = g.oy = g.oz = 0; g.h = 1; g.inv_h = 1; g.nx = g.ny = g.nz = 1;
     if ((e = cudaMalloc(&fb->cell_start, 2 * sizeof(int))) != cudaSuccess) return e;
     cudaMemsetAsync(fb->cell_start, 0, 2 * sizeof(int), st);
-    g.cell_start = fb->cell_start; g.gpos = nullptr; g.gorig = nullptr;
+    g.cell_start = fb->cell_start; g.pos4 = nullptr;
     return cudaSuccess;
   }
   if ((e = cudaMalloc(&d_part, 64 * 6 * sizeof(double))) != cudaSuccess) return e;
@@ -147,21 +147,22 @@ cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches) 
   }
   g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.h = h; g.inv_h = 1.0 / h; g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
   const int ncell = (int)(nx * ny * nz);
-  int *cell_of = nullptr, *counts = nullptr;
+  int *cell_of = nullptr, *counts = nullptr, *gorig = nullptr;
   if ((e = cudaMalloc(&fb->cell_start, (size_t)(ncell + 1) * sizeof(int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&cell_of, (size_t)n * sizeof(int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&counts, (size_t)ncell * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&gorig, (size_t)n * sizeof(int))) != cudaSuccess) return e;
   cudaMemsetAsync(counts, 0, (size_t)ncell * sizeof(int), st);
   const int T = 256, B = (n + T - 1) / T;
   k_cell_count<<<B, T, 0, st>>>(fb->x, fb->y, fb->z, n, g, cell_of, counts); ++*launches;
   k_scan_single<<<1, 1024, 0, st>>>(counts, ncell, fb->cell_start); ++*launches;
   cudaMemsetAsync(counts, 0, (size_t)ncell * sizeof(int), st);
-  k_scatter<<<B, T, 0, st>>>(cell_of, n, fb->cell_start, counts, fb->gorig); ++*launches;
-  k_cell_sort<<<(ncell + T - 1) / T, T, 0, st>>>(fb->cell_start, ncell, fb->gorig); ++*launches;
-  k_fill_pos<<<B, T, 0, st>>>(fb->x, fb->y, fb->z, n, fb->gorig, fb->gpos, fb->sorted_of_orig); ++*launches;
+  k_scatter<<<B, T, 0, st>>>(cell_of, n, fb->cell_start, counts, gorig); ++*launches;
+  k_cell_sort<<<(ncell + T - 1) / T, T, 0, st>>>(fb->cell_start, ncell, gorig); ++*launches;
+  k_fill_pos<<<B, T, 0, st>>>(fb->x, fb->y, fb->z, n, gorig, fb->pos4, fb->sorted_of_orig); ++*launches;
   e = cudaStreamSynchronize(st);
-  cudaFree(cell_of); cudaFree(counts);
-  g.cell_start = fb->cell_start; g.gpos = fb->gpos; g.gorig = fb->gorig;
+  cudaFree(cell_of); cudaFree(counts); cudaFree(gorig);
+  g.cell_start = fb->cell_start; g.pos4 = fb->pos4;
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) k_nn_query(GridDev g, int nq, const doubl
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   int s = lrr_nn_search(g, qx[i], qy[i], qz[i]);
-  out[i] = (s >= 0) ? g.gorig[s] : -1;
+  out[i] = (s >= 0) ? lrr_pos4_orig(lrr_ld_pos4(g.pos4 + s)) : -1;
 }
 
 cudaError_t lrr_nn_query(const GridDev& g, int64_t nq, const double* qx, const double* qy, const double* qz, int* out,

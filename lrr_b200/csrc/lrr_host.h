@@ -1,0 +1,68 @@
+// Host-side objects behind the opaque handles of include/lrr_gpu.h.
+#pragma once
+#include <string>
+#include <vector>
+#include <cstdint>
+#include "../../include/lrr_gpu.h"
+#include "lrr_internal.h"
+#include "lrr_linalg.cuh"
+
+struct lrr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  double* partials = nullptr;
+  unsigned int* ticket = nullptr;
+  unsigned int* sel_hist = nullptr; double* sel_cand = nullptr; unsigned long long* sel_misc = nullptr;
+  SelDev sel[4];
+  SortScratch sort; double* sort_keys = nullptr;
+  double* muse_table = nullptr;
+  double* scratch_d = nullptr;
+  void* pinned = nullptr;
+};
+
+struct lrr_fset {
+  lrr_ctx* ctx = nullptr;
+  int64_t n = 0;
+  double *xyz = nullptr, *s = nullptr, *P6 = nullptr, *C6 = nullptr, *dirs = nullptr;
+  uint8_t* shape = nullptr;
+  double4* pos4 = nullptr; double* rec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
+  FsetDev dev;
+};
+
+// one direction (forward_ / backward_) of an estimator
+struct lrr_dir {
+  lrr_fset *from_all = nullptr, *to_all = nullptr;
+  size_t cap = 0;
+  double *fx = nullptr, *fy = nullptr, *fz = nullptr, *fs = nullptr, *fP6 = nullptr;
+  int *forig = nullptr, *order = nullptr, *sidx = nullptr;
+  double *w = nullptr, *r2 = nullptr, *gkey = nullptr, *skey = nullptr;
+  unsigned long long* stamp = nullptr;
+  Scal* sc = nullptr;
+  int64_t n_in = 0, number_points = 0, matches = 0;
+  unsigned int epoch = 0;
+  bool subset = false, has_order = false, scale_estimated = false, weights_fresh = false;
+  double initial_scale = 0;
+  std::vector<int32_t> host_order;   // RESHUFFLE bookkeeping
+  uint64_t shuffle_calls = 0, rng_state = 0;
+};
+
+struct lrr_est {
+  lrr_ctx* ctx = nullptr;
+  int kind = 0, dof = 12;
+  lrr_fset *moving_all = nullptr, *fixed_all = nullptr;
+  lrr_dir d[2];
+  Scal h[2];                 // host mirrors (head part is kept current)
+  bool normalize = false, strength = false;
+  int shuffle_mode = 0; uint64_t seed = 0;
+  // symmetric iteration control (cdcl sym .h / rrl sym .h:203-224)
+  unsigned oscillation_count = 0; double error_difference = 0, weighted_error = 0;
+  unsigned number_matches = 1000; int finest_level = 0; int iterations_done = 0;
+  bool werr_cache_valid = false; double werr_cache = 0;
+  bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
+  bool rrl() const { return kind == LRR_RRL_FWD || kind == LRR_RRL_SYM; }
+};
+
+// kernels with host-visible extras (lrr_icp.cu / lrr_metrics.cu)
+void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches);

@@ -1,0 +1,193 @@
+// K1/K3/K4/K5: one kernel per phase of the robust ICP iteration (sm_100a).  The phase bodies live in
+// lrr_phases.cuh; this file instantiates them over the whole GPU (GridScope), one grid row per direction of
+// a symmetric estimator, and adds the cross-direction finalisation (merged order statistics, joint solve).
+#include "lrr_phases.cuh"
+
+static inline int nblk_for(long long items) {
+  long long b = (items + LRR_THREADS - 1) / LRR_THREADS;
+  long long cap = (long long)lrr_num_sms() * 4;
+  if (cap > LRR_MAX_BLOCKS) cap = LRR_MAX_BLOCKS;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static inline int maxM(const EstArgs& a) { int m = a.d[0].M; if (a.ndir == 2 && a.d[1].M > m) m = a.d[1].M; return m; }
+
+__device__ __forceinline__ GridScope lrr_scope(const EstArgs& a, int dir) {
+  GridScope s; s.partials = a.partials + (size_t)dir * LRR_MAX_BLOCKS * LRR_NRED; s.ticket = a.ticket + dir; return s;
+}
+// true in every thread of the block that completes the pair of directions (or at once when ndir == 1)
+__device__ __forceinline__ bool lrr_pair_done(const EstArgs& a, int needed) {
+  if (needed <= 1) return true;
+  __shared__ bool s_second;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(a.ticket + 2, 1u);
+    s_second = (t == (unsigned int)needed - 1);
+    if (s_second) a.ticket[2] = 0;
+  }
+  __syncthreads();
+  if (s_second) __threadfence();
+  return s_second;
+}
+
+// ---- upload-time helpers ---------------------------------------------------------------------------------
+__global__ void k_fill_records(FsetDev f, double* __restrict__ rec) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= f.n) return;
+  const int o = lrr_pos4_orig(f.grid.pos4[j]);
+  double* r = rec + 8 * (size_t)j;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) r[p] = f.P6[(size_t)p * f.n + o];
+  const double s = f.s[o];
+  r[6] = s; r[7] = (double)(float)s;
+}
+void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long long* launches) {
+  if (f.n == 0) return;
+  k_fill_records<<<(f.n + 255) / 256, 256, 0, st>>>(f, rec); ++*launches;
+}
+
+__global__ void k_gather_from(FsetDev src, const int* __restrict__ idx, int n_in, double* __restrict__ fx, double* __restrict__ fy,
+                              double* __restrict__ fz, double* __restrict__ fs, double* __restrict__ fP6) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_in) return;
+  const int o = idx ? idx[i] : i;
+  fx[i] = src.x[o]; fy[i] = src.y[o]; fz[i] = src.z[o]; fs[i] = src.s[o];
+#pragma unroll
+  for (int p = 0; p < 6; ++p) fP6[(size_t)p * n_in + i] = src.P6[(size_t)p * src.n + o];
+}
+void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,
+                       cudaStream_t st, long long* launches) {
+  if (n_in == 0) return;
+  k_gather_from<<<(n_in + 255) / 256, 256, 0, st>>>(src, idx, n_in, fx, fy, fz, fs, fP6); ++*launches;
+}
+
+// ---- phase kernels -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LRR_THREADS) k_match(const __grid_constant__ EstArgs a) {
+  __shared__ PhaseShared sh;
+  const int dir = blockIdx.y;
+  lrr_phase_match(lrr_scope(a, dir), a.d[dir], a.flags, sh);
+}
+void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
+  dim3 grid(nblk_for(maxM(a)), a.ndir);
+  k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+}
+
+__global__ void __launch_bounds__(LRR_THREADS) k_norm1(const __grid_constant__ EstArgs a) {
+  __shared__ PhaseShared sh;
+  lrr_phase_norm1(lrr_scope(a, a.src), a.d[a.src], sh);
+}
+void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches) {
+  k_norm1<<<nblk_for(a.d[a.src].M), LRR_THREADS, 0, st>>>(a); ++*launches;
+}
+__global__ void __launch_bounds__(LRR_THREADS) k_norm2(const __grid_constant__ EstArgs a) {
+  __shared__ PhaseShared sh;
+  lrr_phase_norm2(lrr_scope(a, a.src), a.d[a.src], a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, sh);
+}
+void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches) {
+  k_norm2<<<nblk_for(a.d[a.src].M), LRR_THREADS, 0, st>>>(a); ++*launches;
+}
+
+struct WeightExtra { int scale_mode[2]; double scale_in[2]; };
+
+__global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex) {
+  __shared__ PhaseShared sh;
+  const int dir = blockIdx.y;
+  const bool merged = (a.flags & LRR_F_MERGED) != 0;
+  const int group = merged ? 0 : dir;
+  const int reversed = merged && dir != a.src;
+  const bool fin = lrr_phase_weight(lrr_scope(a, dir), a.d[dir], a.flags, reversed, a.selG[group], a.selS[group], ex.scale_mode[dir],
+                                    ex.scale_in[dir], sh);
+  if (!fin) return;
+  // group-level: locate the fine bins of the two order statistics
+  if (merged && a.ndir == 2) {
+    if (!lrr_pair_done(a, 2)) return;
+    const double nG = __ldcg(&a.d[0].sc->n_nonzero) + __ldcg(&a.d[1].sc->n_nonzero);
+    if (a.flags & LRR_F_STRENGTH) lrr_sel_locate(a.selG[0], nG, sh.tmp);
+    if (a.flags & LRR_F_SYM) lrr_sel_locate(a.selS[0], (double)(a.d[0].M + a.d[1].M), sh.tmp);
+  } else {
+    if (a.flags & LRR_F_STRENGTH) lrr_sel_locate(a.selG[group], __ldcg(&a.d[dir].sc->n_nonzero), sh.tmp);
+    if (a.flags & LRR_F_SYM) lrr_sel_locate(a.selS[group], (double)a.d[dir].M, sh.tmp);
+  }
+}
+static WeightExtra g_dummy_extra;
+void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches) {
+  WeightExtra ex;
+  for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
+  dim3 grid(nblk_for(maxM(a)), a.ndir);
+  k_weight<<<grid, LRR_THREADS, 0, st>>>(a, ex); ++*launches;
+}
+void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches) {
+  (void)g_dummy_extra;
+  const int m[2] = {0, 0}; const double s[2] = {0, 0};
+  lrr_k_weight_ex(a, m, s, st, launches);
+}
+
+__global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__ EstArgs a) {
+  __shared__ double sh_cand[LRR_SEL_CAP];
+  const int dir = blockIdx.y;
+  const bool merged = (a.flags & LRR_F_MERGED) != 0;
+  const int group = merged ? 0 : dir;
+  const GridScope scope = lrr_scope(a, dir);
+  // the histograms are not read after the weight phase located the bins: re-zero them for the next use
+  {
+    const int nthreads = gridDim.x * gridDim.y * blockDim.x, t0 = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int g = 0; g < 2; ++g) {
+      for (int i = t0; i < LRR_SEL_FINE; i += nthreads) { a.selG[g].fine[i] = 0; a.selS[g].fine[i] = 0; }
+      for (int i = t0; i < LRR_SEL_COARSE; i += nthreads) { a.selG[g].coarse[i] = 0; a.selS[g].coarse[i] = 0; }
+    }
+  }
+  lrr_phase_collect(scope, a.d[dir], a.flags, a.selG[group], a.selS[group]);
+  if (!scope.last_block()) return;
+  if (merged && a.ndir == 2 && !lrr_pair_done(a, 2)) return;
+  bool ok = true;
+  if (a.flags & LRR_F_STRENGTH) ok = lrr_sel_finish(a.selG[group], sh_cand) && ok;
+  if (a.flags & LRR_F_SYM) ok = lrr_sel_finish(a.selS[group], sh_cand) && ok;
+  if (threadIdx.x == 0) {
+    const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = (a.flags & LRR_F_SYM) ? *a.selS[group].result : 1.0;
+    for (int d = 0; d < a.ndir; ++d) if (merged || d == dir) {
+      a.d[d].sc->G = G; a.d[d].sc->S = S;
+      if (!ok) a.d[d].sc->status |= LRR_ST_SELECT_OVERFLOW;
+    }
+  }
+}
+void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches) {
+  dim3 grid(nblk_for(maxM(a)), a.ndir);
+  k_collect<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+}
+
+__global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constant__ EstArgs a) {
+  __shared__ PhaseShared sh;
+  const int dir = blockIdx.y;
+  const bool merged = (a.flags & LRR_F_MERGED) != 0, sym = (a.flags & LRR_F_SYM) != 0;
+  const int reversed = sym && dir != a.src;
+  const int keep_w = merged && dir != a.src;
+  const Scal* scd = a.d[dir].sc;
+  const double G = (a.flags & LRR_F_STRENGTH) ? scd->G : 1.0, S = sym ? scd->S : 1.0;
+  double jc[3] = {0, 0, 0};
+  if (!(a.flags & LRR_F_NORMALIZE) && !(a.flags & LRR_F_RIGID)) { const Scal* f = a.d[a.src].sc; jc[0] = f->c[0]; jc[1] = f->c[1]; jc[2] = f->c[2]; }
+  const bool fin = lrr_phase_accumulate(lrr_scope(a, dir), a.d[dir], a.flags, reversed, keep_w, G, S, jc, sh);
+  if (!fin) return;
+  if (!lrr_pair_done(a, a.ndir)) return;
+  lrr_solve(a.d[a.src].sc, a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, a.flags, a.dof, a.estimate_parameters);
+}
+void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
+  dim3 grid(nblk_for(4LL * maxM(a)), a.ndir);
+  k_accumulate<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+}
+
+__global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0) {
+  __shared__ PhaseShared sh;
+  const int dir = dir0 + blockIdx.y;
+  lrr_phase_resid(lrr_scope(a, dir), a.d[dir], sh);
+}
+void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches) {
+  if (dir_mask == 3) {
+    dim3 grid(nblk_for(maxM(a)), 2);
+    k_resid<<<grid, LRR_THREADS, 0, st>>>(a, 0); ++*launches;
+  } else {
+    const int d = (dir_mask == 2) ? 1 : 0;
+    k_resid<<<nblk_for(a.d[d].M), LRR_THREADS, 0, st>>>(a, d); ++*launches;
+  }
+}

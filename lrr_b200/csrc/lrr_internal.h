@@ -1,26 +1,60 @@
 // Internal declarations shared by the CUDA translation units of liblrr_b200.so (sm_100a only).
+//
 // Data layout in HBM:
-//   * "from" side of a direction (the streamed side): compact structure-of-arrays in subset order,
-//     fp64 x,y,z,strength (+ P6, C6, dirs, u8 shape) — coalesced loads.
-//   * "to" side (the gathered side): the feature set sorted by uniform-grid cell, one 96-byte record
-//     per feature (x,y,z,Pxx,Pxy,Pxz,Pyy,Pyz,Pzz,strength,orig-index bits,pad): one match gathers 3
-//     32-byte sectors instead of 10 scattered SoA sectors.  A compact interleaved xyz copy (24 B/feature)
-//     in the same order feeds the exact 1-NN search; x-adjacent cells are contiguous in that order.
+//   * every uploaded feature set keeps (a) its caller-order structure-of-arrays (fp64 x,y,z,strength,P6,C6,
+//     dirs + u8 shape) and (b) a copy sorted by uniform-grid cell: `pos4` = one 32-byte record per feature
+//     {x,y,z,original index} — the only array the exact 1-NN search touches, one sector per candidate —
+//     and `rec` = one 64-byte record {Pxx,Pxy,Pxz,Pyy,Pyz,Pzz,strength,strength as fp32} gathered once per
+//     match.  x-adjacent cells are contiguous in the sorted order.
+//   * the "from" side of a direction (the streamed side) is a compact SoA in subset order
+//     (x,y,z,strength,P6): coalesced fp64 loads, gathered once per set_features.
+//   * per-match arrays (sorted slot of the neighbour, weight, residual^2, selection keys) are plain SoA.
+//   * all scalars of a direction (transform, normalisation, reduction results) live in one `Scal` struct
+//     in device memory; the host reads it back once per one_iteration call.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define LRR_REC_STRIDE 12   // doubles per gather record (96 B)
-#define LRR_REC2_STRIDE 16  // doubles per auxiliary record: C6(6) dirs(9) shape(1)
-#define LRR_MAX_BLOCKS 1184 // 148 SMs x 8
-#define LRR_NRED 96         // max doubles reduced per block in one pass
+#define LRR_MAX_BLOCKS 1184   // 148 SMs x 8
+#define LRR_NRED 112          // max doubles reduced per block in one pass (108 moments)
+#define LRR_SEL_FINE 65536    // fine bins of the order-statistic histogram
+#define LRR_SEL_COARSE 1024   // coarse bins (fine >> 6)
+#define LRR_SEL_CAP 2048      // candidate capacity of the final exact selection
+#define LRR_STRENGTH_CAP 90000.0
 
 struct GridDev {
   double ox, oy, oz, h, inv_h;
   int nx, ny, nz, n;
-  const int* cell_start;   // ncell+1
-  const double* gpos;      // 3*n interleaved, cell order
-  const int* gorig;        // n: original index of sorted slot
+  const int* cell_start;    // ncell+1
+  const double4* pos4;      // n, cell order: x,y,z,(original index as int64 bits)
+};
+
+// device view of one uploaded feature set
+struct FsetDev {
+  int n;
+  const double *x, *y, *z, *s;   // caller order
+  const double* P6;              // 6 x n
+  const double* C6;              // 6 x n or null
+  const double* dirs;            // 9 x n or null
+  const uint8_t* shape;          // n
+  GridDev grid;
+  const double* rec;             // 8 x n interleaved, cell order
+  const int* sorted_of_orig;     // n
+};
+
+// one exact order-statistic selector (MAD scale of Q12) = histogram + candidate list
+struct SelDev {
+  unsigned int* fine;      // LRR_SEL_FINE
+  unsigned int* coarse;    // LRR_SEL_COARSE
+  double* cand;            // LRR_SEL_CAP
+  unsigned int* cand_count;
+  unsigned long long* cand_minmax;   // [0]=min bits, [1]=max bits of the candidates
+  // written by the finalizer of the weight phase
+  int* bin;                // fine bin holding the k-th value
+  unsigned int* rank;      // rank of the k-th value inside that bin
+  double* count;           // number of keys
+  double* result;          // the MAD scale (0 when count <= 1)
+  double inv_width;        // key -> fine bin = min(FINE-1, (int)(key * inv_width))
 };
 
 // Device-resident scalars of one direction (forward_ or backward_ of an estimator).
@@ -28,71 +62,78 @@ struct Scal {
   // current transform of this direction, unnormalised: y = A (x - c) + t
   double A[9], t[3], c[3];
   double cov[144];
-  int trans_kind, dof;
-  // previous global transform (rigid increment bookkeeping: the clones of cdcl :455-484)
+  // previous global transform while the matches' from_ are mapped clones (rigid increment, cdcl :455-484)
   double Ag[9], tg[3], cg[3];
-  int from_mapped;         // 1 while matches' from_ are clones mapped through (Ag,tg,cg)
-  // normalisation (A9) and the normalised transform
-  double cm[3], rm, cf[3], rf;
-  double An[9], tn[3], cn[3];
-  // reductions
-  double sum_x[3], sum_q[3], n_unique, sum_rad_m, sum_rad_f;
-  double sum_r2, sum_wr2, sum_w, n_nonzero;
-  double err_num, err_den;     // weighted_error
-  double rms_sum;
-  double scale; int scale_estimated; int pad0;
-  double G, S;                 // strength / spatial MAD scales
+  int from_mapped, status;
+  // normalisation (A9) of this direction's from / to features
+  double cfrom[3], rfrom, cto[3], rto;
+  // reduction results
+  double sum_loc[3], sum_r2;                 // match phase
+  double sum_q[3], n_unique, sum_rad_from;   // norm1
+  double sum_rad_to;                         // norm2
+  double scale; int scale_estimated, pad1;
+  double n_nonzero;
+  double G, S;
+  double res_sum_r2, res_sum_wr2, res_sum_w, res_sum_wr, res_count;   // resid phase
+  double mom[LRR_NRED];
   double AtA[144], Atb[12];
-  int solve_status; int pad1;
   double ang_num, ang_den;
-  double covJ[9];
-  double obj_f; double obj_kl[144];
-};
-
-struct DirArgs {
-  // from side
-  const double *fx, *fy, *fz, *fs;
-  const double *fP6, *fC6, *fdirs;   // SoA with leading dimension n_in
-  const uint8_t* fshape;
-  const int* forig;
-  int n_in;
-  const int* order;
-  int M;
-  // to side
-  const double* rec;
-  const double* rec2;
-  GridDev grid;
-  int n_to;
-  // per-match arrays (length n_in)
-  int* sidx;
-  double *w, *r2, *g, *sw;
-  unsigned char* rep;
-  int* stamp;
-  int stamp_id;
-  // scalars + reduction scratch
-  Scal* sc;
-  double* partials;       // LRR_MAX_BLOCKS * LRR_NRED
-  unsigned int* ticket;
+  double covJ[10];   // scratch: second moments of the Jacobian locations
+  double obj_f, obj_kl[144];
 };
 
 enum {
-  LRR_F_RRL = 1,          // rrl flavour: fp32 strength product, w<1e-4 skip in accumulation
-  LRR_F_RIGID = 2,        // rigid3d increment: from = mapped clone, J = [-[x]x | I], b = q - p
-  LRR_F_NORMALIZED = 4,   // evaluate in normalised coordinates
-  LRR_F_REVERSED = 8,     // accumulate with roles reversed (J at to, P and b of from)
-  LRR_F_STRENGTH = 16,
-  LRR_F_SPATIAL = 32,
-  LRR_F_SKIP_SMALL = 64,
-  LRR_F_USE_OLD_W = 128   // scale from current weights (scale_estimated_)
+  LRR_ST_OK = 0,
+  LRR_ST_SELECT_OVERFLOW = 1,   // candidate list overflow in the exact selection (host falls back to sort)
+  LRR_ST_SINGULAR = 2
 };
 
-struct LaunchCounter { long long n; };
+struct DirArgs {
+  // from side (compact, subset order)
+  const double *fx, *fy, *fz, *fs;
+  const double* fP6;     // 6 x n_in
+  const int* forig;      // n_in: index in the parent *_all set
+  int n_in;
+  const int* order;      // n_in or null (identity): position k -> compact index
+  int M;                 // number_points_: matches in use
+  // to side
+  FsetDev to;
+  FsetDev from_all;      // parent set of the from side (rarely used attributes are gathered through forig)
+  // per-match arrays (length n_in)
+  int* sidx;
+  double *w, *r2, *gkey, *skey;
+  unsigned long long* stamp;   // n_to: (epoch, match position) of the representative match of a to-feature
+  unsigned long long tag;      // epoch tag of the current matches (high bits)
+  Scal* sc;
+};
 
-// grid build / NN  (lrr_grid.cu)
+enum {
+  LRR_F_RRL = 1,          // rrl flavour: fp32 strength product, rrl RMS (Q1), w<1e-4 skip in accumulation
+  LRR_F_RIGID = 2,        // rigid3d increment: from = mapped clone, J = [-[x]x | I], b = q - p
+  LRR_F_NORMALIZE = 4,    // normalize_matches_
+  LRR_F_SYM = 8,          // symmetric estimator (scale before normalisation, spatial weighting)
+  LRR_F_STRENGTH = 16,    // weight_by_strength_
+  LRR_F_MERGED = 32,      // cdcl symmetric: backward matches join the forward list reversed (one G, one S)
+  LRR_F_USE_OLD_W = 64    // scale from the current weights (estimate_LS_backward after estimate_LS)
+};
+
+struct EstArgs {
+  DirArgs d[2];
+  int ndir;
+  int flags;
+  int dof;
+  int src;             // direction that defines the normalisation (0; 1 for rrl estimate_LS_backward)
+  int estimate_parameters;
+  SelDev selG[2], selS[2];
+  double* partials;    // LRR_MAX_BLOCKS * LRR_NRED per direction slot (2 slots)
+  unsigned int* ticket;   // per direction slot
+};
+
+// ---- grid build / NN  (lrr_grid.cu) ----------------------------------------------------------------
 struct FsetBuild {
   int64_t n;
   const double *x, *y, *z;          // device SoA, caller order
-  int* cell_start; double* gpos; int* gorig; int* sorted_of_orig;
+  int* cell_start; double4* pos4; int* sorted_of_orig;
   GridDev grid;
 };
 cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches);
@@ -100,33 +141,32 @@ cudaError_t lrr_nn_query(const GridDev& g, int64_t nq, const double* qx, const d
                          int* out_orig, cudaStream_t st, long long* launches);
 int lrr_num_sms();
 
-// ICP kernels (lrr_icp.cu)
-void lrr_k_gather_from(const double* sx, const double* sy, const double* sz, const double* ss, const double* sP6, const double* sC6,
-                       const double* sdirs, const uint8_t* sshape, int64_t n_src, const int* idx, int n_in,
-                       double* fx, double* fy, double* fz, double* fs, double* fP6, double* fC6, double* fdirs, uint8_t* fshape,
+// ---- ICP kernels (lrr_icp.cu) ----------------------------------------------------------------------
+void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long long* launches);
+void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,
                        cudaStream_t st, long long* launches);
-void lrr_k_fill_records(const double* sx, const double* sy, const double* sz, const double* ss, const double* sP6, const double* sC6,
-                        const double* sdirs, const uint8_t* sshape, int64_t n, const int* gorig, double* rec, double* rec2,
-                        cudaStream_t st, long long* launches);
-void lrr_k_iota(int* a, int n, cudaStream_t st, long long* launches);
-void lrr_k_match(const DirArgs& a, cudaStream_t st, long long* launches);
-void lrr_k_radii(const DirArgs& a, int known /*0: compute, 1: known (cm,rm,cf,rf) already in sc*/, cudaStream_t st, long long* launches);
-void lrr_k_resid(const DirArgs& a, int flags, cudaStream_t st, long long* launches);
-void lrr_k_weight(const DirArgs& a, int flags, double* gsel_out, cudaStream_t st, long long* launches);
-void lrr_k_normal(const DirArgs& a, int flags, const Scal* trans_owner, int accumulate_into_existing, const double* GS /*device: G,S*/, cudaStream_t st, long long* launches);
-void lrr_k_error(const DirArgs& a, int which, int flags, cudaStream_t st, long long* launches);
-void lrr_k_transfer_cov(const DirArgs& a, cudaStream_t st, long long* launches);
-// scalar epilogues (single-block kernels)
-void lrr_k_prepare_norm(Scal* f, Scal* b_or_null, int normalize, int flags, cudaStream_t st, long long* launches);
-void lrr_k_solve(Scal* f, Scal* b_or_null, int estimate_parameters, int normalize, int flags, cudaStream_t st, long long* launches);
-void lrr_k_scale_from_sums(Scal* s, cudaStream_t st, long long* launches);
+void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches);
+void lrr_k_angles(const DirArgs& a, int flags, int which, double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
+void lrr_k_transfer_cov(const DirArgs& a, int dof, double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
+void lrr_k_resid_keys(const DirArgs& a, double* keys, cudaStream_t st, long long* launches);
+void lrr_k_export_matches(const DirArgs& a, int* from_idx, int* to_idx, cudaStream_t st, long long* launches);
+void lrr_k_objcov(const DirArgs& a, int dof, const double* U /*dof x dof upper, device*/, int want_g, double* partials,
+                  unsigned int* ticket, cudaStream_t st, long long* launches);
 
-// selection / sort (lrr_select.cu)
-struct SelectScratch { unsigned int* hist; unsigned long long* state; double* keys; double* keys2; size_t cap; };
-cudaError_t lrr_select_alloc(SelectScratch* s, size_t cap);
-void lrr_select_free(SelectScratch* s);
-// MAD scale (Q12) over keys[0..n) where n is read from device (*n_dev as double); result -> *out_dev
-void lrr_mad_scale(SelectScratch* s, const double* keys, const double* n_dev, int n_max, double* out_dev, cudaStream_t st, long long* launches);
-// sort ascending (for MUSE) n host-known
-void lrr_sort_doubles(SelectScratch* s, double* keys, int n, cudaStream_t st, long long* launches);
-void lrr_muse_from_sorted(const double* sorted, int n, const double* table /*device: 3 doubles per fraction + k*/, int nfrac, double* out_scale, cudaStream_t st, long long* launches);
+// ---- sort / MUSE (lrr_select.cu) -------------------------------------------------------------------
+struct SortScratch { double* keys2; unsigned int* hist; size_t cap; };
+cudaError_t lrr_sort_alloc(SortScratch* s, size_t cap);
+void lrr_sort_free(SortScratch* s);
+// ascending sort of n non-negative doubles in place (single-block LSD radix sort; once per registration)
+void lrr_sort_doubles(SortScratch* s, double* keys, int n, cudaStream_t st, long long* launches);
+// MUSE objective over sorted |r| (table: per fraction {k, expected_kth, stddev_kth, divisor}); writes *out_scale
+void lrr_muse_from_sorted(const double* sorted, int n, const double* table, int nfrac, double* out_scale, cudaStream_t st,
+                          long long* launches);
+// k-th smallest of sorted keys -> MAD scale (fallback of the histogram selector)
+void lrr_mad_from_sorted(const double* sorted, int n, double* out, cudaStream_t st, long long* launches);

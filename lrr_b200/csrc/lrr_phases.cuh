@@ -1,0 +1,591 @@
+// Phase bodies of one robust-ICP iteration, written once against a reduction Scope (lrr_dev.cuh) so that
+// the same code runs (a) as one kernel per phase over the whole GPU for a single large registration and
+// (b) inside one thread block per registration in batched mode.
+//
+// One iteration = MATCH -> NORM1 -> NORM2 -> WEIGHT -> COLLECT -> ACCUMULATE(+SOLVE) -> RESID; each phase
+// ends in a global reduction whose finalizer writes the derived scalars into the direction's Scal.
+// Reference maths: SURVEY.md §3.6; citations at each phase.
+#pragma once
+#include "lrr_dev.cuh"
+#include "lrr_linalg.cuh"
+
+#define LRR_THREADS 256
+#define LRR_NWARPS (LRR_THREADS / 32)
+
+struct PhaseShared {
+  double out[LRR_NRED];
+  double tmp[LRR_NRED * LRR_NWARPS];
+};
+
+__device__ __forceinline__ int lrr_from_index(const DirArgs& a, int k) { return a.order ? __ldg(a.order + k) : k; }
+
+// location of the match's from_ feature: the original, or — while a rigid increment is being estimated —
+// the clone mapped through the previous global transform (cdcl :455-484)
+__device__ __forceinline__ void lrr_from_loc(const DirArgs& a, const Scal* __restrict__ sc, int mapped, int i, double& x, double& y,
+                                             double& z) {
+  x = __ldg(a.fx + i); y = __ldg(a.fy + i); z = __ldg(a.fz + i);
+  if (mapped) { double ox, oy, oz; lrr_map_exact(sc->Ag, sc->tg, sc->cg, x, y, z, ox, oy, oz); x = ox; y = oy; z = oz; }
+}
+
+__device__ __forceinline__ void lrr_ld_P6(const double* __restrict__ rec, int s, double (&P)[6]) {
+  const double2* q = reinterpret_cast<const double2*>(rec + 8 * (size_t)s);
+  double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  P[0] = a.x; P[1] = a.y; P[2] = b.x; P[3] = b.y; P[4] = c.x; P[5] = c.y;
+}
+
+// ---- MATCH: find_closest_euclidean (cdcl :541-654, rrl :494-571) fused with the residuals of
+// RMS_error (cdcl :196-230) and the first normalisation sum (cdcl :1159-1190) ---------------------------
+template <class Scope>
+__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  double A[9], t[3], c[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = sc->A[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { t[i] = sc->t[i]; c[i] = sc->c[i]; }
+  const bool rigid = (flags & LRR_F_RIGID) != 0;
+  double acc[4] = {0, 0, 0, 0};
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int i = lrr_from_index(a, k);
+    const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
+    double yx, yy, yz;
+    lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
+    const int s = lrr_nn_search(a.to.grid, yx, yy, yz);
+    a.sidx[k] = s;
+    double r2 = 0.0;
+    if (s >= 0) {
+      const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
+      double P[6]; lrr_ld_P6(a.to.rec, s, P);
+      r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
+      atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
+    }
+    a.r2[k] = r2;
+    a.w[k] = 1.0;   // cdcl :645
+    if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
+    acc[3] += r2;
+  }
+  if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) {
+      sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
+      sc->res_sum_r2 = sh.out[3]; sc->res_count = (double)a.M;
+      if (rigid) {   // make_incremental: the matches' from_ are now clones mapped through the current transform
+        for (int i = 0; i < 9; ++i) sc->Ag[i] = sc->A[i];
+        for (int i = 0; i < 3; ++i) { sc->tg[i] = sc->t[i]; sc->cg[i] = sc->c[i]; }
+        sc->from_mapped = 1;
+      } else sc->from_mapped = 0;
+    }
+  }
+  scope.phase_end();
+}
+
+// ---- NORM1 / NORM2: cdcl_normalize_matches (cdcl :1159-1240, rrl :864-943).  The std::set of matched
+// fixed features becomes "the match with the lowest position wins the stamp of its to-feature". ----------
+template <class Scope>
+__device__ void lrr_phase_norm1(const Scope& scope, const DirArgs& a, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  const int mapped = sc->from_mapped;
+  const double invM = 1.0;
+  (void)invM;
+  const double cm0 = sc->sum_loc[0] / (double)a.M, cm1 = sc->sum_loc[1] / (double)a.M, cm2 = sc->sum_loc[2] / (double)a.M;
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int i = lrr_from_index(a, k);
+    double x, y, z; lrr_from_loc(a, sc, mapped, i, x, y, z);
+    const double dx = x - cm0, dy = y - cm1, dz = z - cm2;
+    acc[4] += sqrt(dx * dx + dy * dy + dz * dz);
+    const int s = a.sidx[k];
+    if (s >= 0 && a.stamp[s] == (a.tag | (unsigned long long)(unsigned int)k)) {
+      const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
+      acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += 1.0;
+    }
+  }
+  if (scope.template reduce<5>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) {
+      sc->sum_q[0] = sh.out[0]; sc->sum_q[1] = sh.out[1]; sc->sum_q[2] = sh.out[2]; sc->n_unique = sh.out[3];
+      sc->sum_rad_from = sh.out[4];
+      sc->cfrom[0] = cm0; sc->cfrom[1] = cm1; sc->cfrom[2] = cm2;
+      sc->rfrom = sh.out[4] / (double)a.M;
+      for (int d = 0; d < 3; ++d) sc->cto[d] = sh.out[d] / sh.out[3];
+    }
+  }
+  scope.phase_end();
+}
+
+template <class Scope>
+__device__ void lrr_phase_norm2(const Scope& scope, const DirArgs& a, Scal* other /* null or the opposite direction */, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  const double c0 = sc->cto[0], c1 = sc->cto[1], c2 = sc->cto[2];
+  double acc[1] = {0};
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int s = a.sidx[k];
+    if (s >= 0 && a.stamp[s] == (a.tag | (unsigned long long)(unsigned int)k)) {
+      const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
+      const double dx = q.x - c0, dy = q.y - c1, dz = q.z - c2;
+      acc[0] += sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  }
+  if (scope.template reduce<1>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) {
+      sc->sum_rad_to = sh.out[0];
+      sc->rto = sh.out[0] / sc->n_unique;
+      if (other) {   // cdcl_normalize_matches_known with the centres and radii swapped (cdcl sym :470-478)
+        for (int d = 0; d < 3; ++d) { other->cfrom[d] = sc->cto[d]; other->cto[d] = sc->cfrom[d]; }
+        other->rfrom = sc->rto; other->rto = sc->rfrom;
+      }
+    }
+  }
+  scope.phase_end();
+}
+
+// ---- exact order statistic: histogram side --------------------------------------------------------------
+__device__ __forceinline__ int lrr_sel_bin(const SelDev& s, double key) {
+  int b = (int)(key * s.inv_width);
+  return b < 0 ? 0 : (b >= LRR_SEL_FINE ? LRR_SEL_FINE - 1 : b);
+}
+__device__ __forceinline__ void lrr_sel_add(const SelDev& s, double key) {
+  const int b = lrr_sel_bin(s, key);
+  atomicAdd(s.fine + b, 1u);
+  atomicAdd(s.coarse + (b >> 6), 1u);
+}
+// Called by ONE block (all LRR_THREADS threads) once every key of the group is in the histogram: locate
+// the fine bin of the (n-1)/2+1 -th smallest key (0-based) — the element the reference's private
+// rrel_util_median_abs_dev_scale picks with nth_element (cdcl :520-536, Q12).
+static __device__ void lrr_sel_locate(const SelDev& s, double n_keys, double* shd /* >= 2*LRR_THREADS doubles */) {
+  unsigned int* shu = reinterpret_cast<unsigned int*>(shd);
+  __shared__ unsigned int s_target, s_cbin, s_cbase;
+  const long long n = (long long)n_keys;
+  if (threadIdx.x == 0) { *s.count = n_keys; *s.cand_count = 0; s.cand_minmax[0] = ~0ull; s.cand_minmax[1] = 0ull; }
+  if (n <= 1) { if (threadIdx.x == 0) { *s.bin = -1; *s.rank = 0; *s.result = 0.0; } __syncthreads(); return; }
+  const unsigned int target = (unsigned int)((n - 1) / 2 + 1);
+  // coarse level: 4 bins per thread, inclusive scan over threads
+  unsigned int c4[4], loc = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { c4[j] = __ldcg(s.coarse + 4 * threadIdx.x + j); loc += c4[j]; }
+  shu[threadIdx.x] = loc;
+  __syncthreads();
+  for (int o = 1; o < LRR_THREADS; o <<= 1) {
+    unsigned int v = (threadIdx.x >= o) ? shu[threadIdx.x - o] : 0;
+    __syncthreads();
+    shu[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const unsigned int incl = shu[threadIdx.x], excl = incl - loc;
+  if (target >= excl && target < incl) {
+    unsigned int base = excl; int cb = 4 * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { if (target >= base + c4[j]) { base += c4[j]; ++cb; } else break; }
+    s_cbin = cb; s_cbase = base; s_target = target;
+  }
+  __syncthreads();
+  // fine level inside the coarse bin: 64 bins, one per thread of the first two warps
+  unsigned int f = 0;
+  if (threadIdx.x < 64) f = __ldcg(s.fine + s_cbin * 64 + threadIdx.x);
+  shu[threadIdx.x] = f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int base = s_cbase; int fb = 0;
+    for (; fb < 64; ++fb) { if (s_target >= base + shu[fb]) base += shu[fb]; else break; }
+    *s.bin = s_cbin * 64 + fb;
+    *s.rank = s_target - base;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void lrr_sel_offer(const SelDev& s, int bin, double key) {
+  if (lrr_sel_bin(s, key) != bin) return;
+  const unsigned int idx = atomicAdd(s.cand_count, 1u);
+  if (idx < LRR_SEL_CAP) s.cand[idx] = key;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(key);
+  atomicMin(s.cand_minmax, bits); atomicMax(s.cand_minmax + 1, bits);
+}
+// Called by ONE block after every candidate is in the list: exact rank selection, then the MAD scale.
+// Returns (in every thread) false on candidate overflow with distinct values (host falls back to a sort).
+static __device__ bool lrr_sel_finish(const SelDev& s, double* sh_cand /* >= LRR_SEL_CAP doubles */) {
+  __shared__ double s_val; __shared__ int s_ok;
+  const double n_keys = *s.count;
+  if (n_keys <= 1.0) { if (threadIdx.x == 0) *s.result = 0.0; __syncthreads(); return true; }
+  const unsigned int cnt = __ldcg(s.cand_count), rank = *s.rank;
+  if (threadIdx.x == 0) { s_ok = 1; s_val = 0.0; }
+  __syncthreads();
+  if (cnt > LRR_SEL_CAP) {
+    if (threadIdx.x == 0) {
+      const unsigned long long mn = __ldcg(s.cand_minmax), mx = __ldcg(s.cand_minmax + 1);
+      if (mn == mx) s_val = __longlong_as_double((long long)mn); else s_ok = 0;
+    }
+  } else {
+    for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) sh_cand[i] = __ldcg(s.cand + i);
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const double v = sh_cand[i]; unsigned int r = 0;
+      for (unsigned int j = 0; j < cnt; ++j) { const double u = sh_cand[j]; r += (u < v) || (u == v && j < i); }
+      if (r == rank) s_val = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_ok) *s.result = 1.4826 * (1.0 + 5.0 / (n_keys - 1.0)) * s_val;
+  const bool ok = s_ok != 0;
+  __syncthreads();
+  return ok;
+}
+
+// squared scale of the direction in the units the weights are computed in
+__device__ __forceinline__ double lrr_scale_of(const Scal* sc, int M, int flags, double unit, int scale_mode, double scale_in) {
+  if (scale_mode == 2) return scale_in;                 // injected initial scale, estimator units
+  if (scale_mode == 1) return sc->scale / unit;         // MUSE over the unnormalised residuals (written by k_muse)
+  if (flags & LRR_F_USE_OLD_W) return sqrt(sc->res_sum_wr2 / sc->res_sum_w) / unit;   // cdcl :698-701,:731
+  return sqrt(sc->sum_r2 / (double)M) / unit;           // all weights were reset to 1 (Q2)
+}
+
+// ---- WEIGHT: estimate_scale_and_assign_weight (cdcl :660-822, rrl :577-718), the first half of
+// weight_by_strength (cdcl :826-862, rrl :722-752) and of weight_spatially (cdcl :973-1004, rrl :756-778) --
+// dir = 0/1; reversed = this list joins the merged list with from/to swapped (cdcl sym add_constraints)
+template <class Scope>
+__device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags, int reversed, const SelDev& selG, const SelDev& selS,
+                                 int scale_mode, double scale_in, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  const bool sym = (flags & LRR_F_SYM) != 0;
+  const double unit = sym ? 1.0 : sc->rto;   // forward estimators weight in normalised coordinates (Q3)
+  const double scale = lrr_scale_of(sc, a.M, flags, unit, scale_mode, scale_in);
+  const double scale2 = scale * scale, unit2 = unit * unit;
+  const int mapped = sc->from_mapped;
+  // spatial weight uses the normalised location of the match's to_ feature
+  double sc0, sc1, sc2, sr;
+  if (!reversed) { sc0 = sc->cto[0]; sc1 = sc->cto[1]; sc2 = sc->cto[2]; sr = sc->rto; }
+  else { sc0 = sc->cfrom[0]; sc1 = sc->cfrom[1]; sc2 = sc->cfrom[2]; sr = sc->rfrom; }
+  double acc[1] = {0};
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int s = a.sidx[k];
+    const double r2n = a.r2[k] / unit2;
+    double w = lrr_weight_BT(r2n / scale2) / scale2;
+    double gk = -1.0, sk = -1.0;
+    const int i = lrr_from_index(a, k);
+    if ((flags & LRR_F_STRENGTH) && w != 0.0 && s >= 0) {   // Q13
+      const double sq = __ldg(a.to.rec + 8 * (size_t)s + 6);
+      const double sp = __ldg(a.fs + i);
+      double g;
+      if (flags & LRR_F_RRL) g = (double)__fmul_rn((float)sp, (float)sq);   // cdcl_feature_ICP::strength_ is float
+      else g = sp * sq;
+      if (g > LRR_STRENGTH_CAP) g = LRR_STRENGTH_CAP;
+      gk = g;
+      lrr_sel_add(selG, fabs(g));
+      acc[0] += 1.0;
+    }
+    if (sym && s >= 0) {
+      double qx, qy, qz;
+      if (!reversed) { const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s); qx = q.x; qy = q.y; qz = q.z; }
+      else lrr_from_loc(a, sc, mapped, i, qx, qy, qz);
+      qx = (qx - sc0) / sr; qy = (qy - sc1) / sr; qz = (qz - sc2) / sr;
+      const double dist = sqrt(qx * qx + qy * qy + qz * qz);
+      sk = 1.0 / (1.0 + 5.0 * dist * dist);
+      lrr_sel_add(selS, sk);
+    }
+    a.w[k] = w; a.gkey[k] = gk; a.skey[k] = sk;
+  }
+  const bool fin = scope.template reduce<1>(acc, sh.out, sh.tmp);
+  if (fin && threadIdx.x == 0) { sc->n_nonzero = sh.out[0]; sc->scale = scale; sc->scale_estimated = 1; }
+  return fin;
+}
+
+// ---- COLLECT: candidates of the two order statistics ----------------------------------------------------
+template <class Scope>
+__device__ void lrr_phase_collect(const Scope& scope, const DirArgs& a, int flags, const SelDev& selG, const SelDev& selS) {
+  const int binG = (flags & LRR_F_STRENGTH) ? *selG.bin : -1;
+  const int binS = (flags & LRR_F_SYM) ? *selS.bin : -1;
+  if (binG < 0 && binS < 0) return;
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    if (binG >= 0) { const double g = a.gkey[k]; if (g >= 0.0) lrr_sel_offer(selG, binG, fabs(g)); }
+    if (binS >= 0) { const double s = a.skey[k]; if (s >= 0.0) lrr_sel_offer(selS, binS, s); }
+  }
+}
+
+// ---- ACCUMULATE: second half of the re-weighting + the weighted normal equations
+// (cdcl :1029-1069, cdcl sym :551-628, rrl :803-835, rrl sym ThreadedGenerateDataForward/Backward :441-655).
+// Four lanes share one match; lane j owns row x~_j of the Kronecker moments
+//   T[j][b][p] = sum w x~_j x~_b P_p   (b = 0..3, p = xx,xy,xz,yy,yz,zz)      V[j][d] = sum w x~_j (P b^)_d
+// from which J^T W J / J^T W b of ANY transform whose Jacobian is affine in x (affine, small-angle rigid) is
+// assembled once at the end — 27 fp64 accumulators per lane instead of 90 per thread.
+template <class Scope>
+__device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int flags, int reversed, int keep_w, double G, double S,
+                                     const double* jc /* centre subtracted inside the Jacobian */, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  const int mapped = sc->from_mapped;
+  const bool sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0;
+  const bool skip_small = sym && (flags & LRR_F_RRL);
+  const double invG = 1.0 / G, invS = 1.0 / S;
+  const double cf0 = sc->cfrom[0], cf1 = sc->cfrom[1], cf2 = sc->cfrom[2], rf = sc->rfrom;
+  const double ct0 = sc->cto[0], ct1 = sc->cto[1], ct2 = sc->cto[2], rt = sc->rto;
+  const int j = threadIdx.x & 3;
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+  for (int k = scope.first() >> 2; k < a.M; k += scope.stride() >> 2) {
+    const int s = a.sidx[k];
+    double w = a.w[k];                             // Beaton-Tukey weight / scale^2
+    if (strength) {
+      const double g = a.gkey[k];
+      if (g >= 0.0) w *= g;                        // only where w != 0   (cdcl :839-848)
+      w *= invG;                                   // every match         (cdcl :857-860, Q13)
+    }
+    if (sym) { w *= a.skey[k]; w *= invS; }        // cdcl :985-1002
+    // cdcl symmetric: the re-weighted reversed constraints are clones that get erased again (Q11), the
+    // backward originals keep their Beaton-Tukey weights
+    if (j == 0 && !keep_w) a.w[k] = w;
+    if (s < 0) continue;
+    if (skip_small && w < 1e-4) continue;          // rrl sym :463,:571
+    const int i = lrr_from_index(a, k);
+    double px, py, pz; lrr_from_loc(a, sc, mapped, i, px, py, pz);
+    px = (px - cf0) / rf; py = (py - cf1) / rf; pz = (pz - cf2) / rf;
+    const double4 q4 = lrr_ld_pos4(a.to.grid.pos4 + s);
+    const double qx = (q4.x - ct0) / rt, qy = (q4.y - ct1) / rt, qz = (q4.z - ct2) / rt;
+    double P[6], xt[4], b0, b1, b2;
+    if (!reversed) {
+      lrr_ld_P6(a.to.rec, s, P);
+      xt[0] = px - jc[0]; xt[1] = py - jc[1]; xt[2] = pz - jc[2]; b0 = qx; b1 = qy; b2 = qz;
+    } else {   // J at the to_ location, projector and right-hand side of the from_ feature
+#pragma unroll
+      for (int p = 0; p < 6; ++p) P[p] = __ldg(a.fP6 + (size_t)p * a.n_in + i);
+      xt[0] = qx - jc[0]; xt[1] = qy - jc[1]; xt[2] = qz - jc[2]; b0 = px; b1 = py; b2 = pz;
+    }
+    xt[3] = 1.0;
+    const double wxa = w * xt[j];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const double tt = wxa * xt[b];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc[b * 6 + p] += tt * P[p];
+    }
+    acc[24] += wxa * (P[0] * b0 + P[1] * b1 + P[2] * b2);
+    acc[25] += wxa * (P[1] * b0 + P[3] * b1 + P[4] * b2);
+    acc[26] += wxa * (P[2] * b0 + P[4] * b1 + P[5] * b2);
+  }
+  const bool fin = scope.template reduce<27, 4>(acc, sh.out, sh.tmp);
+  if (fin) {
+    for (int i = threadIdx.x; i < 108; i += blockDim.x) sc->mom[i] = sh.out[i];
+    __syncthreads();
+  }
+  return fin;
+}
+
+// ---- SOLVE: mirror / invert / set_parameterization / unnormalize / recompose / inverse
+// (cdcl :1071-1089, cdcl sym :630-695, rrl sym :867-912; cdcl_trans_affine.txx:220-286,
+//  cdcl_trans_rigid3d.cxx:140-166,260-326).  Run by ONE block; F = source direction, B = other or null. ----
+__device__ __forceinline__ int lrr_sym6(int d, int e) {   // index of P_de in (xx,xy,xz,yy,yz,zz)
+  const int lo = d < e ? d : e, hi = d < e ? e : d;
+  return lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+}
+
+// Gauss-Jordan inverse of an SPD n x n matrix in shared memory (n <= 12); n*n threads cooperate.
+// Returns false when a pivot is not safely positive (caller falls back to the Jacobi-SVD pseudo-inverse,
+// the reference's vnl_svd::inverse semantics).
+static __device__ bool lrr_gj_inverse(int n, double* Msh /* n*n, destroyed */, double* inv /* n*n out */) {
+  __shared__ int s_ok;
+  __shared__ double s_piv;
+  const int tid = threadIdx.x, r = tid / n, cidx = tid % n;
+  const bool act = tid < n * n;
+  double maxd = 0;
+  if (tid == 0) { for (int i = 0; i < n; ++i) maxd = fmax(maxd, Msh[i * n + i]); s_ok = 1; s_piv = maxd; }
+  if (act) inv[tid] = (r == cidx) ? 1.0 : 0.0;
+  __syncthreads();
+  maxd = s_piv;
+  for (int p = 0; p < n; ++p) {
+    const double piv = Msh[p * n + p];
+    if (!(piv > 1e-13 * maxd)) { if (tid == 0) s_ok = 0; }
+    __syncthreads();
+    if (!s_ok) break;
+    double f = 0, mp = 0, ip = 0;
+    if (act) { f = Msh[r * n + p] / piv; mp = Msh[p * n + cidx]; ip = inv[p * n + cidx]; }
+    __syncthreads();
+    if (act) {
+      if (r == p) { Msh[tid] = mp / piv; inv[tid] = ip / piv; }
+      else { Msh[tid] -= f * mp; inv[tid] -= f * ip; }
+    }
+    __syncthreads();
+  }
+  const bool ok = s_ok != 0;
+  __syncthreads();
+  return ok;
+}
+
+static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estimate_parameters) {
+  __shared__ double T[4][4][6], V[4][3];
+  __shared__ double AtA[144], Atb[12], Msh[144], inv[144], theta[12];
+  const int tid = threadIdx.x;
+  const bool rigid = (flags & LRR_F_RIGID) != 0, normalize = (flags & LRR_F_NORMALIZE) != 0, sym = (flags & LRR_F_SYM) != 0;
+  for (int i = tid; i < 108; i += blockDim.x) {
+    double v = __ldcg(&F->mom[i]);
+    if (sym && B) v += __ldcg(&B->mom[i]);
+    const int a = i / 27, r = i % 27;
+    if (r < 24) T[a][r / 6][r % 6] = v; else V[a][r - 24] = v;
+  }
+  __syncthreads();
+  if (!rigid) {
+    // affine: parameter index of (row d, column a of x~) = a<3 ? 3d+a : 9+d   (cdcl_trans_affine.txx:65-106,141-161)
+    for (int e = tid; e < 144; e += blockDim.x) {
+      const int i = e / 12, jx = e % 12;
+      const int di = i < 9 ? i / 3 : i - 9, ai = i < 9 ? i % 3 : 3;
+      const int dj = jx < 9 ? jx / 3 : jx - 9, aj = jx < 9 ? jx % 3 : 3;
+      AtA[e] = T[ai][aj][lrr_sym6(di, dj)];
+    }
+    if (tid < 12) { const int di = tid < 9 ? tid / 3 : tid - 9, ai = tid < 9 ? tid % 3 : 3; Atb[tid] = V[ai][di]; }
+  } else {
+    // small-angle rigid: J = [ -[x]x | I ]  (cdcl_trans_rigid3d.cxx:197-225), b = q - p  (cdcl :1051-1054)
+    // J[d][i] = sum_a x~_a E[a][d][i]; non-zero E: rotation columns i<3 from the cross-product matrix, E[3][d][3+d] = 1
+    if (tid < 36 + 6) {
+      // coefficient tensor on the fly: Jc(a,d,i)
+      auto Jc = [](int a, int d, int i) -> double {
+        if (i >= 3) return (a == 3 && d == i - 3) ? 1.0 : 0.0;
+        if (a == 3 || d == i) return 0.0;
+        // column i of -[x]x: col0 = (0,-z,y), col1 = (z,0,-x), col2 = (-y,x,0)
+        // entry (d,i) = eps-like sign * x_a with a = 3 - d - i
+        if (a != 3 - d - i) return 0.0;
+        // (d,i): (1,0)=-z (2,0)=+y (0,1)=+z (2,1)=-x (0,2)=-y (1,2)=+x
+        return ((d == 2 && i == 0) || (d == 0 && i == 1) || (d == 1 && i == 2)) ? 1.0 : -1.0;
+      };
+      if (tid < 36) {
+        const int i = tid / 6, jx = tid % 6;
+        double s = 0;
+        for (int a = 0; a < 4; ++a) for (int d = 0; d < 3; ++d) {
+          const double ca = Jc(a, d, i); if (ca == 0.0) continue;
+          for (int b = 0; b < 4; ++b) for (int e = 0; e < 3; ++e) {
+            const double cb = Jc(b, e, jx); if (cb == 0.0) continue;
+            s += ca * cb * T[a][b][lrr_sym6(d, e)];
+          }
+        }
+        AtA[i * 6 + jx] = s;
+      } else {
+        const int i = tid - 36;
+        double s = 0;
+        for (int a = 0; a < 4; ++a) for (int d = 0; d < 3; ++d) {
+          const double ca = Jc(a, d, i); if (ca == 0.0) continue;
+          double v = V[a][d];
+          for (int b = 0; b < 3; ++b) v -= T[a][b][lrr_sym6(d, b)];   // (P x^)_d
+          s += ca * v;
+        }
+        Atb[i] = s;
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < dof * dof; e += blockDim.x) { F->AtA[e] = AtA[e]; Msh[e] = AtA[e]; }
+  if (tid < dof) F->Atb[tid] = Atb[tid];
+  __syncthreads();
+  bool ok = lrr_gj_inverse(dof, Msh, inv);
+  if (!ok) {   // singular or indefinite normal matrix: pseudo-inverse like vnl_svd::inverse (slow path, one thread)
+    if (tid == 0) { lrr_svd_inverse<12>(dof, AtA, inv); F->status |= LRR_ST_SINGULAR; }
+    __syncthreads();
+  }
+  if (tid < dof) { double s = 0; for (int k = 0; k < dof; ++k) s += inv[tid * dof + k] * Atb[k]; theta[tid] = s; }
+  __syncthreads();
+  const double rm = F->rfrom, rfx = F->rto;
+  // covariance: set_covariance(invAA), then affine unnormalize scales it by B = diag((rf/rm) I9, rf I3)
+  for (int e = tid; e < dof * dof; e += blockDim.x) {
+    double v = inv[e];
+    if (!rigid && normalize) {
+      const int i = e / 12, jx = e % 12;
+      v *= ((i < 9) ? rfx / rm : rfx) * ((jx < 9) ? rfx / rm : rfx);
+    }
+    F->cov[e] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double A[9], t[3], c[3];
+    const double cm[3] = {F->cfrom[0], F->cfrom[1], F->cfrom[2]}, cf[3] = {F->cto[0], F->cto[1], F->cto[2]};
+    if (!rigid) {
+      if (estimate_parameters) {
+        for (int i = 0; i < 9; ++i) A[i] = theta[i];
+        for (int d = 0; d < 3; ++d) t[d] = theta[9 + d];
+        for (int d = 0; d < 3; ++d) c[d] = normalize ? 0.0 : F->c[d];
+      } else {
+        for (int i = 0; i < 9; ++i) A[i] = F->A[i];
+        for (int d = 0; d < 3; ++d) { t[d] = F->t[d]; c[d] = F->c[d]; }
+        if (normalize) {   // cdcl_trans_affine::normalize  (affine.txx:220-253)
+          const double s = rm / rfx;
+          for (int i = 0; i < 9; ++i) A[i] = s * A[i];
+          const double dc[3] = {cm[0] - c[0], cm[1] - c[1], cm[2] - c[2]};
+          for (int r = 0; r < 3; ++r) {
+            double acc = A[3 * r] * dc[0]; acc += A[3 * r + 1] * dc[1]; acc += A[3 * r + 2] * dc[2];
+            t[r] = t[r] / rfx + acc / rm - cf[r] / rfx;
+          }
+          c[0] = c[1] = c[2] = 0.0;
+        }
+      }
+      if (normalize) {   // cdcl_trans_affine::unnormalize  (affine.txx:259-286)
+        const double s = rfx / rm;
+        for (int i = 0; i < 9; ++i) A[i] = s * A[i];
+        for (int r = 0; r < 3; ++r) t[r] = rfx * t[r] + cf[r];
+        for (int d = 0; d < 3; ++d) c[d] = cm[d];
+      }
+      for (int i = 0; i < 9; ++i) F->A[i] = A[i];
+      for (int d = 0; d < 3; ++d) { F->t[d] = t[d]; F->c[d] = c[d]; }
+    } else if (estimate_parameters) {
+      // increment from the small-angle parameterisation (rigid3d.cxx:140-166)
+      const double da = theta[0], db = theta[1], dg = theta[2];
+      A[0] = 1.0; A[1] = -dg; A[2] = db; A[3] = dg; A[4] = 1.0; A[5] = -da; A[6] = -db; A[7] = da; A[8] = 1.0;
+      t[0] = theta[3]; t[1] = theta[4]; t[2] = theta[5];
+      if (normalize) {   // cdcl_trans_rigid3d::unnormalize  (rigid3d.cxx:285-305)
+        const double s = rfx / rm;
+        for (int i = 0; i < 9; ++i) A[i] = s * A[i];
+        for (int r = 0; r < 3; ++r) {
+          double acc = (-A[3 * r]) * cm[0]; acc += (-A[3 * r + 1]) * cm[1]; acc += (-A[3 * r + 2]) * cm[2];
+          t[r] = acc + rfx * t[r] + cf[r];
+        }
+      }
+      // recompose_increment (rigid3d.cxx:309-326): dR = U V^T, R <- R dR, t <- dR t + dt   (Q7)
+      double dR[9]; lrr_orthogonalize3(A, dR);
+      double Rn[9], tn[3];
+      for (int i = 0; i < 3; ++i) for (int jx = 0; jx < 3; ++jx) {
+        double acc = F->Ag[3 * i] * dR[jx]; acc += F->Ag[3 * i + 1] * dR[3 + jx]; acc += F->Ag[3 * i + 2] * dR[6 + jx];
+        Rn[3 * i + jx] = acc;
+      }
+      for (int i = 0; i < 3; ++i) {
+        double acc = dR[3 * i] * F->tg[0]; acc += dR[3 * i + 1] * F->tg[1]; acc += dR[3 * i + 2] * F->tg[2];
+        tn[i] = acc + t[i];
+      }
+      for (int i = 0; i < 9; ++i) F->A[i] = Rn[i];
+      for (int d = 0; d < 3; ++d) { F->t[d] = tn[d]; F->c[d] = F->cg[d]; }
+    }
+    if (B && estimate_parameters) {   // backward = forward->inverse()  (affine.txx:54-59, rigid3d.cxx:113-118)
+      double invA[9]; lrr_inv3(F->A, invA);
+      for (int i = 0; i < 9; ++i) B->A[i] = invA[i];
+      for (int i = 0; i < 3; ++i) {
+        double acc = (-invA[3 * i]) * F->t[0]; acc += (-invA[3 * i + 1]) * F->t[1]; acc += (-invA[3 * i + 2]) * F->t[2];
+        B->t[i] = acc + F->c[i]; B->c[i] = 0.0;
+      }
+      for (int e = 0; e < dof * dof; ++e) B->cov[e] = 0.0;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- RESID: residuals of the current matches under the current transform: RMS_error (cdcl :196-230,
+// rrl :211-241 Q1), weighted_error (cdcl :236-268, rrl :247-276), scale-from-weights sums (cdcl :698-701) ----
+template <class Scope>
+__device__ void lrr_phase_resid(const Scope& scope, const DirArgs& a, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  const int mapped = sc->from_mapped;
+  double A[9], t[3], c[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = sc->A[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { t[i] = sc->t[i]; c[i] = sc->c[i]; }
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int s = a.sidx[k];
+    if (s < 0) continue;
+    const int i = lrr_from_index(a, k);
+    double x, y, z; lrr_from_loc(a, sc, mapped, i, x, y, z);
+    double yx, yy, yz; lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
+    const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
+    double P[6]; lrr_ld_P6(a.to.rec, s, P);
+    const double r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
+    const double w = a.w[k];
+    a.r2[k] = r2;
+    acc[0] += r2; acc[1] += w * r2; acc[2] += w; acc[3] += sqrt(r2) * w; acc[4] += 1.0;
+  }
+  if (scope.template reduce<5>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) {
+      sc->res_sum_r2 = sh.out[0]; sc->res_sum_wr2 = sh.out[1]; sc->res_sum_w = sh.out[2]; sc->res_sum_wr = sh.out[3];
+      sc->res_count = sh.out[4];
+    }
+  }
+  scope.phase_end();
+}

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    """CPU oracle (test infrastructure): oracle/liblrr_oracle.so, built on demand with gcc."""
+    import subprocess
+    from lrr_b200.capi import Lib
+    so = os.path.join(ROOT, "oracle", "liblrr_oracle.so")
+    src = [os.path.join(ROOT, "oracle", f) for f in ("lrr_oracle_capi.cpp", "lrr_oracle_core.hpp", "lrr_oracle_linalg.hpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    return Lib(so, "lrro_")
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    """The product: lrr_b200/liblrr_b200.so (hand-written CUDA behind the C ABI).  No fallback."""
+    import lrr_b200
+    return lrr_b200.lib()

@@ -1,0 +1,135 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Gates: neighbour indices bit-exact; transform parameters and covariance <= 1e-5 relative
+(Frobenius); metrics <= 1e-9 relative; iteration counts identical.
+"""
+import numpy as np
+import pytest
+
+from lrr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_PARAM = 1e-5   # north_star tolerance (fp64 accumulation); observed differences are ~1e-12
+TOL_TIGHT = 1e-8
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return synth.make_pair(11, 6000, 5000)
+
+
+@pytest.fixture(scope="module")
+def pair_rigid():
+    return synth.make_pair(12, 6000, 5000, rigid=True)
+
+
+def make_est(lib, pair, kind, dof=12, normalize=True, strength=True, number_points=None, perm=None, init_scale=None):
+    ctx = lib.context()
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    est = ctx.estimator(kind, mv, fx, dof)
+    est.set_flags(normalize, strength)
+    A, t, c = pair["init"]
+    est.set_transform(A, t, c)
+    if perm is not None:
+        est.set_order(perm, 0)
+    if number_points is not None:
+        est.set_number_points(number_points, 0)
+        if "sym" in kind:
+            est.set_number_points(number_points, 1)
+    if init_scale is not None:
+        est.set_initial_scale(init_scale, 0)
+        if "sym" in kind:
+            est.set_initial_scale(init_scale, 1)
+    return ctx, est
+
+
+def compare_state(g, o, dirs=(0,), tol=TOL_PARAM):
+    for d in dirs:
+        gf, gt, gw = g.get_matches(d)
+        of, ot, ow = o.get_matches(d)
+        assert np.array_equal(gf, of), f"dir {d}: from indices differ"
+        assert np.array_equal(gt, ot), f"dir {d}: neighbour indices differ ({np.count_nonzero(gt != ot)} of {len(gt)})"
+        assert rel(gw, ow) < TOL_TIGHT, f"dir {d}: weights rel {rel(gw, ow)}"
+        G, O = g.get_transform(d), o.get_transform(d)
+        assert rel(G["A"], O["A"]) < tol and rel(G["t"], O["t"]) < tol and np.allclose(G["c"], O["c"], rtol=tol, atol=1e-9), \
+            (d, rel(G["A"], O["A"]), rel(G["t"], O["t"]), G["c"], O["c"])
+        assert rel(G["cov"], O["cov"]) < tol, (d, "cov", rel(G["cov"], O["cov"]))
+
+
+def test_nearest_exact(gpu_lib, oracle_lib, pair):
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-40, 340, size=(3, 20000))          # includes out-of-bounds queries
+    q[:, :3000] = pair["fixed"]["xyz"][:, :3000] + rng.normal(scale=0.5, size=(3, 3000))
+    q[:, 3000:3100] = pair["fixed"]["xyz"][:, :100]     # exact hits
+    g = gpu_lib.context().upload(pair["fixed"]).nearest(q)
+    octx = oracle_lib.context(); ofs = octx.upload(pair["fixed"])
+    out = np.empty(q.shape[1], dtype=np.int32)
+    import ctypes as C
+    oracle_lib.dll.lrro_features_nearest_brute(ofs.h, C.c_int64(q.shape[1]), np.ascontiguousarray(q).ctypes.data_as(C.POINTER(C.c_double)),
+                                               out.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert np.array_equal(g, out)
+
+
+@pytest.mark.parametrize("kind", ["cdcl_fwd", "rrl_fwd"])
+@pytest.mark.parametrize("normalize,strength", [(True, True), (False, False), (True, False)])
+def test_forward_iterations(gpu_lib, oracle_lib, pair, kind, normalize, strength):
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(pair["moving"]["xyz"].shape[1]).astype(np.int32)
+    _, g = make_est(gpu_lib, pair, kind, normalize=normalize, strength=strength, number_points=3000, perm=perm)
+    _, o = make_est(oracle_lib, pair, kind, normalize=normalize, strength=strength, number_points=3000, perm=perm)
+    for it in range(4):
+        cg, co = g.one_iteration(it), o.one_iteration(it)
+        assert cg == co
+        compare_state(g, o)
+        assert abs(g.metric("rms") - o.metric("rms")) <= 1e-9 * max(1.0, abs(o.metric("rms")))
+        assert abs(g.metric("weighted") - o.metric("weighted")) <= 1e-9 * max(1.0, abs(o.metric("weighted")))
+        sg, so = g.state(), o.state()
+        assert abs(sg.scale[0] - so.scale[0]) <= 1e-9 * so.scale[0]
+
+
+@pytest.mark.parametrize("kind", ["cdcl_sym", "rrl_sym"])
+def test_symmetric_run(gpu_lib, oracle_lib, pair, kind):
+    _, g = make_est(gpu_lib, pair, kind)
+    _, o = make_est(oracle_lib, pair, kind)
+    for it in range(12):
+        cg, co = g.one_iteration(it), o.one_iteration(it)
+        sg, so = g.state(), o.state()
+        assert (cg, sg.number_matches, sg.finest_level, sg.oscillation_count) == (co, so.number_matches, so.finest_level, so.oscillation_count)
+        compare_state(g, o, dirs=(0, 1))
+        assert abs(sg.weighted_error - so.weighted_error) <= 1e-9 * max(1.0, abs(so.weighted_error))
+        if cg:
+            break
+
+
+@pytest.mark.parametrize("kind", ["cdcl_fwd", "cdcl_sym"])
+def test_rigid(gpu_lib, oracle_lib, pair_rigid, kind):
+    kw = dict(dof=6, normalize=True, strength=True)
+    if kind == "cdcl_fwd":
+        kw["number_points"] = 4000
+    _, g = make_est(gpu_lib, pair_rigid, kind, **kw)
+    _, o = make_est(oracle_lib, pair_rigid, kind, **kw)
+    for it in range(5):
+        cg, co = g.one_iteration(it), o.one_iteration(it)
+        assert cg == co
+        compare_state(g, o, dirs=(0, 1) if kind == "cdcl_sym" else (0,))
+
+
+def test_metrics_and_backward(gpu_lib, oracle_lib, pair):
+    _, g = make_est(gpu_lib, pair, "rrl_sym")
+    _, o = make_est(oracle_lib, pair, "rrl_sym")
+    for it in range(3):
+        g.one_iteration(it); o.one_iteration(it)
+    for m in ("rms", "weighted", "median", "sheet_angles", "tube_angles"):
+        for d in (0, 1):
+            a, b = g.metric(m, d), o.metric(m, d)
+            assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (m, d, a, b)
+    g.estimate_ls_backward(False); o.estimate_ls_backward(False)
+    compare_state(g, o, dirs=(0, 1))
+    assert rel(g.transfer_cov(1), o.transfer_cov(1)) < 1e-8
+    assert rel(g.transfer_cov(0), o.transfer_cov(0)) < 1e-8
