@@ -543,6 +543,31 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
       for (int i = 0; i < 9; ++i) F->A[i] = Rn[i];
       for (int d = 0; d < 3; ++d) { F->t[d] = tn[d]; F->c[d] = F->cg[d]; }
     }
+    if (B && !estimate_parameters && normalize && !rigid) {
+      // the other direction's transform only goes through normalize() / unnormalize() (cdcl sym :470-478,:668-675):
+      // same map, but its centre moves to the centre of its own from-features
+      const double brm = B->rfrom, brf = B->rto;
+      const double bcm[3] = {B->cfrom[0], B->cfrom[1], B->cfrom[2]}, bcf[3] = {B->cto[0], B->cto[1], B->cto[2]};
+      double A2[9], t2[3];
+      const double s1 = brm / brf;
+      for (int i = 0; i < 9; ++i) A2[i] = s1 * B->A[i];
+      const double dc[3] = {bcm[0] - B->c[0], bcm[1] - B->c[1], bcm[2] - B->c[2]};
+      for (int r = 0; r < 3; ++r) {
+        double acc = A2[3 * r] * dc[0]; acc += A2[3 * r + 1] * dc[1]; acc += A2[3 * r + 2] * dc[2];
+        t2[r] = B->t[r] / brf + acc / brm - bcf[r] / brf;
+      }
+      const double s2 = brf / brm;
+      for (int i = 0; i < 9; ++i) B->A[i] = s2 * A2[i];
+      for (int r = 0; r < 3; ++r) { B->t[r] = brf * t2[r] + bcf[r]; }
+      // covariance: B2 (B1 Sigma B1^T) B2 with B1 = diag(s1 I9, 1/rf I3) + N/rf, B2 = diag(s2 I9, rf I3); N[9+d][3d+k] = dc[k]
+      double K[144], Tm[144];
+      for (int i = 0; i < 144; ++i) K[i] = 0.0;
+      for (int i = 0; i < 9; ++i) K[i * 12 + i] = s2 * s1;
+      for (int d = 0; d < 3; ++d) { K[(9 + d) * 12 + 9 + d] = brf * (1.0 / brf); for (int k = 0; k < 3; ++k) K[(9 + d) * 12 + 3 * d + k] = brf * (dc[k] / brf); }
+      for (int i = 0; i < 12; ++i) for (int jx = 0; jx < 12; ++jx) { double v = 0; for (int k = 0; k < 12; ++k) v += K[i * 12 + k] * B->cov[k * 12 + jx]; Tm[i * 12 + jx] = v; }
+      for (int i = 0; i < 12; ++i) for (int jx = 0; jx < 12; ++jx) { double v = 0; for (int k = 0; k < 12; ++k) v += Tm[i * 12 + k] * K[jx * 12 + k]; B->cov[i * 12 + jx] = v; }
+      for (int d = 0; d < 3; ++d) B->c[d] = bcm[d];
+    }
     if (B && estimate_parameters) {   // backward = forward->inverse()  (affine.txx:54-59, rigid3d.cxx:113-118)
       double invA[9]; lrr_inv3(F->A, invA);
       for (int i = 0; i < 9; ++i) B->A[i] = invA[i];
