@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — ICP iterations/s of the CDCL robust-ICP hot path on B200 (BASELINE.json metric).
+
+A "step" is one `one_iteration` call of the product-default estimator
+(rrl_estimation_symmetric_ICP_matching_all<3,12>) at the FINEST level (all points of both
+directions) on a synthetic lung-CT-sized pair with 100 000 shape features per volume,
+after the reference's own point-count ramp 1000 -> x2 -> all has been run.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 (torchrun): the path shards only across independent registrations, so every rank runs
+its own replica of the registration on its own GPU, no data-path collective; `value` = all ranks' iterations
+divided by the max-over-ranks time ("weak" scaling).
+
+One JSON line on stdout (rank 0).  `value` = device-resident iterations/s with an L2 flush between timed
+iterations; `e2e` = the same metric through the C ABI with HOST buffers (upload of both volumes, estimator
+construction, full ramped run, result read-back inside the timed region).  `--impl reference` times the CPU
+oracle port of the reference's algorithm (the reference itself needs VXL/ITK/VTK and cannot be built here).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FEATURES = 100_000
+SEED = 3
+WORKLOAD = "C3: rrl symmetric ICP matching-all <3,12>, 100k shape features per volume, finest level (all points)"
+METRIC = "icp_iterations_per_s_100k_features"
+UNIT = "iterations/s"
+# compulsory bytes per forward affine iteration = 124 B per match + 24 B per fixed feature
+BYTES_PER_MATCH, BYTES_PER_FIXED = 124, 24
+
+
+def algorithmic_bytes_iteration(m_f, n_f, m_b, n_b):
+    return BYTES_PER_MATCH * (m_f + m_b) + BYTES_PER_FIXED * (n_f + n_b)
+
+
+# per-kernel algorithmic bytes, per match of one direction / per to-feature
+KERNEL_BYTES = {
+    # x 24 + q 24 + P 48 (reads) + idx 4 + r2 8 + w 8 (writes); + 24 B per to-feature read once by the NN search
+    "match": (116, 24),
+    "norm1": (24 + 4 + 8 + 24, 0),
+    "norm2": (4 + 8 + 24, 0),
+    "weight": (8 + 4 + 8 + 8 + 24 + 8 + 8 + 8, 0),
+    "collect": (16, 0),
+    "accumulate": (24 + 4 + 8 + 8 + 8 + 24 + 48 + 8, 0),
+    "resid": (24 + 4 + 24 + 48 + 8 + 8, 0),
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload():
+    from lrr_b200 import synth
+    return synth.make_pair(SEED, N_FEATURES, N_FEATURES)
+
+
+def ramp_to_finest(est, max_iter=70):
+    """The reference's driver loop (rrl/itkLocationRegistration.cxx:2418): one_iteration until converged."""
+    it, conv = 0, False
+    while not conv and it < max_iter:
+        conv = est.one_iteration(it)
+        it += 1
+    return it, conv
+
+
+def cpu_measure(pair, steps, warmup):
+    """CPU arm: the oracle port of the reference algorithm, single thread (the reference pins its estimators to one
+    thread, rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760)."""
+    from lrr_b200.capi import Lib
+    so = os.path.join(ROOT, "oracle", "liblrr_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = Lib(so, "lrro_")
+    ctx = lib.context()
+    t0 = time.perf_counter()
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    est = ctx.estimator("rrl_sym", mv, fx, 12)
+    A, t, c = pair["init"]
+    est.set_transform(A, t, c)
+    iters, conv = ramp_to_finest(est)
+    est.get_transform(0)
+    t_reg = time.perf_counter() - t0
+    for i in range(warmup):
+        est.one_iteration(iters + i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        est.one_iteration(iters + warmup + i)
+    dt = time.perf_counter() - t0
+    return {"finest_iters_per_s": steps / dt, "ms_per_step": 1e3 * dt / steps, "registration_s": t_reg,
+            "registration_iters": iters, "registration_iters_per_s": iters / t_reg, "converged": bool(conv)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    pair = make_workload()
+    steps = max(1, min(args.steps, 40))   # bounded sample: ~0.6 s of CPU per finest-level iteration
+    warm = max(1, min(args.warmup, 2))
+    r = cpu_measure(pair, steps, warm)
+    cores = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["finest_iters_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_fixed": N_FEATURES, "n_moving": N_FEATURES, "seed": SEED, "l2": "host CPU run"},
+        "cpu_baseline": {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} one_iteration calls at the finest level after the full ramp; single thread = the "
+                                   "reference's execution model (its MultiThreader is pinned to 1 thread)",
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": r["finest_iters_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "registration": {"seconds": r["registration_s"], "iterations": r["registration_iters"],
+                         "iters_per_s": r["registration_iters_per_s"], "converged": r["converged"]},
+        "gpu_launches": 0,
+        "note": "reference needs VXL/ITK/VTK (absent): oracle/ CPU port of the same algorithm, see DESIGN.md",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def feature_bytes(feats):
+    return int(sum(v.nbytes for v in feats.values() if v is not None))
+
+
+def pin(feats):
+    import torch
+    out = {}
+    for k, v in feats.items():
+        if v is None:
+            out[k] = None
+            continue
+        t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+        out[k] = t.numpy()
+        out["_keep_" + k] = t
+    return out
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import lrr_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = lrr_b200.lib()
+    pair = make_workload()
+    stream = torch.cuda.Stream()
+    ctx = lib.context(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    A0, t0_, c0 = pair["init"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+        est = ctx.estimator("rrl_sym", mv, fx, 12)
+        est.set_transform(A0, t0_, c0)
+        ramp_iters, ramp_conv = ramp_to_finest(est)
+        st = est.state()
+        assert st.finest_level == 1 and st.number_points[0] == N_FEATURES and st.number_points[1] == N_FEATURES, "ramp did not reach the finest level"
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+        it_no = ramp_iters
+        for _ in range(max(3, args.warmup)):
+            est.one_iteration(it_no); it_no += 1
+
+        # ---- timed region 1: K iterations, L2 flushed between iterations, CUDA events on the launching stream ----
+        sampler = ClockSampler(local_rank); sampler.start()
+        barrier()
+        launches0 = ctx.launch_count()
+        evs = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            est.one_iteration(it_no); it_no += 1
+            b.record(stream)
+            evs.append((a, b))
+        barrier()
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.stop()
+        ms_iters = np.array([a.elapsed_time(b) for a, b in evs])
+        total_ms = float(ms_iters.sum())
+
+        # ---- timed region 2: L2-warm back-to-back iterations (the production steady state) ----
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            est.one_iteration(it_no); it_no += 1
+        b.record(stream)
+        barrier()
+        warm_ms = a.elapsed_time(b)
+
+        # ---- per-kernel CUDA-event times (same conditions as region 1) ----
+        ctx.set_profiling(True)
+        for _ in range(args.steps):
+            flush.fill_(1)
+            est.one_iteration(it_no); it_no += 1
+        phases = ctx.phase_times()
+        ctx.set_profiling(False)
+        final = est.get_transform(0)
+
+    tm = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms_max, warm_ms_max = float(tm[0]), float(tm[1])
+    value = world * args.steps / (total_ms_max * 1e-3)
+    value_warm = world * args.steps / (warm_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (rank-local; max over ranks) ----
+    e2e_steps = max(1, min(3, args.steps))
+    pf, pm = pin(pair["fixed"]), pin(pair["moving"])
+    h2d = feature_bytes(pair["fixed"]) + feature_bytes(pair["moving"])
+    d2h = (9 + 3 + 3 + 144) * 8
+    with torch.cuda.stream(stream):
+        barrier()
+        t_start = time.perf_counter()
+        e2e_iters = 0
+        for _ in range(e2e_steps):
+            fx2, mv2 = ctx.upload({k: v for k, v in pf.items() if not k.startswith("_keep_")}), ctx.upload({k: v for k, v in pm.items() if not k.startswith("_keep_")})
+            est2 = ctx.estimator("rrl_sym", mv2, fx2, 12)
+            est2.set_transform(A0, t0_, c0)
+            n_it, _ = ramp_to_finest(est2)
+            est2.get_transform(0)
+            e2e_iters += n_it
+            est2.close(); fx2.close(); mv2.close()
+        barrier()
+        e2e_s = time.perf_counter() - t_start
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_iters / float(te[0])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    M, N = N_FEATURES, N_FEATURES
+    # dominant kernel by CUDA-event time
+    dom = max(phases.items(), key=lambda kv: kv[1][0])[0] if phases else "match"
+    per_phase = {}
+    for name, (ms, cnt) in phases.items():
+        pm_, pt_ = KERNEL_BYTES.get(name, (0, 0))
+        ndirs = 1 if name in ("norm1", "norm2", "resid") else 2
+        by = ndirs * (pm_ * M + pt_ * N)
+        us = 1e3 * ms / cnt
+        per_phase[name] = {"us_per_launch": us, "launches": cnt, "algorithmic_bytes": by, "gbs": by / (us * 1e-6) / 1e9 if us > 0 else None}
+    d = per_phase.get(dom, {"gbs": 0, "us_per_launch": 0, "algorithmic_bytes": 0})
+    it_bytes = algorithmic_bytes_iteration(M, N, M, N)
+    ms_step = total_ms_max / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_fixed": N, "n_moving": M, "seed": SEED, "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2": "flushed (256 MiB write) between timed iterations; working set ~30 MB is L2-resident otherwise",
+                   "ramp_iterations": ramp_iters, "ramp_converged": bool(ramp_conv)},
+        "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": None, "peak_kind": peak_kind,
+                     "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
+        "roofline_iteration": {"algorithmic_bytes": it_bytes, "achieved_gbs": it_bytes / (ms_step * 1e-3) / 1e9,
+                               "frac": it_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                               "achieved_gbs_l2_warm": it_bytes / (warm_ms_max / args.steps * 1e-3) / 1e9},
+        "kernels": per_phase,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "iterations": e2e_iters, "seconds": float(te[0]),
+                "what": "per step: upload both volumes from pinned host memory (grid build), construct estimator, set_transform, "
+                        "ramped run to convergence (<=70 one_iteration calls), read back transform+covariance"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "final_rms": None,
+    }
+    if world == 1 and not args.no_cpu:
+        r = cpu_measure(pair, 6, 1)
+        line["cpu_baseline"] = {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "full ramped registration + 6 one_iteration calls at the finest level, CPU oracle port, single thread "
+                                          "(the reference's execution model)",
+                                "registration_iters_per_s": r["registration_iters_per_s"], "registration_s": r["registration_s"],
+                                "host_cores_available": os.cpu_count()}
+    else:
+        line["cpu_baseline"] = None
+    line["final_A00"] = float(final["A"][0, 0])
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

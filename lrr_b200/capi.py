@@ -23,6 +23,7 @@ METRIC = {"rms": 0, "weighted": 1, "median": 2, "sheet_angles": 3, "tube_angles"
 # every symbol include/lrr_gpu.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = [
     "ctx_create", "ctx_destroy", "ctx_set_stream", "ctx_synchronize", "ctx_last_error", "ctx_launch_count",
+    "ctx_set_profiling", "ctx_phase_times",
     "features_upload", "features_destroy", "features_size", "features_nearest",
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
@@ -102,6 +103,7 @@ class Lib:
             "ctx_create": (i32, [i32, C.POINTER(vp)]), "ctx_destroy": (None, [vp]),
             "ctx_set_stream": (i32, [vp, vp]), "ctx_synchronize": (i32, [vp]),
             "ctx_last_error": (C.c_char_p, [vp]), "ctx_launch_count": (i64, [vp]),
+            "ctx_set_profiling": (i32, [vp, i32]), "ctx_phase_times": (i32, [vp, i32, pd, C.POINTER(C.c_int64)]),
             "features_upload": (i32, [vp, i64, pd, pd, pd, pd, C.POINTER(C.c_uint8), pd, C.POINTER(vp)]),
             "features_destroy": (None, [vp]), "features_size": (i64, [vp]),
             "features_nearest": (i32, [vp, i64, pd, pi32]),
@@ -155,6 +157,16 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.fn("ctx_launch_count")(self.h))
+
+    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "other"]
+
+    def set_profiling(self, on: bool):
+        self.check(self.lib.fn("ctx_set_profiling")(self.h, int(on)), "ctx_set_profiling")
+
+    def phase_times(self) -> dict:
+        ms = np.zeros(12); cnt = np.zeros(12, dtype=np.int64)
+        self.check(self.lib.fn("ctx_phase_times")(self.h, 12, _dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))), "ctx_phase_times")
+        return {p: (float(ms[i]), int(cnt[i])) for i, p in enumerate(self.PHASES) if cnt[i]}
 
     def upload(self, feats: dict) -> "FeatureSet":
         return FeatureSet(self, feats)

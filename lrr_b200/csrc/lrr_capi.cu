@@ -21,6 +21,41 @@
 
 template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
 
+// ---- instrumentation ------------------------------------------------------------------------------------
+struct PhaseTimer {
+  lrr_ctx* ctx; int phase; cudaEvent_t a = nullptr, b = nullptr;
+  PhaseTimer(lrr_ctx* c, int ph) : ctx(c), phase(ph) {
+    if (!ctx->profiling) return;
+    cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream);
+  }
+  ~PhaseTimer() { if (!a) return; cudaEventRecord(b, ctx->stream); ctx->spans.push_back({phase, a, b}); }
+};
+#define PHASE(ph) PhaseTimer phase_timer_##ph(ctx, ph)
+static void drain_spans(lrr_ctx* ctx) {
+  for (auto& s : ctx->spans) {
+    cudaEventSynchronize(s.b);
+    float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b);
+    ctx->phase_ms[s.phase] += ms; ctx->phase_count[s.phase] += 1;
+    cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+  }
+  ctx->spans.clear();
+}
+extern "C" int lrr_ctx_set_profiling(lrr_ctx* ctx, int enable) {
+  if (!ctx) return LRR_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  drain_spans(ctx);
+  ctx->profiling = enable != 0;
+  for (int i = 0; i < LRR_NPHASE; ++i) { ctx->phase_ms[i] = 0; ctx->phase_count[i] = 0; }
+  return LRR_OK;
+}
+extern "C" int lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count) {
+  if (!ctx || !ms || !count) return LRR_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  drain_spans(ctx);
+  for (int i = 0; i < cap && i < LRR_NPHASE; ++i) { ms[i] = ctx->phase_ms[i]; count[i] = ctx->phase_count[i]; }
+  return LRR_OK;
+}
+
 // ---- context -------------------------------------------------------------------------------------------
 extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
   if (!out) return LRR_ERR_INVALID;
@@ -157,12 +192,15 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
   CK(dmalloc(&d.sidx, cap)); CK(dmalloc(&d.w, 4 * cap)); d.r2 = d.w + cap; d.gkey = d.w + 2 * cap; d.skey = d.w + 3 * cap;
   CK(dmalloc(&d.stamp, nto)); CK(cudaMemsetAsync(d.stamp, 0xFF, nto * sizeof(unsigned long long), ctx->stream));
   CK(dmalloc(&d.sc, 1));
+  CK(dmalloc(&d.hq_k, 3 * cap + 1)); d.hq_s = d.hq_k + cap; d.hq_o = d.hq_k + 2 * cap; d.hq_count = d.hq_k + 3 * cap;
+  CK(dmalloc(&d.prev_s, cap)); CK(dmalloc(&d.proc, cap)); CK(dmalloc(&d.proc_mark, 2 * cap));
+  CK(dmalloc(&d.hq_best, cap)); CK(cudaMemsetAsync(d.hq_count, 0, sizeof(int), ctx->stream));
   d.epoch = 0; d.has_order = false; d.matches = 0; d.weights_fresh = false;
   d.initial_scale = std::numeric_limits<double>::quiet_NaN();
   return LRR_OK;
 }
 static void dir_free(lrr_dir& d) {
-  cudaFree(d.fx); cudaFree(d.fP6); cudaFree(d.forig); cudaFree(d.order); cudaFree(d.sidx); cudaFree(d.w); cudaFree(d.stamp); cudaFree(d.sc);
+  cudaFree(d.fx); cudaFree(d.fP6); cudaFree(d.forig); cudaFree(d.order); cudaFree(d.sidx); cudaFree(d.w); cudaFree(d.stamp); cudaFree(d.sc); cudaFree(d.hq_k); cudaFree(d.hq_best); cudaFree(d.prev_s); cudaFree(d.proc); cudaFree(d.proc_mark);
 }
 static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
   if (n < 0 || (size_t)n > d.cap) return LRR_ERR_INVALID;
@@ -179,6 +217,8 @@ static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t 
     d.subset = false;
   }
   d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false;
+  CK(cudaMemsetAsync(d.prev_s, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));   // no search candidates yet
+  lrr_k_build_proc(d.from_all->dev, d.subset ? d.forig : nullptr, (int)n, d.proc_mark, d.proc, st, &ctx->launches);
   d.host_order.clear();
   return LRR_OK;
 }
@@ -193,6 +233,7 @@ static DirArgs dir_args(const lrr_dir& d) {
   a.to = d.to_all->dev; a.from_all = d.from_all->dev;
   a.sidx = d.sidx; a.w = d.w; a.r2 = d.r2; a.gkey = d.gkey; a.skey = d.skey;
   a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
+  a.prev_s = d.prev_s; a.proc = d.has_order ? nullptr : d.proc; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
   return a;
 }
@@ -440,7 +481,7 @@ static int do_find_closest(lrr_est* e) {
     }
   }
   EstArgs a = est_args(e);
-  lrr_k_match(a, ctx->stream, &ctx->launches);
+  { PHASE(PH_MATCH); lrr_k_match(a, ctx->stream, &ctx->launches); }
   for (int d = 0; d < nd; ++d) { e->d[d].matches = a.d[d].M; e->d[d].weights_fresh = true; }
   e->werr_cache_valid = false;
   return LRR_OK;
@@ -470,20 +511,23 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters) {
   // stale weights (not straight after find_closest): residuals under the current transform first (cdcl :698-701)
   int stale = 0;
   for (int d = 0; d < nd; ++d) if (!e->d[d].weights_fresh) stale |= 1 << d;
-  if (stale) { lrr_k_resid(a, stale, ctx->stream, &ctx->launches); a.flags |= LRR_F_USE_OLD_W; }
+  if (stale) { PHASE(PH_RESID); lrr_k_resid(a, stale, ctx->stream, &ctx->launches); a.flags |= LRR_F_USE_OLD_W; }
   int mode[2] = {0, 0}; double sin[2] = {0, 0};
   for (int d = 0; d < nd; ++d) {
     lrr_dir& D = e->d[d];
     if (!D.scale_estimated) {
-      if (std::isnan(D.initial_scale)) { int rc = muse_for_dir(e, a, d); if (rc != LRR_OK) return rc; mode[d] = 1; }
+      if (std::isnan(D.initial_scale)) { PHASE(PH_MUSE); int rc = muse_for_dir(e, a, d); if (rc != LRR_OK) return rc; mode[d] = 1; }
       else { mode[d] = 2; sin[d] = D.initial_scale; }
       D.scale_estimated = true;
     }
   }
-  if (e->normalize) { lrr_k_norm1(a, ctx->stream, &ctx->launches); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
-  lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches);
-  if (e->strength || e->sym()) lrr_k_collect(a, ctx->stream, &ctx->launches);
-  lrr_k_accumulate(a, ctx->stream, &ctx->launches);
+  if (e->normalize) {
+    { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches); }
+    { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
+  }
+  { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
+  if (e->strength || e->sym()) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
+  { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches); }
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   e->werr_cache_valid = false;
   return LRR_OK;
@@ -517,7 +561,7 @@ static int one_iteration_fwd(lrr_est* e, int* converged) {
   int rc = do_find_closest(e); if (rc != LRR_OK) return rc;
   if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
   EstArgs a = est_args(e);
-  lrr_k_resid(a, 1, ctx->stream, &ctx->launches);
+  { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
   if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double before = rms_of(e, e->h[0], false), after = rms_of(e, e->h[0], true);
@@ -546,7 +590,7 @@ static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out)
   if ((rc = do_find_closest(e)) != LRR_OK) return rc;
   if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
   EstArgs a = est_args(e);
-  lrr_k_resid(a, 1, ctx->stream, &ctx->launches);
+  { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
   if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double after = werr_of(e->h[0]);

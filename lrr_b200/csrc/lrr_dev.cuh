@@ -55,15 +55,26 @@ __device__ __forceinline__ double4 lrr_ld_pos4(const double4* __restrict__ p) {
 }
 __device__ __forceinline__ int lrr_pos4_orig(const double4& p) { return (int)__double_as_longlong(p.w); }
 
-// scan points [lo,hi) of the cell-sorted position array
+// scan points [lo,hi) of the cell-sorted position array; four loads in flight per step
+__device__ __forceinline__ void lrr_nn_upd(const double4& p, int j, double qx, double qy, double qz, double& best, int& best_s, int& best_o) {
+  const double d = lrr_dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+  if (d < best) { best = d; best_s = j; best_o = lrr_pos4_orig(p); }
+  else if (d == best) { const int o = lrr_pos4_orig(p); if (o < best_o) { best_s = j; best_o = o; } }
+}
 __device__ __forceinline__ void lrr_nn_scan(const double4* __restrict__ pos4, int lo, int hi, double qx, double qy, double qz,
                                             double& best, int& best_s, int& best_o) {
-  for (int j = lo; j < hi; ++j) {
-    double4 p = lrr_ld_pos4(pos4 + j);
-    double d = lrr_dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-    if (d < best) { best = d; best_s = j; best_o = lrr_pos4_orig(p); }
-    else if (d == best) { int o = lrr_pos4_orig(p); if (o < best_o) { best_s = j; best_o = o; } }
+  int j = lo;
+  for (; j + 4 <= hi; j += 4) {
+    const double4 p0 = lrr_ld_pos4(pos4 + j), p1 = lrr_ld_pos4(pos4 + j + 1), p2 = lrr_ld_pos4(pos4 + j + 2), p3 = lrr_ld_pos4(pos4 + j + 3);
+    lrr_nn_upd(p0, j, qx, qy, qz, best, best_s, best_o); lrr_nn_upd(p1, j + 1, qx, qy, qz, best, best_s, best_o);
+    lrr_nn_upd(p2, j + 2, qx, qy, qz, best, best_s, best_o); lrr_nn_upd(p3, j + 3, qx, qy, qz, best, best_s, best_o);
   }
+  if (j + 2 <= hi) {
+    const double4 p0 = lrr_ld_pos4(pos4 + j), p1 = lrr_ld_pos4(pos4 + j + 1);
+    lrr_nn_upd(p0, j, qx, qy, qz, best, best_s, best_o); lrr_nn_upd(p1, j + 1, qx, qy, qz, best, best_s, best_o);
+    j += 2;
+  }
+  if (j < hi) { const double4 p0 = lrr_ld_pos4(pos4 + j); lrr_nn_upd(p0, j, qx, qy, qz, best, best_s, best_o); }
 }
 
 // Exact 1-NN over the uniform grid: Chebyshev shells around the query's (clamped) cell.  After shell r
@@ -114,6 +125,120 @@ __device__ __forceinline__ int lrr_nn_search(const GridDev& g, double qx, double
   return best_s;
 }
 
+// ---- search used by the MATCH phase: bounded ball scan ------------------------------------------------------
+// ICP moves the transform a little per iteration, so the neighbour found for a moving feature in the previous
+// iteration is an excellent CANDIDATE for the next one.  Any candidate gives an upper bound on the squared
+// nearest-neighbour distance; the exact neighbour is then the minimum over the cells that intersect the ball
+// of that radius around the query — usually one to four x-runs of the cell-sorted array instead of 27 cells.
+// Exactness: a fixed point p with |p-q|^2 <= best lies in a cell whose (y,z) row intersects the ball and whose
+// x index is inside [floor((qx-rx-ox)/h), floor((qx+rx-ox)/h)] for rx^2 = best - (row distance)^2; all radii
+// are inflated by a slack far above the rounding of the cell assignment, rows are pruned only when their
+// slab distance is STRICTLY above the current best, and ties go to the lowest original index.
+//   pass A (one thread per query): queries whose ball touches at most LRR_BALL_ROWS rows;
+//   pass B (one warp per query): everything else — queries without a candidate first expand Chebyshev
+//   shells until a point is found, then the lanes split the rows of the ball.
+#define LRR_BALL_ROWS 9
+
+struct NNState { double best; int best_s, best_o; };
+
+__device__ __forceinline__ int lrr_cell_clamp(double v, double o, double inv_h, int n) {
+  int c = (int)floor((v - o) * inv_h);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+// distance from coordinate v to the slab [o + c h, o + (c+1) h], shrunk by the slack
+__device__ __forceinline__ double lrr_slab_dist(double v, double o, double h, int c, double slack) {
+  const double lo = o + c * h, hi = lo + h;
+  double d = v < lo ? lo - v : (v > hi ? v - hi : 0.0);
+  d -= slack;
+  return d > 0.0 ? d : 0.0;
+}
+// scan one (y,z) row of the ball: the x-run within sqrt(best - dyz2) of the query
+__device__ __forceinline__ void lrr_ball_row(const GridDev& g, int y, int z, double dyz2, double qx, double qy, double qz, double slack,
+                                             double& best, int& best_s, int& best_o) {
+  const double rx = sqrt(best - dyz2) * (1.0 + 1e-9) + slack;
+  const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
+  const int row = (z * g.ny + y) * g.nx;
+  lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), qx, qy, qz, best, best_s, best_o);
+}
+
+// pass A.  st holds a candidate (best_s >= 0).  Returns false when the ball touches too many rows.
+__device__ __forceinline__ bool lrr_nn_ball_thread(const GridDev& g, double qx, double qy, double qz, NNState& st) {
+  const double slack = 1e-9 * g.h;
+  const double R = sqrt(st.best) * (1.0 + 1e-9) + slack;
+  const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
+  const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
+  if ((z1 - z0 + 1) * (y1 - y0 + 1) > LRR_BALL_ROWS) return false;
+  for (int z = z0; z <= z1; ++z) {
+    const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dz2 = dz * dz;
+    if (dz2 > st.best) continue;
+    for (int y = y0; y <= y1; ++y) {
+      const double dy = lrr_slab_dist(qy, g.oy, g.h, y, slack), dyz2 = dz2 + dy * dy;
+      if (dyz2 > st.best) continue;
+      lrr_ball_row(g, y, z, dyz2, qx, qy, qz, slack, st.best, st.best_s, st.best_o);
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void lrr_warp_min(double& best, int& best_s, int& best_o) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int os = __shfl_xor_sync(0xffffffffu, best_s, o), oo = __shfl_xor_sync(0xffffffffu, best_o, o);
+    if (ob < best || (ob == best && oo < best_o)) { best = ob; best_s = os; best_o = oo; }
+  }
+}
+
+// pass B: whole warp, one query; st identical in every lane (best_s < 0: no candidate yet).
+// Returns the sorted slot of the exact nearest neighbour (-1 for an empty set).
+__device__ __forceinline__ int lrr_nn_pass_b(const GridDev& g, double qx, double qy, double qz, NNState st) {
+  if (g.n <= 0) return -1;
+  const int lane = threadIdx.x & 31;
+  const double slack = 1e-9 * g.h;
+  double best = st.best; int best_s = st.best_s, best_o = st.best_o;
+  if (best_s < 0) {
+    // no candidate: Chebyshev shells around the query's cell until one holds a point (any point will do)
+    best = 1e300; best_o = 0x7fffffff;
+    const int cx = lrr_cell_clamp(qx, g.ox, g.inv_h, g.nx), cy = lrr_cell_clamp(qy, g.oy, g.inv_h, g.ny), cz = lrr_cell_clamp(qz, g.oz, g.inv_h, g.nz);
+    const int rmax = max(max(g.nx, g.ny), g.nz);
+    for (int r = 0; r <= rmax; ++r) {
+      const int side = 2 * r + 1, nface = 2 * side, per_plane = 4 * r, nruns = nface + (side - 2) * per_plane;
+      for (int t = lane; t < nruns; t += 32) {
+        int z, y, xa, xb;
+        if (t < nface) { z = (t < side) ? cz - r : cz + r; y = cy - r + (t % side); xa = cx - r; xb = cx + r; }
+        else {
+          const int u = t - nface, zi = u / per_plane, v = u % per_plane;
+          z = cz - r + 1 + zi;
+          if (v < 2) { y = (v == 0) ? cy - r : cy + r; xa = cx - r; xb = cx + r; }
+          else { const int m = v - 2; y = cy - r + 1 + (m >> 1); xa = xb = (m & 1) ? cx + r : cx - r; }
+        }
+        if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+        xa = max(xa, 0); xb = min(xb, g.nx - 1);
+        if (xa > xb) continue;
+        const int row = (z * g.ny + y) * g.nx;
+        lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), qx, qy, qz, best, best_s, best_o);
+      }
+      lrr_warp_min(best, best_s, best_o);
+      if (best_s >= 0) break;
+    }
+    if (best_s < 0) return -1;
+  }
+  // ball scan: the lanes split the rows
+  const double R = sqrt(best) * (1.0 + 1e-9) + slack;
+  const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
+  const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
+  const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+  for (int t = lane; t < nrows; t += 32) {
+    const int z = z0 + t / ny, y = y0 + t % ny;
+    const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dy = lrr_slab_dist(qy, g.oy, g.h, y, slack);
+    const double dyz2 = dz * dz + dy * dy;
+    if (dyz2 > best) continue;
+    lrr_ball_row(g, y, z, dyz2, qx, qy, qz, slack, best, best_s, best_o);
+  }
+  lrr_warp_min(best, best_s, best_o);
+  return best_s;
+}
+
 // ---- reduction scopes ------------------------------------------------------------------------------
 // A phase body is written once against a Scope: `first()/stride()` drive the element loop, `reduce<K>`
 // sums K doubles per thread over the scope.  It returns true in every thread of the FINALIZER block with
@@ -126,6 +251,7 @@ struct GridScope {
   double* partials; unsigned int* ticket;
   __device__ __forceinline__ int first() const { return blockIdx.x * blockDim.x + threadIdx.x; }
   __device__ __forceinline__ int stride() const { return gridDim.x * blockDim.x; }
+  __device__ __forceinline__ int block_first() const { return blockIdx.x * blockDim.x; }
   // G = lanes per item: lanes with equal (lane % G) are summed; outputs are K*G values, index g*K + k.
   template <int K, int G = 1>
   __device__ __forceinline__ bool reduce(double (&v)[K], double* sh_out /* >= K*G */, double* sh_tmp /* >= K*G*nwarps */) const {
@@ -155,10 +281,13 @@ struct GridScope {
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    for (int k = threadIdx.x; k < KG; k += blockDim.x) {
+    // one warp per value: lanes stride over the block rows (independent loads in flight), fixed shuffle tree
+    for (int k = wid; k < KG; k += nw) {
       double s = 0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
-      sh_out[k] = s;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) sh_out[k] = s;
     }
     __syncthreads();
     return true;
@@ -183,6 +312,7 @@ struct GridScope {
 struct BlockScope {
   __device__ __forceinline__ int first() const { return threadIdx.x; }
   __device__ __forceinline__ int stride() const { return blockDim.x; }
+  __device__ __forceinline__ int block_first() const { return 0; }
   template <int K, int G = 1>
   __device__ __forceinline__ bool reduce(double (&v)[K], double* sh_out, double* sh_tmp) const {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;

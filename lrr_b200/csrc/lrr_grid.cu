@@ -7,6 +7,7 @@
 #include "lrr_internal.h"
 #include "lrr_dev.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 static int g_num_sms = 0;
 int lrr_num_sms() {
@@ -135,14 +136,16 @@ cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches) 
   for (int d = 0; d < 3; ++d) { ext[d] = mx[d] - mn[d]; if (ext[d] > maxext) maxext = ext[d]; }
   if (!(maxext > 0)) maxext = 1.0;
   for (int d = 0; d < 3; ++d) { if (ext[d] < 1e-6 * maxext) ext[d] = 1e-6 * maxext; vol *= ext[d]; }
-  // ~2 features per cell on average; features lie on surfaces, so most cells stay empty and the
-  // occupied ones hold a handful of points
-  double target_cells = fmax(1.0, (double)n / 2.0);
+  // Features lie on surfaces and curves, so most cells stay empty and the occupied ones hold far more than
+  // the average: aim at ~4 cells per feature (LRR_GRID_DENSITY overrides, for tuning runs)
+  double density = 4.0;
+  if (const char* env = getenv("LRR_GRID_DENSITY")) { double v = atof(env); if (v > 0.01 && v <= 16.0) density = v; }
+  double target_cells = fmax(1.0, (double)n * density);
   double h = cbrt(vol / target_cells);
   long long nx, ny, nz;
   for (;;) {
     nx = (long long)floor(ext[0] / h) + 1; ny = (long long)floor(ext[1] / h) + 1; nz = (long long)floor(ext[2] / h) + 1;
-    if (nx * ny * nz <= 8LL * n + 64 && nx * ny * nz < (1LL << 27)) break;
+    if (nx * ny * nz <= 20LL * n + 64 && nx * ny * nz < (1LL << 27)) break;
     h *= 1.25;
   }
   g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.h = h; g.inv_h = 1.0 / h; g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;

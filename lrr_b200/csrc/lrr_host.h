@@ -7,6 +7,8 @@
 #include "lrr_internal.h"
 #include "lrr_linalg.cuh"
 
+#define LRR_NPHASE 12
+enum { PH_MATCH = 0, PH_NORM1, PH_NORM2, PH_WEIGHT, PH_COLLECT, PH_ACCUM, PH_RESID, PH_MUSE, PH_METRIC, PH_OBJCOV, PH_BATCH, PH_OTHER };
 struct lrr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -20,6 +22,11 @@ struct lrr_ctx {
   double* muse_table = nullptr;
   double* scratch_d = nullptr;
   void* pinned = nullptr;
+  // instrumentation: CUDA-event timing per phase kernel (lrr_ctx_set_profiling)
+  bool profiling = false;
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  double phase_ms[LRR_NPHASE] = {0}; long long phase_count[LRR_NPHASE] = {0};
 };
 
 struct lrr_fset {
@@ -39,6 +46,7 @@ struct lrr_dir {
   int *forig = nullptr, *order = nullptr, *sidx = nullptr;
   double *w = nullptr, *r2 = nullptr, *gkey = nullptr, *skey = nullptr;
   unsigned long long* stamp = nullptr;
+  int *hq_k = nullptr, *hq_s = nullptr, *hq_o = nullptr, *hq_count = nullptr, *prev_s = nullptr, *proc = nullptr, *proc_mark = nullptr; double* hq_best = nullptr;
   Scal* sc = nullptr;
   int64_t n_in = 0, number_points = 0, matches = 0;
   unsigned int epoch = 0;

@@ -2,6 +2,7 @@
 // lrr_phases.cuh; this file instantiates them over the whole GPU (GridScope), one grid row per direction of
 // a symmetric estimator, and adds the cross-direction finalisation (merged order statistics, joint solve).
 #include "lrr_phases.cuh"
+#include <algorithm>
 
 static inline int nblk_for(long long items) {
   long long b = (items + LRR_THREADS - 1) / LRR_THREADS;
@@ -63,15 +64,53 @@ void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx,
   k_gather_from<<<(n_in + 255) / 256, 256, 0, st>>>(src, idx, n_in, fx, fy, fz, fs, fP6); ++*launches;
 }
 
+// processing order of the match phase: compact indices sorted by the from-set's own cell order, so that the
+// 32 queries of a warp are spatial neighbours (same rows of the to-grid, shared cache lines, converged loops)
+__global__ void k_proc_mark(FsetDev f, const int* __restrict__ forig, int n_in, int* __restrict__ mark) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_in) return;
+  const int o = forig ? forig[i] : i;
+  mark[f.sorted_of_orig[o]] = i + 1;   // duplicates in the subset: the last writer wins, the others are appended below
+}
+__global__ void __launch_bounds__(1024) k_proc_compact(const int* __restrict__ mark, int n_all, int n_in, int* __restrict__ proc, int* __restrict__ seen) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, T = blockDim.x;
+  const int per = (n_all + T - 1) / T, lo = min(t * per, n_all), hi = min(lo + per, n_all);
+  int cnt = 0;
+  for (int j = lo; j < hi; ++j) cnt += mark[j] != 0;
+  s_part[t] = cnt;
+  __syncthreads();
+  for (int o = 1; o < T; o <<= 1) { int v = (t >= o) ? s_part[t - o] : 0; __syncthreads(); s_part[t] += v; __syncthreads(); }
+  int pos = s_part[t] - cnt;
+  for (int j = lo; j < hi; ++j) { const int m = mark[j]; if (m) { proc[pos++] = m - 1; seen[m - 1] = 1; } }
+  __syncthreads();
+  // subset entries that lost a duplicate slot (same feature listed twice) keep their turn at the end
+  if (t == 0) { int p = s_part[T - 1]; if (p < n_in) for (int i = 0; i < n_in; ++i) if (!seen[i]) proc[p++] = i; }
+}
+void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* mark, int* proc, cudaStream_t st, long long* launches) {
+  if (n_in == 0) return;
+  cudaMemsetAsync(mark, 0, sizeof(int) * ((size_t)from_all.n + n_in), st);
+  k_proc_mark<<<(n_in + 255) / 256, 256, 0, st>>>(from_all, forig, n_in, mark); ++*launches;
+  k_proc_compact<<<1, 1024, 0, st>>>(mark, from_all.n, n_in, proc, mark + from_all.n); ++*launches;
+}
+
 // ---- phase kernels -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LRR_THREADS) k_match(const __grid_constant__ EstArgs a) {
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
   lrr_phase_match(lrr_scope(a, dir), a.d[dir], a.flags, sh);
 }
+__global__ void __launch_bounds__(LRR_THREADS) k_match_hard(const __grid_constant__ EstArgs a) {
+  __shared__ PhaseShared sh;
+  const int dir = blockIdx.y;
+  lrr_phase_match_hard(lrr_scope(a, dir), a.d[dir], a.flags, sh);
+}
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   dim3 grid(nblk_for(maxM(a)), a.ndir);
   k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+  // queue length is only known on the device: a fixed grid of warps strides over it
+  dim3 gridb(nblk_for(std::min<long long>(32LL * maxM(a), (long long)lrr_num_sms() * 4 * LRR_THREADS)), a.ndir);
+  k_match_hard<<<gridb, LRR_THREADS, 0, st>>>(a); ++*launches;
 }
 
 __global__ void __launch_bounds__(LRR_THREADS) k_norm1(const __grid_constant__ EstArgs a) {

@@ -95,6 +95,7 @@ struct DirArgs {
   const int* forig;      // n_in: index in the parent *_all set
   int n_in;
   const int* order;      // n_in or null (identity): position k -> compact index
+  const int* proc;       // n_in or null: match positions in spatially coherent processing order (only when M == n_in)
   int M;                 // number_points_: matches in use
   // to side
   FsetDev to;
@@ -104,6 +105,9 @@ struct DirArgs {
   double *w, *r2, *gkey, *skey;
   unsigned long long* stamp;   // n_to: (epoch, match position) of the representative match of a to-feature
   unsigned long long tag;      // epoch tag of the current matches (high bits)
+  // queue of the queries the 27-cell pass could not finish (pass B, one warp per query)
+  int* hq_k; double* hq_best; int* hq_s; int* hq_o; int* hq_count;
+  int* prev_s;                 // n_in: neighbour slot of each from-feature in its last match (-1: none) = search candidate
   Scal* sc;
 };
 
@@ -142,10 +146,11 @@ cudaError_t lrr_nn_query(const GridDev& g, int64_t nq, const double* qx, const d
 int lrr_num_sms();
 
 // ---- ICP kernels (lrr_icp.cu) ----------------------------------------------------------------------
+void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* mark /* from_all.n ints scratch */, int* proc, cudaStream_t st, long long* launches);
 void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long long* launches);
 void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,
                        cudaStream_t st, long long* launches);
-void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // pass A + pass B
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches);

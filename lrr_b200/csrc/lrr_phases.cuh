@@ -35,6 +35,26 @@ __device__ __forceinline__ void lrr_ld_P6(const double* __restrict__ rec, int s,
 
 // ---- MATCH: find_closest_euclidean (cdcl :541-654, rrl :494-571) fused with the residuals of
 // RMS_error (cdcl :196-230) and the first normalisation sum (cdcl :1159-1190) ---------------------------
+// residual, stamp and sums of one finished match
+__device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, int k, int i, double x, double y, double z, double yx,
+                                                 double yy, double yz, int s, double (&acc)[4]) {
+  a.sidx[k] = s;
+  a.prev_s[i] = s;   // candidate of this from-feature for the next find_closest
+  double r2 = 0.0;
+  if (s >= 0) {
+    const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
+    double P[6]; lrr_ld_P6(a.to.rec, s, P);
+    r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
+    atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
+  }
+  a.r2[k] = r2;
+  a.w[k] = 1.0;   // cdcl :645
+  if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
+  acc[3] += r2;
+}
+
+// pass A: one thread per query, ball scan bounded by the previous neighbour of the same from-feature;
+// queries without a candidate or with a large ball go to the direction's queue
 template <class Scope>
 __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, PhaseShared& sh) {
   Scal* sc = a.sc;
@@ -44,30 +64,66 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
 #pragma unroll
   for (int i = 0; i < 3; ++i) { t[i] = sc->t[i]; c[i] = sc->c[i]; }
   const bool rigid = (flags & LRR_F_RIGID) != 0;
+  const GridDev& g = a.to.grid;
   double acc[4] = {0, 0, 0, 0};
-  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+  const int* __restrict__ proc = (a.proc && a.M == a.n_in) ? a.proc : nullptr;
+  for (int tq = scope.first(); tq < a.M; tq += scope.stride()) {
+    const int k = proc ? __ldg(proc + tq) : tq;
     const int i = lrr_from_index(a, k);
     const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
     double yx, yy, yz;
     lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
-    const int s = lrr_nn_search(a.to.grid, yx, yy, yz);
-    a.sidx[k] = s;
-    double r2 = 0.0;
-    if (s >= 0) {
-      const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
-      double P[6]; lrr_ld_P6(a.to.rec, s, P);
-      r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
-      atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
+    NNState st; st.best = 1e300; st.best_s = a.prev_s[i]; st.best_o = 0x7fffffff;
+    bool done = false;
+    if (st.best_s >= 0) {
+      const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
+      st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
+      done = lrr_nn_ball_thread(g, yx, yy, yz, st);
     }
-    a.r2[k] = r2;
-    a.w[k] = 1.0;   // cdcl :645
-    if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
-    acc[3] += r2;
+    if (done) lrr_match_finish(a, rigid, k, i, x, y, z, yx, yy, yz, st.best_s, acc);
+    else {
+      const int slot = atomicAdd(a.hq_count, 1);
+      a.hq_k[slot] = k; a.hq_best[slot] = st.best; a.hq_s[slot] = st.best_s; a.hq_o[slot] = st.best_o;
+    }
   }
   if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
     if (threadIdx.x == 0) {
       sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
-      sc->res_sum_r2 = sh.out[3]; sc->res_count = (double)a.M;
+    }
+  }
+  scope.phase_end();
+}
+
+// pass B: one warp per queued query, shells 2.. ; adds its sums to the direction's scalars
+template <class Scope>
+__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, PhaseShared& sh) {
+  Scal* sc = a.sc;
+  double A[9], t[3], c[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = sc->A[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { t[i] = sc->t[i]; c[i] = sc->c[i]; }
+  const bool rigid = (flags & LRR_F_RIGID) != 0;
+  const int lane = threadIdx.x & 31;
+  const int nq = *a.hq_count;
+  const GridDev& g = a.to.grid;
+  double acc[4] = {0, 0, 0, 0};
+  for (int qi = scope.first() >> 5; qi < nq; qi += scope.stride() >> 5) {
+    const int kq = a.hq_k[qi];
+    const int i = lrr_from_index(a, kq);
+    const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
+    double yx, yy, yz;
+    lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
+    NNState st; st.best = a.hq_best[qi]; st.best_s = a.hq_s[qi]; st.best_o = a.hq_o[qi];
+    const int s = lrr_nn_pass_b(g, yx, yy, yz, st);
+    if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc);
+  }
+  if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) {
+      const double s0 = sc->sum_loc[0] + sh.out[0], s1 = sc->sum_loc[1] + sh.out[1], s2 = sc->sum_loc[2] + sh.out[2], s3 = sc->sum_r2 + sh.out[3];
+      sc->sum_loc[0] = s0; sc->sum_loc[1] = s1; sc->sum_loc[2] = s2; sc->sum_r2 = s3;
+      sc->res_sum_r2 = s3; sc->res_count = (double)a.M;
+      *a.hq_count = 0;
       if (rigid) {   // make_incremental: the matches' from_ are now clones mapped through the current transform
         for (int i = 0; i < 9; ++i) sc->Ag[i] = sc->A[i];
         for (int i = 0; i < 3; ++i) { sc->tg[i] = sc->t[i]; sc->cg[i] = sc->c[i]; }

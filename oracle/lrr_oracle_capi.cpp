@@ -344,3 +344,7 @@ int lrro_test_dense_normal_equations(lrro_est* e, int d, double* AtA, double* At
 int lrro_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"
+extern "C" {
+int lrro_ctx_set_profiling(lrro_ctx*, int) { return LRR_OK; }
+int lrro_ctx_phase_times(lrro_ctx*, int cap, double* ms, int64_t* count) { for (int i = 0; i < cap; ++i) { ms[i] = 0; count[i] = 0; } return LRR_OK; }
+}

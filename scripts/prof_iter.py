@@ -1,0 +1,25 @@
+"""Short driver for ncu: ramp the C3 workload to the finest level, then run a few finest-level iterations."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from lrr_b200 import synth, lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+extra = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+kind = sys.argv[3] if len(sys.argv) > 3 else "rrl_sym"
+pair = synth.make_pair(3, n, n)
+ctx = lib().context(0)
+fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+est = ctx.estimator(kind, mv, fx, 12)
+A, t, c = pair["init"]
+est.set_transform(A, t, c)
+if "fwd" in kind:
+    est.set_flags(True, True); est.set_number_points(n)
+it, conv = 0, False
+while not conv and it < 70:
+    conv = est.one_iteration(it); it += 1
+print("ramp iterations", it, "converged", conv, "launches", ctx.launch_count())
+ctx.set_profiling(True)
+for k in range(extra):
+    est.one_iteration(it + k)
+print({k: (round(1e3 * v[0] / v[1], 2), v[1]) for k, v in ctx.phase_times().items()})
+print("launches", ctx.launch_count())
