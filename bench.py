@@ -67,7 +67,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -216,11 +216,11 @@ def run_b200(args, rank, world, local_rank):
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
         it_no = ramp_iters
+        sampler = ClockSampler(local_rank); sampler.start()
         for _ in range(max(3, args.warmup)):
             est.one_iteration(it_no); it_no += 1
 
         # ---- timed region 1: K iterations, L2 flushed between iterations, CUDA events on the launching stream ----
-        sampler = ClockSampler(local_rank); sampler.start()
         barrier()
         launches0 = ctx.launch_count()
         evs = []
@@ -233,7 +233,6 @@ def run_b200(args, rank, world, local_rank):
             evs.append((a, b))
         barrier()
         launches = ctx.launch_count() - launches0
-        clocks = sampler.stop()
         ms_iters = np.array([a.elapsed_time(b) for a, b in evs])
         total_ms = float(ms_iters.sum())
 
@@ -254,6 +253,7 @@ def run_b200(args, rank, world, local_rank):
             est.one_iteration(it_no); it_no += 1
         phases = ctx.phase_times()
         ctx.set_profiling(False)
+        clocks = sampler.stop()   # sampled across warm-up, both timed regions and the per-kernel pass
         final = est.get_transform(0)
 
     tm = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
@@ -273,13 +273,20 @@ def run_b200(args, rank, world, local_rank):
         t_start = time.perf_counter()
         e2e_iters = 0
         for _ in range(e2e_steps):
-            fx2, mv2 = ctx.upload({k: v for k, v in pf.items() if not k.startswith("_keep_")}), ctx.upload({k: v for k, v in pm.items() if not k.startswith("_keep_")})
+            ta = time.perf_counter()
+            fx2 = ctx.upload({k: v for k, v in pf.items() if not k.startswith("_keep_")})
+            mv2 = ctx.upload({k: v for k, v in pm.items() if not k.startswith("_keep_")})
+            tb = time.perf_counter()
             est2 = ctx.estimator("rrl_sym", mv2, fx2, 12)
             est2.set_transform(A0, t0_, c0)
+            tc = time.perf_counter()
             n_it, _ = ramp_to_finest(est2)
             est2.get_transform(0)
+            td = time.perf_counter()
             e2e_iters += n_it
             est2.close(); fx2.close(); mv2.close()
+            te_ = time.perf_counter()
+            print(f"[e2e] upload {tb - ta:.4f} est {tc - tb:.4f} run {td - tc:.4f} ({n_it} its) close {te_ - td:.4f}", file=sys.stderr)
         barrier()
         e2e_s = time.perf_counter() - t_start
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

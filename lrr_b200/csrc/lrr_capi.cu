@@ -19,7 +19,12 @@
     if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return LRR_ERR_CUDA; } \
   } while (0)
 
-template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
+// Stream-ordered, pooled device memory: estimators and feature sets come and go per registration, and plain
+// cudaFree costs milliseconds (implicit device synchronisation + unmapping).
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+static void enter(lrr_ctx* ctx) { cudaSetDevice(ctx->device); g_alloc_stream = ctx->stream; }
+template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), g_alloc_stream); }
+static void dfree(void* p) { if (p) cudaFreeAsync(p, g_alloc_stream); }
 
 // ---- instrumentation ------------------------------------------------------------------------------------
 struct PhaseTimer {
@@ -42,7 +47,7 @@ static void drain_spans(lrr_ctx* ctx) {
 }
 extern "C" int lrr_ctx_set_profiling(lrr_ctx* ctx, int enable) {
   if (!ctx) return LRR_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  enter(ctx);
   drain_spans(ctx);
   ctx->profiling = enable != 0;
   for (int i = 0; i < LRR_NPHASE; ++i) { ctx->phase_ms[i] = 0; ctx->phase_count[i] = 0; }
@@ -50,7 +55,7 @@ extern "C" int lrr_ctx_set_profiling(lrr_ctx* ctx, int enable) {
 }
 extern "C" int lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count) {
   if (!ctx || !ms || !count) return LRR_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  enter(ctx);
   drain_spans(ctx);
   for (int i = 0; i < cap && i < LRR_NPHASE; ++i) { ms[i] = ctx->phase_ms[i]; count[i] = ctx->phase_count[i]; }
   return LRR_OK;
@@ -66,6 +71,11 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LRR_ERR_CUDA; }
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
+  {
+    cudaMemPool_t pool; unsigned long long thr = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    g_alloc_stream = ctx->own_stream;
+  }
   ok = ok && dmalloc(&ctx->partials, (size_t)2 * LRR_MAX_BLOCKS * LRR_NRED) == cudaSuccess;
   ok = ok && dmalloc(&ctx->ticket, 8) == cudaSuccess;
   ok = ok && cudaMemset(ctx->ticket, 0, 8 * sizeof(unsigned int)) == cudaSuccess;
@@ -95,23 +105,23 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
 }
 extern "C" void lrr_ctx_destroy(lrr_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  cudaFree(ctx->partials); cudaFree(ctx->ticket); cudaFree(ctx->sel_hist); cudaFree(ctx->sel_cand); cudaFree(ctx->sel_misc);
-  cudaFree(ctx->muse_table); cudaFree(ctx->scratch_d); cudaFree(ctx->sort_keys);
+  enter(ctx);
+  dfree(ctx->partials); dfree(ctx->ticket); dfree(ctx->sel_hist); dfree(ctx->sel_cand); dfree(ctx->sel_misc);
+  dfree(ctx->muse_table); dfree(ctx->scratch_d); dfree(ctx->sort_keys);
   if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 extern "C" int lrr_ctx_set_stream(lrr_ctx* ctx, void* s) { if (!ctx) return LRR_ERR_INVALID; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return LRR_OK; }
-extern "C" int lrr_ctx_synchronize(lrr_ctx* ctx) { if (!ctx) return LRR_ERR_INVALID; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return LRR_OK; }
+extern "C" int lrr_ctx_synchronize(lrr_ctx* ctx) { if (!ctx) return LRR_ERR_INVALID; enter(ctx); CK(cudaStreamSynchronize(ctx->stream)); return LRR_OK; }
 extern "C" const char* lrr_ctx_last_error(lrr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int64_t lrr_ctx_launch_count(lrr_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
 
 int lrr_ctx_need_sort(lrr_ctx* ctx, size_t n) {
   if (ctx->sort.cap >= n && ctx->sort_keys) return LRR_OK;
   if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
-  cudaFree(ctx->sort_keys); ctx->sort_keys = nullptr;
+  dfree(ctx->sort_keys); ctx->sort_keys = nullptr;
   CK(lrr_sort_alloc(&ctx->sort, n));
   CK(dmalloc(&ctx->sort_keys, n));
   return LRR_OK;
@@ -121,7 +131,7 @@ int lrr_ctx_need_sort(lrr_ctx* ctx, size_t n) {
 extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6, const double* strength,
                                    const uint8_t* shape, const double* dirs, lrr_fset** out) {
   if (!ctx || n < 0 || n > 0x7fffff00LL || !out || (n > 0 && (!xyz || !P6))) return LRR_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  enter(ctx);
   lrr_fset* fs = new lrr_fset(); fs->ctx = ctx; fs->n = n;
   std::vector<double> zeros; std::vector<uint8_t> zshape;
   if (!strength) { zeros.assign((size_t)n, 0.0); strength = zeros.data(); }
@@ -153,16 +163,16 @@ extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, c
 }
 extern "C" void lrr_features_destroy(lrr_fset* fs) {
   if (!fs) return;
-  cudaSetDevice(fs->ctx->device);
-  cudaFree(fs->xyz); cudaFree(fs->s); cudaFree(fs->P6); cudaFree(fs->C6); cudaFree(fs->dirs); cudaFree(fs->shape);
-  cudaFree(fs->pos4); cudaFree(fs->rec); cudaFree(fs->sorted_of_orig); cudaFree(fs->cell_start);
+  enter(fs->ctx);
+  dfree(fs->xyz); dfree(fs->s); dfree(fs->P6); dfree(fs->C6); dfree(fs->dirs); dfree(fs->shape);
+  dfree(fs->pos4); dfree(fs->rec); dfree(fs->sorted_of_orig); dfree(fs->cell_start);
   delete fs;
 }
 extern "C" int64_t lrr_features_size(const lrr_fset* fs) { return fs ? fs->n : 0; }
 extern "C" int lrr_features_nearest(lrr_fset* fs, int64_t nq, const double* q, int32_t* idx) {
   if (!fs || nq < 0 || (nq > 0 && (!q || !idx))) return LRR_ERR_INVALID;
   lrr_ctx* ctx = fs->ctx;
-  cudaSetDevice(ctx->device);
+  enter(ctx);
   if (nq == 0) return LRR_OK;
   double* dq = nullptr; int* di = nullptr;
   CK(dmalloc(&dq, (size_t)3 * nq)); CK(dmalloc(&di, (size_t)nq));
@@ -171,7 +181,7 @@ extern "C" int lrr_features_nearest(lrr_fset* fs, int64_t nq, const double* q, i
   CK(lrr_nn_query(fs->dev.grid, nq, dq, dq + nq, dq + 2 * nq, di, st, &ctx->launches));
   CK(cudaMemcpyAsync(idx, di, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  cudaFree(dq); cudaFree(di);
+  dfree(dq); dfree(di);
   return LRR_OK;
 }
 
@@ -200,7 +210,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
   return LRR_OK;
 }
 static void dir_free(lrr_dir& d) {
-  cudaFree(d.fx); cudaFree(d.fP6); cudaFree(d.forig); cudaFree(d.order); cudaFree(d.sidx); cudaFree(d.w); cudaFree(d.stamp); cudaFree(d.sc); cudaFree(d.hq_k); cudaFree(d.hq_best); cudaFree(d.prev_s); cudaFree(d.proc); cudaFree(d.proc_mark);
+  dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark);
 }
 static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
   if (n < 0 || (size_t)n > d.cap) return LRR_ERR_INVALID;
@@ -219,7 +229,6 @@ static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t 
   d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false;
   CK(cudaMemsetAsync(d.prev_s, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));   // no search candidates yet
   lrr_k_build_proc(d.from_all->dev, d.subset ? d.forig : nullptr, (int)n, d.proc_mark, d.proc, st, &ctx->launches);
-  d.host_order.clear();
   return LRR_OK;
 }
 
@@ -229,11 +238,13 @@ static DirArgs dir_args(const lrr_dir& d) {
   a.fx = d.fx; a.fy = d.fx + n; a.fz = d.fx + 2 * n; a.fs = d.fx + 3 * n;   // compact arrays are packed at stride n_in
   a.fP6 = d.fP6; a.forig = d.subset ? d.forig : nullptr; a.n_in = (int)d.n_in;
   a.order = d.has_order ? d.order : nullptr;
+  for (int r = 0; r < 4; ++r) a.perm_key[r] = d.perm_key[r];
+  a.perm_half = d.has_order ? 0 : d.perm_half;
   a.M = (int)std::min<int64_t>(d.number_points, d.n_in);
   a.to = d.to_all->dev; a.from_all = d.from_all->dev;
   a.sidx = d.sidx; a.w = d.w; a.r2 = d.r2; a.gkey = d.gkey; a.skey = d.skey;
   a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
-  a.prev_s = d.prev_s; a.proc = d.has_order ? nullptr : d.proc; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
+  a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
   return a;
 }
@@ -294,7 +305,7 @@ extern "C" int lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset
   if (dim != 3 || (dof != 12 && dof != 6)) return LRR_ERR_UNSUPPORTED;
   if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;   // Q6
   if (kind < 0 || kind > 3) return LRR_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  enter(ctx);
   lrr_est* e = new lrr_est();
   e->ctx = ctx; e->kind = kind; e->dof = dof; e->moving_all = moving_all; e->fixed_all = fixed_all;
   e->normalize = e->sym(); e->strength = e->sym();   // the symmetric ctor switches both on (cdcl sym :151-156)
@@ -318,7 +329,7 @@ extern "C" int lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset
 }
 extern "C" void lrr_est_destroy(lrr_est* e) {
   if (!e) return;
-  cudaSetDevice(e->ctx->device);
+  enter(e->ctx);
   cudaStreamSynchronize(e->ctx->stream);
   dir_free(e->d[0]); if (e->sym()) dir_free(e->d[1]);
   delete e;
@@ -326,7 +337,7 @@ extern "C" void lrr_est_destroy(lrr_est* e) {
 
 extern "C" int lrr_est_set_subsets(lrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
   if (!e || !mi || nm < 0) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   int rc = dir_set_subset(ctx, e->d[0], mi, nm);
   if (rc != LRR_OK) return rc;
   if (e->sym()) {
@@ -346,7 +357,7 @@ static void set_identity_norm(Scal& s) {
 extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
   if (!e || !A9 || !t3) return LRR_ERR_INVALID;
   if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12)) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
   Scal& f = e->h[0];
   memcpy(f.A, A9, 72); memcpy(f.t, t3, 24);
@@ -374,7 +385,7 @@ extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const
 
 extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
   if (!e) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   e->normalize = normalize != 0; e->strength = wbs != 0;
   if (!e->normalize) {
     int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
@@ -385,20 +396,20 @@ extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
 
 extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64_t n) {
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   if (!perm) { d.has_order = false; return LRR_OK; }
   if (n != d.n_in) return LRR_ERR_INVALID;
   for (int64_t i = 0; i < n; ++i) if (perm[i] < 0 || perm[i] >= n) return LRR_ERR_INVALID;
   CK(cudaMemcpyAsync(d.order, perm, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  d.has_order = true;
+  d.has_order = true; d.perm_half = 0;
   return LRR_OK;
 }
 extern "C" int lrr_est_set_shuffle(lrr_est* e, int mode, uint64_t seed) {
   if (!e || (mode != LRR_ORDER_FIXED && mode != LRR_ORDER_RESHUFFLE)) return LRR_ERR_INVALID;
   e->shuffle_mode = mode; e->seed = seed;
-  for (int d = 0; d < 2; ++d) e->d[d].shuffle_calls = 0;
+  for (int d = 0; d < 2; ++d) { e->d[d].shuffle_calls = 0; e->d[d].perm_half = 0; }
   return LRR_OK;
 }
 extern "C" int lrr_est_set_initial_scale(lrr_est* e, int dir, double s) {
@@ -457,14 +468,15 @@ static inline uint64_t splitmix64(uint64_t& s) {
 }
 
 static int apply_shuffle(lrr_est* e, int dir) {
-  lrr_ctx* ctx = e->ctx; lrr_dir& d = e->d[dir];
-  if (e->shuffle_mode != LRR_ORDER_RESHUFFLE) return LRR_OK;
-  // Fisher-Yates with SplitMix64, applied cumulatively to the order vector — same spec as the oracle
-  if ((int64_t)d.host_order.size() != d.n_in) { d.host_order.resize((size_t)d.n_in); for (int64_t i = 0; i < d.n_in; ++i) d.host_order[(size_t)i] = (int32_t)i; d.shuffle_calls = 0; d.rng_state = e->seed + (uint64_t)dir * 0x632BE59BD9B4E019ULL; }
-  for (size_t i = d.host_order.size(); i > 1; --i) { size_t j = (size_t)(splitmix64(d.rng_state) % (uint64_t)i); std::swap(d.host_order[i - 1], d.host_order[j]); }
-  CK(cudaMemcpyAsync(d.order, d.host_order.data(), sizeof(int) * d.n_in, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  d.has_order = true;
+  lrr_dir& d = e->d[dir];
+  if (e->shuffle_mode != LRR_ORDER_RESHUFFLE) { d.perm_half = 0; return LRR_OK; }
+  uint64_t st = e->seed + (uint64_t)dir * 0x632BE59BD9B4E019ULL + d.shuffle_calls * 0xD1342543DE82EF95ULL;
+  d.shuffle_calls += 1;
+  for (int r = 0; r < 4; ++r) d.perm_key[r] = (unsigned int)(splitmix64(st) >> 32);
+  int bits = 2; while ((1ull << bits) < (uint64_t)d.n_in) ++bits;
+  if (bits & 1) ++bits;
+  d.perm_half = bits / 2;
+  d.has_order = false;
   return LRR_OK;
 }
 
@@ -552,7 +564,7 @@ static double werr_of(const Scal& s) { return s.res_sum_w != 0 ? s.res_sum_wr / 
 
 extern "C" int lrr_est_find_closest(lrr_est* e) {
   if (!e) return LRR_ERR_INVALID;
-  cudaSetDevice(e->ctx->device);
+  enter(e->ctx);
   return do_find_closest(e);
 }
 
@@ -629,7 +641,7 @@ static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out)
 
 extern "C" int lrr_est_one_iteration(lrr_est* e, unsigned iteration, int* converged) {
   if (!e) return LRR_ERR_INVALID;
-  cudaSetDevice(e->ctx->device);
+  enter(e->ctx);
   int c = 0;
   int rc = e->sym() ? one_iteration_sym(e, iteration, &c) : one_iteration_fwd(e, &c);
   if (converged) *converged = c;
@@ -646,7 +658,7 @@ extern "C" int lrr_est_run(lrr_est* e, int max_iter, int* converged, int* iterat
 
 extern "C" int lrr_est_get_transform(lrr_est* e, int dir, int* tk, double* A9, double* t3, double* c3, double* cov) {
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
-  cudaSetDevice(e->ctx->device);
+  enter(e->ctx);
   int rc = pull_scal(e, 1 << dir); if (rc != LRR_OK) return rc;
   const Scal& s = e->h[dir];
   if (tk) *tk = e->dof == 12 ? LRR_TRANS_AFFINE : LRR_TRANS_RIGID3D;
@@ -657,7 +669,7 @@ extern "C" int lrr_est_get_transform(lrr_est* e, int dir, int* tk, double* A9, d
 
 extern "C" int lrr_est_get_matches(lrr_est* e, int dir, int64_t cap, int64_t* n, int32_t* from_idx, int32_t* to_idx, double* w) {
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   const int64_t m = d.matches;
   if (n) *n = m;
@@ -672,13 +684,13 @@ extern "C" int lrr_est_get_matches(lrr_est* e, int dir, int64_t cap, int64_t* n,
   if (to_idx) CK(cudaMemcpyAsync(to_idx, tmp + m, sizeof(int) * c, cudaMemcpyDeviceToHost, ctx->stream));
   if (w) CK(cudaMemcpyAsync(w, d.w, sizeof(double) * c, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(tmp);
+  dfree(tmp);
   return LRR_OK;
 }
 
 extern "C" int lrr_est_metric(lrr_est* e, int which, int dir, double* out) {
   if (!e || !out || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   EstArgs a = est_args(e);
   a.d[dir].M = (int)d.matches;   // metrics run over the existing matches
@@ -721,7 +733,7 @@ extern "C" int lrr_est_metric(lrr_est* e, int which, int dir, double* out) {
 
 extern "C" int lrr_est_estimate_ls_backward(lrr_est* e, int estimate_parameters) {
   if (!e || !e->sym()) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   if (e->kind == LRR_CDCL_SYM) { ctx->err = "estimate_LS_backward: cdcl symmetric variant not built yet (rrl only)"; return LRR_ERR_UNSUPPORTED; }
   // rrl: swap forward_/backward_, estimate_LS, swap back (rrl sym :922-934)
   int rc = do_estimate(e, 1, estimate_parameters); if (rc != LRR_OK) return rc;
@@ -732,7 +744,7 @@ extern "C" int lrr_est_estimate_ls_backward(lrr_est* e, int estimate_parameters)
 // compute_transfer_error_covariance: covarJ = mean_i J_i Sigma J_i^T  (cdcl :388-404, rrl :381-397)
 extern "C" int lrr_est_transfer_cov(lrr_est* e, int dir, double* S9) {
   if (!e || !S9 || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
-  lrr_ctx* ctx = e->ctx; cudaSetDevice(ctx->device);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   if (d.matches <= 0) { ctx->err = "transfer covariance without matches"; return LRR_ERR_STATE; }
   EstArgs a = est_args(e);
@@ -766,7 +778,7 @@ extern "C" int lrr_est_transfer_cov(lrr_est* e, int dir, double* S9) {
 
 extern "C" int lrr_est_get_state(lrr_est* e, lrr_est_state* s) {
   if (!e || !s) return LRR_ERR_INVALID;
-  cudaSetDevice(e->ctx->device);
+  enter(e->ctx);
   int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
   memset(s, 0, sizeof(*s));
   const int nd = e->sym() ? 2 : 1;

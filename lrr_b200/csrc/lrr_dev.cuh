@@ -281,13 +281,35 @@ struct GridScope {
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    // one warp per value: lanes stride over the block rows (independent loads in flight), fixed shuffle tree
-    for (int k = wid; k < KG; k += nw) {
-      double s = 0;
-      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
+    if (KG <= 32) {
+      // one warp per value: lanes stride over the block rows (independent loads in flight), fixed shuffle tree
+      for (int k = wid; k < KG; k += nw) {
+        double s = 0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) sh_out[k] = s;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sh_out[k] = s;
+      }
+    } else {
+      // many values: lanes own values (coalesced rows), warps own interleaved rows, fixed-order combine
+      constexpr int KL = (KG + 31) / 32;
+      double s[KL];
+#pragma unroll
+      for (int j = 0; j < KL; ++j) s[j] = 0;
+#pragma unroll 4
+      for (unsigned int b = wid; b < gridDim.x; b += nw) {
+#pragma unroll
+        for (int j = 0; j < KL; ++j) { const int k = lane + 32 * j; if (k < KG) s[j] += __ldcg(&partials[(size_t)b * LRR_NRED + k]); }
+      }
+      __syncthreads();   // sh_tmp is free again
+#pragma unroll
+      for (int j = 0; j < KL; ++j) { const int k = lane + 32 * j; if (k < KG) sh_tmp[wid * KG + k] = s[j]; }
+      __syncthreads();
+      for (int k = threadIdx.x; k < KG; k += blockDim.x) {
+        double t = 0;
+        for (int w = 0; w < nw; ++w) t += sh_tmp[w * KG + k];
+        sh_out[k] = t;
+      }
     }
     __syncthreads();
     return true;

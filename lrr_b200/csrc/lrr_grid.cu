@@ -120,16 +120,16 @@ cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches) 
   cudaError_t e;
   if (n == 0) {
     g.ox = g.oy = g.oz = 0; g.h = 1; g.inv_h = 1; g.nx = g.ny = g.nz = 1;
-    if ((e = cudaMalloc(&fb->cell_start, 2 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync((void**)&fb->cell_start, 2 * sizeof(int), st)) != cudaSuccess) return e;
     cudaMemsetAsync(fb->cell_start, 0, 2 * sizeof(int), st);
     g.cell_start = fb->cell_start; g.pos4 = nullptr;
     return cudaSuccess;
   }
-  if ((e = cudaMalloc(&d_part, 64 * 6 * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&d_part, 64 * 6 * sizeof(double), st)) != cudaSuccess) return e;
   k_bbox<<<64, 256, 0, st>>>(fb->x, fb->y, fb->z, n, d_part); ++*launches;
   if ((e = cudaMemcpyAsync(h_part, d_part, sizeof(h_part), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-  cudaFree(d_part);
+  cudaFreeAsync(d_part, st);
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int b = 0; b < 64; ++b) for (int d = 0; d < 3; ++d) { mn[d] = fmin(mn[d], h_part[b * 6 + d]); mx[d] = fmax(mx[d], h_part[b * 6 + 3 + d]); }
   double ext[3]; double vol = 1.0; double maxext = 0;
@@ -151,10 +151,10 @@ cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches) 
   g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.h = h; g.inv_h = 1.0 / h; g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
   const int ncell = (int)(nx * ny * nz);
   int *cell_of = nullptr, *counts = nullptr, *gorig = nullptr;
-  if ((e = cudaMalloc(&fb->cell_start, (size_t)(ncell + 1) * sizeof(int))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&cell_of, (size_t)n * sizeof(int))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&counts, (size_t)ncell * sizeof(int))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&gorig, (size_t)n * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&fb->cell_start, (size_t)(ncell + 1) * sizeof(int), st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&cell_of, (size_t)n * sizeof(int), st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&counts, (size_t)ncell * sizeof(int), st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&gorig, (size_t)n * sizeof(int), st)) != cudaSuccess) return e;
   cudaMemsetAsync(counts, 0, (size_t)ncell * sizeof(int), st);
   const int T = 256, B = (n + T - 1) / T;
   k_cell_count<<<B, T, 0, st>>>(fb->x, fb->y, fb->z, n, g, cell_of, counts); ++*launches;
@@ -164,7 +164,7 @@ cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches) 
   k_cell_sort<<<(ncell + T - 1) / T, T, 0, st>>>(fb->cell_start, ncell, gorig); ++*launches;
   k_fill_pos<<<B, T, 0, st>>>(fb->x, fb->y, fb->z, n, gorig, fb->pos4, fb->sorted_of_orig); ++*launches;
   e = cudaStreamSynchronize(st);
-  cudaFree(cell_of); cudaFree(counts); cudaFree(gorig);
+  cudaFreeAsync(cell_of, st); cudaFreeAsync(counts, st); cudaFreeAsync(gorig, st);
   g.cell_start = fb->cell_start; g.pos4 = fb->pos4;
   return e != cudaSuccess ? e : cudaGetLastError();
 }

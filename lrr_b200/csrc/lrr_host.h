@@ -52,8 +52,8 @@ struct lrr_dir {
   unsigned int epoch = 0;
   bool subset = false, has_order = false, scale_estimated = false, weights_fresh = false;
   double initial_scale = 0;
-  std::vector<int32_t> host_order;   // RESHUFFLE bookkeeping
-  uint64_t shuffle_calls = 0, rng_state = 0;
+  uint64_t shuffle_calls = 0;        // RESHUFFLE: find_closest calls so far (selects the permutation key)
+  unsigned int perm_key[4] = {0, 0, 0, 0}; int perm_half = 0;
 };
 
 struct lrr_est {

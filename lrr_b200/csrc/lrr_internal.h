@@ -95,6 +95,7 @@ struct DirArgs {
   const int* forig;      // n_in: index in the parent *_all set
   int n_in;
   const int* order;      // n_in or null (identity): position k -> compact index
+  unsigned int perm_key[4]; int perm_half;   // RESHUFFLE: keyed Feistel permutation of [0,n_in) (perm_half = 0: off)
   const int* proc;       // n_in or null: match positions in spatially coherent processing order (only when M == n_in)
   int M;                 // number_points_: matches in use
   // to side

@@ -17,7 +17,26 @@ struct PhaseShared {
   double tmp[LRR_NRED * LRR_NWARPS];
 };
 
-__device__ __forceinline__ int lrr_from_index(const DirArgs& a, int k) { return a.order ? __ldg(a.order + k) : k; }
+// position k of the (possibly permuted) moving vector -> compact index.  RESHUFFLE = keyed 4-round Feistel
+// permutation with cycle walking, evaluated on the fly (the stand-in for vcl_random_shuffle, Q4).
+__device__ __forceinline__ int lrr_from_index(const DirArgs& a, int k) {
+  if (a.order) return __ldg(a.order + k);
+  if (a.perm_half == 0) return k;
+  const unsigned int hmask = (1u << a.perm_half) - 1u, n = (unsigned int)a.n_in;
+  unsigned int x = (unsigned int)k;
+  do {
+    unsigned int L = x >> a.perm_half, R = x & hmask;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      unsigned int F = R * 0x9E3779B1u + a.perm_key[r];
+      F ^= F >> 15; F *= 0x85EBCA6Bu; F ^= F >> 13;
+      F &= hmask;
+      const unsigned int nl = R; R = L ^ F; L = nl;
+    }
+    x = (L << a.perm_half) | R;
+  } while (x >= n);
+  return (int)x;
+}
 
 // location of the match's from_ feature: the original, or — while a rigid increment is being estimated —
 // the clone mapped through the previous global transform (cdcl :455-484)

@@ -13,8 +13,8 @@
 cudaError_t lrr_sort_alloc(SortScratch* s, size_t cap) {
   s->cap = cap;
   cudaError_t e;
-  if ((e = cudaMalloc(&s->keys2, (cap ? cap : 1) * sizeof(double))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&s->hist, 256 * SORT_T * sizeof(unsigned int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc((void**)&s->keys2, (cap ? cap : 1) * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMalloc((void**)&s->hist, 256 * SORT_T * sizeof(unsigned int))) != cudaSuccess) return e;
   return cudaSuccess;
 }
 void lrr_sort_free(SortScratch* s) { cudaFree(s->keys2); cudaFree(s->hist); s->keys2 = nullptr; s->hist = nullptr; }
@@ -57,8 +57,29 @@ __global__ void __launch_bounds__(SORT_T) k_radix_sort(double* __restrict__ keys
   // 8 passes: the result is back in `keys`
 }
 
+// n <= 2048: bitonic sort in shared memory (the MUSE call at the start of every registration: 1000 residuals)
+__global__ void __launch_bounds__(1024) k_bitonic_small(double* __restrict__ keys, int n) {
+  __shared__ double sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = (i < n) ? keys[i] : 1e308;
+  __syncthreads();
+  for (int k = 2; k <= 2048; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const double a = sh[i], b = sh[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { sh[i] = b; sh[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = sh[i];
+}
+
 void lrr_sort_doubles(SortScratch* s, double* keys, int n, cudaStream_t st, long long* launches) {
   if (n <= 1) return;
+  if (n <= 2048) { k_bitonic_small<<<1, 1024, 0, st>>>(keys, n); ++*launches; return; }
   k_radix_sort<<<1, SORT_T, 0, st>>>(keys, s->keys2, s->hist, n); ++*launches;
 }
 

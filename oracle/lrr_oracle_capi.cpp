@@ -41,8 +41,7 @@ static std::vector<FeatureP> clone_subset(const std::vector<Feature>& base, cons
 }
 static void apply_policy(lrro_est* e) {
   for (int d = 0; d < 2; ++d) if (FwdEst* f = e->dir(d)) {
-    f->shuffle_mode = e->shuffle_mode;
-    f->rng = SplitMix64(e->seed + (uint64_t)d * 0x632BE59BD9B4E019ULL);
+    f->shuffle_mode = e->shuffle_mode; f->shuffle_seed = e->seed; f->shuffle_dir = (uint64_t)d; f->shuffle_calls = 0;
   }
 }
 
@@ -263,7 +262,7 @@ static void run_one_job(const lrro_fset* moving_all, const lrro_fset* fixed_all,
   // prebuilt kd-trees are shared: the driver keeps one estimator alive across locations (:1635-1638)
   SymEst est(FLAVOR_RRL, mall, fall, t, t->inverse(), mi, fi, kd_fixed, kd_moving);
   est.forward_->shuffle_mode = est.backward_->shuffle_mode = 1;
-  est.forward_->rng = SplitMix64(seed); est.backward_->rng = SplitMix64(seed + 0x632BE59BD9B4E019ULL);
+  est.forward_->shuffle_seed = est.backward_->shuffle_seed = seed; est.forward_->shuffle_dir = 0; est.backward_->shuffle_dir = 1;
   est.set_transform(t);
   bool converged = false; int it = 0;
   while (!converged && it < max_iter) {                               // :2418

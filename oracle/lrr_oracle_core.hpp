@@ -77,6 +77,34 @@ template <class T> inline void fisher_yates(std::vector<T>& a, SplitMix64& rng) 
     std::swap(a[i - 1], a[j]);
   }
 }
+// RESHUFFLE policy (stand-in for vcl_random_shuffle, Q4): a keyed 4-round Feistel permutation of [0,n) with
+// cycle walking, one fresh key set per find_closest call.  Every element of the permutation can be evaluated
+// independently, which is what a data-parallel backend needs; statistically it plays the role of the
+// reference's unseeded random_shuffle (which subset is used while number_points_ < |moving|).
+struct FeistelPerm {
+  uint32_t key[4]; int half; uint32_t n;
+  FeistelPerm(uint64_t seed, uint64_t dir, uint64_t call, uint32_t n_) : n(n_) {
+    SplitMix64 g(seed + dir * 0x632BE59BD9B4E019ULL + call * 0xD1342543DE82EF95ULL);
+    for (int r = 0; r < 4; ++r) key[r] = (uint32_t)(g.next() >> 32);
+    int bits = 2; while ((1ull << bits) < (uint64_t)n) ++bits;
+    if (bits & 1) ++bits;
+    half = bits / 2;
+  }
+  uint32_t operator()(uint32_t x) const {
+    const uint32_t hmask = (1u << half) - 1u;
+    do {
+      uint32_t L = x >> half, R = x & hmask;
+      for (int r = 0; r < 4; ++r) {
+        uint32_t F = R * 0x9E3779B1u + key[r];
+        F ^= F >> 15; F *= 0x85EBCA6Bu; F ^= F >> 13;
+        F &= hmask;
+        const uint32_t nl = R; R = L ^ F; L = nl;
+      }
+      x = (L << half) | R;
+    } while (x >= n);
+    return x;
+  }
+};
 
 // ----------------------------------------------------------------------------------------------
 // A7/A8 helper: the reference's private copy of rrel_util_median_abs_dev_scale
@@ -447,7 +475,7 @@ struct FwdEst {
   size_t number_points_ = 1000;
   bool normalize_matches_ = false, weight_by_strength_ = false, scale_estimated_ = false;
   // injection points
-  int shuffle_mode = 0; SplitMix64 rng{0};
+  int shuffle_mode = 0; uint64_t shuffle_seed = 0, shuffle_dir = 0, shuffle_calls = 0;
   double initial_scale = std::numeric_limits<double>::quiet_NaN();
   double last_scale = 0;
   double last_norm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cm[3], rm, cf[3], rf
@@ -593,7 +621,10 @@ struct FwdEst {
 
   // find_closest_euclidean (cdcl :541-654; rrl :494-571 with the exact-NN branch, Q5)
   void find_closest_euclidean() {
-    if (shuffle_mode == 1) fisher_yates(moving_, rng);  // vcl_random_shuffle( moving_[res_] )  :557
+    if (shuffle_mode == 1) {   // vcl_random_shuffle( moving_[res_] )  :557
+      FeistelPerm perm(shuffle_seed, shuffle_dir, shuffle_calls++, (uint32_t)moving_base_.size());
+      for (size_t k = 0; k < moving_base_.size(); ++k) moving_[k] = moving_base_[perm((uint32_t)k)];
+    }
     matches_.clear();
     for (size_t i = 0; i < number_points_; ++i) {
       FeatureP p = moving_[i];

@@ -133,3 +133,20 @@ def test_metrics_and_backward(gpu_lib, oracle_lib, pair):
     compare_state(g, o, dirs=(0, 1))
     assert rel(g.transfer_cov(1), o.transfer_cov(1)) < 1e-8
     assert rel(g.transfer_cov(0), o.transfer_cov(0)) < 1e-8
+
+
+def test_reshuffle_policy(gpu_lib, oracle_lib, pair):
+    """Q4: the RESHUFFLE stand-in for vcl_random_shuffle (keyed Feistel permutation) picks the same subsets on both sides."""
+    ests = []
+    for lib in (gpu_lib, oracle_lib):
+        _, e = make_est(lib, pair, "rrl_sym")
+        e.set_shuffle(1, 12345)
+        ests.append(e)
+    g, o = ests
+    for it in range(10):
+        cg, co = g.one_iteration(it), o.one_iteration(it)
+        assert cg == co
+        compare_state(g, o, dirs=(0, 1))
+    gf, _, _ = g.get_matches(0)
+    assert len(set(gf.tolist())) == len(gf)          # a permutation: no feature used twice
+    assert not np.array_equal(gf, np.arange(len(gf)))
