@@ -133,6 +133,7 @@ extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, c
   if (!ctx || n < 0 || n > 0x7fffff00LL || !out || (n > 0 && (!xyz || !P6))) return LRR_ERR_INVALID;
   enter(ctx);
   lrr_fset* fs = new lrr_fset(); fs->ctx = ctx; fs->n = n;
+  fs->host_xyz.assign(xyz, xyz + 3 * n);
   std::vector<double> zeros; std::vector<uint8_t> zshape;
   if (!strength) { zeros.assign((size_t)n, 0.0); strength = zeros.data(); }
   if (!shape) { zshape.assign((size_t)n, 0); shape = zshape.data(); }
@@ -235,7 +236,7 @@ static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t 
 static DirArgs dir_args(const lrr_dir& d) {
   DirArgs a; memset(&a, 0, sizeof(a));
   const size_t n = (size_t)d.n_in;
-  a.fx = d.fx; a.fy = d.fx + n; a.fz = d.fx + 2 * n; a.fs = d.fx + 3 * n;   // compact arrays are packed at stride n_in
+  a.fx = d.fx; a.fy = d.fy; a.fz = d.fz; a.fs = d.fs;
   a.fP6 = d.fP6; a.forig = d.subset ? d.forig : nullptr; a.n_in = (int)d.n_in;
   a.order = d.has_order ? d.order : nullptr;
   for (int r = 0; r < 4; ++r) a.perm_key[r] = d.perm_key[r];
@@ -803,6 +804,55 @@ extern "C" int lrr_est_oscillated(lrr_est* e, int* out) {
 
 extern "C" int lrr_objcov_eval(lrr_est* e, int, const double*, double*, double*) { if (e) e->ctx->err = "objcov not built yet"; return LRR_ERR_UNSUPPORTED; }
 extern "C" int lrr_objcov_refine(lrr_est* e, int, int, double*, double*, int*) { if (e) e->ctx->err = "objcov not built yet"; return LRR_ERR_UNSUPPORTED; }
-extern "C" int lrr_batch_run(lrr_ctx* ctx, lrr_fset*, lrr_fset*, const lrr_job*, int64_t, int, uint64_t, lrr_result*) {
-  if (ctx) ctx->err = "batch not built yet"; return LRR_ERR_UNSUPPORTED;
+// validTransform (rrl/itkLocationRegistration.cxx:2914-2926): singular values of A inside [0.1, 10]
+static bool valid_transform(const double* A) {
+  double U[9], V[9], w[3];
+  lrr_jacobi_svd<3>(3, A, U, w, V);
+  for (int d = 0; d < 3; ++d) if (w[d] > 10.0 || w[d] < 0.1) return false;
+  return true;
+}
+// FeaturesInROIs (rrl/itkLocationRegistration.cxx:1324-1360): indices of the features inside the cube, in order
+static void roi_indices(const lrr_fset* fs, const double* c, double half, std::vector<int32_t>& out) {
+  out.clear();
+  const int64_t n = fs->n; const double* x = fs->host_xyz.data(); const double* y = x + n; const double* z = y + n;
+  const double x0 = c[0] - half, x1 = c[0] + half, y0 = c[1] - half, y1 = c[1] + half, z0 = c[2] - half, z1 = c[2] + half;
+  for (int64_t i = 0; i < n; ++i)
+    if (!(x0 > x[i] || x[i] > x1 || y0 > y[i] || y[i] > y1 || z0 > z[i] || z[i] > z1)) out.push_back((int32_t)i);
+}
+
+// Batched location registration: the outer loops of LocationRegistration::Run (rrl/itkLocationRegistration.cxx:2138,
+// 2230,2332) over one resident volume pair.  One estimator object is reused for every job, like the driver does
+// (:1635-1638: set_features + set_transform).  Jobs are independent; callers shard them across GPUs (one ctx each).
+extern "C" int lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int max_iter,
+                             uint64_t shuffle_seed, lrr_result* out) {
+  if (!ctx || !moving_all || !fixed_all || njobs < 0 || (njobs > 0 && (!jobs || !out))) return LRR_ERR_INVALID;
+  enter(ctx);
+  lrr_est* est = nullptr;
+  int rc = lrr_est_create(ctx, LRR_RRL_SYM, 3, 12, moving_all, fixed_all, &est);
+  if (rc != LRR_OK) return rc;
+  std::vector<int32_t> mi, fi;
+  for (int64_t j = 0; j < njobs && rc == LRR_OK; ++j) {
+    const lrr_job& job = jobs[j]; lrr_result& r = out[j];
+    memset(&r, 0, sizeof(r));
+    roi_indices(fixed_all, job.roi_center_fixed, job.roi_half_size, fi);
+    roi_indices(moving_all, job.roi_center_moving, job.roi_half_size, mi);
+    r.n_moving_inside = (int32_t)mi.size(); r.n_fixed_inside = (int32_t)fi.size();
+    if (mi.size() < 1000 || fi.size() < 1000) { r.status = 1; continue; }   // :1632
+    if ((rc = lrr_est_set_subsets(est, mi.data(), (int64_t)mi.size(), fi.data(), (int64_t)fi.size())) != LRR_OK) break;
+    if ((rc = lrr_est_set_shuffle(est, LRR_ORDER_RESHUFFLE, shuffle_seed + (uint64_t)j)) != LRR_OK) break;
+    if ((rc = lrr_est_set_transform(est, LRR_TRANS_AFFINE, job.A, job.t, job.c, nullptr)) != LRR_OK) break;
+    int converged = 0, it = 0;
+    while (!converged && it < max_iter) {                                   // :2418
+      if ((rc = lrr_est_one_iteration(est, (unsigned)it, &converged)) != LRR_OK) break;
+      ++it;
+      if (!valid_transform(est->h[0].A)) { r.status = 2; break; }           // :2482
+    }
+    if (rc != LRR_OK) break;
+    const Scal& T = est->h[0];
+    r.converged = converged; r.oscillated = est->oscillation_count > 10; r.iterations = it;
+    memcpy(r.A, T.A, 72); memcpy(r.t, T.t, 24); memcpy(r.c, T.c, 24); memcpy(r.cov, T.cov, sizeof(double) * 144);
+    r.rms = rms_of(est, T, true); r.weighted_error = werr_of(T);
+  }
+  lrr_est_destroy(est);
+  return rc;
 }

@@ -36,6 +36,7 @@ struct lrr_fset {
   uint8_t* shape = nullptr;
   double4* pos4 = nullptr; double* rec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
   FsetDev dev;
+  std::vector<double> host_xyz;   // 3 x n copy for host-side ROI selection (FeaturesInROIs)
 };
 
 // one direction (forward_ / backward_) of an estimator

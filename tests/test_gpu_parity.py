@@ -150,3 +150,25 @@ def test_reshuffle_policy(gpu_lib, oracle_lib, pair):
     gf, _, _ = g.get_matches(0)
     assert len(set(gf.tolist())) == len(gf)          # a permutation: no feature used twice
     assert not np.array_equal(gf, np.arange(len(gf)))
+
+
+def test_batch_run(gpu_lib, oracle_lib):
+    """C4 in miniature: jobs over one resident pair, RESHUFFLE subsets, ROI selection, validTransform."""
+    pair = synth.make_pair(4, 30000, 30000, size=110.0)
+    jobs = synth.make_jobs(pair, 3, 3, seed=4)
+    jobs[4]["roi_half_size"] = 3.0          # too few features inside: rejected (status 1)
+    outs = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+        outs.append(ctx.batch_run(mv, fx, jobs, 40, 99))
+    g, o = outs
+    for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"):
+        assert np.array_equal(g[k], o[k]), (k, g[k], o[k])
+    assert g["status"][4] == 1
+    ok = g["status"] == 0
+    assert ok.sum() >= 6
+    for j in np.nonzero(ok)[0]:
+        assert rel(g["A"][j], o["A"][j]) < TOL_PARAM and rel(g["t"][j], o["t"][j]) < TOL_PARAM and rel(g["cov"][j], o["cov"][j]) < TOL_PARAM
+        assert abs(g["weighted_error"][j] - o["weighted_error"][j]) <= 1e-8 * max(1.0, o["weighted_error"][j])
+        assert abs(g["rms"][j] - o["rms"][j]) <= 1e-8 * max(1.0, o["rms"][j])
