@@ -802,8 +802,192 @@ extern "C" int lrr_est_oscillated(lrr_est* e, int* out) {
   return LRR_OK;
 }
 
-extern "C" int lrr_objcov_eval(lrr_est* e, int, const double*, double*, double*) { if (e) e->ctx->err = "objcov not built yet"; return LRR_ERR_UNSUPPORTED; }
-extern "C" int lrr_objcov_refine(lrr_est* e, int, int, double*, double*, int*) { if (e) e->ctx->err = "objcov not built yet"; return LRR_ERR_UNSUPPORTED; }
+// ---- covariance objective (A13) ---------------------------------------------------------------------------
+void lrr_k_objcov_launch(const DirArgs& a, const double* A, const double* t, const double* c, const double* norm8, const double* Sigma_dev,
+                         double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
+
+struct HostTrans { double A[9], t[3], c[3], cov[144]; };
+static void mat_BCBt12(const double* B, const double* C, double* R) {
+  double T[144];
+  for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) { double s = 0; for (int k = 0; k < 12; ++k) s += B[i * 12 + k] * C[k * 12 + j]; T[i * 12 + j] = s; }
+  for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) { double s = 0; for (int k = 0; k < 12; ++k) s += T[i * 12 + k] * B[j * 12 + k]; R[i * 12 + j] = s; }
+}
+// cdcl_trans_affine::normalize / unnormalize (cdcl/cdcl_trans_affine.txx:220-286)
+static void affine_normalize(HostTrans& T, double rm, double rf, const double* cm, const double* cf) {
+  const double s = rm / rf;
+  for (int i = 0; i < 9; ++i) T.A[i] = s * T.A[i];
+  const double dc[3] = {cm[0] - T.c[0], cm[1] - T.c[1], cm[2] - T.c[2]};
+  for (int r = 0; r < 3; ++r) {
+    double acc = T.A[3 * r] * dc[0]; acc += T.A[3 * r + 1] * dc[1]; acc += T.A[3 * r + 2] * dc[2];
+    T.t[r] = T.t[r] / rf + acc / rm - cf[r] / rf;
+  }
+  double B[144] = {0};
+  for (int d = 0; d < 9; ++d) B[d * 12 + d] = s;
+  for (int d1 = 0; d1 < 3; ++d1) for (int d2 = 0; d2 < 3; ++d2) B[(9 + d1) * 12 + d1 * 3 + d2] = dc[d2] / rf;
+  for (int d = 9; d < 12; ++d) B[d * 12 + d] = 1.0 / rf;
+  double R[144]; mat_BCBt12(B, T.cov, R); memcpy(T.cov, R, sizeof(R));
+  T.c[0] = T.c[1] = T.c[2] = 0.0;
+}
+static void affine_unnormalize(HostTrans& T, double rm, double rf, const double* cm, const double* cf) {
+  const double s = rf / rm;
+  for (int i = 0; i < 9; ++i) T.A[i] = s * T.A[i];
+  for (int r = 0; r < 3; ++r) T.t[r] = rf * T.t[r] + cf[r];
+  double B[144] = {0};
+  for (int d = 0; d < 9; ++d) B[d * 12 + d] = rf / rm;
+  for (int d = 9; d < 12; ++d) B[d * 12 + d] = rf;
+  double R[144]; mat_BCBt12(B, T.cov, R); memcpy(T.cov, R, sizeof(R));
+  for (int d = 0; d < 3; ++d) T.c[d] = cm[d];
+}
+static bool cholesky_upper12(const double* C, double* U) {   // C = U^T U  (vnl_cholesky::upper_triangle)
+  for (int i = 0; i < 144; ++i) U[i] = 0.0;
+  for (int i = 0; i < 12; ++i) for (int j = i; j < 12; ++j) {
+    double s = C[i * 12 + j];
+    for (int k = 0; k < i; ++k) s -= U[k * 12 + i] * U[k * 12 + j];
+    if (i == j) { if (s <= 0) return false; U[i * 12 + i] = std::sqrt(s); } else U[i * 12 + j] = s / U[i * 12 + i];
+  }
+  return true;
+}
+
+// one evaluation of f and g at x (length 78) for direction `dir`, transform / normalisation given by the caller
+static int objcov_device_eval(lrr_est* e, int dir, const HostTrans& T, const double* norm8, const double* x, double* f, double* g) {
+  lrr_ctx* ctx = e->ctx;
+  lrr_dir& d = e->d[dir];
+  double U[144] = {0}, Sg[144];
+  int ind = 0;
+  for (int d1 = 0; d1 < 12; ++d1) for (int d2 = d1; d2 < 12; ++d2) U[d1 * 12 + d2] = x[ind++];
+  for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) { double s = 0; for (int k = 0; k < 12; ++k) s += U[k * 12 + i] * U[k * 12 + j]; Sg[i * 12 + j] = s; }
+  double* pin = (double*)ctx->pinned;
+  memcpy(pin, Sg, sizeof(Sg));
+  CK(cudaMemcpyAsync(ctx->scratch_d, pin, sizeof(Sg), cudaMemcpyHostToDevice, ctx->stream));
+  EstArgs a = est_args(e);
+  a.d[dir].M = (int)d.matches;
+  { PHASE(PH_OBJCOV); lrr_k_objcov_launch(a.d[dir], T.A, T.t, T.c, norm8, ctx->scratch_d, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches); }
+  CK(cudaMemcpyAsync(pin + 256, d.sc->mom, 100 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  const double* mom = pin + 256;
+  const double n = (double)d.matches;
+  static const int sym6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  if (f) { double fv = 0; for (int j = 0; j < 4; ++j) fv += mom[j * 25 + 24]; *f = fv / n; }
+  if (g) {
+    double kl[144];
+    for (int i = 0; i < 12; ++i) for (int jx = 0; jx < 12; ++jx) {
+      const int di = i < 9 ? i / 3 : i - 9, ai = i < 9 ? i % 3 : 3, dj = jx < 9 ? jx / 3 : jx - 9, aj = jx < 9 ? jx % 3 : 3;
+      kl[i * 12 + jx] = mom[ai * 25 + aj * 6 + sym6[di][dj]];
+    }
+    ind = 0;   // g[ind] = < kl , U^T E + E^T U >   (cdcl_obj_fun_cov.txx:106-120)
+    for (int d1 = 0; d1 < 12; ++d1) for (int d2 = d1; d2 < 12; ++d2) {
+      double s = 0;
+      for (int i = 0; i < 12; ++i) s += kl[i * 12 + d2] * U[d1 * 12 + i];
+      for (int jx = 0; jx < 12; ++jx) s += kl[d2 * 12 + jx] * U[d1 * 12 + jx];
+      g[ind++] = s * (1.0 / n);
+    }
+  }
+  return LRR_OK;
+}
+
+static int objcov_check(lrr_est* e, int dir) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx;
+  if (e->dof != 12) { ctx->err = "cdcl_obj_fun_cov: only the affine <3,12> instantiation is built"; return LRR_ERR_UNSUPPORTED; }
+  if (e->d[dir].matches <= 0) { ctx->err = "objcov without matches"; return LRR_ERR_STATE; }
+  if (!e->d[dir].from_all->C6 || !e->d[dir].to_all->C6) { ctx->err = "objcov needs feature covariances (C6)"; return LRR_ERR_STATE; }
+  return LRR_OK;
+}
+
+extern "C" int lrr_objcov_eval(lrr_est* e, int dir, const double* x, double* f, double* g) {
+  int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
+  if (!x) return LRR_ERR_INVALID;
+  enter(e->ctx);
+  if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;
+  HostTrans T; memcpy(T.A, e->h[dir].A, 72); memcpy(T.t, e->h[dir].t, 24); memcpy(T.c, e->h[dir].c, 24);
+  const double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
+  return objcov_device_eval(e, dir, T, norm8, x, f, g);
+}
+
+// L-BFGS (stands in for vnl_lbfgs: m = 5, backtracking Armijo line search) with cdcl_lbfgs::report_iter's early stop:
+// finish as soon as |f_start - f| > 5 % |f_start| (cdcl/cdcl_lbfgs.h:30-36), at most max_evals evaluations
+// (cdcl/cdcl_estimation.txx:299).  The iterate trajectory of the netlib routine is unpinned upstream.
+template <class FG>
+static int lbfgs_minimize(FG&& fg, std::vector<double>& x, int max_evals, double* f_start, double* f_end, int* evals_out) {
+  const int n = (int)x.size(), mem = 5;
+  std::vector<double> g(n), gn(n), xn(n), d(n);
+  std::vector<std::vector<double>> S, Y; std::vector<double> RHO;
+  double f = 0; int evals = 0, rc;
+  if ((rc = fg(x.data(), &f, g.data())) != LRR_OK) return rc;
+  ++evals; *f_start = f; *f_end = f;
+  auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double s = 0; for (int i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  int iter = 0;
+  while (evals < max_evals) {
+    d = g;
+    std::vector<double> al(S.size());
+    for (int i = (int)S.size() - 1; i >= 0; --i) { al[i] = RHO[i] * dot(S[i], d); for (int k = 0; k < n; ++k) d[k] -= al[i] * Y[i][k]; }
+    if (!S.empty()) { double gam = dot(S.back(), Y.back()) / dot(Y.back(), Y.back()); for (int k = 0; k < n; ++k) d[k] *= gam; }
+    for (size_t i = 0; i < S.size(); ++i) { double be = RHO[i] * dot(Y[i], d); for (int k = 0; k < n; ++k) d[k] += S[i][k] * (al[i] - be); }
+    for (int k = 0; k < n; ++k) d[k] = -d[k];
+    const double gd = dot(g, d);
+    if (!(gd < 0)) break;
+    const double gnorm = std::sqrt(dot(g, g));
+    double step = (iter == 0) ? 1.0 / (gnorm > 0 ? gnorm : 1.0) : 1.0;
+    bool accepted = false; double fn = f;
+    while (evals < max_evals) {
+      for (int k = 0; k < n; ++k) xn[k] = x[k] + step * d[k];
+      if ((rc = fg(xn.data(), &fn, gn.data())) != LRR_OK) return rc;
+      ++evals;
+      if (std::isfinite(fn) && fn <= f + 1e-4 * step * gd) { accepted = true; break; }
+      step *= 0.5;
+    }
+    if (!accepted) break;
+    std::vector<double> s(n), yv(n);
+    for (int k = 0; k < n; ++k) { s[k] = xn[k] - x[k]; yv[k] = gn[k] - g[k]; }
+    const double sy = dot(s, yv);
+    if (sy > 1e-300) { S.push_back(s); Y.push_back(yv); RHO.push_back(1.0 / sy); if ((int)S.size() > mem) { S.erase(S.begin()); Y.erase(Y.begin()); RHO.erase(RHO.begin()); } }
+    x = xn; g = gn; f = fn; *f_end = f; ++iter;
+    if (std::fabs(*f_start - *f_end) > 0.05 * std::fabs(*f_start)) break;   // report_iter()
+    if (std::sqrt(dot(g, g)) < 1e-12) break;
+  }
+  *evals_out = evals;
+  return LRR_OK;
+}
+
+// estimate_covariance (cdcl/cdcl_estimation.txx:264-337) on the ICP matches of direction `dir`
+extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_start, double* f_end, int* n_evals) {
+  int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
+  lrr_ctx* ctx = e->ctx; enter(ctx);
+  lrr_dir& d = e->d[dir];
+  double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
+  if (e->normalize) {   // cdcl_normalize_matches over the current matches (:271-277)
+    EstArgs a = est_args(e, dir);
+    a.d[dir].M = (int)d.matches;
+    a.ndir = 1; if (dir == 1) { a.d[0] = a.d[1]; a.src = 0; }
+    lrr_k_norm1(a, ctx->stream, &ctx->launches); lrr_k_norm2(a, ctx->stream, &ctx->launches);
+  }
+  if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;
+  Scal& h = e->h[dir];
+  HostTrans T; memcpy(T.A, h.A, 72); memcpy(T.t, h.t, 24); memcpy(T.c, h.c, 24); memcpy(T.cov, h.cov, sizeof(T.cov));
+  if (e->normalize) {
+    for (int k = 0; k < 3; ++k) { norm8[k] = h.cfrom[k]; norm8[4 + k] = h.cto[k]; }
+    norm8[3] = h.rfrom; norm8[7] = h.rto;
+    affine_normalize(T, norm8[3], norm8[7], norm8, norm8 + 4);
+  }
+  double U[144];
+  if (!cholesky_upper12(T.cov, U)) { ctx->err = "estimate_covariance: covariance is not positive definite"; return LRR_ERR_STATE; }
+  std::vector<double> x(78); int ind = 0;
+  for (int d1 = 0; d1 < 12; ++d1) for (int d2 = d1; d2 < 12; ++d2) x[ind++] = U[d1 * 12 + d2];
+  double fs = 0, fe = 0; int ev = 0;
+  rc = lbfgs_minimize([&](const double* xx, double* f, double* g) { return objcov_device_eval(e, dir, T, norm8, xx, f, g); }, x, max_evals, &fs, &fe, &ev);
+  if (rc != LRR_OK) return rc;
+  double Un[144] = {0}; ind = 0;
+  for (int d1 = 0; d1 < 12; ++d1) for (int d2 = d1; d2 < 12; ++d2) Un[d1 * 12 + d2] = x[ind++];
+  for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) { double s = 0; for (int k = 0; k < 12; ++k) s += Un[k * 12 + i] * Un[k * 12 + j]; T.cov[i * 12 + j] = s; }
+  if (e->normalize) affine_unnormalize(T, norm8[3], norm8[7], norm8, norm8 + 4);
+  memcpy(h.A, T.A, 72); memcpy(h.t, T.t, 24); memcpy(h.c, T.c, 24); memcpy(h.cov, T.cov, sizeof(T.cov));
+  if ((rc = push_scal(e, dir)) != LRR_OK) return rc;
+  e->werr_cache_valid = false;
+  if (f_start) *f_start = fs; if (f_end) *f_end = fe; if (n_evals) *n_evals = ev;
+  return LRR_OK;
+}
+
 // validTransform (rrl/itkLocationRegistration.cxx:2914-2926): singular values of A inside [0.1, 10]
 static bool valid_transform(const double* A) {
   double U[9], V[9], w[3];

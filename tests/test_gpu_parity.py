@@ -172,3 +172,24 @@ def test_batch_run(gpu_lib, oracle_lib):
         assert rel(g["A"][j], o["A"][j]) < TOL_PARAM and rel(g["t"][j], o["t"][j]) < TOL_PARAM and rel(g["cov"][j], o["cov"][j]) < TOL_PARAM
         assert abs(g["weighted_error"][j] - o["weighted_error"][j]) <= 1e-8 * max(1.0, o["weighted_error"][j])
         assert abs(g["rms"][j] - o["rms"][j]) <= 1e-8 * max(1.0, o["rms"][j])
+
+
+def test_objcov(gpu_lib, oracle_lib, pair):
+    """A13: cdcl_obj_fun_cov f/g on the ICP matches, and the LBFGS covariance refinement built on it (config 5 in miniature)."""
+    _, g = make_est(gpu_lib, pair, "cdcl_fwd", number_points=5000)
+    _, o = make_est(oracle_lib, pair, "cdcl_fwd", number_points=5000)
+    for it in range(3):
+        g.one_iteration(it); o.one_iteration(it)
+    cov = o.get_transform(0)["cov"]
+    U = np.linalg.cholesky(cov).T
+    x = np.concatenate([U[i, i:] for i in range(12)])
+    rng = np.random.default_rng(0)
+    for trial in range(2):
+        xx = x * (1.0 + 0.05 * rng.normal(size=x.shape))
+        fg_, gg = g.objcov_eval(xx); fo, go = o.objcov_eval(xx)
+        assert abs(fg_ - fo) <= 1e-9 * abs(fo), (fg_, fo)
+        assert rel(gg, go) < 1e-8, rel(gg, go)
+    rg, ro = g.objcov_refine(5), o.objcov_refine(5)
+    assert rg[2] == ro[2] and abs(rg[0] - ro[0]) <= 1e-9 * abs(ro[0]) and abs(rg[1] - ro[1]) <= 1e-7 * abs(ro[1]), (rg, ro)
+    Tg, To = g.get_transform(0), o.get_transform(0)
+    assert rel(Tg["cov"], To["cov"]) < TOL_PARAM and rel(Tg["A"], To["A"]) < 1e-12 and rel(Tg["t"], To["t"]) < 1e-12
