@@ -1,9 +1,9 @@
 """ctypes binding of the C ABI declared in include/lrr_gpu.h.
 
 The binding is generic over (shared library, symbol prefix): the product loads
-``lrr_b200/liblrr_b200.so`` with prefix ``lrr_``; the parity tests instantiate the same class over
-``oracle/liblrr_oracle.so`` with prefix ``lrro_`` so that one script drives both.  Nothing in this
-package imports or loads the oracle — only tests/, __graft_entry__.smoke() and bench.py do.
+``lrr_b200/liblrr_b200.so`` with prefix ``lrr_``; the parity tests instantiate the same class over the
+CPU checker library (same ABI, its own prefix) so that one script drives both.  Nothing in this package
+imports or loads that checker — only tests/, __graft_entry__.smoke() and bench.py do.
 """
 from __future__ import annotations
 

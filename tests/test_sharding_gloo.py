@@ -1,0 +1,53 @@
+"""N > 1 path on CPU: world_size-2 gloo processes shard a job list, each runs its block through the (oracle) backend,
+and the gathered result equals the single-process result — the same code path bench.py uses with NCCL on GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_job_block_partition():
+    from lrr_b200.sharding import job_block
+    for njobs in (0, 1, 7, 8192, 8193):
+        for world in (1, 2, 3, 8):
+            blocks = [job_block(njobs, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == njobs
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from lrr_b200 import synth
+    from lrr_b200.capi import Lib
+    from lrr_b200.sharding import gather_results, run_batch_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = Lib(os.path.join(ROOT, "oracle", "liblrr_oracle.so"), "lrro_")   # CPU stand-in for the device backend
+    pair = synth.make_pair(4, 12000, 12000, size=80.0)
+    jobs = synth.make_jobs(pair, 3, 2, seed=4)
+    ctx = lib.context()
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    local = run_batch_sharded(ctx, mv, fx, jobs, 8, 5, rank, world)
+    full = gather_results(local, len(jobs), rank, world)
+    if rank == 0:
+        ref = ctx.batch_run(mv, fx, jobs, 8, 5)
+        # the oracle normalises shared feature objects in place (Q10), so results drift by O(ulp) with the job history:
+        # integer fields exact, floating-point fields to 1e-9
+        ok = all(np.array_equal(full[k], ref[k]) for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"))
+        ok = ok and all(np.allclose(full[k], ref[k], rtol=1e-9, atol=1e-12) for k in ("A", "t", "c", "cov", "rms", "weighted_error"))
+        open(os.path.join(outdir, "result.txt"), "w").write("OK" if ok else "MISMATCH")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_batch_equals_single_process(tmp_path, oracle_lib):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(os.path.join(str(tmp_path), "result.txt")).read() == "OK"
