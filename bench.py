@@ -140,6 +140,44 @@ def cpu_measure(pair, steps, warmup):
             "registration_iters": iters, "registration_iters_per_s": iters / t_reg, "converged": bool(conv)}
 
 
+BATCH_SEED, BATCH_SIZE_MM, BATCH_LOCATIONS_PER_GPU, BATCH_INITS = 4, 160.0, 16, 8
+
+
+def make_batch_workload(world):
+    """C4, bounded: one 100k/100k pair, per GPU 16 locations x 8 initialisations (first near-correct,
+    the rest perturbed up to 30 deg / 20 mm), 50 mm ROI cubes, rrl symmetric <3,12>, <= 70 iterations each."""
+    from lrr_b200 import synth
+    pair = synth.make_pair(BATCH_SEED, N_FEATURES, N_FEATURES, size=BATCH_SIZE_MM)
+    jobs = synth.make_jobs(pair, BATCH_LOCATIONS_PER_GPU * world, BATCH_INITS, seed=BATCH_SEED)
+    return pair, jobs
+
+
+def verified_count(res):
+    """converged and not oscillated and validTransform (status 0) — rrl/itkLocationRegistration.cxx:2495-2507,2914-2926
+    (the reference's SVM verification needs a model file that is not in the repository)."""
+    return int(((res["status"] == 0) & (res["converged"] == 1) & (res["oscillated"] == 0)).sum())
+
+
+def cpu_batch_measure(pair, jobs, n_single=4):
+    from lrr_b200.capi import Lib, RESULT_DTYPE
+    lib = Lib(os.path.join(ROOT, "oracle", "liblrr_oracle.so"), "lrro_")
+    ctx = lib.context()
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    t0 = time.perf_counter(); ctx.batch_run(mv, fx, jobs[:n_single], 70, BATCH_SEED); t1 = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    nall = min(len(jobs), 2 * cores)
+    out = np.zeros(nall, dtype=RESULT_DTYPE)
+    f = lib.dll.lrro_batch_run_mt
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
+    jj = np.ascontiguousarray(jobs[:nall])
+    t0 = time.perf_counter()
+    f(ctx.h, mv.h, fx.h, jj.ctypes.data_as(ctypes.c_void_p), nall, 70, BATCH_SEED, out.ctypes.data_as(ctypes.c_void_p), cores)
+    tall = time.perf_counter() - t0
+    return {"registrations_per_s_1core": n_single / t1, "registrations_per_s_allcores": nall / tall, "cores_all": cores,
+            "sample": f"{n_single} jobs on 1 thread; {nall} jobs on {cores} threads (parallel over registrations)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -264,7 +302,7 @@ def run_b200(args, rank, world, local_rank):
     value_warm = world * args.steps / (warm_ms_max * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (rank-local; max over ranks) ----
-    e2e_steps = max(1, min(3, args.steps))
+    e2e_steps = 0 if args.only_iterations else max(1, min(3, args.steps))
     pf, pm = pin(pair["fixed"]), pin(pair["moving"])
     h2d = feature_bytes(pair["fixed"]) + feature_bytes(pair["moving"])
     d2h = (9 + 3 + 3 + 144) * 8
@@ -292,7 +330,27 @@ def run_b200(args, rank, world, local_rank):
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_iters / float(te[0])
+    e2e_value = world * e2e_iters / float(te[0]) if e2e_iters else None
+
+    # ---- batched location registration, sharded over the ranks ----
+    from lrr_b200.sharding import gather_results, run_batch_sharded
+    bpair, bjobs = make_batch_workload(world)
+    if args.only_iterations:
+        bjobs = bjobs[:world]
+    with torch.cuda.stream(stream):
+        bfx, bmv = ctx.upload(bpair["fixed"]), ctx.upload(bpair["moving"])
+        run_batch_sharded(ctx, bmv, bfx, bjobs[: 2 * world], 70, BATCH_SEED, rank, world)   # warm-up
+        barrier()
+        tb0 = time.perf_counter()
+        local = run_batch_sharded(ctx, bmv, bfx, bjobs, 70, BATCH_SEED, rank, world)
+        torch.cuda.synchronize()
+        tb_local = time.perf_counter() - tb0
+        full = gather_results(local, len(bjobs), rank, world, device=torch.device("cuda", local_rank) if world > 1 else None)
+        barrier()
+    tb = torch.tensor([tb_local], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    batch_s = float(tb[0])
 
     if rank != 0:
         if dist is not None:
@@ -339,15 +397,20 @@ def run_b200(args, rank, world, local_rank):
                         "ramped run to convergence (<=70 one_iteration calls), read back transform+covariance"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "final_rms": None,
+        "registrations": {"value": len(bjobs) / batch_s, "unit": "registrations/s", "jobs": int(len(bjobs)), "seconds": batch_s,
+                          "verified": verified_count(full), "verified_per_s": verified_count(full) / batch_s,
+                          "rejected": int((full["status"] == 1).sum()), "mean_iterations": float(full["iterations"][full["status"] == 0].mean()),
+                          "what": f"C4 bounded: {BATCH_LOCATIONS_PER_GPU} locations x {BATCH_INITS} initialisations per GPU on one resident "
+                                  "100k/100k pair, 50 mm ROI, rrl symmetric <3,12>, <= 70 iterations, jobs sharded over the ranks, one result gather"},
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not args.only_iterations:
         r = cpu_measure(pair, 6, 1)
         line["cpu_baseline"] = {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "full ramped registration + 6 one_iteration calls at the finest level, CPU oracle port, single thread "
                                           "(the reference's execution model)",
                                 "registration_iters_per_s": r["registration_iters_per_s"], "registration_s": r["registration_s"],
                                 "host_cores_available": os.cpu_count()}
+        line["cpu_baseline"]["registrations"] = cpu_batch_measure(bpair, bjobs)
     else:
         line["cpu_baseline"] = None
     line["final_A00"] = float(final["A"][0, 0])
@@ -363,6 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only-iterations", action="store_true", help="skip the e2e / batch / cpu legs (short run for ncu launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

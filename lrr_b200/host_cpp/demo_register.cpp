@@ -1,0 +1,63 @@
+// Host-side C++ example and self-check of include/lrr/lrr_estimators.h: the counterpart of register_points() in
+// cdcl/examples/estimate.cxx:45-187 and of the estimator use in rrl/itkLocationRegistration.cxx:1640-1643,2418-2446,
+// written against the reference's class and method names.  Synthetic data: points on three spheres (sheet features,
+// radial normals), moving set = exact inverse image under a known affine transform; exits 0 when the recovered
+// transform matches.
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include "../../include/lrr/lrr_estimators.h"
+
+using namespace lrr_b200;
+typedef cdcl_feature_with_shape<3> feature_type;
+
+int main() {
+  const unsigned int dim = 3, dof = 12;
+  std::mt19937_64 rng(7);
+  std::uniform_real_distribution<double> U(0.0, 100.0);
+  std::vector<feature_type::sptr> fixed, moving;
+  const double A[9] = {1.02, 0.03, -0.02, -0.025, 0.99, 0.04, 0.015, -0.035, 1.01}, t[3] = {53.0, 48.5, 51.0}, c[3] = {50, 50, 50};
+  double Ai[9];
+  {  // 3x3 inverse
+    const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    Ai[0] = (A[4] * A[8] - A[5] * A[7]) / det; Ai[1] = (A[2] * A[7] - A[1] * A[8]) / det; Ai[2] = (A[1] * A[5] - A[2] * A[4]) / det;
+    Ai[3] = (A[5] * A[6] - A[3] * A[8]) / det; Ai[4] = (A[0] * A[8] - A[2] * A[6]) / det; Ai[5] = (A[2] * A[3] - A[0] * A[5]) / det;
+    Ai[6] = (A[3] * A[7] - A[4] * A[6]) / det; Ai[7] = (A[1] * A[6] - A[0] * A[7]) / det; Ai[8] = (A[0] * A[4] - A[1] * A[3]) / det;
+  }
+  for (int i = 0; i < 3000; ++i) {
+    feature_type::sptr q(new feature_type), p(new feature_type);
+    const int sph = i % 3;
+    const double cs[3][3] = {{30, 40, 50}, {65, 55, 35}, {50, 30, 70}}, rad[3] = {22.0, 18.0, 25.0};
+    std::normal_distribution<double> G(0.0, 1.0);
+    vec3 n = {G(rng), G(rng), G(rng)};
+    const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int d = 0; d < 3; ++d) n[d] /= nn;
+    vec3 x = {cs[sph][0] + rad[sph] * n[0], cs[sph][1] + rad[sph] * n[1], cs[sph][2] + rad[sph] * n[2]};
+    (void)U;
+    q->location_ = x; q->strength_ = 50.0 + U(rng); q->shape_ = feature_type::SHEET; q->directions_.push_back(n);
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { q->error_projector_[3 * a + b] = n[a] * n[b]; q->covariance_[3 * a + b] = (a == b) ? 1.0 : 0.0; }
+    *p = *q;
+    for (int r = 0; r < 3; ++r) p->location_[r] = Ai[3 * r] * (x[0] - t[0]) + Ai[3 * r + 1] * (x[1] - t[1]) + Ai[3 * r + 2] * (x[2] - t[2]) + c[r];
+    fixed.push_back(q); moving.push_back(p);
+  }
+  device_context ctx(0);
+  cdcl_trans<dim, dof>::sptr init(new cdcl_trans<dim, dof>(mat3{1, 0, 0, 0, 1, 0, 0, 0, 1}, vec3{52.0, 49.5, 50.0}, vec3{50, 50, 50}));
+  rrl_estimation_symmetric_ICP_matching_all<dim, dof> estimation(ctx, moving, fixed, init);
+  estimation.weight_by_strength(true);
+  estimation.normalize_matches();
+  bool converged = false; unsigned int iteration = 0;
+  while (!converged && iteration < 70) { converged = estimation.one_iteration(0, 0, iteration); ++iteration; }   // driver loop :2418
+  cdcl_trans<dim, dof>::sptr T = estimation.get_transform();
+  T->print();
+  double err = 0;
+  for (size_t i = 0; i < moving.size(); ++i) {
+    const vec3 y = T->map_loc(moving[i]->location_);
+    for (int d = 0; d < 3; ++d) err = std::fmax(err, std::fabs(y[d] - fixed[i]->location_[d]));
+  }
+  std::printf("iterations %u converged %d oscillated %d weighted_error %.3e max map error %.3e\n", iteration, (int)converged, (int)estimation.oscillated(),
+              estimation.weighted_error(), err);
+  estimation.estimate_LS_backward(false);
+  const mat3 S = estimation.compute_transfer_error_covariance();
+  std::printf("transfer error covariance trace %.3e\n", S[0] + S[4] + S[8]);
+  return (converged && err < 1e-6) ? 0 : 1;
+}

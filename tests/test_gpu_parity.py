@@ -193,3 +193,14 @@ def test_objcov(gpu_lib, oracle_lib, pair):
     assert rg[2] == ro[2] and abs(rg[0] - ro[0]) <= 1e-9 * abs(ro[0]) and abs(rg[1] - ro[1]) <= 1e-7 * abs(ro[1]), (rg, ro)
     Tg, To = g.get_transform(0), o.get_transform(0)
     assert rel(Tg["cov"], To["cov"]) < TOL_PARAM and rel(Tg["A"], To["A"]) < 1e-12 and rel(Tg["t"], To["t"]) < 1e-12
+
+
+def test_cpp_host_api():
+    """The header-only C++ mirror of the reference template API (include/lrr/lrr_estimators.h) drives the C ABI."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "lrr_b200", "host_cpp", "demo_register")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
