@@ -140,11 +140,11 @@ def cpu_measure(pair, steps, warmup):
             "registration_iters": iters, "registration_iters_per_s": iters / t_reg, "converged": bool(conv)}
 
 
-BATCH_SEED, BATCH_SIZE_MM, BATCH_LOCATIONS_PER_GPU, BATCH_INITS = 4, 160.0, 16, 8
+BATCH_SEED, BATCH_SIZE_MM, BATCH_LOCATIONS_PER_GPU, BATCH_INITS = 4, 160.0, 32, 32
 
 
 def make_batch_workload(world):
-    """C4, bounded: one 100k/100k pair, per GPU 16 locations x 8 initialisations (first near-correct,
+    """C4, bounded: one 100k/100k pair, per GPU 32 locations x 32 initialisations (first near-correct,
     the rest perturbed up to 30 deg / 20 mm), 50 mm ROI cubes, rrl symmetric <3,12>, <= 70 iterations each."""
     from lrr_b200 import synth
     pair = synth.make_pair(BATCH_SEED, N_FEATURES, N_FEATURES, size=BATCH_SIZE_MM)

@@ -1004,39 +1004,75 @@ static void roi_indices(const lrr_fset* fs, const double* c, double half, std::v
     if (!(x0 > x[i] || x[i] > x1 || y0 > y[i] || y[i] > y1 || z0 > z[i] || z[i] > z1)) out.push_back((int32_t)i);
 }
 
+// one job through the per-iteration kernels of the single-registration path (estimator reused, like the driver :1635-1638)
+static int batch_job_host(lrr_est* est, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job& job, int64_t j, int max_iter, uint64_t shuffle_seed,
+                          lrr_result& r, std::vector<int32_t>& mi, std::vector<int32_t>& fi) {
+  int rc;
+  memset(&r, 0, sizeof(r));
+  roi_indices(fixed_all, job.roi_center_fixed, job.roi_half_size, fi);
+  roi_indices(moving_all, job.roi_center_moving, job.roi_half_size, mi);
+  r.n_moving_inside = (int32_t)mi.size(); r.n_fixed_inside = (int32_t)fi.size();
+  if (mi.size() < 1000 || fi.size() < 1000) { r.status = 1; return LRR_OK; }   // :1632
+  if ((rc = lrr_est_set_subsets(est, mi.data(), (int64_t)mi.size(), fi.data(), (int64_t)fi.size())) != LRR_OK) return rc;
+  if ((rc = lrr_est_set_shuffle(est, LRR_ORDER_RESHUFFLE, shuffle_seed + (uint64_t)j)) != LRR_OK) return rc;
+  if ((rc = lrr_est_set_transform(est, LRR_TRANS_AFFINE, job.A, job.t, job.c, nullptr)) != LRR_OK) return rc;
+  int converged = 0, it = 0;
+  while (!converged && it < max_iter) {                                   // :2418
+    if ((rc = lrr_est_one_iteration(est, (unsigned)it, &converged)) != LRR_OK) return rc;
+    ++it;
+    if (!valid_transform(est->h[0].A)) { r.status = 2; break; }           // :2482
+  }
+  const Scal& T = est->h[0];
+  r.converged = converged; r.oscillated = est->oscillation_count > 10; r.iterations = it;
+  memcpy(r.A, T.A, 72); memcpy(r.t, T.t, 24); memcpy(r.c, T.c, 24); memcpy(r.cov, T.cov, sizeof(double) * 144);
+  r.rms = rms_of(est, T, true); r.weighted_error = werr_of(T);
+  return LRR_OK;
+}
+
+cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
+                             int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st, long long* launches);
+size_t lrr_batch_workspace_bytes(int nblocks, int n_moving, int n_fixed);
+int lrr_batch_blocks_per_sm();
+
 // Batched location registration: the outer loops of LocationRegistration::Run (rrl/itkLocationRegistration.cxx:2138,
-// 2230,2332) over one resident volume pair.  One estimator object is reused for every job, like the driver does
-// (:1635-1638: set_features + set_transform).  Jobs are independent; callers shard them across GPUs (one ctx each).
+// 2230,2332) over one resident volume pair.  Device path: one persistent thread block per registration
+// (lrr_batch.cu).  Jobs the block kernel hands back (ROI above its capacity, selector overflow) and the
+// LRR_BATCH_MODE=host debugging mode go through one reused estimator object and the per-iteration kernels.
+// Jobs are independent; callers shard them across GPUs (one ctx each).
 extern "C" int lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int max_iter,
                              uint64_t shuffle_seed, lrr_result* out) {
   if (!ctx || !moving_all || !fixed_all || njobs < 0 || (njobs > 0 && (!jobs || !out))) return LRR_ERR_INVALID;
   enter(ctx);
+  if (njobs == 0) return LRR_OK;
+  const char* mode = getenv("LRR_BATCH_MODE");
+  const bool host_only = (mode && std::string(mode) == "host") || max_iter > 250;
+  std::vector<int64_t> todo;
+  if (!host_only) {
+    const int nblocks = (int)std::min<int64_t>(njobs, (int64_t)lrr_num_sms() * lrr_batch_blocks_per_sm());
+    const size_t wbytes = lrr_batch_workspace_bytes(nblocks, (int)moving_all->n, (int)fixed_all->n);
+    void* work = nullptr; lrr_job* djobs = nullptr; lrr_result* dout = nullptr;
+    CK(cudaMallocAsync(&work, wbytes, ctx->stream));
+    CK(dmalloc(&djobs, (size_t)njobs)); CK(dmalloc(&dout, (size_t)njobs));
+    CK(cudaMemcpyAsync(djobs, jobs, sizeof(lrr_job) * njobs, cudaMemcpyHostToDevice, ctx->stream));
+    double table[4 * 32] = {0};
+    const int rows = build_muse_table(1000u, table);
+    { PHASE(PH_BATCH);
+      CK(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, max_iter, shuffle_seed, table, rows, nblocks, work, wbytes, ctx->stream, &ctx->launches)); }
+    CK(cudaMemcpyAsync(out, dout, sizeof(lrr_result) * njobs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    dfree(work); dfree(djobs); dfree(dout);
+    for (int64_t j = 0; j < njobs; ++j) if (out[j].status < 0) todo.push_back(j);
+  } else {
+    for (int64_t j = 0; j < njobs; ++j) todo.push_back(j);
+  }
+  if (todo.empty()) return LRR_OK;
   lrr_est* est = nullptr;
   int rc = lrr_est_create(ctx, LRR_RRL_SYM, 3, 12, moving_all, fixed_all, &est);
   if (rc != LRR_OK) return rc;
   std::vector<int32_t> mi, fi;
-  for (int64_t j = 0; j < njobs && rc == LRR_OK; ++j) {
-    const lrr_job& job = jobs[j]; lrr_result& r = out[j];
-    memset(&r, 0, sizeof(r));
-    roi_indices(fixed_all, job.roi_center_fixed, job.roi_half_size, fi);
-    roi_indices(moving_all, job.roi_center_moving, job.roi_half_size, mi);
-    r.n_moving_inside = (int32_t)mi.size(); r.n_fixed_inside = (int32_t)fi.size();
-    if (mi.size() < 1000 || fi.size() < 1000) { r.status = 1; continue; }   // :1632
-    if ((rc = lrr_est_set_subsets(est, mi.data(), (int64_t)mi.size(), fi.data(), (int64_t)fi.size())) != LRR_OK) break;
-    if ((rc = lrr_est_set_shuffle(est, LRR_ORDER_RESHUFFLE, shuffle_seed + (uint64_t)j)) != LRR_OK) break;
-    if ((rc = lrr_est_set_transform(est, LRR_TRANS_AFFINE, job.A, job.t, job.c, nullptr)) != LRR_OK) break;
-    int converged = 0, it = 0;
-    while (!converged && it < max_iter) {                                   // :2418
-      if ((rc = lrr_est_one_iteration(est, (unsigned)it, &converged)) != LRR_OK) break;
-      ++it;
-      if (!valid_transform(est->h[0].A)) { r.status = 2; break; }           // :2482
-    }
-    if (rc != LRR_OK) break;
-    const Scal& T = est->h[0];
-    r.converged = converged; r.oscillated = est->oscillation_count > 10; r.iterations = it;
-    memcpy(r.A, T.A, 72); memcpy(r.t, T.t, 24); memcpy(r.c, T.c, 24); memcpy(r.cov, T.cov, sizeof(double) * 144);
-    r.rms = rms_of(est, T, true); r.weighted_error = werr_of(T);
-  }
+  for (int64_t j : todo) if ((rc = batch_job_host(est, moving_all, fixed_all, jobs[j], j, max_iter, shuffle_seed, out[j], mi, fi)) != LRR_OK) break;
   lrr_est_destroy(est);
   return rc;
 }

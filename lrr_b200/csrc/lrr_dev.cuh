@@ -180,6 +180,32 @@ __device__ __forceinline__ bool lrr_nn_ball_thread(const GridDev& g, double qx, 
   return true;
 }
 
+// pass A for a query WITHOUT a candidate (first use of a from-feature): the 27 cells around the query, one thread.
+// Returns 1 when that already proves the neighbour (best closer than the block boundary), 0 when a candidate was
+// found but cells beyond the block may hold a closer point, -1 when the block is empty.
+__device__ __forceinline__ int lrr_nn_block27_thread(const GridDev& g, double qx, double qy, double qz, NNState& st) {
+  st.best = 1e300; st.best_s = -1; st.best_o = 0x7fffffff;
+  const int cx = lrr_cell_clamp(qx, g.ox, g.inv_h, g.nx), cy = lrr_cell_clamp(qy, g.oy, g.inv_h, g.ny), cz = lrr_cell_clamp(qz, g.oz, g.inv_h, g.nz);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
+    for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
+      const int row = (z * g.ny + y) * g.nx;
+      lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + x0), __ldg(g.cell_start + row + x1 + 1), qx, qy, qz, st.best, st.best_s, st.best_o);
+    }
+  if (st.best_s < 0) return -1;
+  // distance to the nearest face of the 3x3x3 block that still has cells behind it
+  double bound = 1e300; bool any = false;
+  if (cx - 1 > 0) { bound = fmin(bound, qx - (g.ox + (cx - 1) * g.h)); any = true; }
+  if (cx + 2 < g.nx) { bound = fmin(bound, (g.ox + (cx + 2) * g.h) - qx); any = true; }
+  if (cy - 1 > 0) { bound = fmin(bound, qy - (g.oy + (cy - 1) * g.h)); any = true; }
+  if (cy + 2 < g.ny) { bound = fmin(bound, (g.oy + (cy + 2) * g.h) - qy); any = true; }
+  if (cz - 1 > 0) { bound = fmin(bound, qz - (g.oz + (cz - 1) * g.h)); any = true; }
+  if (cz + 2 < g.nz) { bound = fmin(bound, (g.oz + (cz + 2) * g.h) - qz); any = true; }
+  if (!any) return 1;
+  bound -= 1e-9 * g.h;
+  return (bound > 0.0 && st.best < bound * bound) ? 1 : 0;
+}
+
 __device__ __forceinline__ void lrr_warp_min(double& best, int& best_s, int& best_o) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) {

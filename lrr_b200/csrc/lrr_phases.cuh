@@ -98,6 +98,10 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
       const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
       st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
       done = lrr_nn_ball_thread(g, yx, yy, yz, st);
+    } else if (g.n > 0) {
+      const int r27 = lrr_nn_block27_thread(g, yx, yy, yz, st);
+      if (r27 == 1) done = true;
+      else if (r27 == 0) done = lrr_nn_ball_thread(g, yx, yy, yz, st);   // rescans the block's rows inside the ball: still exact
     }
     if (done) lrr_match_finish(a, rigid, k, i, x, y, z, yx, yy, yz, st.best_s, acc);
     else {
@@ -343,7 +347,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else g = sp * sq;
       if (g > LRR_STRENGTH_CAP) g = LRR_STRENGTH_CAP;
       gk = g;
-      lrr_sel_add(selG, fabs(g));
+      if (selG.fine) lrr_sel_add(selG, fabs(g));
       acc[0] += 1.0;
     }
     if (sym && s >= 0) {
@@ -352,7 +356,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else lrr_from_loc(a, sc, mapped, i, qx, qy, qz);
       qx = (qx - sc0) * isr; qy = (qy - sc1) * isr; qz = (qz - sc2) * isr;
       sk = 1.0 / (1.0 + 5.0 * (qx * qx + qy * qy + qz * qz));   // reference: sqrt then square (cdcl :984-985)
-      lrr_sel_add(selS, sk);
+      if (selS.fine) lrr_sel_add(selS, sk);
     }
     a.w[k] = w; a.gkey[k] = gk; a.skey[k] = sk;
   }
