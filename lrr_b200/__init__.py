@@ -18,5 +18,5 @@ def lib() -> Lib:
     """The product library (hand-written CUDA kernels behind the C ABI).  Raises if it is not built."""
     global _lib
     if _lib is None:
-        _lib = Lib(LIB_PATH, "lrr_")
+        _lib = Lib(os.environ.get("LRR_B200_LIB", LIB_PATH), "lrr_")   # override only for A/B builds of the same product
     return _lib

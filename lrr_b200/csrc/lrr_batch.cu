@@ -15,6 +15,7 @@
 #define BATCH_CAP 16384            // max features of one ROI (larger ROIs are returned to the host path)
 #define BATCH_SEL_BINS 2048
 #define BATCH_SEL_CAND 1024
+#define BATCH_THREADS 512           // one block of 16 warps per SM: half the per-registration latency of 2 x 256
 
 struct BatchWork {                 // per-block workspace in global memory
   // per direction
@@ -200,7 +201,7 @@ __device__ double block_muse(const DirArgs& a, const BatchArgs& B, double* buf /
 }
 
 struct BatchShared {
-  PhaseShared ph;
+  PhaseSharedT<BATCH_THREADS / 32> ph;
   DirArgs d[2];
   unsigned int hist[BATCH_SEL_BINS];
   double cand[BATCH_SEL_CAND];          // also the 1024-double MUSE sort buffer
@@ -219,7 +220,7 @@ struct BatchShared {
 extern __shared__ __align__(16) unsigned char batch_smem[];
 #define TPH(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); S.tph[i] += now_ - tmark; tmark = now_; } } while (0)
 
-__global__ void __launch_bounds__(LRR_THREADS) k_batch(const __grid_constant__ BatchArgs B) {
+__global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__ BatchArgs B) {
   BatchShared& S = *reinterpret_cast<BatchShared*>(batch_smem);
   int* list = reinterpret_cast<int*>(batch_smem + ((sizeof(BatchShared) + 15) & ~size_t(15)));   // BATCH_CAP ints
   const BlockScope scope;
@@ -441,7 +442,7 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
   if ((e = cudaMemsetAsync(B.w_sc, 0, nb * 2 * sizeof(Scal), st)) != cudaSuccess) return e;
   const size_t smem = lrr_batch_smem_bytes();
   if ((e = cudaFuncSetAttribute(k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-  k_batch<<<nblocks, LRR_THREADS, smem, st>>>(B); ++*launches;
+  k_batch<<<nblocks, BATCH_THREADS, smem, st>>>(B); ++*launches;
   if (B.dbg) {
     long long h[16]; cudaStreamSynchronize(st); cudaMemcpy(h, B.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const char* nm[12] = {"roi", "ctl", "matchA", "matchB", "muse", "norm", "weight", "mad", "accum", "solve", "resid", "result"};
@@ -460,6 +461,6 @@ size_t lrr_batch_workspace_bytes(int nblocks, int n_moving, int n_fixed) {
 int lrr_batch_blocks_per_sm() {
   int n = 0;
   cudaFuncSetAttribute(k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrr_batch_smem_bytes());
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_batch, LRR_THREADS, lrr_batch_smem_bytes());
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_batch, BATCH_THREADS, lrr_batch_smem_bytes());
   return n < 1 ? 1 : n;
 }

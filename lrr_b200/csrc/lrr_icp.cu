@@ -95,7 +95,10 @@ void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* 
 }
 
 // ---- phase kernels -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LRR_THREADS) k_match(const __grid_constant__ EstArgs a) {
+#ifndef LRR_MATCH_MINBLK
+#define LRR_MATCH_MINBLK 2
+#endif
+__global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const __grid_constant__ EstArgs a) {
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
   lrr_phase_match(lrr_scope(a, dir), a.d[dir], a.flags, sh);

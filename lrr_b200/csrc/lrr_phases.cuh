@@ -12,10 +12,12 @@
 #define LRR_THREADS 256
 #define LRR_NWARPS (LRR_THREADS / 32)
 
-struct PhaseShared {
+template <int NW>
+struct PhaseSharedT {
   double out[LRR_NRED];
-  double tmp[LRR_NRED * LRR_NWARPS];
+  double tmp[LRR_NRED * NW];
 };
+typedef PhaseSharedT<LRR_NWARPS> PhaseShared;
 
 // position k of the (possibly permuted) moving vector -> compact index.  RESHUFFLE = keyed 4-round Feistel
 // permutation with cycle walking, evaluated on the fly (the stand-in for vcl_random_shuffle, Q4).
@@ -74,8 +76,8 @@ __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, i
 
 // pass A: one thread per query, ball scan bounded by the previous neighbour of the same from-feature;
 // queries without a candidate or with a large ball go to the direction's queue
-template <class Scope>
-__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, PhaseShared& sh) {
+template <class Scope, class SH>
+__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
   Scal* sc = a.sc;
   double A[9], t[3], c[3];
 #pragma unroll
@@ -118,8 +120,8 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
 }
 
 // pass B: one warp per queued query, shells 2.. ; adds its sums to the direction's scalars
-template <class Scope>
-__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, PhaseShared& sh) {
+template <class Scope, class SH>
+__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
   Scal* sc = a.sc;
   double A[9], t[3], c[3];
 #pragma unroll
@@ -159,8 +161,8 @@ __device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int f
 
 // ---- NORM1 / NORM2: cdcl_normalize_matches (cdcl :1159-1240, rrl :864-943).  The std::set of matched
 // fixed features becomes "the match with the lowest position wins the stamp of its to-feature". ----------
-template <class Scope>
-__device__ void lrr_phase_norm1(const Scope& scope, const DirArgs& a, PhaseShared& sh) {
+template <class Scope, class SH>
+__device__ void lrr_phase_norm1(const Scope& scope, const DirArgs& a, SH& sh) {
   Scal* sc = a.sc;
   const int mapped = sc->from_mapped;
   const double invM = 1.0;
@@ -190,8 +192,8 @@ __device__ void lrr_phase_norm1(const Scope& scope, const DirArgs& a, PhaseShare
   scope.phase_end();
 }
 
-template <class Scope>
-__device__ void lrr_phase_norm2(const Scope& scope, const DirArgs& a, Scal* other /* null or the opposite direction */, PhaseShared& sh) {
+template <class Scope, class SH>
+__device__ void lrr_phase_norm2(const Scope& scope, const DirArgs& a, Scal* other /* null or the opposite direction */, SH& sh) {
   Scal* sc = a.sc;
   const double c0 = sc->cto[0], c1 = sc->cto[1], c2 = sc->cto[2];
   double acc[1] = {0};
@@ -317,9 +319,9 @@ __device__ __forceinline__ double lrr_scale_of(const Scal* sc, int M, int flags,
 // ---- WEIGHT: estimate_scale_and_assign_weight (cdcl :660-822, rrl :577-718), the first half of
 // weight_by_strength (cdcl :826-862, rrl :722-752) and of weight_spatially (cdcl :973-1004, rrl :756-778) --
 // dir = 0/1; reversed = this list joins the merged list with from/to swapped (cdcl sym add_constraints)
-template <class Scope>
+template <class Scope, class SH>
 __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags, int reversed, const SelDev& selG, const SelDev& selS,
-                                 int scale_mode, double scale_in, PhaseShared& sh) {
+                                 int scale_mode, double scale_in, SH& sh) {
   Scal* sc = a.sc;
   const bool sym = (flags & LRR_F_SYM) != 0;
   const double unit = sym ? 1.0 : sc->rto;   // forward estimators weight in normalised coordinates (Q3)
@@ -383,9 +385,9 @@ __device__ void lrr_phase_collect(const Scope& scope, const DirArgs& a, int flag
 //   T[j][b][p] = sum w x~_j x~_b P_p   (b = 0..3, p = xx,xy,xz,yy,yz,zz)      V[j][d] = sum w x~_j (P b^)_d
 // from which J^T W J / J^T W b of ANY transform whose Jacobian is affine in x (affine, small-angle rigid) is
 // assembled once at the end — 27 fp64 accumulators per lane instead of 90 per thread.
-template <class Scope>
+template <class Scope, class SH>
 __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int flags, int reversed, int keep_w, double G, double S,
-                                     const double* jc /* centre subtracted inside the Jacobian */, PhaseShared& sh) {
+                                     const double* jc /* centre subtracted inside the Jacobian */, SH& sh) {
   Scal* sc = a.sc;
   const int mapped = sc->from_mapped;
   const bool sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0;
@@ -665,8 +667,8 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
 
 // ---- RESID: residuals of the current matches under the current transform: RMS_error (cdcl :196-230,
 // rrl :211-241 Q1), weighted_error (cdcl :236-268, rrl :247-276), scale-from-weights sums (cdcl :698-701) ----
-template <class Scope>
-__device__ void lrr_phase_resid(const Scope& scope, const DirArgs& a, PhaseShared& sh) {
+template <class Scope, class SH>
+__device__ void lrr_phase_resid(const Scope& scope, const DirArgs& a, SH& sh) {
   Scal* sc = a.sc;
   const int mapped = sc->from_mapped;
   double A[9], t[3], c[3];
