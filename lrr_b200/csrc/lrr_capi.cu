@@ -538,8 +538,11 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters) {
     { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches); }
     { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
   }
+  if (getenv("LRR_DEBUG_NOHIST")) a.flags |= 256;
   { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
-  if (e->strength || e->sym()) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
+  static const bool dbg_nohist = getenv("LRR_DEBUG_NOHIST") != nullptr;   // timing experiment only: wrong scales
+  if (dbg_nohist) a.flags |= 256;
+  if ((e->strength || e->sym()) && !dbg_nohist) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
   { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches); }
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   e->werr_cache_valid = false;

@@ -295,9 +295,9 @@ struct GridScope {
       double s = 0;
       for (int w = 0; w < nw; ++w) s += sh_tmp[w * KG + k];
       partials[(size_t)blockIdx.x * LRR_NRED + k] = s;
+      __threadfence();   // only the writers of the partial row fence (a gpu-scope fence per thread is not free)
     }
     __shared__ bool is_last;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned int t = atomicAdd(ticket, 1u);

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
   const int reversed = merged && dir != a.src;
   const bool fin = lrr_phase_weight(lrr_scope(a, dir), a.d[dir], a.flags, reversed, a.selG[group], a.selS[group], ex.scale_mode[dir],
                                     ex.scale_in[dir], sh);
-  if (!fin) return;
+  if (!fin || (a.flags & 256)) return;
   // group-level: locate the fine bins of the two order statistics
   if (merged && a.ndir == 2) {
     if (!lrr_pair_done(a, 2)) return;

@@ -79,11 +79,12 @@ __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, i
 template <class Scope, class SH>
 __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
   Scal* sc = a.sc;
-  double A[9], t[3], c[3];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) A[i] = sc->A[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { t[i] = sc->t[i]; c[i] = sc->c[i]; }
+  // the transform is uniform: keep it in shared memory (broadcast loads) instead of 30 registers per thread
+  __shared__ double s_T[15];
+  __syncthreads();
+  if (threadIdx.x < 15) s_T[threadIdx.x] = threadIdx.x < 9 ? sc->A[threadIdx.x] : (threadIdx.x < 12 ? sc->t[threadIdx.x - 9] : sc->c[threadIdx.x - 12]);
+  __syncthreads();
+  const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
   const bool rigid = (flags & LRR_F_RIGID) != 0;
   const GridDev& g = a.to.grid;
   double acc[4] = {0, 0, 0, 0};
@@ -223,10 +224,18 @@ __device__ __forceinline__ int lrr_sel_bin(const SelDev& s, double key) {
   int b = (int)(key * s.inv_width);
   return b < 0 ? 0 : (b >= LRR_SEL_FINE ? LRR_SEL_FINE - 1 : b);
 }
+// Histogram update with warp aggregation: lanes that hit the same fine bin (the strength cap puts ~1.5 % of all
+// keys into the last bin) elect a leader that adds their count once, so no address sees more than one atomic
+// per warp.  Called under divergence: the mask is the set of currently active lanes.
 __device__ __forceinline__ void lrr_sel_add(const SelDev& s, double key) {
   const int b = lrr_sel_bin(s, key);
-  atomicAdd(s.fine + b, 1u);
-  atomicAdd(s.coarse + (b >> 6), 1u);
+  const unsigned int active = __activemask();
+  const unsigned int same = __match_any_sync(active, b);
+  const int lane = threadIdx.x & 31;
+  if (lane == __ffs(same) - 1) atomicAdd(s.fine + b, (unsigned int)__popc(same));
+  const int cb = b >> 6;
+  const unsigned int samec = __match_any_sync(active, cb);
+  if (lane == __ffs(samec) - 1) atomicAdd(s.coarse + cb, (unsigned int)__popc(samec));
 }
 // Called by ONE block (all LRR_THREADS threads) once every key of the group is in the histogram: locate
 // the fine bin of the (n-1)/2+1 -th smallest key (0-based) — the element the reference's private
@@ -349,7 +358,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else g = sp * sq;
       if (g > LRR_STRENGTH_CAP) g = LRR_STRENGTH_CAP;
       gk = g;
-      if (selG.fine) lrr_sel_add(selG, fabs(g));
+      if (selG.fine && !(flags & 256)) lrr_sel_add(selG, fabs(g));
       acc[0] += 1.0;
     }
     if (sym && s >= 0) {
@@ -358,7 +367,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else lrr_from_loc(a, sc, mapped, i, qx, qy, qz);
       qx = (qx - sc0) * isr; qy = (qy - sc1) * isr; qz = (qz - sc2) * isr;
       sk = 1.0 / (1.0 + 5.0 * (qx * qx + qy * qy + qz * qz));   // reference: sqrt then square (cdcl :984-985)
-      if (selS.fine) lrr_sel_add(selS, sk);
+      if (selS.fine && !(flags & 256)) lrr_sel_add(selS, sk);
     }
     a.w[k] = w; a.gkey[k] = gk; a.skey[k] = sk;
   }
