@@ -486,6 +486,7 @@ static int do_find_closest(lrr_est* e) {
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1;
   for (int d = 0; d < nd; ++d) {
+    if (e->d[d].to_all->n == 0 || e->d[d].n_in == 0) { ctx->err = "find_closest_euclidean: empty feature set"; return LRR_ERR_STATE; }
     int rc = apply_shuffle(e, d); if (rc != LRR_OK) return rc;
     e->d[d].epoch += 1;
     if (e->d[d].epoch == 0xFFFFFFFFu) {   // stamp epochs exhausted: start over

@@ -1,0 +1,114 @@
+"""Edge cases of the hot path on the GPU against the CPU oracle: ties and duplicates in the neighbour search, tiny and
+ragged feature sets, degenerate order statistics (all keys equal / capped), subsets with repeated entries, empty sets."""
+import numpy as np
+import pytest
+
+from lrr_b200 import synth
+from lrr_b200.capi import LrrError
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def both(gpu_lib, oracle_lib, pair, kind, n_iter, setup=None, dof=12):
+    out = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+        est = ctx.estimator(kind, mv, fx, dof)
+        est.set_flags(True, True)
+        est.set_transform(*pair["init"])
+        if setup:
+            setup(est)
+        conv = [est.one_iteration(i) for i in range(n_iter)]
+        out.append((est, conv))
+    (g, cg), (o, co) = out
+    assert cg == co
+    for d in ((0, 1) if "sym" in kind else (0,)):
+        gf, gt, gw = g.get_matches(d); of, ot, ow = o.get_matches(d)
+        assert np.array_equal(gf, of) and np.array_equal(gt, ot)
+        assert rel(gw, ow) < 1e-8
+        G, O = g.get_transform(d), o.get_transform(d)
+        assert rel(G["A"], O["A"]) < 1e-5 and rel(G["t"], O["t"]) < 1e-5 and rel(G["cov"], O["cov"]) < 1e-5
+    return g, o
+
+
+def test_duplicate_fixed_points_tie_to_lowest_index(gpu_lib, oracle_lib):
+    pair = synth.make_pair(41, 3000, 2000)
+    f = pair["fixed"]
+    # every feature of the second half is an exact copy (location) of one in the first half: ties everywhere
+    n = f["xyz"].shape[1]; h = n // 2
+    f["xyz"][:, h:2 * h] = f["xyz"][:, :h]
+    q = np.ascontiguousarray(f["xyz"][:, :500] + 1e-9)
+    gi = gpu_lib.context().upload(f).nearest(q)
+    oi = oracle_lib.context().upload(f).nearest(q)
+    assert np.array_equal(gi, oi)
+    exact = gpu_lib.context().upload(f).nearest(np.ascontiguousarray(f["xyz"][:, h:h + 300]))
+    assert np.array_equal(exact, np.arange(300))          # the copy with the lower index wins
+    both(gpu_lib, oracle_lib, pair, "rrl_sym", 4)
+
+
+def test_tiny_sets_below_the_1000_point_start(gpu_lib, oracle_lib):
+    """number_points_ = min(1000, |moving|): 60 / 45 features, first iteration already at the finest level."""
+    pair = synth.make_pair(42, 60, 45, size=40.0)
+    g, o = both(gpu_lib, oracle_lib, pair, "cdcl_sym", 5)
+    assert g.state().number_points[0] == 45 and g.state().number_points[1] == 60
+    both(gpu_lib, oracle_lib, pair, "rrl_fwd", 3)
+
+
+def test_ragged_sizes(gpu_lib, oracle_lib):
+    pair = synth.make_pair(43, 7001, 1033, size=90.0)     # very different set sizes, not multiples of anything
+    both(gpu_lib, oracle_lib, pair, "rrl_sym", 6)
+    both(gpu_lib, oracle_lib, pair, "cdcl_fwd", 3, setup=lambda e: e.set_number_points(1033))
+
+
+def test_equal_and_capped_strengths(gpu_lib, oracle_lib):
+    """All strength products equal (order statistic among identical keys) and all above the 90000 cap (cdcl :843)."""
+    pair = synth.make_pair(44, 3000, 2500, size=80.0)
+    for s in (7.0, 1000.0):
+        pair["fixed"]["strength"][:] = s; pair["moving"]["strength"][:] = s
+        both(gpu_lib, oracle_lib, pair, "rrl_sym", 4)
+        both(gpu_lib, oracle_lib, pair, "cdcl_fwd", 3, setup=lambda e: e.set_number_points(2500))
+
+
+def test_subset_with_repeated_entries_and_order(gpu_lib, oracle_lib):
+    pair = synth.make_pair(45, 4000, 3000, size=80.0)
+    rng = np.random.default_rng(1)
+    mi = rng.integers(0, 3000, size=1800).astype(np.int32)      # with repetitions, unsorted
+    fi = rng.permutation(4000)[:2200].astype(np.int32)
+
+    def setup(e):
+        e.set_subsets(mi, fi)
+        e.set_transform(*pair["init"])
+    both(gpu_lib, oracle_lib, pair, "rrl_sym", 5, setup=setup)
+
+
+def test_empty_inputs(gpu_lib):
+    ctx = gpu_lib.context()
+    empty = {"xyz": np.zeros((3, 0)), "P6": np.zeros((6, 0)), "C6": None, "strength": np.zeros(0), "shape": np.zeros(0, np.uint8), "dirs": None}
+    fs = ctx.upload(empty)
+    assert fs.nearest(np.zeros((3, 5))).tolist() == [-1] * 5       # empty set: no neighbour
+    pair = synth.make_pair(46, 500, 400, size=40.0)
+    mv = ctx.upload(pair["moving"])
+    est = ctx.estimator("cdcl_fwd", mv, fs, 12)
+    est.set_transform(*pair["init"])
+    with pytest.raises(LrrError):
+        est.one_iteration(0)                                       # nothing to match against: reported, not crashed
+    assert ctx.batch_run(mv, ctx.upload(pair["fixed"]), np.zeros(0, dtype=synth.make_jobs(pair, 1, 1, 0).dtype), 10, 0).shape == (0,)
+
+
+def test_bad_arguments(gpu_lib):
+    ctx = gpu_lib.context()
+    pair = synth.make_pair(47, 300, 300, size=30.0)
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    with pytest.raises(LrrError):
+        ctx.estimator("rrl_sym", mv, fx, 6)                        # Q6: rrl is not instantiated for <3,6>
+    est = ctx.estimator("cdcl_fwd", mv, fx, 12)
+    with pytest.raises(LrrError):
+        est.set_subsets(np.array([0, 5, 300], dtype=np.int32))     # index out of range
+    with pytest.raises(LrrError):
+        est.set_order(np.arange(10, dtype=np.int32))               # wrong length
