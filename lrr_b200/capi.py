@@ -158,7 +158,7 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.fn("ctx_launch_count")(self.h))
 
-    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "other"]
+    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "fused_iteration"]
 
     def set_profiling(self, on: bool):
         self.check(self.lib.fn("ctx_set_profiling")(self.h, int(on)), "ctx_set_profiling")

@@ -481,8 +481,8 @@ static int apply_shuffle(lrr_est* e, int dir) {
   return LRR_OK;
 }
 
-// find_closest_euclidean of every direction (cdcl :541-654, sym wrappers)
-static int do_find_closest(lrr_est* e) {
+// find_closest_euclidean of every direction (cdcl :541-654, sym wrappers): host part (permutation keys, stamp epochs)
+static int prepare_find_closest(lrr_est* e) {
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1;
   for (int d = 0; d < nd; ++d) {
@@ -494,10 +494,43 @@ static int do_find_closest(lrr_est* e) {
       e->d[d].epoch = 1;
     }
   }
-  EstArgs a = est_args(e);
-  { PHASE(PH_MATCH); lrr_k_match(a, ctx->stream, &ctx->launches); }
+  return LRR_OK;
+}
+static void finish_find_closest(lrr_est* e, const EstArgs& a) {
+  const int nd = e->sym() ? 2 : 1;
   for (int d = 0; d < nd; ++d) { e->d[d].matches = a.d[d].M; e->d[d].weights_fresh = true; }
   e->werr_cache_valid = false;
+}
+static int do_find_closest(lrr_est* e) {
+  lrr_ctx* ctx = e->ctx;
+  int rc = prepare_find_closest(e); if (rc != LRR_OK) return rc;
+  EstArgs a = est_args(e);
+  { PHASE(PH_MATCH); lrr_k_match(a, ctx->stream, &ctx->launches); }
+  finish_find_closest(e, a);
+  return LRR_OK;
+}
+
+// One whole iteration (find_closest + estimate_LS + residuals under the new transform) as one cooperative persistent
+// kernel (lrr_coop.cu).  Steady state only: the first estimate after set_transform needs the MUSE sort.
+cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches);
+static bool fused_ok(lrr_est* e) {
+  static const bool off = getenv("LRR_NO_FUSED") != nullptr;
+  if (off) return false;
+  const int nd = e->sym() ? 2 : 1;
+  for (int d = 0; d < nd; ++d) if (!e->d[d].scale_estimated) return false;
+  return true;
+}
+static int do_iteration_fused(lrr_est* e) {
+  lrr_ctx* ctx = e->ctx;
+  int rc = prepare_find_closest(e); if (rc != LRR_OK) return rc;
+  EstArgs a = est_args(e, 0);
+  a.estimate_parameters = 1;
+  const int nd = e->sym() ? 2 : 1;
+  for (int d = 0; d < nd; ++d) if (a.d[d].M <= 0) { ctx->err = "one_iteration without points"; return LRR_ERR_STATE; }
+  const int mode[2] = {0, 0}; const double sin[2] = {0, 0};
+  { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, ctx->stream, &ctx->launches)); }
+  finish_find_closest(e, a);
+  for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   return LRR_OK;
 }
 
@@ -575,10 +608,14 @@ extern "C" int lrr_est_find_closest(lrr_est* e) {
 
 static int one_iteration_fwd(lrr_est* e, int* converged) {
   lrr_ctx* ctx = e->ctx;
-  int rc = do_find_closest(e); if (rc != LRR_OK) return rc;
-  if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
-  EstArgs a = est_args(e);
-  { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
+  int rc;
+  if (fused_ok(e)) { if ((rc = do_iteration_fused(e)) != LRR_OK) return rc; }
+  else {
+    if ((rc = do_find_closest(e)) != LRR_OK) return rc;
+    if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
+    EstArgs a = est_args(e);
+    { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
+  }
   if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double before = rms_of(e, e->h[0], false), after = rms_of(e, e->h[0], true);
@@ -604,10 +641,13 @@ static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out)
   double before;
   if (e->werr_cache_valid) before = e->werr_cache;
   else if ((rc = weighted_error_now(e, 0, &before)) != LRR_OK) return rc;
-  if ((rc = do_find_closest(e)) != LRR_OK) return rc;
-  if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
-  EstArgs a = est_args(e);
-  { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
+  if (fused_ok(e)) { if ((rc = do_iteration_fused(e)) != LRR_OK) return rc; }
+  else {
+    if ((rc = do_find_closest(e)) != LRR_OK) return rc;
+    if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
+    EstArgs a = est_args(e);
+    { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
+  }
   if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double after = werr_of(e->h[0]);

@@ -74,20 +74,20 @@ __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, i
   acc[3] += r2;
 }
 
-// pass A: one thread per query, ball scan bounded by the previous neighbour of the same from-feature;
-// queries without a candidate or with a large ball go to the direction's queue
-template <class Scope, class SH>
-__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
-  Scal* sc = a.sc;
-  // the transform is uniform: keep it in shared memory (broadcast loads) instead of 30 registers per thread
-  __shared__ double s_T[15];
+// stage the (uniform) transform of a direction in shared memory: broadcast loads instead of 30 registers per thread
+__device__ __forceinline__ void lrr_stage_transform(const Scal* sc, double* s_T /* 15 doubles shared */) {
   __syncthreads();
   if (threadIdx.x < 15) s_T[threadIdx.x] = threadIdx.x < 9 ? sc->A[threadIdx.x] : (threadIdx.x < 12 ? sc->t[threadIdx.x - 9] : sc->c[threadIdx.x - 12]);
   __syncthreads();
+}
+
+// pass A: one thread per query, ball scan bounded by the previous neighbour of the same from-feature;
+// queries without a candidate take the 27 cells around them; unfinished queries go to the direction's queue
+template <class Scope>
+__device__ __forceinline__ void lrr_match_a_body(const Scope& scope, const DirArgs& a, int flags, const double* s_T, double (&acc)[4]) {
   const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
   const bool rigid = (flags & LRR_F_RIGID) != 0;
   const GridDev& g = a.to.grid;
-  double acc[4] = {0, 0, 0, 0};
   const int* __restrict__ proc = (a.proc && a.M == a.n_in) ? a.proc : nullptr;
   for (int tq = scope.first(); tq < a.M; tq += scope.stride()) {
     const int k = proc ? __ldg(proc + tq) : tq;
@@ -112,28 +112,16 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
       a.hq_k[slot] = k; a.hq_best[slot] = st.best; a.hq_s[slot] = st.best_s; a.hq_o[slot] = st.best_o;
     }
   }
-  if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
-    if (threadIdx.x == 0) {
-      sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
-    }
-  }
-  scope.phase_end();
 }
 
-// pass B: one warp per queued query, shells 2.. ; adds its sums to the direction's scalars
-template <class Scope, class SH>
-__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
-  Scal* sc = a.sc;
-  double A[9], t[3], c[3];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) A[i] = sc->A[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { t[i] = sc->t[i]; c[i] = sc->c[i]; }
+// pass B: one warp per queued query
+template <class Scope>
+__device__ __forceinline__ void lrr_match_b_body(const Scope& scope, const DirArgs& a, int flags, const double* s_T, double (&acc)[4]) {
+  const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
   const bool rigid = (flags & LRR_F_RIGID) != 0;
   const int lane = threadIdx.x & 31;
   const int nq = *a.hq_count;
   const GridDev& g = a.to.grid;
-  double acc[4] = {0, 0, 0, 0};
   for (int qi = scope.first() >> 5; qi < nq; qi += scope.stride() >> 5) {
     const int kq = a.hq_k[qi];
     const int i = lrr_from_index(a, kq);
@@ -144,17 +132,44 @@ __device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int f
     const int s = lrr_nn_pass_b(g, yx, yy, yz, st);
     if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc);
   }
+}
+
+// bookkeeping once every match of the direction exists (sums of both passes in `tot`)
+__device__ __forceinline__ void lrr_match_finalize(const DirArgs& a, int flags, const double* tot) {
+  Scal* sc = a.sc;
+  sc->sum_loc[0] = tot[0]; sc->sum_loc[1] = tot[1]; sc->sum_loc[2] = tot[2]; sc->sum_r2 = tot[3];
+  sc->res_sum_r2 = tot[3]; sc->res_count = (double)a.M;
+  *a.hq_count = 0;
+  if (flags & LRR_F_RIGID) {   // make_incremental: the matches' from_ are now clones mapped through the current transform
+    for (int i = 0; i < 9; ++i) sc->Ag[i] = sc->A[i];
+    for (int i = 0; i < 3; ++i) { sc->tg[i] = sc->t[i]; sc->cg[i] = sc->c[i]; }
+    sc->from_mapped = 1;
+  } else sc->from_mapped = 0;
+}
+
+template <class Scope, class SH>
+__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
+  __shared__ double s_T[15];
+  lrr_stage_transform(a.sc, s_T);
+  double acc[4] = {0, 0, 0, 0};
+  lrr_match_a_body(scope, a, flags, s_T, acc);
+  if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) { Scal* sc = a.sc; sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3]; }
+  }
+  scope.phase_end();
+}
+
+template <class Scope, class SH>
+__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
+  __shared__ double s_T[15];
+  lrr_stage_transform(a.sc, s_T);
+  double acc[4] = {0, 0, 0, 0};
+  lrr_match_b_body(scope, a, flags, s_T, acc);
   if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
     if (threadIdx.x == 0) {
-      const double s0 = sc->sum_loc[0] + sh.out[0], s1 = sc->sum_loc[1] + sh.out[1], s2 = sc->sum_loc[2] + sh.out[2], s3 = sc->sum_r2 + sh.out[3];
-      sc->sum_loc[0] = s0; sc->sum_loc[1] = s1; sc->sum_loc[2] = s2; sc->sum_r2 = s3;
-      sc->res_sum_r2 = s3; sc->res_count = (double)a.M;
-      *a.hq_count = 0;
-      if (rigid) {   // make_incremental: the matches' from_ are now clones mapped through the current transform
-        for (int i = 0; i < 9; ++i) sc->Ag[i] = sc->A[i];
-        for (int i = 0; i < 3; ++i) { sc->tg[i] = sc->t[i]; sc->cg[i] = sc->c[i]; }
-        sc->from_mapped = 1;
-      } else sc->from_mapped = 0;
+      const Scal* sc = a.sc;
+      const double tot[4] = {sc->sum_loc[0] + sh.out[0], sc->sum_loc[1] + sh.out[1], sc->sum_loc[2] + sh.out[2], sc->sum_r2 + sh.out[3]};
+      lrr_match_finalize(a, flags, tot);
     }
   }
   scope.phase_end();
@@ -240,11 +255,11 @@ __device__ __forceinline__ void lrr_sel_add(const SelDev& s, double key) {
 // Called by ONE block (all LRR_THREADS threads) once every key of the group is in the histogram: locate
 // the fine bin of the (n-1)/2+1 -th smallest key (0-based) — the element the reference's private
 // rrel_util_median_abs_dev_scale picks with nth_element (cdcl :520-536, Q12).
-static __device__ void lrr_sel_locate(const SelDev& s, double n_keys, double* shd /* >= 2*LRR_THREADS doubles */) {
+static __device__ void lrr_sel_locate(const SelDev& s, double n_keys, double* shd /* >= 2*LRR_THREADS doubles */, bool reset_cand = true) {
   unsigned int* shu = reinterpret_cast<unsigned int*>(shd);
   __shared__ unsigned int s_target, s_cbin, s_cbase;
   const long long n = (long long)n_keys;
-  if (threadIdx.x == 0) { *s.count = n_keys; *s.cand_count = 0; s.cand_minmax[0] = ~0ull; s.cand_minmax[1] = 0ull; }
+  if (threadIdx.x == 0) { *s.count = n_keys; if (reset_cand) { *s.cand_count = 0; s.cand_minmax[0] = ~0ull; s.cand_minmax[1] = 0ull; } }
   if (n <= 1) { if (threadIdx.x == 0) { *s.bin = -1; *s.rank = 0; *s.result = 0.0; } __syncthreads(); return; }
   const unsigned int target = (unsigned int)((n - 1) / 2 + 1);
   // coarse level: 4 bins per thread, inclusive scan over threads
