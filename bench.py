@@ -54,6 +54,8 @@ KERNEL_BYTES = {
     "collect": (16, 0),
     "accumulate": (24 + 4 + 8 + 8 + 8 + 24 + 48 + 8, 0),
     "resid": (24 + 4 + 24 + 48 + 8 + 8, 0),
+    # the whole iteration as one cooperative kernel: SURVEY.md §8(d) bytes per iteration (124 B per match + 24 B per to-feature)
+    "fused_iteration": (BYTES_PER_MATCH, BYTES_PER_FIXED),
 }
 
 
@@ -385,7 +387,7 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "flushed (256 MiB write) between timed iterations; working set ~30 MB is L2-resident otherwise",
                    "ramp_iterations": ramp_iters, "ramp_converged": bool(ramp_conv)},
         "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else "k_" + dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": None, "peak_kind": peak_kind,
                      "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
         "roofline_iteration": {"algorithmic_bytes": it_bytes, "achieved_gbs": it_bytes / (ms_step * 1e-3) / 1e9,

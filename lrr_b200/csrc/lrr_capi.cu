@@ -512,7 +512,7 @@ static int do_find_closest(lrr_est* e) {
 
 // One whole iteration (find_closest + estimate_LS + residuals under the new transform) as one cooperative persistent
 // kernel (lrr_coop.cu).  Steady state only: the first estimate after set_transform needs the MUSE sort.
-cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches);
+cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, long long* dbg, cudaStream_t st, long long* launches);
 static bool fused_ok(lrr_est* e) {
   static const bool off = getenv("LRR_NO_FUSED") != nullptr;
   if (off) return false;
@@ -528,7 +528,17 @@ static int do_iteration_fused(lrr_est* e) {
   const int nd = e->sym() ? 2 : 1;
   for (int d = 0; d < nd; ++d) if (a.d[d].M <= 0) { ctx->err = "one_iteration without points"; return LRR_ERR_STATE; }
   const int mode[2] = {0, 0}; const double sin[2] = {0, 0};
-  { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, ctx->stream, &ctx->launches)); }
+  static const bool dbgph = getenv("LRR_FUSED_DEBUG") != nullptr;
+  long long* dbg = dbgph ? (long long*)(ctx->scratch_d + 512) : nullptr;
+  { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, dbg, ctx->stream, &ctx->launches)); }
+  if (dbgph) {
+    static int calls = 0;
+    if (++calls % 20 == 0) {
+      long long h[16]; cudaStreamSynchronize(ctx->stream); cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost); cudaMemset(dbg, 0, sizeof(h));
+      const char* nm[12] = {"matchA", "sync", "matchB", "reduce", "norm", "weight", "locate", "collect+sel", "accum", "solve", "sync2", "resid"};
+      for (int i = 0; i < 12; ++i) fprintf(stderr, "[fused block 0] %-12s %8.1f us/iter\n", nm[i], h[i] / 1.9e3 / 20);
+    }
+  }
   finish_find_closest(e, a);
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   return LRR_OK;

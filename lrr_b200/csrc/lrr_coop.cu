@@ -74,7 +74,8 @@ struct CoopScope {
   __device__ __forceinline__ void phase_end() const { __syncthreads(); }   // the block's own Scal writes become visible to its threads
 };
 
-struct CoopExtra { int scale_mode[2]; double scale_in[2]; };
+struct CoopExtra { int scale_mode[2]; double scale_in[2]; long long* dbg; };
+#define CPH(i) do { if (ex.dbg && blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); ex.dbg[i] += now_ - tmark; tmark = now_; } } while (0)
 
 __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_constant__ EstArgs a, const CoopExtra ex) {
   __shared__ PhaseShared sh;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
   const int nd = a.ndir, flags = a.flags;
   const bool merged = (flags & LRR_F_MERGED) != 0, sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0;
   const bool use_sel = strength || sym;
+  long long tmark = clock64();
 
   // ---- housekeeping: candidate lists empty (invariant shared with the multi-kernel path: the histograms are zero on entry) ----
   if (use_sel) {
@@ -100,14 +102,18 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
   // ---- MATCH: pass A, barrier (queues complete), pass B, one reduction for both directions ----
   for (int d = 0; d < nd; ++d) lrr_stage_transform(a.d[d].sc, s_T[d]);
   double m0[4] = {0, 0, 0, 0}, m1[4] = {0, 0, 0, 0};
-  lrr_match_a_body(scope, a.d[0], flags, s_T[0], m0);
-  if (nd == 2) lrr_match_a_body(scope, a.d[1], flags, s_T[1], m1);
+  lrr_match_a_body_dynamic(a.d[0], flags, s_T[0], a.ticket + 4, m0);
+  if (nd == 2) lrr_match_a_body_dynamic(a.d[1], flags, s_T[1], a.ticket + 5, m1);
+  CPH(0);
   grid.sync();
-  lrr_match_b_body(scope, a.d[0], flags, s_T[0], m0);
-  if (nd == 2) lrr_match_b_body(scope, a.d[1], flags, s_T[1], m1);
+  CPH(1);
+  lrr_match_b_body_dynamic(a.d[0], flags, s_T[0], a.ticket + 6, m0);
+  if (nd == 2) lrr_match_b_body_dynamic(a.d[1], flags, s_T[1], a.ticket + 7, m1);
   {
+    CPH(2);
     double acc[8] = {m0[0], m0[1], m0[2], m0[3], m1[0], m1[1], m1[2], m1[3]};
     scope.reduce<8>(acc, sh.out, sh.tmp);
+    CPH(3);
     if (threadIdx.x < nd) lrr_match_finalize(a.d[threadIdx.x], flags, sh.out + 4 * threadIdx.x);
     scope.phase_end();
   }
@@ -116,12 +122,14 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
     lrr_phase_norm1(scope, a.d[a.src], sh);
     lrr_phase_norm2(scope, a.d[a.src], nd == 2 ? a.d[1 - a.src].sc : nullptr, sh);
   }
+  CPH(4);
   // ---- WEIGHT ----
   for (int d = 0; d < nd; ++d) {
     const int group = merged ? 0 : d;
     lrr_phase_weight(scope, a.d[d], flags, merged && d != a.src, a.selG[group], a.selS[group], ex.scale_mode[d], ex.scale_in[d], sh);
     scope.phase_end();
   }
+  CPH(5);
   if (use_sel) {
     // every block locates the bins of the order statistics itself (identical results)
     if (merged && nd == 2) {
@@ -134,6 +142,7 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
       }
     }
     __syncthreads();
+    CPH(6);
     // ---- COLLECT ----
     for (int d = 0; d < nd; ++d) { const int group = merged ? 0 : d; lrr_phase_collect(scope, a.d[d], flags, a.selG[group], a.selS[group]); }
     grid.sync();
@@ -149,6 +158,7 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
     }
     __syncthreads();
   }
+  CPH(7);
   // ---- ACCUMULATE + SOLVE ----
   {
     double jc[3] = {0, 0, 0};
@@ -158,9 +168,12 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
       lrr_phase_accumulate(scope, a.d[d], flags, sym && d != a.src, merged && d != a.src, strength ? scd->G : 1.0, sym ? scd->S : 1.0, jc, sh);
     }
     __syncthreads();
+    CPH(8);
     if (blockIdx.x == 0) lrr_solve(a.d[a.src].sc, nd == 2 ? a.d[1 - a.src].sc : nullptr, flags, a.dof, a.estimate_parameters);
     __threadfence();
+    CPH(9);
     grid.sync();
+    CPH(10);
   }
   // the histograms are not read after the bins were located: zero them again for the next weight phase
   if (use_sel) {
@@ -172,6 +185,9 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
   }
   // ---- RESID under the new transform ----
   lrr_phase_resid(scope, a.d[0], sh);
+  // work counters of the two search passes: zero again for the next launch (every block is past the last barrier)
+  if (blockIdx.x == 0 && threadIdx.x < 4) a.ticket[4 + threadIdx.x] = 0;
+  CPH(11);
 }
 
 int lrr_coop_blocks() {
@@ -187,8 +203,8 @@ int lrr_coop_blocks() {
   return nb;
 }
 
-cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches) {
-  CoopExtra ex;
+cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, long long* dbg, cudaStream_t st, long long* launches) {
+  CoopExtra ex; ex.dbg = dbg;
   for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
   void* args[2] = {(void*)&a, (void*)&ex};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_iteration, dim3(lrr_coop_blocks()), dim3(LRR_THREADS), args, 0, st);

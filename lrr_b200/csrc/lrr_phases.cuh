@@ -83,55 +83,87 @@ __device__ __forceinline__ void lrr_stage_transform(const Scal* sc, double* s_T 
 
 // pass A: one thread per query, ball scan bounded by the previous neighbour of the same from-feature;
 // queries without a candidate take the 27 cells around them; unfinished queries go to the direction's queue
-template <class Scope>
-__device__ __forceinline__ void lrr_match_a_body(const Scope& scope, const DirArgs& a, int flags, const double* s_T, double (&acc)[4]) {
+__device__ __forceinline__ void lrr_match_a_one(const DirArgs& a, int flags, const double* s_T, const int* __restrict__ proc, int tq, double (&acc)[4]) {
   const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
   const bool rigid = (flags & LRR_F_RIGID) != 0;
   const GridDev& g = a.to.grid;
+  const int k = proc ? __ldg(proc + tq) : tq;
+  const int i = lrr_from_index(a, k);
+  const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
+  double yx, yy, yz;
+  lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
+  NNState st; st.best = 1e300; st.best_s = a.prev_s[i]; st.best_o = 0x7fffffff;
+  bool done = false;
+  if (st.best_s >= 0) {
+    const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
+    st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
+    done = lrr_nn_ball_thread(g, yx, yy, yz, st);
+  } else if (g.n > 0) {
+    const int r27 = lrr_nn_block27_thread(g, yx, yy, yz, st);
+    if (r27 == 1) done = true;
+    else if (r27 == 0) done = lrr_nn_ball_thread(g, yx, yy, yz, st);   // rescans the block's rows inside the ball: still exact
+  }
+  if (done) lrr_match_finish(a, rigid, k, i, x, y, z, yx, yy, yz, st.best_s, acc);
+  else {
+    const int slot = atomicAdd(a.hq_count, 1);
+    a.hq_k[slot] = k; a.hq_best[slot] = st.best; a.hq_s[slot] = st.best_s; a.hq_o[slot] = st.best_o;
+  }
+}
+
+template <class Scope>
+__device__ __forceinline__ void lrr_match_a_body(const Scope& scope, const DirArgs& a, int flags, const double* s_T, double (&acc)[4]) {
   const int* __restrict__ proc = (a.proc && a.M == a.n_in) ? a.proc : nullptr;
-  for (int tq = scope.first(); tq < a.M; tq += scope.stride()) {
-    const int k = proc ? __ldg(proc + tq) : tq;
-    const int i = lrr_from_index(a, k);
-    const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
-    double yx, yy, yz;
-    lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
-    NNState st; st.best = 1e300; st.best_s = a.prev_s[i]; st.best_o = 0x7fffffff;
-    bool done = false;
-    if (st.best_s >= 0) {
-      const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
-      st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
-      done = lrr_nn_ball_thread(g, yx, yy, yz, st);
-    } else if (g.n > 0) {
-      const int r27 = lrr_nn_block27_thread(g, yx, yy, yz, st);
-      if (r27 == 1) done = true;
-      else if (r27 == 0) done = lrr_nn_ball_thread(g, yx, yy, yz, st);   // rescans the block's rows inside the ball: still exact
-    }
-    if (done) lrr_match_finish(a, rigid, k, i, x, y, z, yx, yy, yz, st.best_s, acc);
-    else {
-      const int slot = atomicAdd(a.hq_count, 1);
-      a.hq_k[slot] = k; a.hq_best[slot] = st.best; a.hq_s[slot] = st.best_s; a.hq_o[slot] = st.best_o;
-    }
+  for (int tq = scope.first(); tq < a.M; tq += scope.stride()) lrr_match_a_one(a, flags, s_T, proc, tq, acc);
+}
+// persistent-kernel variant: warps pull 32-query chunks from a global counter, so blocks whose queries fall into
+// dense regions of the fixed set do not make everybody else wait at the next grid barrier
+__device__ __forceinline__ void lrr_match_a_body_dynamic(const DirArgs& a, int flags, const double* s_T, unsigned int* counter, double (&acc)[4]) {
+  const int* __restrict__ proc = (a.proc && a.M == a.n_in) ? a.proc : nullptr;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(counter, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const long long base = (long long)chunk * 32;
+    if (base >= a.M) break;
+    const int tq = (int)base + lane;
+    if (tq < a.M) lrr_match_a_one(a, flags, s_T, proc, tq, acc);
+    __syncwarp();
+  }
+}
+
+// one queued query, whole warp
+__device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, const double* s_T, int qi, double (&acc)[4]) {
+  const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
+  const bool rigid = (flags & LRR_F_RIGID) != 0;
+  const int lane = threadIdx.x & 31;
+  const int kq = a.hq_k[qi];
+  const int i = lrr_from_index(a, kq);
+  const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
+  double yx, yy, yz;
+  lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
+  NNState st; st.best = a.hq_best[qi]; st.best_s = a.hq_s[qi]; st.best_o = a.hq_o[qi];
+  const int s = lrr_nn_pass_b(a.to.grid, yx, yy, yz, st);
+  if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc);
+}
+__device__ __forceinline__ void lrr_match_b_body_dynamic(const DirArgs& a, int flags, const double* s_T, unsigned int* counter, double (&acc)[4]) {
+  const int lane = threadIdx.x & 31;
+  const int nq = *a.hq_count;
+  for (;;) {
+    unsigned int qi = 0;
+    if (lane == 0) qi = atomicAdd(counter, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if ((int)qi >= nq) break;
+    lrr_match_b_one(a, flags, s_T, (int)qi, acc);
+    __syncwarp();
   }
 }
 
 // pass B: one warp per queued query
 template <class Scope>
 __device__ __forceinline__ void lrr_match_b_body(const Scope& scope, const DirArgs& a, int flags, const double* s_T, double (&acc)[4]) {
-  const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
-  const bool rigid = (flags & LRR_F_RIGID) != 0;
-  const int lane = threadIdx.x & 31;
   const int nq = *a.hq_count;
-  const GridDev& g = a.to.grid;
-  for (int qi = scope.first() >> 5; qi < nq; qi += scope.stride() >> 5) {
-    const int kq = a.hq_k[qi];
-    const int i = lrr_from_index(a, kq);
-    const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
-    double yx, yy, yz;
-    lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
-    NNState st; st.best = a.hq_best[qi]; st.best_s = a.hq_s[qi]; st.best_o = a.hq_o[qi];
-    const int s = lrr_nn_pass_b(g, yx, yy, yz, st);
-    if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc);
-  }
+  for (int qi = scope.first() >> 5; qi < nq; qi += scope.stride() >> 5) lrr_match_b_one(a, flags, s_T, qi, acc);
 }
 
 // bookkeeping once every match of the direction exists (sums of both passes in `tot`)
