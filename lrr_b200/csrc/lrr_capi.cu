@@ -514,8 +514,10 @@ static int do_find_closest(lrr_est* e) {
 // kernel (lrr_coop.cu).  Steady state only: the first estimate after set_transform needs the MUSE sort.
 cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, long long* dbg, cudaStream_t st, long long* launches);
 static bool fused_ok(lrr_est* e) {
-  static const bool off = getenv("LRR_NO_FUSED") != nullptr;
-  if (off) return false;
+  // Measured on B200 (profiles/r1_summary.md): the fused kernel is not faster than the per-phase kernels (fewer threads in
+  // flight per phase at 128 registers; ~5 us per in-kernel reduction), so it is opt-in.
+  static const bool on = getenv("LRR_FUSED") != nullptr;
+  if (!on) return false;
   const int nd = e->sym() ? 2 : 1;
   for (int d = 0; d < nd; ++d) if (!e->d[d].scale_estimated) return false;
   return true;

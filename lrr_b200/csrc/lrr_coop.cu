@@ -211,3 +211,30 @@ cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const doubl
   ++*launches;
   return e;
 }
+
+// ---- micro-benchmark of the barrier / reduction primitives (diagnostics, not part of the product path) ----
+__global__ void __launch_bounds__(LRR_THREADS, 2) k_sync_probe(double* partials, int reps, int mode, double* out) {
+  __shared__ PhaseShared sh;
+  __shared__ int s_phase;
+  if (threadIdx.x == 0) s_phase = 0;
+  __syncthreads();
+  CoopScope scope; scope.partials = partials; scope.phase = &s_phase;
+  double acc[5] = {1, 2, 3, 4, 5};
+  for (int r = 0; r < reps; ++r) {
+    if (mode == 0) cg::this_grid().sync();
+    else { scope.reduce<5>(acc, sh.out, sh.tmp); acc[0] = sh.out[0] * 1e-9; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = acc[0];
+}
+extern "C" int lrr_debug_sync_probe(double* partials, double* out, int reps, int mode, float* ms) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  void* args[4] = {(void*)&partials, (void*)&reps, (void*)&mode, (void*)&out};
+  const int nb = lrr_coop_blocks();
+  cudaLaunchCooperativeKernel((const void*)k_sync_probe, dim3(nb), dim3(LRR_THREADS), args, 0, 0);
+  cudaDeviceSynchronize();
+  cudaEventRecord(a, 0);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_sync_probe, dim3(nb), dim3(LRR_THREADS), args, 0, 0);
+  cudaEventRecord(b, 0); cudaEventSynchronize(b);
+  cudaEventElapsedTime(ms, a, b);
+  return (int)e;
+}
