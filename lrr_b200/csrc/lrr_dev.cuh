@@ -322,7 +322,7 @@ struct GridScope {
       double s[KL];
 #pragma unroll
       for (int j = 0; j < KL; ++j) s[j] = 0;
-#pragma unroll 4
+#pragma unroll 8
       for (unsigned int b = wid; b < gridDim.x; b += nw) {
 #pragma unroll
         for (int j = 0; j < KL; ++j) { const int k = lane + 32 * j; if (k < KG) s[j] += __ldcg(&partials[(size_t)b * LRR_NRED + k]); }

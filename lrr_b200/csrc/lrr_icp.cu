@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
   lrr_solve(a.d[a.src].sc, a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, a.flags, a.dof, a.estimate_parameters);
 }
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
-  dim3 grid(nblk_for(4LL * maxM(a)), a.ndir);
+  // two blocks per SM at most: the last block sums one row of 108 moments per block before it can solve
+  dim3 grid(std::min(nblk_for(4LL * maxM(a)), 2 * lrr_num_sms()), a.ndir);
   k_accumulate<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
 }
 

@@ -715,9 +715,10 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
         double acc = (-invA[3 * i]) * F->t[0]; acc += (-invA[3 * i + 1]) * F->t[1]; acc += (-invA[3 * i + 2]) * F->t[2];
         B->t[i] = acc + F->c[i]; B->c[i] = 0.0;
       }
-      for (int e = 0; e < dof * dof; ++e) B->cov[e] = 0.0;
     }
   }
+  __syncthreads();
+  if (B && estimate_parameters) for (int e = tid; e < dof * dof; e += blockDim.x) B->cov[e] = 0.0;   // inverse(): fresh covariance
   __syncthreads();
 }
 
