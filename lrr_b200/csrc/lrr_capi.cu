@@ -84,8 +84,8 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
   ok = ok && dmalloc(&ctx->sel_hist, 4 * sel_uints) == cudaSuccess;
   ok = ok && cudaMemset(ctx->sel_hist, 0, 4 * sel_uints * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && dmalloc(&ctx->sel_cand, (size_t)4 * LRR_SEL_CAP) == cudaSuccess;
-  ok = ok && dmalloc(&ctx->sel_misc, (size_t)4 * 8) == cudaSuccess;   // 8 x 8 bytes per selector
-  ok = ok && cudaMemset(ctx->sel_misc, 0, 4 * 8 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && dmalloc(&ctx->sel_misc, (size_t)4 * 16) == cudaSuccess;   // 16 x 8 bytes per selector
+  ok = ok && cudaMemset(ctx->sel_misc, 0, 4 * 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && dmalloc(&ctx->muse_table, 4 * 32) == cudaSuccess;
   ok = ok && dmalloc(&ctx->scratch_d, 1024) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&ctx->pinned, 2 * sizeof(Scal) + 4096) == cudaSuccess;
@@ -95,9 +95,9 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
     SelDev& s = ctx->sel[i];
     s.fine = ctx->sel_hist + (size_t)i * sel_uints; s.coarse = s.fine + LRR_SEL_FINE;
     s.cand = ctx->sel_cand + (size_t)i * LRR_SEL_CAP;
-    unsigned long long* m = ctx->sel_misc + (size_t)i * 8;
+    unsigned long long* m = ctx->sel_misc + (size_t)i * 16;
     s.cand_minmax = m; s.cand_count = (unsigned int*)(m + 2); s.bin = (int*)(m + 3); s.rank = (unsigned int*)(m + 4);
-    s.count = (double*)(m + 5); s.result = (double*)(m + 6);
+    s.count = (double*)(m + 5); s.result = (double*)(m + 6); s.bracket = (double*)(m + 8);
     s.inv_width = (i < 2) ? (double)LRR_SEL_FINE / LRR_STRENGTH_CAP : (double)LRR_SEL_FINE;   // G keys in [0,9e4], S keys in (0,1]
   }
   *out = ctx;
@@ -532,6 +532,7 @@ static int do_iteration_fused(lrr_est* e) {
   const int mode[2] = {0, 0}; const double sin[2] = {0, 0};
   static const bool dbgph = getenv("LRR_FUSED_DEBUG") != nullptr;
   long long* dbg = dbgph ? (long long*)(ctx->scratch_d + 512) : nullptr;
+  ctx->sel_owner = 0;
   { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, dbg, ctx->stream, &ctx->launches)); }
   if (dbgph) {
     static int calls = 0;
@@ -561,7 +562,7 @@ static int muse_for_dir(lrr_est* e, const EstArgs& a, int d) {
 }
 
 // estimate_LS (cdcl :1009-1093, cdcl sym :398-701, rrl :783-859, rrl sym :699-918) on the device
-static int do_estimate(lrr_est* e, int src, int estimate_parameters) {
+static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_hist = false) {
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1;
   EstArgs a = est_args(e, src);
@@ -584,15 +585,44 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters) {
     { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches); }
     { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
   }
-  if (getenv("LRR_DEBUG_NOHIST")) a.flags |= 256;
+  // order statistics: window around the previous iteration's values when this estimator was the last user of the
+  // context's selectors with the same configuration, else (first estimate, other estimator) histograms + collect pass
+  // (the signature also covers the point counts: a ramp step resamples the keys, so the first estimate after it uses histograms)
+  const unsigned long long sel_sig = (unsigned long long)(uintptr_t)e ^ ((unsigned long long)a.flags << 48) ^ ((unsigned long long)src << 40) ^
+                                     ((unsigned long long)a.d[0].M * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)(nd == 2 ? a.d[1].M : 0) * 0xC2B2AE3D27D4EB4FULL);
+  const bool window = !force_hist && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym());
+  if (window) a.flags |= LRR_F_BRACKET;
+  ctx->sel_owner = sel_sig;
   { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
-  static const bool dbg_nohist = getenv("LRR_DEBUG_NOHIST") != nullptr;   // timing experiment only: wrong scales
-  if (dbg_nohist) a.flags |= 256;
-  if ((e->strength || e->sym()) && !dbg_nohist) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
+  if ((e->strength || e->sym()) && !window) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
   { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches); }
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   e->werr_cache_valid = false;
   return LRR_OK;
+}
+
+// estimate_LS + residuals under the new transform + scalar read-back.  A miss of the order-statistic window (rare: the
+// key distribution jumped) leaves the transform untouched on the device; the estimate is then repeated with histograms.
+static int estimate_and_pull(lrr_est* e, int resid_mask) {
+  lrr_ctx* ctx = e->ctx;
+  const int nd = e->sym() ? 2 : 1, mask = dmask(e);
+  bool fresh0[2], se0[2];
+  for (int d = 0; d < 2; ++d) { fresh0[d] = e->d[d].weights_fresh; se0[d] = e->d[d].scale_estimated; }
+  int rc = do_estimate(e, 0, 1); if (rc != LRR_OK) return rc;
+  { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
+  if ((rc = pull_scal(e, mask)) != LRR_OK) return rc;
+  bool miss = false;
+  for (int d = 0; d < nd; ++d) miss = miss || (e->h[d].status & LRR_ST_SELECT_MISS);
+  if (!miss) return LRR_OK;
+  ctx->window_misses += 1;
+  for (int d = 0; d < nd; ++d) {
+    e->h[d].status &= ~LRR_ST_SELECT_MISS;
+    if ((rc = push_scal(e, d)) != LRR_OK) return rc;
+    e->d[d].weights_fresh = fresh0[d]; e->d[d].scale_estimated = se0[d];
+  }
+  if ((rc = do_estimate(e, 0, 1, true)) != LRR_OK) return rc;
+  { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
+  return pull_scal(e, mask);
 }
 
 static int check_status(lrr_est* e) {
@@ -621,14 +651,13 @@ extern "C" int lrr_est_find_closest(lrr_est* e) {
 static int one_iteration_fwd(lrr_est* e, int* converged) {
   lrr_ctx* ctx = e->ctx;
   int rc;
-  if (fused_ok(e)) { if ((rc = do_iteration_fused(e)) != LRR_OK) return rc; }
-  else {
+  if (fused_ok(e)) {
+    if ((rc = do_iteration_fused(e)) != LRR_OK) return rc;
+    if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
+  } else {
     if ((rc = do_find_closest(e)) != LRR_OK) return rc;
-    if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
-    EstArgs a = est_args(e);
-    { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
+    if ((rc = estimate_and_pull(e, 1)) != LRR_OK) return rc;
   }
-  if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double before = rms_of(e, e->h[0], false), after = rms_of(e, e->h[0], true);
   *converged = std::fabs(before - after) < 1e-4;   // cdcl :506
@@ -653,14 +682,13 @@ static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out)
   double before;
   if (e->werr_cache_valid) before = e->werr_cache;
   else if ((rc = weighted_error_now(e, 0, &before)) != LRR_OK) return rc;
-  if (fused_ok(e)) { if ((rc = do_iteration_fused(e)) != LRR_OK) return rc; }
-  else {
+  if (fused_ok(e)) {
+    if ((rc = do_iteration_fused(e)) != LRR_OK) return rc;
+    if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
+  } else {
     if ((rc = do_find_closest(e)) != LRR_OK) return rc;
-    if ((rc = do_estimate(e, 0, 1)) != LRR_OK) return rc;
-    EstArgs a = est_args(e);
-    { PHASE(PH_RESID); lrr_k_resid(a, 1, ctx->stream, &ctx->launches); }
+    if ((rc = estimate_and_pull(e, 1)) != LRR_OK) return rc;
   }
-  if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double after = werr_of(e->h[0]);
   e->werr_cache = after; e->werr_cache_valid = true;

@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
     const int ngroups = (merged || nd == 1) ? 1 : 2;
     for (int g = 0; g < ngroups; ++g) {
       bool ok = true;
-      if (strength) ok = lrr_sel_finish(a.selG[g], sh_cand) && ok;
-      if (sym) ok = lrr_sel_finish(a.selS[g], sh_cand) && ok;
+      if (strength) ok = lrr_sel_finish(a.selG[g], sh_cand, false) && ok;   // every block reads the list: no reset here
+      if (sym) ok = lrr_sel_finish(a.selS[g], sh_cand, false) && ok;
       if (threadIdx.x == 0) {
         const double G = strength ? *a.selG[g].result : 1.0, S = sym ? *a.selS[g].result : 1.0;
         for (int d = 0; d < nd; ++d) if (merged || d == g) { a.d[d].sc->G = G; a.d[d].sc->S = S; if (!ok) a.d[d].sc->status |= LRR_ST_SELECT_OVERFLOW; }

@@ -18,6 +18,7 @@ struct lrr_ctx {
   unsigned int* ticket = nullptr;
   unsigned int* sel_hist = nullptr; double* sel_cand = nullptr; unsigned long long* sel_misc = nullptr;
   SelDev sel[4];
+  unsigned long long sel_owner = 0; long long window_misses = 0;   // signature of the last estimate that left valid search windows in the selectors
   SortScratch sort; double* sort_keys = nullptr;
   double* muse_table = nullptr;
   double* scratch_d = nullptr;

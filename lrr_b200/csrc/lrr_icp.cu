@@ -135,22 +135,39 @@ struct WeightExtra { int scale_mode[2]; double scale_in[2]; };
 
 __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex) {
   __shared__ PhaseShared sh;
+  __shared__ double sh_cand[LRR_SEL_CAP];
   const int dir = blockIdx.y;
-  const bool merged = (a.flags & LRR_F_MERGED) != 0;
+  const bool merged = (a.flags & LRR_F_MERGED) != 0, window = (a.flags & LRR_F_BRACKET) != 0;
   const int group = merged ? 0 : dir;
   const int reversed = merged && dir != a.src;
   const bool fin = lrr_phase_weight(lrr_scope(a, dir), a.d[dir], a.flags, reversed, a.selG[group], a.selS[group], ex.scale_mode[dir],
                                     ex.scale_in[dir], sh);
-  if (!fin || (a.flags & 256)) return;
-  // group-level: locate the fine bins of the two order statistics
-  if (merged && a.ndir == 2) {
-    if (!lrr_pair_done(a, 2)) return;
-    const double nG = __ldcg(&a.d[0].sc->n_nonzero) + __ldcg(&a.d[1].sc->n_nonzero);
-    if (a.flags & LRR_F_STRENGTH) lrr_sel_locate(a.selG[0], nG, sh.tmp);
-    if (a.flags & LRR_F_SYM) lrr_sel_locate(a.selS[0], (double)(a.d[0].M + a.d[1].M), sh.tmp);
+  if (!fin) return;
+  // group-level: the two order statistics (window mode: finished here; histogram mode: bins located for k_collect)
+  const bool pair = merged && a.ndir == 2;
+  if (pair && !lrr_pair_done(a, 2)) return;
+  double nG, nS, bG, bS;
+  if (pair) {
+    nG = __ldcg(&a.d[0].sc->n_nonzero) + __ldcg(&a.d[1].sc->n_nonzero); nS = (double)(a.d[0].M + a.d[1].M);
+    bG = __ldcg(&a.d[0].sc->sel_below[0]) + __ldcg(&a.d[1].sc->sel_below[0]); bS = __ldcg(&a.d[0].sc->sel_below[1]) + __ldcg(&a.d[1].sc->sel_below[1]);
   } else {
-    if (a.flags & LRR_F_STRENGTH) lrr_sel_locate(a.selG[group], __ldcg(&a.d[dir].sc->n_nonzero), sh.tmp);
-    if (a.flags & LRR_F_SYM) lrr_sel_locate(a.selS[group], (double)a.d[dir].M, sh.tmp);
+    nG = __ldcg(&a.d[dir].sc->n_nonzero); nS = (double)a.d[dir].M;
+    bG = __ldcg(&a.d[dir].sc->sel_below[0]); bS = __ldcg(&a.d[dir].sc->sel_below[1]);
+  }
+  if (!window) {
+    if (a.flags & LRR_F_STRENGTH) lrr_sel_locate(a.selG[group], nG, sh.tmp);
+    if (a.flags & LRR_F_SYM) lrr_sel_locate(a.selS[group], nS, sh.tmp);
+    return;
+  }
+  bool hit = true;
+  if (a.flags & LRR_F_STRENGTH) hit = lrr_sel_window_finish(a.selG[group], nG, bG, sh_cand) && hit;
+  if (a.flags & LRR_F_SYM) hit = lrr_sel_window_finish(a.selS[group], nS, bS, sh_cand) && hit;
+  if (threadIdx.x == 0) {
+    const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = (a.flags & LRR_F_SYM) ? *a.selS[group].result : 1.0;
+    for (int d = 0; d < a.ndir; ++d) {
+      if (merged || d == dir) { a.d[d].sc->G = G; a.d[d].sc->S = S; }
+      if (!hit) atomicOr(&a.d[d].sc->status, LRR_ST_SELECT_MISS);   // every direction: k_accumulate must skip as a whole
+    }
   }
 }
 static WeightExtra g_dummy_extra;
@@ -209,6 +226,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
   const double G = (a.flags & LRR_F_STRENGTH) ? scd->G : 1.0, S = sym ? scd->S : 1.0;
   double jc[3] = {0, 0, 0};
   if (!(a.flags & LRR_F_NORMALIZE) && !(a.flags & LRR_F_RIGID)) { const Scal* f = a.d[a.src].sc; jc[0] = f->c[0]; jc[1] = f->c[1]; jc[2] = f->c[2]; }
+  if (scd->status & LRR_ST_SELECT_MISS) return;   // window miss (set on every direction by k_weight): nothing is committed, the host reruns
   const bool fin = lrr_phase_accumulate(lrr_scope(a, dir), a.d[dir], a.flags, reversed, keep_w, G, S, jc, sh);
   if (!fin) return;
   if (!lrr_pair_done(a, a.ndir)) return;
@@ -223,6 +241,7 @@ void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
 __global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0) {
   __shared__ PhaseShared sh;
   const int dir = dir0 + blockIdx.y;
+  if (a.d[dir].sc->status & LRR_ST_SELECT_MISS) return;   // the estimate was not committed: keep the residuals of the match for the rerun
   lrr_phase_resid(lrr_scope(a, dir), a.d[dir], sh);
 }
 void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches) {

@@ -55,6 +55,7 @@ struct SelDev {
   double* count;           // number of keys
   double* result;          // the MAD scale (0 when count <= 1)
   double inv_width;        // key -> fine bin = min(FINE-1, (int)(key * inv_width))
+  double* bracket;         // [0] lo, [1] hi, [2] relative half width, [3] last order statistic: search window of the next call
 };
 
 // Device-resident scalars of one direction (forward_ or backward_ of an estimator).
@@ -72,7 +73,7 @@ struct Scal {
   double sum_q[3], n_unique, sum_rad_from;   // norm1
   double sum_rad_to;                         // norm2
   double scale; int scale_estimated, pad1;
-  double n_nonzero;
+  double n_nonzero, sel_below[2];
   double G, S;
   double res_sum_r2, res_sum_wr2, res_sum_w, res_sum_wr, res_count;   // resid phase
   double mom[LRR_NRED];
@@ -85,7 +86,8 @@ struct Scal {
 enum {
   LRR_ST_OK = 0,
   LRR_ST_SELECT_OVERFLOW = 1,   // candidate list overflow in the exact selection (host falls back to sort)
-  LRR_ST_SINGULAR = 2
+  LRR_ST_SINGULAR = 2,
+  LRR_ST_SELECT_MISS = 4        // the order statistic fell outside the predicted window: the host reruns the estimate with histograms
 };
 
 struct DirArgs {
@@ -119,7 +121,8 @@ enum {
   LRR_F_SYM = 8,          // symmetric estimator (scale before normalisation, spatial weighting)
   LRR_F_STRENGTH = 16,    // weight_by_strength_
   LRR_F_MERGED = 32,      // cdcl symmetric: backward matches join the forward list reversed (one G, one S)
-  LRR_F_USE_OLD_W = 64    // scale from the current weights (estimate_LS_backward after estimate_LS)
+  LRR_F_USE_OLD_W = 64,   // scale from the current weights (estimate_LS_backward after estimate_LS)
+  LRR_F_BRACKET = 512     // order statistics from the window around the previous iteration's values (no histogram atomics, no collect pass)
 };
 
 struct EstArgs {

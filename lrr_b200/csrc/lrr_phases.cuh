@@ -336,7 +336,7 @@ __device__ __forceinline__ void lrr_sel_offer(const SelDev& s, int bin, double k
 }
 // Called by ONE block after every candidate is in the list: exact rank selection, then the MAD scale.
 // Returns (in every thread) false on candidate overflow with distinct values (host falls back to a sort).
-static __device__ bool lrr_sel_finish(const SelDev& s, double* sh_cand /* >= LRR_SEL_CAP doubles */) {
+static __device__ bool lrr_sel_finish(const SelDev& s, double* sh_cand /* >= LRR_SEL_CAP doubles */, bool reset_cand = true) {
   __shared__ double s_val; __shared__ int s_ok;
   const double n_keys = *s.count;
   if (n_keys <= 1.0) { if (threadIdx.x == 0) *s.result = 0.0; __syncthreads(); return true; }
@@ -358,10 +358,79 @@ static __device__ bool lrr_sel_finish(const SelDev& s, double* sh_cand /* >= LRR
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && s_ok) *s.result = 1.4826 * (1.0 + 5.0 / (n_keys - 1.0)) * s_val;
+  if (threadIdx.x == 0) {
+    if (s_ok) {
+      *s.result = 1.4826 * (1.0 + 5.0 / (n_keys - 1.0)) * s_val;
+      // search window of the next call: sized from the local key density (cnt keys in one fine bin) to hold ~1.5 % of the keys
+      double want = n_keys / 512.0; want = want < 64.0 ? 64.0 : (want > 256.0 ? 256.0 : want);
+      const double density = (double)(cnt > 0 ? cnt : 1) * s.inv_width;
+      double d = s_val > 0.0 ? 0.5 * want / density / s_val : 0.02;
+      d = d < 1e-5 ? 1e-5 : (d > 0.25 ? 0.25 : d);
+      s.bracket[0] = s_val * (1.0 - d); s.bracket[1] = s_val * (1.0 + d); s.bracket[2] = d; s.bracket[3] = s_val;
+    }
+    if (reset_cand) *s.cand_count = 0;
+  }
   const bool ok = s_ok != 0;
   __syncthreads();
   return ok;
+}
+
+// ---- exact order statistic without a histogram: window predicted from the previous iteration ---------------
+// ICP changes the key distributions slowly, so the wanted element almost always lies inside a narrow window around
+// its previous value.  The weight pass counts the keys below the window and appends the keys inside it (a few hundred
+// atomics instead of two per key); if the wanted rank falls into the window the exact element is picked by rank
+// counting, otherwise the call reports a miss and the host reruns the estimate on the histogram path.
+__device__ __forceinline__ void lrr_sel_window_offer(const SelDev& s, double key, double lo, double hi, double& below) {
+  if (key < lo) below += 1.0;
+  else if (key <= hi) { const unsigned int slot = atomicAdd(s.cand_count, 1u); if (slot < LRR_SEL_CAP) s.cand[slot] = key; }
+}
+// Called by ONE block once every key was offered.  Returns (every thread) true on a hit.
+static __device__ bool lrr_sel_window_finish(const SelDev& s, double n_keys, double below, double* sh_cand) {
+  __shared__ double s_val; __shared__ int s_hit;
+  const long long n = (long long)n_keys;
+  const unsigned int cnt = __ldcg(s.cand_count);
+  if (threadIdx.x == 0) { s_hit = 0; s_val = 0.0; *s.count = n_keys; }
+  __syncthreads();
+  if (n <= 1) {
+    if (threadIdx.x == 0) { *s.result = 0.0; *s.cand_count = 0; }
+    __syncthreads();
+    return true;
+  }
+  const long long target = (n - 1) / 2 + 1, nb = (long long)below;
+  const bool hit = cnt <= LRR_SEL_CAP && nb <= target && target < nb + (long long)cnt;
+  if (hit) {
+    // bitonic sort of the window's keys in shared memory, then the element of the wanted rank
+    const unsigned int rank = (unsigned int)(target - nb);
+    unsigned int np = 1; while (np < cnt) np <<= 1;
+    for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) sh_cand[i] = (i < cnt) ? __ldcg(s.cand + i) : 1e308;
+    __syncthreads();
+    for (unsigned int k = 2; k <= np; k <<= 1)
+      for (unsigned int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) {
+          const unsigned int ixj = i ^ jj;
+          if (ixj > i) {
+            const double x = sh_cand[i], y = sh_cand[ixj];
+            if ((x > y) == ((i & k) == 0)) { sh_cand[i] = y; sh_cand[ixj] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    if (threadIdx.x == 0) { s_val = sh_cand[rank]; s_hit = 1; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (s_hit) {
+      *s.result = 1.4826 * (1.0 + 5.0 / (n_keys - 1.0)) * s_val;
+      double want = n_keys / 512.0; want = want < 64.0 ? 64.0 : (want > 256.0 ? 256.0 : want);   // ~0.2 % of the keys inside the window
+      double d = s.bracket[2] * want / (double)(cnt > 0 ? cnt : 1);
+      d = d < 1e-5 ? 1e-5 : (d > 0.25 ? 0.25 : d);
+      s.bracket[0] = s_val * (1.0 - d); s.bracket[1] = s_val * (1.0 + d); s.bracket[2] = d; s.bracket[3] = s_val;
+    }
+    *s.cand_count = 0;
+  }
+  const bool res = s_hit != 0;
+  __syncthreads();
+  return res;
 }
 
 // squared scale of the direction in the units the weights are computed in
@@ -390,7 +459,10 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
   if (!reversed) { sc0 = sc->cto[0]; sc1 = sc->cto[1]; sc2 = sc->cto[2]; sr = sc->rto; }
   else { sc0 = sc->cfrom[0]; sc1 = sc->cfrom[1]; sc2 = sc->cfrom[2]; sr = sc->rfrom; }
   const double isr = 1.0 / sr;
-  double acc[1] = {0};
+  const bool window = (flags & LRR_F_BRACKET) != 0;
+  double gLo = 0, gHi = 0, sLo = 0, sHi = 0;
+  if (window) { if (selG.bracket) { gLo = selG.bracket[0]; gHi = selG.bracket[1]; } if (selS.bracket) { sLo = selS.bracket[0]; sHi = selS.bracket[1]; } }
+  double acc[3] = {0, 0, 0};   // keys of G, keys of G below its window, keys of S below its window
   for (int k = scope.first(); k < a.M; k += scope.stride()) {
     const int s = a.sidx[k];
     const double r2n = a.r2[k] * inv_unit2;
@@ -405,7 +477,8 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else g = sp * sq;
       if (g > LRR_STRENGTH_CAP) g = LRR_STRENGTH_CAP;
       gk = g;
-      if (selG.fine && !(flags & 256)) lrr_sel_add(selG, fabs(g));
+      if (window) lrr_sel_window_offer(selG, fabs(g), gLo, gHi, acc[1]);
+      else if (selG.fine) lrr_sel_add(selG, fabs(g));
       acc[0] += 1.0;
     }
     if (sym && s >= 0) {
@@ -414,12 +487,13 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else lrr_from_loc(a, sc, mapped, i, qx, qy, qz);
       qx = (qx - sc0) * isr; qy = (qy - sc1) * isr; qz = (qz - sc2) * isr;
       sk = 1.0 / (1.0 + 5.0 * (qx * qx + qy * qy + qz * qz));   // reference: sqrt then square (cdcl :984-985)
-      if (selS.fine && !(flags & 256)) lrr_sel_add(selS, sk);
+      if (window) lrr_sel_window_offer(selS, sk, sLo, sHi, acc[2]);
+      else if (selS.fine) lrr_sel_add(selS, sk);
     }
     a.w[k] = w; a.gkey[k] = gk; a.skey[k] = sk;
   }
-  const bool fin = scope.template reduce<1>(acc, sh.out, sh.tmp);
-  if (fin && threadIdx.x == 0) { sc->n_nonzero = sh.out[0]; sc->scale = scale; sc->scale_estimated = 1; }
+  const bool fin = scope.template reduce<3>(acc, sh.out, sh.tmp);
+  if (fin && threadIdx.x == 0) { sc->n_nonzero = sh.out[0]; sc->sel_below[0] = sh.out[1]; sc->sel_below[1] = sh.out[2]; sc->scale = scale; sc->scale_estimated = 1; }
   return fin;
 }
 
