@@ -590,7 +590,11 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   // (the signature also covers the point counts: a ramp step resamples the keys, so the first estimate after it uses histograms)
   const unsigned long long sel_sig = (unsigned long long)(uintptr_t)e ^ ((unsigned long long)a.flags << 48) ^ ((unsigned long long)src << 40) ^
                                      ((unsigned long long)a.d[0].M * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)(nd == 2 ? a.d[1].M : 0) * 0xC2B2AE3D27D4EB4FULL);
-  const bool window = !force_hist && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym());
+  // (small problems are latency-bound either way, and while the transform still moves fast the medians move too: after a
+  //  miss the window is not tried again for a growing number of estimates)
+  const int maxM = std::max(a.d[0].M, nd == 2 ? a.d[1].M : 0);
+  bool window = !force_hist && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym()) && maxM >= 16384;
+  if (window && e->window_holdoff > 0) { e->window_holdoff -= 1; window = false; }
   if (window) a.flags |= LRR_F_BRACKET;
   ctx->sel_owner = sel_sig;
   { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
@@ -613,8 +617,9 @@ static int estimate_and_pull(lrr_est* e, int resid_mask) {
   if ((rc = pull_scal(e, mask)) != LRR_OK) return rc;
   bool miss = false;
   for (int d = 0; d < nd; ++d) miss = miss || (e->h[d].status & LRR_ST_SELECT_MISS);
-  if (!miss) return LRR_OK;
+  if (!miss) { if (e->window_holdoff == 0) e->window_backoff = 0; return LRR_OK; }
   ctx->window_misses += 1;
+  e->window_backoff = std::min(2 * (e->window_backoff + 1), 16); e->window_holdoff = e->window_backoff;
   for (int d = 0; d < nd; ++d) {
     e->h[d].status &= ~LRR_ST_SELECT_MISS;
     if ((rc = push_scal(e, d)) != LRR_OK) return rc;

@@ -70,6 +70,7 @@ struct lrr_est {
   unsigned oscillation_count = 0; double error_difference = 0, weighted_error = 0;
   unsigned number_matches = 1000; int finest_level = 0; int iterations_done = 0;
   bool werr_cache_valid = false; double werr_cache = 0;
+  int window_holdoff = 0, window_backoff = 0;   // order-statistic window: estimates to skip after a miss
   bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
   bool rrl() const { return kind == LRR_RRL_FWD || kind == LRR_RRL_SYM; }
 };
