@@ -101,18 +101,22 @@ void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* 
 __global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const __grid_constant__ EstArgs a) {
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
-  lrr_phase_match(lrr_scope(a, dir), a.d[dir], a.flags, sh);
+  lrr_phase_match(lrr_scope(a, dir), a.d[dir], a.flags, sh, a.ticket + 4 + dir);
 }
-__global__ void __launch_bounds__(LRR_THREADS) k_match_hard(const __grid_constant__ EstArgs a) {
+#ifndef LRR_HARD_MINBLK
+#define LRR_HARD_MINBLK 2
+#endif
+__global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(const __grid_constant__ EstArgs a) {
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
-  lrr_phase_match_hard(lrr_scope(a, dir), a.d[dir], a.flags, sh);
+  lrr_phase_match_hard(lrr_scope(a, dir), a.d[dir], a.flags, sh, a.ticket + 6 + dir);
 }
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
-  dim3 grid(nblk_for(maxM(a)), a.ndir);
+  // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
+  dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
   k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
   // queue length is only known on the device: a fixed grid of warps strides over it
-  dim3 gridb(nblk_for(std::min<long long>(32LL * maxM(a), (long long)lrr_num_sms() * 4 * LRR_THREADS)), a.ndir);
+  dim3 gridb(std::min(nblk_for(32LL * maxM(a)), 2 * lrr_num_sms()), a.ndir);
   k_match_hard<<<gridb, LRR_THREADS, 0, st>>>(a); ++*launches;
 }
 

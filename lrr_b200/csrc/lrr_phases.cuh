@@ -179,29 +179,37 @@ __device__ __forceinline__ void lrr_match_finalize(const DirArgs& a, int flags, 
   } else sc->from_mapped = 0;
 }
 
+// `counter` (grid scope only): work counter for dynamic 32-query chunks — warps that drew cheap queries keep pulling
+// instead of waiting at the block reduction for the warp that drew a dense region (23 % barrier stalls before).
 template <class Scope, class SH>
-__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
+__device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags, SH& sh, unsigned int* counter = nullptr) {
   __shared__ double s_T[15];
   lrr_stage_transform(a.sc, s_T);
   double acc[4] = {0, 0, 0, 0};
-  lrr_match_a_body(scope, a, flags, s_T, acc);
+  if (counter) lrr_match_a_body_dynamic(a, flags, s_T, counter, acc);
+  else lrr_match_a_body(scope, a, flags, s_T, acc);
   if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
-    if (threadIdx.x == 0) { Scal* sc = a.sc; sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3]; }
+    if (threadIdx.x == 0) {
+      Scal* sc = a.sc; sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
+      if (counter) *counter = 0;
+    }
   }
   scope.phase_end();
 }
 
 template <class Scope, class SH>
-__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, SH& sh) {
+__device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int flags, SH& sh, unsigned int* counter = nullptr) {
   __shared__ double s_T[15];
   lrr_stage_transform(a.sc, s_T);
   double acc[4] = {0, 0, 0, 0};
-  lrr_match_b_body(scope, a, flags, s_T, acc);
+  if (counter) lrr_match_b_body_dynamic(a, flags, s_T, counter, acc);
+  else lrr_match_b_body(scope, a, flags, s_T, acc);
   if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
     if (threadIdx.x == 0) {
       const Scal* sc = a.sc;
       const double tot[4] = {sc->sum_loc[0] + sh.out[0], sc->sum_loc[1] + sh.out[1], sc->sum_loc[2] + sh.out[2], sc->sum_r2 + sh.out[3]};
       lrr_match_finalize(a, flags, tot);
+      if (counter) *counter = 0;
     }
   }
   scope.phase_end();
