@@ -162,19 +162,23 @@ __device__ __forceinline__ void lrr_ball_row(const GridDev& g, int y, int z, dou
 }
 
 // pass A.  st holds a candidate (best_s >= 0).  Returns false when the ball touches too many rows.
+// The x-range of the ball's bounding box is used for every row (no square root / floor per row: for the one to four
+// rows of a typical ball the extra cells cost less than the per-row arithmetic did).
 __device__ __forceinline__ bool lrr_nn_ball_thread(const GridDev& g, double qx, double qy, double qz, NNState& st) {
   const double slack = 1e-9 * g.h;
   const double R = sqrt(st.best) * (1.0 + 1e-9) + slack;
   const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
   const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
   if ((z1 - z0 + 1) * (y1 - y0 + 1) > LRR_BALL_ROWS) return false;
+  const int xa = lrr_cell_clamp(qx - R, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + R, g.ox, g.inv_h, g.nx);
   for (int z = z0; z <= z1; ++z) {
     const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dz2 = dz * dz;
     if (dz2 > st.best) continue;
     for (int y = y0; y <= y1; ++y) {
-      const double dy = lrr_slab_dist(qy, g.oy, g.h, y, slack), dyz2 = dz2 + dy * dy;
-      if (dyz2 > st.best) continue;
-      lrr_ball_row(g, y, z, dyz2, qx, qy, qz, slack, st.best, st.best_s, st.best_o);
+      const double dy = lrr_slab_dist(qy, g.oy, g.h, y, slack);
+      if (dz2 + dy * dy > st.best) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), qx, qy, qz, st.best, st.best_s, st.best_o);
     }
   }
   return true;
