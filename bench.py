@@ -381,6 +381,15 @@ def run_b200(args, rank, world, local_rank):
         us = 1e3 * ms / cnt
         per_phase[name] = {"us_per_launch": us, "launches": cnt, "algorithmic_bytes": by, "gbs": by / (us * 1e-6) / 1e9 if us > 0 else None}
     d = per_phase.get(dom, {"gbs": 0, "us_per_launch": 0, "algorithmic_bytes": 0})
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bench.py cannot run under a profiler)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        names = {"match": ["k_match", "k_match_hard"], "accumulate": ["k_accumulate"], "weight": ["k_weight"]}.get(dom, [])
+        if names and all(n in tj["dram_bytes_per_launch"] for n in names):
+            traffic = sum(tj["dram_bytes_per_launch"][n] for n in names); traffic_src = tj["source"]
+    except Exception:
+        pass
     it_bytes = algorithmic_bytes_iteration(M, N, M, N)
     ms_step = total_ms_max / args.steps
     line = {
@@ -391,7 +400,7 @@ def run_b200(args, rank, world, local_rank):
                    "ramp_iterations": ramp_iters, "ramp_converged": bool(ramp_conv)},
         "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else "k_" + dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": None, "peak_kind": peak_kind,
+                     "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                      "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
         "roofline_iteration": {"algorithmic_bytes": it_bytes, "achieved_gbs": it_bytes / (ms_step * 1e-3) / 1e9,
                                "frac": it_bytes / (ms_step * 1e-3) / 1e9 / peak,
