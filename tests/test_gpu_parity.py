@@ -204,3 +204,49 @@ def test_cpp_host_api():
         subprocess.check_call(["make", "-C", os.path.dirname(exe)])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_order_statistic_window_miss_and_rerun(gpu_lib, oracle_lib):
+    """Steady-state iterations take the order statistics from a window around the previous value; jumping the transform
+    between iterations moves the key distributions out of the window: the miss must be detected and the estimate rerun
+    on the histogram path with results identical to the oracle."""
+    pair = synth.make_pair(51, 24000, 22000, size=140.0)
+    ests = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        e = ctx.estimator("rrl_sym", ctx.upload(pair["moving"]), ctx.upload(pair["fixed"]), 12)
+        e.set_transform(*pair["init"])
+        e.set_number_points(22000, 0); e.set_number_points(24000, 1)
+        ests.append(e)
+    g, o = ests
+    A0, t0, c0 = pair["init"]
+    for it in range(9):
+        if it in (4, 7):   # jump: new transform, same point counts (the window of the previous iteration is stale)
+            dA = synth.rot_xyz(0.05 * (it - 3), -0.04, 0.03)
+            for e in (g, o):
+                e.set_transform(dA @ A0, t0 + np.array([4.0, -3.0, 2.0]), c0)
+                e.set_number_points(22000, 0); e.set_number_points(24000, 1)
+        cg, co = g.one_iteration(it), o.one_iteration(it)
+        assert cg == co
+        compare_state(g, o, dirs=(0, 1))
+
+
+def test_fused_iteration_kernel():
+    """The cooperative one-kernel-per-iteration path (opt-in, LRR_FUSED=1) reproduces the oracle as well."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from lrr_b200 import synth, lib\nfrom lrr_b200.capi import Lib\n"
+        "pair = synth.make_pair(52, 9000, 8000, size=100.0)\nres = []\n"
+        "for L in (lib(), Lib(%r, 'lrro_')):\n"
+        "    ctx = L.context(); e = ctx.estimator('rrl_sym', ctx.upload(pair['moving']), ctx.upload(pair['fixed']), 12)\n"
+        "    e.set_transform(*pair['init']); conv = [e.one_iteration(i) for i in range(12)]\n"
+        "    res.append((e.get_transform(0), e.get_matches(0), e.get_matches(1), conv))\n"
+        "(Tg, mg, bg, cg), (To, mo, bo, co) = res\n"
+        "assert cg == co and np.array_equal(mg[1], mo[1]) and np.array_equal(bg[1], bo[1])\n"
+        "for k in ('A', 't', 'cov'): assert np.linalg.norm(Tg[k] - To[k]) / np.linalg.norm(To[k]) < 1e-5, k\n"
+        "print('fused ok', lib().context().launch_count())\n"
+    ) % (root, os.path.join(root, "oracle", "liblrr_oracle.so"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LRR_FUSED="1"), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout + out.stderr
