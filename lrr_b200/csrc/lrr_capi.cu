@@ -562,11 +562,12 @@ static int muse_for_dir(lrr_est* e, const EstArgs& a, int d) {
 }
 
 // estimate_LS (cdcl :1009-1093, cdcl sym :398-701, rrl :783-859, rrl sym :699-918) on the device
-static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_hist = false) {
+static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_hist = false, bool cdcl_backward = false) {
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1;
   EstArgs a = est_args(e, src);
   a.estimate_parameters = estimate_parameters;
+  if (cdcl_backward) a.flags |= LRR_F_NOSPATIAL | LRR_F_NO_OTHER_RENORM;
   for (int d = 0; d < nd; ++d) if (e->d[d].matches <= 0 || a.d[d].M <= 0) { ctx->err = "estimate_LS without matches"; return LRR_ERR_STATE; }
   // stale weights (not straight after find_closest): residuals under the current transform first (cdcl :698-701)
   int stale = 0;
@@ -581,7 +582,8 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
       D.scale_estimated = true;
     }
   }
-  if (e->normalize) {
+  if (e->normalize && cdcl_backward) { PHASE(PH_NORM1); lrr_k_norm_merged(a, ctx->stream, &ctx->launches); }
+  else if (e->normalize) {
     { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches); }
     { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
   }
@@ -593,12 +595,12 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   // (small problems are latency-bound either way, and while the transform still moves fast the medians move too: after a
   //  miss the window is not tried again for a growing number of estimates)
   const int maxM = std::max(a.d[0].M, nd == 2 ? a.d[1].M : 0);
-  bool window = !force_hist && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym()) && maxM >= 16384;
+  bool window = !force_hist && !cdcl_backward && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym()) && maxM >= 16384;
   if (window && e->window_holdoff > 0) { e->window_holdoff -= 1; window = false; }
   if (window) a.flags |= LRR_F_BRACKET;
   ctx->sel_owner = sel_sig;
   { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
-  if ((e->strength || e->sym()) && !window) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
+  if ((e->strength || (e->sym() && !cdcl_backward)) && !window) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
   { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches); }
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   e->werr_cache_valid = false;
@@ -824,9 +826,16 @@ extern "C" int lrr_est_metric(lrr_est* e, int which, int dir, double* out) {
 extern "C" int lrr_est_estimate_ls_backward(lrr_est* e, int estimate_parameters) {
   if (!e || !e->sym()) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
-  if (e->kind == LRR_CDCL_SYM) { ctx->err = "estimate_LS_backward: cdcl symmetric variant not built yet (rrl only)"; return LRR_ERR_UNSUPPORTED; }
+  if (e->kind == LRR_CDCL_SYM) {
+    // cdcl variant (cdcl sym :705-863): the backward matches plus the forward matches reversed, normalised as ONE list,
+    // strength re-weighting over the merged list, no spatial weighting; only backward_->trans_ is (un)normalised.
+    if (e->dof != 12) { ctx->err = "estimate_LS_backward: cdcl symmetric rigid variant (doubly mapped clones) is not built"; return LRR_ERR_UNSUPPORTED; }
+    int rc = do_estimate(e, 1, estimate_parameters, true, true); if (rc != LRR_OK) return rc;
+    if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
+    return check_status(e);
+  }
   // rrl: swap forward_/backward_, estimate_LS, swap back (rrl sym :922-934)
-  int rc = do_estimate(e, 1, estimate_parameters); if (rc != LRR_OK) return rc;
+  int rc = do_estimate(e, 1, estimate_parameters, true); if (rc != LRR_OK) return rc;
   if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
   return check_status(e);
 }

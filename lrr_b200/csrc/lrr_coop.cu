@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
   __syncthreads();
   CoopScope scope; scope.partials = a.partials; scope.phase = &s_phase;
   const int nd = a.ndir, flags = a.flags;
-  const bool merged = (flags & LRR_F_MERGED) != 0, sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0;
+  const bool merged = (flags & LRR_F_MERGED) != 0, sym = LRR_SPATIAL(flags), strength = (flags & LRR_F_STRENGTH) != 0;   // sym: spatial weighting on
   const bool use_sel = strength || sym;
   long long tmark = clock64();
 
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(LRR_THREADS, 2) k_iteration(const __grid_const
     if (!(flags & LRR_F_NORMALIZE) && !(flags & LRR_F_RIGID)) { const Scal* f = a.d[a.src].sc; jc[0] = f->c[0]; jc[1] = f->c[1]; jc[2] = f->c[2]; }
     for (int d = 0; d < nd; ++d) {
       const Scal* scd = a.d[d].sc;
-      lrr_phase_accumulate(scope, a.d[d], flags, sym && d != a.src, merged && d != a.src, strength ? scd->G : 1.0, sym ? scd->S : 1.0, jc, sh);
+      lrr_phase_accumulate(scope, a.d[d], flags, (flags & LRR_F_SYM) && d != a.src, merged && d != a.src, strength ? scd->G : 1.0, sym ? scd->S : 1.0, jc, sh);
     }
     __syncthreads();
     CPH(8);

@@ -135,6 +135,65 @@ void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches) {
   k_norm2<<<nblk_for(a.d[a.src].M), LRR_THREADS, 0, st>>>(a); ++*launches;
 }
 
+// ---- cdcl estimate_LS_backward (cdcl sym :705-863): cdcl_normalize_matches over the MERGED list = the estimated
+// direction's own matches (src) plus the other direction's matches reversed (add_constraints, :744).  The reversed
+// clones are distinct objects, so each of them counts in the "unique to" set; the own to-features count once (stamps).
+// pass 0: centres, pass 1: mean radii.  Scratch: sc->mom[0..8).
+__global__ void __launch_bounds__(LRR_THREADS) k_norm_merged(const __grid_constant__ EstArgs a, int pass) {
+  __shared__ PhaseShared sh;
+  const int dir = blockIdx.y;
+  const DirArgs& d = a.d[dir];
+  Scal* sc = d.sc;
+  const bool own = dir == a.src;
+  const GridScope scope = lrr_scope(a, dir);
+  const int mapped = sc->from_mapped;
+  // centres of the merged from / to sides in THIS direction's roles (own: from/to, reversed: to/from)
+  const Scal* S = a.d[a.src].sc;
+  const double cm0 = S->cfrom[0], cm1 = S->cfrom[1], cm2 = S->cfrom[2], cf0 = S->cto[0], cf1 = S->cto[1], cf2 = S->cto[2];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = scope.first(); k < d.M; k += scope.stride()) {
+    const int s = d.sidx[k];
+    if (s < 0) continue;
+    const int i = lrr_from_index(d, k);
+    double px, py, pz; lrr_from_loc(d, sc, mapped, i, px, py, pz);
+    const double4 q = lrr_ld_pos4(d.to.grid.pos4 + s);
+    const bool rep = own ? (d.stamp[s] == (d.tag | (unsigned long long)(unsigned int)k)) : true;
+    // merged "from" = own from / reversed to ; merged "to" = own to (unique) / reversed from (every clone)
+    const double fx = own ? px : q.x, fy = own ? py : q.y, fz = own ? pz : q.z;
+    const double tx = own ? q.x : px, ty = own ? q.y : py, tz = own ? q.z : pz;
+    if (pass == 0) {
+      acc[0] += fx; acc[1] += fy; acc[2] += fz; acc[6] += 1.0;
+      if (rep) { acc[3] += tx; acc[4] += ty; acc[5] += tz; acc[7] += 1.0; }
+    } else {
+      const double ax = fx - cm0, ay = fy - cm1, az = fz - cm2;
+      acc[0] += sqrt(ax * ax + ay * ay + az * az);
+      if (rep) { const double bx = tx - cf0, by = ty - cf1, bz = tz - cf2; acc[1] += sqrt(bx * bx + by * by + bz * bz); }
+    }
+  }
+  if (!scope.reduce<8>(acc, sh.out, sh.tmp)) return;
+  if (threadIdx.x < 8) sc->mom[threadIdx.x] = sh.out[threadIdx.x];
+  if (!lrr_pair_done(a, 2)) return;
+  if (threadIdx.x == 0) {
+    Scal* own_sc = a.d[a.src].sc; Scal* oth = a.d[1 - a.src].sc;
+    double m[8];
+    for (int j = 0; j < 8; ++j) m[j] = __ldcg(&own_sc->mom[j]) + __ldcg(&oth->mom[j]);
+    if (pass == 0) {
+      for (int j = 0; j < 3; ++j) { own_sc->cfrom[j] = m[j] / m[6]; own_sc->cto[j] = m[3 + j] / m[7]; }
+      own_sc->n_unique = m[7]; own_sc->res_count = m[6];   // res_count: scratch for the merged list length until pass 1
+    } else {
+      own_sc->rfrom = m[0] / own_sc->res_count; own_sc->rto = m[1] / own_sc->n_unique;
+      // the reversed list sees the same normalisation with the roles swapped
+      for (int j = 0; j < 3; ++j) { oth->cfrom[j] = own_sc->cto[j]; oth->cto[j] = own_sc->cfrom[j]; }
+      oth->rfrom = own_sc->rto; oth->rto = own_sc->rfrom;
+    }
+  }
+}
+void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches) {
+  dim3 grid(nblk_for(maxM(a)), 2);
+  k_norm_merged<<<grid, LRR_THREADS, 0, st>>>(a, 0); ++*launches;
+  k_norm_merged<<<grid, LRR_THREADS, 0, st>>>(a, 1); ++*launches;
+}
+
 struct WeightExtra { int scale_mode[2]; double scale_in[2]; };
 
 __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex) {
@@ -160,14 +219,14 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
   }
   if (!window) {
     if (a.flags & LRR_F_STRENGTH) lrr_sel_locate(a.selG[group], nG, sh.tmp);
-    if (a.flags & LRR_F_SYM) lrr_sel_locate(a.selS[group], nS, sh.tmp);
+    if (LRR_SPATIAL(a.flags)) lrr_sel_locate(a.selS[group], nS, sh.tmp);
     return;
   }
   bool hit = true;
   if (a.flags & LRR_F_STRENGTH) hit = lrr_sel_window_finish(a.selG[group], nG, bG, sh_cand) && hit;
-  if (a.flags & LRR_F_SYM) hit = lrr_sel_window_finish(a.selS[group], nS, bS, sh_cand) && hit;
+  if (LRR_SPATIAL(a.flags)) hit = lrr_sel_window_finish(a.selS[group], nS, bS, sh_cand) && hit;
   if (threadIdx.x == 0) {
-    const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = (a.flags & LRR_F_SYM) ? *a.selS[group].result : 1.0;
+    const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = LRR_SPATIAL(a.flags) ? *a.selS[group].result : 1.0;
     for (int d = 0; d < a.ndir; ++d) {
       if (merged || d == dir) { a.d[d].sc->G = G; a.d[d].sc->S = S; }
       if (!hit) atomicOr(&a.d[d].sc->status, LRR_ST_SELECT_MISS);   // every direction: k_accumulate must skip as a whole
@@ -206,9 +265,9 @@ __global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__
   if (merged && a.ndir == 2 && !lrr_pair_done(a, 2)) return;
   bool ok = true;
   if (a.flags & LRR_F_STRENGTH) ok = lrr_sel_finish(a.selG[group], sh_cand) && ok;
-  if (a.flags & LRR_F_SYM) ok = lrr_sel_finish(a.selS[group], sh_cand) && ok;
+  if (LRR_SPATIAL(a.flags)) ok = lrr_sel_finish(a.selS[group], sh_cand) && ok;
   if (threadIdx.x == 0) {
-    const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = (a.flags & LRR_F_SYM) ? *a.selS[group].result : 1.0;
+    const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = LRR_SPATIAL(a.flags) ? *a.selS[group].result : 1.0;
     for (int d = 0; d < a.ndir; ++d) if (merged || d == dir) {
       a.d[d].sc->G = G; a.d[d].sc->S = S;
       if (!ok) a.d[d].sc->status |= LRR_ST_SELECT_OVERFLOW;
@@ -227,7 +286,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
   const int reversed = sym && dir != a.src;
   const int keep_w = merged && dir != a.src;
   const Scal* scd = a.d[dir].sc;
-  const double G = (a.flags & LRR_F_STRENGTH) ? scd->G : 1.0, S = sym ? scd->S : 1.0;
+  const double G = (a.flags & LRR_F_STRENGTH) ? scd->G : 1.0, S = LRR_SPATIAL(a.flags) ? scd->S : 1.0;
   double jc[3] = {0, 0, 0};
   if (!(a.flags & LRR_F_NORMALIZE) && !(a.flags & LRR_F_RIGID)) { const Scal* f = a.d[a.src].sc; jc[0] = f->c[0]; jc[1] = f->c[1]; jc[2] = f->c[2]; }
   if (scd->status & LRR_ST_SELECT_MISS) return;   // window miss (set on every direction by k_weight): nothing is committed, the host reruns

@@ -122,6 +122,8 @@ enum {
   LRR_F_STRENGTH = 16,    // weight_by_strength_
   LRR_F_MERGED = 32,      // cdcl symmetric: backward matches join the forward list reversed (one G, one S)
   LRR_F_USE_OLD_W = 64,   // scale from the current weights (estimate_LS_backward after estimate_LS)
+  LRR_F_NOSPATIAL = 1024, // cdcl estimate_LS_backward: merged list without weight_spatially (cdcl sym :744-763)
+  LRR_F_NO_OTHER_RENORM = 2048,   // ... and only the estimated direction's transform goes through normalize / unnormalize
   LRR_F_BRACKET = 512     // order statistics from the window around the previous iteration's values (no histogram atomics, no collect pass)
 };
 
@@ -157,6 +159,7 @@ void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx,
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // pass A + pass B
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches);   // cdcl estimate_LS_backward: normalisation over the merged list
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches);

@@ -10,6 +10,7 @@
 #include "lrr_linalg.cuh"
 
 #define LRR_THREADS 256
+#define LRR_SPATIAL(flags) (((flags) & LRR_F_SYM) && !((flags) & LRR_F_NOSPATIAL))   // weight_spatially is part of this estimate
 #define LRR_NWARPS (LRR_THREADS / 32)
 
 template <int NW>
@@ -456,7 +457,7 @@ template <class Scope, class SH>
 __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags, int reversed, const SelDev& selG, const SelDev& selS,
                                  int scale_mode, double scale_in, SH& sh) {
   Scal* sc = a.sc;
-  const bool sym = (flags & LRR_F_SYM) != 0;
+  const bool sym = (flags & LRR_F_SYM) != 0, spatial = LRR_SPATIAL(flags);
   const double unit = sym ? 1.0 : sc->rto;   // forward estimators weight in normalised coordinates (Q3)
   const double scale = lrr_scale_of(sc, a.M, flags, unit, scale_mode, scale_in);
   const double scale2 = scale * scale, unit2 = unit * unit;
@@ -489,7 +490,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
       else if (selG.fine) lrr_sel_add(selG, fabs(g));
       acc[0] += 1.0;
     }
-    if (sym && s >= 0) {
+    if (spatial && s >= 0) {
       double qx, qy, qz;
       if (!reversed) { const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s); qx = q.x; qy = q.y; qz = q.z; }
       else lrr_from_loc(a, sc, mapped, i, qx, qy, qz);
@@ -509,7 +510,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
 template <class Scope>
 __device__ void lrr_phase_collect(const Scope& scope, const DirArgs& a, int flags, const SelDev& selG, const SelDev& selS) {
   const int binG = (flags & LRR_F_STRENGTH) ? *selG.bin : -1;
-  const int binS = (flags & LRR_F_SYM) ? *selS.bin : -1;
+  const int binS = LRR_SPATIAL(flags) ? *selS.bin : -1;
   if (binG < 0 && binS < 0) return;
   for (int k = scope.first(); k < a.M; k += scope.stride()) {
     if (binG >= 0) { const double g = a.gkey[k]; if (g >= 0.0) lrr_sel_offer(selG, binG, fabs(g)); }
@@ -528,7 +529,7 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
                                      const double* jc /* centre subtracted inside the Jacobian */, SH& sh) {
   Scal* sc = a.sc;
   const int mapped = sc->from_mapped;
-  const bool sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0;
+  const bool sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0, spatial = LRR_SPATIAL(flags);
   const bool skip_small = sym && (flags & LRR_F_RRL);
   const double invG = 1.0 / G, invS = 1.0 / S;
   // normalised coordinates (x - c) / r as a multiplication by 1/r: one rounding apart from the reference's
@@ -547,7 +548,7 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
       if (g >= 0.0) w *= g;                        // only where w != 0   (cdcl :839-848)
       w *= invG;                                   // every match         (cdcl :857-860, Q13)
     }
-    if (sym) { w *= a.skey[k]; w *= invS; }        // cdcl :985-1002
+    if (spatial) { w *= a.skey[k]; w *= invS; }    // cdcl :985-1002
     // cdcl symmetric: the re-weighted reversed constraints are clones that get erased again (Q11), the
     // backward originals keep their Beaton-Tukey weights
     if (j == 0 && !keep_w) a.w[k] = w;
@@ -765,7 +766,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
       for (int i = 0; i < 9; ++i) F->A[i] = Rn[i];
       for (int d = 0; d < 3; ++d) { F->t[d] = tn[d]; F->c[d] = F->cg[d]; }
     }
-    if (B && !estimate_parameters && normalize && !rigid) {
+    if (B && !estimate_parameters && normalize && !rigid && !(flags & LRR_F_NO_OTHER_RENORM)) {
       // the other direction's transform only goes through normalize() / unnormalize() (cdcl sym :470-478,:668-675):
       // same map, but its centre moves to the centre of its own from-features
       const double brm = B->rfrom, brf = B->rto;

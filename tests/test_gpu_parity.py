@@ -250,3 +250,16 @@ def test_fused_iteration_kernel():
     ) % (root, os.path.join(root, "oracle", "liblrr_oracle.so"))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LRR_FUSED="1"), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cdcl_estimate_ls_backward(gpu_lib, oracle_lib, pair):
+    """cdcl symmetric estimate_LS_backward (cdcl sym :705-863): merged list, merged normalisation, no spatial weighting."""
+    for ep in (False, True):
+        _, g = make_est(gpu_lib, pair, "cdcl_sym")
+        _, o = make_est(oracle_lib, pair, "cdcl_sym")
+        for it in range(4):
+            g.one_iteration(it); o.one_iteration(it)
+        g.estimate_ls_backward(ep); o.estimate_ls_backward(ep)
+        compare_state(g, o, dirs=(0, 1))
+        sg, so = g.state(), o.state()
+        assert abs(g.metric("weighted", 1) - o.metric("weighted", 1)) <= 1e-9 * max(1.0, abs(o.metric("weighted", 1)))
