@@ -112,3 +112,37 @@ def test_bad_arguments(gpu_lib):
         est.set_subsets(np.array([0, 5, 300], dtype=np.int32))     # index out of range
     with pytest.raises(LrrError):
         est.set_order(np.arange(10, dtype=np.int32))               # wrong length
+
+
+@pytest.mark.parametrize("scale,noise", [(1.0, 1e-7), (1000.0, 1e-3), (1e-3, 1e-9), (1.0, 0.3)])
+def test_neighbours_exact_under_scale_offset_and_tiny_distances(gpu_lib, oracle_lib, scale, noise):
+    """Neighbour distances far below the coordinate magnitude, huge and tiny coordinate scales and an offset origin must
+    all give the oracle's indices (this also guards any future reduced-precision pre-filter of the candidate scan: an
+    fp32 pre-filter was tried in round 1, passed this test, and was dropped because it was slower)."""
+    rng = np.random.default_rng(7)
+    pair = synth.make_pair(48, 6000, 5000, size=120.0)
+    f, m = pair["fixed"], pair["moving"]
+    A, t, c = pair["init"]
+    # moving := preimages of (a subset of) the fixed locations, plus noise: every query has a neighbour at ~noise
+    src = rng.integers(0, 6000, size=5000)
+    y = f["xyz"][:, src].T + rng.normal(scale=noise, size=(5000, 3))
+    m["xyz"] = np.ascontiguousarray(((y - t) @ np.linalg.inv(A).T + c).T)
+    off = np.array([7.0e3, -4.0e3, 1.0e3])
+    for k in (f, m):
+        k["xyz"] = np.ascontiguousarray((k["xyz"] + off[:, None]) * scale)
+    init = (A, (t + off - A @ off) * scale + 0.0, c * scale)     # T'(x') = A (x' - c') + t' in the shifted, scaled frame
+    init = (A, scale * (t + off) , scale * (c + off))
+    out = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        e = ctx.estimator("cdcl_fwd", ctx.upload(m), ctx.upload(f), 12)
+        e.set_flags(True, False); e.set_transform(*init); e.set_number_points(5000)
+        res = []
+        for it in range(3):
+            e.one_iteration(it)
+            res.append(e.get_matches(0)[1].copy())
+        out.append(res)
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    if noise <= 1e-3 * scale:
+        assert np.mean(out[0][0] == src) > 0.9          # the planted neighbours are found
