@@ -230,8 +230,12 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    out_fd = 1
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner)
+        # stdout carries exactly one JSON line: NCCL writes its version banner to fd 1, so libraries get stderr there
+        sys.stdout.flush()
+        out_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -429,7 +433,8 @@ def run_b200(args, rank, world, local_rank):
     else:
         line["cpu_baseline"] = None
     line["final_A00"] = float(final["A"][0, 0])
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
