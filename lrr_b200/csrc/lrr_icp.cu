@@ -233,7 +233,6 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
     }
   }
 }
-static WeightExtra g_dummy_extra;
 void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches) {
   WeightExtra ex;
   for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
@@ -241,7 +240,6 @@ void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scal
   k_weight<<<grid, LRR_THREADS, 0, st>>>(a, ex); ++*launches;
 }
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches) {
-  (void)g_dummy_extra;
   const int m[2] = {0, 0}; const double s[2] = {0, 0};
   lrr_k_weight_ex(a, m, s, st, launches);
 }
