@@ -1,0 +1,1 @@
+// included by the reference but unused on the hot path (stand-in, test infrastructure only)

@@ -1,0 +1,1 @@
+#include "vcl_shim_all.h"

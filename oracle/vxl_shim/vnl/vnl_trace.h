@@ -1,0 +1,1 @@
+#include "vnl_shim_core.h"

@@ -18,9 +18,9 @@ def oracle_lib():
     import subprocess
     from lrr_b200.capi import Lib
     so = os.path.join(ROOT, "oracle", "liblrr_oracle.so")
-    src = [os.path.join(ROOT, "oracle", f) for f in ("lrr_oracle_capi.cpp", "lrr_oracle_core.hpp", "lrr_oracle_linalg.hpp")]
+    src = [os.path.join(ROOT, "oracle", f) for f in ("lrr_oracle_capi.cpp", "lrr_oracle_core.hpp", "lrr_oracle_linalg.hpp", "lrr_oracle_muse.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liblrr_oracle.so"])
     return Lib(so, "lrro_")
 
 
