@@ -14,8 +14,8 @@ divided by the max-over-ranks time ("weak" scaling).
 
 One JSON line on stdout (rank 0).  `value` = device-resident iterations/s with an L2 flush between timed
 iterations; `e2e` = the same metric through the C ABI with HOST buffers (upload of both volumes, estimator
-construction, full ramped run, result read-back inside the timed region).  `--impl reference` times the CPU
-oracle port of the reference's algorithm (the reference itself needs VXL/ITK/VTK and cannot be built here).
+construction, full ramped run, result read-back inside the timed region).  `--impl reference` times the reference's own
+estimator code on the host (oracle/_ref: its sources compiled unmodified against oracle/vxl_shim; the oracle port if absent).
 """
 import argparse
 import ctypes
@@ -115,14 +115,30 @@ def ramp_to_finest(est, max_iter=70):
     return it, conv
 
 
-def cpu_measure(pair, steps, warmup):
-    """CPU arm: the oracle port of the reference algorithm, single thread (the reference pins its estimators to one
-    thread, rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760)."""
+def cpu_library():
+    """CPU arm library: oracle/_ref/liblrr_ref.so when it exists = the REFERENCE's own estimator sources compiled unmodified
+    against oracle/vxl_shim (kind "reference"; the prebuilt .so travels to the GPU box), else the oracle port (kind "port")."""
     from lrr_b200.capi import Lib
+    ref = os.path.join(ROOT, "oracle", "_ref", "liblrr_ref.so")
+    if os.path.exists(ref) and not os.environ.get("LRR_BENCH_CPU_PORT"):
+        return Lib(ref, "lrrr_"), "reference"
     so = os.path.join(ROOT, "oracle", "liblrr_oracle.so")
     if not os.path.exists(so):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
-    lib = Lib(so, "lrro_")
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liblrr_oracle.so"])
+    return Lib(so, "lrro_"), "port"
+
+
+CPU_KIND_NOTE = {
+    "reference": "the reference's own rrl_estimation_symmetric_ICP_matching_all<3,12> (sources compiled unmodified, oracle/_ref; "
+                 "VXL/ITK third-party calls served by oracle/vxl_shim, exact-NN k-d tree instead of the Voronoi image)",
+    "port": "oracle/ CPU port of the same algorithm (oracle/_ref not built on this machine)",
+}
+
+
+def cpu_measure(pair, steps, warmup):
+    """CPU arm, single thread: the reference pins its estimators to one thread
+    (rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760) and one registration has no other parallel axis."""
+    lib, kind = cpu_library()
     ctx = lib.context()
     t0 = time.perf_counter()
     fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
@@ -138,7 +154,7 @@ def cpu_measure(pair, steps, warmup):
     for i in range(steps):
         est.one_iteration(iters + warmup + i)
     dt = time.perf_counter() - t0
-    return {"finest_iters_per_s": steps / dt, "ms_per_step": 1e3 * dt / steps, "registration_s": t_reg,
+    return {"kind": kind, "finest_iters_per_s": steps / dt, "ms_per_step": 1e3 * dt / steps, "registration_s": t_reg,
             "registration_iters": iters, "registration_iters_per_s": iters / t_reg, "converged": bool(conv)}
 
 
@@ -184,7 +200,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     pair = make_workload()
-    steps = max(1, min(args.steps, 40))   # bounded sample: ~0.6 s of CPU per finest-level iteration
+    steps = max(1, min(args.steps, 30))   # bounded sample: ~0.9 s of CPU per finest-level iteration
     warm = max(1, min(args.warmup, 2))
     r = cpu_measure(pair, steps, warm)
     cores = 1
@@ -193,15 +209,18 @@ def run_reference(args, rank):
         "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_fixed": N_FEATURES, "n_moving": N_FEATURES, "seed": SEED, "l2": "host CPU run"},
-        "cpu_baseline": {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": cores, "kind": r["kind"],
                          "sample": f"{steps} one_iteration calls at the finest level after the full ramp; single thread = the "
-                                   "reference's execution model (its MultiThreader is pinned to 1 thread)",
+                                   "reference's execution model (its MultiThreader is pinned to 1 thread); " + CPU_KIND_NOTE[r["kind"]],
                          "host_cores_available": os.cpu_count()},
-        "e2e": {"value": r["finest_iters_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # same definition as the b200 arm's e2e: iterations of one whole ramped registration / its wall time (setup included),
+        # so that the driver's e2e ratio compares like with like; `value` is the finest-level figure like the b200 arm's `value`
+        "e2e": {"value": r["registration_iters_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "what": "feature-set construction (k-d trees), estimator, set_transform, ramped run to convergence (<=70 one_iteration calls)"},
         "registration": {"seconds": r["registration_s"], "iterations": r["registration_iters"],
                          "iters_per_s": r["registration_iters_per_s"], "converged": r["converged"]},
         "gpu_launches": 0,
-        "note": "reference needs VXL/ITK/VTK (absent): oracle/ CPU port of the same algorithm, see DESIGN.md",
+        "note": CPU_KIND_NOTE[r["kind"]],
     }
     print(json.dumps(line), flush=True)
 
@@ -424,9 +443,9 @@ def run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu and not args.only_iterations:
         r = cpu_measure(pair, 6, 1)
-        line["cpu_baseline"] = {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "full ramped registration + 6 one_iteration calls at the finest level, CPU oracle port, single thread "
-                                          "(the reference's execution model)",
+        line["cpu_baseline"] = {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                "sample": "full ramped registration + 6 one_iteration calls at the finest level, single thread "
+                                          "(the reference's execution model); " + CPU_KIND_NOTE[r["kind"]],
                                 "registration_iters_per_s": r["registration_iters_per_s"], "registration_s": r["registration_s"],
                                 "host_cores_available": os.cpu_count()}
         line["cpu_baseline"]["registrations"] = cpu_batch_measure(bpair, bjobs)
