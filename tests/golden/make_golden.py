@@ -1,5 +1,5 @@
-"""Golden vectors for the hot path.  The reference ships no fixtures and cannot be built here (VXL/ITK/VTK absent),
-so these are outputs of the CPU ORACLE (oracle/, pinned by tests/test_oracle_kat.py), NOT of the reference itself:
+"""Older, ORACLE-derived regression vectors (the reference-generated ones are ref_*.npz, see make_ref_golden.py).
+The reference ships no fixtures, so these are outputs of the CPU ORACLE (oracle/, pinned by tests/test_oracle_kat.py), NOT of the reference itself:
 they freeze the oracle's behaviour (regression pin) and give the GPU tests an input/output set that needs no
 oracle at run time.  Regenerate with:  python tests/golden/make_golden.py
 """
