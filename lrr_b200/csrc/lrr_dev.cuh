@@ -2,6 +2,17 @@
 #pragma once
 #include "lrr_internal.h"
 
+// development aid (scripts/timeline.py): per-block %globaltimer marks of the phase kernels of this translation unit.
+// Off (null pointer, one uniform load per mark) unless lrr_debug_timeline() armed it.
+static __device__ unsigned long long* g_lrr_tl = nullptr;
+__device__ __forceinline__ void lrr_tl(int kern, int slot) {
+  unsigned long long* p = g_lrr_tl;
+  if (p && threadIdx.x == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p[((size_t)kern * 2048 + blockIdx.y * gridDim.x + blockIdx.x) * 4 + slot] = t;
+  }
+}
+
 // y = A (x - c) + t with the reference's evaluation order (vnl row dot product left to right, then + t;
 // cdcl/cdcl_trans_affine.txx:112-115) and NO FMA contraction, so that the mapped point — and therefore
 // the neighbour index — is bit-identical to the CPU oracle for the same transform bits.
@@ -313,9 +324,17 @@ struct GridScope {
     __threadfence();
     if (KG <= 32) {
       // one warp per value: lanes stride over the block rows (independent loads in flight), fixed shuffle tree
+      // (all loads of a lane are issued before the first add: one L2 round trip instead of gridDim.x/32 dependent ones;
+      //  the adds keep the ascending-row order, so the sum is bitwise what the plain loop gives)
       for (int k = wid; k < KG; k += nw) {
         double s = 0;
-        for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * LRR_NRED + k]);
+        for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 32 * 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const unsigned int b = b0 + 32 * u; v[u] = b < gridDim.x ? __ldcg(&partials[(size_t)b * LRR_NRED + k]) : 0.0; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) s += v[u];
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) sh_out[k] = s;

@@ -3,10 +3,34 @@
 // a symmetric estimator, and adds the cross-direction finalisation (merged order statistics, joint solve).
 #include "lrr_phases.cuh"
 #include <algorithm>
+#include <unordered_map>
+#include <cstdlib>
 
 static inline int nblk_for(long long items) {
   long long b = (items + LRR_THREADS - 1) / LRR_THREADS;
   long long cap = (long long)lrr_num_sms() * 4;
+  if (cap > LRR_MAX_BLOCKS) cap = LRR_MAX_BLOCKS;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+// Grid width such that ALL blocks of the launch (gridDim.y = directions) are resident at once.  Measured with per-block
+// %globaltimer marks (scripts/timeline.py): with more blocks than fit, the blocks of direction 1 (scheduled after those of
+// direction 0) only start when direction 0 has finished, and every phase kernel ends in a last-block reduction — the two
+// directions ran back to back, each with its own tail.
+template <class K>
+static inline int resident_width(K kernel, int threads, int ny, long long items) {
+  static std::unordered_map<const void*, int> cache;   // host calls on one context are serialised by the caller (lrr_gpu.h)
+  int per_sm;
+  auto it = cache.find((const void*)kernel);
+  if (it != cache.end()) per_sm = it->second;
+  else {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+    cache[(const void*)kernel] = per_sm = n;
+  }
+  long long b = (items + threads - 1) / threads;
+  long long cap = (long long)lrr_num_sms() * per_sm / (ny < 1 ? 1 : ny);
   if (cap > LRR_MAX_BLOCKS) cap = LRR_MAX_BLOCKS;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -101,7 +125,9 @@ void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* 
 __global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const __grid_constant__ EstArgs a) {
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
+  lrr_tl(0, 0);
   lrr_phase_match(lrr_scope(a, dir), a.d[dir], a.flags, sh, a.ticket + 4 + dir);
+  lrr_tl(0, 3);
 }
 #ifndef LRR_HARD_MINBLK
 #define LRR_HARD_MINBLK 2
@@ -109,13 +135,20 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const _
 __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(const __grid_constant__ EstArgs a) {
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
+  lrr_tl(1, 0);
   lrr_phase_match_hard(lrr_scope(a, dir), a.d[dir], a.flags, sh, a.ticket + 6 + dir);
+  lrr_tl(1, 3);
 }
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
-  dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
-  k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+  static const bool no_tile = getenv("LRR_NO_TILE") != nullptr;   // A/B switch for measurements
+  if (!no_tile && lrr_match_tile_usable(a)) lrr_k_match_tile(a, st, launches);   // finest level: shared-memory-staged cells (lrr_tile.cu)
+  else {
+    dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
+    k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+  }
   // queue length is only known on the device: a fixed grid of warps strides over it
+  // (two waves on purpose: each direction's queue is drained by all resident warps, measured faster than co-resident halves)
   dim3 gridb(std::min(nblk_for(32LL * maxM(a)), 2 * lrr_num_sms()), a.ndir);
   k_match_hard<<<gridb, LRR_THREADS, 0, st>>>(a); ++*launches;
 }
@@ -236,7 +269,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
 void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches) {
   WeightExtra ex;
   for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
-  dim3 grid(nblk_for(maxM(a)), a.ndir);
+  dim3 grid(resident_width(k_weight, LRR_THREADS, a.ndir, maxM(a)), a.ndir);
   k_weight<<<grid, LRR_THREADS, 0, st>>>(a, ex); ++*launches;
 }
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches) {
@@ -288,14 +321,17 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
   double jc[3] = {0, 0, 0};
   if (!(a.flags & LRR_F_NORMALIZE) && !(a.flags & LRR_F_RIGID)) { const Scal* f = a.d[a.src].sc; jc[0] = f->c[0]; jc[1] = f->c[1]; jc[2] = f->c[2]; }
   if (scd->status & LRR_ST_SELECT_MISS) return;   // window miss (set on every direction by k_weight): nothing is committed, the host reruns
+  lrr_tl(2, 0);
   const bool fin = lrr_phase_accumulate(lrr_scope(a, dir), a.d[dir], a.flags, reversed, keep_w, G, S, jc, sh);
   if (!fin) return;
   if (!lrr_pair_done(a, a.ndir)) return;
+  lrr_tl(2, 2);
   lrr_solve(a.d[a.src].sc, a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, a.flags, a.dof, a.estimate_parameters);
+  lrr_tl(2, 3);
 }
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
   // two blocks per SM at most: the last block sums one row of 108 moments per block before it can solve
-  dim3 grid(std::min(nblk_for(4LL * maxM(a)), 2 * lrr_num_sms()), a.ndir);
+  dim3 grid(resident_width(k_accumulate, LRR_THREADS, a.ndir, 4LL * maxM(a)), a.ndir);
   k_accumulate<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
 }
 
@@ -307,10 +343,29 @@ __global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ E
 }
 void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches) {
   if (dir_mask == 3) {
-    dim3 grid(nblk_for(maxM(a)), 2);
+    dim3 grid(resident_width(k_resid, LRR_THREADS, 2, maxM(a)), 2);
     k_resid<<<grid, LRR_THREADS, 0, st>>>(a, 0); ++*launches;
   } else {
     const int d = (dir_mask == 2) ? 1 : 0;
     k_resid<<<nblk_for(a.d[d].M), LRR_THREADS, 0, st>>>(a, d); ++*launches;
   }
+}
+
+// development aid: arm / read the per-block timeline marks (lrr_dev.cuh).  out: 4 kernels x 2048 blocks x 4 marks.
+extern "C" int lrr_debug_timeline(int arm, unsigned long long* out) {
+  static unsigned long long* buf = nullptr;
+  const size_t n = 4 * 2048 * 4;
+  if (arm) {
+    if (!buf) { if (cudaMalloc(&buf, n * sizeof(unsigned long long)) != cudaSuccess) return 1; }
+    cudaMemset(buf, 0, n * sizeof(unsigned long long));
+    cudaMemcpyToSymbol(g_lrr_tl, &buf, sizeof(buf));
+    lrr_tile_set_timeline(buf);
+  } else {
+    unsigned long long* z = nullptr;
+    cudaDeviceSynchronize();
+    cudaMemcpyToSymbol(g_lrr_tl, &z, sizeof(z));
+    lrr_tile_set_timeline(nullptr);
+    if (buf && out) cudaMemcpy(out, buf, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  }
+  return 0;
 }

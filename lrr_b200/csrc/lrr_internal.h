@@ -22,6 +22,12 @@
 #define LRR_SEL_CAP 2048      // candidate capacity of the final exact selection
 #define LRR_STRENGTH_CAP 90000.0
 
+// spatial tiles of the from-features (lrr_tile.cu): cubes of LRR_TILE_T cells of the to-grid; the finest-level match stages
+// the cells of one tile's queries plus a halo of LRR_TILE_H cells in shared memory
+#define LRR_TILE_T 8
+#define LRR_TILE_H 1
+struct TileGeom { double ox, oy, oz, inv_edge; int ntx, nty, ntz; };
+
 struct GridDev {
   double ox, oy, oz, h, inv_h;
   int nx, ny, nz, n;
@@ -98,7 +104,9 @@ struct DirArgs {
   int n_in;
   const int* order;      // n_in or null (identity): position k -> compact index
   unsigned int perm_key[4]; int perm_half;   // RESHUFFLE: keyed Feistel permutation of [0,n_in) (perm_half = 0: off)
-  const int* proc;       // n_in or null: match positions in spatially coherent processing order (only when M == n_in)
+  const int* proc;       // n_in or null: match positions in spatially coherent (tile) processing order (only when M == n_in)
+  const int2* chunk_tab; // or null: chunk c = positions [chunk_tab[c].x, chunk_tab[c].y) of proc, at most 32 queries of one row of tiles (lrr_tile.cu)
+  const int* nchunks;    // device scalar: number of chunks
   int M;                 // number_points_: matches in use
   // to side
   FsetDev to;
@@ -157,6 +165,12 @@ void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long lon
 void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,
                        cudaStream_t st, long long* launches);
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // pass A + pass B
+// lrr_tile.cu: tile construction and the shared-memory-staged pass A of the finest level
+void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
+                       int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches);
+bool lrr_match_tile_usable(const EstArgs& a);
+void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_tile_set_timeline(unsigned long long* p);
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches);   // cdcl estimate_LS_backward: normalisation over the merged list

@@ -189,7 +189,9 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
   double acc[4] = {0, 0, 0, 0};
   if (counter) lrr_match_a_body_dynamic(a, flags, s_T, counter, acc);
   else lrr_match_a_body(scope, a, flags, s_T, acc);
+  lrr_tl(0, 1);
   if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
+    lrr_tl(0, 2);
     if (threadIdx.x == 0) {
       Scal* sc = a.sc; sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
       if (counter) *counter = 0;
@@ -205,7 +207,9 @@ __device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int f
   double acc[4] = {0, 0, 0, 0};
   if (counter) lrr_match_b_body_dynamic(a, flags, s_T, counter, acc);
   else lrr_match_b_body(scope, a, flags, s_T, acc);
+  lrr_tl(1, 1);
   if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
+    lrr_tl(1, 2);
     if (threadIdx.x == 0) {
       const Scal* sc = a.sc;
       const double tot[4] = {sc->sum_loc[0] + sh.out[0], sc->sum_loc[1] + sh.out[1], sc->sum_loc[2] + sh.out[2], sc->sum_r2 + sh.out[3]};
@@ -580,7 +584,9 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
     acc[25] += wxa * (P[1] * b0 + P[3] * b1 + P[4] * b2);
     acc[26] += wxa * (P[2] * b0 + P[4] * b1 + P[5] * b2);
   }
+  lrr_tl(2, 1);
   const bool fin = scope.template reduce<27, 4>(acc, sh.out, sh.tmp);
+  lrr_tl(2, 2);
   if (fin) {
     for (int i = threadIdx.x; i < 108; i += blockDim.x) sc->mom[i] = sh.out[i];
     __syncthreads();
@@ -639,6 +645,12 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
     const int a = i / 27, r = i % 27;
     if (r < 24) T[a][r / 6][r % 6] = v; else V[a][r - 24] = v;
   }
+  // The scalars the serial part below works on are staged in shared memory by 46 different threads (one L2 round trip)
+  // instead of being read and written one by one by thread 0 (~40 dependent round trips on the critical path of every
+  // iteration): sF/sB = A[9] t[3] c[3], sFg = Ag[9] tg[3] cg[3], sFn/sBn = cfrom[3] rfrom cto[3] rto.
+  __shared__ double sF[15], sFg[15], sFn[8], sB[15], sBn[8];
+  if (tid < 15) { sF[tid] = __ldcg(&F->A[0] + tid); sFg[tid] = __ldcg(&F->Ag[0] + tid); if (B) sB[tid] = __ldcg(&B->A[0] + tid); }
+  else if (tid >= 32 && tid < 40) { sFn[tid - 32] = __ldcg(&F->cfrom[0] + (tid - 32)); if (B) sBn[tid - 32] = __ldcg(&B->cfrom[0] + (tid - 32)); }
   __syncthreads();
   if (!rigid) {
     // affine: parameter index of (row d, column a of x~) = a<3 ? 3d+a : 9+d   (cdcl_trans_affine.txx:65-106,141-161)
@@ -698,7 +710,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   }
   if (tid < dof) { double s = 0; for (int k = 0; k < dof; ++k) s += inv[tid * dof + k] * Atb[k]; theta[tid] = s; }
   __syncthreads();
-  const double rm = F->rfrom, rfx = F->rto;
+  const double rm = sFn[3], rfx = sFn[7];
   // covariance: set_covariance(invAA), then affine unnormalize scales it by B = diag((rf/rm) I9, rf I3)
   for (int e = tid; e < dof * dof; e += blockDim.x) {
     double v = inv[e];
@@ -711,15 +723,15 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   __syncthreads();
   if (tid == 0) {
     double A[9], t[3], c[3];
-    const double cm[3] = {F->cfrom[0], F->cfrom[1], F->cfrom[2]}, cf[3] = {F->cto[0], F->cto[1], F->cto[2]};
+    const double cm[3] = {sFn[0], sFn[1], sFn[2]}, cf[3] = {sFn[4 + 0], sFn[4 + 1], sFn[4 + 2]};
     if (!rigid) {
       if (estimate_parameters) {
         for (int i = 0; i < 9; ++i) A[i] = theta[i];
         for (int d = 0; d < 3; ++d) t[d] = theta[9 + d];
-        for (int d = 0; d < 3; ++d) c[d] = normalize ? 0.0 : F->c[d];
+        for (int d = 0; d < 3; ++d) c[d] = normalize ? 0.0 : sF[12 + d];
       } else {
-        for (int i = 0; i < 9; ++i) A[i] = F->A[i];
-        for (int d = 0; d < 3; ++d) { t[d] = F->t[d]; c[d] = F->c[d]; }
+        for (int i = 0; i < 9; ++i) A[i] = sF[i];
+        for (int d = 0; d < 3; ++d) { t[d] = sF[9 + d]; c[d] = sF[12 + d]; }
         if (normalize) {   // cdcl_trans_affine::normalize  (affine.txx:220-253)
           const double s = rm / rfx;
           for (int i = 0; i < 9; ++i) A[i] = s * A[i];
@@ -737,8 +749,8 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
         for (int r = 0; r < 3; ++r) t[r] = rfx * t[r] + cf[r];
         for (int d = 0; d < 3; ++d) c[d] = cm[d];
       }
-      for (int i = 0; i < 9; ++i) F->A[i] = A[i];
-      for (int d = 0; d < 3; ++d) { F->t[d] = t[d]; F->c[d] = c[d]; }
+      for (int i = 0; i < 9; ++i) sF[i] = A[i];
+      for (int d = 0; d < 3; ++d) { sF[9 + d] = t[d]; sF[12 + d] = c[d]; }
     } else if (estimate_parameters) {
       // increment from the small-angle parameterisation (rigid3d.cxx:140-166)
       const double da = theta[0], db = theta[1], dg = theta[2];
@@ -756,32 +768,32 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
       double dR[9]; lrr_orthogonalize3(A, dR);
       double Rn[9], tn[3];
       for (int i = 0; i < 3; ++i) for (int jx = 0; jx < 3; ++jx) {
-        double acc = F->Ag[3 * i] * dR[jx]; acc += F->Ag[3 * i + 1] * dR[3 + jx]; acc += F->Ag[3 * i + 2] * dR[6 + jx];
+        double acc = sFg[3 * i] * dR[jx]; acc += sFg[3 * i + 1] * dR[3 + jx]; acc += sFg[3 * i + 2] * dR[6 + jx];
         Rn[3 * i + jx] = acc;
       }
       for (int i = 0; i < 3; ++i) {
-        double acc = dR[3 * i] * F->tg[0]; acc += dR[3 * i + 1] * F->tg[1]; acc += dR[3 * i + 2] * F->tg[2];
+        double acc = dR[3 * i] * sFg[9 + 0]; acc += dR[3 * i + 1] * sFg[9 + 1]; acc += dR[3 * i + 2] * sFg[9 + 2];
         tn[i] = acc + t[i];
       }
-      for (int i = 0; i < 9; ++i) F->A[i] = Rn[i];
-      for (int d = 0; d < 3; ++d) { F->t[d] = tn[d]; F->c[d] = F->cg[d]; }
+      for (int i = 0; i < 9; ++i) sF[i] = Rn[i];
+      for (int d = 0; d < 3; ++d) { sF[9 + d] = tn[d]; sF[12 + d] = sFg[12 + d]; }
     }
     if (B && !estimate_parameters && normalize && !rigid && !(flags & LRR_F_NO_OTHER_RENORM)) {
       // the other direction's transform only goes through normalize() / unnormalize() (cdcl sym :470-478,:668-675):
       // same map, but its centre moves to the centre of its own from-features
-      const double brm = B->rfrom, brf = B->rto;
-      const double bcm[3] = {B->cfrom[0], B->cfrom[1], B->cfrom[2]}, bcf[3] = {B->cto[0], B->cto[1], B->cto[2]};
+      const double brm = sBn[3], brf = sBn[7];
+      const double bcm[3] = {sBn[0], sBn[1], sBn[2]}, bcf[3] = {sBn[4 + 0], sBn[4 + 1], sBn[4 + 2]};
       double A2[9], t2[3];
       const double s1 = brm / brf;
-      for (int i = 0; i < 9; ++i) A2[i] = s1 * B->A[i];
-      const double dc[3] = {bcm[0] - B->c[0], bcm[1] - B->c[1], bcm[2] - B->c[2]};
+      for (int i = 0; i < 9; ++i) A2[i] = s1 * sB[i];
+      const double dc[3] = {bcm[0] - sB[12 + 0], bcm[1] - sB[12 + 1], bcm[2] - sB[12 + 2]};
       for (int r = 0; r < 3; ++r) {
         double acc = A2[3 * r] * dc[0]; acc += A2[3 * r + 1] * dc[1]; acc += A2[3 * r + 2] * dc[2];
-        t2[r] = B->t[r] / brf + acc / brm - bcf[r] / brf;
+        t2[r] = sB[9 + r] / brf + acc / brm - bcf[r] / brf;
       }
       const double s2 = brf / brm;
-      for (int i = 0; i < 9; ++i) B->A[i] = s2 * A2[i];
-      for (int r = 0; r < 3; ++r) { B->t[r] = brf * t2[r] + bcf[r]; }
+      for (int i = 0; i < 9; ++i) sB[i] = s2 * A2[i];
+      for (int r = 0; r < 3; ++r) { sB[9 + r] = brf * t2[r] + bcf[r]; }
       // covariance: B2 (B1 Sigma B1^T) B2 with B1 = diag(s1 I9, 1/rf I3) + N/rf, B2 = diag(s2 I9, rf I3); N[9+d][3d+k] = dc[k]
       double K[144], Tm[144];
       for (int i = 0; i < 144; ++i) K[i] = 0.0;
@@ -789,18 +801,19 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
       for (int d = 0; d < 3; ++d) { K[(9 + d) * 12 + 9 + d] = brf * (1.0 / brf); for (int k = 0; k < 3; ++k) K[(9 + d) * 12 + 3 * d + k] = brf * (dc[k] / brf); }
       for (int i = 0; i < 12; ++i) for (int jx = 0; jx < 12; ++jx) { double v = 0; for (int k = 0; k < 12; ++k) v += K[i * 12 + k] * B->cov[k * 12 + jx]; Tm[i * 12 + jx] = v; }
       for (int i = 0; i < 12; ++i) for (int jx = 0; jx < 12; ++jx) { double v = 0; for (int k = 0; k < 12; ++k) v += Tm[i * 12 + k] * K[jx * 12 + k]; B->cov[i * 12 + jx] = v; }
-      for (int d = 0; d < 3; ++d) B->c[d] = bcm[d];
+      for (int d = 0; d < 3; ++d) sB[12 + d] = bcm[d];
     }
     if (B && estimate_parameters) {   // backward = forward->inverse()  (affine.txx:54-59, rigid3d.cxx:113-118)
-      double invA[9]; lrr_inv3(F->A, invA);
-      for (int i = 0; i < 9; ++i) B->A[i] = invA[i];
+      double invA[9]; lrr_inv3(sF, invA);
+      for (int i = 0; i < 9; ++i) sB[i] = invA[i];
       for (int i = 0; i < 3; ++i) {
-        double acc = (-invA[3 * i]) * F->t[0]; acc += (-invA[3 * i + 1]) * F->t[1]; acc += (-invA[3 * i + 2]) * F->t[2];
-        B->t[i] = acc + F->c[i]; B->c[i] = 0.0;
+        double acc = (-invA[3 * i]) * sF[9 + 0]; acc += (-invA[3 * i + 1]) * sF[9 + 1]; acc += (-invA[3 * i + 2]) * sF[9 + 2];
+        sB[9 + i] = acc + sF[12 + i]; sB[12 + i] = 0.0;
       }
     }
   }
   __syncthreads();
+  if (tid < 15) { (&F->A[0])[tid] = sF[tid]; if (B) (&B->A[0])[tid] = sB[tid]; }
   if (B && estimate_parameters) for (int e = tid; e < dof * dof; e += blockDim.x) B->cov[e] = 0.0;   // inverse(): fresh covariance
   __syncthreads();
 }

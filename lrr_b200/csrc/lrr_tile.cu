@@ -1,0 +1,335 @@
+// K2, finest level: exact 1-NN with SHARED-MEMORY-STAGED CELLS (sm_100a).
+//
+// Why: the per-thread ball scan of lrr_dev.cuh walks a chain of dependent L2 loads (cell_start -> points -> next row)
+// under heavy divergence; a 32-query chunk occupies its warp for 10-19 us and every resident warp has to work through
+// several chunks one after the other (profiles/r1_summary.md, per-block timeline).  Here the from-features are put into
+// spatial TILES once per set_features (cubes of LRR_TILE_T cells of the to-grid); a warp takes the queries of one tile
+// 32 at a time, maps them, takes the bounding box of their cells plus a halo of LRR_TILE_H cells, copies the x-runs of
+// that box (two coalesced rounds of independent loads: the run bounds, then the points) into its slice of shared memory
+// and every lane scans from there: the dependent chain runs at shared-memory latency.
+//
+// Exactness is the ball-scan argument of lrr_dev.cuh unchanged: a query is finished here only when every cell its
+// candidate ball touches lies inside the staged box (checked per query with the same inflated radius / slack), rows are
+// pruned only when strictly farther than the current best, distances use lrr_dist2_exact, ties go to the lowest
+// original index.  Everything else (no candidate and an empty neighbourhood, ball leaving the box, box too big for
+// shared memory) goes to the same queue as before and is finished by k_match_hard.
+// Replaces rsdl_kd_tree::n_nearest (cdcl/cdcl_estimation_ICP_matching_all.txx:572) / the Voronoi lookup
+// (rrl/rrl_estimation_ICP_matching_all.txx:530-543) for the iterations where all points are in use.
+#include "lrr_phases.cuh"
+#include <algorithm>
+
+#define LRR_TILE_WARPS 4
+#define LRR_TILE_THREADS (32 * LRR_TILE_WARPS)
+#define LRR_TW_CAP 512      // staged points per warp
+#define LRR_TW_ROWS 128     // staged (y,z) rows per warp
+
+struct TileWarp {
+  double px[LRR_TW_CAP], py[LRR_TW_CAP], pz[LRR_TW_CAP];
+  int rowlo[LRR_TW_ROWS];        // sorted slot of the first staged point of the row
+  int rowbase[LRR_TW_ROWS + 1];  // offset of the row inside px/py/pz
+};
+struct TileBox { int rx0, rx1, ry0, ry1, rz0, rz1, RY; };
+
+__device__ __forceinline__ GridScope lrr_scope_of(const EstArgs& a, int dir) {
+  GridScope s; s.partials = a.partials + (size_t)dir * LRR_MAX_BLOCKS * LRR_NRED; s.ticket = a.ticket + dir; return s;
+}
+void lrr_tile_set_timeline(unsigned long long* p) { cudaMemcpyToSymbol(g_lrr_tl, &p, sizeof(p)); }
+
+// ---- tile construction (once per set_features) --------------------------------------------------------------
+// tile_of[i] = tile * 512 + fine, fine = Morton code of the sub-cell (edge / 8) of feature i inside its tile: queries of one tile
+// are processed in (fine, index) order, so the 32 queries of a chunk of a DENSE tile cover only part of the tile and
+// their staged box stays small.
+__global__ void k_tile_count(const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz, int n,
+                             TileGeom g, int* __restrict__ cnt, int* __restrict__ tile_of) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ux = (fx[i] - g.ox) * g.inv_edge, uy = (fy[i] - g.oy) * g.inv_edge, uz = (fz[i] - g.oz) * g.inv_edge;
+  int tx = (int)floor(ux), ty = (int)floor(uy), tz = (int)floor(uz);
+  tx = tx < 0 ? 0 : (tx >= g.ntx ? g.ntx - 1 : tx); ty = ty < 0 ? 0 : (ty >= g.nty ? g.nty - 1 : ty); tz = tz < 0 ? 0 : (tz >= g.ntz ? g.ntz - 1 : tz);
+  int sx = (int)((ux - tx) * 8.0), sy = (int)((uy - ty) * 8.0), sz = (int)((uz - tz) * 8.0);
+  sx = sx < 0 ? 0 : (sx > 7 ? 7 : sx); sy = sy < 0 ? 0 : (sy > 7 ? 7 : sy); sz = sz < 0 ? 0 : (sz > 7 ? 7 : sz);
+  int fine = 0;   // Morton code of the 8 x 8 x 8 sub-cells: 32 consecutive queries of a tile form a compact block
+#pragma unroll
+  for (int b = 0; b < 3; ++b) fine |= (((sx >> b) & 1) << (3 * b)) | (((sy >> b) & 1) << (3 * b + 1)) | (((sz >> b) & 1) << (3 * b + 2));
+  const int t = (tz * g.nty + ty) * g.ntx + tx;
+  tile_of[i] = t * 512 + fine;
+  atomicAdd(cnt + t, 1);
+}
+// exclusive scan of the tile counts (single block); the counts are zeroed for their second life as scatter cursors
+__global__ void __launch_bounds__(1024) k_tile_scan(int* __restrict__ cnt, int ntiles, int* __restrict__ tile_start) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, T = blockDim.x;
+  const int per = (ntiles + T - 1) / T, lo = min(t * per, ntiles), hi = min(lo + per, ntiles);
+  int sum = 0;
+  for (int j = lo; j < hi; ++j) sum += cnt[j];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < T; o <<= 1) { const int v = (t >= o) ? s_part[t - o] : 0; __syncthreads(); s_part[t] += v; __syncthreads(); }
+  int run = s_part[t] - sum;
+  for (int j = lo; j < hi; ++j) { const int c = cnt[j]; tile_start[j] = run; run += c; cnt[j] = 0; }
+  if (t == T - 1) tile_start[ntiles] = s_part[T - 1];
+}
+// Chunks = runs of at most 32 consecutive entries of proc that stay inside one group of `ntx` consecutive tiles
+// (ntx = 1: one tile; ntx = tiles per row: sparse tiles share chunks with their x-neighbours).
+// Single block: scan of the rows' chunk counts, then the table entries (begin, end positions in proc).
+__global__ void __launch_bounds__(1024) k_tile_chunks(const int* __restrict__ tile_start, int ntx, int nrows_t, int* __restrict__ chunk_start,
+                                                     int2* __restrict__ chunk_tab) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, T = blockDim.x;
+  const int per = (nrows_t + T - 1) / T, lo = min(t * per, nrows_t), hi = min(lo + per, nrows_t);
+  int sum = 0;
+  for (int r = lo; r < hi; ++r) sum += (tile_start[(r + 1) * ntx] - tile_start[r * ntx] + 31) >> 5;
+  s_part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < T; o <<= 1) { const int v = (t >= o) ? s_part[t - o] : 0; __syncthreads(); s_part[t] += v; __syncthreads(); }
+  int run = s_part[t] - sum;
+  for (int r = lo; r < hi; ++r) {
+    const int q0 = tile_start[r * ntx], q1 = tile_start[(r + 1) * ntx];
+    for (int q = q0; q < q1; q += 32) chunk_tab[run++] = make_int2(q, min(q + 32, q1));
+  }
+  if (t == T - 1) chunk_start[0] = s_part[T - 1];   // total number of chunks
+}
+__global__ void k_tile_scatter(const int* __restrict__ tile_of, int n, const int* __restrict__ tile_start, int* __restrict__ cursor,
+                               int* __restrict__ proc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = tile_of[i] >> 9;
+  proc[tile_start[t] + atomicAdd(cursor + t, 1)] = i;
+}
+// The scatter order inside a tile depends on the atomics: sort each tile's entries by (fine cell, index) so that the
+// processing order (and with it the summation order of the match phase) is the same from run to run.  One warp per tile,
+// rank sort.
+__global__ void k_tile_sort(int* __restrict__ proc, const int* __restrict__ tile_of, const int* __restrict__ tile_start, int ntiles,
+                            int* __restrict__ tmp) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = warp; t < ntiles; t += nwarps) {
+    const int q0 = tile_start[t], n = tile_start[t + 1] - q0;
+    if (n < 2 || n > 4096) continue;   // (a tile that dense keeps its scatter order: still a valid processing order)
+    for (int e = lane; e < n; e += 32) {
+      const int v = proc[q0 + e];
+      const long long kv = ((long long)(tile_of[v] & 511) << 32) | (unsigned int)v;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) { const int u = proc[q0 + j]; rank += ((((long long)(tile_of[u] & 511)) << 32) | (unsigned int)u) < kv; }
+      tmp[q0 + rank] = v;
+    }
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) proc[q0 + e] = tmp[q0 + e];
+    __syncwarp();
+  }
+}
+
+void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
+                       int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches) {
+  if (n_in == 0) return;
+  const int ntiles = g.ntx * g.nty * g.ntz;
+  cudaMemsetAsync(tile_cnt, 0, sizeof(int) * (size_t)ntiles, st);
+  k_tile_count<<<(n_in + 255) / 256, 256, 0, st>>>(fx, fy, fz, n_in, g, tile_cnt, tile_of); ++*launches;
+  k_tile_scan<<<1, 1024, 0, st>>>(tile_cnt, ntiles, tile_start); ++*launches;
+  k_tile_chunks<<<1, 1024, 0, st>>>(tile_start, 1, ntiles, chunk_start, chunk_tab); ++*launches;
+  k_tile_scatter<<<(n_in + 255) / 256, 256, 0, st>>>(tile_of, n_in, tile_start, tile_cnt, proc); ++*launches;
+  k_tile_sort<<<std::min((ntiles + 7) / 8, 4 * lrr_num_sms()), 256, 0, st>>>(proc, tile_of, tile_start, ntiles, tmp); ++*launches;
+}
+
+// ---- search over the staged box ---------------------------------------------------------------------------------
+// Every lane scans ALL staged points of the chunk's box (broadcast shared-memory reads, no per-lane control flow, four
+// independent distance chains in flight).  The result is the exact neighbour iff the ball of the found distance lies
+// inside the box — checked once at the end with the inflated radius / slack of lrr_dev.cuh; otherwise the query goes to
+// pass B with what was found as its candidate.  Exact ties (equal fp64 distances of different points) are resolved
+// towards the lowest original index in a second look at the tied points.
+__device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags, const double* s_T, TileWarp& W, unsigned int* counter, double (&acc)[4]) {
+  const double* A = s_T; const double* tt = s_T + 9; const double* cc = s_T + 12;
+  const bool rigid = (flags & LRR_F_RIGID) != 0;
+  const GridDev& g = a.to.grid;
+  const int lane = threadIdx.x & 31;
+  const unsigned int full = 0xffffffffu;
+  const int nchunks = __ldg(a.nchunks);
+  const double slack = 1e-9 * g.h;
+  unsigned long long* dbg = g_lrr_tl ? g_lrr_tl + 3 * 2048 * 4 : nullptr;   // development counters (scripts/timeline.py)
+  for (;;) {
+    unsigned int ch = 0;
+    if (lane == 0) ch = atomicAdd(counter, 1u);
+    ch = __shfl_sync(full, ch, 0);
+    if ((int)ch >= nchunks) break;
+    const int2 qq = __ldg(a.chunk_tab + ch);
+    const int tq = qq.x + lane;
+    const bool valid = tq < qq.y;
+    int k = 0; double x = 0, y = 0, z = 0, yx = 0, yy = 0, yz = 0;
+    int cx = 0, cy = 0, cz = 0;
+    if (valid) {
+      k = __ldg(a.proc + tq);   // identity order: position k == compact index
+      x = __ldg(a.fx + k); y = __ldg(a.fy + k); z = __ldg(a.fz + k);
+      lrr_map_exact(A, tt, cc, x, y, z, yx, yy, yz);
+      cx = lrr_cell_clamp(yx, g.ox, g.inv_h, g.nx); cy = lrr_cell_clamp(yy, g.oy, g.inv_h, g.ny); cz = lrr_cell_clamp(yz, g.oz, g.inv_h, g.nz);
+    }
+    // box of the chunk's cells plus the halo
+    TileBox B;
+    B.rx0 = max(__reduce_min_sync(full, valid ? cx : 0x7fffffff) - LRR_TILE_H, 0); B.rx1 = min(__reduce_max_sync(full, valid ? cx : -1) + LRR_TILE_H, g.nx - 1);
+    B.ry0 = max(__reduce_min_sync(full, valid ? cy : 0x7fffffff) - LRR_TILE_H, 0); B.ry1 = min(__reduce_max_sync(full, valid ? cy : -1) + LRR_TILE_H, g.ny - 1);
+    B.rz0 = max(__reduce_min_sync(full, valid ? cz : 0x7fffffff) - LRR_TILE_H, 0); B.rz1 = min(__reduce_max_sync(full, valid ? cz : -1) + LRR_TILE_H, g.nz - 1);
+    B.RY = B.ry1 - B.ry0 + 1;
+    const int nrows = B.RY * (B.rz1 - B.rz0 + 1);
+    bool staged = nrows <= LRR_TW_ROWS;
+    int total = 0;
+    __syncwarp();   // the previous chunk's scans are done with W
+    if (staged) {
+      // bounds of the box's x-runs: all loads of a lane (up to LRR_TW_ROWS / 32 rows) in flight together
+      int lo4[LRR_TW_ROWS / 32], sz4[LRR_TW_ROWS / 32];
+#pragma unroll
+      for (int u = 0; u < LRR_TW_ROWS / 32; ++u) {
+        const int r = 32 * u + lane;
+        lo4[u] = 0; sz4[u] = 0;
+        if (r < nrows) {
+          const int row = ((B.rz0 + r / B.RY) * g.ny + (B.ry0 + r % B.RY)) * g.nx;
+          lo4[u] = __ldg(g.cell_start + row + B.rx0); sz4[u] = __ldg(g.cell_start + row + B.rx1 + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < LRR_TW_ROWS / 32; ++u) {
+        if (32 * u < nrows) {   // warp-uniform
+          const int r = 32 * u + lane, sz = (r < nrows) ? sz4[u] - lo4[u] : 0;
+          int inc = sz;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(full, inc, o); if (lane >= o) inc += v; }
+          if (r < nrows) { W.rowlo[r] = lo4[u]; W.rowbase[r] = total + inc - sz; }
+          total += __shfl_sync(full, inc, 31);
+        }
+      }
+      if (lane == 0) W.rowbase[nrows] = total;
+      staged = total <= LRR_TW_CAP;
+    }
+    __syncwarp();
+    if (dbg && lane == 0) { atomicAdd(dbg + 0, 1ull); if (!staged) atomicAdd(dbg + (nrows > LRR_TW_ROWS ? 1 : 2), 1ull); atomicAdd(dbg + 4, (unsigned long long)total); atomicAdd(dbg + 5, (unsigned long long)nrows); atomicAdd(dbg + 6, (unsigned long long)(qq.y - qq.x)); }
+    if (!staged) {
+      if (valid) lrr_match_a_one(a, flags, s_T, a.proc, tq, acc);   // box too large for shared memory: the global-memory scan
+      continue;
+    }
+    // copy the points: four independent loads per lane in flight
+    for (int p0 = 0; p0 < total; p0 += 128) {
+      double4 P[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + 32 * u + lane;
+        if (p < total) {
+          int ra = 0, rb = nrows;   // last row with rowbase <= p
+          while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (W.rowbase[mid] <= p) ra = mid; else rb = mid; }
+          P[u] = lrr_ld_pos4(g.pos4 + W.rowlo[ra] + (p - W.rowbase[ra]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + 32 * u + lane;
+        if (p < total) { W.px[p] = P[u].x; W.py[p] = P[u].y; W.pz[p] = P[u].z; }
+      }
+    }
+    __syncwarp();
+    // uniform scan: every lane, every staged point
+    double best = 1e300; int bi = -1; bool tie = false;
+    {
+      int p = 0;
+      for (; p + 4 <= total; p += 4) {
+        const double d0 = lrr_dist2_exact(yx, yy, yz, W.px[p], W.py[p], W.pz[p]);
+        const double d1 = lrr_dist2_exact(yx, yy, yz, W.px[p + 1], W.py[p + 1], W.pz[p + 1]);
+        const double d2 = lrr_dist2_exact(yx, yy, yz, W.px[p + 2], W.py[p + 2], W.pz[p + 2]);
+        const double d3 = lrr_dist2_exact(yx, yy, yz, W.px[p + 3], W.py[p + 3], W.pz[p + 3]);
+        if (d0 <= best) { tie = (d0 == best); best = d0; bi = p; }
+        if (d1 <= best) { tie = (d1 == best); best = d1; bi = p + 1; }
+        if (d2 <= best) { tie = (d2 == best); best = d2; bi = p + 2; }
+        if (d3 <= best) { tie = (d3 == best); best = d3; bi = p + 3; }
+      }
+      for (; p < total; ++p) {
+        const double d0 = lrr_dist2_exact(yx, yy, yz, W.px[p], W.py[p], W.pz[p]);
+        if (d0 <= best) { tie = (d0 == best); best = d0; bi = p; }
+      }
+    }
+    // (tie is true iff the final minimum was reached by at least two points: a smaller distance found later clears it)
+    int best_s = -1, best_o = 0x7fffffff;
+    bool done = false;
+    if (valid && bi >= 0) {
+      int ra = 0, rb = nrows;
+      while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (W.rowbase[mid] <= bi) ra = mid; else rb = mid; }
+      best_s = W.rowlo[ra] + (bi - W.rowbase[ra]);
+      if (tie) {   // rare: several points at exactly the minimum distance -> lowest original index
+        best_o = lrr_pos4_orig(lrr_ld_pos4(g.pos4 + best_s));
+        for (int p = 0; p < total; ++p) {
+          if (p != bi && lrr_dist2_exact(yx, yy, yz, W.px[p], W.py[p], W.pz[p]) == best) {
+            int r2a = 0, r2b = nrows;
+            while (r2b - r2a > 1) { const int mid = (r2a + r2b) >> 1; if (W.rowbase[mid] <= p) r2a = mid; else r2b = mid; }
+            const int s2 = W.rowlo[r2a] + (p - W.rowbase[r2a]);
+            const int o2 = lrr_pos4_orig(lrr_ld_pos4(g.pos4 + s2));
+            if (o2 < best_o) { best_o = o2; best_s = s2; }
+          }
+        }
+      }
+      // proven iff every cell the ball touches is inside the staged box (grid borders clamp on both sides alike)
+      const double R = sqrt(best) * (1.0 + 1e-9) + slack;
+      const int z0 = lrr_cell_clamp(yz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(yz + R, g.oz, g.inv_h, g.nz);
+      const int y0 = lrr_cell_clamp(yy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(yy + R, g.oy, g.inv_h, g.ny);
+      const int xa = lrr_cell_clamp(yx - R, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(yx + R, g.ox, g.inv_h, g.nx);
+      done = !(z0 < B.rz0 || z1 > B.rz1 || y0 < B.ry0 || y1 > B.ry1 || xa < B.rx0 || xb > B.rx1);
+    }
+    // unfinished queries -> pass B queue, one atomic per warp
+    const unsigned int qm = __ballot_sync(full, valid && !done);
+    if (qm) {
+      int base = 0;
+      if (lane == __ffs(qm) - 1) base = atomicAdd(a.hq_count, __popc(qm));
+      base = __shfl_sync(full, base, __ffs(qm) - 1);
+      if (valid && !done) {
+        if (best_s >= 0 && !tie) best_o = lrr_pos4_orig(lrr_ld_pos4(g.pos4 + best_s));
+        if (best_s < 0) best = 1e300;
+        const int cand = a.prev_s[k];   // the neighbour of the previous iteration is usually a much tighter bound than the best point of the box
+        if (cand >= 0) {
+          const double4 pc = lrr_ld_pos4(g.pos4 + cand);
+          const double dc = lrr_dist2_exact(yx, yy, yz, pc.x, pc.y, pc.z);
+          const int oc = lrr_pos4_orig(pc);
+          if (dc < best || (dc == best && oc < best_o)) { best = dc; best_s = cand; best_o = oc; }
+        }
+        const int slot = base + __popc(qm & ((1u << lane) - 1u));
+        a.hq_k[slot] = k; a.hq_best[slot] = best_s >= 0 ? best : 1e300; a.hq_s[slot] = best_s; a.hq_o[slot] = best_s >= 0 ? best_o : 0x7fffffff;
+      }
+      if (dbg && lane == 0) atomicAdd(dbg + 3, (unsigned long long)__popc(qm));
+    }
+    if (valid && done) lrr_match_finish(a, rigid, k, k, x, y, z, yx, yy, yz, best_s, acc);
+  }
+}
+
+__global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid_constant__ EstArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_T[15];
+  __shared__ double s_out[8], s_tmp[8 * LRR_TILE_WARPS];
+  const int dir = blockIdx.y;
+  const DirArgs& d = a.d[dir];
+  unsigned int* counter = a.ticket + 4 + dir;
+  lrr_tl(0, 0);
+  lrr_stage_transform(d.sc, s_T);
+  double acc[4] = {0, 0, 0, 0};
+  if (d.chunk_tab && d.proc && d.M == d.n_in) {
+    TileWarp& W = reinterpret_cast<TileWarp*>(smem_raw)[threadIdx.x >> 5];
+    lrr_match_tile_body(d, a.flags, s_T, W, counter, acc);
+  } else {
+    lrr_match_a_body_dynamic(d, a.flags, s_T, counter, acc);
+  }
+  lrr_tl(0, 1);
+  const GridScope scope = lrr_scope_of(a, dir);
+  if (scope.reduce<4>(acc, s_out, s_tmp)) {
+    lrr_tl(0, 2);
+    if (threadIdx.x == 0) {
+      Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3];
+      *counter = 0;
+    }
+  }
+  lrr_tl(0, 3);
+}
+
+bool lrr_match_tile_usable(const EstArgs& a) {
+  for (int d = 0; d < a.ndir; ++d) if (a.d[d].chunk_tab && a.d[d].proc && a.d[d].M == a.d[d].n_in) return true;
+  return false;
+}
+void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(TileWarp) * LRR_TILE_WARPS;
+  if (!attr_set) { cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  // every block of both directions resident at once (4 blocks of 128 threads per SM): no second wave
+  dim3 grid(std::max(1, (4 * lrr_num_sms()) / a.ndir), a.ndir);
+  k_match_tile<<<grid, LRR_TILE_THREADS, smem, st>>>(a); ++*launches;
+}

@@ -1,0 +1,37 @@
+"""Per-block timeline of k_match / k_match_hard / k_accumulate at the finest level (development aid; %globaltimer marks).
+marks: 0 block start, 1 end of the element loop, 2 finalizer entered (last block only; accumulate: reduce returned), 3 block end."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from lrr_b200 import synth, lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+pair = synth.make_pair(3, n, n)
+L = lib(); ctx = L.context(0)
+fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+est = ctx.estimator("rrl_sym", mv, fx, 12)
+est.set_transform(*pair["init"])
+it, conv = 0, False
+while not conv and it < 70:
+    conv = est.one_iteration(it); it += 1
+for k in range(3):
+    est.one_iteration(it); it += 1
+f = L.dll.lrr_debug_timeline; f.restype = C.c_int; f.argtypes = [C.c_int, C.c_void_p]
+f(1, None)
+est.one_iteration(it)
+out = np.zeros(4 * 2048 * 4, dtype=np.uint64)
+f(0, out.ctypes.data_as(C.c_void_p))
+tl = out.reshape(4, 2048, 4).astype(np.float64)
+for kid, name in enumerate(["k_match", "k_match_hard", "k_accumulate"]):
+    t = tl[kid]; live = t[:, 0] > 0
+    if not live.any():
+        continue
+    t = t[live]; t0 = t[:, 0].min()
+    rel = lambda x: (x - t0) / 1e3
+    end = np.where(t[:, 3] > 0, t[:, 3], np.where(t[:, 2] > 0, t[:, 2], t[:, 1]))
+    print(f"{name}: blocks {live.sum()}  start spread {rel(t[:,0].max()):.1f} us | loop end: median {np.median(rel(t[:,1])):.1f} p90 {np.percentile(rel(t[:,1]),90):.1f} max {rel(t[:,1].max()):.1f} us"
+          f" | finalizer entered {rel(t[:,2][t[:,2]>0].min()) if (t[:,2]>0).any() else -1:.1f} .. {rel(t[:,2].max()):.1f} us | last block end {rel(end.max()):.1f} us")
+    body = (t[:, 1] - t[:, 0]) / 1e3
+    print(f"   per-block loop time: min {body.min():.1f} median {np.median(body):.1f} p90 {np.percentile(body,90):.1f} max {body.max():.1f} us")
+c = out.reshape(4, 2048 * 4)[3][:8].astype(np.int64)
+if c[0]:
+    print(f"tile chunks {c[0]} (both directions): fallback rows {c[1]} cap {c[2]} | queued for pass B {c[3]} queries | per chunk: staged points {c[4]/c[0]:.0f} rows {c[5]/c[0]:.0f} queries {c[6]/c[0]:.1f}")
