@@ -142,8 +142,11 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
   static const bool no_tile = getenv("LRR_NO_TILE") != nullptr;   // A/B switch for measurements
-  if (!no_tile && lrr_match_tile_usable(a)) lrr_k_match_tile(a, st, launches);   // finest level: shared-memory-staged cells (lrr_tile.cu)
-  else {
+  const int tile = no_tile ? 0 : lrr_match_tile_usable(a);
+  if (tile) {   // finest level: shared-memory-staged cells (lrr_tile.cu); with every direction there it also finishes the hard queries
+    lrr_k_match_tile(a, tile == 2, st, launches);
+    if (tile == 2) return;
+  } else {
     dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
     k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
   }

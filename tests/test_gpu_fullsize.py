@@ -44,9 +44,11 @@ def test_symmetric_iterations_at_finest_level_100k(gpu_lib, oracle_lib, pair100k
         g.one_iteration(it); o.one_iteration(it)
         for d in (0, 1):
             gf, gt, gw = g.get_matches(d); of, ot, ow = o.get_matches(d)
-            assert np.array_equal(gt, ot) and rel(gw, ow) < 1e-8
+            assert np.array_equal(gt, ot), (it, d, "neighbours differ", int(np.count_nonzero(gt != ot)))
+            assert rel(gw, ow) < 1e-8, (it, d, "weights", rel(gw, ow), list(g.state().scale), list(o.state().scale))
             G, O = g.get_transform(d), o.get_transform(d)
-            assert rel(G["A"], O["A"]) < 1e-5 and rel(G["t"], O["t"]) < 1e-5 and rel(G["cov"], O["cov"]) < 1e-5
+            assert rel(G["A"], O["A"]) < 1e-5 and rel(G["t"], O["t"]) < 1e-5 and rel(G["cov"], O["cov"]) < 1e-5, \
+                (it, d, rel(G["A"], O["A"]), rel(G["t"], O["t"]), rel(G["cov"], O["cov"]))
 
 
 def test_recovers_known_affine_100k(gpu_lib):
