@@ -142,11 +142,8 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
   static const bool no_tile = getenv("LRR_NO_TILE") != nullptr;   // A/B switch for measurements
-  const int tile = no_tile ? 0 : lrr_match_tile_usable(a);
-  if (tile) {   // finest level: shared-memory-staged cells (lrr_tile.cu); with every direction there it also finishes the hard queries
-    lrr_k_match_tile(a, tile == 2, st, launches);
-    if (tile == 2) return;
-  } else {
+  if (!no_tile && lrr_match_tile_usable(a)) lrr_k_match_tile(a, st, launches);   // finest level: shared-memory-staged cells (lrr_tile.cu)
+  else {
     dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
     k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
   }
@@ -239,9 +236,12 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
   const bool merged = (a.flags & LRR_F_MERGED) != 0, window = (a.flags & LRR_F_BRACKET) != 0;
   const int group = merged ? 0 : dir;
   const int reversed = merged && dir != a.src;
+  lrr_tl(4, 0);
   const bool fin = lrr_phase_weight(lrr_scope(a, dir), a.d[dir], a.flags, reversed, a.selG[group], a.selS[group], ex.scale_mode[dir],
                                     ex.scale_in[dir], sh);
+  lrr_tl(4, 1);
   if (!fin) return;
+  lrr_tl(4, 2);
   // group-level: the two order statistics (window mode: finished here; histogram mode: bins located for k_collect)
   const bool pair = merged && a.ndir == 2;
   if (pair && !lrr_pair_done(a, 2)) return;
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
       if (!hit) atomicOr(&a.d[d].sc->status, LRR_ST_SELECT_MISS);   // every direction: k_accumulate must skip as a whole
     }
   }
+  lrr_tl(4, 3);
 }
 void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches) {
   WeightExtra ex;
@@ -357,7 +358,7 @@ void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* lau
 // development aid: arm / read the per-block timeline marks (lrr_dev.cuh).  out: 4 kernels x 2048 blocks x 4 marks.
 extern "C" int lrr_debug_timeline(int arm, unsigned long long* out) {
   static unsigned long long* buf = nullptr;
-  const size_t n = 4 * 2048 * 4;
+  const size_t n = 8 * 2048 * 4;
   if (arm) {
     if (!buf) { if (cudaMalloc(&buf, n * sizeof(unsigned long long)) != cudaSuccess) return 1; }
     cudaMemset(buf, 0, n * sizeof(unsigned long long));

@@ -168,8 +168,8 @@ void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // p
 // lrr_tile.cu: tile construction and the shared-memory-staged pass A of the finest level
 void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
                        int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches);
-int lrr_match_tile_usable(const EstArgs& a);
-void lrr_k_match_tile(const EstArgs& a, int final_match, cudaStream_t st, long long* launches);
+bool lrr_match_tile_usable(const EstArgs& a);
+void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_tile_set_timeline(unsigned long long* p);
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);

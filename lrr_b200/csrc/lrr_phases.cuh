@@ -412,24 +412,38 @@ static __device__ bool lrr_sel_window_finish(const SelDev& s, double n_keys, dou
   const long long target = (n - 1) / 2 + 1, nb = (long long)below;
   const bool hit = cnt <= LRR_SEL_CAP && nb <= target && target < nb + (long long)cnt;
   if (hit) {
-    // bitonic sort of the window's keys in shared memory, then the element of the wanted rank
     const unsigned int rank = (unsigned int)(target - nb);
-    unsigned int np = 1; while (np < cnt) np <<= 1;
-    for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) sh_cand[i] = (i < cnt) ? __ldcg(s.cand + i) : 1e308;
+    for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) sh_cand[i] = __ldcg(s.cand + i);
     __syncthreads();
-    for (unsigned int k = 2; k <= np; k <<= 1)
-      for (unsigned int jj = k >> 1; jj > 0; jj >>= 1) {
-        for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) {
-          const unsigned int ixj = i ^ jj;
-          if (ixj > i) {
-            const double x = sh_cand[i], y = sh_cand[ixj];
-            if ((x > y) == ((i & k) == 0)) { sh_cand[i] = y; sh_cand[ixj] = x; }
-          }
-        }
-        __syncthreads();
+    if (cnt <= 1024) {
+      // exact element of the wanted rank by rank counting (broadcast shared-memory reads, no barriers): the window holds
+      // a few hundred keys, and 45 barrier-separated bitonic stages cost more than cnt^2 / blockDim comparisons
+      for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const double v = sh_cand[i];
+        unsigned int r = 0;
+        for (unsigned int j = 0; j < cnt; ++j) { const double u = sh_cand[j]; r += (u < v) || (u == v && j < i); }
+        if (r == rank) { s_val = v; s_hit = 1; }
       }
-    if (threadIdx.x == 0) { s_val = sh_cand[rank]; s_hit = 1; }
-    __syncthreads();
+      __syncthreads();
+    } else {
+      // bitonic sort of the window's keys in shared memory, then the element of the wanted rank
+      unsigned int np = 1; while (np < cnt) np <<= 1;
+      for (unsigned int i = cnt + threadIdx.x; i < np; i += blockDim.x) sh_cand[i] = 1e308;
+      __syncthreads();
+      for (unsigned int k = 2; k <= np; k <<= 1)
+        for (unsigned int jj = k >> 1; jj > 0; jj >>= 1) {
+          for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) {
+            const unsigned int ixj = i ^ jj;
+            if (ixj > i) {
+              const double x = sh_cand[i], y = sh_cand[ixj];
+              if ((x > y) == ((i & k) == 0)) { sh_cand[i] = y; sh_cand[ixj] = x; }
+            }
+          }
+          __syncthreads();
+        }
+      if (threadIdx.x == 0) { s_val = sh_cand[rank]; s_hit = 1; }
+      __syncthreads();
+    }
   }
   if (threadIdx.x == 0) {
     if (s_hit) {
@@ -620,11 +634,14 @@ static __device__ bool lrr_gj_inverse(int n, double* Msh /* n*n, destroyed */, d
     if (!(piv > 1e-13 * maxd)) { if (tid == 0) s_ok = 0; }
     __syncthreads();
     if (!s_ok) break;
+    // one reciprocal per pivot instead of three divisions per thread (~40 dependent instructions each) on the critical path
+    // of every iteration; a rounding apart from the quotient, far inside the 1e-5 gate
+    const double ipv = 1.0 / piv;
     double f = 0, mp = 0, ip = 0;
-    if (act) { f = Msh[r * n + p] / piv; mp = Msh[p * n + cidx]; ip = inv[p * n + cidx]; }
+    if (act) { f = Msh[r * n + p] * ipv; mp = Msh[p * n + cidx]; ip = inv[p * n + cidx]; }
     __syncthreads();
     if (act) {
-      if (r == p) { Msh[tid] = mp / piv; inv[tid] = ip / piv; }
+      if (r == p) { Msh[tid] = mp * ipv; inv[tid] = ip * ipv; }
       else { Msh[tid] -= f * mp; inv[tid] -= f * ip; }
     }
     __syncthreads();

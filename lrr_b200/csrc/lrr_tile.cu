@@ -200,24 +200,10 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
     }
     __syncwarp();
     if (dbg && lane == 0) { atomicAdd(dbg + 0, 1ull); if (!staged) atomicAdd(dbg + (nrows > LRR_TW_ROWS ? 1 : 2), 1ull); atomicAdd(dbg + 4, (unsigned long long)total); atomicAdd(dbg + 5, (unsigned long long)nrows); atomicAdd(dbg + 6, (unsigned long long)(qq.y - qq.x)); }
-    double best = 1e300; int best_s = -1, best_o = 0x7fffffff;
-    bool done = false, tie = false;
     if (!staged) {
-      // box too large for shared memory (rare): the per-thread global-memory scan of lrr_dev.cuh
-      if (valid) {
-        NNState st; st.best = 1e300; st.best_s = a.prev_s[k]; st.best_o = 0x7fffffff;
-        if (st.best_s >= 0) {
-          const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
-          st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
-          done = lrr_nn_ball_thread(g, yx, yy, yz, st);
-        } else {
-          const int r27 = lrr_nn_block27_thread(g, yx, yy, yz, st);
-          if (r27 == 1) done = true;
-          else if (r27 == 0) done = lrr_nn_ball_thread(g, yx, yy, yz, st);
-        }
-        best = st.best; best_s = st.best_s; best_o = st.best_o;
-      }
-    } else {
+      if (valid) lrr_match_a_one(a, flags, s_T, a.proc, tq, acc);   // box too large for shared memory: the global-memory scan
+      continue;
+    }
     // copy the points: four independent loads per lane in flight
     for (int p0 = 0; p0 < total; p0 += 128) {
       double4 P[4];
@@ -238,7 +224,7 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
     }
     __syncwarp();
     // uniform scan: every lane, every staged point
-    int bi = -1;
+    double best = 1e300; int bi = -1; bool tie = false;
     {
       int p = 0;
       for (; p + 4 <= total; p += 4) {
@@ -257,6 +243,8 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
       }
     }
     // (tie is true iff the final minimum was reached by at least two points: a smaller distance found later clears it)
+    int best_s = -1, best_o = 0x7fffffff;
+    bool done = false;
     if (valid && bi >= 0) {
       int ra = 0, rb = nrows;
       while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (W.rowbase[mid] <= bi) ra = mid; else rb = mid; }
@@ -280,38 +268,32 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
       const int xa = lrr_cell_clamp(yx - R, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(yx + R, g.ox, g.inv_h, g.nx);
       done = !(z0 < B.rz0 || z1 > B.rz1 || y0 < B.ry0 || y1 > B.ry1 || xa < B.rx0 || xb > B.rx1);
     }
+    // unfinished queries -> pass B queue, one atomic per warp
+    const unsigned int qm = __ballot_sync(full, valid && !done);
+    if (qm) {
+      int base = 0;
+      if (lane == __ffs(qm) - 1) base = atomicAdd(a.hq_count, __popc(qm));
+      base = __shfl_sync(full, base, __ffs(qm) - 1);
       if (valid && !done) {
-        // candidate for the cooperative completion below: the better of (best point of the box, neighbour of the previous
-        // iteration — usually a much tighter bound when the true neighbour lies outside the box)
         if (best_s >= 0 && !tie) best_o = lrr_pos4_orig(lrr_ld_pos4(g.pos4 + best_s));
         if (best_s < 0) best = 1e300;
-        const int cand = a.prev_s[k];
+        const int cand = a.prev_s[k];   // the neighbour of the previous iteration is usually a much tighter bound than the best point of the box
         if (cand >= 0) {
           const double4 pc = lrr_ld_pos4(g.pos4 + cand);
           const double dc = lrr_dist2_exact(yx, yy, yz, pc.x, pc.y, pc.z);
           const int oc = lrr_pos4_orig(pc);
           if (dc < best || (dc == best && oc < best_o)) { best = dc; best_s = cand; best_o = oc; }
         }
+        const int slot = base + __popc(qm & ((1u << lane) - 1u));
+        a.hq_k[slot] = k; a.hq_best[slot] = best_s >= 0 ? best : 1e300; a.hq_s[slot] = best_s; a.hq_o[slot] = best_s >= 0 ? best_o : 0x7fffffff;
       }
-    }
-    // unfinished queries (ball leaving the box, no point in the box): the whole warp finishes them one by one with the
-    // exact shell / ball scan of lrr_dev.cuh (what k_match_hard does for the per-thread path) — no queue, no second kernel
-    unsigned int qm = __ballot_sync(full, valid && !done);
-    if (dbg && lane == 0 && qm) atomicAdd(dbg + 3, (unsigned long long)__popc(qm));
-    while (qm) {
-      const int src = __ffs(qm) - 1;
-      qm &= qm - 1;
-      NNState sb;
-      sb.best = __shfl_sync(full, best, src); sb.best_s = __shfl_sync(full, best_s, src); sb.best_o = __shfl_sync(full, best_o, src);
-      const double qx = __shfl_sync(full, yx, src), qy = __shfl_sync(full, yy, src), qz = __shfl_sync(full, yz, src);
-      const int sfin = lrr_nn_pass_b(g, qx, qy, qz, sb);
-      if (lane == src) { best_s = sfin; done = true; }
+      if (dbg && lane == 0) atomicAdd(dbg + 3, (unsigned long long)__popc(qm));
     }
     if (valid && done) lrr_match_finish(a, rigid, k, k, x, y, z, yx, yy, yz, best_s, acc);
   }
 }
 
-__global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid_constant__ EstArgs a, const int final_match) {
+__global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid_constant__ EstArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_T[15];
   __shared__ double s_out[8], s_tmp[8 * LRR_TILE_WARPS];
@@ -332,25 +314,22 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
   if (scope.reduce<4>(acc, s_out, s_tmp)) {
     lrr_tl(0, 2);
     if (threadIdx.x == 0) {
-      if (final_match) lrr_match_finalize(d, a.flags, s_out);   // every match of the direction exists: no pass B follows
-      else { Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3]; }
+      Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3];
       *counter = 0;
     }
   }
   lrr_tl(0, 3);
 }
 
-// 0: no direction is at the finest level; 1: some are (pass B still needed for the others); 2: all are (the tile kernel finishes every match)
-int lrr_match_tile_usable(const EstArgs& a) {
-  int n = 0;
-  for (int d = 0; d < a.ndir; ++d) if (a.d[d].chunk_tab && a.d[d].proc && a.d[d].M == a.d[d].n_in) ++n;
-  return n == 0 ? 0 : (n == a.ndir ? 2 : 1);
+bool lrr_match_tile_usable(const EstArgs& a) {
+  for (int d = 0; d < a.ndir; ++d) if (a.d[d].chunk_tab && a.d[d].proc && a.d[d].M == a.d[d].n_in) return true;
+  return false;
 }
-void lrr_k_match_tile(const EstArgs& a, int final_match, cudaStream_t st, long long* launches) {
+void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches) {
   static bool attr_set = false;
   const size_t smem = sizeof(TileWarp) * LRR_TILE_WARPS;
   if (!attr_set) { cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   // every block of both directions resident at once (4 blocks of 128 threads per SM): no second wave
   dim3 grid(std::max(1, (4 * lrr_num_sms()) / a.ndir), a.ndir);
-  k_match_tile<<<grid, LRR_TILE_THREADS, smem, st>>>(a, final_match); ++*launches;
+  k_match_tile<<<grid, LRR_TILE_THREADS, smem, st>>>(a); ++*launches;
 }

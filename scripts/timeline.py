@@ -18,10 +18,10 @@ for k in range(3):
 f = L.dll.lrr_debug_timeline; f.restype = C.c_int; f.argtypes = [C.c_int, C.c_void_p]
 f(1, None)
 est.one_iteration(it)
-out = np.zeros(4 * 2048 * 4, dtype=np.uint64)
+out = np.zeros(8 * 2048 * 4, dtype=np.uint64)
 f(0, out.ctypes.data_as(C.c_void_p))
-tl = out.reshape(4, 2048, 4).astype(np.float64)
-for kid, name in enumerate(["k_match", "k_match_hard", "k_accumulate"]):
+tl = out.reshape(8, 2048, 4).astype(np.float64)
+for kid, name in [(0, "k_match"), (1, "k_match_hard"), (2, "k_accumulate"), (4, "k_weight")]:
     t = tl[kid]; live = t[:, 0] > 0
     if not live.any():
         continue
@@ -32,6 +32,10 @@ for kid, name in enumerate(["k_match", "k_match_hard", "k_accumulate"]):
           f" | finalizer entered {rel(t[:,2][t[:,2]>0].min()) if (t[:,2]>0).any() else -1:.1f} .. {rel(t[:,2].max()):.1f} us | last block end {rel(end.max()):.1f} us")
     body = (t[:, 1] - t[:, 0]) / 1e3
     print(f"   per-block loop time: min {body.min():.1f} median {np.median(body):.1f} p90 {np.percentile(body,90):.1f} max {body.max():.1f} us")
-c = out.reshape(4, 2048 * 4)[3][:8].astype(np.int64)
+c = out.reshape(8, 2048 * 4)[3][:8].astype(np.int64)
 if c[0]:
     print(f"tile chunks {c[0]} (both directions): fallback rows {c[1]} cap {c[2]} | queued for pass B {c[3]} queries | per chunk: staged points {c[4]/c[0]:.0f} rows {c[5]/c[0]:.0f} queries {c[6]/c[0]:.1f}")
+ph = out.reshape(8, 2048 * 4)[3][8:16].astype(np.float64)
+if ph.sum() > 0:
+    names = ["load+map+cand", "row bounds", "stage", "filter", "exact", "check", "cooperative", "finish"]
+    print("tile kernel, warp-time per chunk (us): " + ", ".join(f"{n} {v / 1.965e3 / max(c[0], 1):.2f}" for n, v in zip(names, ph)))
