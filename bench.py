@@ -60,45 +60,64 @@ KERNEL_BYTES = {
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML in a thread (nvidia-smi -lms
+    block-buffers its pipe, so a short run only ever delivered one line); nvidia-smi one-shot calls as the fallback."""
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.gpu, self.stop_flag, self.t, self.mode = [], gpu_index, threading.Event(), None, None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.mode = pynvml, "nvml"
         except Exception:
-            self.proc = None
+            self.mode = "smi"
+        self.t = threading.Thread(target=self._loop, daemon=True); self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _loop(self):
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                if self.mode == "nvml":
+                    nv = self.nv
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM); mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    names = []
+                    for nm, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+                        bit = getattr(nv, attr, None)
+                        if bit is not None and (r & bit):
+                            names.append(nm)
+                    self.rows.append((float(sm), float(mx), names))
+                else:
+                    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    names = [nm for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:6])
+                             if v.strip().lower().startswith("active")]
+                    self.rows.append((float(out[0]), float(out[1]), names))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.stop_flag.wait(0.05)
+
+    def stop(self):
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler not started"]}
+        self.stop_flag.set(); self.t.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples (NVML / nvidia-smi unavailable)"]}
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": reasons, "samples": len(self.rows), "source": self.mode}
 
 
 def make_workload():
@@ -329,8 +348,12 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- end to end through the C ABI with host buffers (rank-local; max over ranks) ----
     e2e_steps = 0 if args.only_iterations else max(1, min(5, args.steps))
-    pf, pm = pin(pair["fixed"]), pin(pair["moving"])
-    h2d = feature_bytes(pair["fixed"]) + feature_bytes(pair["moving"])
+    # the rrl estimators work on cdcl_feature_ICP (location, float strength, shape, error projector, directions — no
+    # covariance, cdcl/cdcl_feature_ICP.h:23-96), so the end-to-end call uploads exactly those arrays
+    e2e_fixed = {k: v for k, v in pair["fixed"].items() if k != "C6"}
+    e2e_moving = {k: v for k, v in pair["moving"].items() if k != "C6"}
+    pf, pm = pin(e2e_fixed), pin(e2e_moving)
+    h2d = feature_bytes(e2e_fixed) + feature_bytes(e2e_moving)
     d2h = (9 + 3 + 3 + 144) * 8
     with torch.cuda.stream(stream):
         e2e_iters = 0
@@ -408,7 +431,7 @@ def run_b200(args, rank, world, local_rank):
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        names = {"match": ["k_match", "k_match_hard"], "accumulate": ["k_accumulate"], "weight": ["k_weight"]}.get(dom, [])
+        names = {"match": ["k_match_tile", "k_match_hard"], "accumulate": ["k_accumulate"], "weight": ["k_weight"]}.get(dom, [])
         if names and all(n in tj["dram_bytes_per_launch"] for n in names):
             traffic = sum(tj["dram_bytes_per_launch"][n] for n in names); traffic_src = tj["source"]
     except Exception:
@@ -422,7 +445,7 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "flushed (256 MiB write) between timed iterations; working set ~30 MB is L2-resident otherwise",
                    "ramp_iterations": ramp_iters, "ramp_converged": bool(ramp_conv)},
         "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else "k_" + dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else ("k_match_tile + k_match_hard (exact 1-NN: shared-memory-staged cells, then the queued far queries)" if dom == "match" else "k_" + dom), "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                      "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
         "roofline_iteration": {"algorithmic_bytes": it_bytes, "achieved_gbs": it_bytes / (ms_step * 1e-3) / 1e9,
@@ -431,7 +454,7 @@ def run_b200(args, rank, world, local_rank):
         "kernels": per_phase,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "iterations": e2e_iters, "seconds": float(te[0]),
-                "what": "per step: upload both volumes from pinned host memory (grid build), construct estimator, set_transform, "
+                "what": "per step: upload both volumes (cdcl_feature_ICP arrays: locations, projectors, strengths, shapes, directions) from pinned host memory (grid build), construct estimator, set_transform, "
                         "ramped run to convergence (<=70 one_iteration calls), read back transform+covariance"},
         "gpu_launches": int(launches),
         "clocks": clocks,

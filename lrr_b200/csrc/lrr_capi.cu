@@ -535,8 +535,12 @@ static bool fused_ok(lrr_est* e) {
   // Measured on B200 (profiles/r1_summary.md): the fused kernel is not faster than the per-phase kernels (fewer threads in
   // flight per phase at 128 registers; ~5 us per in-kernel reduction), so it is opt-in.
   static const bool on = getenv("LRR_FUSED") != nullptr;
-  if (!on) return false;
+  static const int small_max = getenv("LRR_FUSED_SMALL") ? atoi(getenv("LRR_FUSED_SMALL")) : 0;
   const int nd = e->sym() ? 2 : 1;
+  if (!on) {
+    if (small_max <= 0) return false;
+    for (int d = 0; d < nd; ++d) if (std::min<int64_t>(e->d[d].number_points, e->d[d].n_in) > small_max) return false;
+  }
   for (int d = 0; d < nd; ++d) if (!e->d[d].scale_estimated) return false;
   return true;
 }

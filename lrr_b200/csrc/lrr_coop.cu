@@ -8,6 +8,7 @@
 // Used for the steady state (scales estimated); the first iteration after set_transform (MUSE sort) takes the
 // multi-kernel path.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "lrr_phases.cuh"
 namespace cg = cooperative_groups;
 
@@ -207,7 +208,12 @@ cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const doubl
   CoopExtra ex; ex.dbg = dbg;
   for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
   void* args[2] = {(void*)&a, (void*)&ex};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_iteration, dim3(lrr_coop_blocks()), dim3(LRR_THREADS), args, 0, st);
+  // grid sized to the problem: with few points most of a full grid only adds barrier participants and partial rows
+  int maxM = a.d[0].M; if (a.ndir == 2 && a.d[1].M > maxM) maxM = a.d[1].M;
+  int nb = (maxM + LRR_THREADS - 1) / LRR_THREADS;
+  if (const char* env = getenv("LRR_FUSED_BLOCKS")) nb = atoi(env);
+  nb = nb < 8 ? 8 : (nb > lrr_coop_blocks() ? lrr_coop_blocks() : nb);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_iteration, dim3(nb), dim3(LRR_THREADS), args, 0, st);
   ++*launches;
   return e;
 }

@@ -97,26 +97,34 @@ __global__ void k_tile_scatter(const int* __restrict__ tile_of, int n, const int
   proc[tile_start[t] + atomicAdd(cursor + t, 1)] = i;
 }
 // The scatter order inside a tile depends on the atomics: sort each tile's entries by (fine cell, index) so that the
-// processing order (and with it the summation order of the match phase) is the same from run to run.  One warp per tile,
-// rank sort.
-__global__ void k_tile_sort(int* __restrict__ proc, const int* __restrict__ tile_of, const int* __restrict__ tile_start, int ntiles,
-                            int* __restrict__ tmp) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int t = warp; t < ntiles; t += nwarps) {
-    const int q0 = tile_start[t], n = tile_start[t + 1] - q0;
-    if (n < 2 || n > 4096) continue;   // (a tile that dense keeps its scatter order: still a valid processing order)
-    for (int e = lane; e < n; e += 32) {
-      const int v = proc[q0 + e];
-      const long long kv = ((long long)(tile_of[v] & 511) << 32) | (unsigned int)v;
-      int rank = 0;
-      for (int j = 0; j < n; ++j) { const int u = proc[q0 + j]; rank += ((((long long)(tile_of[u] & 511)) << 32) | (unsigned int)u) < kv; }
-      tmp[q0 + rank] = v;
-    }
-    __syncwarp();
-    for (int e = lane; e < n; e += 32) proc[q0 + e] = tmp[q0 + e];
-    __syncwarp();
+// processing order (and with it the summation order of the match phase) is the same from run to run.  One block per
+// tile, bitonic sort of 64-bit keys in shared memory (a tile with more than 2048 entries keeps its scatter order: still a
+// valid processing order).
+#define LRR_TILE_SORT_CAP 2048
+__global__ void __launch_bounds__(256) k_tile_sort(int* __restrict__ proc, const int* __restrict__ tile_of, const int* __restrict__ tile_start) {
+  __shared__ unsigned long long keys[LRR_TILE_SORT_CAP];
+  const int t = blockIdx.x;
+  const int q0 = tile_start[t], n = tile_start[t + 1] - q0;
+  if (n < 2 || n > LRR_TILE_SORT_CAP) return;
+  unsigned int np = 2; while ((int)np < n) np <<= 1;
+  for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) {
+    unsigned long long kv = ~0ull;
+    if ((int)i < n) { const int v = proc[q0 + i]; kv = ((unsigned long long)(tile_of[v] & 511) << 32) | (unsigned int)v; }
+    keys[i] = kv;
   }
+  __syncthreads();
+  for (unsigned int k = 2; k <= np; k <<= 1)
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned int i = threadIdx.x; i < np; i += blockDim.x) {
+        const unsigned int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = keys[i], y = keys[ixj];
+          if ((x > y) == ((i & k) == 0)) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) proc[q0 + i] = (int)(unsigned int)(keys[i] & 0xffffffffull);
 }
 
 void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
@@ -128,7 +136,8 @@ void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int
   k_tile_scan<<<1, 1024, 0, st>>>(tile_cnt, ntiles, tile_start); ++*launches;
   k_tile_chunks<<<1, 1024, 0, st>>>(tile_start, 1, ntiles, chunk_start, chunk_tab); ++*launches;
   k_tile_scatter<<<(n_in + 255) / 256, 256, 0, st>>>(tile_of, n_in, tile_start, tile_cnt, proc); ++*launches;
-  k_tile_sort<<<std::min((ntiles + 7) / 8, 4 * lrr_num_sms()), 256, 0, st>>>(proc, tile_of, tile_start, ntiles, tmp); ++*launches;
+  k_tile_sort<<<ntiles, 256, 0, st>>>(proc, tile_of, tile_start); ++*launches;
+  (void)tmp;
 }
 
 // ---- search over the staged box ---------------------------------------------------------------------------------
