@@ -41,16 +41,23 @@ enum {
   LRR_ERR_STATE = 5         /* call order violated (e.g. metric before any match exists)           */
 };
 
-/* estimator kinds = the four reference classes on the path */
+/* estimator kinds = the four reference classes on the path + the 2-D demo estimator of config 1 */
 enum {
   LRR_CDCL_FWD = 0, /* cdcl_estimation_ICP_matching_all<dim,dof>            cdcl/cdcl_estimation_ICP_matching_all.h:34  */
   LRR_CDCL_SYM = 1, /* cdcl_estimation_symmetric_ICP_matching_all<dim,dof>  cdcl/cdcl_estimation_symmetric_ICP_matching_all.h */
   LRR_RRL_FWD  = 2, /* rrl_estimation_ICP_matching_all<dim,dof>             rrl/rrl_estimation_ICP_matching_all.h       */
-  LRR_RRL_SYM  = 3  /* rrl_estimation_symmetric_ICP_matching_all<dim,dof>   rrl/rrl_estimation_symmetric_ICP_matching_all.h */
+  LRR_RRL_SYM  = 3, /* rrl_estimation_symmetric_ICP_matching_all<dim,dof>   rrl/rrl_estimation_symmetric_ICP_matching_all.h */
+  LRR_CDCL_ICP = 4  /* cdcl_estimation_ICP<2,4> (ctor #1, one resolution): normal-distance ICP over plain cdcl_feature<2> with
+                       cdcl_trans_similarity2d, cdcl/cdcl_estimation_ICP.txx:352-746; selected by `-method 4` in
+                       cdcl/examples/estimate.cxx:99-101 (BASELINE.json configs[0]).  All moving points in every iteration (no
+                       point ramp), scale = 2 x (MUSE, then RMS of the fresh matches) (:567-584), convergence |dRMS| < 1e-4 (:424) */
 };
 
-/* transform kinds (cdcl/cdcl_trans_affine.h, cdcl/cdcl_trans_rigid3d.h) */
-enum { LRR_TRANS_AFFINE = 0, LRR_TRANS_RIGID3D = 1 };
+/* transform kinds (cdcl/cdcl_trans_affine.h, cdcl/cdcl_trans_rigid3d.h, cdcl/cdcl_trans_similarity2d.h).
+ * LRR_TRANS_SIMILARITY2D: y = s R x + t in the plane; at this boundary it travels as the 3x3 / 3-vector pair (A = s R in the upper
+ * left 2x2 block, A22 = 1, t2 = 0, centre 0) and its covariance is 4x4 over (s cos a, s sin a, tx, ty)
+ * (cdcl_trans_similarity2d.cxx:76-110). */
+enum { LRR_TRANS_AFFINE = 0, LRR_TRANS_RIGID3D = 1, LRR_TRANS_SIMILARITY2D = 2 };
 
 /* direction selector for symmetric estimators (forward_ / backward_ members) */
 enum { LRR_DIR_FORWARD = 0, LRR_DIR_BACKWARD = 1 };
@@ -110,6 +117,12 @@ int  lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count);
  * rrl/examples/compute_distance_map.cxx:55-151: the upload also builds the exact-NN uniform grid. */
 int  lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6,
                          const double* strength, const uint8_t* shape, const double* dirs, lrr_fset** out);
+/* Plain cdcl_feature<dim> sets (location, strength, covariance; cdcl/cdcl_feature.h:17-64) for LRR_CDCL_ICP.  loc = dim x n SoA,
+ * cov = dim(dim+1)/2 x n SoA (xx, xy, yy).  The error projector the reference re-derives at every use from the fixed feature's
+ * covariance — outer product of the eigenvector of the smallest eigenvalue, cdcl/cdcl_estimation_ICP.txx:470-477,686-696 — is
+ * computed once here, on the device.  dim must be 2 (the 3-D form of that estimator needs the multi-resolution subsampling of
+ * cdcl/cdcl_utils.txx:640-960, which is outside the path). */
+int  lrr_features_upload_cov(lrr_ctx* ctx, int dim, int64_t n, const double* loc, const double* cov, const double* strength, lrr_fset** out);
 void lrr_features_destroy(lrr_fset* fs);
 int64_t lrr_features_size(const lrr_fset* fs);
 /* exact Euclidean 1-NN of n_query host points (SoA xyz) among the set; lowest index wins ties.
@@ -119,8 +132,8 @@ int  lrr_features_nearest(lrr_fset* fs, int64_t n_query, const double* q_xyz, in
 /* ---- estimators ------------------------------------------------------------------------------ */
 /* ctor #3 semantics (cdcl sym .txx:144-164, rrl sym .txx:198-220): forward_ = (moving_inside -> fixed_all),
  * backward_ = (fixed_inside -> moving_all).  Until lrr_est_set_subsets is called the inside sets are
- * the whole sets.  Forward kinds ignore the backward half.  dim must be 3; dof 12 (affine) or 6
- * (rigid3d, cdcl kinds only — Q6). */
+ * the whole sets.  Forward kinds ignore the backward half.  dim must be 3 with dof 12 (affine) or 6
+ * (rigid3d, cdcl kinds only — Q6), or — LRR_CDCL_ICP only — dim 2 with dof 4 over sets from lrr_features_upload_cov. */
 int  lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset* moving_all, lrr_fset* fixed_all, lrr_est** out);
 void lrr_est_destroy(lrr_est* est);
 /* set_features(moving_inside, fixed_inside)  (cdcl sym :206-226, rrl sym :269-289; forward: set_moving_data).

@@ -14,8 +14,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 LRR_OK = 0
-KIND = {"cdcl_fwd": 0, "cdcl_sym": 1, "rrl_fwd": 2, "rrl_sym": 3}
-TRANS_AFFINE, TRANS_RIGID3D = 0, 1
+KIND = {"cdcl_fwd": 0, "cdcl_sym": 1, "rrl_fwd": 2, "rrl_sym": 3, "cdcl_icp": 4}
+TRANS_AFFINE, TRANS_RIGID3D, TRANS_SIMILARITY2D = 0, 1, 2
 DIR_FORWARD, DIR_BACKWARD = 0, 1
 ORDER_FIXED, ORDER_RESHUFFLE = 0, 1
 METRIC = {"rms": 0, "weighted": 1, "median": 2, "sheet_angles": 3, "tube_angles": 4}
@@ -24,7 +24,7 @@ METRIC = {"rms": 0, "weighted": 1, "median": 2, "sheet_angles": 3, "tube_angles"
 ABI_SYMBOLS = [
     "ctx_create", "ctx_destroy", "ctx_set_stream", "ctx_synchronize", "ctx_last_error", "ctx_launch_count",
     "ctx_set_profiling", "ctx_phase_times",
-    "features_upload", "features_destroy", "features_size", "features_nearest",
+    "features_upload", "features_upload_cov", "features_destroy", "features_size", "features_nearest",
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
@@ -105,6 +105,7 @@ class Lib:
             "ctx_last_error": (C.c_char_p, [vp]), "ctx_launch_count": (i64, [vp]),
             "ctx_set_profiling": (i32, [vp, i32]), "ctx_phase_times": (i32, [vp, i32, pd, C.POINTER(C.c_int64)]),
             "features_upload": (i32, [vp, i64, pd, pd, pd, pd, C.POINTER(C.c_uint8), pd, C.POINTER(vp)]),
+            "features_upload_cov": (i32, [vp, i32, i64, pd, pd, pd, C.POINTER(vp)]),
             "features_destroy": (None, [vp]), "features_size": (i64, [vp]),
             "features_nearest": (i32, [vp, i64, pd, pi32]),
             "est_create": (i32, [vp, i32, i32, i32, vp, vp, C.POINTER(vp)]), "est_destroy": (None, [vp]),
@@ -189,10 +190,19 @@ class Context:
 
 
 class FeatureSet:
-    """SoA host arrays -> lrr_fset.  feats: dict(xyz(3,n), P6(6,n), C6(6,n)|None, strength(n), shape(n) u8, dirs(9,n)|None)."""
+    """SoA host arrays -> lrr_fset.  feats: dict(xyz(3,n), P6(6,n), C6(6,n)|None, strength(n), shape(n) u8, dirs(9,n)|None),
+    or — plain 2-D cdcl_feature sets of the cdcl_icp kind — dict(xy(2,n), C3(3,n) = (xx,xy,yy), strength(n)|None)."""
 
     def __init__(self, ctx: Context, feats: dict):
         self.ctx = ctx
+        if "xy" in feats:
+            n = int(feats["xy"].shape[1]); self.n = n
+            xy = _f64(feats["xy"], (2, n)); C3 = _f64(feats["C3"], (3, n))
+            st = _f64(feats["strength"], (n,)) if feats.get("strength") is not None else None
+            h = C.c_void_p()
+            ctx.check(ctx.lib.fn("features_upload_cov")(ctx.h, 2, n, _dp(xy), _dp(C3), _dp(st), C.byref(h)), "features_upload_cov")
+            self.h = h
+            return
         n = int(feats["xyz"].shape[1])
         self.n = n
         xyz = _f64(feats["xyz"], (3, n)); P6 = _f64(feats["P6"], (6, n))
@@ -243,7 +253,7 @@ class Estimator:
 
     def set_transform(self, A, t, c=None, cov=None, kind=None):
         if kind is None:
-            kind = TRANS_AFFINE if self.dof == 12 else TRANS_RIGID3D
+            kind = TRANS_AFFINE if self.dof == 12 else (TRANS_RIGID3D if self.dof == 6 else TRANS_SIMILARITY2D)
         A = _f64(np.asarray(A).reshape(9)); t = _f64(t, (3,))
         c = _f64(c if c is not None else np.zeros(3), (3,))
         cov = _f64(np.asarray(cov).reshape(-1)) if cov is not None else None

@@ -128,11 +128,11 @@ int lrr_ctx_need_sort(lrr_ctx* ctx, size_t n) {
 }
 
 // ---- feature sets ----------------------------------------------------------------------------------------
-extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6, const double* strength,
-                                   const uint8_t* shape, const double* dirs, lrr_fset** out) {
-  if (!ctx || n < 0 || n > 0x7fffff00LL || !out || (n > 0 && (!xyz || !P6))) return LRR_ERR_INVALID;
+// cov2 != null: planar set, P6 / C6 are derived on the device from the 2x2 covariances (lrr_features_upload_cov)
+static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6, const double* strength,
+                                const uint8_t* shape, const double* dirs, const double* cov2, lrr_fset** out) {
   enter(ctx);
-  lrr_fset* fs = new lrr_fset(); fs->ctx = ctx; fs->n = n;
+  lrr_fset* fs = new lrr_fset(); fs->ctx = ctx; fs->n = n; fs->dim = cov2 ? 2 : 3;
   fs->host_xyz.assign(xyz, xyz + 3 * n);
   std::vector<double> zeros; std::vector<uint8_t> zshape;
   if (!strength) { zeros.assign((size_t)n, 0.0); strength = zeros.data(); }
@@ -142,10 +142,15 @@ extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, c
   FCK(dmalloc(&fs->xyz, (size_t)3 * n)); FCK(dmalloc(&fs->s, (size_t)n)); FCK(dmalloc(&fs->P6, (size_t)6 * n));
   FCK(dmalloc(&fs->shape, (size_t)n));
   FCK(cudaMemcpyAsync(fs->xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
-  FCK(cudaMemcpyAsync(fs->P6, P6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st));
+  double* cov2_d = nullptr;
+  if (cov2) {
+    FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(dmalloc(&cov2_d, (size_t)3 * n));
+    FCK(cudaMemcpyAsync(cov2_d, cov2, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+    lrr_k_projector2_from_cov(cov2_d, (int)n, fs->P6, fs->C6, st, &ctx->launches);
+  } else FCK(cudaMemcpyAsync(fs->P6, P6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st));
   FCK(cudaMemcpyAsync(fs->s, strength, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   FCK(cudaMemcpyAsync(fs->shape, shape, (size_t)n, cudaMemcpyHostToDevice, st));
-  if (C6) { FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(cudaMemcpyAsync(fs->C6, C6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st)); }
+  if (C6 && !cov2) { FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(cudaMemcpyAsync(fs->C6, C6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st)); }
   if (dirs) { FCK(dmalloc(&fs->dirs, (size_t)9 * n)); FCK(cudaMemcpyAsync(fs->dirs, dirs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, st)); }
   FCK(dmalloc(&fs->pos4, (size_t)n)); FCK(dmalloc(&fs->rec, (size_t)8 * n)); FCK(dmalloc(&fs->sorted_of_orig, (size_t)n));
   FsetBuild fb; memset(&fb, 0, sizeof(fb));
@@ -158,9 +163,25 @@ extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, c
   lrr_k_fill_records(d, fs->rec, st, &ctx->launches);
   FCK(cudaStreamSynchronize(st));
   FCK(cudaGetLastError());
+  dfree(cov2_d);
 #undef FCK
   *out = fs;
   return LRR_OK;
+}
+extern "C" int lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6, const double* strength,
+                                   const uint8_t* shape, const double* dirs, lrr_fset** out) {
+  if (!ctx || n < 0 || n > 0x7fffff00LL || !out || (n > 0 && (!xyz || !P6))) return LRR_ERR_INVALID;
+  return features_upload_impl(ctx, n, xyz, P6, C6, strength, shape, dirs, nullptr, out);
+}
+// plain cdcl_feature<dim> sets (cdcl/cdcl_feature.h:17-64) for LRR_CDCL_ICP: planar locations stored with z = 0, so the uniform
+// grid degenerates to one layer of cells and every kernel of the 3-D path runs unchanged
+extern "C" int lrr_features_upload_cov(lrr_ctx* ctx, int dim, int64_t n, const double* loc, const double* cov, const double* strength, lrr_fset** out) {
+  if (!ctx || n < 0 || n > 0x7fffff00LL || !out || (n > 0 && (!loc || !cov))) return LRR_ERR_INVALID;
+  if (dim != 2) return LRR_ERR_UNSUPPORTED;
+  std::vector<double> xyz((size_t)3 * n, 0.0);
+  if (n) memcpy(xyz.data(), loc, sizeof(double) * 2 * n);
+  static const double dummy = 0.0;
+  return features_upload_impl(ctx, n, xyz.data(), nullptr, nullptr, strength, nullptr, nullptr, n ? cov : &dummy, out);
 }
 extern "C" void lrr_features_destroy(lrr_fset* fs) {
   if (!fs) return;
@@ -280,6 +301,8 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
   if (e->sym()) f |= LRR_F_SYM;
   if (e->strength) f |= LRR_F_STRENGTH;
   if (e->kind == LRR_CDCL_SYM) f |= LRR_F_MERGED;
+  if (e->icp()) f |= LRR_F_ICP;
+  if (e->dof == 4) f |= LRR_F_SIM2D;
   a.flags = f; a.dof = e->dof; a.src = src; a.estimate_parameters = 1;
   a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
   a.partials = ctx->partials; a.ticket = ctx->ticket;
@@ -321,12 +344,16 @@ static void reset_control(lrr_est* e) { e->oscillation_count = 0; e->error_diffe
 extern "C" int lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset* moving_all, lrr_fset* fixed_all, lrr_est** out) {
   if (!ctx || !moving_all || !fixed_all || !out) return LRR_ERR_INVALID;
   if (moving_all->ctx != ctx || fixed_all->ctx != ctx) return LRR_ERR_INVALID;
-  if (dim != 3 || (dof != 12 && dof != 6)) return LRR_ERR_UNSUPPORTED;
-  if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;   // Q6
-  if (kind < 0 || kind > 3) return LRR_ERR_INVALID;
+  if (kind < 0 || kind > 4) return LRR_ERR_INVALID;
+  if (kind == LRR_CDCL_ICP) {   // cdcl_estimation_ICP<2,4> over planar cdcl_feature<2> sets (cdcl/Templates/cdcl_estimation_ICP+2.4-.cxx)
+    if (dim != 2 || dof != 4 || moving_all->dim != 2 || fixed_all->dim != 2) return LRR_ERR_UNSUPPORTED;
+  } else {
+    if (dim != 3 || (dof != 12 && dof != 6) || moving_all->dim != 3 || fixed_all->dim != 3) return LRR_ERR_UNSUPPORTED;
+    if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;   // Q6
+  }
   enter(ctx);
   lrr_est* e = new lrr_est();
-  e->ctx = ctx; e->kind = kind; e->dof = dof; e->moving_all = moving_all; e->fixed_all = fixed_all;
+  e->ctx = ctx; e->kind = kind; e->dof = dof; e->dim = dim; e->moving_all = moving_all; e->fixed_all = fixed_all;
   e->normalize = e->sym(); e->strength = e->sym();   // the symmetric ctor switches both on (cdcl sym :151-156)
   reset_control(e);
   int rc = dir_alloc(ctx, e->d[0], moving_all, fixed_all);
@@ -336,7 +363,7 @@ extern "C" int lrr_est_create(lrr_ctx* ctx, int kind, int dim, int dof, lrr_fset
   if (rc != LRR_OK) { lrr_est_destroy(e); return rc; }
   for (int d = 0; d < 2; ++d) {
     identity_scal(e->h[d], dof);
-    e->d[d].number_points = std::min<int64_t>(1000, e->d[d].n_in);
+    e->d[d].number_points = e->icp() ? e->d[d].n_in : std::min<int64_t>(1000, e->d[d].n_in);   // (cdcl_estimation_ICP: no point ramp)
     e->d[d].scale_estimated = false;
   }
   for (int d = 0; d < (e->sym() ? 2 : 1); ++d) {
@@ -364,6 +391,7 @@ extern "C" int lrr_est_set_subsets(lrr_est* e, const int32_t* mi, int64_t nm, co
     if (rc != LRR_OK) return rc;
     reset_control(e);   // set_features (cdcl sym :206-226)
   }
+  if (e->icp()) e->d[0].number_points = e->d[0].n_in;   // set_moving_data (cdcl_estimation_ICP.h:80): every point, every iteration
   e->werr_cache_valid = false;
   return LRR_OK;
 }
@@ -375,19 +403,27 @@ static void set_identity_norm(Scal& s) {
 
 extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
   if (!e || !A9 || !t3) return LRR_ERR_INVALID;
-  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12)) return LRR_ERR_INVALID;
+  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
   Scal& f = e->h[0];
   memcpy(f.A, A9, 72); memcpy(f.t, t3, 24);
   if (c3) memcpy(f.c, c3, 24); else memset(f.c, 0, 24);
+  if (tk == LRR_TRANS_SIMILARITY2D) {
+    // (A = s R, t) -> cdcl_trans_similarity2d(s, ang, t) -> s * R(ang)  (ctor #2, similarity2d.cxx:33-47): the planar block is
+    // re-formed from scale and angle, everything outside it is fixed (z stays 0), the centre is always 0
+    const double s_ = std::sqrt(A9[0] * A9[0] + A9[3] * A9[3]), ang = std::atan2(A9[3], A9[0]);
+    const double sa = std::sin(ang), ca = std::cos(ang);
+    memset(f.A, 0, 72); f.A[0] = s_ * ca; f.A[1] = s_ * -sa; f.A[3] = s_ * sa; f.A[4] = s_ * ca; f.A[8] = 1.0;
+    f.t[2] = 0.0; memset(f.c, 0, 24);
+  }
   memset(f.cov, 0, sizeof(f.cov));
   if (cov) for (int i = 0; i < e->dof * e->dof; ++i) f.cov[i] = cov[i];
   f.from_mapped = 0; f.status = 0; f.scale_estimated = 0;
   if (!e->normalize) set_identity_norm(f);
   for (int d = 0; d < 2; ++d) {   // set_transform (cdcl :141-153): scale_estimated_ = false, number_points_ = 1000
     e->d[d].scale_estimated = false;
-    e->d[d].number_points = std::min<int64_t>(1000, e->d[d].n_in);
+    e->d[d].number_points = e->icp() ? e->d[d].n_in : std::min<int64_t>(1000, e->d[d].n_in);   // (cdcl_estimation_ICP.h:70 only resets scale_estimated_)
   }
   if ((rc = push_scal(e, 0)) != LRR_OK) return rc;
   if (e->sym()) {
@@ -437,6 +473,7 @@ extern "C" int lrr_est_set_initial_scale(lrr_est* e, int dir, double s) {
 }
 extern "C" int lrr_est_set_number_points(lrr_est* e, int dir, int64_t m, int* at_max) {
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0) || m < 0) return LRR_ERR_INVALID;
+  if (e->icp()) return LRR_ERR_INVALID;   // cdcl_estimation_ICP has no set_number_points (cdcl_estimation_ICP.h)
   lrr_dir& d = e->d[dir];
   bool r;
   if (m >= d.n_in) { d.number_points = d.n_in; r = true; } else { d.number_points = m; r = false; }   // cdcl :95-108
@@ -537,6 +574,7 @@ static bool fused_ok(lrr_est* e) {
   static const bool on = getenv("LRR_FUSED") != nullptr;
   static const int small_max = getenv("LRR_FUSED_SMALL") ? atoi(getenv("LRR_FUSED_SMALL")) : 0;
   const int nd = e->sym() ? 2 : 1;
+  if (e->icp()) return false;
   if (!on) {
     if (small_max <= 0) return false;
     for (int d = 0; d < nd; ++d) if (std::min<int64_t>(e->d[d].number_points, e->d[d].n_in) > small_max) return false;
@@ -617,12 +655,12 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   // (small problems are latency-bound either way, and while the transform still moves fast the medians move too: after a
   //  miss the window is not tried again for a growing number of estimates)
   const int maxM = std::max(a.d[0].M, nd == 2 ? a.d[1].M : 0);
-  bool window = !force_hist && !cdcl_backward && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym()) && maxM >= 16384;
+  bool window = !force_hist && !cdcl_backward && !stale && ctx->sel_owner == sel_sig && (e->strength || e->sym()) && maxM >= 16384 && !e->icp();
   if (window && e->window_holdoff > 0) { e->window_holdoff -= 1; window = false; }
   if (window) a.flags |= LRR_F_BRACKET;
   ctx->sel_owner = sel_sig;
   { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
-  if ((e->strength || (e->sym() && !cdcl_backward)) && !window) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
+  if ((e->strength || (e->sym() && !cdcl_backward)) && !window && !e->icp()) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
   { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches); }
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   e->werr_cache_valid = false;
@@ -775,7 +813,7 @@ extern "C" int lrr_est_get_transform(lrr_est* e, int dir, int* tk, double* A9, d
   enter(e->ctx);
   int rc = pull_scal(e, 1 << dir); if (rc != LRR_OK) return rc;
   const Scal& s = e->h[dir];
-  if (tk) *tk = e->dof == 12 ? LRR_TRANS_AFFINE : LRR_TRANS_RIGID3D;
+  if (tk) *tk = e->dof == 12 ? LRR_TRANS_AFFINE : (e->dof == 6 ? LRR_TRANS_RIGID3D : LRR_TRANS_SIMILARITY2D);
   if (A9) memcpy(A9, s.A, 72); if (t3) memcpy(t3, s.t, 24); if (c3) memcpy(c3, s.c, 24);
   if (cov) memcpy(cov, s.cov, sizeof(double) * e->dof * e->dof);
   return LRR_OK;
@@ -884,6 +922,12 @@ extern "C" int lrr_est_transfer_cov(lrr_est* e, int dir, double* S9) {
   // J[dd][i] = sum_a x~_a E[a][dd][i]
   auto E = [&](int a_, int dd, int i) -> double {
     if (dof == 12) { const int di = i < 9 ? i / 3 : i - 9, ai = i < 9 ? i % 3 : 3; return (di == dd && ai == a_) ? 1.0 : 0.0; }
+    if (dof == 4) {   // similarity2d: J = [x -y 1 0; y x 0 1]
+      if (dd > 1) return 0.0;
+      if (i == 0) return a_ == dd ? 1.0 : 0.0;
+      if (i == 1) return (dd == 0 && a_ == 1) ? -1.0 : ((dd == 1 && a_ == 0) ? 1.0 : 0.0);
+      return (a_ == 3 && dd == i - 2) ? 1.0 : 0.0;
+    }
     if (i >= 3) return (a_ == 3 && dd == i - 3) ? 1.0 : 0.0;
     if (a_ == 3 || dd == i || a_ != 3 - dd - i) return 0.0;
     return ((dd == 2 && i == 0) || (dd == 0 && i == 1) || (dd == 1 && i == 2)) ? 1.0 : -1.0;

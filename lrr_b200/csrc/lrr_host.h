@@ -33,6 +33,7 @@ struct lrr_ctx {
 struct lrr_fset {
   lrr_ctx* ctx = nullptr;
   int64_t n = 0;
+  int dim = 3;   // 2: plain planar cdcl_feature<2> set (lrr_features_upload_cov), stored with z = 0
   double *xyz = nullptr, *s = nullptr, *P6 = nullptr, *C6 = nullptr, *dirs = nullptr;
   uint8_t* shape = nullptr;
   double4* pos4 = nullptr; double* rec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
@@ -61,7 +62,7 @@ struct lrr_dir {
 
 struct lrr_est {
   lrr_ctx* ctx = nullptr;
-  int kind = 0, dof = 12;
+  int kind = 0, dof = 12, dim = 3;
   lrr_fset *moving_all = nullptr, *fixed_all = nullptr;
   lrr_dir d[2];
   Scal h[2];                 // host mirrors (head part is kept current)
@@ -73,6 +74,7 @@ struct lrr_est {
   bool werr_cache_valid = false; double werr_cache = 0;
   int window_holdoff = 0, window_backoff = 0;   // order-statistic window: estimates to skip after a miss
   bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
+  bool icp() const { return kind == LRR_CDCL_ICP; }   // cdcl_estimation_ICP<2,4>: no point ramp, scale constant 2, strength by sum
   bool rrl() const { return kind == LRR_RRL_FWD || kind == LRR_RRL_SYM; }
 };
 

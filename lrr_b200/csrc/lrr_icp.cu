@@ -73,6 +73,33 @@ void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long lon
   k_fill_records<<<(f.n + 255) / 256, 256, 0, st>>>(f, rec); ++*launches;
 }
 
+// Error projector of a planar cdcl_feature: outer product of the eigenvector of the smallest eigenvalue of its 2x2 covariance = the
+// point normal (cdcl/cdcl_estimation_ICP.txx:470-477, re-derived there at every use; constant per feature, so computed once here).
+// Closed form of the symmetric 2x2 eigenproblem; an isotropic covariance (no defined normal) gives the x axis.
+__global__ void k_projector2_from_cov(const double* __restrict__ cov3, int n, double* __restrict__ P6, double* __restrict__ C6) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = cov3[i], b = cov3[(size_t)n + i], c = cov3[2 * (size_t)n + i];
+  const double half = __dmul_rn(0.5, a - c), rad = sqrt(__dadd_rn(__dmul_rn(half, half), __dmul_rn(b, b)));
+  const double lam = __dmul_rn(0.5, a + c) - rad;
+  double v0, v1;
+  if (a >= c) { v0 = b; v1 = lam - a; } else { v0 = lam - c; v1 = b; }
+  const double n2 = __dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1));
+  double pxx = 1.0, pxy = 0.0, pyy = 0.0;
+  if (n2 > 0.0) {
+    const double inv = 1.0 / sqrt(n2);
+    v0 = __dmul_rn(v0, inv); v1 = __dmul_rn(v1, inv);
+    pxx = __dmul_rn(v0, v0); pxy = __dmul_rn(v0, v1); pyy = __dmul_rn(v1, v1);
+  }
+  const size_t N = (size_t)n;
+  P6[i] = pxx; P6[N + i] = pxy; P6[2 * N + i] = 0.0; P6[3 * N + i] = pyy; P6[4 * N + i] = 0.0; P6[5 * N + i] = 0.0;
+  C6[i] = a; C6[N + i] = b; C6[2 * N + i] = 0.0; C6[3 * N + i] = c; C6[4 * N + i] = 0.0; C6[5 * N + i] = 0.0;
+}
+void lrr_k_projector2_from_cov(const double* cov3, int n, double* P6, double* C6, cudaStream_t st, long long* launches) {
+  if (n == 0) return;
+  k_projector2_from_cov<<<(n + 255) / 256, 256, 0, st>>>(cov3, n, P6, C6); ++*launches;
+}
+
 __global__ void k_gather_from(FsetDev src, const int* __restrict__ idx, int n_in, double* __restrict__ fx, double* __restrict__ fy,
                               double* __restrict__ fz, double* __restrict__ fs, double* __restrict__ fP6) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,6 +269,10 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
   lrr_tl(4, 1);
   if (!fin) return;
   lrr_tl(4, 2);
+  if (a.flags & LRR_F_ICP) {   // cdcl_estimation_ICP: the strength weights are normalised by their sum, no order statistic
+    if (threadIdx.x == 0) { Scal* sc = a.d[dir].sc; sc->G = (a.flags & LRR_F_STRENGTH) ? sc->n_nonzero : 1.0; sc->S = 1.0; }
+    return;
+  }
   // group-level: the two order statistics (window mode: finished here; histogram mode: bins located for k_collect)
   const bool pair = merged && a.ndir == 2;
   if (pair && !lrr_pair_done(a, 2)) return;

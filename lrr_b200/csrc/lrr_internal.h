@@ -132,6 +132,8 @@ enum {
   LRR_F_USE_OLD_W = 64,   // scale from the current weights (estimate_LS_backward after estimate_LS)
   LRR_F_NOSPATIAL = 1024, // cdcl estimate_LS_backward: merged list without weight_spatially (cdcl sym :744-763)
   LRR_F_NO_OTHER_RENORM = 2048,   // ... and only the estimated direction's transform goes through normalize / unnormalize
+  LRR_F_ICP = 4096,       // cdcl_estimation_ICP: scale constant 2.0 (cdcl_estimation_ICP.txx:580), strength weights normalised by their SUM (:607-637)
+  LRR_F_SIM2D = 8192,     // cdcl_trans_similarity2d<2,4>: J = [x -y 1 0; y x 0 1], parameters (s cos a, s sin a, tx, ty)
   LRR_F_BRACKET = 512     // order statistics from the window around the previous iteration's values (no histogram atomics, no collect pass)
 };
 
@@ -162,6 +164,8 @@ int lrr_num_sms();
 // ---- ICP kernels (lrr_icp.cu) ----------------------------------------------------------------------
 void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* mark /* from_all.n ints scratch */, int* proc, cudaStream_t st, long long* launches);
 void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long long* launches);
+// planar cdcl_feature<2> sets: P6 / C6 (3-D layout, z parts zero) from the 2x2 covariances (xx, xy, yy) x n
+void lrr_k_projector2_from_cov(const double* cov3, int n, double* P6, double* C6, cudaStream_t st, long long* launches);
 void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,
                        cudaStream_t st, long long* launches);
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // pass A + pass B

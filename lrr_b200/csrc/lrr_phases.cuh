@@ -477,7 +477,8 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
   Scal* sc = a.sc;
   const bool sym = (flags & LRR_F_SYM) != 0, spatial = LRR_SPATIAL(flags);
   const double unit = sym ? 1.0 : sc->rto;   // forward estimators weight in normalised coordinates (Q3)
-  const double scale = lrr_scale_of(sc, a.M, flags, unit, scale_mode, scale_in);
+  // cdcl_estimation_ICP doubles whatever scale it found (`constant = 2.0`, cdcl_estimation_ICP.txx:580-581)
+  const double scale = lrr_scale_of(sc, a.M, flags, unit, scale_mode, scale_in) * ((flags & LRR_F_ICP) ? 2.0 : 1.0);
   const double scale2 = scale * scale, unit2 = unit * unit;
   const double inv_unit2 = 1.0 / unit2, inv_scale2 = 1.0 / scale2;
   const int mapped = sc->from_mapped;
@@ -496,7 +497,11 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
     double w = lrr_weight_BT(r2n * inv_scale2) * inv_scale2;
     double gk = -1.0, sk = -1.0;
     const int i = lrr_from_index(a, k);
-    if ((flags & LRR_F_STRENGTH) && w != 0.0 && s >= 0) {   // Q13
+    if ((flags & LRR_F_ICP) && (flags & LRR_F_STRENGTH)) {
+      // cdcl_estimation_ICP.txx:607-611,629-637: every match is multiplied by p.strength * q.strength (no cap, zero weights
+      // included) and the weights are then divided by the SUM of those products (acc[0]; written to sc->G by k_weight)
+      if (s >= 0) { gk = __ldg(a.fs + i) * __ldg(a.to.rec + 8 * (size_t)s + 6); acc[0] += gk; }
+    } else if ((flags & LRR_F_STRENGTH) && w != 0.0 && s >= 0) {   // Q13
       const double sq = __ldg(a.to.rec + 8 * (size_t)s + 6);
       const double sp = __ldg(a.fs + i);
       double g;
@@ -563,7 +568,7 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
     double w = a.w[k];                             // Beaton-Tukey weight / scale^2
     if (strength) {
       const double g = a.gkey[k];
-      if (g >= 0.0) w *= g;                        // only where w != 0   (cdcl :839-848)
+      if (g >= 0.0 || (flags & LRR_F_ICP)) w *= g; // only where w != 0   (cdcl :839-848); cdcl_estimation_ICP: every match
       w *= invG;                                   // every match         (cdcl :857-860, Q13)
     }
     if (spatial) { w *= a.skey[k]; w *= invS; }    // cdcl :985-1002
@@ -656,6 +661,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   __shared__ double AtA[144], Atb[12], Msh[144], inv[144], theta[12];
   const int tid = threadIdx.x;
   const bool rigid = (flags & LRR_F_RIGID) != 0, normalize = (flags & LRR_F_NORMALIZE) != 0, sym = (flags & LRR_F_SYM) != 0;
+  const bool sim2d = (flags & LRR_F_SIM2D) != 0;
   for (int i = tid; i < 108; i += blockDim.x) {
     double v = __ldcg(&F->mom[i]);
     if (sym && B) v += __ldcg(&B->mom[i]);
@@ -669,7 +675,35 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   if (tid < 15) { sF[tid] = __ldcg(&F->A[0] + tid); sFg[tid] = __ldcg(&F->Ag[0] + tid); if (B) sB[tid] = __ldcg(&B->A[0] + tid); }
   else if (tid >= 32 && tid < 40) { sFn[tid - 32] = __ldcg(&F->cfrom[0] + (tid - 32)); if (B) sBn[tid - 32] = __ldcg(&B->cfrom[0] + (tid - 32)); }
   __syncthreads();
-  if (!rigid) {
+  if (sim2d) {
+    // similarity2d: J = [x -y 1 0; y x 0 1] (cdcl_trans_similarity2d.cxx:150-164), b = q.  J[d][i] = sum_a x~_a E[a][d][i] with
+    // E[0][0][0] = E[1][1][0] = 1, E[1][0][1] = -1, E[0][1][1] = 1, E[3][0][2] = E[3][1][3] = 1
+    if (tid < 16 + 4) {
+      auto Jc = [](int a, int d, int i) -> double {
+        if (d > 1) return 0.0;
+        if (i == 0) return (a == d) ? 1.0 : 0.0;
+        if (i == 1) return (d == 0 && a == 1) ? -1.0 : ((d == 1 && a == 0) ? 1.0 : 0.0);
+        return (a == 3 && d == i - 2) ? 1.0 : 0.0;
+      };
+      if (tid < 16) {
+        const int i = tid / 4, jx = tid % 4;
+        double s = 0;
+        for (int a = 0; a < 4; ++a) for (int d = 0; d < 2; ++d) {
+          const double ca = Jc(a, d, i); if (ca == 0.0) continue;
+          for (int b = 0; b < 4; ++b) for (int e = 0; e < 2; ++e) {
+            const double cb = Jc(b, e, jx); if (cb == 0.0) continue;
+            s += ca * cb * T[a][b][lrr_sym6(d, e)];
+          }
+        }
+        AtA[i * 4 + jx] = s;
+      } else {
+        const int i = tid - 16;
+        double s = 0;
+        for (int a = 0; a < 4; ++a) for (int d = 0; d < 2; ++d) { const double ca = Jc(a, d, i); if (ca != 0.0) s += ca * V[a][d]; }
+        Atb[i] = s;
+      }
+    }
+  } else if (!rigid) {
     // affine: parameter index of (row d, column a of x~) = a<3 ? 3d+a : 9+d   (cdcl_trans_affine.txx:65-106,141-161)
     for (int e = tid; e < 144; e += blockDim.x) {
       const int i = e / 12, jx = e % 12;
@@ -731,7 +765,10 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   // covariance: set_covariance(invAA), then affine unnormalize scales it by B = diag((rf/rm) I9, rf I3)
   for (int e = tid; e < dof * dof; e += blockDim.x) {
     double v = inv[e];
-    if (!rigid && normalize) {
+    if (sim2d && normalize) {   // similarity2d unnormalize: B = diag(rf/rm, rf/rm, rf, rf)  (similarity2d.cxx:293-304)
+      const int i = e / 4, jx = e % 4;
+      v *= ((i < 2) ? rfx / rm : rfx) * ((jx < 2) ? rfx / rm : rfx);
+    } else if (!rigid && normalize) {
       const int i = e / 12, jx = e % 12;
       v *= ((i < 9) ? rfx / rm : rfx) * ((jx < 9) ? rfx / rm : rfx);
     }
@@ -741,7 +778,29 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   if (tid == 0) {
     double A[9], t[3], c[3];
     const double cm[3] = {sFn[0], sFn[1], sFn[2]}, cf[3] = {sFn[4 + 0], sFn[4 + 1], sFn[4 + 2]};
-    if (!rigid) {
+    if (sim2d) {
+      if (estimate_parameters) {
+        // set_parameterization (similarity2d.cxx:93-110): s = |(p0,p1)|, R from (p0,p1)/s, ang = atan2; then unnormalize (:271-291)
+        // rebuilds s R from cos / sin of that angle
+        double s_ = sqrt(theta[0] * theta[0] + theta[1] * theta[1]);
+        double ca = theta[0] / s_, sa = theta[1] / s_;
+        t[0] = theta[2]; t[1] = theta[3]; t[2] = 0.0;
+        if (normalize) {
+          const double ang = atan2(sa, ca);
+          s_ = rfx / rm * s_;
+          const double c2 = cos(ang), s2 = sin(ang);
+          const double sR[4] = {s_ * c2, -s_ * s2, s_ * s2, s_ * c2};
+          for (int r = 0; r < 2; ++r) {
+            double acc = (-sR[2 * r]) * cm[0]; acc += (-sR[2 * r + 1]) * cm[1];
+            t[r] = acc + rfx * t[r] + cf[r];
+          }
+        }
+        for (int i = 0; i < 9; ++i) A[i] = 0.0;
+        A[0] = s_ * ca; A[1] = s_ * -sa; A[3] = s_ * sa; A[4] = s_ * ca; A[8] = 1.0;
+        for (int i = 0; i < 9; ++i) sF[i] = A[i];
+        for (int d = 0; d < 3; ++d) { sF[9 + d] = t[d]; sF[12 + d] = 0.0; }
+      }
+    } else if (!rigid) {
       if (estimate_parameters) {
         for (int i = 0; i < 9; ++i) A[i] = theta[i];
         for (int d = 0; d < 3; ++d) t[d] = theta[9 + d];

@@ -164,6 +164,63 @@ def make_pair(seed: int, n_fixed: int, n_moving: int, size: float = 300.0, noise
     }
 
 
+def make_pair_2d(seed: int, n_fixed: int = 2000, n_moving: int = 2000, noise: float = 0.004, outliers: float = 0.10,
+                 gt_scale: float = 1.08, gt_ang_deg: float = 12.0, gt_trans=(0.15, -0.1), init_ang_deg: float = 4.0, init_trans: float = 0.04):
+    """BASELINE.json configs[0]: 2-D point sets with normals for cdcl_estimation_ICP<2,4> + cdcl_trans_similarity2d
+    (cdcl/examples/estimate.cxx method 4).  Points on an "H"-like set of strokes plus an arc, in the normalised units the
+    demo hands to the estimator (cdcl_normalize_data: centred, mean radius ~1).  Each feature carries the 2x2 location
+    covariance C = R diag(s_t^2, s_n^2) R^T (tangent spread >> normal spread), from which the estimator takes the normal.
+    Returns dict(fixed, moving: dict(xy(2,n), C3(3,n), strength(n)), gt=(s, ang, t), init=(A 3x3, t3))."""
+    rng = np.random.default_rng(seed)
+
+    def strokes(n, rng):
+        # five straight strokes of an "H" with a slanted bar, and one arc; arclength-uniform sampling
+        segs = [((-0.9, -1.2), (-0.9, 1.2)), ((0.9, -1.2), (0.9, 1.2)), ((-0.9, 0.1), (0.9, -0.2)), ((-1.4, 1.2), (-0.4, 1.2)), ((0.4, -1.2), (1.4, -1.2))]
+        lens = np.array([np.hypot(b[0] - a[0], b[1] - a[1]) for a, b in segs] + [np.pi * 0.6])
+        which = rng.choice(len(lens), size=n, p=lens / lens.sum())
+        u = rng.uniform(size=n)
+        xy = np.zeros((n, 2)); tan = np.zeros((n, 2))
+        for k, (a, b) in enumerate(segs):
+            m = which == k
+            a = np.array(a); b = np.array(b)
+            xy[m] = a + u[m, None] * (b - a); tan[m] = (b - a) / np.linalg.norm(b - a)
+        m = which == len(segs)
+        th = np.pi * u[m]
+        xy[m] = np.stack([0.6 * np.cos(th), 1.2 + 0.6 * np.sin(th) - 0.6], axis=1); tan[m] = np.stack([-np.sin(th), np.cos(th)], axis=1)
+        return xy, tan
+
+    def feats(xy, tan, rng):
+        n = len(xy)
+        st = rng.uniform(0.03, 0.08, size=n); sn = rng.uniform(0.004, 0.012, size=n)
+        nx, ny = -tan[:, 1], tan[:, 0]
+        cxx = st ** 2 * tan[:, 0] ** 2 + sn ** 2 * nx ** 2
+        cxy = st ** 2 * tan[:, 0] * tan[:, 1] + sn ** 2 * nx * ny
+        cyy = st ** 2 * tan[:, 1] ** 2 + sn ** 2 * ny ** 2
+        return {"xy": np.ascontiguousarray(xy.T), "C3": np.ascontiguousarray(np.stack([cxx, cxy, cyy])),
+                "strength": np.exp(rng.normal(0.0, 0.4, size=n))}
+
+    fxy, ftan = strokes(n_fixed, rng)
+    mxy, mtan = strokes(n_moving, rng)
+    fxy = fxy + rng.normal(scale=noise, size=fxy.shape)
+    mxy = mxy + rng.normal(scale=noise, size=mxy.shape)
+    ang = np.deg2rad(gt_ang_deg)
+    R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+    t = np.asarray(gt_trans, dtype=np.float64)
+    # moving coordinates: x = (s R)^-1 (y - t); tangents rotate with R^-1
+    mxy = (mxy - t) @ np.linalg.inv(gt_scale * R).T
+    mtan = mtan @ R          # (R^-1 v)^T = v^T R
+    n_out = int(round(outliers * n_moving))
+    if n_out:
+        oi = rng.choice(n_moving, size=n_out, replace=False)
+        mxy[oi] = rng.uniform(-1.6, 1.6, size=(n_out, 2))
+        a = rng.uniform(0, 2 * np.pi, size=n_out); mtan[oi] = np.stack([np.cos(a), np.sin(a)], axis=1)
+    a0 = ang + np.deg2rad(init_ang_deg) * (1 if seed % 2 == 0 else -1)
+    s0 = gt_scale * 0.97
+    A0 = np.eye(3); A0[:2, :2] = s0 * np.array([[np.cos(a0), -np.sin(a0)], [np.sin(a0), np.cos(a0)]])
+    t0 = np.array([t[0] + init_trans, t[1] - init_trans, 0.0])
+    return {"fixed": feats(fxy, ftan, rng), "moving": feats(mxy, mtan, rng), "gt": (gt_scale, ang, t), "init": (A0, t0)}
+
+
 def subset(feats: dict, idx) -> dict:
     idx = np.asarray(idx)
     return {k: (np.ascontiguousarray(v[..., idx]) if v is not None else None) for k, v in feats.items()}

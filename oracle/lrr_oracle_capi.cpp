@@ -17,6 +17,7 @@ struct lrro_fset {
   std::vector<Feature> base;   // pristine copies
   std::shared_ptr<KdTree> kd;
   bool has_cov = false, has_dirs = false;
+  int dim = 3;
 };
 struct lrro_est {
   lrro_ctx* ctx; int kind, dof; lrro_fset *moving_all, *fixed_all;
@@ -24,7 +25,8 @@ struct lrro_est {
   std::vector<int32_t> moving_inside_idx, fixed_inside_idx;
   std::shared_ptr<FwdEst> fwd; std::shared_ptr<SymEst> sym;
   int shuffle_mode = 0; uint64_t seed = 0;
-  int flavor() const { return (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM) ? FLAVOR_RRL : FLAVOR_CDCL; }
+  int flavor() const { return kind == LRR_CDCL_ICP ? FLAVOR_ICP : ((kind == LRR_RRL_FWD || kind == LRR_RRL_SYM) ? FLAVOR_RRL : FLAVOR_CDCL); }
+  int trans_kind() const { return dof == 12 ? TRANS_AFFINE : (dof == 6 ? TRANS_RIGID3D : TRANS_SIM2D); }
   bool is_sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
   FwdEst* dir(int d) { if (is_sym()) return d == 0 ? sym->forward_.get() : sym->backward_.get(); return d == 0 ? fwd.get() : nullptr; }
 };
@@ -74,6 +76,28 @@ int lrro_features_upload(lrro_ctx* ctx, int64_t n, const double* xyz, const doub
   fs->kd = std::make_shared<KdTree>(); fs->kd->build(pts);
   *out = fs; return LRR_OK;
 }
+// plain cdcl_feature<2> sets for cdcl_estimation_ICP<2,4>: the projector is the normal's outer product (cdcl_estimation_ICP.txx:470-477)
+int lrro_features_upload_cov(lrro_ctx* ctx, int dim, int64_t n, const double* loc, const double* cov, const double* strength, lrro_fset** out) {
+  if (!ctx || n < 0 || !loc || !cov || !out) return LRR_ERR_INVALID;
+  if (dim != 2) return LRR_ERR_UNSUPPORTED;
+  auto* fs = new lrro_fset(); fs->ctx = ctx; fs->base.resize(n); fs->has_cov = true; fs->dim = 2;
+  std::vector<double> pts(3 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    Feature& f = fs->base[i];
+    f.loc[0] = loc[i]; f.loc[1] = loc[n + i]; f.loc[2] = 0.0;
+    for (int d = 0; d < 3; ++d) pts[3 * i + d] = f.loc[d];
+    f.strength = strength ? strength[i] : 0.0; f.strength_f = (float)f.strength;
+    for (int k = 0; k < 9; ++k) { f.P[k] = 0.0; f.cov[k] = 0.0; }
+    f.cov[0] = cov[i]; f.cov[1] = f.cov[3] = cov[n + i]; f.cov[4] = cov[2 * n + i];
+    double P3[3]; projector2_from_cov(cov[i], cov[n + i], cov[2 * n + i], P3);
+    f.P[0] = P3[0]; f.P[1] = f.P[3] = P3[1]; f.P[4] = P3[2];
+    f.shape = CORNER; f.ndirs = 0;
+    for (int a = 0; a < 3; ++a) for (int d = 0; d < 3; ++d) f.dirs[a][d] = 0.0;
+    f.id = (int)i;
+  }
+  fs->kd = std::make_shared<KdTree>(); fs->kd->build(pts);
+  *out = fs; return LRR_OK;
+}
 void lrro_features_destroy(lrro_fset* fs) { delete fs; }
 int64_t lrro_features_size(const lrro_fset* fs) { return (int64_t)fs->base.size(); }
 int lrro_features_nearest(lrro_fset* fs, int64_t nq, const double* q, int32_t* idx) {
@@ -99,12 +123,15 @@ static void rebuild(lrro_est* e, TransP trans) {
 
 int lrro_est_create(lrro_ctx* ctx, int kind, int dim, int dof, lrro_fset* moving_all, lrro_fset* fixed_all, lrro_est** out) {
   if (!ctx || !moving_all || !fixed_all || !out) return LRR_ERR_INVALID;
-  if (dim != 3 || (dof != 12 && dof != 6)) return LRR_ERR_UNSUPPORTED;
-  if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;  // Q6
-  if (kind < 0 || kind > 3) return LRR_ERR_INVALID;
+  if (kind < 0 || kind > 4) return LRR_ERR_INVALID;
+  if (kind == LRR_CDCL_ICP) { if (dim != 2 || dof != 4 || moving_all->dim != 2 || fixed_all->dim != 2) return LRR_ERR_UNSUPPORTED; }
+  else {
+    if (dim != 3 || (dof != 12 && dof != 6) || moving_all->dim != 3 || fixed_all->dim != 3) return LRR_ERR_UNSUPPORTED;
+    if (dof == 6 && (kind == LRR_RRL_FWD || kind == LRR_RRL_SYM)) return LRR_ERR_UNSUPPORTED;  // Q6
+  }
   auto* e = new lrro_est(); e->ctx = ctx; e->kind = kind; e->dof = dof; e->moving_all = moving_all; e->fixed_all = fixed_all;
   e->moving_all_f = clone_set(moving_all->base); e->fixed_all_f = clone_set(fixed_all->base);
-  rebuild(e, std::make_shared<Trans>(dof == 12 ? TRANS_AFFINE : TRANS_RIGID3D));
+  rebuild(e, std::make_shared<Trans>(e->trans_kind()));
   *out = e; return LRR_OK;
 }
 void lrro_est_destroy(lrro_est* e) { delete e; }
@@ -121,10 +148,14 @@ int lrro_est_set_subsets(lrro_est* e, const int32_t* mi, int64_t nm, const int32
   return LRR_OK;
 }
 int lrro_est_set_transform(lrro_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
-  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12)) return LRR_ERR_INVALID;
-  auto t = std::make_shared<Trans>(tk == LRR_TRANS_AFFINE ? TRANS_AFFINE : TRANS_RIGID3D);
-  std::memcpy(t->A, A9, sizeof(double) * 9); std::memcpy(t->t, t3, sizeof(double) * 3);
-  if (c3) std::memcpy(t->c, c3, sizeof(double) * 3);
+  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
+  auto t = std::make_shared<Trans>(e->trans_kind());
+  if (tk == LRR_TRANS_SIMILARITY2D) {   // (A = s R, t) -> (s, ang, t): ctor #2 of cdcl_trans_similarity2d
+    t->sim2d_set(std::sqrt(A9[0] * A9[0] + A9[3] * A9[3]), std::atan2(A9[3], A9[0]), t3[0], t3[1]);
+  } else {
+    std::memcpy(t->A, A9, sizeof(double) * 9); std::memcpy(t->t, t3, sizeof(double) * 3);
+    if (c3) std::memcpy(t->c, c3, sizeof(double) * 3);
+  }
   if (cov) t->covar.assign(cov, cov + e->dof * e->dof);
   if (e->is_sym()) e->sym->set_transform(t); else e->fwd->set_transform(t);
   return LRR_OK;
@@ -141,7 +172,7 @@ int lrro_est_set_order(lrro_est* e, int d, const int32_t* perm, int64_t n) {
 int lrro_est_set_shuffle(lrro_est* e, int mode, uint64_t seed) { e->shuffle_mode = mode; e->seed = seed; apply_policy(e); return LRR_OK; }
 int lrro_est_set_initial_scale(lrro_est* e, int d, double s) { FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID; f->initial_scale = s; return LRR_OK; }
 int lrro_est_set_number_points(lrro_est* e, int d, int64_t m, int* at_max) {
-  FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
+  FwdEst* f = e->dir(d); if (!f || e->kind == LRR_CDCL_ICP) return LRR_ERR_INVALID;   // (cdcl_estimation_ICP has no point ramp)
   bool r = f->set_number_points((size_t)m); if (at_max) *at_max = r; return LRR_OK;
 }
 int lrro_est_find_closest(lrro_est* e) { if (e->is_sym()) e->sym->find_closest_euclidean(); else e->fwd->find_closest_euclidean(); return LRR_OK; }
@@ -156,7 +187,7 @@ int lrro_est_run(lrro_est* e, int max_iter, int* conv, int* iters) {
 int lrro_est_get_transform(lrro_est* e, int d, int* tk, double* A9, double* t3, double* c3, double* cov) {
   FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
   const Trans& t = *f->trans_;
-  if (tk) *tk = t.kind == TRANS_AFFINE ? LRR_TRANS_AFFINE : LRR_TRANS_RIGID3D;
+  if (tk) *tk = t.kind == TRANS_AFFINE ? LRR_TRANS_AFFINE : (t.kind == TRANS_RIGID3D ? LRR_TRANS_RIGID3D : LRR_TRANS_SIMILARITY2D);
   if (A9) std::memcpy(A9, t.A, 72); if (t3) std::memcpy(t3, t.t, 24); if (c3) std::memcpy(c3, t.c, 24);
   if (cov) std::memcpy(cov, t.covar.data(), sizeof(double) * t.covar.size());
   return LRR_OK;
@@ -324,6 +355,16 @@ void lrro_test_trans_inverse(int kind, double* A9, double* t3, double* c3) {
   std::memcpy(t.A, A9, 72); std::memcpy(t.t, t3, 24); std::memcpy(t.c, c3, 24);
   auto r = t.inverse();
   std::memcpy(A9, r->A, 72); std::memcpy(t3, r->t, 24); std::memcpy(c3, r->c, 24);
+}
+void lrro_test_projector2d(const double* C3, double* P3) { projector2_from_cov(C3[0], C3[1], C3[2], P3); }
+void lrro_test_sim2d_roundtrip(double* s, double* ang, double* t2, double* cov16, double rm, double rf, const double* cm2, const double* cf2, int do_un) {
+  Trans t(TRANS_SIM2D); t.sim2d_set(*s, *ang, t2[0], t2[1]);
+  if (cov16) t.covar.assign(cov16, cov16 + 16);
+  const double cm[3] = {cm2[0], cm2[1], 0}, cf[3] = {cf2[0], cf2[1], 0};
+  t.normalize(rm, rf, cm, cf);
+  if (do_un) t.unnormalize(rm, rf, cm, cf);
+  *s = t.s_; *ang = t.ang_; t2[0] = t.t[0]; t2[1] = t.t[1];
+  if (cov16) std::memcpy(cov16, t.covar.data(), 128);
 }
 void lrro_test_recompose(double* R9, double* t3, const double* dR9, const double* dt3) {
   Trans g(TRANS_RIGID3D), inc(TRANS_RIGID3D);

@@ -45,8 +45,10 @@
 namespace lrro {
 
 enum { CORNER = 0, TUBE = 1, SHEET = 2 };           // cdcl_feature_with_shape.h:32
-enum { TRANS_AFFINE = 0, TRANS_RIGID3D = 1 };
-enum { FLAVOR_CDCL = 0, FLAVOR_RRL = 1 };
+enum { TRANS_AFFINE = 0, TRANS_RIGID3D = 1, TRANS_SIM2D = 2 };
+// FLAVOR_ICP: cdcl_estimation_ICP<2,4> (cdcl/cdcl_estimation_ICP.txx), the 2-D demo estimator of BASELINE.json configs[0]: the
+// forward cdcl loop without the point ramp, scale constant 2.0 (:580), strength weights normalised by their sum (:607-637).
+enum { FLAVOR_CDCL = 0, FLAVOR_RRL = 1, FLAVOR_ICP = 2 };
 
 // ----------------------------------------------------------------------------------------------
 // A1: cdcl_feature_with_shape<3> / cdcl_feature_ICP<3>  (cdcl/cdcl_feature_with_shape.h:23-89,
@@ -228,7 +230,8 @@ struct KdTree {
 };
 
 // ----------------------------------------------------------------------------------------------
-// A2/A3/A9: cdcl_trans_affine<3,12> and cdcl_trans_rigid3d (<3,6>).
+// A2/A3/A9: cdcl_trans_affine<3,12>, cdcl_trans_rigid3d (<3,6>) and cdcl_trans_similarity2d (<2,4>, embedded in the x-y plane:
+// A = s_ * R_ in the upper-left 2x2 block, A22 = 1, centre 0).
 struct Trans {
   int kind = TRANS_AFFINE;
   int dof = 12;
@@ -238,8 +241,19 @@ struct Trans {
   std::vector<double> covar;                   // covar_ dof x dof
   double covarJ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double alpha = 0, beta = 0, gamma = 0;       // rigid only
+  double s_ = 1.0, ang_ = 0.0, R_[4] = {1, 0, 0, 1};   // similarity2d only (cdcl_trans_similarity2d.h: s_, ang_, R_)
 
-  explicit Trans(int k = TRANS_AFFINE) : kind(k), dof(k == TRANS_AFFINE ? 12 : 6), covar((size_t)dof * dof, 0.0) {}
+  explicit Trans(int k = TRANS_AFFINE) : kind(k), dof(k == TRANS_AFFINE ? 12 : (k == TRANS_RIGID3D ? 6 : 4)), covar((size_t)dof * dof, 0.0) {}
+  // similarity2d: A <- s_ * R_ (what map_loc multiplies with: `s_ * R_ * from + t_`, similarity2d.cxx:124-127)
+  void sim2d_sync() { A[0] = s_ * R_[0]; A[1] = s_ * R_[1]; A[3] = s_ * R_[2]; A[4] = s_ * R_[3]; A[2] = A[5] = A[6] = A[7] = 0.0; A[8] = 1.0; }
+  // similarity2d from (s, ang, t): ctor #2 (similarity2d.cxx:33-47)
+  void sim2d_set(double s, double ang, double t0, double t1) {
+    s_ = s; ang_ = ang;
+    const double sina = std::sin(ang_), cosa = std::cos(ang_);
+    R_[0] = cosa; R_[1] = -sina; R_[2] = sina; R_[3] = cosa;
+    t[0] = t0; t[1] = t1; t[2] = 0.0; c[0] = c[1] = c[2] = 0.0;
+    sim2d_sync();
+  }
   // create_new(): identity of the same kind, zero covariance, zero centre.
   std::shared_ptr<Trans> create_new() const { return std::make_shared<Trans>(kind); }
 
@@ -262,6 +276,10 @@ struct Trans {
       int p = 0;
       for (int d1 = 0; d1 < 3; ++d1) for (int d2 = 0; d2 < 3; ++d2) { J[d1 * dof + p] = lc[d2]; ++p; }
       for (int d = 0; d < 3; ++d, ++p) J[d * dof + p] = 1.0;
+    } else if (kind == TRANS_SIM2D) {   // similarity2d.cxx:150-164
+      J[0 * dof + 0] = x[0]; J[1 * dof + 0] = x[1];
+      J[0 * dof + 1] = -x[1]; J[1 * dof + 1] = x[0];
+      J[0 * dof + 2] = 1.0; J[1 * dof + 3] = 1.0;
     } else {
       J[1 * dof + 0] = -lc[2]; J[2 * dof + 0] = lc[1];
       J[0 * dof + 1] = lc[2];  J[2 * dof + 1] = -lc[0];
@@ -273,13 +291,21 @@ struct Trans {
   std::vector<double> get_parameterization() const {
     std::vector<double> p(dof, 0.0);
     if (kind == TRANS_AFFINE) { for (int i = 0; i < 9; ++i) p[i] = A[i]; for (int d = 0; d < 3; ++d) p[9 + d] = t[d]; }
+    else if (kind == TRANS_SIM2D) { p[0] = s_ * std::cos(ang_); p[1] = s_ * std::sin(ang_); p[2] = t[0]; p[3] = t[1]; }   // similarity2d.cxx:76-90
     else { p[0] = alpha; p[1] = beta; p[2] = gamma; for (int d = 0; d < 3; ++d) p[3 + d] = t[d]; }
     return p;
   }
   // set_parameterization (affine.txx:89-106; rigid3d.cxx:140-166: small-angle R, Q7).
   void set_parameterization(const double* p) {
     if (kind == TRANS_AFFINE) { for (int i = 0; i < 9; ++i) A[i] = p[i]; for (int d = 0; d < 3; ++d) t[d] = p[9 + d]; }
-    else {
+    else if (kind == TRANS_SIM2D) {   // similarity2d.cxx:93-110
+      s_ = std::sqrt(p[0] * p[0] + p[1] * p[1]);
+      const double cosa = p[0] / s_, sina = p[1] / s_;
+      ang_ = std::atan2(sina, cosa);
+      R_[0] = cosa; R_[1] = -sina; R_[2] = sina; R_[3] = cosa;
+      t[0] = p[2]; t[1] = p[3];
+      sim2d_sync();
+    } else {
       alpha = p[0]; beta = p[1]; gamma = p[2];
       double da = p[0], db = p[1], dg = p[2];
       A[0] = 1.0; A[1] = -dg; A[2] = db;
@@ -291,6 +317,14 @@ struct Trans {
   // inverse() (affine.txx:54-59, rigid3d.cxx:113-118): (invA, -invA*t + c, centre 0), fresh covariance (zeros).
   std::shared_ptr<Trans> inverse() const {
     auto r = std::make_shared<Trans>(kind);
+    if (kind == TRANS_SIM2D) {   // similarity2d.cxx:62-73: (1/s, angle of R^-1, -1/s * R^-1 * t)
+      double R3[9] = {R_[0], R_[1], 0, R_[2], R_[3], 0, 0, 0, 1}, iR[9];
+      svd_inverse(3, R3, iR);
+      const double k = -1.0 / s_;
+      const double u0 = (k * iR[0]) * t[0] + (k * iR[1]) * t[1], u1 = (k * iR[3]) * t[0] + (k * iR[4]) * t[1];
+      r->sim2d_set(1.0 / s_, std::atan2(iR[3], iR[0]), u0, u1);
+      return r;
+    }
     double invA[9]; svd_inverse(3, A, invA);
     for (int i = 0; i < 9; ++i) r->A[i] = invA[i];
     for (int i = 0; i < 3; ++i) {
@@ -311,6 +345,25 @@ struct Trans {
   }
   // normalize (affine.txx:220-253; rigid3d.cxx:260-281: no covariance update, centre NOT reset).
   void normalize(double rm, double rf, const double* cm, const double* cf) {
+    if (kind == TRANS_SIM2D) {   // similarity2d.cxx:227-268 (R_ is not touched; sR is rebuilt from cos / sin of ang_)
+      s_ = rm / rf * s_;
+      const double cosa = std::cos(ang_), sina = std::sin(ang_);
+      const double sR[4] = {s_ * cosa, -s_ * sina, s_ * sina, s_ * cosa};
+      for (int r = 0; r < 2; ++r) {
+        double acc = sR[2 * r] * cm[0]; acc += sR[2 * r + 1] * cm[1];
+        t[r] = t[r] / rf + acc / rm - cf[r] / rf;
+      }
+      std::vector<double> B(16, 0.0);
+      double temp = rm / rf;
+      B[0] = temp; B[5] = temp;
+      const double f0 = cm[0] / rf, f1 = cm[1] / rf;
+      B[2 * 4 + 0] = f0; B[2 * 4 + 1] = -f1; B[3 * 4 + 0] = f1; B[3 * 4 + 1] = f0;
+      temp = 1.0 / rf;
+      B[10] = temp; B[15] = temp;
+      covar = mat_BCBt(B, covar, 4);
+      sim2d_sync();
+      return;
+    }
     double s = rm / rf;
     for (int i = 0; i < 9; ++i) A[i] = s * A[i];
     double dc[3] = {cm[0] - c[0], cm[1] - c[1], cm[2] - c[2]};
@@ -333,6 +386,20 @@ struct Trans {
   }
   // unnormalize (affine.txx:259-286; rigid3d.cxx:285-305).
   void unnormalize(double rm, double rf, const double* cm, const double* cf) {
+    if (kind == TRANS_SIM2D) {   // similarity2d.cxx:271-305
+      s_ = rf / rm * s_;
+      const double cosa = std::cos(ang_), sina = std::sin(ang_);
+      const double sR[4] = {s_ * cosa, -s_ * sina, s_ * sina, s_ * cosa};
+      for (int r = 0; r < 2; ++r) {
+        double acc = (-sR[2 * r]) * cm[0]; acc += (-sR[2 * r + 1]) * cm[1];
+        t[r] = acc + rf * t[r] + cf[r];
+      }
+      std::vector<double> B(16, 0.0);
+      B[0] = B[5] = rf / rm; B[10] = B[15] = rf;
+      covar = mat_BCBt(B, covar, 4);
+      sim2d_sync();
+      return;
+    }
     double s = rf / rm;
     for (int i = 0; i < 9; ++i) A[i] = s * A[i];
     if (kind == TRANS_AFFINE) {
@@ -410,6 +477,7 @@ struct FwdEst {
          std::shared_ptr<const KdTree> prebuilt = nullptr)
       : flavor(flavor_), moving_base_(moving), moving_(moving), fixed_(fixed), trans_(trans), kd_(prebuilt) {
     if (!kd_) build_kd_trees();
+    if (flavor == FLAVOR_ICP) number_points_ = moving_.size();   // cdcl_estimation_ICP walks all of moving_[res_] (:449)
     if (number_points_ > moving_.size()) number_points_ = moving_.size();
   }
   // build_kd_trees (cdcl :113-135)
@@ -426,10 +494,10 @@ struct FwdEst {
   // set_transform (cdcl :141-153)
   void set_transform(TransP t) {
     trans_ = t; scale_estimated_ = false; number_points_ = 1000;
-    if (number_points_ > moving_.size()) number_points_ = moving_.size();
+    if (number_points_ > moving_.size() || flavor == FLAVOR_ICP) number_points_ = moving_.size();   // (ICP .h:70: no ramp)
   }
   // set_moving_data (cdcl .h:96)
-  void set_moving_data(const std::vector<FeatureP>& m) { matches_.clear(); moving_base_ = m; moving_ = m; }
+  void set_moving_data(const std::vector<FeatureP>& m) { matches_.clear(); moving_base_ = m; moving_ = m; if (flavor == FLAVOR_ICP) number_points_ = m.size(); }
   void set_order(const int32_t* perm, size_t n) {
     std::vector<FeatureP> m(n);
     for (size_t i = 0; i < n; ++i) m[i] = moving_base_[perm[i]];
@@ -443,7 +511,7 @@ struct FwdEst {
       double y[3]; trans_->map_loc(m.from->loc, y);
       double e[3] = {y[0] - m.to->loc[0], y[1] - m.to->loc[1], y[2] - m.to->loc[2]};
       error += proj_residual2(e, m.to->P);
-      if (flavor == FLAVOR_CDCL) count += 1;
+      if (flavor != FLAVOR_RRL) count += 1;
     }
     if (count != 0) error = std::sqrt(error / double(count));
     return error;
@@ -546,7 +614,7 @@ struct FwdEst {
 
   // find_closest_euclidean (cdcl :541-654; rrl :494-571 with the exact-NN branch, Q5)
   void find_closest_euclidean() {
-    if (shuffle_mode == 1) {   // vcl_random_shuffle( moving_[res_] )  :557
+    if (shuffle_mode == 1 && flavor != FLAVOR_ICP) {   // vcl_random_shuffle( moving_[res_] )  :557 (cdcl_estimation_ICP does not shuffle)
       FeistelPerm perm(shuffle_seed, shuffle_dir, shuffle_calls++, (uint32_t)moving_base_.size());
       for (size_t k = 0; k < moving_base_.size(); ++k) moving_[k] = moving_base_[perm((uint32_t)k)];
     }
@@ -580,12 +648,18 @@ struct FwdEst {
     } else {
       scale = std::sqrt(sum_weighted_error / sum_weights);
     }
-    const double constant = 1.0;
+    const double constant = flavor == FLAVOR_ICP ? 2.0 : 1.0;   // cdcl_estimation_ICP.txx:580
     scale = constant * scale;
+    double sum_grad_w = 0.0;
     for (auto& m : matches_) {
       double scale2 = scale * scale;
       m.w = weight_BT(m.w / scale2) / scale2;
+      if (flavor == FLAVOR_ICP && weight_by_strength_) {   // cdcl_estimation_ICP.txx:607-611
+        double grad_w = m.from->strength * m.to->strength;
+        m.w *= grad_w; sum_grad_w += grad_w;
+      }
     }
+    if (flavor == FLAVOR_ICP && weight_by_strength_) for (auto& m : matches_) m.w *= (1.0 / sum_grad_w);   // :629-637
     last_scale = scale;
     return scale;
   }
@@ -638,11 +712,11 @@ struct FwdEst {
     rf /= double(fixed_matched.size());
     for (auto& m : matches_) {
       for (int d = 0; d < 3; ++d) m.from->loc[d] /= rm;
-      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.from->cov[k] /= (rm * rm);
+      if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) m.from->cov[k] /= (rm * rm);
     }
     for (Feature* q : fixed_matched) {
       for (int d = 0; d < 3; ++d) q->loc[d] /= rf;
-      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) q->cov[k] /= (rf * rf);
+      if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) q->cov[k] /= (rf * rf);
     }
     for (int d = 0; d < 3; ++d) { last_norm[d] = cm[d]; last_norm[4 + d] = cf[d]; }
     last_norm[3] = rm; last_norm[7] = rf;
@@ -652,10 +726,10 @@ struct FwdEst {
     std::set<Feature*> fixed_matched;
     for (auto& m : matches_) {
       for (int d = 0; d < 3; ++d) { m.from->loc[d] *= rm; m.from->loc[d] += cm[d]; }
-      if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.from->cov[k] *= (rm * rm);
+      if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) m.from->cov[k] *= (rm * rm);
       if (fixed_matched.insert(m.to.get()).second) {
         for (int d = 0; d < 3; ++d) { m.to->loc[d] *= rf; m.to->loc[d] += cf[d]; }
-        if (flavor == FLAVOR_CDCL) for (int k = 0; k < 9; ++k) m.to->cov[k] *= (rf * rf);
+        if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) m.to->cov[k] *= (rf * rf);
       }
     }
   }
@@ -686,7 +760,7 @@ struct FwdEst {
     if (normalize_matches_) { normalize_matches_fn(cm, rm, cf, rf); trans_->normalize(rm, rf, cm, cf); }
     double scale = estimate_scale_and_assign_weight();
     if (scale < 0.005) scale = 0.005;
-    if (weight_by_strength_) weight_by_strength_fn();
+    if (weight_by_strength_ && flavor != FLAVOR_ICP) weight_by_strength_fn();
     const int dof = trans_->dof;
     std::vector<double> AtA((size_t)dof * dof, 0.0), Atb(dof, 0.0);
     for (auto& m : matches_) {

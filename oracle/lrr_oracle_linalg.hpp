@@ -106,6 +106,21 @@ inline void inv3(const double* m, double* o) {
 // Cyclic Jacobi eigen-decomposition of a symmetric 3x3; eigenvalues ascending, eigenvectors in
 // the COLUMNS of V (vnl_symmetric_eigensystem_compute convention used at
 // cdcl/cdcl_estimation_ICP_matching_all.txx:300-306: column 0 = smallest eigenvalue).
+// Error projector of a plain 2-D cdcl_feature: outer product of the eigenvector of the SMALLEST eigenvalue of its covariance
+// (the point normal; cdcl/cdcl_estimation_ICP.txx:470-477 via vnl_symmetric_eigensystem_compute).  Closed form for the symmetric
+// 2x2 case; P3 = (xx, xy, yy).  Isotropic covariances (no defined normal) give the x axis, like an identity eigenvector matrix.
+inline void projector2_from_cov(double a, double b, double c, double* P3) {
+  const double half = 0.5 * (a - c), rad = std::sqrt(half * half + b * b);
+  const double lam = 0.5 * (a + c) - rad;
+  double v0, v1;
+  if (a >= c) { v0 = b; v1 = lam - a; } else { v0 = lam - c; v1 = b; }
+  const double n2 = v0 * v0 + v1 * v1;
+  if (!(n2 > 0.0)) { P3[0] = 1.0; P3[1] = 0.0; P3[2] = 0.0; return; }
+  const double inv = 1.0 / std::sqrt(n2);
+  v0 *= inv; v1 *= inv;
+  P3[0] = v0 * v0; P3[1] = v0 * v1; P3[2] = v1 * v1;
+}
+
 inline void sym_eig3(const double* C, double* V, double* D) {
   double a[9];
   std::memcpy(a, C, sizeof(a));

@@ -6,7 +6,7 @@
 #include "lrr_ref_iface.hpp"
 
 struct lrrr_ctx { std::string err; };
-struct lrrr_fset { lrrr_ctx* ctx; std::vector<RefFeat> base; };
+struct lrrr_fset { lrrr_ctx* ctx; std::vector<RefFeat> base; int dim = 3; };
 struct lrrr_est { lrrr_ctx* ctx; int kind, dof; RefEst* impl; };
 
 extern "C" {
@@ -34,12 +34,31 @@ int lrrr_features_upload(lrrr_ctx* ctx, int64_t n, const double* xyz, const doub
   }
   *out = fs; return LRR_OK;
 }
+// plain cdcl_feature<2> sets (location, strength, 2x2 covariance) for cdcl_estimation_ICP<2,4>
+int lrrr_features_upload_cov(lrrr_ctx* ctx, int dim, int64_t n, const double* loc, const double* cov, const double* strength, lrrr_fset** out) {
+  if (!ctx || n < 0 || !loc || !cov || !out) return LRR_ERR_INVALID;
+  if (dim != 2) return LRR_ERR_UNSUPPORTED;
+  lrrr_fset* fs = new lrrr_fset(); fs->ctx = ctx; fs->dim = 2; fs->base.resize(n);
+  for (int64_t i = 0; i < n; ++i) {
+    RefFeat& f = fs->base[i];
+    std::memset(&f, 0, sizeof f);
+    f.loc[0] = loc[i]; f.loc[1] = loc[n + i];
+    f.cov[0] = cov[i]; f.cov[1] = f.cov[3] = cov[n + i]; f.cov[4] = cov[2 * n + i];
+    f.strength = strength ? strength[i] : 0.0;
+  }
+  *out = fs; return LRR_OK;
+}
 void lrrr_features_destroy(lrrr_fset* fs) { delete fs; }
 int64_t lrrr_features_size(const lrrr_fset* fs) { return (int64_t)fs->base.size(); }
 
 int lrrr_est_create(lrrr_ctx* ctx, int kind, int dim, int dof, lrrr_fset* moving_all, lrrr_fset* fixed_all, lrrr_est** out) {
   if (!ctx || !moving_all || !fixed_all || !out) return LRR_ERR_INVALID;
-  if (dim != 3) return LRR_ERR_UNSUPPORTED;
+  if (kind == LRR_CDCL_ICP) {
+    if (dim != 2 || dof != 4 || moving_all->dim != 2 || fixed_all->dim != 2) return LRR_ERR_UNSUPPORTED;
+    lrrr_est* e = new lrrr_est(); e->ctx = ctx; e->kind = kind; e->dof = dof; e->impl = lrr_ref_make_icp2d(moving_all->base, fixed_all->base);
+    *out = e; return LRR_OK;
+  }
+  if (dim != 3 || moving_all->dim != 3 || fixed_all->dim != 3) return LRR_ERR_UNSUPPORTED;
   RefEst* impl = (kind == LRR_CDCL_FWD || kind == LRR_CDCL_SYM) ? lrr_ref_make_cdcl(kind, dof, moving_all->base, fixed_all->base)
                                                                  : lrr_ref_make_rrl(kind, dof, moving_all->base, fixed_all->base);
   if (!impl) return LRR_ERR_UNSUPPORTED;
@@ -49,7 +68,7 @@ int lrrr_est_create(lrrr_ctx* ctx, int kind, int dim, int dof, lrrr_fset* moving
 void lrrr_est_destroy(lrrr_est* e) { if (e) { delete e->impl; delete e; } }
 int lrrr_est_set_subsets(lrrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) { e->impl->set_subsets(mi, nm, fi, nf); return LRR_OK; }
 int lrrr_est_set_transform(lrrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
-  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12)) return LRR_ERR_INVALID;
+  if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
   RefTrans t; t.kind = tk; std::memcpy(t.A, A9, 72); std::memcpy(t.t, t3, 24);
   if (c3) std::memcpy(t.c, c3, 24); else std::memset(t.c, 0, 24);
   if (cov) t.cov.assign(cov, cov + e->dof * e->dof);
@@ -92,5 +111,9 @@ void lrrr_test_trans_roundtrip(int kind, double* A9, double* t3, double* c3, dou
   lrr_ref_trans_roundtrip(kind, A9, t3, c3, cov, rm, rf, cm, cf, do_un);
 }
 void lrrr_test_trans_inverse(int kind, double* A9, double* t3, double* c3) { lrr_ref_trans_inverse(kind, A9, t3, c3); }
+void lrrr_test_projector2d(const double* C3, double* P3) { lrr_ref_projector2d(C3, P3); }
+void lrrr_test_sim2d_roundtrip(double* s, double* ang, double* t2, double* cov16, double rm, double rf, const double* cm2, const double* cf2, int do_un) {
+  lrr_ref_sim2d_roundtrip(s, ang, t2, cov16, rm, rf, cm2, cf2, do_un);
+}
 void lrrr_test_recompose(double* R9, double* t3, const double* dR9, const double* dt3) { lrr_ref_recompose(R9, t3, dR9, dt3); }
 }

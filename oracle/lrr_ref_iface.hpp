@@ -35,6 +35,9 @@ struct RefEst {
 
 RefEst* lrr_ref_make_cdcl(int kind, int dof, const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);
 RefEst* lrr_ref_make_rrl(int kind, int dof, const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);
+RefEst* lrr_ref_make_icp2d(const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);   // cdcl_estimation_ICP<2,4> (lrr_ref_icp2d.cpp)
+void lrr_ref_projector2d(const double* C3, double* P3);
+void lrr_ref_sim2d_roundtrip(double* s, double* ang, double* t2, double* cov16, double rm, double rf, const double* cm2, const double* cf2, int do_unnormalize);
 void lrr_ref_set_shuffle(int mode, unsigned long long seed);
 // small direct probes of reference functions (known-answer pins of the oracle's restatements)
 double lrr_ref_weight_BT(double u);

@@ -36,6 +36,16 @@ inline double rsdl_dist_sq(const rsdl_point& p, const rsdl_point& q) {
 }
 inline double rsdl_dist(const rsdl_point& p, const rsdl_point& q) { return std::sqrt(rsdl_dist_sq(p, q)); }
 
+// axis-aligned box (rsdl_bounding_box): only min/max points are used by the call sites (cdcl/cdcl_utils.txx:724,901)
+class rsdl_bounding_box {
+ public:
+  rsdl_bounding_box(const rsdl_point& mn, const rsdl_point& mx) : min_(mn), max_(mx) {}
+  const rsdl_point& min_point() const { return min_; }
+  const rsdl_point& max_point() const { return max_; }
+ private:
+  rsdl_point min_, max_;
+};
+
 class rsdl_kd_tree : public vbl_ref_count {
  public:
   rsdl_kd_tree(const std::vector<rsdl_point>& pts, double /*min_angle*/ = 0, int points_per_leaf = 8)
@@ -61,6 +71,15 @@ class rsdl_kd_tree : public vbl_ref_count {
     points.clear(); indices.clear();
     rsdl_point p(dim_, 0);
     for (unsigned i = 0; i < n_; ++i) { p.set_cartesian(&xyz_[(size_t)i * dim_]); if (rsdl_dist_sq(query, p) <= radius * radius) { points.push_back(p); indices.push_back((int)i); } }
+  }
+  void points_in_bounding_box(const rsdl_bounding_box& box, std::vector<rsdl_point>& points, std::vector<int>& indices) {
+    points.clear(); indices.clear();
+    rsdl_point p(dim_, 0);
+    for (unsigned i = 0; i < n_; ++i) {
+      bool in = true;
+      for (unsigned d = 0; d < dim_ && in; ++d) { const double v = xyz_[(size_t)i * dim_ + d]; in = v >= box.min_point().cartesian(d) && v <= box.max_point().cartesian(d); }
+      if (in) { p.set_cartesian(&xyz_[(size_t)i * dim_]); points.push_back(p); indices.push_back((int)i); }
+    }
   }
  private:
   struct Node { unsigned lo, hi; int left, right; unsigned axis; double split; };
