@@ -7,9 +7,12 @@
 // cdcl/cdcl_trans.h:21-148, cdcl/cdcl_trans_affine.h, cdcl/cdcl_trans_rigid3d.h, cdcl/cdcl_estimation_abs.h:20-65,
 // cdcl/cdcl_estimation_ICP_matching_all.h, cdcl/cdcl_estimation_symmetric_ICP_matching_all.h,
 // rrl/rrl_estimation_ICP_matching_all.h, rrl/rrl_estimation_symmetric_ICP_matching_all.h.
+// Config 1 (cdcl/examples/estimate.cxx -method 4): cdcl/cdcl_feature.h:17-64, cdcl/cdcl_trans_similarity2d.h,
+// cdcl/cdcl_estimation_ICP.h — the planar section at the end of this file.
 // No VXL: vnl fixed vectors/matrices become std::array, vbl_smart_ptr becomes std::shared_ptr.
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -242,5 +245,128 @@ template <unsigned int dim, unsigned int dof> using cdcl_estimation_ICP_matching
 template <unsigned int dim, unsigned int dof> using cdcl_estimation_symmetric_ICP_matching_all = estimation_impl<dim, dof, LRR_CDCL_SYM>;
 template <unsigned int dim, unsigned int dof> using rrl_estimation_ICP_matching_all = estimation_impl<dim, dof, LRR_RRL_FWD>;
 template <unsigned int dim, unsigned int dof> using rrl_estimation_symmetric_ICP_matching_all = estimation_impl<dim, dof, LRR_RRL_SYM>;
+
+// ---- planar demo estimator (BASELINE.json configs[0]) -----------------------------------------------------------
+typedef std::array<double, 2> vec2;
+typedef std::array<double, 4> mat2;   // row-major
+
+// cdcl_feature<2>: location, strength, covariance (cdcl/cdcl_feature.h:17-64); the normal is the eigenvector of the smallest
+// eigenvalue of covariance_ (cdcl_estimation_ICP.txx:470-477) and is derived on the device at upload
+struct cdcl_feature2 {
+  typedef std::shared_ptr<cdcl_feature2> sptr;
+  cdcl_feature2() {}
+  cdcl_feature2(vec2 const& location, double strength, mat2 const& covariance) : location_(location), strength_(strength), covariance_(covariance) {}
+  vec2 location_{}; double strength_ = 0.0; mat2 covariance_{};
+};
+
+// cdcl_trans_similarity2d (cdcl/cdcl_trans_similarity2d.{h,cxx}): y = s R(ang) x + t, parameters (s cos, s sin, tx, ty)
+class cdcl_trans_similarity2d {
+ public:
+  static const unsigned int dim = 2, dof = 4;
+  typedef std::shared_ptr<cdcl_trans_similarity2d> sptr;
+  cdcl_trans_similarity2d() { covar_.assign(16, 0.0); }
+  cdcl_trans_similarity2d(double s, double ang, vec2 const& t) : s_(s), ang_(ang), t_(t) { covar_.assign(16, 0.0); }
+  vec2 map_loc(vec2 const& x) const { const mat2 A = jacobian_wrt_loc(); return vec2{A[0] * x[0] + A[1] * x[1] + t_[0], A[2] * x[0] + A[3] * x[1] + t_[1]}; }
+  mat2 jacobian_wrt_loc() const { const double c = std::cos(ang_), s = std::sin(ang_); return mat2{s_ * c, -s_ * s, s_ * s, s_ * c}; }
+  std::vector<double> get_parameterization() const { return {s_ * std::cos(ang_), s_ * std::sin(ang_), t_[0], t_[1]}; }
+  void set_parameterization(std::vector<double> const& p) { s_ = std::sqrt(p[0] * p[0] + p[1] * p[1]); ang_ = std::atan2(p[1] / s_, p[0] / s_); t_ = {p[2], p[3]}; }
+  std::vector<double> const& get_covariance() const { return covar_; }   // 4 x 4 row-major
+  void set_covariance(std::vector<double> const& c) { covar_ = c; }
+  mat2 const& get_covarianceJ() const { return covarJ_; }
+  // normalize / unnormalize of the parameters (similarity2d.cxx:227-305); the covariance follows B C B^T with the same B
+  void normalize(double rm, double rf, vec2 const& cm, vec2 const& cf) {
+    s_ = rm / rf * s_;
+    const mat2 sR = jacobian_wrt_loc();
+    for (int r = 0; r < 2; ++r) t_[r] = t_[r] / rf + (sR[2 * r] * cm[0] + sR[2 * r + 1] * cm[1]) / rm - cf[r] / rf;
+    double B[16] = {0}; B[0] = B[5] = rm / rf; B[8] = cm[0] / rf; B[9] = -cm[1] / rf; B[12] = cm[1] / rf; B[13] = cm[0] / rf; B[10] = B[15] = 1.0 / rf;
+    congruence(B);
+  }
+  void unnormalize(double rm, double rf, vec2 const& cm, vec2 const& cf) {
+    s_ = rf / rm * s_;
+    const mat2 sR = jacobian_wrt_loc();
+    for (int r = 0; r < 2; ++r) t_[r] = -(sR[2 * r] * cm[0] + sR[2 * r + 1] * cm[1]) + rf * t_[r] + cf[r];
+    double B[16] = {0}; B[0] = B[5] = rf / rm; B[10] = B[15] = rf;
+    congruence(B);
+  }
+  void print(FILE* f = stdout) const { std::fprintf(f, "s: %.12g ang: %.12g t: %.12g, %.12g\n", s_, ang_, t_[0], t_[1]); }
+  double s_ = 1.0, ang_ = 0.0; vec2 t_{}; std::vector<double> covar_; mat2 covarJ_{};
+ private:
+  void congruence(const double* B) {
+    double T[16], R[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double v = 0; for (int k = 0; k < 4; ++k) v += B[4 * i + k] * covar_[4 * k + j]; T[4 * i + j] = v; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double v = 0; for (int k = 0; k < 4; ++k) v += T[4 * i + k] * B[4 * j + k]; R[4 * i + j] = v; }
+    covar_.assign(R, R + 16);
+  }
+};
+
+// cdcl_normalize_data (cdcl/cdcl_utils.txx): centre and mean radius of a feature vector; locations and covariances rescaled in place
+inline void cdcl_normalize_data(std::vector<cdcl_feature2::sptr>& f, vec2& center, double& avg_rad) {
+  center = {0, 0}; avg_rad = 0;
+  for (auto& p : f) { center[0] += p->location_[0]; center[1] += p->location_[1]; }
+  center[0] /= (double)f.size(); center[1] /= (double)f.size();
+  for (auto& p : f) { p->location_[0] -= center[0]; p->location_[1] -= center[1]; avg_rad += std::sqrt(p->location_[0] * p->location_[0] + p->location_[1] * p->location_[1]); }
+  avg_rad /= (double)f.size();
+  for (auto& p : f) { for (int d = 0; d < 2; ++d) p->location_[d] /= avg_rad; for (int k = 0; k < 4; ++k) p->covariance_[k] /= avg_rad * avg_rad; }
+}
+
+// cdcl_estimation_ICP<2,4> (cdcl/cdcl_estimation_ICP.{h,txx}): ctor #1, run / one_iteration, the setters of the header
+template <unsigned int dim, unsigned int dof>
+class cdcl_estimation_ICP {
+ public:
+  static_assert(dim == 2 && dof == 4, "the device path of this estimator is built for <2,4> (cdcl/Templates/cdcl_estimation_ICP+2.4-.cxx)");
+  typedef cdcl_feature2 feature_type;
+  typedef feature_type::sptr feature_sptr_type;
+  typedef cdcl_trans_similarity2d::sptr trans_sptr_type;
+  typedef std::shared_ptr<cdcl_estimation_ICP> sptr;
+  cdcl_estimation_ICP(device_context& ctx, std::vector<feature_sptr_type> const& moving, std::vector<feature_sptr_type> const& fixed, trans_sptr_type const& trans) : ctx_(ctx) {
+    moving_ = upload(moving); fixed_ = upload(fixed);
+    ctx_.check(lrr_est_create(ctx_.get(), LRR_CDCL_ICP, 2, 4, moving_, fixed_, &est_), "lrr_est_create");
+    set_transform(trans);
+  }
+  ~cdcl_estimation_ICP() { if (est_) lrr_est_destroy(est_); if (moving_) lrr_features_destroy(moving_); if (fixed_) lrr_features_destroy(fixed_); }
+  cdcl_estimation_ICP(cdcl_estimation_ICP const&) = delete;
+  void initialize() {}
+  bool run(void* = 0, void* = 0) {   // cdcl_estimation_ICP.txx:330-346
+    bool converged = false; unsigned int iteration = 0;
+    while (!converged && iteration < 30) { converged = one_iteration(0, 0, iteration); ++iteration; }
+    return converged;
+  }
+  bool one_iteration(void*, void*, unsigned int iteration) { int c = 0; ctx_.check(lrr_est_one_iteration(est_, iteration, &c), "lrr_est_one_iteration"); return c != 0; }
+  void set_transform(trans_sptr_type const& trans) {
+    const mat2 A = trans->jacobian_wrt_loc();
+    const double A9[9] = {A[0], A[1], 0, A[2], A[3], 0, 0, 0, 1}, t3[3] = {trans->t_[0], trans->t_[1], 0};
+    ctx_.check(lrr_est_set_transform(est_, LRR_TRANS_SIMILARITY2D, A9, t3, nullptr, trans->get_covariance().data()), "lrr_est_set_transform");
+  }
+  trans_sptr_type get_transform() {
+    double A9[9], t3[3], c3[3]; int kind = 0; std::vector<double> cov(16);
+    ctx_.check(lrr_est_get_transform(est_, 0, &kind, A9, t3, c3, cov.data()), "lrr_est_get_transform");
+    trans_sptr_type t(new cdcl_trans_similarity2d(std::sqrt(A9[0] * A9[0] + A9[3] * A9[3]), std::atan2(A9[3], A9[0]), vec2{t3[0], t3[1]}));
+    t->set_covariance(cov);
+    return t;
+  }
+  void normalize_matches() { normalize_ = true; ctx_.check(lrr_est_set_flags(est_, normalize_, strength_), "lrr_est_set_flags"); }
+  void weight_by_strength(bool w) { strength_ = w; ctx_.check(lrr_est_set_flags(est_, normalize_, strength_), "lrr_est_set_flags"); }
+  double RMS_error() { return metric(LRR_METRIC_RMS); }
+  double weighted_error() { return metric(LRR_METRIC_WEIGHTED); }
+  double median_error() { return metric(LRR_METRIC_MEDIAN); }
+  mat2 compute_transfer_error_covariance() { double S[9]; ctx_.check(lrr_est_transfer_cov(est_, 0, S), "lrr_est_transfer_cov"); return mat2{S[0], S[1], S[3], S[4]}; }
+ private:
+  lrr_fset* upload(std::vector<feature_sptr_type> const& f) {
+    const size_t n = f.size();
+    std::vector<double> loc(2 * n), cov(3 * n), s(n);
+    for (size_t i = 0; i < n; ++i) {
+      loc[i] = f[i]->location_[0]; loc[n + i] = f[i]->location_[1];
+      cov[i] = f[i]->covariance_[0]; cov[n + i] = f[i]->covariance_[1]; cov[2 * n + i] = f[i]->covariance_[3];
+      s[i] = f[i]->strength_;
+    }
+    lrr_fset* fs = nullptr;
+    ctx_.check(lrr_features_upload_cov(ctx_.get(), 2, (int64_t)n, loc.data(), cov.data(), s.data(), &fs), "lrr_features_upload_cov");
+    return fs;
+  }
+  double metric(int which) { double v = 0; ctx_.check(lrr_est_metric(est_, which, 0, &v), "lrr_est_metric"); return v; }
+  device_context& ctx_;
+  lrr_fset *moving_ = nullptr, *fixed_ = nullptr; lrr_est* est_ = nullptr;
+  bool normalize_ = false, strength_ = false;
+};
 
 }  // namespace lrr_b200

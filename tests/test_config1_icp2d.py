@@ -185,3 +185,15 @@ def test_gpu_argument_checks_config1(gpu_lib):
     idx = fx.nearest(q)
     d = ((pair["fixed"]["xy"][:, :, None] - q[:2, None, :]) ** 2).sum(0)
     assert np.array_equal(idx, d.argmin(0))
+
+
+@pytest.mark.gpu
+def test_cpp_host_api_config1():
+    """include/lrr/lrr_estimators.h: cdcl_estimation_ICP<2,4> / cdcl_trans_similarity2d / cdcl_normalize_data under the reference's
+    names drive the C ABI the way cdcl/examples/estimate.cxx register_points() does (lrr_b200/host_cpp/demo_estimate2d.cpp)."""
+    import subprocess
+    exe = os.path.join(ROOT, "lrr_b200", "host_cpp", "demo_estimate2d")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
