@@ -227,6 +227,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
   CK(dmalloc(&d.hq_k, 3 * cap + 1)); d.hq_s = d.hq_k + cap; d.hq_o = d.hq_k + 2 * cap; d.hq_count = d.hq_k + 3 * cap;
   CK(dmalloc(&d.prev_s, cap)); CK(dmalloc(&d.proc, cap)); CK(dmalloc(&d.proc_mark, 2 * cap));
   CK(dmalloc(&d.hq_best, cap)); CK(cudaMemsetAsync(d.hq_count, 0, sizeof(int), ctx->stream));
+  CK(dmalloc(&d.proof, cap ? cap : 1));
   {  // tiles of the from-features: cubes of LRR_TILE_T cells of the to-grid over the bounding box of the parent set
     const GridDev& gf = from_all->dev.grid; const GridDev& gt = to_all->dev.grid;
     double edge = LRR_TILE_T * gt.h;
@@ -242,14 +243,15 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
     CK(dmalloc(&d.tile_cnt, (size_t)d.ntiles)); CK(dmalloc(&d.tile_start, (size_t)d.ntiles + 1)); CK(dmalloc(&d.chunk_start, (size_t)d.ntiles + 1));
     CK(dmalloc(&d.tile_of, cap ? cap : 1));
     CK(dmalloc(&d.chunk_tab, cap / 32 + (size_t)d.ntiles + 1));   // every tile adds at most one partly filled chunk
+    CK(dmalloc(&d.todo, cap / 32 + (size_t)d.ntiles + 1)); CK(dmalloc(&d.todo_count, 1)); CK(cudaMemsetAsync(d.todo_count, 0, sizeof(int), ctx->stream));
   }
   d.epoch = 0; d.has_order = false; d.matches = 0; d.weights_fresh = false;
   d.initial_scale = std::numeric_limits<double>::quiet_NaN();
   return LRR_OK;
 }
 static void dir_free(lrr_dir& d) {
-  dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark);
-  dfree(d.tile_cnt); dfree(d.tile_start); dfree(d.chunk_start); dfree(d.tile_of); dfree(d.chunk_tab);
+  dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark); dfree(d.proof);
+  dfree(d.tile_cnt); dfree(d.tile_start); dfree(d.chunk_start); dfree(d.tile_of); dfree(d.chunk_tab); dfree(d.todo); dfree(d.todo_count);
 }
 static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
   if (n < 0 || (size_t)n > d.cap) return LRR_ERR_INVALID;
@@ -267,6 +269,7 @@ static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t 
   }
   d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false;
   CK(cudaMemsetAsync(d.prev_s, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));   // no search candidates yet
+  CK(cudaMemsetAsync(d.proof, 0, sizeof(double4) * (size_t)(n ? n : 1), st));   // ... and no neighbour certificates
   // processing order of the match phase = tile order (spatially coherent; the finest level stages each tile's cells in shared memory)
   lrr_k_build_tiles(d.fx, d.fy, d.fz, (int)n, d.tgeom, d.tile_cnt, d.tile_start, d.chunk_start, d.tile_of, d.proc_mark, d.chunk_tab, d.proc, st, &ctx->launches);
   return LRR_OK;
@@ -284,6 +287,8 @@ static DirArgs dir_args(const lrr_dir& d) {
   a.to = d.to_all->dev; a.from_all = d.from_all->dev;
   a.sidx = d.sidx; a.w = d.w; a.r2 = d.r2; a.gkey = d.gkey; a.skey = d.skey;
   a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
+  static const bool no_proof = getenv("LRR_NO_PROOF") != nullptr;   // A/B switch for measurements
+  a.proof = no_proof ? nullptr : d.proof; a.todo = no_proof ? nullptr : d.todo; a.todo_count = d.todo_count;
   a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.chunk_tab = (a.proc && d.n_in > 0) ? d.chunk_tab : nullptr; a.nchunks = d.chunk_start; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
   return a;

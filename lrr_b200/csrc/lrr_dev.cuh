@@ -280,6 +280,92 @@ __device__ __forceinline__ int lrr_nn_pass_b(const GridDev& g, double qx, double
   return best_s;
 }
 
+// pass B with a NEIGHBOUR CERTIFICATE (DirArgs::proof): the same exact search over the ball inflated by `margin`, which also
+// yields the smallest distance of any OTHER point inside it.  Every point within (final distance + margin) of the query is
+// examined (each lane prunes with its own current best >= the final one), so afterwards
+//     bound = min( second smallest distance, final distance + margin )
+// is a lower bound on the distance from the query to every feature but the winner.  `*bound_out` <= 0: no certificate (tie).
+__device__ __forceinline__ void lrr_nn_upd2(const double4& p, int j, double qx, double qy, double qz, double& best, int& best_s, int& best_o, double& second) {
+  if (j == best_s) return;   // the incoming candidate is scanned again by the lane that owns its row
+  const double d = lrr_dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+  const int o = lrr_pos4_orig(p);
+  if (d < best || (d == best && o < best_o)) { second = best; best = d; best_s = j; best_o = o; }
+  else second = fmin(second, d);
+}
+// one thread, candidate known (st.best_s >= 0): the inflated ball as in lrr_nn_pass_b_cert.  Returns false when the ball touches too
+// many rows for one thread (the caller queues the query for pass B).
+__device__ __forceinline__ bool lrr_nn_ball_thread_cert(const GridDev& g, double qx, double qy, double qz, NNState& st, double margin, double* bound_out) {
+  *bound_out = 0.0;
+  const double slack = 1e-9 * g.h;
+  const double R = sqrt(st.best) * (1.0 + 1e-9) + slack + margin;
+  const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
+  const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
+  if ((z1 - z0 + 1) * (y1 - y0 + 1) > LRR_BALL_ROWS) return false;
+  double second = 1e300;
+  for (int z = z0; z <= z1; ++z) {
+    const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dz2 = dz * dz;
+    for (int y = y0; y <= y1; ++y) {
+      const double dy = lrr_slab_dist(qy, g.oy, g.h, y, slack);
+      const double dyz2 = dz2 + dy * dy;
+      const double Rm = sqrt(st.best) * (1.0 + 1e-9) + slack + margin;
+      if (dyz2 > Rm * Rm) continue;
+      const double rx = sqrt(Rm * Rm - dyz2) * (1.0 + 1e-9) + slack;
+      const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
+      const int row = (z * g.ny + y) * g.nx;
+      const int lo = __ldg(g.cell_start + row + xa), hi = __ldg(g.cell_start + row + xb + 1);
+      int j = lo;
+      for (; j + 2 <= hi; j += 2) {
+        const double4 p0 = lrr_ld_pos4(g.pos4 + j), p1 = lrr_ld_pos4(g.pos4 + j + 1);
+        lrr_nn_upd2(p0, j, qx, qy, qz, st.best, st.best_s, st.best_o, second); lrr_nn_upd2(p1, j + 1, qx, qy, qz, st.best, st.best_s, st.best_o, second);
+      }
+      if (j < hi) { const double4 p0 = lrr_ld_pos4(g.pos4 + j); lrr_nn_upd2(p0, j, qx, qy, qz, st.best, st.best_s, st.best_o, second); }
+    }
+  }
+  const double bound = fmin(sqrt(second), sqrt(st.best) + margin) * (1.0 - 1e-9) - slack;
+  *bound_out = (second > st.best && bound > 0.0) ? bound : 0.0;
+  return true;
+}
+__device__ __forceinline__ int lrr_nn_pass_b_cert(const GridDev& g, double qx, double qy, double qz, NNState st, double margin, double* bound_out) {
+  *bound_out = 0.0;
+  if (g.n <= 0) return -1;
+  if (st.best_s < 0) return lrr_nn_pass_b(g, qx, qy, qz, st);   // no candidate yet: plain search, certificate next time
+  const int lane = threadIdx.x & 31;
+  const double slack = 1e-9 * g.h;
+  double best = st.best; int best_s = st.best_s, best_o = st.best_o; double second = 1e300;
+  const double R = sqrt(best) * (1.0 + 1e-9) + slack + margin;
+  const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
+  const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
+  const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+  for (int t = lane; t < nrows; t += 32) {
+    const int z = z0 + t / ny, y = y0 + t % ny;
+    const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dy = lrr_slab_dist(qy, g.oy, g.h, y, slack);
+    const double dyz2 = dz * dz + dy * dy;
+    const double Rm = sqrt(best) * (1.0 + 1e-9) + slack + margin;   // inflated radius at this lane's current best
+    if (dyz2 > Rm * Rm) continue;
+    const double rx = sqrt(Rm * Rm - dyz2) * (1.0 + 1e-9) + slack;
+    const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
+    const int row = (z * g.ny + y) * g.nx;
+    const int lo = __ldg(g.cell_start + row + xa), hi = __ldg(g.cell_start + row + xb + 1);
+    int j = lo;
+    for (; j + 4 <= hi; j += 4) {
+      const double4 p0 = lrr_ld_pos4(g.pos4 + j), p1 = lrr_ld_pos4(g.pos4 + j + 1), p2 = lrr_ld_pos4(g.pos4 + j + 2), p3 = lrr_ld_pos4(g.pos4 + j + 3);
+      lrr_nn_upd2(p0, j, qx, qy, qz, best, best_s, best_o, second); lrr_nn_upd2(p1, j + 1, qx, qy, qz, best, best_s, best_o, second);
+      lrr_nn_upd2(p2, j + 2, qx, qy, qz, best, best_s, best_o, second); lrr_nn_upd2(p3, j + 3, qx, qy, qz, best, best_s, best_o, second);
+    }
+    for (; j < hi; ++j) { const double4 p0 = lrr_ld_pos4(g.pos4 + j); lrr_nn_upd2(p0, j, qx, qy, qz, best, best_s, best_o, second); }
+  }
+  double gb = best; int gs = best_s, go = best_o;
+  lrr_warp_min(gb, gs, go);
+  // lanes whose winner is the global one contribute their second; the others' best is a different point (or the shared incoming
+  // candidate, which then lost and is a different point as well)
+  double sec = (best_s == gs) ? second : best;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sec = fmin(sec, __shfl_xor_sync(0xffffffffu, sec, o));
+  const double bound = fmin(sqrt(sec), sqrt(gb) + margin) * (1.0 - 1e-9) - slack;
+  *bound_out = (sec > gb && bound > 0.0) ? bound : 0.0;
+  return gs;
+}
+
 // ---- reduction scopes ------------------------------------------------------------------------------
 // A phase body is written once against a Scope: `first()/stride()` drive the element loop, `reduce<K>`
 // sums K doubles per thread over the scope.  It returns true in every thread of the FINALIZER block with

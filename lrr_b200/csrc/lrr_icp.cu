@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
   static const bool no_tile = getenv("LRR_NO_TILE") != nullptr;   // A/B switch for measurements
-  if (!no_tile && lrr_match_tile_usable(a)) lrr_k_match_tile(a, st, launches);   // finest level: shared-memory-staged cells (lrr_tile.cu)
+  if (!no_tile && lrr_match_tile_usable(a)) {   // finest level (lrr_tile.cu): neighbour certificates, then shared-memory-staged cells for the rest
+    if (lrr_match_cert_usable(a)) lrr_k_match_cert(a, st, launches);
+    lrr_k_match_tile(a, st, launches);
+  }
   else {
     dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
     k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;

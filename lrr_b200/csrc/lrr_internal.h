@@ -119,6 +119,13 @@ struct DirArgs {
   // queue of the queries the 27-cell pass could not finish (pass B, one warp per query)
   int* hq_k; double* hq_best; int* hq_s; int* hq_o; int* hq_count;
   int* prev_s;                 // n_in: neighbour slot of each from-feature in its last match (-1: none) = search candidate
+  // n_in or null: NEIGHBOUR CERTIFICATE of each from-feature = {mapped position y0 at which prev_s was proven to be the unique
+  // nearest neighbour, lower bound B on the distance from y0 to every OTHER to-feature} (w <= 0: none).  For a new mapped position
+  // y the neighbour is unchanged, without any search, when |y - q_prev| + |y - y0| < B (triangle inequality; lrr_tile.cu).
+  double4* proof;
+  // work list of the staged search when certificates are in use: (chunk, lane mask of the queries the certificate pass could not
+  // keep), appended by k_match_cert, drained and re-armed by k_match_tile
+  int2* todo; int* todo_count;
   Scal* sc;
 };
 
@@ -174,6 +181,8 @@ void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int
                        int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches);
 bool lrr_match_tile_usable(const EstArgs& a);
 void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches);
+bool lrr_match_cert_usable(const EstArgs& a);
+void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_tile_set_timeline(unsigned long long* p);
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);

@@ -58,10 +58,16 @@ __device__ __forceinline__ void lrr_ld_P6(const double* __restrict__ rec, int s,
 // ---- MATCH: find_closest_euclidean (cdcl :541-654, rrl :494-571) fused with the residuals of
 // RMS_error (cdcl :196-230) and the first normalisation sum (cdcl :1159-1190) ---------------------------
 // residual, stamp and sums of one finished match
+// pmode: what happens to the neighbour certificate of from-feature i (DirArgs::proof): 0 = none comes with this match (any old one
+// is void), 1 = the match was accepted BY the certificate (it stays as it is), 2 = new certificate (bound) at this mapped position
 __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, int k, int i, double x, double y, double z, double yx,
-                                                 double yy, double yz, int s, double (&acc)[4]) {
+                                                 double yy, double yz, int s, double (&acc)[4], int pmode = 0, double bound = 0.0) {
   a.sidx[k] = s;
   a.prev_s[i] = s;   // candidate of this from-feature for the next find_closest
+  if (a.proof) {
+    if (pmode == 2) { double2* pr = reinterpret_cast<double2*>(a.proof + i); pr[0] = make_double2(yx, yy); pr[1] = make_double2(yz, bound); }
+    else if (pmode == 0) reinterpret_cast<double*>(a.proof + i)[3] = 0.0;
+  }
   double r2 = 0.0;
   if (s >= 0) {
     const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
@@ -95,16 +101,18 @@ __device__ __forceinline__ void lrr_match_a_one(const DirArgs& a, int flags, con
   lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
   NNState st; st.best = 1e300; st.best_s = a.prev_s[i]; st.best_o = 0x7fffffff;
   bool done = false;
+  double bound = 0.0;
+  const bool cert = a.proof && a.todo && a.M == a.n_in && proc;   // certificates are read at the finest level in tile order only
   if (st.best_s >= 0) {
     const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
     st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
-    done = lrr_nn_ball_thread(g, yx, yy, yz, st);
+    done = cert ? lrr_nn_ball_thread_cert(g, yx, yy, yz, st, 0.125 * g.h, &bound) : lrr_nn_ball_thread(g, yx, yy, yz, st);
   } else if (g.n > 0) {
     const int r27 = lrr_nn_block27_thread(g, yx, yy, yz, st);
     if (r27 == 1) done = true;
     else if (r27 == 0) done = lrr_nn_ball_thread(g, yx, yy, yz, st);   // rescans the block's rows inside the ball: still exact
   }
-  if (done) lrr_match_finish(a, rigid, k, i, x, y, z, yx, yy, yz, st.best_s, acc);
+  if (done) lrr_match_finish(a, rigid, k, i, x, y, z, yx, yy, yz, st.best_s, acc, (bound > 0.0 && i == k) ? 2 : 0, bound);
   else {
     const int slot = atomicAdd(a.hq_count, 1);
     a.hq_k[slot] = k; a.hq_best[slot] = st.best; a.hq_s[slot] = st.best_s; a.hq_o[slot] = st.best_o;
@@ -144,8 +152,12 @@ __device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, con
   double yx, yy, yz;
   lrr_map_exact(A, t, c, x, y, z, yx, yy, yz);
   NNState st; st.best = a.hq_best[qi]; st.best_s = a.hq_s[qi]; st.best_o = a.hq_o[qi];
-  const int s = lrr_nn_pass_b(a.to.grid, yx, yy, yz, st);
-  if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc);
+  int s; double bound = 0.0;
+  // (certificates only where they are read: finest level in tile order; margin = an eighth of a cell, far above the per-iteration
+  //  motion near convergence and ~1.4x the ball volume at worst)
+  if (a.proof && a.todo && a.M == a.n_in) s = lrr_nn_pass_b_cert(a.to.grid, yx, yy, yz, st, 0.125 * a.to.grid.h, &bound);
+  else s = lrr_nn_pass_b(a.to.grid, yx, yy, yz, st);
+  if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc, (bound > 0.0 && i == kq) ? 2 : 0, bound);
 }
 __device__ __forceinline__ void lrr_match_b_body_dynamic(const DirArgs& a, int flags, const double* s_T, unsigned int* counter, double (&acc)[4]) {
   const int lane = threadIdx.x & 31;

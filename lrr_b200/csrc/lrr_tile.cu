@@ -33,6 +33,8 @@ struct TileBox { int rx0, rx1, ry0, ry1, rz0, rz1, RY; };
 __device__ __forceinline__ GridScope lrr_scope_of(const EstArgs& a, int dir) {
   GridScope s; s.partials = a.partials + (size_t)dir * LRR_MAX_BLOCKS * LRR_NRED; s.ticket = a.ticket + dir; return s;
 }
+// true when this direction's matches go through the certificate pass first (finest level, tile order, certificates allocated)
+__device__ __forceinline__ bool lrr_dir_certified(const DirArgs& d) { return d.proof && d.todo && d.chunk_tab && d.proc && d.M == d.n_in; }
 void lrr_tile_set_timeline(unsigned long long* p) { cudaMemcpyToSymbol(g_lrr_tl, &p, sizeof(p)); }
 
 // ---- tile construction (once per set_features) --------------------------------------------------------------
@@ -155,14 +157,19 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
   const int nchunks = __ldg(a.nchunks);
   const double slack = 1e-9 * g.h;
   unsigned long long* dbg = g_lrr_tl ? g_lrr_tl + 3 * 2048 * 4 : nullptr;   // development counters (scripts/timeline.py)
+  // work list: every chunk of the direction, or — certificates in use — the (chunk, lane mask) entries k_match_cert left over
+  const bool use_todo = a.todo != nullptr && a.proof != nullptr;
+  const int nwork = use_todo ? *reinterpret_cast<volatile int*>(a.todo_count) : nchunks;
   for (;;) {
-    unsigned int ch = 0;
-    if (lane == 0) ch = atomicAdd(counter, 1u);
-    ch = __shfl_sync(full, ch, 0);
-    if ((int)ch >= nchunks) break;
+    unsigned int wi = 0;
+    if (lane == 0) wi = atomicAdd(counter, 1u);
+    wi = __shfl_sync(full, wi, 0);
+    if ((int)wi >= nwork) break;
+    int ch = (int)wi; unsigned int lanes = full;
+    if (use_todo) { const int2 e = __ldcg(a.todo + wi); ch = e.x; lanes = (unsigned int)e.y; }
     const int2 qq = __ldg(a.chunk_tab + ch);
     const int tq = qq.x + lane;
-    const bool valid = tq < qq.y;
+    const bool valid = tq < qq.y && ((lanes >> lane) & 1u);
     int k = 0; double x = 0, y = 0, z = 0, yx = 0, yy = 0, yz = 0;
     int cx = 0, cy = 0, cz = 0;
     if (valid) {
@@ -233,7 +240,8 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
     }
     __syncwarp();
     // uniform scan: every lane, every staged point
-    double best = 1e300; int bi = -1; bool tie = false;
+    // (second = smallest squared distance of any staged point other than the winner, for the certificate)
+    double best = 1e300, second = 1e300; int bi = -1; bool tie = false;
     {
       int p = 0;
       for (; p + 4 <= total; p += 4) {
@@ -241,14 +249,14 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
         const double d1 = lrr_dist2_exact(yx, yy, yz, W.px[p + 1], W.py[p + 1], W.pz[p + 1]);
         const double d2 = lrr_dist2_exact(yx, yy, yz, W.px[p + 2], W.py[p + 2], W.pz[p + 2]);
         const double d3 = lrr_dist2_exact(yx, yy, yz, W.px[p + 3], W.py[p + 3], W.pz[p + 3]);
-        if (d0 <= best) { tie = (d0 == best); best = d0; bi = p; }
-        if (d1 <= best) { tie = (d1 == best); best = d1; bi = p + 1; }
-        if (d2 <= best) { tie = (d2 == best); best = d2; bi = p + 2; }
-        if (d3 <= best) { tie = (d3 == best); best = d3; bi = p + 3; }
+        if (d0 <= best) { tie = (d0 == best); second = best; best = d0; bi = p; } else second = fmin(second, d0);
+        if (d1 <= best) { tie = (d1 == best); second = best; best = d1; bi = p + 1; } else second = fmin(second, d1);
+        if (d2 <= best) { tie = (d2 == best); second = best; best = d2; bi = p + 2; } else second = fmin(second, d2);
+        if (d3 <= best) { tie = (d3 == best); second = best; best = d3; bi = p + 3; } else second = fmin(second, d3);
       }
       for (; p < total; ++p) {
         const double d0 = lrr_dist2_exact(yx, yy, yz, W.px[p], W.py[p], W.pz[p]);
-        if (d0 <= best) { tie = (d0 == best); best = d0; bi = p; }
+        if (d0 <= best) { tie = (d0 == best); second = best; best = d0; bi = p; } else second = fmin(second, d0);
       }
     }
     // (tie is true iff the final minimum was reached by at least two points: a smaller distance found later clears it)
@@ -298,7 +306,20 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
       }
       if (dbg && lane == 0) atomicAdd(dbg + 3, (unsigned long long)__popc(qm));
     }
-    if (valid && done) lrr_match_finish(a, rigid, k, k, x, y, z, yx, yy, yz, best_s, acc);
+    if (valid && done) {
+      // certificate: every other staged point is at least sqrt(second) away, every point that was not staged lies outside the
+      // box, i.e. at least as far as the nearest box face that has cells behind it (faces on the grid border have none: border
+      // cells hold everything beyond them).  Rounded down.
+      double bound = sqrt(second);
+      if (B.rx0 > 0) bound = fmin(bound, yx - (g.ox + B.rx0 * g.h));
+      if (B.rx1 < g.nx - 1) bound = fmin(bound, (g.ox + (B.rx1 + 1) * g.h) - yx);
+      if (B.ry0 > 0) bound = fmin(bound, yy - (g.oy + B.ry0 * g.h));
+      if (B.ry1 < g.ny - 1) bound = fmin(bound, (g.oy + (B.ry1 + 1) * g.h) - yy);
+      if (B.rz0 > 0) bound = fmin(bound, yz - (g.oz + B.rz0 * g.h));
+      if (B.rz1 < g.nz - 1) bound = fmin(bound, (g.oz + (B.rz1 + 1) * g.h) - yz);
+      bound = bound * (1.0 - 1e-9) - slack;
+      lrr_match_finish(a, rigid, k, k, x, y, z, yx, yy, yz, best_s, acc, (a.proof && !tie && bound > 0.0) ? 2 : 0, bound);
+    }
   }
 }
 
@@ -323,11 +344,91 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
   if (scope.reduce<4>(acc, s_out, s_tmp)) {
     lrr_tl(0, 2);
     if (threadIdx.x == 0) {
-      Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3];
+      Scal* sc = d.sc;
+      if (lrr_dir_certified(d)) {   // the certificate pass wrote its share of the sums
+        sc->sum_loc[0] += s_out[0]; sc->sum_loc[1] += s_out[1]; sc->sum_loc[2] += s_out[2]; sc->sum_r2 += s_out[3];
+        *d.todo_count = 0;
+      } else { sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3]; }
       *counter = 0;
     }
   }
   lrr_tl(0, 3);
+}
+
+// ---- certificate pass ------------------------------------------------------------------------------------------------
+// NEIGHBOUR CERTIFICATE of a from-feature: (y0, B) = the mapped position at which its neighbour q_prev was proven the UNIQUE nearest
+// to-feature, and a lower bound B on the distance from y0 to every OTHER to-feature (written by the staged search: second smallest
+// staged distance / nearest box face; by pass B: second smallest distance inside the inflated ball / its radius).  For a new
+// mapped position y and any other feature p:  |y - p| >= |y0 - p| - |y - y0| >= B - |y - y0|,  so
+//        |y - q_prev| + |y - y0| < B     =>     q_prev is still the unique nearest neighbour (no search, no tie possible).
+// ICP moves the mapped positions less and less, so near convergence almost every query is kept this way; the others go to the
+// staged search through the work list.  The result is the exact neighbour either way (bit-exact index sets vs the oracle).
+// One warp per chunk, no shared-memory staging: full occupancy, coalesced along the tile order.
+#define LRR_CERT_THREADS 256
+__global__ void __launch_bounds__(LRR_CERT_THREADS) k_match_cert(const __grid_constant__ EstArgs a) {
+  __shared__ double s_T[15];
+  __shared__ double s_out[8], s_tmp[8 * (LRR_CERT_THREADS / 32)];
+  const int dir = blockIdx.y;
+  const DirArgs& d = a.d[dir];
+  lrr_tl(5, 0);
+  lrr_stage_transform(d.sc, s_T);
+  double acc[4] = {0, 0, 0, 0};
+  if (lrr_dir_certified(d)) {
+    const double* A = s_T; const double* tt = s_T + 9; const double* cc = s_T + 12;
+    const bool rigid = (a.flags & LRR_F_RIGID) != 0;
+    const GridDev& g = d.to.grid;
+    const double slack = 1e-9 * g.h;
+    const int lane = threadIdx.x & 31;
+    const int nchunks = __ldg(d.nchunks);
+    const int wpb = LRR_CERT_THREADS / 32;
+    for (int ch = blockIdx.x * wpb + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * wpb) {
+      const int2 qq = __ldg(d.chunk_tab + ch);
+      const int tq = qq.x + lane;
+      const bool valid = tq < qq.y;
+      bool kept = false;
+      if (valid) {
+        const int k = __ldg(d.proc + tq);
+        // everything indexed by k in flight together, then everything indexed by the previous neighbour
+        const int sp = d.prev_s[k];
+        const double2* pr = reinterpret_cast<const double2*>(d.proof + k);
+        const double2 p0 = __ldcg(pr), p1 = __ldcg(pr + 1);
+        const double x = __ldg(d.fx + k), y = __ldg(d.fy + k), z = __ldg(d.fz + k);
+        if (sp >= 0 && p1.y > 0.0) {
+          double yx, yy, yz;
+          lrr_map_exact(A, tt, cc, x, y, z, yx, yy, yz);
+          const double4 q = lrr_ld_pos4(g.pos4 + sp);
+          const double dq = sqrt(lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z));
+          const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
+          const double dm = sqrt(ex * ex + ey * ey + ez * ez);
+          // (1e-9 relative + slack covers the rounding of the square roots and sums; B itself was rounded down when written)
+          if ((dq + dm) * (1.0 + 1e-9) + slack < p1.y) { lrr_match_finish(d, rigid, k, k, x, y, z, yx, yy, yz, sp, acc, 1); kept = true; }
+          if (kept && g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + 7, 1ull);   // development counter (scripts/timeline.py)
+          if (!kept && g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + 18, 1ull);
+        } else if (g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + (sp < 0 ? 16 : 17), 1ull);
+      }
+      const unsigned int rest = __ballot_sync(0xffffffffu, valid && !kept);
+      if (rest && lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); }
+    }
+  }
+  lrr_tl(5, 1);
+  const GridScope scope = lrr_scope_of(a, dir);
+  if (scope.reduce<4>(acc, s_out, s_tmp)) {
+    if (threadIdx.x == 0) { Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3]; }
+  }
+  lrr_tl(5, 3);
+}
+bool lrr_match_cert_usable(const EstArgs& a) {
+  for (int d = 0; d < a.ndir; ++d) if (a.d[d].proof && a.d[d].todo && a.d[d].chunk_tab && a.d[d].proc && a.d[d].M == a.d[d].n_in) return true;
+  return false;
+}
+void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches) {
+  int maxM = a.d[0].M; if (a.ndir == 2 && a.d[1].M > maxM) maxM = a.d[1].M;
+  int nb = (maxM / 32 + LRR_CERT_THREADS / 32 - 1) / (LRR_CERT_THREADS / 32) + 1;   // about one chunk per warp ...
+  static int per_sm = 0;
+  if (!per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_cert, LRR_CERT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1; }
+  nb = std::max(1, std::min(nb, per_sm * lrr_num_sms() / a.ndir));   // ... but every block resident at once (no second wave)
+  dim3 grid(nb, a.ndir);
+  k_match_cert<<<grid, LRR_CERT_THREADS, 0, st>>>(a); ++*launches;
 }
 
 bool lrr_match_tile_usable(const EstArgs& a) {

@@ -21,7 +21,7 @@ est.one_iteration(it)
 out = np.zeros(8 * 2048 * 4, dtype=np.uint64)
 f(0, out.ctypes.data_as(C.c_void_p))
 tl = out.reshape(8, 2048, 4).astype(np.float64)
-for kid, name in [(0, "k_match"), (1, "k_match_hard"), (2, "k_accumulate"), (4, "k_weight")]:
+for kid, name in [(5, "k_match_cert"), (0, "k_match(_tile)"), (1, "k_match_hard"), (2, "k_accumulate"), (4, "k_weight")]:
     t = tl[kid]; live = t[:, 0] > 0
     if not live.any():
         continue
@@ -34,8 +34,10 @@ for kid, name in [(0, "k_match"), (1, "k_match_hard"), (2, "k_accumulate"), (4, 
     print(f"   per-block loop time: min {body.min():.1f} median {np.median(body):.1f} p90 {np.percentile(body,90):.1f} max {body.max():.1f} us")
 c = out.reshape(8, 2048 * 4)[3][:8].astype(np.int64)
 if c[0]:
-    print(f"tile chunks {c[0]} (both directions): fallback rows {c[1]} cap {c[2]} | queued for pass B {c[3]} queries | per chunk: staged points {c[4]/c[0]:.0f} rows {c[5]/c[0]:.0f} queries {c[6]/c[0]:.1f}")
+    print(f"tile chunks {c[0]} (both directions): fallback rows {c[1]} cap {c[2]} | queued for pass B {c[3]} queries | per chunk: staged points {c[4]/c[0]:.0f} rows {c[5]/c[0]:.0f} queries {c[6]/c[0]:.1f} | kept by certificate {c[7]} queries")
 ph = out.reshape(8, 2048 * 4)[3][8:16].astype(np.float64)
 if ph.sum() > 0:
     names = ["load+map+cand", "row bounds", "stage", "filter", "exact", "check", "cooperative", "finish"]
     print("tile kernel, warp-time per chunk (us): " + ", ".join(f"{n} {v / 1.965e3 / max(c[0], 1):.2f}" for n, v in zip(names, ph)))
+cc = out.reshape(8, 2048 * 4)[3][16:24].astype(np.int64)
+print("certificate pass: no previous neighbour", cc[0], "| no certificate", cc[1], "| certificate too weak for the motion", cc[2])
