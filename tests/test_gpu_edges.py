@@ -146,3 +146,49 @@ def test_neighbours_exact_under_scale_offset_and_tiny_distances(gpu_lib, oracle_
         assert np.array_equal(a, b)
     if noise <= 1e-3 * scale:
         assert np.mean(out[0][0] == src) > 0.9          # the planted neighbours are found
+
+
+@pytest.mark.parametrize("kind,dof", [("rrl_sym", 12), ("cdcl_fwd", 6)])
+def test_neighbour_certificates_under_transform_jitter(gpu_lib, oracle_lib, kind, dof):
+    """Finest-level matches are kept without a search while the neighbour certificate of a from-feature (lrr_tile.cu: proven
+    position, lower bound on every other to-feature) covers the motion of its mapped position.  Jitter the transform by amounts
+    from far below to far above the certificates' reach, in both orders, with duplicate fixed points in the set (ties must never
+    be certified): the index sets must stay bit-exact against the oracle's fresh k-d tree search every time."""
+    pair = synth.make_pair(61, 20000, 18000, size=120.0, rigid=(dof == 6))
+    f = pair["fixed"]
+    for k in f:   # exact duplicates of 50 fixed features at the end: lowest index wins ties
+        if f[k] is not None:
+            f[k] = np.ascontiguousarray(np.concatenate([f[k], f[k][..., :50]], axis=-1))
+    A0, t0, c0 = pair["init"]
+    rng = np.random.default_rng(3)
+    ests = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        est = ctx.estimator(kind, ctx.upload(pair["moving"]), ctx.upload(pair["fixed"]), dof)
+        est.set_flags(True, True)
+        ests.append(est)
+    dirs = (0, 1) if "sym" in kind else (0,)
+    n_kept_changes = 0
+    prev = None
+    for step, mag in enumerate([0.0, 1e-7, 1e-5, 1e-3, 1e-2, 0.1, 1.0, 5.0, 1e-4, 0.0, 0.3, 1e-6, 2.0, 1e-3]):
+        w = rng.normal(size=3) * mag / 60.0   # rotation that moves points at 60 mm from the centre by ~mag
+        K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        R, _ = np.linalg.qr(np.eye(3) + K)
+        R = R * np.sign(np.diag(R))
+        A = R @ A0 if dof == 12 else R @ A0
+        t = t0 + rng.normal(size=3) * mag
+        res = []
+        for est in ests:
+            est.set_transform(A, t, c0)
+            for d in dirs:
+                est.set_number_points(10 ** 9, d)
+            est.find_closest()
+            res.append([est.get_matches(d) for d in dirs])
+        for d in dirs:
+            assert np.array_equal(res[0][d][0], res[1][d][0]), (step, mag, d)
+            bad = np.count_nonzero(res[0][d][1] != res[1][d][1])
+            assert bad == 0, (step, mag, d, bad)
+        if prev is not None:
+            n_kept_changes += int(np.count_nonzero(prev != res[1][0][1]))
+        prev = res[1][0][1]
+    assert n_kept_changes > 0   # the jitter did change neighbours (the certificates had something to get wrong)
