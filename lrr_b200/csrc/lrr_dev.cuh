@@ -4,6 +4,15 @@
 
 // development aid (scripts/timeline.py): per-block %globaltimer marks of the phase kernels of this translation unit.
 // Off (null pointer, one uniform load per mark) unless lrr_debug_timeline() armed it.
+// Programmatic dependent launch (sm_90+): the kernels of one iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (lrr_launch_pdl, lrr_internal.h).  Each of them first waits for the complete
+// predecessor grid (griddepcontrol.wait: all its memory operations are visible afterwards); once a block is through its element loop
+// it lets the successor be scheduled (lrr_pdl_trigger, at the start of the final reduction), so the successor's blocks become
+// resident while the last block is still adding the partial rows / solving, and the launch latency between two dependent kernels
+// overlaps that serial tail.  (Triggering at kernel entry measured SLOWER: the waiting successor blocks take SM slots from the
+// later waves of the running kernel.)
+__device__ __forceinline__ void lrr_pdl_enter() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void lrr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 static __device__ unsigned long long* g_lrr_tl = nullptr;
 __device__ __forceinline__ void lrr_tl(int kern, int slot) {
   unsigned long long* p = g_lrr_tl;
@@ -384,6 +393,7 @@ struct GridScope {
   __device__ __forceinline__ bool reduce(double (&v)[K], double* sh_out /* >= K*G */, double* sh_tmp /* >= K*G*nwarps */) const {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     constexpr int KG = K * G;
+    lrr_pdl_trigger();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       double x = v[k];
@@ -452,6 +462,7 @@ struct GridScope {
   // ticket only (no sums): true in every thread of the last block
   __device__ __forceinline__ bool last_block() const {
     __shared__ bool is_last2;
+    lrr_pdl_trigger();
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {

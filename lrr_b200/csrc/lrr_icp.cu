@@ -150,6 +150,7 @@ void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* 
 #define LRR_MATCH_MINBLK 2
 #endif
 __global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
   lrr_tl(0, 0);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const _
 #define LRR_HARD_MINBLK 2
 #endif
 __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
   lrr_tl(1, 0);
@@ -175,27 +177,29 @@ void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   }
   else {
     dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
-    k_match<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+    lrr_launch_pdl(k_match, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
   }
   // queue length is only known on the device: a fixed grid of warps strides over it
   // (two waves on purpose: each direction's queue is drained by all resident warps, measured faster than co-resident halves)
   dim3 gridb(std::min(nblk_for(32LL * maxM(a)), 2 * lrr_num_sms()), a.ndir);
-  k_match_hard<<<gridb, LRR_THREADS, 0, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_match_hard, gridb, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
 __global__ void __launch_bounds__(LRR_THREADS) k_norm1(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   lrr_phase_norm1(lrr_scope(a, a.src), a.d[a.src], sh);
 }
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches) {
-  k_norm1<<<nblk_for(a.d[a.src].M), LRR_THREADS, 0, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_norm1, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 __global__ void __launch_bounds__(LRR_THREADS) k_norm2(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   lrr_phase_norm2(lrr_scope(a, a.src), a.d[a.src], a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, sh);
 }
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches) {
-  k_norm2<<<nblk_for(a.d[a.src].M), LRR_THREADS, 0, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_norm2, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
 // ---- cdcl estimate_LS_backward (cdcl sym :705-863): cdcl_normalize_matches over the MERGED list = the estimated
@@ -260,6 +264,7 @@ void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches) {
 struct WeightExtra { int scale_mode[2]; double scale_in[2]; };
 
 __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   __shared__ double sh_cand[LRR_SEL_CAP];
   const int dir = blockIdx.y;
@@ -308,7 +313,7 @@ void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scal
   WeightExtra ex;
   for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
   dim3 grid(resident_width(k_weight, LRR_THREADS, a.ndir, maxM(a)), a.ndir);
-  k_weight<<<grid, LRR_THREADS, 0, st>>>(a, ex); ++*launches;
+  lrr_launch_pdl(k_weight, grid, dim3(LRR_THREADS), 0, st, a, ex); ++*launches;
 }
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches) {
   const int m[2] = {0, 0}; const double s[2] = {0, 0};
@@ -316,6 +321,7 @@ void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches) {
 }
 
 __global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ double sh_cand[LRR_SEL_CAP];
   const int dir = blockIdx.y;
   const bool merged = (a.flags & LRR_F_MERGED) != 0;
@@ -345,10 +351,11 @@ __global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__
 }
 void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches) {
   dim3 grid(nblk_for(maxM(a)), a.ndir);
-  k_collect<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_collect, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
 __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   const int dir = blockIdx.y;
   const bool merged = (a.flags & LRR_F_MERGED) != 0, sym = (a.flags & LRR_F_SYM) != 0;
@@ -370,10 +377,11 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
   // two blocks per SM at most: the last block sums one row of 108 moments per block before it can solve
   dim3 grid(resident_width(k_accumulate, LRR_THREADS, a.ndir, 4LL * maxM(a)), a.ndir);
-  k_accumulate<<<grid, LRR_THREADS, 0, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_accumulate, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
 __global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0) {
+  lrr_pdl_enter();
   __shared__ PhaseShared sh;
   const int dir = dir0 + blockIdx.y;
   if (a.d[dir].sc->status & LRR_ST_SELECT_MISS) return;   // the estimate was not committed: keep the residuals of the match for the rerun
@@ -382,10 +390,10 @@ __global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ E
 void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches) {
   if (dir_mask == 3) {
     dim3 grid(resident_width(k_resid, LRR_THREADS, 2, maxM(a)), 2);
-    k_resid<<<grid, LRR_THREADS, 0, st>>>(a, 0); ++*launches;
+    lrr_launch_pdl(k_resid, grid, dim3(LRR_THREADS), 0, st, a, 0); ++*launches;
   } else {
     const int d = (dir_mask == 2) ? 1 : 0;
-    k_resid<<<nblk_for(a.d[d].M), LRR_THREADS, 0, st>>>(a, d); ++*launches;
+    lrr_launch_pdl(k_resid, dim3(nblk_for(a.d[d].M)), dim3(LRR_THREADS), 0, st, a, d); ++*launches;
   }
 }
 

@@ -156,6 +156,22 @@ struct EstArgs {
   unsigned int* ticket;   // per direction slot
 };
 
+// launch with programmatic stream serialization (see lrr_pdl_enter, lrr_dev.cuh); LRR_NO_PDL=1 falls back to plain launches (A/B)
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+template <class... KArgs, class... Args>
+static inline void lrr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool off = getenv("LRR_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 // ---- grid build / NN  (lrr_grid.cu) ----------------------------------------------------------------
 struct FsetBuild {
   int64_t n;

@@ -324,6 +324,7 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
 }
 
 __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_T[15];
   __shared__ double s_out[8], s_tmp[8 * LRR_TILE_WARPS];
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
 // One warp per chunk, no shared-memory staging: full occupancy, coalesced along the tile order.
 #define LRR_CERT_THREADS 256
 __global__ void __launch_bounds__(LRR_CERT_THREADS) k_match_cert(const __grid_constant__ EstArgs a) {
+  lrr_pdl_enter();
   __shared__ double s_T[15];
   __shared__ double s_out[8], s_tmp[8 * (LRR_CERT_THREADS / 32)];
   const int dir = blockIdx.y;
@@ -428,7 +430,7 @@ void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches) {
   if (!per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_cert, LRR_CERT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1; }
   nb = std::max(1, std::min(nb, per_sm * lrr_num_sms() / a.ndir));   // ... but every block resident at once (no second wave)
   dim3 grid(nb, a.ndir);
-  k_match_cert<<<grid, LRR_CERT_THREADS, 0, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_match_cert, grid, dim3(LRR_CERT_THREADS), 0, st, a); ++*launches;
 }
 
 bool lrr_match_tile_usable(const EstArgs& a) {
@@ -441,5 +443,5 @@ void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches) {
   if (!attr_set) { cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   // every block of both directions resident at once (4 blocks of 128 threads per SM): no second wave
   dim3 grid(std::max(1, (4 * lrr_num_sms()) / a.ndir), a.ndir);
-  k_match_tile<<<grid, LRR_TILE_THREADS, smem, st>>>(a); ++*launches;
+  lrr_launch_pdl(k_match_tile, grid, dim3(LRR_TILE_THREADS), smem, st, a); ++*launches;
 }
