@@ -431,7 +431,7 @@ def run_b200(args, rank, world, local_rank):
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        names = {"match": ["k_match_tile", "k_match_hard"], "accumulate": ["k_accumulate"], "weight": ["k_weight"]}.get(dom, [])
+        names = {"match": ["k_match_cert", "k_match_tile", "k_match_hard"], "accumulate": ["k_accumulate"], "weight": ["k_weight"]}.get(dom, [])
         if names and all(n in tj["dram_bytes_per_launch"] for n in names):
             traffic = sum(tj["dram_bytes_per_launch"][n] for n in names); traffic_src = tj["source"]
     except Exception:
@@ -445,7 +445,7 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "flushed (256 MiB write) between timed iterations; working set ~30 MB is L2-resident otherwise",
                    "ramp_iterations": ramp_iters, "ramp_converged": bool(ramp_conv)},
         "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else ("k_match_tile + k_match_hard (exact 1-NN: shared-memory-staged cells, then the queued far queries)" if dom == "match" else "k_" + dom), "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else ("k_match_cert + k_match_tile + k_match_hard (exact 1-NN: neighbour certificates, shared-memory-staged cells for the queries they do not cover, queued far queries)" if dom == "match" else "k_" + dom), "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                      "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
         "roofline_iteration": {"algorithmic_bytes": it_bytes, "achieved_gbs": it_bytes / (ms_step * 1e-3) / 1e9,
@@ -464,6 +464,19 @@ def run_b200(args, rank, world, local_rank):
                           "what": f"C4 bounded: {BATCH_LOCATIONS_PER_GPU} locations x {BATCH_INITS} initialisations per GPU on one resident "
                                   "100k/100k pair, 50 mm ROI, rrl symmetric <3,12>, <= 70 iterations, jobs sharded over the ranks, one result gather"},
     }
+    if world == 1 and not args.only_iterations and os.environ.get("LRR_NO_PROOF") is None:
+        # the same timed loop with the neighbour certificates switched off (every finest-level query searched in every iteration):
+        # what an iteration costs when nothing can be kept, e.g. the first iteration at the finest level
+        try:
+            env = dict(os.environ, LRR_NO_PROOF="1")
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--only-iterations", "--steps", str(args.steps), "--warmup", str(args.warmup)],
+                                 env=env, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
+            sub = json.loads(out[-1])
+            line["certificates_off"] = {"value": sub["value"], "unit": UNIT, "ms_per_step": sub["ms_per_step"], "value_l2_warm": sub["value_l2_warm"],
+                                        "match_us": sub["kernels"]["match"]["us_per_launch"],
+                                        "what": "LRR_NO_PROOF=1: same loop, every query of both directions searched in every iteration (no neighbour certificates)"}
+        except Exception as ex:   # noqa: BLE001
+            line["certificates_off"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu and not args.only_iterations:
         r = cpu_measure(pair, 6, 1)
         line["cpu_baseline"] = {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": 1, "kind": r["kind"],

@@ -575,8 +575,13 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
   double acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-  for (int k = scope.first() >> 2; k < a.M; k += scope.stride() >> 2) {
-    const int s = a.sidx[k];
+  // (the neighbour slot of the NEXT match of this quad is fetched one trip ahead: the dependent chain per trip is then one gather
+  //  hop — position and projector of the neighbour — instead of two)
+  const int k0 = scope.first() >> 2, kstep = scope.stride() >> 2;
+  int s_next = k0 < a.M ? a.sidx[k0] : -1;
+  for (int k = k0; k < a.M; k += kstep) {
+    const int s = s_next;
+    if (k + kstep < a.M) s_next = a.sidx[k + kstep];
     double w = a.w[k];                             // Beaton-Tukey weight / scale^2
     if (strength) {
       const double g = a.gkey[k];

@@ -18,8 +18,18 @@ it, conv = 0, False
 while not conv and it < 70:
     conv = est.one_iteration(it); it += 1
 print("ramp iterations", it, "converged", conv, "launches", ctx.launch_count())
-ctx.set_profiling(True)
+for k in range(3):   # settle at the finest level (neighbour certificates in place)
+    est.one_iteration(it); it += 1
+rng = os.environ.get("LRR_PROF_RANGE")   # ncu --profile-from-start off: capture only the iterations below
+if rng:
+    import torch
+    torch.cuda.cudart().cudaProfilerStart()
+else:
+    ctx.set_profiling(True)
 for k in range(extra):
     est.one_iteration(it + k)
-print({k: (round(1e3 * v[0] / v[1], 2), v[1]) for k, v in ctx.phase_times().items()})
+if rng:
+    ctx.synchronize(); torch.cuda.cudart().cudaProfilerStop()
+if not rng:
+    print({k: (round(1e3 * v[0] / v[1], 2), v[1]) for k, v in ctx.phase_times().items()})
 print("launches", ctx.launch_count())
