@@ -160,12 +160,53 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_MATCH_MINBLK) k_match(const _
 #ifndef LRR_HARD_MINBLK
 #define LRR_HARD_MINBLK 2
 #endif
+// Pass B of every direction in ONE 1-D grid that is resident as a whole: each warp drains the queue of "its" direction
+// (blockIdx.x parity) and then helps with the other one, so both queues have the whole GPU and neither waits for a second wave
+// (measured with per-block timeline marks: as gridDim.y = 2 the blocks of direction 1 only started when direction 0 had finished,
+// two serial tails of ~15 us each when the queues hold a few hundred far queries).  One reduction of 2 x 4 sums, one finalizer.
 __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(const __grid_constant__ EstArgs a) {
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
-  const int dir = blockIdx.y;
+  __shared__ double s_T[2][15];
   lrr_tl(1, 0);
-  lrr_phase_match_hard(lrr_scope(a, dir), a.d[dir], a.flags, sh, a.ticket + 6 + dir);
+  {
+    // nothing queued in any direction (the steady state: every query kept by its certificate or finished by the staged search):
+    // one thread per direction does the bookkeeping, every other block leaves at once
+    bool any = false;
+    for (int d = 0; d < a.ndir; ++d) any = any || *reinterpret_cast<volatile int*>(a.d[d].hq_count) > 0;
+    if (!any) {
+      if (blockIdx.x == 0 && threadIdx.x < a.ndir) {
+        const Scal* sc = a.d[threadIdx.x].sc;
+        const double tot[4] = {sc->sum_loc[0], sc->sum_loc[1], sc->sum_loc[2], sc->sum_r2};
+        lrr_match_finalize(a.d[threadIdx.x], a.flags, tot);
+      }
+      return;
+    }
+  }
+  if (threadIdx.x < 15 * a.ndir) {
+    const int d = threadIdx.x / 15, j = threadIdx.x % 15;
+    const Scal* sc = a.d[d].sc;
+    s_T[d][j] = j < 9 ? sc->A[j] : (j < 12 ? sc->t[j - 9] : sc->c[j - 12]);
+  }
+  __syncthreads();
+  double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+  const int wg = blockIdx.x * LRR_NWARPS + (threadIdx.x >> 5), nwg = gridDim.x * LRR_NWARPS;
+  if (a.ndir == 2) {
+    if (blockIdx.x & 1) { lrr_match_b_body_dynamic(a.d[1], a.flags, s_T[1], a.ticket + 7, acc1, wg, nwg); lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg); }
+    else { lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg); lrr_match_b_body_dynamic(a.d[1], a.flags, s_T[1], a.ticket + 7, acc1, wg, nwg); }
+  } else lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg);
+  lrr_tl(1, 1);
+  double v[8] = {acc0[0], acc0[1], acc0[2], acc0[3], acc1[0], acc1[1], acc1[2], acc1[3]};
+  if (lrr_scope(a, 0).template reduce<8>(v, sh.out, sh.tmp)) {
+    lrr_tl(1, 2);
+    if (threadIdx.x < a.ndir) {
+      const int d = threadIdx.x;
+      const Scal* sc = a.d[d].sc;
+      const double tot[4] = {sc->sum_loc[0] + sh.out[4 * d], sc->sum_loc[1] + sh.out[4 * d + 1], sc->sum_loc[2] + sh.out[4 * d + 2], sc->sum_r2 + sh.out[4 * d + 3]};
+      lrr_match_finalize(a.d[d], a.flags, tot);
+      a.ticket[6 + d] = 0;
+    }
+  }
   lrr_tl(1, 3);
 }
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
@@ -180,15 +221,16 @@ void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
     lrr_launch_pdl(k_match, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
   }
   // queue length is only known on the device: a fixed grid of warps strides over it
-  // (two waves on purpose: each direction's queue is drained by all resident warps, measured faster than co-resident halves)
-  dim3 gridb(std::min(nblk_for(32LL * maxM(a)), 2 * lrr_num_sms()), a.ndir);
+  dim3 gridb(resident_width(k_match_hard, LRR_THREADS, 1, 32LL * maxM(a)));
   lrr_launch_pdl(k_match_hard, gridb, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
 __global__ void __launch_bounds__(LRR_THREADS) k_norm1(const __grid_constant__ EstArgs a) {
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
+  lrr_tl(6, 0);
   lrr_phase_norm1(lrr_scope(a, a.src), a.d[a.src], sh);
+  lrr_tl(6, 3);
 }
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches) {
   lrr_launch_pdl(k_norm1, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a); ++*launches;
@@ -196,7 +238,9 @@ void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches) {
 __global__ void __launch_bounds__(LRR_THREADS) k_norm2(const __grid_constant__ EstArgs a) {
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
+  lrr_tl(7, 0);
   lrr_phase_norm2(lrr_scope(a, a.src), a.d[a.src], a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, sh);
+  lrr_tl(7, 3);
 }
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches) {
   lrr_launch_pdl(k_norm2, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a); ++*launches;
@@ -385,7 +429,9 @@ __global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ E
   __shared__ PhaseShared sh;
   const int dir = dir0 + blockIdx.y;
   if (a.d[dir].sc->status & LRR_ST_SELECT_MISS) return;   // the estimate was not committed: keep the residuals of the match for the rerun
+  lrr_tl(8, 0);
   lrr_phase_resid(lrr_scope(a, dir), a.d[dir], sh);
+  lrr_tl(8, 3);
 }
 void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches) {
   if (dir_mask == 3) {
@@ -397,10 +443,10 @@ void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* lau
   }
 }
 
-// development aid: arm / read the per-block timeline marks (lrr_dev.cuh).  out: 4 kernels x 2048 blocks x 4 marks.
+// development aid: arm / read the per-block timeline marks (lrr_dev.cuh).  out: 12 kernels x 2048 blocks x 4 marks.
 extern "C" int lrr_debug_timeline(int arm, unsigned long long* out) {
   static unsigned long long* buf = nullptr;
-  const size_t n = 8 * 2048 * 4;
+  const size_t n = 12 * 2048 * 4;
   if (arm) {
     if (!buf) { if (cudaMalloc(&buf, n * sizeof(unsigned long long)) != cudaSuccess) return 1; }
     cudaMemset(buf, 0, n * sizeof(unsigned long long));

@@ -159,13 +159,22 @@ __device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, con
   else s = lrr_nn_pass_b(a.to.grid, yx, yy, yz, st);
   if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc, (bound > 0.0 && i == kq) ? 2 : 0, bound);
 }
-__device__ __forceinline__ void lrr_match_b_body_dynamic(const DirArgs& a, int flags, const double* s_T, unsigned int* counter, double (&acc)[4]) {
+// first_item >= 0: the warp's first query is assigned statically (its number among the nstatic warps of the launch) and only the
+// following ones are pulled from the counter — a launch whose queue is shorter than the number of warps (the steady state: empty)
+// does not touch the counter at all (a few thousand same-address atomics are several microseconds of an otherwise empty kernel)
+__device__ __forceinline__ void lrr_match_b_body_dynamic(const DirArgs& a, int flags, const double* s_T, unsigned int* counter, double (&acc)[4],
+                                                         int first_item = -1, int nstatic = 0) {
   const int lane = threadIdx.x & 31;
   const int nq = *a.hq_count;
+  if (nq <= 0) return;
+  unsigned int qi = (unsigned int)first_item;
+  bool pull = first_item < 0;
   for (;;) {
-    unsigned int qi = 0;
-    if (lane == 0) qi = atomicAdd(counter, 1u);
-    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (pull) {
+      if (lane == 0) qi = atomicAdd(counter, 1u) + (unsigned int)nstatic;
+      qi = __shfl_sync(0xffffffffu, qi, 0);
+    }
+    pull = true;
     if ((int)qi >= nq) break;
     lrr_match_b_one(a, flags, s_T, (int)qi, acc);
     __syncwarp();
@@ -253,6 +262,7 @@ __device__ void lrr_phase_norm1(const Scope& scope, const DirArgs& a, SH& sh) {
       acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += 1.0;
     }
   }
+  lrr_tl(6, 1);
   if (scope.template reduce<5>(acc, sh.out, sh.tmp)) {
     if (threadIdx.x == 0) {
       sc->sum_q[0] = sh.out[0]; sc->sum_q[1] = sh.out[1]; sc->sum_q[2] = sh.out[2]; sc->n_unique = sh.out[3];
@@ -278,6 +288,7 @@ __device__ void lrr_phase_norm2(const Scope& scope, const DirArgs& a, Scal* othe
       acc[0] += sqrt(dx * dx + dy * dy + dz * dz);
     }
   }
+  lrr_tl(7, 1);
   if (scope.template reduce<1>(acc, sh.out, sh.tmp)) {
     if (threadIdx.x == 0) {
       sc->sum_rad_to = sh.out[0];
@@ -936,6 +947,7 @@ __device__ void lrr_phase_resid(const Scope& scope, const DirArgs& a, SH& sh) {
     a.r2[k] = r2;
     acc[0] += r2; acc[1] += w * r2; acc[2] += w; acc[3] += sqrt(r2) * w; acc[4] += 1.0;
   }
+  lrr_tl(8, 1);
   if (scope.template reduce<5>(acc, sh.out, sh.tmp)) {
     if (threadIdx.x == 0) {
       sc->res_sum_r2 = sh.out[0]; sc->res_sum_wr2 = sh.out[1]; sc->res_sum_w = sh.out[2]; sc->res_sum_wr = sh.out[3];

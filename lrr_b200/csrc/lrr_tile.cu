@@ -160,10 +160,17 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
   // work list: every chunk of the direction, or — certificates in use — the (chunk, lane mask) entries k_match_cert left over
   const bool use_todo = a.todo != nullptr && a.proof != nullptr;
   const int nwork = use_todo ? *reinterpret_cast<volatile int*>(a.todo_count) : nchunks;
+  // (the first item of a warp is assigned statically, the following ones are pulled from the counter: a work list shorter than the
+  //  number of warps — the steady state with certificates — costs no same-address atomics)
+  const int nstatic = gridDim.x * LRR_TILE_WARPS;
+  unsigned int wi = blockIdx.x * LRR_TILE_WARPS + (threadIdx.x >> 5);
+  bool pull = false;
   for (;;) {
-    unsigned int wi = 0;
-    if (lane == 0) wi = atomicAdd(counter, 1u);
-    wi = __shfl_sync(full, wi, 0);
+    if (pull) {
+      if (lane == 0) wi = atomicAdd(counter, 1u) + (unsigned int)nstatic;
+      wi = __shfl_sync(full, wi, 0);
+    }
+    pull = true;
     if ((int)wi >= nwork) break;
     int ch = (int)wi; unsigned int lanes = full;
     if (use_todo) { const int2 e = __ldcg(a.todo + wi); ch = e.x; lanes = (unsigned int)e.y; }
@@ -332,6 +339,8 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
   const DirArgs& d = a.d[dir];
   unsigned int* counter = a.ticket + 4 + dir;
   lrr_tl(0, 0);
+  // certificates in use and nothing left over by k_match_cert (the steady state): its sums stand, the work list is empty already
+  if (lrr_dir_certified(d) && *reinterpret_cast<volatile int*>(d.todo_count) == 0) return;
   lrr_stage_transform(d.sc, s_T);
   double acc[4] = {0, 0, 0, 0};
   if (d.chunk_tab && d.proc && d.M == d.n_in) {

@@ -18,8 +18,13 @@ it, conv = 0, False
 while not conv and it < 70:
     conv = est.one_iteration(it); it += 1
 print("ramp iterations", it, "converged", conv, "launches", ctx.launch_count())
-for k in range(3):   # settle at the finest level (neighbour certificates in place)
+for k in range(int(os.environ.get("LRR_PROF_SETTLE", "3"))):   # settle at the finest level (neighbour certificates in place)
     est.one_iteration(it); it += 1
+import time
+ctx.synchronize(); t0 = time.perf_counter()
+for k in range(40):   # un-profiled back-to-back iterations (host wall clock; each call ends in a stream synchronisation)
+    est.one_iteration(it); it += 1
+ctx.synchronize(); print(f"wall per iteration (L2 warm, 40 calls): {1e6 * (time.perf_counter() - t0) / 40:.1f} us")
 rng = os.environ.get("LRR_PROF_RANGE")   # ncu --profile-from-start off: capture only the iterations below
 if rng:
     import torch

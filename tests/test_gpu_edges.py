@@ -192,3 +192,49 @@ def test_neighbour_certificates_under_transform_jitter(gpu_lib, oracle_lib, kind
             n_kept_changes += int(np.count_nonzero(prev != res[1][0][1]))
         prev = res[1][0][1]
     assert n_kept_changes > 0   # the jitter did change neighbours (the certificates had something to get wrong)
+
+
+def test_certificates_with_far_queries_and_near_ties(gpu_lib, oracle_lib):
+    """The hard cases of the neighbour certificates: far queries (many fixed features at almost the same distance) and near ties
+    (two fixed features mirrored about the query), where the margin between the nearest and the second nearest is tiny.  Tiny
+    translations along x flip the winner, larger ones break every bound: the index sets must stay bit-exact against the
+    oracle's fresh search at every step (kept by certificate, staged search and queued pass B alike)."""
+    rng = np.random.default_rng(9)
+    nf, nm = 6000, 4000
+    # fixed: two thin slabs mirrored about x = 0 (every moving feature near x = 0 has near-tied neighbours on both sides) + a dense blob
+    yz = rng.uniform(-40, 40, size=(2, nf // 3))
+    slab_a = np.vstack([np.full(nf // 3, -15.0) + rng.normal(0, 1e-4, nf // 3), yz])
+    slab_b = np.vstack([np.full(nf // 3, 15.0) + rng.normal(0, 1e-4, nf // 3), yz + rng.normal(0, 1e-4, yz.shape)])
+    blob = rng.normal(0, 3.0, size=(3, nf - 2 * (nf // 3))) + np.array([[60.0], [0.0], [0.0]])
+    floc = np.ascontiguousarray(np.hstack([slab_a, slab_b, blob]))
+    mloc = np.vstack([rng.normal(0, 0.02, nm), rng.uniform(-35, 35, size=(2, nm))])
+    mloc[:, : nm // 4] = rng.normal(0, 3.0, size=(3, nm // 4)) + np.array([[60.0], [0.0], [0.0]])   # ordinary near queries too
+    mloc = np.ascontiguousarray(mloc)
+    shape = lambda n: rng.integers(0, 3, n).astype(np.uint8)
+    frame = lambda n: np.linalg.qr(rng.normal(size=(n, 3, 3)))[0]
+    pair = {"fixed": synth.make_features(np.ascontiguousarray(floc.T), shape(nf), frame(nf), 1),
+            "moving": synth.make_features(np.ascontiguousarray(mloc.T), shape(nm), frame(nm), 2)}
+    ests = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        est = ctx.estimator("rrl_sym", ctx.upload(pair["moving"]), ctx.upload(pair["fixed"]), 12)
+        est.set_flags(True, True)
+        ests.append(est)
+    flips = 0
+    prev = None
+    for step, dx in enumerate([0.0, 1e-6, -1e-6, 3e-5, -3e-5, 1e-3, -1e-3, 2e-3, 0.05, -0.05, 1e-5, -1e-5, 0.5, 1e-4, -1e-4, 0.0]):
+        res = []
+        for est in ests:
+            est.set_transform(np.eye(3), np.array([dx, 1e-7 * step, 0.0]), np.zeros(3))
+            for d in (0, 1):
+                est.set_number_points(10 ** 9, d)
+            est.find_closest()
+            res.append([est.get_matches(d) for d in (0, 1)])
+        for d in (0, 1):
+            assert np.array_equal(res[0][d][0], res[1][d][0]), (step, dx, d)
+            bad = np.count_nonzero(res[0][d][1] != res[1][d][1])
+            assert bad == 0, (step, dx, d, bad)
+        if prev is not None:
+            flips += int(np.count_nonzero(prev != res[1][0][1]))
+        prev = res[1][0][1]
+    assert flips > 1000   # the mirrored slabs did flip the neighbours of the near-tied queries
