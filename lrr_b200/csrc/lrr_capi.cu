@@ -387,6 +387,7 @@ extern "C" void lrr_est_destroy(lrr_est* e) {
 }
 
 extern "C" int lrr_est_set_subsets(lrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
+  if (e) e->norm_token = false;
   if (!e || !mi || nm < 0) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   int rc = dir_set_subset(ctx, e->d[0], mi, nm);
@@ -407,6 +408,7 @@ static void set_identity_norm(Scal& s) {
 }
 
 extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
+  if (e) e->norm_token = false;
   if (!e || !A9 || !t3) return LRR_ERR_INVALID;
   if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
@@ -444,6 +446,7 @@ extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const
 }
 
 extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
+  if (e) e->norm_token = false;
   if (!e) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   e->normalize = normalize != 0; e->strength = wbs != 0;
@@ -455,6 +458,7 @@ extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
 }
 
 extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64_t n) {
+  if (e) e->norm_token = false;
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
@@ -467,6 +471,7 @@ extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64
   return LRR_OK;
 }
 extern "C" int lrr_est_set_shuffle(lrr_est* e, int mode, uint64_t seed) {
+  if (e) e->norm_token = false;
   if (!e || (mode != LRR_ORDER_FIXED && mode != LRR_ORDER_RESHUFFLE)) return LRR_ERR_INVALID;
   e->shuffle_mode = mode; e->seed = seed;
   for (int d = 0; d < 2; ++d) { e->d[d].shuffle_calls = 0; e->d[d].perm_half = 0; }
@@ -477,6 +482,7 @@ extern "C" int lrr_est_set_initial_scale(lrr_est* e, int dir, double s) {
   e->d[dir].initial_scale = s; return LRR_OK;
 }
 extern "C" int lrr_est_set_number_points(lrr_est* e, int dir, int64_t m, int* at_max) {
+  if (e) e->norm_token = false;
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0) || m < 0) return LRR_ERR_INVALID;
   if (e->icp()) return LRR_ERR_INVALID;   // cdcl_estimation_ICP has no set_number_points (cdcl_estimation_ICP.h)
   lrr_dir& d = e->d[dir];
@@ -597,7 +603,7 @@ static int do_iteration_fused(lrr_est* e) {
   const int mode[2] = {0, 0}; const double sin[2] = {0, 0};
   static const bool dbgph = getenv("LRR_FUSED_DEBUG") != nullptr;
   long long* dbg = dbgph ? (long long*)(ctx->scratch_d + 512) : nullptr;
-  ctx->sel_owner = 0;
+  ctx->sel_owner = 0; e->norm_token = false;
   { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, dbg, ctx->stream, &ctx->launches)); }
   if (dbgph) {
     static int calls = 0;
@@ -649,9 +655,13 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   }
   if (e->normalize && cdcl_backward) { PHASE(PH_NORM1); lrr_k_norm_merged(a, ctx->stream, &ctx->launches); }
   else if (e->normalize) {
-    { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches); }
-    { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches); }
+    // (rigid increments normalise mapped clones of the from-features, which move with the transform: never skipped)
+    static const bool no_skip = getenv("LRR_NO_NORM_SKIP") != nullptr;   // A/B switch for measurements
+    const int skip_clean = (e->norm_token && src == 0 && e->dof != 6 && !stale && !no_skip) ? 1 : 0;
+    { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches, skip_clean); }
+    { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches, skip_clean); }
   }
+  e->norm_token = e->normalize && !cdcl_backward && src == 0 && e->dof != 6;
   // order statistics: window around the previous iteration's values when this estimator was the last user of the
   // context's selectors with the same configuration, else (first estimate, other estimator) histograms + collect pass
   // (the signature also covers the point counts: a ramp step resamples the keys, so the first estimate after it uses histograms)
@@ -1065,6 +1075,7 @@ static int objcov_check(lrr_est* e, int dir) {
 }
 
 extern "C" int lrr_objcov_eval(lrr_est* e, int dir, const double* x, double* f, double* g) {
+  if (e) e->norm_token = false;
   int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
   if (!x) return LRR_ERR_INVALID;
   enter(e->ctx);
@@ -1121,6 +1132,7 @@ static int lbfgs_minimize(FG&& fg, std::vector<double>& x, int max_evals, double
 
 // estimate_covariance (cdcl/cdcl_estimation.txx:264-337) on the ICP matches of direction `dir`
 extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_start, double* f_end, int* n_evals) {
+  if (e) e->norm_token = false;
   int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];

@@ -73,6 +73,9 @@ struct lrr_est {
   unsigned number_matches = 1000; int finest_level = 0; int iterations_done = 0;
   bool werr_cache_valid = false; double werr_cache = 0;
   int window_holdoff = 0, window_backoff = 0;   // order-statistic window: estimates to skip after a miss
+  // the normalisation scalars on the device are those of this estimator's last forward-source estimate_LS (nothing else wrote
+  // them since): k_norm1 / k_norm2 may leave at entry while the device says no match changed (Scal::norm_dirty)
+  bool norm_token = false;
   bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
   bool icp() const { return kind == LRR_CDCL_ICP; }   // cdcl_estimation_ICP<2,4>: no point ramp, scale constant 2, strength by sum
   bool rrl() const { return kind == LRR_RRL_FWD || kind == LRR_RRL_SYM; }

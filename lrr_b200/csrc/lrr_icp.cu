@@ -225,25 +225,30 @@ void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
   lrr_launch_pdl(k_match_hard, gridb, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
-__global__ void __launch_bounds__(LRR_THREADS) k_norm1(const __grid_constant__ EstArgs a) {
+// skip_clean: the host knows that the normalisation scalars on the device are those of this estimator's last estimate_LS in the
+// same configuration (lrr_est::norm_token); if in addition no match of the source direction changed since (Scal::norm_dirty),
+// they are what this launch would recompute bit for bit, and every block leaves at entry.
+__global__ void __launch_bounds__(LRR_THREADS) k_norm1(const __grid_constant__ EstArgs a, int skip_clean) {
   lrr_pdl_enter();
+  if (skip_clean && !a.d[a.src].sc->norm_dirty) return;
   __shared__ PhaseShared sh;
   lrr_tl(6, 0);
   lrr_phase_norm1(lrr_scope(a, a.src), a.d[a.src], sh);
   lrr_tl(6, 3);
 }
-void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches) {
-  lrr_launch_pdl(k_norm1, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a); ++*launches;
+void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean) {
+  lrr_launch_pdl(k_norm1, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a, skip_clean); ++*launches;
 }
-__global__ void __launch_bounds__(LRR_THREADS) k_norm2(const __grid_constant__ EstArgs a) {
+__global__ void __launch_bounds__(LRR_THREADS) k_norm2(const __grid_constant__ EstArgs a, int skip_clean) {
   lrr_pdl_enter();
+  if (skip_clean && !a.d[a.src].sc->norm_dirty) return;
   __shared__ PhaseShared sh;
   lrr_tl(7, 0);
   lrr_phase_norm2(lrr_scope(a, a.src), a.d[a.src], a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, sh);
   lrr_tl(7, 3);
 }
-void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches) {
-  lrr_launch_pdl(k_norm2, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a); ++*launches;
+void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean) {
+  lrr_launch_pdl(k_norm2, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a, skip_clean); ++*launches;
 }
 
 // ---- cdcl estimate_LS_backward (cdcl sym :705-863): cdcl_normalize_matches over the MERGED list = the estimated
@@ -413,6 +418,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
   lrr_tl(2, 0);
   const bool fin = lrr_phase_accumulate(lrr_scope(a, dir), a.d[dir], a.flags, reversed, keep_w, G, S, jc, sh);
   if (!fin) return;
+  lrr_tl(9, 0);
   if (!lrr_pair_done(a, a.ndir)) return;
   lrr_tl(2, 2);
   lrr_solve(a.d[a.src].sc, a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, a.flags, a.dof, a.estimate_parameters);
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
 }
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
   // two blocks per SM at most: the last block sums one row of 108 moments per block before it can solve
-  dim3 grid(resident_width(k_accumulate, LRR_THREADS, a.ndir, 4LL * maxM(a)), a.ndir);
+  dim3 grid(resident_width(k_accumulate, LRR_THREADS, a.ndir, maxM(a)), a.ndir);   // one match per lane and trip
   lrr_launch_pdl(k_accumulate, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 

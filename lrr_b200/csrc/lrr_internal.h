@@ -78,7 +78,12 @@ struct Scal {
   double sum_loc[3], sum_r2;                 // match phase
   double sum_q[3], n_unique, sum_rad_from;   // norm1
   double sum_rad_to;                         // norm2
-  double scale; int scale_estimated, pad1;
+  double scale; int scale_estimated;
+  // 1 = some match of this direction was (re)written since its normalisation was last computed.  Set by the finalizers of the
+  // match kernels (the certificate pass only when it left work over), cleared by k_norm2: while every query of the source
+  // direction is kept by its certificate the match set — all the normalisation depends on for an affine estimate — is unchanged,
+  // and k_norm1 / k_norm2 leave at entry (see do_estimate, lrr_capi.cu).
+  int norm_dirty;
   double n_nonzero, sel_below[2];
   double G, S;
   double res_sum_r2, res_sum_wr2, res_sum_w, res_sum_wr, res_count;   // resid phase
@@ -200,8 +205,8 @@ void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches);
 bool lrr_match_cert_usable(const EstArgs& a);
 void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_tile_set_timeline(unsigned long long* p);
-void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches);
-void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);
+void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);
 void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches);   // cdcl estimate_LS_backward: normalisation over the merged list
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches);

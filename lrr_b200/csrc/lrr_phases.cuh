@@ -215,6 +215,7 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
     lrr_tl(0, 2);
     if (threadIdx.x == 0) {
       Scal* sc = a.sc; sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
+      sc->norm_dirty = 1;
       if (counter) *counter = 0;
     }
   }
@@ -293,6 +294,7 @@ __device__ void lrr_phase_norm2(const Scope& scope, const DirArgs& a, Scal* othe
     if (threadIdx.x == 0) {
       sc->sum_rad_to = sh.out[0];
       sc->rto = sh.out[0] / sc->n_unique;
+      sc->norm_dirty = 0;
       if (other) {   // cdcl_normalize_matches_known with the centres and radii swapped (cdcl sym :470-478)
         for (int d = 0; d < 3; ++d) { other->cfrom[d] = sc->cto[d]; other->cto[d] = sc->cfrom[d]; }
         other->rfrom = sc->rto; other->rto = sc->rfrom;
@@ -582,54 +584,71 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
   // division, far inside the 1e-5 gate, and it removes six fp64 divisions (~40 instructions each) per match
   const double cf0 = sc->cfrom[0], cf1 = sc->cfrom[1], cf2 = sc->cfrom[2], irf = 1.0 / sc->rfrom;
   const double ct0 = sc->cto[0], ct1 = sc->cto[1], ct2 = sc->cto[2], irt = 1.0 / sc->rto;
-  const int j = threadIdx.x & 3;
+  const int lane = threadIdx.x & 31, j = lane & 3, qbase = lane & ~3;
   double acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-  // (the neighbour slot of the NEXT match of this quad is fetched one trip ahead: the dependent chain per trip is then one gather
-  //  hop — position and projector of the neighbour — instead of two)
-  const int k0 = scope.first() >> 2, kstep = scope.stride() >> 2;
-  int s_next = k0 < a.M ? a.sidx[k0] : -1;
-  for (int k = k0; k < a.M; k += kstep) {
+  // Every LANE loads one match per trip (consecutive lanes = consecutive k: coalesced streams, one gather hop behind sidx, which
+  // is fetched a trip ahead), finishes its weight and forms (w, x~, P, P b^); the four lanes of a quad then pass their four
+  // matches round by shuffle and each adds row x~_j of all four.  Against "the four lanes of a quad load the same match":
+  // four times the matches in flight per warp for the same registers, a quarter of the dependent trips.
+  const int wfirst = scope.first() - lane, wstride = scope.stride();
+  int s_next = (wfirst + lane) < a.M ? a.sidx[wfirst + lane] : -1;
+  for (int base = wfirst; base < a.M; base += wstride) {
+    const int k = base + lane;
     const int s = s_next;
-    if (k + kstep < a.M) s_next = a.sidx[k + kstep];
-    double w = a.w[k];                             // Beaton-Tukey weight / scale^2
-    if (strength) {
-      const double g = a.gkey[k];
-      if (g >= 0.0 || (flags & LRR_F_ICP)) w *= g; // only where w != 0   (cdcl :839-848); cdcl_estimation_ICP: every match
-      w *= invG;                                   // every match         (cdcl :857-860, Q13)
-    }
-    if (spatial) { w *= a.skey[k]; w *= invS; }    // cdcl :985-1002
-    // cdcl symmetric: the re-weighted reversed constraints are clones that get erased again (Q11), the
-    // backward originals keep their Beaton-Tukey weights
-    if (j == 0 && !keep_w) a.w[k] = w;
-    if (s < 0) continue;
-    if (skip_small && w < 1e-4) continue;          // rrl sym :463,:571
-    const int i = lrr_from_index(a, k);
-    double px, py, pz; lrr_from_loc(a, sc, mapped, i, px, py, pz);
-    px = (px - cf0) * irf; py = (py - cf1) * irf; pz = (pz - cf2) * irf;
-    const double4 q4 = lrr_ld_pos4(a.to.grid.pos4 + s);
-    const double qx = (q4.x - ct0) * irt, qy = (q4.y - ct1) * irt, qz = (q4.z - ct2) * irt;
-    double P[6], xt[4], b0, b1, b2;
-    if (!reversed) {
-      lrr_ld_P6(a.to.rec, s, P);
-      xt[0] = px - jc[0]; xt[1] = py - jc[1]; xt[2] = pz - jc[2]; b0 = qx; b1 = qy; b2 = qz;
-    } else {   // J at the to_ location, projector and right-hand side of the from_ feature
+    s_next = (k + wstride) < a.M ? a.sidx[k + wstride] : -1;
+    double w = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, P[6] = {0, 0, 0, 0, 0, 0}, pb0 = 0.0, pb1 = 0.0, pb2 = 0.0;
+    if (k < a.M) {
+      w = a.w[k];                                    // Beaton-Tukey weight / scale^2
+      if (strength) {
+        const double g = a.gkey[k];
+        if (g >= 0.0 || (flags & LRR_F_ICP)) w *= g; // only where w != 0   (cdcl :839-848); cdcl_estimation_ICP: every match
+        w *= invG;                                   // every match         (cdcl :857-860, Q13)
+      }
+      if (spatial) { w *= a.skey[k]; w *= invS; }    // cdcl :985-1002
+      // cdcl symmetric: the re-weighted reversed constraints are clones that get erased again (Q11), the
+      // backward originals keep their Beaton-Tukey weights
+      if (!keep_w) a.w[k] = w;
+      if (s < 0 || (skip_small && w < 1e-4)) w = 0.0;   // contributes nothing (rrl sym :463,:571)
+      else {
+        const int i = lrr_from_index(a, k);
+        double px, py, pz; lrr_from_loc(a, sc, mapped, i, px, py, pz);
+        px = (px - cf0) * irf; py = (py - cf1) * irf; pz = (pz - cf2) * irf;
+        const double4 q4 = lrr_ld_pos4(a.to.grid.pos4 + s);
+        const double qx = (q4.x - ct0) * irt, qy = (q4.y - ct1) * irt, qz = (q4.z - ct2) * irt;
+        double b0, b1, b2;
+        if (!reversed) {
+          lrr_ld_P6(a.to.rec, s, P);
+          x0 = px - jc[0]; x1 = py - jc[1]; x2 = pz - jc[2]; b0 = qx; b1 = qy; b2 = qz;
+        } else {   // J at the to_ location, projector and right-hand side of the from_ feature
 #pragma unroll
-      for (int p = 0; p < 6; ++p) P[p] = __ldg(a.fP6 + (size_t)p * a.n_in + i);
-      xt[0] = qx - jc[0]; xt[1] = qy - jc[1]; xt[2] = qz - jc[2]; b0 = px; b1 = py; b2 = pz;
+          for (int p = 0; p < 6; ++p) P[p] = __ldg(a.fP6 + (size_t)p * a.n_in + i);
+          x0 = qx - jc[0]; x1 = qy - jc[1]; x2 = qz - jc[2]; b0 = px; b1 = py; b2 = pz;
+        }
+        pb0 = P[0] * b0 + P[1] * b1 + P[2] * b2;
+        pb1 = P[1] * b0 + P[3] * b1 + P[4] * b2;
+        pb2 = P[2] * b0 + P[4] * b1 + P[5] * b2;
+      }
     }
-    xt[3] = 1.0;
-    const double wxa = w * xt[j];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const double tt = wxa * xt[b];
+    for (int m = 0; m < 4; ++m) {
+      const int src = qbase + m;
+      const double wm = __shfl_sync(0xffffffffu, w, src);
+      const double xm[4] = {__shfl_sync(0xffffffffu, x0, src), __shfl_sync(0xffffffffu, x1, src), __shfl_sync(0xffffffffu, x2, src), 1.0};
+      double Pm[6];
 #pragma unroll
-      for (int p = 0; p < 6; ++p) acc[b * 6 + p] += tt * P[p];
+      for (int p = 0; p < 6; ++p) Pm[p] = __shfl_sync(0xffffffffu, P[p], src);
+      const double c0 = __shfl_sync(0xffffffffu, pb0, src), c1 = __shfl_sync(0xffffffffu, pb1, src), c2 = __shfl_sync(0xffffffffu, pb2, src);
+      const double wxa = wm * (j == 0 ? xm[0] : (j == 1 ? xm[1] : (j == 2 ? xm[2] : 1.0)));
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double tt = wxa * xm[b];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) acc[b * 6 + p] += tt * Pm[p];
+      }
+      acc[24] += wxa * c0; acc[25] += wxa * c1; acc[26] += wxa * c2;
     }
-    acc[24] += wxa * (P[0] * b0 + P[1] * b1 + P[2] * b2);
-    acc[25] += wxa * (P[1] * b0 + P[3] * b1 + P[4] * b2);
-    acc[26] += wxa * (P[2] * b0 + P[4] * b1 + P[5] * b2);
   }
   lrr_tl(2, 1);
   const bool fin = scope.template reduce<27, 4>(acc, sh.out, sh.tmp);
@@ -703,6 +722,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   if (tid < 15) { sF[tid] = __ldcg(&F->A[0] + tid); sFg[tid] = __ldcg(&F->Ag[0] + tid); if (B) sB[tid] = __ldcg(&B->A[0] + tid); }
   else if (tid >= 32 && tid < 40) { sFn[tid - 32] = __ldcg(&F->cfrom[0] + (tid - 32)); if (B) sBn[tid - 32] = __ldcg(&B->cfrom[0] + (tid - 32)); }
   __syncthreads();
+  lrr_tl(9, 1);
   if (sim2d) {
     // similarity2d: J = [x -y 1 0; y x 0 1] (cdcl_trans_similarity2d.cxx:150-164), b = q.  J[d][i] = sum_a x~_a E[a][d][i] with
     // E[0][0][0] = E[1][1][0] = 1, E[1][0][1] = -1, E[0][1][1] = 1, E[3][0][2] = E[3][1][3] = 1
@@ -782,7 +802,9 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   for (int e = tid; e < dof * dof; e += blockDim.x) { F->AtA[e] = AtA[e]; Msh[e] = AtA[e]; }
   if (tid < dof) F->Atb[tid] = Atb[tid];
   __syncthreads();
+  lrr_tl(9, 2);
   bool ok = lrr_gj_inverse(dof, Msh, inv);
+  lrr_tl(9, 3);
   if (!ok) {   // singular or indefinite normal matrix: pseudo-inverse like vnl_svd::inverse (slow path, one thread)
     if (tid == 0) { lrr_svd_inverse<12>(dof, AtA, inv); F->status |= LRR_ST_SINGULAR; }
     __syncthreads();
@@ -803,6 +825,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
     F->cov[e] = v;
   }
   __syncthreads();
+  lrr_tl(10, 0);
   if (tid == 0) {
     double A[9], t[3], c[3];
     const double cm[3] = {sFn[0], sFn[1], sFn[2]}, cf[3] = {sFn[4 + 0], sFn[4 + 1], sFn[4 + 2]};
@@ -917,6 +940,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
     }
   }
   __syncthreads();
+  lrr_tl(10, 1);
   if (tid < 15) { (&F->A[0])[tid] = sF[tid]; if (B) (&B->A[0])[tid] = sB[tid]; }
   if (B && estimate_parameters) for (int e = tid; e < dof * dof; e += blockDim.x) B->cov[e] = 0.0;   // inverse(): fresh covariance
   __syncthreads();

@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
     lrr_tl(0, 2);
     if (threadIdx.x == 0) {
       Scal* sc = d.sc;
+      sc->norm_dirty = 1;
       if (lrr_dir_certified(d)) {   // the certificate pass wrote its share of the sums
         sc->sum_loc[0] += s_out[0]; sc->sum_loc[1] += s_out[1]; sc->sum_loc[2] += s_out[2]; sc->sum_r2 += s_out[3];
         *d.todo_count = 0;
@@ -424,7 +425,11 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS) k_match_cert(const __grid_co
   lrr_tl(5, 1);
   const GridScope scope = lrr_scope_of(a, dir);
   if (scope.reduce<4>(acc, s_out, s_tmp)) {
-    if (threadIdx.x == 0) { Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3]; }
+    if (threadIdx.x == 0) {
+      Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3];
+      // every query kept <=> nothing on the work list (this block is the last one of the direction: all appends are visible)
+      if (lrr_dir_certified(d) && (*reinterpret_cast<volatile int*>(d.todo_count) > 0 || *reinterpret_cast<volatile int*>(d.hq_count) > 0)) sc->norm_dirty = 1;
+    }
   }
   lrr_tl(5, 3);
 }

@@ -55,3 +55,11 @@ if ph.sum() > 0:
     print("tile kernel, warp-time per chunk (us): " + ", ".join(f"{n} {v / 1.965e3 / max(c[0], 1):.2f}" for n, v in zip(names, ph)))
 cc = out.reshape(NK, 2048 * 4)[3][16:24].astype(np.int64)
 print("certificate pass: no previous neighbour", cc[0], "| no certificate", cc[1], "| certificate too weak for the motion", cc[2])
+
+# serial tail of k_accumulate (marks of the finalizer blocks only): reduce returned / pair complete / scalars staged / normal
+# equations assembled / inverse / covariance / transform chain / end
+t2, t9, t10 = tl[2], tl[9], tl[10]
+if (t9 > 0).any():
+    base = tl[2][:, 1][tl[2][:, 1] > 0].max()   # last block's loop end
+    g = lambda arr, slot: (arr[:, slot][arr[:, slot] > 0].max() - base) / 1e3 if (arr[:, slot] > 0).any() else float("nan")
+    print(f"accumulate tail (us after the last loop end): reduce done {g(t9,0):.1f} | pair done {g(t2,2):.1f} | staged {g(t9,1):.1f} | AtA {g(t9,2):.1f} | inverse {g(t9,3):.1f} | cov {g(t10,0):.1f} | transforms {g(t10,1):.1f} | end {g(t2,3):.1f}")

@@ -238,3 +238,40 @@ def test_certificates_with_far_queries_and_near_ties(gpu_lib, oracle_lib):
             flips += int(np.count_nonzero(prev != res[1][0][1]))
         prev = res[1][0][1]
     assert flips > 1000   # the mirrored slabs did flip the neighbours of the near-tied queries
+
+
+def test_normalisation_is_recomputed_whenever_a_match_changes(gpu_lib, oracle_lib):
+    """k_norm1 / k_norm2 leave at entry while every query of the source direction is kept by its certificate (the match set, which
+    is all the normalisation of an affine estimate depends on, is unchanged).  Run far past convergence (skips active), then jump
+    the transform (matches change, the normalisation must be recomputed), then converge again: transform, covariance and index
+    sets must follow the oracle — which recomputes everything every time — at every step, far inside the 1e-5 gate."""
+    pair = synth.make_pair(77, 24000, 22000, size=150.0)
+    A0, t0, c0 = pair["init"]
+    ests = []
+    for lib in (gpu_lib, oracle_lib):
+        ctx = lib.context()
+        est = ctx.estimator("rrl_sym", ctx.upload(pair["moving"]), ctx.upload(pair["fixed"]), 12)
+        est.set_transform(A0, t0, c0)
+        ests.append(est)
+    g, o = ests
+
+    def step(it, tol):
+        cg, co = g.one_iteration(it), o.one_iteration(it)
+        assert cg == co, it
+        for d in (0, 1):
+            assert np.array_equal(g.get_matches(d)[1], o.get_matches(d)[1]), (it, d)
+        G, O = g.get_transform(0), o.get_transform(0)
+        assert rel(G["A"], O["A"]) < tol and rel(G["t"], O["t"]) < tol and rel(G["cov"], O["cov"]) < tol, (it, rel(G["A"], O["A"]), rel(G["cov"], O["cov"]))
+
+    for it in range(45):
+        step(it, 1e-8)
+    assert g.state().finest_level == 1
+    # jump: a rotation of ~0.5 degree and 1 mm, both estimators restart from the same transform (set_transform resets the ramp)
+    T = o.get_transform(0)
+    w = np.array([0.004, -0.006, 0.008])
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    A1 = (np.eye(3) + K) @ T["A"]; t1 = T["t"] + np.array([1.0, -0.7, 0.4])
+    for est in ests:
+        est.set_transform(A1, t1, T["c"])
+    for it in range(40):
+        step(it, 1e-8)
