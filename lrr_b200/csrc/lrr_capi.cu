@@ -2,6 +2,7 @@
 // iteration control (ramp / oscillation state machine of the symmetric estimators), driving the sm_100a
 // kernels of lrr_grid.cu, lrr_icp.cu, lrr_select.cu, lrr_metrics.cu and lrr_batch.cu.
 // There is NO CPU fallback: every entry point that computes needs a CUDA device.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -89,6 +90,12 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
   ok = ok && dmalloc(&ctx->muse_table, 4 * 32) == cudaSuccess;
   ok = ok && dmalloc(&ctx->scratch_d, 1024) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&ctx->pinned, 2 * sizeof(Scal) + 4096) == cudaSuccess;
+  if (ok && getenv("LRR_NO_MAILBOX") == nullptr) {   // result mailbox: mapped pinned memory the resid kernel writes directly (optional: plain copies otherwise)
+    if (cudaHostAlloc((void**)&ctx->mailbox, 2 * 512 * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
+      memset(ctx->mailbox, 0, 2 * 512 * sizeof(double));
+      if (cudaHostGetDevicePointer((void**)&ctx->mailbox_dev, ctx->mailbox, 0) != cudaSuccess) { cudaFreeHost(ctx->mailbox); ctx->mailbox = nullptr; ctx->mailbox_dev = nullptr; }
+    } else { ctx->mailbox = nullptr; cudaGetLastError(); }
+  }
   ctx->sort.keys2 = nullptr; ctx->sort.hist = nullptr; ctx->sort.cap = 0; ctx->sort_keys = nullptr;
   if (!ok) { cudaGetLastError(); lrr_ctx_destroy(ctx); return LRR_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) {
@@ -110,6 +117,7 @@ extern "C" void lrr_ctx_destroy(lrr_ctx* ctx) {
   dfree(ctx->muse_table); dfree(ctx->scratch_d); dfree(ctx->sort_keys);
   if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -333,6 +341,25 @@ static int pull_scal(lrr_est* e, int mask) {
   return LRR_OK;
 }
 static int dmask(const lrr_est* e) { return e->sym() ? 3 : 1; }
+
+// Read the scalars the resid kernel posted into the mailbox (sequence number seq): poll, no copy, no stream synchronisation.
+// Falls back to the plain copies when the stream has drained without the number showing up (cannot happen) or reports an error.
+static int pull_scal_mailbox(lrr_est* e, int mask, unsigned long long seq) {
+  lrr_ctx* ctx = e->ctx;
+  volatile unsigned long long* flag[2] = {reinterpret_cast<volatile unsigned long long*>(ctx->mailbox + 500),
+                                          reinterpret_cast<volatile unsigned long long*>(ctx->mailbox + 512 + 500)};
+  auto ready = [&]() { for (int d = 0; d < 2; ++d) if ((mask & (1 << d)) && *flag[d] != seq) return false; return true; };
+  for (unsigned long long spins = 1; !ready(); ++spins) {
+    if ((spins & 0xfff) == 0) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q == cudaSuccess) { if (ready()) break; return pull_scal(e, mask); }
+      if (q != cudaErrorNotReady) { ctx->err = cudaGetErrorString(q); return LRR_ERR_CUDA; }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  for (int d = 0; d < 2; ++d) if (mask & (1 << d)) memcpy(&e->h[d], ctx->mailbox + 512 * d, kScalHead);
+  return LRR_OK;
+}
 
 static void inverse_trans(const Scal& f, Scal& b) {   // cdcl_trans_affine::inverse / rigid3d::inverse
   double invA[9]; lrr_inv3(f.A, invA);
@@ -690,8 +717,15 @@ static int estimate_and_pull(lrr_est* e, int resid_mask) {
   bool fresh0[2], se0[2];
   for (int d = 0; d < 2; ++d) { fresh0[d] = e->d[d].weights_fresh; se0[d] = e->d[d].scale_estimated; }
   int rc = do_estimate(e, 0, 1); if (rc != LRR_OK) return rc;
-  { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
-  if ((rc = pull_scal(e, mask)) != LRR_OK) return rc;
+  static_assert(kScalHead % 8 == 0 && kScalHead / 8 <= 500, "Scal head does not fit a mailbox slot");
+  if (ctx->mailbox_dev) {
+    const unsigned long long seq = ++ctx->mailbox_seq;
+    { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches, ctx->mailbox_dev, seq, mask, (int)(kScalHead / 8)); }
+    if ((rc = pull_scal_mailbox(e, mask, seq)) != LRR_OK) return rc;
+  } else {
+    { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
+    if ((rc = pull_scal(e, mask)) != LRR_OK) return rc;
+  }
   bool miss = false;
   for (int d = 0; d < nd; ++d) miss = miss || (e->h[d].status & LRR_ST_SELECT_MISS);
   if (!miss) { if (e->window_holdoff == 0) e->window_backoff = 0; return LRR_OK; }

@@ -23,6 +23,7 @@ struct lrr_ctx {
   double* muse_table = nullptr;
   double* scratch_d = nullptr;
   void* pinned = nullptr;
+  double* mailbox = nullptr; double* mailbox_dev = nullptr; unsigned long long mailbox_seq = 0;   // result mailbox (mapped pinned, lrr_icp.cu)
   // instrumentation: CUDA-event timing per phase kernel (lrr_ctx_set_profiling)
   bool profiling = false;
   struct Span { int phase; cudaEvent_t a, b; };

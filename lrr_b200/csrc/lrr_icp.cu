@@ -430,22 +430,47 @@ void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
   lrr_launch_pdl(k_accumulate, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
-__global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0) {
+// Result MAILBOX: one_iteration returns `converged`, so the host reads ~1.6 kB of scalars per direction after every iteration.
+// Instead of two device-to-host copies behind the kernel and a stream synchronisation, the block that finishes the residuals
+// writes the head of each Scal into mapped pinned host memory, fences at system scope and publishes a sequence number; the host
+// polls that number (pull_scal_mailbox, lrr_capi.cu).  Slot d = mbox + 512 d doubles, sequence number at [500].
+#define LRR_MBOX_STRIDE 512
+#define LRR_MBOX_FLAG 500
+__device__ __forceinline__ void lrr_mailbox_post(const EstArgs& a, int dir_mask, double* mbox, unsigned long long seq, int nhead) {
+  __syncthreads();   // the finalizer's scalar writes are visible to the block
+  for (int d = 0; d < a.ndir; ++d) if (dir_mask & (1 << d)) {
+    const double* src = reinterpret_cast<const double*>(a.d[d].sc);
+    for (int i = threadIdx.x; i < nhead; i += blockDim.x) mbox[d * LRR_MBOX_STRIDE + i] = __ldcg(src + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < a.ndir; ++d) if (dir_mask & (1 << d)) *reinterpret_cast<volatile unsigned long long*>(mbox + d * LRR_MBOX_STRIDE + LRR_MBOX_FLAG) = seq;
+    __threadfence_system();
+  }
+}
+__global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0, double* mbox, unsigned long long seq, int pull_mask, int nhead) {
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
   const int dir = dir0 + blockIdx.y;
-  if (a.d[dir].sc->status & LRR_ST_SELECT_MISS) return;   // the estimate was not committed: keep the residuals of the match for the rerun
+  // one row of blocks: its finalizer posts every direction the host wants; two rows: each finalizer posts its own direction
+  const int post = gridDim.y == 2 ? (pull_mask & (1 << dir)) : pull_mask;
+  if (a.d[dir].sc->status & LRR_ST_SELECT_MISS) {   // the estimate was not committed: keep the residuals of the match for the rerun
+    if (mbox && blockIdx.x == 0) lrr_mailbox_post(a, post, mbox, seq, nhead);
+    return;
+  }
   lrr_tl(8, 0);
-  lrr_phase_resid(lrr_scope(a, dir), a.d[dir], sh);
+  const bool fin = lrr_phase_resid(lrr_scope(a, dir), a.d[dir], sh);
+  if (fin && mbox) lrr_mailbox_post(a, post, mbox, seq, nhead);
   lrr_tl(8, 3);
 }
-void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches) {
+void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches, double* mbox, unsigned long long seq, int pull_mask, int nhead) {
   if (dir_mask == 3) {
     dim3 grid(resident_width(k_resid, LRR_THREADS, 2, maxM(a)), 2);
-    lrr_launch_pdl(k_resid, grid, dim3(LRR_THREADS), 0, st, a, 0); ++*launches;
+    lrr_launch_pdl(k_resid, grid, dim3(LRR_THREADS), 0, st, a, 0, mbox, seq, pull_mask, nhead); ++*launches;
   } else {
     const int d = (dir_mask == 2) ? 1 : 0;
-    lrr_launch_pdl(k_resid, dim3(nblk_for(a.d[d].M)), dim3(LRR_THREADS), 0, st, a, d); ++*launches;
+    lrr_launch_pdl(k_resid, dim3(nblk_for(a.d[d].M)), dim3(LRR_THREADS), 0, st, a, d, mbox, seq, pull_mask, nhead); ++*launches;
   }
 }
 

@@ -211,7 +211,8 @@ void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches); 
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches);
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches);
-void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches);
+void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches, double* mbox = nullptr, unsigned long long seq = 0,
+                 int pull_mask = 0, int nhead = 0);   // mbox: result mailbox in mapped host memory (lrr_icp.cu)
 void lrr_k_angles(const DirArgs& a, int flags, int which, double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
 void lrr_k_transfer_cov(const DirArgs& a, int dof, double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
 void lrr_k_resid_keys(const DirArgs& a, double* keys, cudaStream_t st, long long* launches);

@@ -949,7 +949,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
 // ---- RESID: residuals of the current matches under the current transform: RMS_error (cdcl :196-230,
 // rrl :211-241 Q1), weighted_error (cdcl :236-268, rrl :247-276), scale-from-weights sums (cdcl :698-701) ----
 template <class Scope, class SH>
-__device__ void lrr_phase_resid(const Scope& scope, const DirArgs& a, SH& sh) {
+__device__ bool lrr_phase_resid(const Scope& scope, const DirArgs& a, SH& sh) {
   Scal* sc = a.sc;
   const int mapped = sc->from_mapped;
   double A[9], t[3], c[3];
@@ -972,11 +972,13 @@ __device__ void lrr_phase_resid(const Scope& scope, const DirArgs& a, SH& sh) {
     acc[0] += r2; acc[1] += w * r2; acc[2] += w; acc[3] += sqrt(r2) * w; acc[4] += 1.0;
   }
   lrr_tl(8, 1);
-  if (scope.template reduce<5>(acc, sh.out, sh.tmp)) {
+  const bool fin = scope.template reduce<5>(acc, sh.out, sh.tmp);
+  if (fin) {
     if (threadIdx.x == 0) {
       sc->res_sum_r2 = sh.out[0]; sc->res_sum_wr2 = sh.out[1]; sc->res_sum_w = sh.out[2]; sc->res_sum_wr = sh.out[3];
       sc->res_count = sh.out[4];
     }
   }
   scope.phase_end();
+  return fin;
 }
