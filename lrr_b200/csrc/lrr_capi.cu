@@ -235,7 +235,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
   CK(dmalloc(&d.hq_k, 3 * cap + 1)); d.hq_s = d.hq_k + cap; d.hq_o = d.hq_k + 2 * cap; d.hq_count = d.hq_k + 3 * cap;
   CK(dmalloc(&d.prev_s, cap)); CK(dmalloc(&d.proc, cap)); CK(dmalloc(&d.proc_mark, 2 * cap));
   CK(dmalloc(&d.hq_best, cap)); CK(cudaMemsetAsync(d.hq_count, 0, sizeof(int), ctx->stream));
-  CK(dmalloc(&d.proof, cap ? cap : 1));
+  CK(dmalloc(&d.proof, cap ? cap : 1)); CK(dmalloc(&d.pos_of, cap ? cap : 1)); CK(dmalloc(&d.cprev, cap ? cap : 1)); CK(dmalloc(&d.tf, 3 * (cap ? cap : 1)));
   {  // tiles of the from-features: cubes of LRR_TILE_T cells of the to-grid over the bounding box of the parent set
     const GridDev& gf = from_all->dev.grid; const GridDev& gt = to_all->dev.grid;
     double edge = LRR_TILE_T * gt.h;
@@ -258,7 +258,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
   return LRR_OK;
 }
 static void dir_free(lrr_dir& d) {
-  dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark); dfree(d.proof);
+  dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark); dfree(d.proof); dfree(d.pos_of); dfree(d.cprev); dfree(d.tf);
   dfree(d.tile_cnt); dfree(d.tile_start); dfree(d.chunk_start); dfree(d.tile_of); dfree(d.chunk_tab); dfree(d.todo); dfree(d.todo_count);
 }
 static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
@@ -278,8 +278,10 @@ static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t 
   d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false;
   CK(cudaMemsetAsync(d.prev_s, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));   // no search candidates yet
   CK(cudaMemsetAsync(d.proof, 0, sizeof(double4) * (size_t)(n ? n : 1), st));   // ... and no neighbour certificates
+  CK(cudaMemsetAsync(d.cprev, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));
   // processing order of the match phase = tile order (spatially coherent; the finest level stages each tile's cells in shared memory)
   lrr_k_build_tiles(d.fx, d.fy, d.fz, (int)n, d.tgeom, d.tile_cnt, d.tile_start, d.chunk_start, d.tile_of, d.proc_mark, d.chunk_tab, d.proc, st, &ctx->launches);
+  lrr_k_tile_mirror(d.proc, d.fx, d.fy, d.fz, (int)n, d.pos_of, d.tf, st, &ctx->launches);
   return LRR_OK;
 }
 
@@ -297,6 +299,7 @@ static DirArgs dir_args(const lrr_dir& d) {
   a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
   static const bool no_proof = getenv("LRR_NO_PROOF") != nullptr;   // A/B switch for measurements
   a.proof = no_proof ? nullptr : d.proof; a.todo = no_proof ? nullptr : d.todo; a.todo_count = d.todo_count;
+  if (a.proof) { a.pos_of = d.pos_of; a.cprev = d.cprev; a.tfx = d.tf; a.tfy = d.tf + n; a.tfz = d.tf + 2 * n; }
   a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.chunk_tab = (a.proc && d.n_in > 0) ? d.chunk_tab : nullptr; a.nchunks = d.chunk_start; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
   return a;

@@ -128,6 +128,10 @@ struct DirArgs {
   // nearest neighbour, lower bound B on the distance from y0 to every OTHER to-feature} (w <= 0: none).  For a new mapped position
   // y the neighbour is unchanged, without any search, when |y - q_prev| + |y - y0| < B (triangle inequality; lrr_tile.cu).
   double4* proof;
+  // The certificate pass reads everything of a query by its TILE-ORDER position tq (coalesced, no hop through proc): `proof` is
+  // indexed by tq = pos_of[from-feature], tfx/tfy/tfz are the from-locations in tile order and cprev[tq] mirrors prev_s of the
+  // feature at tq (both written by lrr_match_finish only).  null: certificates off.
+  const int* pos_of; const double *tfx, *tfy, *tfz; int* cprev;
   // work list of the staged search when certificates are in use: (chunk, lane mask of the queries the certificate pass could not
   // keep), appended by k_match_cert, drained and re-armed by k_match_tile
   int2* todo; int* todo_count;
@@ -200,6 +204,8 @@ void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // p
 // lrr_tile.cu: tile construction and the shared-memory-staged pass A of the finest level
 void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
                        int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches);
+// tile-order mirrors for the certificate pass: pos_of[proc[tq]] = tq, tf*[tq] = f*[proc[tq]]
+void lrr_k_tile_mirror(const int* proc, const double* fx, const double* fy, const double* fz, int n_in, int* pos_of, double* tf, cudaStream_t st, long long* launches);
 bool lrr_match_tile_usable(const EstArgs& a);
 void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches);
 bool lrr_match_cert_usable(const EstArgs& a);

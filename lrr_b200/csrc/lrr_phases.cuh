@@ -64,9 +64,11 @@ __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, i
                                                  double yy, double yz, int s, double (&acc)[4], int pmode = 0, double bound = 0.0) {
   a.sidx[k] = s;
   a.prev_s[i] = s;   // candidate of this from-feature for the next find_closest
-  if (a.proof) {
-    if (pmode == 2) { double2* pr = reinterpret_cast<double2*>(a.proof + i); pr[0] = make_double2(yx, yy); pr[1] = make_double2(yz, bound); }
-    else if (pmode == 0) reinterpret_cast<double*>(a.proof + i)[3] = 0.0;
+  if (a.proof && pmode != 1) {   // (certificates live at the feature's tile-order position, with a mirror of prev_s: DirArgs::pos_of)
+    const int tq = __ldg(a.pos_of + i);
+    if (pmode == 2) { double2* pr = reinterpret_cast<double2*>(a.proof + tq); pr[0] = make_double2(yx, yy); pr[1] = make_double2(yz, bound); }
+    else reinterpret_cast<double*>(a.proof + tq)[3] = 0.0;
+    a.cprev[tq] = s;
   }
   double r2 = 0.0;
   if (s >= 0) {
@@ -75,6 +77,20 @@ __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, i
     r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
     atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
   }
+  a.r2[k] = r2;
+  a.w[k] = 1.0;   // cdcl :645
+  if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
+  acc[3] += r2;
+}
+
+// a match KEPT by its neighbour certificate (identity order: position k == from-feature k; neighbour slot s, its location q and
+// projector P already loaded): prev_s, its mirror and the certificate stay as they are; the match index, the residual under the new
+// transform, the stamp of the new epoch and the sums are produced
+__device__ __forceinline__ void lrr_match_keep(const DirArgs& a, bool rigid, int k, double x, double y, double z, double yx, double yy,
+                                               double yz, int s, const double4& q, const double (&P)[6], double (&acc)[4]) {
+  a.sidx[k] = s;
+  const double r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
+  atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
   a.r2[k] = r2;
   a.w[k] = 1.0;   // cdcl :645
   if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }

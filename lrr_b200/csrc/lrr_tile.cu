@@ -142,6 +142,19 @@ void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int
   (void)tmp;
 }
 
+__global__ void k_tile_mirror(const int* __restrict__ proc, const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz, int n,
+                              int* __restrict__ pos_of, double* __restrict__ tf) {
+  const int tq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tq >= n) return;
+  const int k = proc[tq];
+  pos_of[k] = tq;
+  tf[tq] = fx[k]; tf[(size_t)n + tq] = fy[k]; tf[2 * (size_t)n + tq] = fz[k];
+}
+void lrr_k_tile_mirror(const int* proc, const double* fx, const double* fy, const double* fz, int n_in, int* pos_of, double* tf, cudaStream_t st, long long* launches) {
+  if (n_in <= 0) return;
+  k_tile_mirror<<<(n_in + 255) / 256, 256, 0, st>>>(proc, fx, fy, fz, n_in, pos_of, tf); ++*launches;
+}
+
 // ---- search over the staged box ---------------------------------------------------------------------------------
 // Every lane scans ALL staged points of the chunk's box (broadcast shared-memory reads, no per-lane control flow, four
 // independent distance chains in flight).  The result is the exact neighbour iff the ball of the found distance lies
@@ -376,7 +389,10 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
 // staged search through the work list.  The result is the exact neighbour either way (bit-exact index sets vs the oracle).
 // One warp per chunk, no shared-memory staging: full occupancy, coalesced along the tile order.
 #define LRR_CERT_THREADS 256
-__global__ void __launch_bounds__(LRR_CERT_THREADS) k_match_cert(const __grid_constant__ EstArgs a) {
+#ifndef LRR_CERT_MINBLK
+#define LRR_CERT_MINBLK 3   // 79 registers, no spills: measured 95.8 us per iteration against 99.7 at 4 blocks per SM (64 registers, 144 B spilled)
+#endif
+__global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cert(const __grid_constant__ EstArgs a) {
   lrr_pdl_enter();
   __shared__ double s_T[15];
   __shared__ double s_out[8], s_tmp[8 * (LRR_CERT_THREADS / 32)];
@@ -393,33 +409,40 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS) k_match_cert(const __grid_co
     const int lane = threadIdx.x & 31;
     const int nchunks = __ldg(d.nchunks);
     const int wpb = LRR_CERT_THREADS / 32;
-    for (int ch = blockIdx.x * wpb + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * wpb) {
-      const int2 qq = __ldg(d.chunk_tab + ch);
+    // per query: one hop for everything at its tile-order position (neighbour, certificate, location, match position), one hop for
+    // the neighbour's location and projector (both issued before the certificate is checked), then the stores
+    const int cstep = gridDim.x * wpb;
+    int ch = blockIdx.x * wpb + (threadIdx.x >> 5);
+    int2 qq = ch < nchunks ? __ldg(d.chunk_tab + ch) : make_int2(0, 0);
+    while (ch < nchunks) {
+      const int chn = ch + cstep;
+      const int2 qqn = chn < nchunks ? __ldg(d.chunk_tab + chn) : make_int2(0, 0);   // (the next chunk's bounds are fetched a chunk ahead)
       const int tq = qq.x + lane;
       const bool valid = tq < qq.y;
       bool kept = false;
       if (valid) {
         const int k = __ldg(d.proc + tq);
-        // everything indexed by k in flight together, then everything indexed by the previous neighbour
-        const int sp = d.prev_s[k];
-        const double2* pr = reinterpret_cast<const double2*>(d.proof + k);
+        const int sp = d.cprev[tq];
+        const double2* pr = reinterpret_cast<const double2*>(d.proof + tq);
         const double2 p0 = __ldcg(pr), p1 = __ldcg(pr + 1);
-        const double x = __ldg(d.fx + k), y = __ldg(d.fy + k), z = __ldg(d.fz + k);
+        const double x = __ldg(d.tfx + tq), y = __ldg(d.tfy + tq), z = __ldg(d.tfz + tq);
         if (sp >= 0 && p1.y > 0.0) {
+          const double4 q = lrr_ld_pos4(g.pos4 + sp);
+          double P[6]; lrr_ld_P6(d.to.rec, sp, P);
           double yx, yy, yz;
           lrr_map_exact(A, tt, cc, x, y, z, yx, yy, yz);
-          const double4 q = lrr_ld_pos4(g.pos4 + sp);
           const double dq = sqrt(lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z));
           const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
           const double dm = sqrt(ex * ex + ey * ey + ez * ez);
           // (1e-9 relative + slack covers the rounding of the square roots and sums; B itself was rounded down when written)
-          if ((dq + dm) * (1.0 + 1e-9) + slack < p1.y) { lrr_match_finish(d, rigid, k, k, x, y, z, yx, yy, yz, sp, acc, 1); kept = true; }
+          if ((dq + dm) * (1.0 + 1e-9) + slack < p1.y) { lrr_match_keep(d, rigid, k, x, y, z, yx, yy, yz, sp, q, P, acc); kept = true; }
           if (kept && g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + 7, 1ull);   // development counter (scripts/timeline.py)
           if (!kept && g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + 18, 1ull);
         } else if (g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + (sp < 0 ? 16 : 17), 1ull);
       }
       const unsigned int rest = __ballot_sync(0xffffffffu, valid && !kept);
       if (rest && lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); }
+      ch = chn; qq = qqn;
     }
   }
   lrr_tl(5, 1);
