@@ -426,6 +426,10 @@ def run_b200(args, rank, world, local_rank):
         by = ndirs * (pm_ * M + pt_ * N)
         us = 1e3 * ms / cnt
         per_phase[name] = {"us_per_launch": us, "launches": cnt, "algorithmic_bytes": by, "gbs": by / (us * 1e-6) / 1e9 if us > 0 else None}
+        if name in ("norm1", "norm2") and os.environ.get("LRR_NO_NORM_SKIP") is None and os.environ.get("LRR_NO_PROOF") is None:
+            # steady state: every query is kept by its certificate, the match set — all the normalisation depends on — is unchanged,
+            # and the launch leaves at entry (Scal::norm_dirty): no bytes are moved, the time is the launch itself
+            per_phase[name].update({"algorithmic_bytes": 0, "gbs": None, "note": "leaves at entry while no match changed (steady state)"})
     d = per_phase.get(dom, {"gbs": 0, "us_per_launch": 0, "algorithmic_bytes": 0})
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bench.py cannot run under a profiler)
     traffic, traffic_src = None, None
