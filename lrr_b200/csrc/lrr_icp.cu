@@ -315,7 +315,7 @@ struct WeightExtra { int scale_mode[2]; double scale_in[2]; };
 __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex) {
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
-  __shared__ double sh_cand[LRR_SEL_CAP];
+  __shared__ double sh_cand[LRR_SEL_CAP], sh_cand2[LRR_SEL_CAP];
   const int dir = blockIdx.y;
   const bool merged = (a.flags & LRR_F_MERGED) != 0, window = (a.flags & LRR_F_BRACKET) != 0;
   const int group = merged ? 0 : dir;
@@ -347,8 +347,16 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
     return;
   }
   bool hit = true;
-  if (a.flags & LRR_F_STRENGTH) hit = lrr_sel_window_finish(a.selG[group], nG, bG, sh_cand) && hit;
-  if (LRR_SPATIAL(a.flags)) hit = lrr_sel_window_finish(a.selS[group], nS, bS, sh_cand) && hit;
+  {
+    // both candidate lists into shared memory in one round trip (counts, then keys), then the two exact selections
+    const bool useG = (a.flags & LRR_F_STRENGTH) != 0, useS = LRR_SPATIAL(a.flags);
+    const unsigned int cG = useG ? __ldcg(a.selG[group].cand_count) : 0u, cS = useS ? __ldcg(a.selS[group].cand_count) : 0u;
+    const unsigned int lG = cG <= LRR_SEL_CAP ? cG : 0u, lS = cS <= LRR_SEL_CAP ? cS : 0u;
+    for (unsigned int i = threadIdx.x; i < lG; i += blockDim.x) sh_cand[i] = __ldcg(a.selG[group].cand + i);
+    for (unsigned int i = threadIdx.x; i < lS; i += blockDim.x) sh_cand2[i] = __ldcg(a.selS[group].cand + i);
+    if (useG) hit = lrr_sel_window_finish(a.selG[group], nG, bG, sh_cand, (int)cG) && hit;
+    if (useS) hit = lrr_sel_window_finish(a.selS[group], nS, bS, sh_cand2, (int)cS) && hit;
+  }
   if (threadIdx.x == 0) {
     const double G = (a.flags & LRR_F_STRENGTH) ? *a.selG[group].result : 1.0, S = LRR_SPATIAL(a.flags) ? *a.selS[group].result : 1.0;
     for (int d = 0; d < a.ndir; ++d) {
@@ -403,9 +411,14 @@ void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches) {
   lrr_launch_pdl(k_collect, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
 }
 
-__global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constant__ EstArgs a) {
+// 512 threads, one block per SM (128 registers): half as many partial rows of 108 moments for the last block to add as with two
+// blocks of 256 per SM — its row sum is one batch of loads in flight instead of three
+#ifndef LRR_ACC_THREADS
+#define LRR_ACC_THREADS 512
+#endif
+__global__ void __launch_bounds__(LRR_ACC_THREADS) k_accumulate(const __grid_constant__ EstArgs a) {
   lrr_pdl_enter();
-  __shared__ PhaseShared sh;
+  __shared__ PhaseSharedT<LRR_ACC_THREADS / 32> sh;
   const int dir = blockIdx.y;
   const bool merged = (a.flags & LRR_F_MERGED) != 0, sym = (a.flags & LRR_F_SYM) != 0;
   const int reversed = sym && dir != a.src;
@@ -426,8 +439,8 @@ __global__ void __launch_bounds__(LRR_THREADS) k_accumulate(const __grid_constan
 }
 void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
   // two blocks per SM at most: the last block sums one row of 108 moments per block before it can solve
-  dim3 grid(resident_width(k_accumulate, LRR_THREADS, a.ndir, maxM(a)), a.ndir);   // one match per lane and trip
-  lrr_launch_pdl(k_accumulate, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
+  dim3 grid(resident_width(k_accumulate, LRR_ACC_THREADS, a.ndir, maxM(a)), a.ndir);   // one match per lane and trip
+  lrr_launch_pdl(k_accumulate, grid, dim3(LRR_ACC_THREADS), 0, st, a); ++*launches;
 }
 
 // Result MAILBOX: one_iteration returns `converged`, so the host reads ~1.6 kB of scalars per direction after every iteration.

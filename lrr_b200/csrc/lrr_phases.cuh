@@ -439,10 +439,12 @@ __device__ __forceinline__ void lrr_sel_window_offer(const SelDev& s, double key
   else if (key <= hi) { const unsigned int slot = atomicAdd(s.cand_count, 1u); if (slot < LRR_SEL_CAP) s.cand[slot] = key; }
 }
 // Called by ONE block once every key was offered.  Returns (every thread) true on a hit.
-static __device__ bool lrr_sel_window_finish(const SelDev& s, double n_keys, double below, double* sh_cand) {
+// preloaded >= 0: the caller already copied that many candidates into sh_cand (k_weight loads the lists of both selectors in one
+// round trip before it finishes them one after the other)
+static __device__ bool lrr_sel_window_finish(const SelDev& s, double n_keys, double below, double* sh_cand, int preloaded = -1) {
   __shared__ double s_val; __shared__ int s_hit;
   const long long n = (long long)n_keys;
-  const unsigned int cnt = __ldcg(s.cand_count);
+  const unsigned int cnt = preloaded >= 0 ? (unsigned int)preloaded : __ldcg(s.cand_count);
   if (threadIdx.x == 0) { s_hit = 0; s_val = 0.0; *s.count = n_keys; }
   __syncthreads();
   if (n <= 1) {
@@ -454,7 +456,7 @@ static __device__ bool lrr_sel_window_finish(const SelDev& s, double n_keys, dou
   const bool hit = cnt <= LRR_SEL_CAP && nb <= target && target < nb + (long long)cnt;
   if (hit) {
     const unsigned int rank = (unsigned int)(target - nb);
-    for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) sh_cand[i] = __ldcg(s.cand + i);
+    if (preloaded < 0) for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) sh_cand[i] = __ldcg(s.cand + i);
     __syncthreads();
     if (cnt <= 1024) {
       // exact element of the wanted rank by rank counting (broadcast shared-memory reads, no barriers): the window holds
@@ -699,9 +701,8 @@ static __device__ bool lrr_gj_inverse(int n, double* Msh /* n*n, destroyed */, d
   maxd = s_piv;
   for (int p = 0; p < n; ++p) {
     const double piv = Msh[p * n + p];
-    if (!(piv > 1e-13 * maxd)) { if (tid == 0) s_ok = 0; }
-    __syncthreads();
-    if (!s_ok) break;
+    // (every thread reads the same pivot after the barrier that ended the previous step: the decision is uniform, no flag round trip)
+    if (!(piv > 1e-13 * maxd)) { s_ok = 0; break; }
     // one reciprocal per pivot instead of three divisions per thread (~40 dependent instructions each) on the critical path
     // of every iteration; a rounding apart from the quotient, far inside the 1e-5 gate
     const double ipv = 1.0 / piv;
