@@ -10,7 +10,7 @@ for kind, dof in (("cdcl_fwd", 12), ("rrl_sym", 12), ("cdcl_sym", 12)):
     e = ctx.estimator(kind, mv, fx, dof)
     e.set_flags(True, True); e.set_transform(*pair["init"])
     if "fwd" in kind: e.set_number_points(2200)
-    for it in range(4): e.one_iteration(it)
+    for it in range(10 if kind == "rrl_sym" else 4): e.one_iteration(it)   # rrl_sym: far enough for the certificate pass, the normalisation skip and the mailbox
     for m in ("rms", "weighted", "median", "sheet_angles", "tube_angles"): e.metric(m)
     if "sym" in kind: e.estimate_ls_backward(False); e.transfer_cov(0)
     if kind == "cdcl_fwd":
