@@ -417,7 +417,7 @@ extern "C" void lrr_est_destroy(lrr_est* e) {
 }
 
 extern "C" int lrr_est_set_subsets(lrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   if (!e || !mi || nm < 0) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   int rc = dir_set_subset(ctx, e->d[0], mi, nm);
@@ -438,7 +438,7 @@ static void set_identity_norm(Scal& s) {
 }
 
 extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   if (!e || !A9 || !t3) return LRR_ERR_INVALID;
   if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
@@ -476,7 +476,7 @@ extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const
 }
 
 extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   if (!e) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   e->normalize = normalize != 0; e->strength = wbs != 0;
@@ -488,7 +488,7 @@ extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
 }
 
 extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64_t n) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
@@ -501,7 +501,7 @@ extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64
   return LRR_OK;
 }
 extern "C" int lrr_est_set_shuffle(lrr_est* e, int mode, uint64_t seed) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   if (!e || (mode != LRR_ORDER_FIXED && mode != LRR_ORDER_RESHUFFLE)) return LRR_ERR_INVALID;
   e->shuffle_mode = mode; e->seed = seed;
   for (int d = 0; d < 2; ++d) { e->d[d].shuffle_calls = 0; e->d[d].perm_half = 0; }
@@ -512,7 +512,7 @@ extern "C" int lrr_est_set_initial_scale(lrr_est* e, int dir, double s) {
   e->d[dir].initial_scale = s; return LRR_OK;
 }
 extern "C" int lrr_est_set_number_points(lrr_est* e, int dir, int64_t m, int* at_max) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0) || m < 0) return LRR_ERR_INVALID;
   if (e->icp()) return LRR_ERR_INVALID;   // cdcl_estimation_ICP has no set_number_points (cdcl_estimation_ICP.h)
   lrr_dir& d = e->d[dir];
@@ -597,13 +597,38 @@ static void finish_find_closest(lrr_est* e, const EstArgs& a) {
   for (int d = 0; d < nd; ++d) { e->d[d].matches = a.d[d].M; e->d[d].weights_fresh = true; }
   e->werr_cache_valid = false;
 }
-static int do_find_closest(lrr_est* e) {
+static int do_find_closest(lrr_est* e, bool cert_only = false) {
   lrr_ctx* ctx = e->ctx;
   int rc = prepare_find_closest(e); if (rc != LRR_OK) return rc;
   EstArgs a = est_args(e);
-  { PHASE(PH_MATCH); lrr_k_match(a, ctx->stream, &ctx->launches); }
+  { PHASE(PH_MATCH); lrr_k_match(a, ctx->stream, &ctx->launches, cert_only); }
   finish_find_closest(e, a);
   return LRR_OK;
+}
+
+// Every direction of the next find_closest goes through the certificate pass (finest level, identity order, certificates on):
+// the condition under which Scal::match_left means "queries not kept", and the structural half of the speculative plan.
+static bool cert_path(const lrr_est* e) {
+  static const bool no_proof = getenv("LRR_NO_PROOF") != nullptr, no_tile = getenv("LRR_NO_TILE") != nullptr;
+  if (no_proof || no_tile || e->icp() || e->shuffle_mode == LRR_ORDER_RESHUFFLE) return false;
+  for (int d = 0; d < (e->sym() ? 2 : 1); ++d) {
+    const lrr_dir& D = e->d[d];
+    if (D.n_in <= 0 || D.number_points < D.n_in || D.has_order || D.perm_half) return false;
+  }
+  return true;
+}
+// SPECULATIVE PLAN.  When the last iteration kept every query of every direction (steady_hint, read back with the scalars) the next
+// one is launched as certificate pass -> weight -> accumulate -> resid: the staged search, pass B and both normalisation kernels
+// would find nothing to do (4 launches, ~9 us of a ~92 us iteration).  The bet is verified on the device: weight / collect /
+// accumulate / resid first check that no direction left a query over and that the normalisation is clean (lrr_spec_bad) and commit
+// nothing otherwise; the host then sees LRR_ST_NOT_STEADY, completes the match (lrr_k_match_rest) and runs the ordinary plan.
+// LRR_SPEC_FORCE=1 bets in every iteration the certificate pass can run (tests: the fallback in every non-steady iteration),
+// LRR_NO_SPEC=1 never.
+static bool spec_ok(const lrr_est* e) {
+  static const bool off = getenv("LRR_NO_SPEC") != nullptr, force = getenv("LRR_SPEC_FORCE") != nullptr;
+  if (off || !e->ctx->mailbox_dev || !e->normalize || e->dof == 6 || !e->norm_token || !cert_path(e)) return false;
+  for (int d = 0; d < (e->sym() ? 2 : 1); ++d) if (!e->d[d].scale_estimated || e->d[d].matches <= 0) return false;
+  return force || e->steady_hint;
 }
 
 // One whole iteration (find_closest + estimate_LS + residuals under the new transform) as one cooperative persistent
@@ -633,7 +658,7 @@ static int do_iteration_fused(lrr_est* e) {
   const int mode[2] = {0, 0}; const double sin[2] = {0, 0};
   static const bool dbgph = getenv("LRR_FUSED_DEBUG") != nullptr;
   long long* dbg = dbgph ? (long long*)(ctx->scratch_d + 512) : nullptr;
-  ctx->sel_owner = 0; e->norm_token = false;
+  ctx->sel_owner = 0; e->norm_token = false; e->steady_hint = false;
   { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, dbg, ctx->stream, &ctx->launches)); }
   if (dbgph) {
     static int calls = 0;
@@ -663,7 +688,7 @@ static int muse_for_dir(lrr_est* e, const EstArgs& a, int d) {
 }
 
 // estimate_LS (cdcl :1009-1093, cdcl sym :398-701, rrl :783-859, rrl sym :699-918) on the device
-static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_hist = false, bool cdcl_backward = false) {
+static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_hist = false, bool cdcl_backward = false, bool spec = false) {
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1;
   EstArgs a = est_args(e, src);
@@ -684,7 +709,7 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
     }
   }
   if (e->normalize && cdcl_backward) { PHASE(PH_NORM1); lrr_k_norm_merged(a, ctx->stream, &ctx->launches); }
-  else if (e->normalize) {
+  else if (e->normalize && !spec) {   // (speculative plan: the normalisation is clean or the kernels below refuse)
     // (rigid increments normalise mapped clones of the from-features, which move with the transform: never skipped)
     static const bool no_skip = getenv("LRR_NO_NORM_SKIP") != nullptr;   // A/B switch for measurements
     const int skip_clean = (e->norm_token && src == 0 && e->dof != 6 && !stale && !no_skip) ? 1 : 0;
@@ -704,9 +729,9 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   if (window && e->window_holdoff > 0) { e->window_holdoff -= 1; window = false; }
   if (window) a.flags |= LRR_F_BRACKET;
   ctx->sel_owner = sel_sig;
-  { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches); }
-  if ((e->strength || (e->sym() && !cdcl_backward)) && !window && !e->icp()) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches); }
-  { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches); }
+  { PHASE(PH_WEIGHT); lrr_k_weight_ex(a, mode, sin, ctx->stream, &ctx->launches, spec ? 1 : 0); }
+  if ((e->strength || (e->sym() && !cdcl_backward)) && !window && !e->icp()) { PHASE(PH_COLLECT); lrr_k_collect(a, ctx->stream, &ctx->launches, spec ? 1 : 0); }
+  { PHASE(PH_ACCUM); lrr_k_accumulate(a, ctx->stream, &ctx->launches, spec ? 1 : 0); }
   for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
   e->werr_cache_valid = false;
   return LRR_OK;
@@ -714,34 +739,58 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
 
 // estimate_LS + residuals under the new transform + scalar read-back.  A miss of the order-statistic window (rare: the
 // key distribution jumped) leaves the transform untouched on the device; the estimate is then repeated with histograms.
-static int estimate_and_pull(lrr_est* e, int resid_mask) {
+static int estimate_and_pull(lrr_est* e, int resid_mask, bool spec = false) {
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1, mask = dmask(e);
   bool fresh0[2], se0[2];
   for (int d = 0; d < 2; ++d) { fresh0[d] = e->d[d].weights_fresh; se0[d] = e->d[d].scale_estimated; }
-  int rc = do_estimate(e, 0, 1); if (rc != LRR_OK) return rc;
+  const int holdoff0 = e->window_holdoff; const unsigned long long owner0 = ctx->sel_owner;
+  const bool used_cert = cert_path(e);   // this iteration's find_closest went through the certificate pass in every direction
+  int rc = do_estimate(e, 0, 1, false, false, spec); if (rc != LRR_OK) return rc;
   static_assert(kScalHead % 8 == 0 && kScalHead / 8 <= 500, "Scal head does not fit a mailbox slot");
-  if (ctx->mailbox_dev) {
-    const unsigned long long seq = ++ctx->mailbox_seq;
-    { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches, ctx->mailbox_dev, seq, mask, (int)(kScalHead / 8)); }
-    if ((rc = pull_scal_mailbox(e, mask, seq)) != LRR_OK) return rc;
-  } else {
+  auto resid_and_pull = [&](bool sp) -> int {
+    if (ctx->mailbox_dev) {
+      const unsigned long long seq = ++ctx->mailbox_seq;
+      { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches, ctx->mailbox_dev, seq, mask, (int)(kScalHead / 8), sp ? 1 : 0); }
+      return pull_scal_mailbox(e, mask, seq);
+    }
     { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
-    if ((rc = pull_scal(e, mask)) != LRR_OK) return rc;
+    return pull_scal(e, mask);
+  };
+  if ((rc = resid_and_pull(spec)) != LRR_OK) return rc;
+  auto restore = [&](int bit) -> int {
+    for (int d = 0; d < nd; ++d) {
+      e->h[d].status &= ~bit;
+      int r = push_scal(e, d); if (r != LRR_OK) return r;
+      e->d[d].weights_fresh = fresh0[d]; e->d[d].scale_estimated = se0[d];
+    }
+    return LRR_OK;
+  };
+  if (spec) {
+    bool refused = false;
+    for (int d = 0; d < nd; ++d) refused = refused || (e->h[d].status & LRR_ST_NOT_STEADY);
+    if (refused) {   // the bet is lost: nothing was committed; complete the match and run the ordinary plan
+      ctx->spec_misses += 1;
+      e->steady_hint = false;
+      if ((rc = restore(LRR_ST_NOT_STEADY)) != LRR_OK) return rc;
+      e->window_holdoff = holdoff0; ctx->sel_owner = owner0;
+      { EstArgs a = est_args(e); PHASE(PH_MATCH); lrr_k_match_rest(a, ctx->stream, &ctx->launches); }
+      return estimate_and_pull(e, resid_mask, false);
+    }
   }
   bool miss = false;
   for (int d = 0; d < nd; ++d) miss = miss || (e->h[d].status & LRR_ST_SELECT_MISS);
-  if (!miss) { if (e->window_holdoff == 0) e->window_backoff = 0; return LRR_OK; }
-  ctx->window_misses += 1;
-  e->window_backoff = std::min(2 * (e->window_backoff + 1), 16); e->window_holdoff = e->window_backoff;
-  for (int d = 0; d < nd; ++d) {
-    e->h[d].status &= ~LRR_ST_SELECT_MISS;
-    if ((rc = push_scal(e, d)) != LRR_OK) return rc;
-    e->d[d].weights_fresh = fresh0[d]; e->d[d].scale_estimated = se0[d];
-  }
-  if ((rc = do_estimate(e, 0, 1, true)) != LRR_OK) return rc;
-  { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
-  return pull_scal(e, mask);
+  if (miss) {
+    ctx->window_misses += 1;
+    e->window_backoff = std::min(2 * (e->window_backoff + 1), 16); e->window_holdoff = e->window_backoff;
+    if ((rc = restore(LRR_ST_SELECT_MISS)) != LRR_OK) return rc;
+    if ((rc = do_estimate(e, 0, 1, true, false, spec)) != LRR_OK) return rc;   // (a speculative plan was verified by the first attempt)
+    if ((rc = resid_and_pull(spec)) != LRR_OK) return rc;
+  } else if (e->window_holdoff == 0) e->window_backoff = 0;
+  bool all_kept = used_cert;
+  for (int d = 0; d < nd; ++d) all_kept = all_kept && e->h[d].match_left == 0;
+  e->steady_hint = all_kept;
+  return LRR_OK;
 }
 
 static int check_status(lrr_est* e) {
@@ -774,8 +823,9 @@ static int one_iteration_fwd(lrr_est* e, int* converged) {
     if ((rc = do_iteration_fused(e)) != LRR_OK) return rc;
     if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
   } else {
-    if ((rc = do_find_closest(e)) != LRR_OK) return rc;
-    if ((rc = estimate_and_pull(e, 1)) != LRR_OK) return rc;
+    const bool spec = spec_ok(e);
+    if ((rc = do_find_closest(e, spec)) != LRR_OK) return rc;
+    if ((rc = estimate_and_pull(e, 1, spec)) != LRR_OK) return rc;
   }
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double before = rms_of(e, e->h[0], false), after = rms_of(e, e->h[0], true);
@@ -805,8 +855,9 @@ static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out)
     if ((rc = do_iteration_fused(e)) != LRR_OK) return rc;
     if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
   } else {
-    if ((rc = do_find_closest(e)) != LRR_OK) return rc;
-    if ((rc = estimate_and_pull(e, 1)) != LRR_OK) return rc;
+    const bool spec = spec_ok(e);
+    if ((rc = do_find_closest(e, spec)) != LRR_OK) return rc;
+    if ((rc = estimate_and_pull(e, 1, spec)) != LRR_OK) return rc;
   }
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double after = werr_of(e->h[0]);
@@ -1112,7 +1163,7 @@ static int objcov_check(lrr_est* e, int dir) {
 }
 
 extern "C" int lrr_objcov_eval(lrr_est* e, int dir, const double* x, double* f, double* g) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
   if (!x) return LRR_ERR_INVALID;
   enter(e->ctx);
@@ -1169,7 +1220,7 @@ static int lbfgs_minimize(FG&& fg, std::vector<double>& x, int max_evals, double
 
 // estimate_covariance (cdcl/cdcl_estimation.txx:264-337) on the ICP matches of direction `dir`
 extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_start, double* f_end, int* n_evals) {
-  if (e) e->norm_token = false;
+  if (e) { e->norm_token = false; e->steady_hint = false; }
   int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];

@@ -23,7 +23,7 @@ struct lrr_ctx {
   double* muse_table = nullptr;
   double* scratch_d = nullptr;
   void* pinned = nullptr;
-  double* mailbox = nullptr; double* mailbox_dev = nullptr; unsigned long long mailbox_seq = 0;   // result mailbox (mapped pinned, lrr_icp.cu)
+  double* mailbox = nullptr; double* mailbox_dev = nullptr; unsigned long long mailbox_seq = 0; long long spec_misses = 0;   // result mailbox (mapped pinned, lrr_icp.cu)
   // instrumentation: CUDA-event timing per phase kernel (lrr_ctx_set_profiling)
   bool profiling = false;
   struct Span { int phase; cudaEvent_t a, b; };
@@ -77,10 +77,13 @@ struct lrr_est {
   // the normalisation scalars on the device are those of this estimator's last forward-source estimate_LS (nothing else wrote
   // them since): k_norm1 / k_norm2 may leave at entry while the device says no match changed (Scal::norm_dirty)
   bool norm_token = false;
+  // every query of every direction was kept by its certificate in the last iteration (Scal::match_left == 0): the next iteration is
+  // launched without the staged search, pass B and the normalisation (speculative plan; verified on the device, see estimate_and_pull)
+  bool steady_hint = false;
   bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
   bool icp() const { return kind == LRR_CDCL_ICP; }   // cdcl_estimation_ICP<2,4>: no point ramp, scale constant 2, strength by sum
   bool rrl() const { return kind == LRR_RRL_FWD || kind == LRR_RRL_SYM; }
 };
 
 // kernels with host-visible extras (lrr_icp.cu / lrr_metrics.cu)
-void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches);
+void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches, int spec = 0);

@@ -57,6 +57,15 @@ __device__ __forceinline__ bool lrr_pair_done(const EstArgs& a, int needed) {
   return s_second;
 }
 
+// Speculative plan (lrr_capi.cu): the host left out the staged search, pass B and the normalisation because the previous iteration
+// kept every query.  True when that bet is lost for this iteration: nothing may be committed, the host completes the match and
+// reruns.  Every kernel of the plan evaluates the same device scalars, which none of them writes.
+__device__ __forceinline__ bool lrr_spec_bad(const EstArgs& a) {
+  bool bad = a.d[a.src].sc->norm_dirty != 0;
+  for (int d = 0; d < a.ndir; ++d) bad = bad || a.d[d].sc->match_left != 0;
+  return bad;
+}
+
 // ---- upload-time helpers ---------------------------------------------------------------------------------
 __global__ void k_fill_records(FsetDev f, double* __restrict__ rec) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,11 +218,15 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
   }
   lrr_tl(1, 3);
 }
-void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches) {
+static bool lrr_no_tile() { static const bool v = getenv("LRR_NO_TILE") != nullptr; return v; }   // A/B switch for measurements
+void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches, bool cert_only) {
+  if (cert_only) { lrr_k_match_cert(a, st, launches); return; }   // speculative plan: the caller has checked that every direction is certified
+  if (!lrr_no_tile() && lrr_match_tile_usable(a) && lrr_match_cert_usable(a)) lrr_k_match_cert(a, st, launches);
+  lrr_k_match_rest(a, st, launches);
+}
+void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
-  static const bool no_tile = getenv("LRR_NO_TILE") != nullptr;   // A/B switch for measurements
-  if (!no_tile && lrr_match_tile_usable(a)) {   // finest level (lrr_tile.cu): neighbour certificates, then shared-memory-staged cells for the rest
-    if (lrr_match_cert_usable(a)) lrr_k_match_cert(a, st, launches);
+  if (!lrr_no_tile() && lrr_match_tile_usable(a)) {   // finest level (lrr_tile.cu): shared-memory-staged cells for what the certificates did not keep
     lrr_k_match_tile(a, st, launches);
   }
   else {
@@ -312,8 +325,12 @@ void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches) {
 
 struct WeightExtra { int scale_mode[2]; double scale_in[2]; };
 
-__global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex) {
+__global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ EstArgs a, const WeightExtra ex, int spec) {
   lrr_pdl_enter();
+  if (spec && lrr_spec_bad(a)) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) for (int d = 0; d < a.ndir; ++d) atomicOr(&a.d[d].sc->status, LRR_ST_NOT_STEADY);
+    return;
+  }
   __shared__ PhaseShared sh;
   __shared__ double sh_cand[LRR_SEL_CAP], sh_cand2[LRR_SEL_CAP];
   const int dir = blockIdx.y;
@@ -366,19 +383,20 @@ __global__ void __launch_bounds__(LRR_THREADS) k_weight(const __grid_constant__ 
   }
   lrr_tl(4, 3);
 }
-void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches) {
+void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches, int spec) {
   WeightExtra ex;
   for (int d = 0; d < 2; ++d) { ex.scale_mode[d] = scale_mode[d]; ex.scale_in[d] = scale_in[d]; }
   dim3 grid(resident_width(k_weight, LRR_THREADS, a.ndir, maxM(a)), a.ndir);
-  lrr_launch_pdl(k_weight, grid, dim3(LRR_THREADS), 0, st, a, ex); ++*launches;
+  lrr_launch_pdl(k_weight, grid, dim3(LRR_THREADS), 0, st, a, ex, spec); ++*launches;
 }
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches) {
   const int m[2] = {0, 0}; const double s[2] = {0, 0};
-  lrr_k_weight_ex(a, m, s, st, launches);
+  lrr_k_weight_ex(a, m, s, st, launches, 0);
 }
 
-__global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__ EstArgs a) {
+__global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__ EstArgs a, int spec) {
   lrr_pdl_enter();
+  if (spec && lrr_spec_bad(a)) return;
   __shared__ double sh_cand[LRR_SEL_CAP];
   const int dir = blockIdx.y;
   const bool merged = (a.flags & LRR_F_MERGED) != 0;
@@ -406,9 +424,9 @@ __global__ void __launch_bounds__(LRR_THREADS) k_collect(const __grid_constant__
     }
   }
 }
-void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches) {
+void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches, int spec) {
   dim3 grid(nblk_for(maxM(a)), a.ndir);
-  lrr_launch_pdl(k_collect, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
+  lrr_launch_pdl(k_collect, grid, dim3(LRR_THREADS), 0, st, a, spec); ++*launches;
 }
 
 // 512 threads, one block per SM (128 registers): half as many partial rows of 108 moments for the last block to add as with two
@@ -416,8 +434,9 @@ void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches) {
 #ifndef LRR_ACC_THREADS
 #define LRR_ACC_THREADS 512
 #endif
-__global__ void __launch_bounds__(LRR_ACC_THREADS) k_accumulate(const __grid_constant__ EstArgs a) {
+__global__ void __launch_bounds__(LRR_ACC_THREADS) k_accumulate(const __grid_constant__ EstArgs a, int spec) {
   lrr_pdl_enter();
+  if (spec && lrr_spec_bad(a)) return;
   __shared__ PhaseSharedT<LRR_ACC_THREADS / 32> sh;
   const int dir = blockIdx.y;
   const bool merged = (a.flags & LRR_F_MERGED) != 0, sym = (a.flags & LRR_F_SYM) != 0;
@@ -437,10 +456,10 @@ __global__ void __launch_bounds__(LRR_ACC_THREADS) k_accumulate(const __grid_con
   lrr_solve(a.d[a.src].sc, a.ndir == 2 ? a.d[1 - a.src].sc : nullptr, a.flags, a.dof, a.estimate_parameters);
   lrr_tl(2, 3);
 }
-void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches) {
+void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches, int spec) {
   // two blocks per SM at most: the last block sums one row of 108 moments per block before it can solve
   dim3 grid(resident_width(k_accumulate, LRR_ACC_THREADS, a.ndir, maxM(a)), a.ndir);   // one match per lane and trip
-  lrr_launch_pdl(k_accumulate, grid, dim3(LRR_ACC_THREADS), 0, st, a); ++*launches;
+  lrr_launch_pdl(k_accumulate, grid, dim3(LRR_ACC_THREADS), 0, st, a, spec); ++*launches;
 }
 
 // Result MAILBOX: one_iteration returns `converged`, so the host reads ~1.6 kB of scalars per direction after every iteration.
@@ -462,13 +481,13 @@ __device__ __forceinline__ void lrr_mailbox_post(const EstArgs& a, int dir_mask,
     __threadfence_system();
   }
 }
-__global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0, double* mbox, unsigned long long seq, int pull_mask, int nhead) {
+__global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ EstArgs a, int dir0, double* mbox, unsigned long long seq, int pull_mask, int nhead, int spec) {
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
   const int dir = dir0 + blockIdx.y;
   // one row of blocks: its finalizer posts every direction the host wants; two rows: each finalizer posts its own direction
   const int post = gridDim.y == 2 ? (pull_mask & (1 << dir)) : pull_mask;
-  if (a.d[dir].sc->status & LRR_ST_SELECT_MISS) {   // the estimate was not committed: keep the residuals of the match for the rerun
+  if ((a.d[dir].sc->status & LRR_ST_SELECT_MISS) || (spec && lrr_spec_bad(a))) {   // the estimate was not committed: keep the residuals of the match for the rerun
     if (mbox && blockIdx.x == 0) lrr_mailbox_post(a, post, mbox, seq, nhead);
     return;
   }
@@ -477,13 +496,13 @@ __global__ void __launch_bounds__(LRR_THREADS) k_resid(const __grid_constant__ E
   if (fin && mbox) lrr_mailbox_post(a, post, mbox, seq, nhead);
   lrr_tl(8, 3);
 }
-void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches, double* mbox, unsigned long long seq, int pull_mask, int nhead) {
+void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches, double* mbox, unsigned long long seq, int pull_mask, int nhead, int spec) {
   if (dir_mask == 3) {
     dim3 grid(resident_width(k_resid, LRR_THREADS, 2, maxM(a)), 2);
-    lrr_launch_pdl(k_resid, grid, dim3(LRR_THREADS), 0, st, a, 0, mbox, seq, pull_mask, nhead); ++*launches;
+    lrr_launch_pdl(k_resid, grid, dim3(LRR_THREADS), 0, st, a, 0, mbox, seq, pull_mask, nhead, spec); ++*launches;
   } else {
     const int d = (dir_mask == 2) ? 1 : 0;
-    lrr_launch_pdl(k_resid, dim3(nblk_for(a.d[d].M)), dim3(LRR_THREADS), 0, st, a, d, mbox, seq, pull_mask, nhead); ++*launches;
+    lrr_launch_pdl(k_resid, dim3(nblk_for(a.d[d].M)), dim3(LRR_THREADS), 0, st, a, d, mbox, seq, pull_mask, nhead, spec); ++*launches;
   }
 }
 

@@ -84,6 +84,11 @@ struct Scal {
   // direction is kept by its certificate the match set — all the normalisation depends on for an affine estimate — is unchanged,
   // and k_norm1 / k_norm2 leave at entry (see do_estimate, lrr_capi.cu).
   int norm_dirty;
+  // queries of this direction's last find_closest that the certificate pass could NOT keep (work list + queue; any non-zero value
+  // when the search did not go through the certificate pass).  0 in every direction and norm_dirty == 0 = the steady state: the
+  // staged search, pass B and the normalisation have nothing to do — the host may leave their launches out (speculative plan,
+  // lrr_capi.cu), and the kernels after them verify exactly this before they commit anything.
+  int match_left, spec_pad;
   double n_nonzero, sel_below[2];
   double G, S;
   double res_sum_r2, res_sum_wr2, res_sum_w, res_sum_wr, res_count;   // resid phase
@@ -98,7 +103,8 @@ enum {
   LRR_ST_OK = 0,
   LRR_ST_SELECT_OVERFLOW = 1,   // candidate list overflow in the exact selection (host falls back to sort)
   LRR_ST_SINGULAR = 2,
-  LRR_ST_SELECT_MISS = 4        // the order statistic fell outside the predicted window: the host reruns the estimate with histograms
+  LRR_ST_SELECT_MISS = 4,       // the order statistic fell outside the predicted window: the host reruns the estimate with histograms
+  LRR_ST_NOT_STEADY = 8         // speculative plan refused: some query was not kept / the normalisation is stale; the host completes the match and reruns
 };
 
 struct DirArgs {
@@ -200,7 +206,8 @@ void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long lon
 void lrr_k_projector2_from_cov(const double* cov3, int n, double* P6, double* C6, cudaStream_t st, long long* launches);
 void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,
                        cudaStream_t st, long long* launches);
-void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches);   // pass A + pass B
+void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches, bool cert_only = false);   // certificate pass / pass A + pass B
+void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches);   // what a cert_only call left out: staged search + pass B
 // lrr_tile.cu: tile construction and the shared-memory-staged pass A of the finest level
 void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
                        int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches);
@@ -215,10 +222,10 @@ void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches, int ski
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);
 void lrr_k_norm_merged(const EstArgs& a, cudaStream_t st, long long* launches);   // cdcl estimate_LS_backward: normalisation over the merged list
 void lrr_k_weight(const EstArgs& a, cudaStream_t st, long long* launches);
-void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches);
-void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches);
+void lrr_k_collect(const EstArgs& a, cudaStream_t st, long long* launches, int spec = 0);
+void lrr_k_accumulate(const EstArgs& a, cudaStream_t st, long long* launches, int spec = 0);
 void lrr_k_resid(const EstArgs& a, int dir_mask, cudaStream_t st, long long* launches, double* mbox = nullptr, unsigned long long seq = 0,
-                 int pull_mask = 0, int nhead = 0);   // mbox: result mailbox in mapped host memory (lrr_icp.cu)
+                 int pull_mask = 0, int nhead = 0, int spec = 0);   // mbox: result mailbox in mapped host memory (lrr_icp.cu)
 void lrr_k_angles(const DirArgs& a, int flags, int which, double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
 void lrr_k_transfer_cov(const DirArgs& a, int dof, double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
 void lrr_k_resid_keys(const DirArgs& a, double* keys, cudaStream_t st, long long* launches);

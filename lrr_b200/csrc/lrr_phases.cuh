@@ -231,7 +231,7 @@ __device__ void lrr_phase_match(const Scope& scope, const DirArgs& a, int flags,
     lrr_tl(0, 2);
     if (threadIdx.x == 0) {
       Scal* sc = a.sc; sc->sum_loc[0] = sh.out[0]; sc->sum_loc[1] = sh.out[1]; sc->sum_loc[2] = sh.out[2]; sc->sum_r2 = sh.out[3];
-      sc->norm_dirty = 1;
+      sc->norm_dirty = 1; sc->match_left = 1;
       if (counter) *counter = 0;
     }
   }

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
     if (threadIdx.x == 0) {
       Scal* sc = d.sc;
       sc->norm_dirty = 1;
+      if (!lrr_dir_certified(d)) sc->match_left = 1;
       if (lrr_dir_certified(d)) {   // the certificate pass wrote its share of the sums
         sc->sum_loc[0] += s_out[0]; sc->sum_loc[1] += s_out[1]; sc->sum_loc[2] += s_out[2]; sc->sum_r2 += s_out[3];
         *d.todo_count = 0;
@@ -451,7 +452,13 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
     if (threadIdx.x == 0) {
       Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3];
       // every query kept <=> nothing on the work list (this block is the last one of the direction: all appends are visible)
-      if (lrr_dir_certified(d) && (*reinterpret_cast<volatile int*>(d.todo_count) > 0 || *reinterpret_cast<volatile int*>(d.hq_count) > 0)) sc->norm_dirty = 1;
+      const int left = lrr_dir_certified(d) ? *reinterpret_cast<volatile int*>(d.todo_count) + *reinterpret_cast<volatile int*>(d.hq_count) : 1;
+      sc->match_left = left;
+      if (left > 0) sc->norm_dirty = 1;
+      else {   // nothing follows for this direction: the bookkeeping of a finished find_closest (k_match_hard repeats it when it is launched)
+        const double tot[4] = {s_out[0], s_out[1], s_out[2], s_out[3]};
+        lrr_match_finalize(d, a.flags, tot);
+      }
     }
   }
   lrr_tl(5, 3);

@@ -252,6 +252,42 @@ def test_fused_iteration_kernel():
     assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_speculative_plan_and_its_fallback():
+    """Steady-state iterations are launched without the staged search, pass B and the normalisation (lrr_capi.cu, speculative
+    plan); the kernels that follow verify on the device that nothing was left over and refuse otherwise, and the host then
+    completes the match and reruns.  LRR_SPEC_FORCE=1 makes the host bet in EVERY finest-level iteration, so the refusal /
+    rerun path runs in each of them: all four estimator kinds must still follow the oracle iteration by iteration, and the run
+    must go through a transform jump (matches change after a kept-everything stretch)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from lrr_b200 import synth, lib\nfrom lrr_b200.capi import Lib\n"
+        "pair = synth.make_pair(53, 7000, 6500, size=90.0)\n"
+        "A0, t0, c0 = pair['init']\n"
+        "for kind in ('rrl_sym', 'cdcl_sym', 'rrl_fwd', 'cdcl_fwd'):\n"
+        "    es = []\n"
+        "    for L in (lib(), Lib(%r, 'lrro_')):\n"
+        "        ctx = L.context(); e = ctx.estimator(kind, ctx.upload(pair['moving']), ctx.upload(pair['fixed']), 12)\n"
+        "        e.set_flags(True, True); e.set_transform(A0, t0, c0); es.append(e)\n"
+        "    g, o = es\n"
+        "    dirs = (0, 1) if 'sym' in kind else (0,)\n"
+        "    for it in range(34):\n"
+        "        if it == 24:\n"
+        "            for e in es:\n"
+        "                e.set_transform(synth.rot_xyz(0.01, -0.008, 0.006) @ A0, t0 + np.array([0.8, -0.5, 0.3]), c0)\n"
+        "                for d in dirs: e.set_number_points(10 ** 9, d)\n"
+        "        assert g.one_iteration(it) == o.one_iteration(it), (kind, it)\n"
+        "        for d in dirs: assert np.array_equal(g.get_matches(d)[1], o.get_matches(d)[1]), (kind, it, d)\n"
+        "        Tg, To = g.get_transform(0), o.get_transform(0)\n"
+        "        for k in ('A', 't', 'cov'): assert np.linalg.norm(Tg[k] - To[k]) / np.linalg.norm(To[k]) < 1e-7, (kind, it, k)\n"
+        "print('spec ok')\n"
+    ) % (root, os.path.join(root, "oracle", "liblrr_oracle.so"))
+    for env in ({"LRR_SPEC_FORCE": "1"}, {}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "spec ok" in out.stdout, str(env) + out.stdout + out.stderr
+
+
 def test_cdcl_estimate_ls_backward(gpu_lib, oracle_lib, pair):
     """cdcl symmetric estimate_LS_backward (cdcl sym :705-863): merged list, merged normalisation, no spatial weighting."""
     for ep in (False, True):
