@@ -22,9 +22,10 @@ for k in range(int(os.environ.get("LRR_PROF_SETTLE", "3"))):   # settle at the f
     est.one_iteration(it); it += 1
 import time
 ctx.synchronize(); t0 = time.perf_counter()
-for k in range(40):   # un-profiled back-to-back iterations (host wall clock; each call ends in a stream synchronisation)
+for k in range(0 if os.environ.get("LRR_PROF_NOWALL") else 40):   # un-profiled back-to-back iterations (host wall clock; each call ends in a stream synchronisation)
     est.one_iteration(it); it += 1
-ctx.synchronize(); print(f"wall per iteration (L2 warm, 40 calls): {1e6 * (time.perf_counter() - t0) / 40:.1f} us")
+ctx.synchronize()
+if not os.environ.get("LRR_PROF_NOWALL"): print(f"wall per iteration (L2 warm, 40 calls): {1e6 * (time.perf_counter() - t0) / 40:.1f} us")
 rng = os.environ.get("LRR_PROF_RANGE")   # ncu --profile-from-start off: capture only the iterations below
 if rng:
     import torch
