@@ -157,7 +157,9 @@ __device__ __forceinline__ int lrr_nn_search(const GridDev& g, double qx, double
 //   pass A (one thread per query): queries whose ball touches at most LRR_BALL_ROWS rows;
 //   pass B (one warp per query): everything else — queries without a candidate first expand Chebyshev
 //   shells until a point is found, then the lanes split the rows of the ball.
+#ifndef LRR_BALL_ROWS
 #define LRR_BALL_ROWS 9
+#endif
 
 struct NNState { double best; int best_s, best_o; };
 
@@ -184,12 +186,12 @@ __device__ __forceinline__ void lrr_ball_row(const GridDev& g, int y, int z, dou
 // pass A.  st holds a candidate (best_s >= 0).  Returns false when the ball touches too many rows.
 // The x-range of the ball's bounding box is used for every row (no square root / floor per row: for the one to four
 // rows of a typical ball the extra cells cost less than the per-row arithmetic did).
-__device__ __forceinline__ bool lrr_nn_ball_thread(const GridDev& g, double qx, double qy, double qz, NNState& st) {
+__device__ __forceinline__ bool lrr_nn_ball_thread(const GridDev& g, double qx, double qy, double qz, NNState& st, int max_rows = LRR_BALL_ROWS) {
   const double slack = 1e-9 * g.h;
   const double R = sqrt(st.best) * (1.0 + 1e-9) + slack;
   const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
   const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
-  if ((z1 - z0 + 1) * (y1 - y0 + 1) > LRR_BALL_ROWS) return false;
+  if ((z1 - z0 + 1) * (y1 - y0 + 1) > max_rows) return false;
   const int xa = lrr_cell_clamp(qx - R, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + R, g.ox, g.inv_h, g.nx);
   for (int z = z0; z <= z1; ++z) {
     const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dz2 = dz * dz;
@@ -303,13 +305,13 @@ __device__ __forceinline__ void lrr_nn_upd2(const double4& p, int j, double qx, 
 }
 // one thread, candidate known (st.best_s >= 0): the inflated ball as in lrr_nn_pass_b_cert.  Returns false when the ball touches too
 // many rows for one thread (the caller queues the query for pass B).
-__device__ __forceinline__ bool lrr_nn_ball_thread_cert(const GridDev& g, double qx, double qy, double qz, NNState& st, double margin, double* bound_out) {
+__device__ __forceinline__ bool lrr_nn_ball_thread_cert(const GridDev& g, double qx, double qy, double qz, NNState& st, double margin, double* bound_out, int max_rows = LRR_BALL_ROWS) {
   *bound_out = 0.0;
   const double slack = 1e-9 * g.h;
   const double R = sqrt(st.best) * (1.0 + 1e-9) + slack + margin;
   const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
   const int y0 = lrr_cell_clamp(qy - R, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + R, g.oy, g.inv_h, g.ny);
-  if ((z1 - z0 + 1) * (y1 - y0 + 1) > LRR_BALL_ROWS) return false;
+  if ((z1 - z0 + 1) * (y1 - y0 + 1) > max_rows) return false;
   double second = 1e300;
   for (int z = z0; z <= z1; ++z) {
     const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dz2 = dz * dz;

@@ -119,6 +119,7 @@ struct DirArgs {
   const int2* chunk_tab; // or null: chunk c = positions [chunk_tab[c].x, chunk_tab[c].y) of proc, at most 32 queries of one row of tiles (lrr_tile.cu)
   const int* nchunks;    // device scalar: number of chunks
   int M;                 // number_points_: matches in use
+  int ball_rows;         // pass A keeps a query whose candidate ball touches at most this many grid rows (0: LRR_BALL_ROWS), the rest goes to pass B
   // to side
   FsetDev to;
   FsetDev from_all;      // parent set of the from side (rarely used attributes are gathered through forig)

@@ -122,7 +122,8 @@ __device__ __forceinline__ void lrr_match_a_one(const DirArgs& a, int flags, con
   if (st.best_s >= 0) {
     const double4 p = lrr_ld_pos4(g.pos4 + st.best_s);
     st.best = lrr_dist2_exact(yx, yy, yz, p.x, p.y, p.z); st.best_o = lrr_pos4_orig(p);
-    done = cert ? lrr_nn_ball_thread_cert(g, yx, yy, yz, st, 0.125 * g.h, &bound) : lrr_nn_ball_thread(g, yx, yy, yz, st);
+    const int max_rows = a.ball_rows > 0 ? a.ball_rows : LRR_BALL_ROWS;
+    done = cert ? lrr_nn_ball_thread_cert(g, yx, yy, yz, st, 0.125 * g.h, &bound, max_rows) : lrr_nn_ball_thread(g, yx, yy, yz, st, max_rows);
   } else if (g.n > 0) {
     const int r27 = lrr_nn_block27_thread(g, yx, yy, yz, st);
     if (r27 == 1) done = true;
