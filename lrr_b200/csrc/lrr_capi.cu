@@ -72,6 +72,7 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LRR_ERR_CUDA; }
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming) == cudaSuccess;
   {
     cudaMemPool_t pool; unsigned long long thr = ~0ull;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
@@ -118,6 +119,8 @@ extern "C" void lrr_ctx_destroy(lrr_ctx* ctx) {
   if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  if (ctx->copy_ev) cudaEventDestroy(ctx->copy_ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -141,12 +144,14 @@ static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, cons
                                 const uint8_t* shape, const double* dirs, const double* cov2, lrr_fset** out) {
   enter(ctx);
   lrr_fset* fs = new lrr_fset(); fs->ctx = ctx; fs->n = n; fs->dim = cov2 ? 2 : 3;
-  fs->host_xyz.assign(xyz, xyz + 3 * n);
   std::vector<double> zeros; std::vector<uint8_t> zshape;
   if (!strength) { zeros.assign((size_t)n, 0.0); strength = zeros.data(); }
   if (!shape) { zshape.assign((size_t)n, 0); shape = zshape.data(); }
   cudaStream_t st = ctx->stream;
-#define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); lrr_features_destroy(fs); return LRR_ERR_CUDA; } } while (0)
+#define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cudaStreamSynchronize(ctx->copy_stream); lrr_features_destroy(fs); return LRR_ERR_CUDA; } } while (0)
+  // the grid is built from the locations alone: they go first on the work stream, everything else (5x the bytes) is copied on
+  // ctx->copy_stream while the grid kernels run, and joins before the cell-ordered records are filled
+  cudaStream_t cs = ctx->copy_stream;
   FCK(dmalloc(&fs->xyz, (size_t)3 * n)); FCK(dmalloc(&fs->s, (size_t)n)); FCK(dmalloc(&fs->P6, (size_t)6 * n));
   FCK(dmalloc(&fs->shape, (size_t)n));
   FCK(cudaMemcpyAsync(fs->xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
@@ -155,11 +160,12 @@ static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, cons
     FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(dmalloc(&cov2_d, (size_t)3 * n));
     FCK(cudaMemcpyAsync(cov2_d, cov2, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
     lrr_k_projector2_from_cov(cov2_d, (int)n, fs->P6, fs->C6, st, &ctx->launches);
-  } else FCK(cudaMemcpyAsync(fs->P6, P6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st));
-  FCK(cudaMemcpyAsync(fs->s, strength, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  FCK(cudaMemcpyAsync(fs->shape, shape, (size_t)n, cudaMemcpyHostToDevice, st));
-  if (C6 && !cov2) { FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(cudaMemcpyAsync(fs->C6, C6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st)); }
-  if (dirs) { FCK(dmalloc(&fs->dirs, (size_t)9 * n)); FCK(cudaMemcpyAsync(fs->dirs, dirs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, st)); }
+  } else FCK(cudaMemcpyAsync(fs->P6, P6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, cs));
+  FCK(cudaMemcpyAsync(fs->s, strength, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+  FCK(cudaMemcpyAsync(fs->shape, shape, (size_t)n, cudaMemcpyHostToDevice, cs));
+  if (C6 && !cov2) { FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(cudaMemcpyAsync(fs->C6, C6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, cs)); }
+  if (dirs) { FCK(dmalloc(&fs->dirs, (size_t)9 * n)); FCK(cudaMemcpyAsync(fs->dirs, dirs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, cs)); }
+  FCK(cudaEventRecord(ctx->copy_ev, cs));
   FCK(dmalloc(&fs->pos4, (size_t)n)); FCK(dmalloc(&fs->rec, (size_t)8 * n)); FCK(dmalloc(&fs->sorted_of_orig, (size_t)n));
   FsetBuild fb; memset(&fb, 0, sizeof(fb));
   fb.n = n; fb.x = fs->xyz; fb.y = fs->xyz + n; fb.z = fs->xyz + 2 * n; fb.pos4 = fs->pos4; fb.sorted_of_orig = fs->sorted_of_orig;
@@ -168,6 +174,7 @@ static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, cons
   FsetDev& d = fs->dev;
   d.n = (int)n; d.x = fs->xyz; d.y = fs->xyz + n; d.z = fs->xyz + 2 * n; d.s = fs->s; d.P6 = fs->P6; d.C6 = fs->C6; d.dirs = fs->dirs;
   d.shape = fs->shape; d.grid = fb.grid; d.rec = fs->rec; d.sorted_of_orig = fs->sorted_of_orig;
+  FCK(cudaStreamWaitEvent(st, ctx->copy_ev, 0));
   lrr_k_fill_records(d, fs->rec, st, &ctx->launches);
   FCK(cudaStreamSynchronize(st));
   FCK(cudaGetLastError());
@@ -1268,8 +1275,13 @@ static bool valid_transform(const double* A) {
   return true;
 }
 // FeaturesInROIs (rrl/itkLocationRegistration.cxx:1324-1360): indices of the features inside the cube, in order
-static void roi_indices(const lrr_fset* fs, const double* c, double half, std::vector<int32_t>& out) {
+static void roi_indices(lrr_fset* fs, const double* c, double half, std::vector<int32_t>& out) {
   out.clear();
+  if (fs->host_xyz.empty() && fs->n > 0) {   // first host-side ROI selection on this set: fetch the locations once
+    fs->host_xyz.resize((size_t)3 * fs->n);
+    cudaMemcpyAsync(fs->host_xyz.data(), fs->xyz, sizeof(double) * 3 * fs->n, cudaMemcpyDeviceToHost, fs->ctx->stream);
+    cudaStreamSynchronize(fs->ctx->stream);
+  }
   const int64_t n = fs->n; const double* x = fs->host_xyz.data(); const double* y = x + n; const double* z = y + n;
   const double x0 = c[0] - half, x1 = c[0] + half, y0 = c[1] - half, y1 = c[1] + half, z0 = c[2] - half, z1 = c[2] + half;
   for (int64_t i = 0; i < n; ++i)

@@ -12,6 +12,8 @@ enum { PH_MATCH = 0, PH_NORM1, PH_NORM2, PH_WEIGHT, PH_COLLECT, PH_ACCUM, PH_RES
 struct lrr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // uploads: everything but the locations is copied on a second stream while the grid is built from the locations
+  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev = nullptr;
   std::string err;
   long long launches = 0;
   double* partials = nullptr;
@@ -39,7 +41,7 @@ struct lrr_fset {
   uint8_t* shape = nullptr;
   double4* pos4 = nullptr; double* rec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
   FsetDev dev;
-  std::vector<double> host_xyz;   // 3 x n copy for host-side ROI selection (FeaturesInROIs)
+  std::vector<double> host_xyz;   // 3 x n copy for host-side ROI selection (FeaturesInROIs); fetched from the device on first use
 };
 
 // one direction (forward_ / backward_) of an estimator
