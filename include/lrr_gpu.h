@@ -167,6 +167,14 @@ int  lrr_est_estimate_ls_backward(lrr_est* est, int estimate_parameters);
 /* compute_transfer_error_covariance(): covarJ = mean_i J_i Sigma J_i^T  (cdcl :388-404, rrl :381-397) */
 int  lrr_est_transfer_cov(lrr_est* est, int dir, double* S9);
 int  lrr_est_get_state(lrr_est* est, lrr_est_state* out);
+/* instrumentation of the neighbour search (no reference counterpart): per direction, the queries the last certificate pass could
+ * not keep and the queries finished by the one-warp-per-query pass in the last find_closest; order-statistic windows missed and
+ * steady-state bets lost on this estimator's context so far. */
+typedef struct lrr_est_stats {
+  int64_t cert_failed[2], passb_queries[2], work_list_entries[2];
+  int64_t window_misses, spec_misses;
+} lrr_est_stats;
+int  lrr_est_get_stats(lrr_est* est, lrr_est_stats* out);
 /* oscillated()  (rrl sym .h:156) */
 int  lrr_est_oscillated(lrr_est* est, int* out);
 

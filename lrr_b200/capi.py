@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
-    "est_get_state", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run",
+    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run",
 ]
 
 
@@ -40,6 +40,11 @@ class EstState(C.Structure):
         ("norm_center_moving", C.c_double * 3), ("norm_center_fixed", C.c_double * 3),
         ("norm_radius_moving", C.c_double), ("norm_radius_fixed", C.c_double),
     ]
+
+
+class EstStats(C.Structure):
+    _fields_ = [("cert_failed", C.c_int64 * 2), ("passb_queries", C.c_int64 * 2), ("work_list_entries", C.c_int64 * 2),
+                ("window_misses", C.c_int64), ("spec_misses", C.c_int64)]
 
 
 class Job(C.Structure):
@@ -120,7 +125,7 @@ class Lib:
             "est_get_matches": (i32, [vp, i32, i64, C.POINTER(i64), pi32, pi32, pd]),
             "est_metric": (i32, [vp, i32, i32, pd]), "est_estimate_ls_backward": (i32, [vp, i32]),
             "est_transfer_cov": (i32, [vp, i32, pd]), "est_get_state": (i32, [vp, C.POINTER(EstState)]),
-            "est_oscillated": (i32, [vp, C.POINTER(i32)]),
+            "est_oscillated": (i32, [vp, C.POINTER(i32)]), "est_get_stats": (i32, [vp, C.POINTER(EstStats)]),
             "objcov_eval": (i32, [vp, i32, pd, pd, pd]),
             "objcov_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32)]),
             "batch_run": (i32, [vp, vp, vp, vp, i64, i32, u64, vp]),
@@ -159,7 +164,7 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.fn("ctx_launch_count")(self.h))
 
-    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "fused_iteration"]
+    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "restamp"]
 
     def set_profiling(self, on: bool):
         self.check(self.lib.fn("ctx_set_profiling")(self.h, int(on)), "ctx_set_profiling")
@@ -322,6 +327,12 @@ class Estimator:
         s = EstState()
         self._c(self.lib.fn("est_get_state")(self.h, C.byref(s)), "est_get_state")
         return s
+
+    def stats(self) -> dict:
+        s = EstStats()
+        self._c(self.lib.fn("est_get_stats")(self.h, C.byref(s)), "est_get_stats")
+        return {"cert_failed": list(s.cert_failed), "passb_queries": list(s.passb_queries), "work_list_entries": list(s.work_list_entries),
+                "window_misses": int(s.window_misses), "spec_misses": int(s.spec_misses)}
 
     def oscillated(self) -> bool:
         o = C.c_int(0)

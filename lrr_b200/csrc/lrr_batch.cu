@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__
       a.hq_best = B.w_hqb + (blk * 2 + d) * BATCH_CAP;
       a.prev_s = B.w_prev + (blk * 2 + d) * BATCH_CAP;
       a.sc = B.w_sc + blk * 2 + d;
+      a.stamp_in_match = 1;   // (no certificates in batched mode: every finished match stamps its to-feature)
       *a.hq_count = 0;
       S.d[d] = a;
       S.calls[d] = 0; S.number_points[d] = a.M; S.scale_estimated[d] = 0;

@@ -312,6 +312,8 @@ static DirArgs dir_args(const lrr_dir& d) {
   if (a.proof) { a.pos_of = d.pos_of; a.cprev = d.cprev; a.tfx = d.tf; a.tfy = d.tf + n; a.tfz = d.tf + 2 * n; }
   a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.chunk_tab = (a.proc && d.n_in > 0) ? d.chunk_tab : nullptr; a.nchunks = d.chunk_start; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
+  // certified finest level (lrr_dir_certified, lrr_tile.cu): kept matches are not touched, the stamps come from k_restamp
+  a.stamp_in_match = !(a.proof && a.todo && a.chunk_tab && a.proc && a.M == a.n_in);
   return a;
 }
 
@@ -329,6 +331,7 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
   if (e->kind == LRR_CDCL_SYM) f |= LRR_F_MERGED;
   if (e->icp()) f |= LRR_F_ICP;
   if (e->dof == 4) f |= LRR_F_SIM2D;
+  { static const bool noflat = getenv("LRR_NO_FLAT") != nullptr; if (noflat) f |= LRR_F_NOFLAT; }
   a.flags = f; a.dof = e->dof; a.src = src; a.estimate_parameters = 1;
   a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
   a.partials = ctx->partials; a.ticket = ctx->ticket;
@@ -426,8 +429,32 @@ extern "C" void lrr_est_destroy(lrr_est* e) {
   delete e;
 }
 
+// Called by every entry point that changes what the next find_closest / estimate depends on: the device-side normalisation is no
+// longer known to be this estimator's (norm_token), and a pre-match (the certificate pass of the next find_closest, run as the trailing
+// pass of the last iteration) is dropped together with the work list it may have left.
+static void touch(lrr_est* e) {
+  if (!e) return;
+  e->norm_token = false; e->steady_hint = false;
+  if (e->pre_matched) {
+    enter(e->ctx);
+    for (int d = 0; d < (e->sym() ? 2 : 1); ++d) cudaMemsetAsync(e->d[d].todo_count, 0, sizeof(int), e->ctx->stream);
+    e->pre_matched = false;
+  }
+}
+// the certificates assume that match position k holds from-feature k: void them whenever the order policy changes
+static void void_certificates(lrr_est* e) {
+  enter(e->ctx);
+  for (int d = 0; d < (e->sym() ? 2 : 1); ++d) {
+    lrr_dir& D = e->d[d];
+    const size_t n = (size_t)(D.n_in ? D.n_in : 1);
+    cudaMemsetAsync(D.proof, 0, sizeof(double4) * n, e->ctx->stream);
+    cudaMemsetAsync(D.cprev, 0xFF, sizeof(int) * n, e->ctx->stream);
+    cudaMemsetAsync(D.prev_s, 0xFF, sizeof(int) * n, e->ctx->stream);
+  }
+}
+
 extern "C" int lrr_est_set_subsets(lrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   if (!e || !mi || nm < 0) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   int rc = dir_set_subset(ctx, e->d[0], mi, nm);
@@ -448,7 +475,7 @@ static void set_identity_norm(Scal& s) {
 }
 
 extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   if (!e || !A9 || !t3) return LRR_ERR_INVALID;
   if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
@@ -486,7 +513,7 @@ extern "C" int lrr_est_set_transform(lrr_est* e, int tk, const double* A9, const
 }
 
 extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   if (!e) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   e->normalize = normalize != 0; e->strength = wbs != 0;
@@ -498,10 +525,11 @@ extern "C" int lrr_est_set_flags(lrr_est* e, int normalize, int wbs) {
 }
 
 extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64_t n) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
+  void_certificates(e);
   if (!perm) { d.has_order = false; return LRR_OK; }
   if (n != d.n_in) return LRR_ERR_INVALID;
   for (int64_t i = 0; i < n; ++i) if (perm[i] < 0 || perm[i] >= n) return LRR_ERR_INVALID;
@@ -511,8 +539,9 @@ extern "C" int lrr_est_set_order(lrr_est* e, int dir, const int32_t* perm, int64
   return LRR_OK;
 }
 extern "C" int lrr_est_set_shuffle(lrr_est* e, int mode, uint64_t seed) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   if (!e || (mode != LRR_ORDER_FIXED && mode != LRR_ORDER_RESHUFFLE)) return LRR_ERR_INVALID;
+  if (mode != e->shuffle_mode) void_certificates(e);
   e->shuffle_mode = mode; e->seed = seed;
   for (int d = 0; d < 2; ++d) { e->d[d].shuffle_calls = 0; e->d[d].perm_half = 0; }
   return LRR_OK;
@@ -522,7 +551,7 @@ extern "C" int lrr_est_set_initial_scale(lrr_est* e, int dir, double s) {
   e->d[dir].initial_scale = s; return LRR_OK;
 }
 extern "C" int lrr_est_set_number_points(lrr_est* e, int dir, int64_t m, int* at_max) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0) || m < 0) return LRR_ERR_INVALID;
   if (e->icp()) return LRR_ERR_INVALID;   // cdcl_estimation_ICP has no set_number_points (cdcl_estimation_ICP.h)
   lrr_dir& d = e->d[dir];
@@ -587,6 +616,16 @@ static int apply_shuffle(lrr_est* e, int dir) {
   return LRR_OK;
 }
 
+// a fresh stamp epoch for direction d (the tag of the "unique matched to-feature" stamps, DirArgs::tag)
+static int bump_epoch(lrr_est* e, int d) {
+  lrr_ctx* ctx = e->ctx;
+  e->d[d].epoch += 1;
+  if (e->d[d].epoch == 0xFFFFFFFFu) {   // stamp epochs exhausted: start over
+    CK(cudaMemsetAsync(e->d[d].stamp, 0xFF, (size_t)e->d[d].to_all->n * sizeof(unsigned long long), ctx->stream));
+    e->d[d].epoch = 1;
+  }
+  return LRR_OK;
+}
 // find_closest_euclidean of every direction (cdcl :541-654, sym wrappers): host part (permutation keys, stamp epochs)
 static int prepare_find_closest(lrr_est* e) {
   lrr_ctx* ctx = e->ctx;
@@ -594,11 +633,7 @@ static int prepare_find_closest(lrr_est* e) {
   for (int d = 0; d < nd; ++d) {
     if (e->d[d].to_all->n == 0 || e->d[d].n_in == 0) { ctx->err = "find_closest_euclidean: empty feature set"; return LRR_ERR_STATE; }
     int rc = apply_shuffle(e, d); if (rc != LRR_OK) return rc;
-    e->d[d].epoch += 1;
-    if (e->d[d].epoch == 0xFFFFFFFFu) {   // stamp epochs exhausted: start over
-      CK(cudaMemsetAsync(e->d[d].stamp, 0xFF, (size_t)e->d[d].to_all->n * sizeof(unsigned long long), ctx->stream));
-      e->d[d].epoch = 1;
-    }
+    if ((rc = bump_epoch(e, d)) != LRR_OK) return rc;
   }
   return LRR_OK;
 }
@@ -641,48 +676,6 @@ static bool spec_ok(const lrr_est* e) {
   return force || e->steady_hint;
 }
 
-// One whole iteration (find_closest + estimate_LS + residuals under the new transform) as one cooperative persistent
-// kernel (lrr_coop.cu).  Steady state only: the first estimate after set_transform needs the MUSE sort.
-cudaError_t lrr_k_iteration(const EstArgs& a, const int* scale_mode, const double* scale_in, long long* dbg, cudaStream_t st, long long* launches);
-static bool fused_ok(lrr_est* e) {
-  // Measured on B200 (profiles/r1_summary.md): the fused kernel is not faster than the per-phase kernels (fewer threads in
-  // flight per phase at 128 registers; ~5 us per in-kernel reduction), so it is opt-in.
-  static const bool on = getenv("LRR_FUSED") != nullptr;
-  static const int small_max = getenv("LRR_FUSED_SMALL") ? atoi(getenv("LRR_FUSED_SMALL")) : 0;
-  const int nd = e->sym() ? 2 : 1;
-  if (e->icp()) return false;
-  if (!on) {
-    if (small_max <= 0) return false;
-    for (int d = 0; d < nd; ++d) if (std::min<int64_t>(e->d[d].number_points, e->d[d].n_in) > small_max) return false;
-  }
-  for (int d = 0; d < nd; ++d) if (!e->d[d].scale_estimated) return false;
-  return true;
-}
-static int do_iteration_fused(lrr_est* e) {
-  lrr_ctx* ctx = e->ctx;
-  int rc = prepare_find_closest(e); if (rc != LRR_OK) return rc;
-  EstArgs a = est_args(e, 0);
-  a.estimate_parameters = 1;
-  const int nd = e->sym() ? 2 : 1;
-  for (int d = 0; d < nd; ++d) if (a.d[d].M <= 0) { ctx->err = "one_iteration without points"; return LRR_ERR_STATE; }
-  const int mode[2] = {0, 0}; const double sin[2] = {0, 0};
-  static const bool dbgph = getenv("LRR_FUSED_DEBUG") != nullptr;
-  long long* dbg = dbgph ? (long long*)(ctx->scratch_d + 512) : nullptr;
-  ctx->sel_owner = 0; e->norm_token = false; e->steady_hint = false;
-  { PHASE(PH_OTHER); CK(lrr_k_iteration(a, mode, sin, dbg, ctx->stream, &ctx->launches)); }
-  if (dbgph) {
-    static int calls = 0;
-    if (++calls % 20 == 0) {
-      long long h[16]; cudaStreamSynchronize(ctx->stream); cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost); cudaMemset(dbg, 0, sizeof(h));
-      const char* nm[12] = {"matchA", "sync", "matchB", "reduce", "norm", "weight", "locate", "collect+sel", "accum", "solve", "sync2", "resid"};
-      for (int i = 0; i < 12; ++i) fprintf(stderr, "[fused block 0] %-12s %8.1f us/iter\n", nm[i], h[i] / 1.9e3 / 20);
-    }
-  }
-  finish_find_closest(e, a);
-  for (int d = 0; d < nd; ++d) e->d[d].weights_fresh = false;
-  return LRR_OK;
-}
-
 static int muse_for_dir(lrr_est* e, const EstArgs& a, int d) {
   lrr_ctx* ctx = e->ctx;
   const int M = a.d[d].M;
@@ -702,12 +695,23 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   lrr_ctx* ctx = e->ctx;
   const int nd = e->sym() ? 2 : 1;
   EstArgs a = est_args(e, src);
-  a.estimate_parameters = estimate_parameters;
-  if (cdcl_backward) a.flags |= LRR_F_NOSPATIAL | LRR_F_NO_OTHER_RENORM;
-  for (int d = 0; d < nd; ++d) if (e->d[d].matches <= 0 || a.d[d].M <= 0) { ctx->err = "estimate_LS without matches"; return LRR_ERR_STATE; }
   // stale weights (not straight after find_closest): residuals under the current transform first (cdcl :698-701)
   int stale = 0;
   for (int d = 0; d < nd; ++d) if (!e->d[d].weights_fresh) stale |= 1 << d;
+  // The "unique matched to-feature" stamps exist already only when this estimate follows its own find_closest at a ramp level
+  // (DirArgs::stamp_in_match).  Everywhere else — certified finest level, estimate_LS_backward — the normalisation lays them down
+  // itself (k_restamp), in a fresh epoch.
+  const bool restamp = e->normalize && !spec && (!a.d[src].stamp_in_match || stale || src != 0 || cdcl_backward);
+  if (restamp) {
+    int rc = bump_epoch(e, src); if (rc != LRR_OK) return rc;
+    a = est_args(e, src);
+  }
+  a.estimate_parameters = estimate_parameters;
+  if (cdcl_backward) a.flags |= LRR_F_NOSPATIAL | LRR_F_NO_OTHER_RENORM;
+  for (int d = 0; d < nd; ++d) if (e->d[d].matches <= 0 || a.d[d].M <= 0) { ctx->err = "estimate_LS without matches"; return LRR_ERR_STATE; }
+  // estimate_LS works on the matches that EXIST (the reference iterates over matches_): number_points_ may have moved on since the
+  // last find_closest (a ramp step at the end of one_iteration, then estimate_LS_backward)
+  for (int d = 0; d < nd; ++d) a.d[d].M = (int)e->d[d].matches;
   if (stale) { PHASE(PH_RESID); lrr_k_resid(a, stale, ctx->stream, &ctx->launches); a.flags |= LRR_F_USE_OLD_W; }
   int mode[2] = {0, 0}; double sin[2] = {0, 0};
   for (int d = 0; d < nd; ++d) {
@@ -718,11 +722,15 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
       D.scale_estimated = true;
     }
   }
-  if (e->normalize && cdcl_backward) { PHASE(PH_NORM1); lrr_k_norm_merged(a, ctx->stream, &ctx->launches); }
+  if (e->normalize && cdcl_backward) {
+    if (restamp) { PHASE(PH_RESTAMP); lrr_k_restamp(a, ctx->stream, &ctx->launches, 0); }
+    PHASE(PH_NORM1); lrr_k_norm_merged(a, ctx->stream, &ctx->launches);
+  }
   else if (e->normalize && !spec) {   // (speculative plan: the normalisation is clean or the kernels below refuse)
     // (rigid increments normalise mapped clones of the from-features, which move with the transform: never skipped)
     static const bool no_skip = getenv("LRR_NO_NORM_SKIP") != nullptr;   // A/B switch for measurements
     const int skip_clean = (e->norm_token && src == 0 && e->dof != 6 && !stale && !no_skip) ? 1 : 0;
+    if (restamp) { PHASE(PH_RESTAMP); lrr_k_restamp(a, ctx->stream, &ctx->launches, skip_clean); }
     { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches, skip_clean); }
     { PHASE(PH_NORM2); lrr_k_norm2(a, ctx->stream, &ctx->launches, skip_clean); }
   }
@@ -747,6 +755,19 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   return LRR_OK;
 }
 
+// PIPELINED FINEST LEVEL.  The pass that ends an iteration (residuals of the matches under the new transform) and the certificate
+// pass that starts the next find_closest read the same data and evaluate the same e^T P e under the same transform, so at the
+// certified finest level of an affine estimator ONE launch does both (k_match_cert with LRR_CERT_RESID, lrr_tile.cu): the next
+// one_iteration then starts at the weights, and the host already knows from this iteration's scalars whether every query was kept
+// (steady state: certificate/residual pass -> weight -> accumulate+solve, three launches) or the match has to be completed first
+// (staged search + pass B, then the normalisation).  LRR_NO_PIPE=1 switches it off (A/B).
+static bool pipe_ok(const lrr_est* e) {
+  static const bool off = getenv("LRR_NO_PIPE") != nullptr;
+  if (off || e->dof != 12 || !cert_path(e)) return false;
+  for (int d = 0; d < (e->sym() ? 2 : 1); ++d) if (e->d[d].matches != e->d[d].n_in) return false;   // the finished iteration matched every point
+  return true;
+}
+
 // estimate_LS + residuals under the new transform + scalar read-back.  A miss of the order-statistic window (rare: the
 // key distribution jumped) leaves the transform untouched on the device; the estimate is then repeated with histograms.
 static int estimate_and_pull(lrr_est* e, int resid_mask, bool spec = false) {
@@ -756,16 +777,20 @@ static int estimate_and_pull(lrr_est* e, int resid_mask, bool spec = false) {
   for (int d = 0; d < 2; ++d) { fresh0[d] = e->d[d].weights_fresh; se0[d] = e->d[d].scale_estimated; }
   const int holdoff0 = e->window_holdoff; const unsigned long long owner0 = ctx->sel_owner;
   const bool used_cert = cert_path(e);   // this iteration's find_closest went through the certificate pass in every direction
+  const bool pipe = pipe_ok(e);          // ... and the trailing pass is the certificate pass of the next one
   int rc = do_estimate(e, 0, 1, false, false, spec); if (rc != LRR_OK) return rc;
   static_assert(kScalHead % 8 == 0 && kScalHead / 8 <= 500, "Scal head does not fit a mailbox slot");
   auto resid_and_pull = [&](bool sp) -> int {
-    if (ctx->mailbox_dev) {
-      const unsigned long long seq = ++ctx->mailbox_seq;
-      { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches, ctx->mailbox_dev, seq, mask, (int)(kScalHead / 8), sp ? 1 : 0); }
-      return pull_scal_mailbox(e, mask, seq);
+    const unsigned long long seq = ctx->mailbox_dev ? ++ctx->mailbox_seq : 0;
+    if (pipe) {
+      int r = prepare_find_closest(e); if (r != LRR_OK) return r;
+      EstArgs a = est_args(e); PHASE(PH_RESID);
+      lrr_k_match_cert(a, ctx->stream, &ctx->launches, 1 /* LRR_CERT_RESID */, ctx->mailbox_dev, seq, mask, (int)(kScalHead / 8));
+    } else {
+      EstArgs a = est_args(e); PHASE(PH_RESID);
+      lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches, ctx->mailbox_dev, seq, mask, (int)(kScalHead / 8), sp ? 1 : 0);
     }
-    { EstArgs a = est_args(e); PHASE(PH_RESID); lrr_k_resid(a, resid_mask, ctx->stream, &ctx->launches); }
-    return pull_scal(e, mask);
+    return ctx->mailbox_dev ? pull_scal_mailbox(e, mask, seq) : pull_scal(e, mask);
   };
   if ((rc = resid_and_pull(spec)) != LRR_OK) return rc;
   auto restore = [&](int bit) -> int {
@@ -799,8 +824,31 @@ static int estimate_and_pull(lrr_est* e, int resid_mask, bool spec = false) {
   } else if (e->window_holdoff == 0) e->window_backoff = 0;
   bool all_kept = used_cert;
   for (int d = 0; d < nd; ++d) all_kept = all_kept && e->h[d].match_left == 0;
+  // pipelined: match_left is that of the NEXT find_closest (its certificate pass has just run); otherwise that of this iteration's,
+  // the bet of the speculative plan
   e->steady_hint = all_kept;
+  e->pre_matched = pipe;
   return LRR_OK;
+}
+
+// find_closest + estimate_LS + residuals + read-back of one iteration
+static int match_estimate_pull(lrr_est* e, int resid_mask) {
+  lrr_ctx* ctx = e->ctx;
+  int rc;
+  bool spec;
+  if (e->pre_matched) {
+    // the certificate pass of this find_closest ran as the trailing pass of the last iteration, and its outcome came back with that
+    // iteration's scalars: every query kept (steady_hint) -> nothing to complete, and the normalisation is unchanged
+    e->pre_matched = false;
+    spec = spec_ok(e);
+    EstArgs a = est_args(e);
+    if (!spec) { PHASE(PH_MATCH); lrr_k_match_rest(a, ctx->stream, &ctx->launches); }
+    finish_find_closest(e, a);
+  } else {
+    spec = spec_ok(e);
+    if ((rc = do_find_closest(e, spec)) != LRR_OK) return rc;
+  }
+  return estimate_and_pull(e, resid_mask, spec);
 }
 
 static int check_status(lrr_est* e) {
@@ -813,30 +861,36 @@ static int check_status(lrr_est* e) {
 }
 
 static double rms_of(const lrr_est* e, const Scal& s, bool after) {   // RMS_error (cdcl :196-230; rrl :211-241, Q1)
-  const double sum = after ? s.res_sum_r2 : s.sum_r2;
+  const double sum = after ? s.res_sum_r2 : s.used_sum_r2;   // (sum_r2 may already belong to the next match: pre-match, lrr_tile.cu)
   if (e->rrl()) return sum;
   const double cnt = s.res_count;
   return cnt != 0 ? std::sqrt(sum / cnt) : sum;
 }
 static double werr_of(const Scal& s) { return s.res_sum_w != 0 ? s.res_sum_wr / s.res_sum_w : s.res_sum_wr; }
 
+void lrr_k_fill_ones(double* w, int n, cudaStream_t st, long long* launches);
 extern "C" int lrr_est_find_closest(lrr_est* e) {
   if (!e) return LRR_ERR_INVALID;
-  enter(e->ctx);
-  return do_find_closest(e);
+  lrr_ctx* ctx = e->ctx; enter(ctx);
+  if (e->pre_matched) {   // the certificate pass has run already (trailing pass of the last iteration): complete the match
+    e->pre_matched = false;
+    EstArgs a = est_args(e);
+    { PHASE(PH_MATCH); lrr_k_match_rest(a, ctx->stream, &ctx->launches); }
+    finish_find_closest(e, a);
+  } else {
+    int rc = do_find_closest(e); if (rc != LRR_OK) return rc;
+  }
+  // find_closest resets every weight to 1 (cdcl :645); matches kept by their certificate are not rewritten, so where certificates
+  // are in use the weights are reset here (inside one_iteration the weights are recomputed before anything reads them)
+  EstArgs a = est_args(e);
+  for (int d = 0; d < a.ndir; ++d) if (!a.d[d].stamp_in_match) lrr_k_fill_ones(a.d[d].w, a.d[d].M, ctx->stream, &ctx->launches);
+  e->steady_hint = false;
+  return LRR_OK;
 }
 
 static int one_iteration_fwd(lrr_est* e, int* converged) {
-  lrr_ctx* ctx = e->ctx;
   int rc;
-  if (fused_ok(e)) {
-    if ((rc = do_iteration_fused(e)) != LRR_OK) return rc;
-    if ((rc = pull_scal(e, 1)) != LRR_OK) return rc;
-  } else {
-    const bool spec = spec_ok(e);
-    if ((rc = do_find_closest(e, spec)) != LRR_OK) return rc;
-    if ((rc = estimate_and_pull(e, 1, spec)) != LRR_OK) return rc;
-  }
+  if ((rc = match_estimate_pull(e, 1)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double before = rms_of(e, e->h[0], false), after = rms_of(e, e->h[0], true);
   *converged = std::fabs(before - after) < 1e-4;   // cdcl :506
@@ -856,19 +910,11 @@ static int weighted_error_now(lrr_est* e, int dir, double* out) {
 
 // one_iteration of the symmetric estimators (cdcl sym :268-363, rrl sym :341-438)
 static int one_iteration_sym(lrr_est* e, unsigned iteration, int* converged_out) {
-  lrr_ctx* ctx = e->ctx;
   int rc;
   double before;
   if (e->werr_cache_valid) before = e->werr_cache;
   else if ((rc = weighted_error_now(e, 0, &before)) != LRR_OK) return rc;
-  if (fused_ok(e)) {
-    if ((rc = do_iteration_fused(e)) != LRR_OK) return rc;
-    if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
-  } else {
-    const bool spec = spec_ok(e);
-    if ((rc = do_find_closest(e, spec)) != LRR_OK) return rc;
-    if ((rc = estimate_and_pull(e, 1, spec)) != LRR_OK) return rc;
-  }
+  if ((rc = match_estimate_pull(e, 1)) != LRR_OK) return rc;
   if ((rc = check_status(e)) != LRR_OK) return rc;
   const double after = werr_of(e->h[0]);
   e->werr_cache = after; e->werr_cache_valid = true;
@@ -999,6 +1045,7 @@ extern "C" int lrr_est_metric(lrr_est* e, int which, int dir, double* out) {
 extern "C" int lrr_est_estimate_ls_backward(lrr_est* e, int estimate_parameters) {
   if (!e || !e->sym()) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx; enter(ctx);
+  touch(e);   // (the transforms go through normalize / unnormalize at least: a pre-match of the next find_closest is dropped)
   if (e->kind == LRR_CDCL_SYM) {
     // cdcl variant (cdcl sym :705-863): the backward matches plus the forward matches reversed, normalised as ONE list,
     // strength re-weighting over the merged list, no spatial weighting; only backward_->trans_ is (un)normalised.
@@ -1071,6 +1118,17 @@ extern "C" int lrr_est_get_state(lrr_est* e, lrr_est_state* s) {
     s->error_difference = e->error_difference; s->weighted_error = e->weighted_error;
   }
   s->iterations_done = e->iterations_done;
+  return LRR_OK;
+}
+extern "C" int lrr_est_get_stats(lrr_est* e, lrr_est_stats* s) {
+  if (!e || !s) return LRR_ERR_INVALID;
+  enter(e->ctx);
+  int rc = pull_scal(e, dmask(e)); if (rc != LRR_OK) return rc;
+  memset(s, 0, sizeof(*s));
+  for (int d = 0; d < (e->sym() ? 2 : 1); ++d) {
+    s->cert_failed[d] = (int64_t)e->h[d].cert_failed; s->passb_queries[d] = (int64_t)e->h[d].passb_queries; s->work_list_entries[d] = e->h[d].match_left;
+  }
+  s->window_misses = e->ctx->window_misses; s->spec_misses = e->ctx->spec_misses;
   return LRR_OK;
 }
 extern "C" int lrr_est_oscillated(lrr_est* e, int* out) {
@@ -1173,7 +1231,7 @@ static int objcov_check(lrr_est* e, int dir) {
 }
 
 extern "C" int lrr_objcov_eval(lrr_est* e, int dir, const double* x, double* f, double* g) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
   if (!x) return LRR_ERR_INVALID;
   enter(e->ctx);
@@ -1230,15 +1288,17 @@ static int lbfgs_minimize(FG&& fg, std::vector<double>& x, int max_evals, double
 
 // estimate_covariance (cdcl/cdcl_estimation.txx:264-337) on the ICP matches of direction `dir`
 extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_start, double* f_end, int* n_evals) {
-  if (e) { e->norm_token = false; e->steady_hint = false; }
+  touch(e);
   int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
   if (e->normalize) {   // cdcl_normalize_matches over the current matches (:271-277)
+    if ((rc = bump_epoch(e, dir)) != LRR_OK) return rc;
     EstArgs a = est_args(e, dir);
     a.d[dir].M = (int)d.matches;
     a.ndir = 1; if (dir == 1) { a.d[0] = a.d[1]; a.src = 0; }
+    lrr_k_restamp(a, ctx->stream, &ctx->launches);
     lrr_k_norm1(a, ctx->stream, &ctx->launches); lrr_k_norm2(a, ctx->stream, &ctx->launches);
   }
   if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;

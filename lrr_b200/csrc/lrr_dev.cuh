@@ -241,6 +241,37 @@ __device__ __forceinline__ void lrr_warp_min(double& best, int& best_s, int& bes
   }
 }
 
+// Whole warp, one query without a candidate: Chebyshev shells around the query's cell until one holds a point (any point will do as
+// the candidate that bounds the ball scan).  Returns false for an empty set.
+__device__ __forceinline__ bool lrr_nn_shell_first(const GridDev& g, double qx, double qy, double qz, double& best, int& best_s, int& best_o) {
+  const int lane = threadIdx.x & 31;
+  best = 1e300; best_s = -1; best_o = 0x7fffffff;
+  if (g.n <= 0) return false;
+  const int cx = lrr_cell_clamp(qx, g.ox, g.inv_h, g.nx), cy = lrr_cell_clamp(qy, g.oy, g.inv_h, g.ny), cz = lrr_cell_clamp(qz, g.oz, g.inv_h, g.nz);
+  const int rmax = max(max(g.nx, g.ny), g.nz);
+  for (int r = 0; r <= rmax; ++r) {
+    const int side = 2 * r + 1, nface = 2 * side, per_plane = 4 * r, nruns = nface + (side - 2) * per_plane;
+    for (int t = lane; t < nruns; t += 32) {
+      int z, y, xa, xb;
+      if (t < nface) { z = (t < side) ? cz - r : cz + r; y = cy - r + (t % side); xa = cx - r; xb = cx + r; }
+      else {
+        const int u = t - nface, zi = u / per_plane, v = u % per_plane;
+        z = cz - r + 1 + zi;
+        if (v < 2) { y = (v == 0) ? cy - r : cy + r; xa = cx - r; xb = cx + r; }
+        else { const int m = v - 2; y = cy - r + 1 + (m >> 1); xa = xb = (m & 1) ? cx + r : cx - r; }
+      }
+      if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+      xa = max(xa, 0); xb = min(xb, g.nx - 1);
+      if (xa > xb) continue;
+      const int row = (z * g.ny + y) * g.nx;
+      lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), qx, qy, qz, best, best_s, best_o);
+    }
+    lrr_warp_min(best, best_s, best_o);
+    if (best_s >= 0) break;
+  }
+  return best_s >= 0;
+}
+
 // pass B: whole warp, one query; st identical in every lane (best_s < 0: no candidate yet).
 // Returns the sorted slot of the exact nearest neighbour (-1 for an empty set).
 __device__ __forceinline__ int lrr_nn_pass_b(const GridDev& g, double qx, double qy, double qz, NNState st) {
@@ -248,33 +279,7 @@ __device__ __forceinline__ int lrr_nn_pass_b(const GridDev& g, double qx, double
   const int lane = threadIdx.x & 31;
   const double slack = 1e-9 * g.h;
   double best = st.best; int best_s = st.best_s, best_o = st.best_o;
-  if (best_s < 0) {
-    // no candidate: Chebyshev shells around the query's cell until one holds a point (any point will do)
-    best = 1e300; best_o = 0x7fffffff;
-    const int cx = lrr_cell_clamp(qx, g.ox, g.inv_h, g.nx), cy = lrr_cell_clamp(qy, g.oy, g.inv_h, g.ny), cz = lrr_cell_clamp(qz, g.oz, g.inv_h, g.nz);
-    const int rmax = max(max(g.nx, g.ny), g.nz);
-    for (int r = 0; r <= rmax; ++r) {
-      const int side = 2 * r + 1, nface = 2 * side, per_plane = 4 * r, nruns = nface + (side - 2) * per_plane;
-      for (int t = lane; t < nruns; t += 32) {
-        int z, y, xa, xb;
-        if (t < nface) { z = (t < side) ? cz - r : cz + r; y = cy - r + (t % side); xa = cx - r; xb = cx + r; }
-        else {
-          const int u = t - nface, zi = u / per_plane, v = u % per_plane;
-          z = cz - r + 1 + zi;
-          if (v < 2) { y = (v == 0) ? cy - r : cy + r; xa = cx - r; xb = cx + r; }
-          else { const int m = v - 2; y = cy - r + 1 + (m >> 1); xa = xb = (m & 1) ? cx + r : cx - r; }
-        }
-        if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
-        xa = max(xa, 0); xb = min(xb, g.nx - 1);
-        if (xa > xb) continue;
-        const int row = (z * g.ny + y) * g.nx;
-        lrr_nn_scan(g.pos4, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), qx, qy, qz, best, best_s, best_o);
-      }
-      lrr_warp_min(best, best_s, best_o);
-      if (best_s >= 0) break;
-    }
-    if (best_s < 0) return -1;
-  }
+  if (best_s < 0 && !lrr_nn_shell_first(g, qx, qy, qz, best, best_s, best_o)) return -1;
   // ball scan: the lanes split the rows
   const double R = sqrt(best) * (1.0 + 1e-9) + slack;
   const int z0 = lrr_cell_clamp(qz - R, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + R, g.oz, g.inv_h, g.nz);
@@ -372,6 +377,89 @@ __device__ __forceinline__ int lrr_nn_pass_b_cert(const GridDev& g, double qx, d
   double sec = (best_s == gs) ? second : best;
 #pragma unroll
   for (int o = 16; o; o >>= 1) sec = fmin(sec, __shfl_xor_sync(0xffffffffu, sec, o));
+  const double bound = fmin(sqrt(sec), sqrt(gb) + margin) * (1.0 - 1e-9) - slack;
+  *bound_out = (sec > gb && bound > 0.0) ? bound : 0.0;
+  return gs;
+}
+
+// FLATTENED warp-cooperative ball scan (whole warp, one query, candidate known: st.best_s >= 0; st identical in every lane).
+// lrr_nn_pass_b_cert gives every lane its own rows: a far outlier's ball touches a few hundred rows of three or four points each and
+// every lane walks a chain of dependent loads (run bounds -> points -> next row), 15-25 us per query.  Here the run bounds of up to
+// LRR_FLAT_ROWS rows are fetched together (four independent loads per lane), a warp prefix sum lays the runs end to end in the
+// warp's row table (shared memory: `rowlo`, `rowbase`, LRR_FLAT_ROWS + 1 entries each) and the lanes stride over the flattened
+// points with four independent loads in flight: two round trips per LRR_FLAT_ROWS rows, whatever the shape of the ball.
+// The radius is fixed by the candidate (the neighbour of the previous iteration): every point within sqrt(st.best) + margin of the
+// query lies in a scanned run — the exactness argument of lrr_nn_pass_b_cert with no pruning at all.  Returns the sorted slot of
+// the exact neighbour (ties: lowest original index) and the certificate bound (0: none).
+#define LRR_FLAT_ROWS 128
+__device__ __forceinline__ int lrr_nn_ball_flat(const GridDev& g, double qx, double qy, double qz, NNState st, double margin, double* bound_out,
+                                                int* rowlo, int* rowbase) {
+  *bound_out = 0.0;
+  const int lane = threadIdx.x & 31;
+  const unsigned int full = 0xffffffffu;
+  const double slack = 1e-9 * g.h;
+  double best = st.best; int best_s = st.best_s, best_o = st.best_o; double second = 1e300;
+  const double Rm = sqrt(st.best) * (1.0 + 1e-9) + slack + margin, Rm2 = Rm * Rm;
+  const int z0 = lrr_cell_clamp(qz - Rm, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + Rm, g.oz, g.inv_h, g.nz);
+  const int y0 = lrr_cell_clamp(qy - Rm, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + Rm, g.oy, g.inv_h, g.ny);
+  const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+  for (int r0 = 0; r0 < nrows; r0 += LRR_FLAT_ROWS) {
+    const int nb = min(LRR_FLAT_ROWS, nrows - r0);
+    int lo4[LRR_FLAT_ROWS / 32], sz4[LRR_FLAT_ROWS / 32];
+#pragma unroll
+    for (int u = 0; u < LRR_FLAT_ROWS / 32; ++u) {
+      const int rl = 32 * u + lane;
+      lo4[u] = 0; sz4[u] = 0;
+      if (rl < nb) {
+        const int r = r0 + rl, z = z0 + r / ny, y = y0 + r % ny;
+        const double dz = lrr_slab_dist(qz, g.oz, g.h, z, slack), dy = lrr_slab_dist(qy, g.oy, g.h, y, slack);
+        const double dyz2 = dz * dz + dy * dy;
+        if (dyz2 <= Rm2) {
+          const double rx = sqrt(Rm2 - dyz2) * (1.0 + 1e-9) + slack;
+          const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
+          const int row = (z * g.ny + y) * g.nx;
+          lo4[u] = __ldg(g.cell_start + row + xa); sz4[u] = __ldg(g.cell_start + row + xb + 1);
+        }
+      }
+    }
+    int total = 0;
+    __syncwarp();   // the previous batch's points are done with the table
+#pragma unroll
+    for (int u = 0; u < LRR_FLAT_ROWS / 32; ++u) {
+      if (32 * u < nb) {   // warp-uniform
+        const int rl = 32 * u + lane, sz = (rl < nb) ? sz4[u] - lo4[u] : 0;
+        int inc = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(full, inc, o); if (lane >= o) inc += v; }
+        if (rl < nb) { rowlo[rl] = lo4[u]; rowbase[rl] = total + inc - sz; }
+        total += __shfl_sync(full, inc, 31);
+      }
+    }
+    if (lane == 0) rowbase[nb] = total;
+    __syncwarp();
+    for (int p0 = 0; p0 < total; p0 += 128) {
+      double4 P[4]; int J[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + 32 * u + lane;
+        J[u] = -1;
+        if (p < total) {
+          int ra = 0, rb = nb;   // last row with rowbase <= p
+          while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (rowbase[mid] <= p) ra = mid; else rb = mid; }
+          J[u] = rowlo[ra] + (p - rowbase[ra]);
+          P[u] = lrr_ld_pos4(g.pos4 + J[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (J[u] >= 0) lrr_nn_upd2(P[u], J[u], qx, qy, qz, best, best_s, best_o, second);
+    }
+  }
+  __syncwarp();
+  double gb = best; int gs = best_s, go = best_o;
+  lrr_warp_min(gb, gs, go);
+  double sec = (best_s == gs) ? second : best;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sec = fmin(sec, __shfl_xor_sync(full, sec, o));
   const double bound = fmin(sqrt(sec), sqrt(gb) + margin) * (1.0 - 1e-9) - slack;
   *bound_out = (sec > gb && bound > 0.0) ? bound : 0.0;
   return gs;

@@ -8,7 +8,7 @@
 #include "lrr_linalg.cuh"
 
 #define LRR_NPHASE 12
-enum { PH_MATCH = 0, PH_NORM1, PH_NORM2, PH_WEIGHT, PH_COLLECT, PH_ACCUM, PH_RESID, PH_MUSE, PH_METRIC, PH_OBJCOV, PH_BATCH, PH_OTHER };
+enum { PH_MATCH = 0, PH_NORM1, PH_NORM2, PH_WEIGHT, PH_COLLECT, PH_ACCUM, PH_RESID, PH_MUSE, PH_METRIC, PH_OBJCOV, PH_BATCH, PH_RESTAMP };
 struct lrr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -82,6 +82,8 @@ struct lrr_est {
   // every query of every direction was kept by its certificate in the last iteration (Scal::match_left == 0): the next iteration is
   // launched without the staged search, pass B and the normalisation (speculative plan; verified on the device, see estimate_and_pull)
   bool steady_hint = false;
+  // the certificate pass of the NEXT find_closest has already run, as the trailing (residual) pass of the last one_iteration (lrr_tile.cu)
+  bool pre_matched = false;
   bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
   bool icp() const { return kind == LRR_CDCL_ICP; }   // cdcl_estimation_ICP<2,4>: no point ramp, scale constant 2, strength by sum
   bool rrl() const { return kind == LRR_RRL_FWD || kind == LRR_RRL_SYM; }

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
   lrr_pdl_enter();
   __shared__ PhaseShared sh;
   __shared__ double s_T[2][15];
+  __shared__ int s_rows[LRR_NWARPS][2 * (LRR_FLAT_ROWS + 1)];   // row tables of the flattened ball scan, one per warp
+  int* const rowtab = (a.flags & LRR_F_NOFLAT) ? nullptr : s_rows[threadIdx.x >> 5];
   lrr_tl(1, 0);
   {
     // nothing queued in any direction (the steady state: every query kept by its certificate or finished by the staged search):
@@ -201,9 +203,9 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
   double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
   const int wg = blockIdx.x * LRR_NWARPS + (threadIdx.x >> 5), nwg = gridDim.x * LRR_NWARPS;
   if (a.ndir == 2) {
-    if (blockIdx.x & 1) { lrr_match_b_body_dynamic(a.d[1], a.flags, s_T[1], a.ticket + 7, acc1, wg, nwg); lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg); }
-    else { lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg); lrr_match_b_body_dynamic(a.d[1], a.flags, s_T[1], a.ticket + 7, acc1, wg, nwg); }
-  } else lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg);
+    if (blockIdx.x & 1) { lrr_match_b_body_dynamic(a.d[1], a.flags, s_T[1], a.ticket + 7, acc1, wg, nwg, rowtab); lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg, rowtab); }
+    else { lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg, rowtab); lrr_match_b_body_dynamic(a.d[1], a.flags, s_T[1], a.ticket + 7, acc1, wg, nwg, rowtab); }
+  } else lrr_match_b_body_dynamic(a.d[0], a.flags, s_T[0], a.ticket + 6, acc0, wg, nwg, rowtab);
   lrr_tl(1, 1);
   double v[8] = {acc0[0], acc0[1], acc0[2], acc0[3], acc1[0], acc1[1], acc1[2], acc1[3]};
   if (lrr_scope(a, 0).template reduce<8>(v, sh.out, sh.tmp)) {
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
 }
 static bool lrr_no_tile() { static const bool v = getenv("LRR_NO_TILE") != nullptr; return v; }   // A/B switch for measurements
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches, bool cert_only) {
-  if (cert_only) { lrr_k_match_cert(a, st, launches); return; }   // speculative plan: the caller has checked that every direction is certified
+  if (cert_only) { lrr_k_match_cert(a, st, launches); return; }   // the caller has checked that every direction is certified
   if (!lrr_no_tile() && lrr_match_tile_usable(a) && lrr_match_cert_usable(a)) lrr_k_match_cert(a, st, launches);
   lrr_k_match_rest(a, st, launches);
 }
@@ -236,6 +238,30 @@ void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches) {
   // queue length is only known on the device: a fixed grid of warps strides over it
   dim3 gridb(resident_width(k_match_hard, LRR_THREADS, 1, 32LL * maxM(a)));
   lrr_launch_pdl(k_match_hard, gridb, dim3(LRR_THREADS), 0, st, a); ++*launches;
+}
+
+// Certified finest level (DirArgs::stamp_in_match == 0): no match kernel stamps there — a kept match is not touched at all — so the
+// "unique matched to-features" stamps (the reference's std::set of smart pointers, cdcl :1173-1189) are laid down here, in a fresh
+// epoch, right before the normalisation reads them; like the normalisation itself only when some match changed.
+__global__ void __launch_bounds__(LRR_THREADS) k_restamp(const __grid_constant__ EstArgs a, int skip_clean) {
+  lrr_pdl_enter();
+  const DirArgs& d = a.d[a.src];
+  if (skip_clean && !d.sc->norm_dirty) return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.M; k += gridDim.x * blockDim.x) {
+    const int s = d.sidx[k];
+    if (s >= 0) atomicMin(d.stamp + s, d.tag | (unsigned long long)(unsigned int)k);
+  }
+}
+__global__ void k_fill_ones(double* __restrict__ w, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = 1.0;
+}
+void lrr_k_fill_ones(double* w, int n, cudaStream_t st, long long* launches) {
+  if (n <= 0) return;
+  k_fill_ones<<<(n + 255) / 256, 256, 0, st>>>(w, n); ++*launches;
+}
+void lrr_k_restamp(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean) {
+  lrr_launch_pdl(k_restamp, dim3(nblk_for(a.d[a.src].M)), dim3(LRR_THREADS), 0, st, a, skip_clean); ++*launches;
 }
 
 // skip_clean: the host knows that the normalisation scalars on the device are those of this estimator's last estimate_LS in the

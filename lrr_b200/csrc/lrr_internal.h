@@ -16,7 +16,7 @@
 #include <stdint.h>
 
 #define LRR_MAX_BLOCKS 1184   // 148 SMs x 8
-#define LRR_NRED 112          // max doubles reduced per block in one pass (108 moments)
+#define LRR_NRED 128          // max doubles reduced per block in one pass (108 moments + 12 sums of the fused estimate pass)
 #define LRR_SEL_FINE 65536    // fine bins of the order-statistic histogram
 #define LRR_SEL_COARSE 1024   // coarse bins (fine >> 6)
 #define LRR_SEL_CAP 2048      // candidate capacity of the final exact selection
@@ -92,6 +92,15 @@ struct Scal {
   double n_nonzero, sel_below[2];
   double G, S;
   double res_sum_r2, res_sum_wr2, res_sum_w, res_sum_wr, res_count;   // resid phase
+  // PRE-MATCH (lrr_tile.cu, k_match_cert in its trailing role): the residual pass that ends an iteration at the finest level is at
+  // the same time the certificate pass of the NEXT find_closest (same x, q, P, same e^T P e under the same transform).  When it
+  // keeps every query it writes the next match's sums into sum_loc / sum_r2 at once; otherwise those stay what they are (the
+  // matches of the finished iteration remain intact for any call in between) and the kept part waits here until the staged search
+  // completes the match (k_match_tile's finalizer folds it in).
+  double pm_sum_loc[3], pm_sum_r2;
+  double used_sum_r2;   // sum_r2 of the match the last estimate was made from (RMS_error "before", cdcl :440): copied by the weight phase
+  double cert_failed, passb_queries;   // instrumentation: queries the last certificate pass could not keep / queries finished by pass B in the last find_closest
+  double wfac;          // fused estimate pass: the weights it stored are final up to this factor 1 / (G S), applied by the trailing pass
   double mom[LRR_NRED];
   double AtA[144], Atb[12];
   double ang_num, ang_den;
@@ -128,6 +137,10 @@ struct DirArgs {
   double *w, *r2, *gkey, *skey;
   unsigned long long* stamp;   // n_to: (epoch, match position) of the representative match of a to-feature
   unsigned long long tag;      // epoch tag of the current matches (high bits)
+  // 1: every finished match stamps its to-feature at once (ramp levels, batched mode).  0: the certified finest level — kept matches
+  // are not touched at all there, so the stamps are laid down by k_restamp right before the normalisation reads them (and only when
+  // the match set changed).
+  int stamp_in_match;
   // queue of the queries the 27-cell pass could not finish (pass B, one warp per query)
   int* hq_k; double* hq_best; int* hq_s; int* hq_o; int* hq_count;
   int* prev_s;                 // n_in: neighbour slot of each from-feature in its last match (-1: none) = search candidate
@@ -157,6 +170,7 @@ enum {
   LRR_F_NO_OTHER_RENORM = 2048,   // ... and only the estimated direction's transform goes through normalize / unnormalize
   LRR_F_ICP = 4096,       // cdcl_estimation_ICP: scale constant 2.0 (cdcl_estimation_ICP.txx:580), strength weights normalised by their SUM (:607-637)
   LRR_F_SIM2D = 8192,     // cdcl_trans_similarity2d<2,4>: J = [x -y 1 0; y x 0 1], parameters (s cos a, s sin a, tx, ty)
+  LRR_F_NOFLAT = 16384,   // A/B switch: lane-per-row ball scans instead of the flattened warp-cooperative one (lrr_dev.cuh)
   LRR_F_BRACKET = 512     // order statistics from the window around the previous iteration's values (no histogram atomics, no collect pass)
 };
 
@@ -217,7 +231,11 @@ void lrr_k_tile_mirror(const int* proc, const double* fx, const double* fy, cons
 bool lrr_match_tile_usable(const EstArgs& a);
 void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches);
 bool lrr_match_cert_usable(const EstArgs& a);
-void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches);
+// mode: LRR_CERT_RESID (1) = also the residual pass of the finished iteration (+ result mailbox), LRR_CERT_RESCALE (2) = the stored
+// weights are final up to Scal::wfac (fused estimate pass)
+void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches, int mode = 0, double* mbox = nullptr, unsigned long long seq = 0,
+                      int pull_mask = 0, int nhead = 0);
+void lrr_k_restamp(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);   // stamps of the source direction's matches (DirArgs::stamp_in_match == 0)
 void lrr_tile_set_timeline(unsigned long long* p);
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);

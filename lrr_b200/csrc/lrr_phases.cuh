@@ -75,22 +75,8 @@ __device__ __forceinline__ void lrr_match_finish(const DirArgs& a, bool rigid, i
     const double4 q = lrr_ld_pos4(a.to.grid.pos4 + s);
     double P[6]; lrr_ld_P6(a.to.rec, s, P);
     r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
-    atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
+    if (a.stamp_in_match) atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
   }
-  a.r2[k] = r2;
-  a.w[k] = 1.0;   // cdcl :645
-  if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
-  acc[3] += r2;
-}
-
-// a match KEPT by its neighbour certificate (identity order: position k == from-feature k; neighbour slot s, its location q and
-// projector P already loaded): prev_s, its mirror and the certificate stay as they are; the match index, the residual under the new
-// transform, the stamp of the new epoch and the sums are produced
-__device__ __forceinline__ void lrr_match_keep(const DirArgs& a, bool rigid, int k, double x, double y, double z, double yx, double yy,
-                                               double yz, int s, const double4& q, const double (&P)[6], double (&acc)[4]) {
-  a.sidx[k] = s;
-  const double r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
-  atomicMin(a.stamp + s, a.tag | (unsigned long long)(unsigned int)k);
   a.r2[k] = r2;
   a.w[k] = 1.0;   // cdcl :645
   if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
@@ -158,8 +144,9 @@ __device__ __forceinline__ void lrr_match_a_body_dynamic(const DirArgs& a, int f
   }
 }
 
-// one queued query, whole warp
-__device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, const double* s_T, int qi, double (&acc)[4]) {
+// one queued query, whole warp.  rowtab: the warp's row table in shared memory (2 x (LRR_FLAT_ROWS + 1) ints) for the flattened
+// ball scan, or null (batched mode: the lane-per-row scan)
+__device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, const double* s_T, int qi, double (&acc)[4], int* rowtab = nullptr) {
   const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
   const bool rigid = (flags & LRR_F_RIGID) != 0;
   const int lane = threadIdx.x & 31;
@@ -172,7 +159,15 @@ __device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, con
   int s; double bound = 0.0;
   // (certificates only where they are read: finest level in tile order; margin = an eighth of a cell, far above the per-iteration
   //  motion near convergence and ~1.4x the ball volume at worst)
-  if (a.proof && a.todo && a.M == a.n_in) s = lrr_nn_pass_b_cert(a.to.grid, yx, yy, yz, st, 0.125 * a.to.grid.h, &bound);
+  const bool cert = a.proof && a.todo && a.M == a.n_in;
+  if (rowtab) {
+    bool have = st.best_s >= 0;
+    if (!have) have = lrr_nn_shell_first(a.to.grid, yx, yy, yz, st.best, st.best_s, st.best_o);   // (certificate next time, as before)
+    const bool had = a.hq_s[qi] >= 0;
+    s = have ? lrr_nn_ball_flat(a.to.grid, yx, yy, yz, st, (cert && had) ? 0.125 * a.to.grid.h : 0.0, &bound, rowtab, rowtab + LRR_FLAT_ROWS + 1) : -1;
+    if (!(cert && had)) bound = 0.0;
+  }
+  else if (cert) s = lrr_nn_pass_b_cert(a.to.grid, yx, yy, yz, st, 0.125 * a.to.grid.h, &bound);
   else s = lrr_nn_pass_b(a.to.grid, yx, yy, yz, st);
   if (lane == 0) lrr_match_finish(a, rigid, kq, i, x, y, z, yx, yy, yz, s, acc, (bound > 0.0 && i == kq) ? 2 : 0, bound);
 }
@@ -180,7 +175,7 @@ __device__ __forceinline__ void lrr_match_b_one(const DirArgs& a, int flags, con
 // following ones are pulled from the counter — a launch whose queue is shorter than the number of warps (the steady state: empty)
 // does not touch the counter at all (a few thousand same-address atomics are several microseconds of an otherwise empty kernel)
 __device__ __forceinline__ void lrr_match_b_body_dynamic(const DirArgs& a, int flags, const double* s_T, unsigned int* counter, double (&acc)[4],
-                                                         int first_item = -1, int nstatic = 0) {
+                                                         int first_item = -1, int nstatic = 0, int* rowtab = nullptr) {
   const int lane = threadIdx.x & 31;
   const int nq = *a.hq_count;
   if (nq <= 0) return;
@@ -193,7 +188,7 @@ __device__ __forceinline__ void lrr_match_b_body_dynamic(const DirArgs& a, int f
     }
     pull = true;
     if ((int)qi >= nq) break;
-    lrr_match_b_one(a, flags, s_T, (int)qi, acc);
+    lrr_match_b_one(a, flags, s_T, (int)qi, acc, rowtab);
     __syncwarp();
   }
 }
@@ -210,6 +205,7 @@ __device__ __forceinline__ void lrr_match_finalize(const DirArgs& a, int flags, 
   Scal* sc = a.sc;
   sc->sum_loc[0] = tot[0]; sc->sum_loc[1] = tot[1]; sc->sum_loc[2] = tot[2]; sc->sum_r2 = tot[3];
   sc->res_sum_r2 = tot[3]; sc->res_count = (double)a.M;
+  sc->passb_queries = (double)*a.hq_count;
   *a.hq_count = 0;
   if (flags & LRR_F_RIGID) {   // make_incremental: the matches' from_ are now clones mapped through the current transform
     for (int i = 0; i < 9; ++i) sc->Ag[i] = sc->A[i];
@@ -569,7 +565,7 @@ __device__ bool lrr_phase_weight(const Scope& scope, const DirArgs& a, int flags
     a.w[k] = w; a.gkey[k] = gk; a.skey[k] = sk;
   }
   const bool fin = scope.template reduce<3>(acc, sh.out, sh.tmp);
-  if (fin && threadIdx.x == 0) { sc->n_nonzero = sh.out[0]; sc->sel_below[0] = sh.out[1]; sc->sel_below[1] = sh.out[2]; sc->scale = scale; sc->scale_estimated = 1; }
+  if (fin && threadIdx.x == 0) { sc->n_nonzero = sh.out[0]; sc->sel_below[0] = sh.out[1]; sc->sel_below[1] = sh.out[2]; sc->scale = scale; sc->scale_estimated = 1; sc->used_sum_r2 = sc->sum_r2; }
   return fin;
 }
 

@@ -22,6 +22,8 @@
 #define LRR_TILE_THREADS (32 * LRR_TILE_WARPS)
 #define LRR_TW_CAP 512      // staged points per warp
 #define LRR_TW_ROWS 128     // staged (y,z) rows per warp
+#define LRR_TILE_SPARSE 4   // work-list entries with at most this many queries left are searched query by query (flattened ball scan)
+static_assert(LRR_FLAT_ROWS <= LRR_TW_ROWS, "the flattened ball scan uses the warp's row table");
 
 struct TileWarp {
   double px[LRR_TW_CAP], py[LRR_TW_CAP], pz[LRR_TW_CAP];
@@ -188,6 +190,33 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
     int ch = (int)wi; unsigned int lanes = full;
     if (use_todo) { const int2 e = __ldcg(a.todo + wi); ch = e.x; lanes = (unsigned int)e.y; }
     const int2 qq = __ldg(a.chunk_tab + ch);
+    if (use_todo && !(flags & LRR_F_NOFLAT) && __popc(lanes) <= LRR_TILE_SPARSE) {
+      // SPARSE entry (near convergence the certificate pass leaves one or two queries of a chunk over, typically far outliers whose
+      // two nearest features are almost equally far): staging the chunk's whole box and scanning it in every lane costs ~25 us of
+      // single-warp latency for 31 idle lanes.  The warp takes the queries one by one instead, each with the flattened ball scan
+      // around its previous neighbour (lrr_dev.cuh) — exact, with a new certificate, nothing queued for pass B.
+      __syncwarp();
+      unsigned int m = lanes;
+      while (m) {
+        const int L = __ffs(m) - 1; m &= m - 1;
+        const int tqs = qq.x + L;
+        if (tqs >= qq.y) continue;
+        const int ks = __ldg(a.proc + tqs);
+        const double xs = __ldg(a.fx + ks), ys = __ldg(a.fy + ks), zs = __ldg(a.fz + ks);
+        double mx, my, mz;
+        lrr_map_exact(A, tt, cc, xs, ys, zs, mx, my, mz);
+        NNState st; st.best = 1e300; st.best_s = a.prev_s[ks]; st.best_o = 0x7fffffff;
+        const bool had = st.best_s >= 0;
+        bool have = had;
+        if (had) { const double4 pc = lrr_ld_pos4(g.pos4 + st.best_s); st.best = lrr_dist2_exact(mx, my, mz, pc.x, pc.y, pc.z); st.best_o = lrr_pos4_orig(pc); }
+        else have = lrr_nn_shell_first(g, mx, my, mz, st.best, st.best_s, st.best_o);
+        double bnd = 0.0;
+        const int sres = have ? lrr_nn_ball_flat(g, mx, my, mz, st, had ? 0.125 * g.h : 0.0, &bnd, W.rowlo, W.rowbase) : -1;
+        if (lane == 0) lrr_match_finish(a, rigid, ks, ks, xs, ys, zs, mx, my, mz, sres, acc, (a.proof && had && bnd > 0.0) ? 2 : 0, bnd);
+        __syncwarp();
+      }
+      continue;
+    }
     const int tq = qq.x + lane;
     const bool valid = tq < qq.y && ((lanes >> lane) & 1u);
     int k = 0; double x = 0, y = 0, z = 0, yx = 0, yy = 0, yz = 0;
@@ -370,8 +399,9 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
       Scal* sc = d.sc;
       sc->norm_dirty = 1;
       if (!lrr_dir_certified(d)) sc->match_left = 1;
-      if (lrr_dir_certified(d)) {   // the certificate pass wrote its share of the sums
-        sc->sum_loc[0] += s_out[0]; sc->sum_loc[1] += s_out[1]; sc->sum_loc[2] += s_out[2]; sc->sum_r2 += s_out[3];
+      if (lrr_dir_certified(d)) {   // the certificate pass left its share of the sums in pm_*
+        sc->sum_loc[0] = sc->pm_sum_loc[0] + s_out[0]; sc->sum_loc[1] = sc->pm_sum_loc[1] + s_out[1]; sc->sum_loc[2] = sc->pm_sum_loc[2] + s_out[2];
+        sc->sum_r2 = sc->pm_sum_r2 + s_out[3];
         *d.todo_count = 0;
       } else { sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3]; }
       *counter = 0;
@@ -383,25 +413,53 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
 // ---- certificate pass ------------------------------------------------------------------------------------------------
 // NEIGHBOUR CERTIFICATE of a from-feature: (y0, B) = the mapped position at which its neighbour q_prev was proven the UNIQUE nearest
 // to-feature, and a lower bound B on the distance from y0 to every OTHER to-feature (written by the staged search: second smallest
-// staged distance / nearest box face; by pass B: second smallest distance inside the inflated ball / its radius).  For a new
-// mapped position y and any other feature p:  |y - p| >= |y0 - p| - |y - y0| >= B - |y - y0|,  so
+// staged distance / nearest box face; by the ball scans: second smallest distance inside the inflated ball / its radius).  For a
+// new mapped position y and any other feature p:  |y - p| >= |y0 - p| - |y - y0| >= B - |y - y0|,  so
 //        |y - q_prev| + |y - y0| < B     =>     q_prev is still the unique nearest neighbour (no search, no tie possible).
 // ICP moves the mapped positions less and less, so near convergence almost every query is kept this way; the others go to the
 // staged search through the work list.  The result is the exact neighbour either way (bit-exact index sets vs the oracle).
 // One warp per chunk, no shared-memory staging: full occupancy, coalesced along the tile order.
+//
+// TWO ROLES IN ONE PASS.  At the finest level the match of iteration i+1 is the match of iteration i for every kept query, and the
+// certificate test evaluates y = T(x), q, P and e^T P e of exactly that match under exactly the transform the residual pass of
+// iteration i (RMS_error / weighted_error after estimate_LS: cdcl :499, rrl sym :366) evaluates them under.  So the pass that ENDS
+// one_iteration(i) is this kernel with LRR_CERT_RESID: it produces the residual sums of iteration i over all matches (weights of
+// iteration i) AND runs the certificate test of find_closest(i+1); one_iteration(i+1) then starts at the weights (pre-match,
+// lrr_capi.cu).  A kept match is not touched at all (index, certificate and — see DirArgs::stamp_in_match — stamp stay what they
+// are); the residual r2 is rewritten for every match, as the residual pass does.  Queries that are not kept stay what they were in
+// iteration i until the staged search completes the match, and the sums of the kept part wait in Scal::pm_*.
 #define LRR_CERT_THREADS 256
 #ifndef LRR_CERT_MINBLK
-#define LRR_CERT_MINBLK 3   // 79 registers, no spills: measured 95.8 us per iteration against 99.7 at 4 blocks per SM (64 registers, 144 B spilled)
+#define LRR_CERT_MINBLK 3
 #endif
-__global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cert(const __grid_constant__ EstArgs a) {
+enum { LRR_CERT_RESID = 1, LRR_CERT_RESCALE = 2 };
+#define LRR_MBOX_STRIDE 512
+#define LRR_MBOX_FLAG 500
+// (same protocol as lrr_mailbox_post in lrr_icp.cu: slot d = mbox + 512 d doubles, sequence number at [500])
+__device__ __forceinline__ void lrr_cert_mailbox_post(const DirArgs& d, int dir, double* mbox, unsigned long long seq, int nhead) {
+  __syncthreads();
+  const double* src = reinterpret_cast<const double*>(d.sc);
+  for (int i = threadIdx.x; i < nhead; i += blockDim.x) mbox[dir * LRR_MBOX_STRIDE + i] = __ldcg(src + i);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned long long*>(mbox + dir * LRR_MBOX_STRIDE + LRR_MBOX_FLAG) = seq; __threadfence_system(); }
+}
+__global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cert(const __grid_constant__ EstArgs a, int mode, double* mbox, unsigned long long seq,
+                                                                                  int pull_mask, int nhead) {
   lrr_pdl_enter();
   __shared__ double s_T[15];
-  __shared__ double s_out[8], s_tmp[8 * (LRR_CERT_THREADS / 32)];
+  __shared__ double s_out[16], s_tmp[16 * (LRR_CERT_THREADS / 32)];
   const int dir = blockIdx.y;
   const DirArgs& d = a.d[dir];
+  const bool resid = (mode & LRR_CERT_RESID) != 0;
   lrr_tl(5, 0);
+  if (resid && (d.sc->status & (LRR_ST_SELECT_MISS | LRR_ST_NOT_STEADY))) {
+    // the estimate was not committed (order-statistic window missed / speculative plan refused): nothing changes, the host reruns
+    if (mbox && blockIdx.x == 0 && (pull_mask & (1 << dir))) lrr_cert_mailbox_post(d, dir, mbox, seq, nhead);
+    return;
+  }
   lrr_stage_transform(d.sc, s_T);
-  double acc[4] = {0, 0, 0, 0};
+  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [9]: queries not kept (instrumentation); kept part of the next match: sum of from-locations (3), sum r2; residual pass: r2, w r2, w, w sqrt(r2), count
   if (lrr_dir_certified(d)) {
     const double* A = s_T; const double* tt = s_T + 9; const double* cc = s_T + 12;
     const bool rigid = (a.flags & LRR_F_RIGID) != 0;
@@ -410,8 +468,9 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
     const int lane = threadIdx.x & 31;
     const int nchunks = __ldg(d.nchunks);
     const int wpb = LRR_CERT_THREADS / 32;
+    const double wfac = (mode & LRR_CERT_RESCALE) ? d.sc->wfac : 1.0;
     // per query: one hop for everything at its tile-order position (neighbour, certificate, location, match position), one hop for
-    // the neighbour's location and projector (both issued before the certificate is checked), then the stores
+    // the neighbour's location and projector and the match's weight (all issued before the certificate is checked), then the stores
     const int cstep = gridDim.x * wpb;
     int ch = blockIdx.x * wpb + (threadIdx.x >> 5);
     int2 qq = ch < nchunks ? __ldg(d.chunk_tab + ch) : make_int2(0, 0);
@@ -427,39 +486,60 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
         const double2* pr = reinterpret_cast<const double2*>(d.proof + tq);
         const double2 p0 = __ldcg(pr), p1 = __ldcg(pr + 1);
         const double x = __ldg(d.tfx + tq), y = __ldg(d.tfy + tq), z = __ldg(d.tfz + tq);
-        if (sp >= 0 && p1.y > 0.0) {
+        if (sp >= 0 && (resid || p1.y > 0.0)) {
           const double4 q = lrr_ld_pos4(g.pos4 + sp);
           double P[6]; lrr_ld_P6(d.to.rec, sp, P);
+          double w = 0.0;
+          if (resid) w = d.w[k];
           double yx, yy, yz;
           lrr_map_exact(A, tt, cc, x, y, z, yx, yy, yz);
-          const double dq = sqrt(lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z));
-          const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
-          const double dm = sqrt(ex * ex + ey * ey + ez * ez);
-          // (1e-9 relative + slack covers the rounding of the square roots and sums; B itself was rounded down when written)
-          if ((dq + dm) * (1.0 + 1e-9) + slack < p1.y) { lrr_match_keep(d, rigid, k, x, y, z, yx, yy, yz, sp, q, P, acc); kept = true; }
-          if (kept && g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + 7, 1ull);   // development counter (scripts/timeline.py)
-          if (!kept && g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + 18, 1ull);
+          const double r2 = lrr_proj_r2(yx - q.x, yy - q.y, yz - q.z, P[0], P[1], P[2], P[3], P[4], P[5]);
+          if (resid) {
+            if (mode & LRR_CERT_RESCALE) { w *= wfac; d.w[k] = w; }
+            d.r2[k] = r2;
+            acc[4] += r2; acc[5] += w * r2; acc[6] += w; acc[7] += sqrt(r2) * w; acc[8] += 1.0;
+          }
+          if (p1.y > 0.0) {
+            const double dq = sqrt(lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z));
+            const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
+            const double dm = sqrt(ex * ex + ey * ey + ez * ez);
+            // (1e-9 relative + slack covers the rounding of the square roots and sums; B itself was rounded down when written)
+            if ((dq + dm) * (1.0 + 1e-9) + slack < p1.y) {
+              kept = true;
+              if (!resid) d.r2[k] = r2;
+              if (rigid) { acc[0] += yx; acc[1] += yy; acc[2] += yz; } else { acc[0] += x; acc[1] += y; acc[2] += z; }
+              acc[3] += r2;
+            }
+          }
+          if (g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + (kept ? 7 : 18), 1ull);   // development counters (scripts/timeline.py)
         } else if (g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + (sp < 0 ? 16 : 17), 1ull);
       }
       const unsigned int rest = __ballot_sync(0xffffffffu, valid && !kept);
-      if (rest && lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); }
+      if (rest && lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); acc[9] += (double)__popc(rest); }
       ch = chn; qq = qqn;
     }
   }
   lrr_tl(5, 1);
   const GridScope scope = lrr_scope_of(a, dir);
-  if (scope.reduce<4>(acc, s_out, s_tmp)) {
+  if (scope.reduce<10>(acc, s_out, s_tmp)) {
     if (threadIdx.x == 0) {
-      Scal* sc = d.sc; sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3];
+      Scal* sc = d.sc;
+      sc->cert_failed = s_out[9];
       // every query kept <=> nothing on the work list (this block is the last one of the direction: all appends are visible)
       const int left = lrr_dir_certified(d) ? *reinterpret_cast<volatile int*>(d.todo_count) + *reinterpret_cast<volatile int*>(d.hq_count) : 1;
       sc->match_left = left;
-      if (left > 0) sc->norm_dirty = 1;
-      else {   // nothing follows for this direction: the bookkeeping of a finished find_closest (k_match_hard repeats it when it is launched)
+      if (left > 0) {
+        sc->norm_dirty = 1;
+        sc->pm_sum_loc[0] = s_out[0]; sc->pm_sum_loc[1] = s_out[1]; sc->pm_sum_loc[2] = s_out[2]; sc->pm_sum_r2 = s_out[3];
+      } else {   // nothing follows for this direction: the bookkeeping of a finished find_closest (k_match_hard repeats it when it is launched)
         const double tot[4] = {s_out[0], s_out[1], s_out[2], s_out[3]};
         lrr_match_finalize(d, a.flags, tot);
       }
+      if (resid) {
+        sc->res_sum_r2 = s_out[4]; sc->res_sum_wr2 = s_out[5]; sc->res_sum_w = s_out[6]; sc->res_sum_wr = s_out[7]; sc->res_count = s_out[8];
+      }
     }
+    if (mbox && (pull_mask & (1 << dir))) lrr_cert_mailbox_post(d, dir, mbox, seq, nhead);
   }
   lrr_tl(5, 3);
 }
@@ -467,14 +547,14 @@ bool lrr_match_cert_usable(const EstArgs& a) {
   for (int d = 0; d < a.ndir; ++d) if (a.d[d].proof && a.d[d].todo && a.d[d].chunk_tab && a.d[d].proc && a.d[d].M == a.d[d].n_in) return true;
   return false;
 }
-void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches) {
+void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches, int mode, double* mbox, unsigned long long seq, int pull_mask, int nhead) {
   int maxM = a.d[0].M; if (a.ndir == 2 && a.d[1].M > maxM) maxM = a.d[1].M;
   int nb = (maxM / 32 + LRR_CERT_THREADS / 32 - 1) / (LRR_CERT_THREADS / 32) + 1;   // about one chunk per warp ...
   static int per_sm = 0;
   if (!per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_cert, LRR_CERT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1; }
   nb = std::max(1, std::min(nb, per_sm * lrr_num_sms() / a.ndir));   // ... but every block resident at once (no second wave)
   dim3 grid(nb, a.ndir);
-  lrr_launch_pdl(k_match_cert, grid, dim3(LRR_CERT_THREADS), 0, st, a); ++*launches;
+  lrr_launch_pdl(k_match_cert, grid, dim3(LRR_CERT_THREADS), 0, st, a, mode, mbox, seq, pull_mask, nhead); ++*launches;
 }
 
 bool lrr_match_tile_usable(const EstArgs& a) {

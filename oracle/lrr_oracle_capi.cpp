@@ -219,6 +219,8 @@ int lrro_est_transfer_cov(lrro_est* e, int d, double* S9) {
   FwdEst* f = e->dir(d); if (!f) return LRR_ERR_INVALID;
   f->compute_transfer_error_covariance(); std::memcpy(S9, f->trans_->covarJ, 72); return LRR_OK;
 }
+// (instrumentation of the GPU neighbour search: nothing to report on the CPU)
+int lrro_est_get_stats(lrro_est*, lrr_est_stats* s) { std::memset(s, 0, sizeof(*s)); return LRR_OK; }
 int lrro_est_get_state(lrro_est* e, lrr_est_state* s) {
   std::memset(s, 0, sizeof(*s));
   for (int d = 0; d < 2; ++d) if (FwdEst* f = e->dir(d)) {

@@ -231,25 +231,38 @@ def test_order_statistic_window_miss_and_rerun(gpu_lib, oracle_lib):
         compare_state(g, o, dirs=(0, 1))
 
 
-def test_fused_iteration_kernel():
-    """The cooperative one-kernel-per-iteration path (opt-in, LRR_FUSED=1) reproduces the oracle as well."""
-    import os, subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, numpy as np; sys.path.insert(0, %r)\n"
-        "from lrr_b200 import synth, lib\nfrom lrr_b200.capi import Lib\n"
-        "pair = synth.make_pair(52, 9000, 8000, size=100.0)\nres = []\n"
-        "for L in (lib(), Lib(%r, 'lrro_')):\n"
-        "    ctx = L.context(); e = ctx.estimator('rrl_sym', ctx.upload(pair['moving']), ctx.upload(pair['fixed']), 12)\n"
-        "    e.set_transform(*pair['init']); conv = [e.one_iteration(i) for i in range(12)]\n"
-        "    res.append((e.get_transform(0), e.get_matches(0), e.get_matches(1), conv))\n"
-        "(Tg, mg, bg, cg), (To, mo, bo, co) = res\n"
-        "assert cg == co and np.array_equal(mg[1], mo[1]) and np.array_equal(bg[1], bo[1])\n"
-        "for k in ('A', 't', 'cov'): assert np.linalg.norm(Tg[k] - To[k]) / np.linalg.norm(To[k]) < 1e-5, k\n"
-        "print('fused ok', lib().context().launch_count())\n"
-    ) % (root, os.path.join(root, "oracle", "liblrr_oracle.so"))
-    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LRR_FUSED="1"), capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout + out.stderr
+def test_pipelined_finest_level_with_calls_in_between(gpu_lib, oracle_lib):
+    """At the certified finest level the pass that ends one_iteration(i) is at the same time the certificate pass of
+    find_closest(i+1) (pre-match, lrr_tile.cu / lrr_capi.cu).  Everything a caller can ask for between two iterations must still
+    be that of the FINISHED iteration — matches, weights, metrics, estimate_LS_backward, explicit find_closest — whether or not
+    the pre-match kept every query."""
+    pair = synth.make_pair(54, 9000, 8500, size=100.0)
+    for kind in ("rrl_sym", "cdcl_fwd"):
+        es = []
+        for lib in (gpu_lib, oracle_lib):
+            ctx = lib.context()
+            e = ctx.estimator(kind, ctx.upload(pair["moving"]), ctx.upload(pair["fixed"]), 12)
+            e.set_flags(True, True); e.set_transform(*pair["init"])
+            dirs = (0, 1) if "sym" in kind else (0,)
+            for d in dirs:
+                e.set_number_points(10 ** 9, d)
+            es.append(e)
+        g, o = es
+        for it in range(14):
+            assert g.one_iteration(it) == o.one_iteration(it), (kind, it)
+            compare_state(g, o, dirs=dirs)
+            for d in dirs:
+                for m in ("rms", "weighted"):
+                    a, b = g.metric(m, d), o.metric(m, d)
+                    assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (kind, it, d, m, a, b)
+            if it == 5 and "sym" in kind:
+                g.estimate_ls_backward(False); o.estimate_ls_backward(False)
+                compare_state(g, o, dirs=dirs)
+            if it == 8:
+                g.find_closest(); o.find_closest()
+                for d in dirs:
+                    gm, om = g.get_matches(d), o.get_matches(d)
+                    assert np.array_equal(gm[1], om[1]) and np.array_equal(gm[2], om[2]), (kind, d)
 
 
 def test_speculative_plan_and_its_fallback():
@@ -283,7 +296,7 @@ def test_speculative_plan_and_its_fallback():
         "        for k in ('A', 't', 'cov'): assert np.linalg.norm(Tg[k] - To[k]) / np.linalg.norm(To[k]) < 1e-7, (kind, it, k)\n"
         "print('spec ok')\n"
     ) % (root, os.path.join(root, "oracle", "liblrr_oracle.so"))
-    for env in ({"LRR_SPEC_FORCE": "1"}, {}):
+    for env in ({"LRR_SPEC_FORCE": "1"}, {}, {"LRR_NO_PIPE": "1"}, {"LRR_NO_FLAT": "1"}, {"LRR_NO_PIPE": "1", "LRR_SPEC_FORCE": "1"}):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "spec ok" in out.stdout, str(env) + out.stdout + out.stderr
 
