@@ -258,7 +258,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
     CK(dmalloc(&d.tile_cnt, (size_t)d.ntiles)); CK(dmalloc(&d.tile_start, (size_t)d.ntiles + 1)); CK(dmalloc(&d.chunk_start, (size_t)d.ntiles + 1));
     CK(dmalloc(&d.tile_of, cap ? cap : 1));
     CK(dmalloc(&d.chunk_tab, cap / 32 + (size_t)d.ntiles + 1));   // every tile adds at most one partly filled chunk
-    CK(dmalloc(&d.todo, cap / 32 + (size_t)d.ntiles + 1)); CK(dmalloc(&d.todo_count, 1)); CK(cudaMemsetAsync(d.todo_count, 0, sizeof(int), ctx->stream));
+    CK(dmalloc(&d.todo, cap / 32 + (size_t)d.ntiles + 1)); CK(dmalloc(&d.todo_count, 2)); CK(cudaMemsetAsync(d.todo_count, 0, 2 * sizeof(int), ctx->stream)); CK(dmalloc(&d.fq, cap ? cap : 1));
   }
   d.epoch = 0; d.has_order = false; d.matches = 0; d.weights_fresh = false;
   d.initial_scale = std::numeric_limits<double>::quiet_NaN();
@@ -266,7 +266,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
 }
 static void dir_free(lrr_dir& d) {
   dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark); dfree(d.proof); dfree(d.pos_of); dfree(d.cprev); dfree(d.tf);
-  dfree(d.tile_cnt); dfree(d.tile_start); dfree(d.chunk_start); dfree(d.tile_of); dfree(d.chunk_tab); dfree(d.todo); dfree(d.todo_count);
+  dfree(d.tile_cnt); dfree(d.tile_start); dfree(d.chunk_start); dfree(d.tile_of); dfree(d.chunk_tab); dfree(d.todo); dfree(d.todo_count); dfree(d.fq);
 }
 static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
   if (n < 0 || (size_t)n > d.cap) return LRR_ERR_INVALID;
@@ -308,7 +308,7 @@ static DirArgs dir_args(const lrr_dir& d) {
   a.sidx = d.sidx; a.w = d.w; a.r2 = d.r2; a.gkey = d.gkey; a.skey = d.skey;
   a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
   static const bool no_proof = getenv("LRR_NO_PROOF") != nullptr;   // A/B switch for measurements
-  a.proof = no_proof ? nullptr : d.proof; a.todo = no_proof ? nullptr : d.todo; a.todo_count = d.todo_count;
+  a.proof = no_proof ? nullptr : d.proof; a.todo = no_proof ? nullptr : d.todo; a.todo_count = d.todo_count; a.fq = d.fq; a.fq_count = d.todo_count + 1;
   if (a.proof) { a.pos_of = d.pos_of; a.cprev = d.cprev; a.tfx = d.tf; a.tfy = d.tf + n; a.tfz = d.tf + 2 * n; }
   a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.chunk_tab = (a.proc && d.n_in > 0) ? d.chunk_tab : nullptr; a.nchunks = d.chunk_start; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
@@ -333,6 +333,7 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
   if (e->dof == 4) f |= LRR_F_SIM2D;
   { static const bool noflat = getenv("LRR_NO_FLAT") != nullptr; if (noflat) f |= LRR_F_NOFLAT; }
   a.flags = f; a.dof = e->dof; a.src = src; a.estimate_parameters = 1;
+  { static const int ts = getenv("LRR_TILE_SPARSE") ? atoi(getenv("LRR_TILE_SPARSE")) : 8; a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : ts; }
   a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
   a.partials = ctx->partials; a.ticket = ctx->ticket;
   return a;
@@ -437,7 +438,7 @@ static void touch(lrr_est* e) {
   e->norm_token = false; e->steady_hint = false;
   if (e->pre_matched) {
     enter(e->ctx);
-    for (int d = 0; d < (e->sym() ? 2 : 1); ++d) cudaMemsetAsync(e->d[d].todo_count, 0, sizeof(int), e->ctx->stream);
+    for (int d = 0; d < (e->sym() ? 2 : 1); ++d) cudaMemsetAsync(e->d[d].todo_count, 0, 2 * sizeof(int), e->ctx->stream);
     e->pre_matched = false;
   }
 }

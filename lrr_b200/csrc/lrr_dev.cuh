@@ -436,6 +436,7 @@ __device__ __forceinline__ int lrr_nn_ball_flat(const GridDev& g, double qx, dou
       }
     }
     if (lane == 0) rowbase[nb] = total;
+    if (g_lrr_tl && lane == 0) { unsigned long long* c = g_lrr_tl + 3 * 2048 * 4; if (r0 == 0) atomicAdd(c + 25, 1ull); atomicAdd(c + 26, (unsigned long long)nb); atomicAdd(c + 27, (unsigned long long)total); }
     __syncwarp();
     for (int p0 = 0; p0 < total; p0 += 128) {
       double4 P[4]; int J[4];

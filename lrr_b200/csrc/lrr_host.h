@@ -52,7 +52,7 @@ struct lrr_dir {
   int *forig = nullptr, *order = nullptr, *sidx = nullptr;
   double *w = nullptr, *r2 = nullptr, *gkey = nullptr, *skey = nullptr;
   unsigned long long* stamp = nullptr;
-  int *hq_k = nullptr, *hq_s = nullptr, *hq_o = nullptr, *hq_count = nullptr, *prev_s = nullptr, *proc = nullptr, *proc_mark = nullptr; double* hq_best = nullptr; double4* proof = nullptr; int* pos_of = nullptr; int* cprev = nullptr; double* tf = nullptr; int2* todo = nullptr; int* todo_count = nullptr;
+  int *hq_k = nullptr, *hq_s = nullptr, *hq_o = nullptr, *hq_count = nullptr, *prev_s = nullptr, *proc = nullptr, *proc_mark = nullptr; double* hq_best = nullptr; double4* proof = nullptr; int* pos_of = nullptr; int* cprev = nullptr; double* tf = nullptr; int2* todo = nullptr; int* todo_count = nullptr; FqRec* fq = nullptr;
   int *tile_cnt = nullptr, *tile_start = nullptr, *chunk_start = nullptr, *tile_of = nullptr; int2* chunk_tab = nullptr; int ntiles = 0; TileGeom tgeom;   // lrr_tile.cu
   Scal* sc = nullptr;
   int64_t n_in = 0, number_points = 0, matches = 0;

@@ -116,6 +116,9 @@ enum {
   LRR_ST_NOT_STEADY = 8         // speculative plan refused: some query was not kept / the normalisation is stale; the host completes the match and reruns
 };
 
+// one query the certificate pass could not keep, with everything it had already loaded for it (one hop instead of four)
+struct __align__(16) FqRec { int k, cand, cand_o, tq; double x, y, z, best; };
+
 struct DirArgs {
   // from side (compact, subset order)
   const double *fx, *fy, *fz, *fs;
@@ -155,6 +158,8 @@ struct DirArgs {
   // work list of the staged search when certificates are in use: (chunk, lane mask of the queries the certificate pass could not
   // keep), appended by k_match_cert, drained and re-armed by k_match_tile
   int2* todo; int* todo_count;
+  // ... and, for chunks with only a few such queries, the queries themselves (tile-order positions): searched by groups of eight lanes
+  struct FqRec* fq; int* fq_count;
   Scal* sc;
 };
 
@@ -181,6 +186,7 @@ struct EstArgs {
   int dof;
   int src;             // direction that defines the normalisation (0; 1 for rrl estimate_LS_backward)
   int estimate_parameters;
+  int tile_sparse;     // certificate pass: chunks with at most this many queries left put them on the sparse list (DirArgs::fq) instead of the staged work list
   SelDev selG[2], selS[2];
   double* partials;    // LRR_MAX_BLOCKS * LRR_NRED per direction slot (2 slots)
   unsigned int* ticket;   // per direction slot

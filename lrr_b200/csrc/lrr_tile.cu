@@ -22,8 +22,6 @@
 #define LRR_TILE_THREADS (32 * LRR_TILE_WARPS)
 #define LRR_TW_CAP 512      // staged points per warp
 #define LRR_TW_ROWS 128     // staged (y,z) rows per warp
-#define LRR_TILE_SPARSE 4   // work-list entries with at most this many queries left are searched query by query (flattened ball scan)
-static_assert(LRR_FLAT_ROWS <= LRR_TW_ROWS, "the flattened ball scan uses the warp's row table");
 
 struct TileWarp {
   double px[LRR_TW_CAP], py[LRR_TW_CAP], pz[LRR_TW_CAP];
@@ -190,33 +188,6 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
     int ch = (int)wi; unsigned int lanes = full;
     if (use_todo) { const int2 e = __ldcg(a.todo + wi); ch = e.x; lanes = (unsigned int)e.y; }
     const int2 qq = __ldg(a.chunk_tab + ch);
-    if (use_todo && !(flags & LRR_F_NOFLAT) && __popc(lanes) <= LRR_TILE_SPARSE) {
-      // SPARSE entry (near convergence the certificate pass leaves one or two queries of a chunk over, typically far outliers whose
-      // two nearest features are almost equally far): staging the chunk's whole box and scanning it in every lane costs ~25 us of
-      // single-warp latency for 31 idle lanes.  The warp takes the queries one by one instead, each with the flattened ball scan
-      // around its previous neighbour (lrr_dev.cuh) — exact, with a new certificate, nothing queued for pass B.
-      __syncwarp();
-      unsigned int m = lanes;
-      while (m) {
-        const int L = __ffs(m) - 1; m &= m - 1;
-        const int tqs = qq.x + L;
-        if (tqs >= qq.y) continue;
-        const int ks = __ldg(a.proc + tqs);
-        const double xs = __ldg(a.fx + ks), ys = __ldg(a.fy + ks), zs = __ldg(a.fz + ks);
-        double mx, my, mz;
-        lrr_map_exact(A, tt, cc, xs, ys, zs, mx, my, mz);
-        NNState st; st.best = 1e300; st.best_s = a.prev_s[ks]; st.best_o = 0x7fffffff;
-        const bool had = st.best_s >= 0;
-        bool have = had;
-        if (had) { const double4 pc = lrr_ld_pos4(g.pos4 + st.best_s); st.best = lrr_dist2_exact(mx, my, mz, pc.x, pc.y, pc.z); st.best_o = lrr_pos4_orig(pc); }
-        else have = lrr_nn_shell_first(g, mx, my, mz, st.best, st.best_s, st.best_o);
-        double bnd = 0.0;
-        const int sres = have ? lrr_nn_ball_flat(g, mx, my, mz, st, had ? 0.125 * g.h : 0.0, &bnd, W.rowlo, W.rowbase) : -1;
-        if (lane == 0) lrr_match_finish(a, rigid, ks, ks, xs, ys, zs, mx, my, mz, sres, acc, (a.proof && had && bnd > 0.0) ? 2 : 0, bnd);
-        __syncwarp();
-      }
-      continue;
-    }
     const int tq = qq.x + lane;
     const bool valid = tq < qq.y && ((lanes >> lane) & 1u);
     int k = 0; double x = 0, y = 0, z = 0, yx = 0, yy = 0, yz = 0;
@@ -372,6 +343,126 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
   }
 }
 
+
+// ---- sparse list: the queries of chunks in which the certificate pass left only a few over ----------------------------------
+// Near convergence a failing certificate is almost always a near tie (the second nearest feature a few micrometres farther than the
+// nearest: measured, scripts/cert_stats2.py) of an ordinary query whose ball touches ~10 rows and ~20 points.  Staging a whole
+// chunk's box for one or two such queries costs ~25 us of single-warp latency, and so does a whole warp per query one after the
+// other.  Here a group of EIGHT lanes takes one query: the run bounds of up to 32 rows in one round trip (four per lane), a prefix
+// sum over the group, the points in a second round trip, group minimum — the flattened ball scan of lrr_dev.cuh at a quarter of a
+// warp, four queries per warp at a time, every query of the list in (almost) one round.  Balls of more than LRR_G8_ROWS rows or
+// LRR_G8_PTS points (far outliers) are queued for the one-warp-per-query pass.  Exact, with a new certificate.
+#define LRR_G8_ROWS 32
+#define LRR_G8_PTS 256
+__device__ __forceinline__ void lrr_match_sparse_body(const DirArgs& a, int flags, const double* s_T, TileWarp& W, double (&acc)[4]) {
+  const int nfq = *reinterpret_cast<volatile int*>(a.fq_count);
+  if (nfq <= 0) return;
+  const double* A = s_T; const double* tt = s_T + 9; const double* cc = s_T + 12;
+  const bool rigid = (flags & LRR_F_RIGID) != 0;
+  const GridDev& g = a.to.grid;
+  const int lane = threadIdx.x & 31, gl = lane & 7, gi = lane >> 3;
+  const unsigned int gmask = 0xffu << (8 * gi);
+  int* rowlo = W.rowlo + LRR_G8_ROWS * gi; int* rowbase = W.rowbase + LRR_G8_ROWS * gi;
+  const int ngroups = gridDim.x * LRR_TILE_WARPS * 4;
+  const double slack = 1e-9 * g.h, margin = 0.125 * g.h;
+  __syncwarp();
+  for (int qi = (blockIdx.x * LRR_TILE_WARPS + (threadIdx.x >> 5)) * 4 + gi; qi < nfq; qi += ngroups) {
+    // the record the certificate pass left: match position, previous neighbour (slot, original index, squared distance under the
+    // current transform) and the from-location, three 16-byte loads of one hop
+    const int4* rp = reinterpret_cast<const int4*>(a.fq + qi);
+    const int4 ri = __ldcg(rp);
+    const double2 r1 = __ldcg(reinterpret_cast<const double2*>(rp + 1)), r2 = __ldcg(reinterpret_cast<const double2*>(rp + 2));
+    const int k = ri.x, cand = ri.y;
+    const double x = r1.x, y = r1.y, z = r2.x;
+    double qx, qy, qz;
+    lrr_map_exact(A, tt, cc, x, y, z, qx, qy, qz);
+    bool queue = cand < 0;
+    double best = 1e300, second = 1e300, bound = 0.0; int best_s = -1, best_o = 0x7fffffff;
+    if (!queue) {
+      best = r2.y; best_s = cand; best_o = ri.z;
+      const double cand_best = best;
+      const double Rm = sqrt(best) * (1.0 + 1e-9) + slack + margin, Rm2 = Rm * Rm;
+      const int z0 = lrr_cell_clamp(qz - Rm, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + Rm, g.oz, g.inv_h, g.nz);
+      const int y0 = lrr_cell_clamp(qy - Rm, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + Rm, g.oy, g.inv_h, g.ny);
+      const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+      if (nrows > LRR_G8_ROWS) queue = true;
+      else {
+        int lo4[4], sz4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rl = 8 * u + gl;
+          lo4[u] = 0; sz4[u] = 0;
+          if (rl < nrows) {
+            const int zz = z0 + rl / ny, yy = y0 + rl % ny;
+            const double dz = lrr_slab_dist(qz, g.oz, g.h, zz, slack), dy = lrr_slab_dist(qy, g.oy, g.h, yy, slack);
+            const double dyz2 = dz * dz + dy * dy;
+            if (dyz2 <= Rm2) {
+              const double rx = sqrt(Rm2 - dyz2) * (1.0 + 1e-9) + slack;
+              const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
+              const int row = (zz * g.ny + yy) * g.nx;
+              lo4[u] = __ldg(g.cell_start + row + xa); sz4[u] = __ldg(g.cell_start + row + xb + 1);
+            }
+          }
+        }
+        int total = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (8 * u < nrows) {   // uniform in the group
+            const int rl = 8 * u + gl, sz = (rl < nrows) ? sz4[u] - lo4[u] : 0;
+            int inc = sz;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { const int v = __shfl_up_sync(gmask, inc, o, 8); if (gl >= o) inc += v; }
+            if (rl < nrows) { rowlo[rl] = lo4[u]; rowbase[rl] = total + inc - sz; }
+            total += __shfl_sync(gmask, inc, 7, 8);
+          }
+        }
+        __syncwarp(gmask);
+        if (total > LRR_G8_PTS) queue = true;
+        else {
+          for (int p0 = 0; p0 < total; p0 += 32) {
+            double4 P[4]; int J[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int p = p0 + 8 * u + gl;
+              J[u] = -1;
+              if (p < total) {
+                int ra = 0, rb = nrows;   // last row with rowbase <= p
+                while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (rowbase[mid] <= p) ra = mid; else rb = mid; }
+                J[u] = rowlo[ra] + (p - rowbase[ra]);
+                P[u] = lrr_ld_pos4(g.pos4 + J[u]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (J[u] >= 0) lrr_nn_upd2(P[u], J[u], qx, qy, qz, best, best_s, best_o, second);
+          }
+          double gb = best; int gs = best_s, go = best_o;
+#pragma unroll
+          for (int o = 4; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(gmask, gb, o, 8);
+            const int os = __shfl_xor_sync(gmask, gs, o, 8), oo = __shfl_xor_sync(gmask, go, o, 8);
+            if (ob < gb || (ob == gb && oo < go)) { gb = ob; gs = os; go = oo; }
+          }
+          double sec = (best_s == gs) ? second : best;
+#pragma unroll
+          for (int o = 4; o; o >>= 1) sec = fmin(sec, __shfl_xor_sync(gmask, sec, o, 8));
+          const double bd = fmin(sqrt(sec), sqrt(gb) + margin) * (1.0 - 1e-9) - slack;
+          bound = (sec > gb && bd > 0.0) ? bd : 0.0;
+          best = gb; best_s = gs; best_o = go;
+        }
+        __syncwarp(gmask);   // the group is done with its row table
+        if (queue) { best = cand_best; best_s = cand; best_o = ri.z; }
+      }
+    }
+    if (gl == 0) {
+      if (queue) {
+        const int slot = atomicAdd(a.hq_count, 1);
+        a.hq_k[slot] = k; a.hq_best[slot] = best_s >= 0 ? best : 1e300; a.hq_s[slot] = best_s; a.hq_o[slot] = best_s >= 0 ? best_o : 0x7fffffff;
+      } else lrr_match_finish(a, rigid, k, k, x, y, z, qx, qy, qz, best_s, acc, (a.proof && bound > 0.0) ? 2 : 0, bound);
+    }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid_constant__ EstArgs a) {
   lrr_pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -382,12 +473,13 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
   unsigned int* counter = a.ticket + 4 + dir;
   lrr_tl(0, 0);
   // certificates in use and nothing left over by k_match_cert (the steady state): its sums stand, the work list is empty already
-  if (lrr_dir_certified(d) && *reinterpret_cast<volatile int*>(d.todo_count) == 0) return;
+  if (lrr_dir_certified(d) && *reinterpret_cast<volatile int*>(d.todo_count) == 0 && *reinterpret_cast<volatile int*>(d.fq_count) == 0) return;
   lrr_stage_transform(d.sc, s_T);
   double acc[4] = {0, 0, 0, 0};
   if (d.chunk_tab && d.proc && d.M == d.n_in) {
     TileWarp& W = reinterpret_cast<TileWarp*>(smem_raw)[threadIdx.x >> 5];
     lrr_match_tile_body(d, a.flags, s_T, W, counter, acc);
+    if (lrr_dir_certified(d)) lrr_match_sparse_body(d, a.flags, s_T, W, acc);
   } else {
     lrr_match_a_body_dynamic(d, a.flags, s_T, counter, acc);
   }
@@ -402,7 +494,7 @@ __global__ void __launch_bounds__(LRR_TILE_THREADS, 4) k_match_tile(const __grid
       if (lrr_dir_certified(d)) {   // the certificate pass left its share of the sums in pm_*
         sc->sum_loc[0] = sc->pm_sum_loc[0] + s_out[0]; sc->sum_loc[1] = sc->pm_sum_loc[1] + s_out[1]; sc->sum_loc[2] = sc->pm_sum_loc[2] + s_out[2];
         sc->sum_r2 = sc->pm_sum_r2 + s_out[3];
-        *d.todo_count = 0;
+        *d.todo_count = 0; *d.fq_count = 0;
       } else { sc->sum_loc[0] = s_out[0]; sc->sum_loc[1] = s_out[1]; sc->sum_loc[2] = s_out[2]; sc->sum_r2 = s_out[3]; }
       *counter = 0;
     }
@@ -480,12 +572,14 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
       const int tq = qq.x + lane;
       const bool valid = tq < qq.y;
       bool kept = false;
+      int fk = 0, fsp = -1, fo = 0x7fffffff; double fx_ = 0, fy_ = 0, fz_ = 0, fbest = 1e300;   // what a sparse-list record needs
       if (valid) {
         const int k = __ldg(d.proc + tq);
         const int sp = d.cprev[tq];
         const double2* pr = reinterpret_cast<const double2*>(d.proof + tq);
         const double2 p0 = __ldcg(pr), p1 = __ldcg(pr + 1);
         const double x = __ldg(d.tfx + tq), y = __ldg(d.tfy + tq), z = __ldg(d.tfz + tq);
+        fk = k; fx_ = x; fy_ = y; fz_ = z;
         if (sp >= 0 && (resid || p1.y > 0.0)) {
           const double4 q = lrr_ld_pos4(g.pos4 + sp);
           double P[6]; lrr_ld_P6(d.to.rec, sp, P);
@@ -499,8 +593,9 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
             d.r2[k] = r2;
             acc[4] += r2; acc[5] += w * r2; acc[6] += w; acc[7] += sqrt(r2) * w; acc[8] += 1.0;
           }
+          fsp = sp; fo = lrr_pos4_orig(q); fbest = lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z);
           if (p1.y > 0.0) {
-            const double dq = sqrt(lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z));
+            const double dq = sqrt(fbest);
             const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
             const double dm = sqrt(ex * ex + ey * ey + ez * ez);
             // (1e-9 relative + slack covers the rounding of the square roots and sums; B itself was rounded down when written)
@@ -511,11 +606,35 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
               acc[3] += r2;
             }
           }
-          if (g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + (kept ? 7 : 18), 1ull);   // development counters (scripts/timeline.py)
+          if (g_lrr_tl) {   // development counters (scripts/cert_stats.py)
+            unsigned long long* c = g_lrr_tl + 3 * 2048 * 4;
+            atomicAdd(c + (kept ? 7 : 18), 1ull);
+            if (!kept && p1.y > 0.0) {
+              const double dq0 = sqrt(lrr_dist2_exact(p0.x, p0.y, p1.x, q.x, q.y, q.z));
+              const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
+              const double dm = sqrt(ex * ex + ey * ey + ez * ez);
+              if (dq0 > 2.0 * g.h) atomicAdd(c + 20, 1ull);
+              if (p1.y >= 0.999 * (dq0 + 0.125 * g.h)) atomicAdd(c + 21, 1ull); else atomicAdd(c + 22, 1ull);
+              atomicAdd(c + 23, (unsigned long long)(dm * 1e6));
+              atomicAdd(c + 24, (unsigned long long)(fmax(p1.y - dq0, 0.0) * 1e6));
+            }
+          }
         } else if (g_lrr_tl) atomicAdd(g_lrr_tl + 3 * 2048 * 4 + (sp < 0 ? 16 : 17), 1ull);
       }
       const unsigned int rest = __ballot_sync(0xffffffffu, valid && !kept);
-      if (rest && lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); acc[9] += (double)__popc(rest); }
+      if (rest) {
+        const int nrest = __popc(rest);
+        if (nrest <= a.tile_sparse) {   // a few queries: each goes to the sparse list on its own (lrr_match_sparse_body)
+          int base = 0;
+          if (lane == 0) base = atomicAdd(d.fq_count, nrest);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (valid && !kept) {
+            FqRec r; r.k = fk; r.cand = fsp; r.cand_o = fo; r.tq = tq; r.x = fx_; r.y = fy_; r.z = fz_; r.best = fbest;
+            d.fq[base + __popc(rest & ((1u << lane) - 1u))] = r;
+          }
+        } else if (lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); }
+        if (lane == 0) acc[9] += (double)nrest;
+      }
       ch = chn; qq = qqn;
     }
   }
@@ -526,7 +645,7 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
       Scal* sc = d.sc;
       sc->cert_failed = s_out[9];
       // every query kept <=> nothing on the work list (this block is the last one of the direction: all appends are visible)
-      const int left = lrr_dir_certified(d) ? *reinterpret_cast<volatile int*>(d.todo_count) + *reinterpret_cast<volatile int*>(d.hq_count) : 1;
+      const int left = lrr_dir_certified(d) ? *reinterpret_cast<volatile int*>(d.todo_count) + *reinterpret_cast<volatile int*>(d.fq_count) + *reinterpret_cast<volatile int*>(d.hq_count) : 1;
       sc->match_left = left;
       if (left > 0) {
         sc->norm_dirty = 1;
