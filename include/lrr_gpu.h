@@ -2,7 +2,8 @@
  *
  * Drop-in boundary for the LRR hot path.  Every entry point cites the reference
  * interface (file:line under the upstream msofka/LRR tree) it replaces.  Plain C: opaque handles,
- * plain pointers and sizes, `int` status returns (0 = ok), no exceptions, no global state.
+ * plain pointers and sizes, `int` status returns (0 = ok), no exceptions, no mutable global state (per-device facts such as the
+ * SM count are cached per device; contexts on different devices may be driven from different threads of one process).
  * One lrr_ctx per CUDA device; calls on one ctx are serialised by the caller — the reference
  * estimators are single-threaded too (rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760).
  *
@@ -67,7 +68,8 @@ enum { LRR_DIR_FORWARD = 0, LRR_DIR_BACKWARD = 1 };
  * unseeded libstdc++ rand().  The permutation is therefore an injectable input here. */
 enum {
   LRR_ORDER_FIXED = 0,     /* keep the order given by lrr_est_set_order (identity by default)      */
-  LRR_ORDER_RESHUFFLE = 1  /* Fisher-Yates with SplitMix64(seed) applied cumulatively per call     */
+  LRR_ORDER_RESHUFFLE = 1  /* a new keyed 4-round Feistel permutation (cycle walking) of the moving vector per find_closest call,
+                              keys from SplitMix64(seed, direction, call number): every element computable independently */
 };
 
 /* scalar metrics (lrr_est_metric) */
@@ -208,6 +210,17 @@ typedef struct lrr_result {
  * one_iteration calls each) over one resident volume pair. */
 int  lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs,
                    int max_iter, uint64_t shuffle_seed, lrr_result* out);
+/* The same over a SHARD of a larger list: job_ids[i] is the index of jobs[i] in the whole list.  Job i is seeded with
+ * shuffle_seed + job_ids[i], so its result does not depend on how the list was sharded (one process per GPU: block-cyclic shards,
+ * the 32 candidates of a location — rrl/itkLocationRegistration.cxx:2230 — spread over all devices). */
+int  lrr_batch_run_ids(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, const int64_t* job_ids,
+                       int64_t njobs, int max_iter, uint64_t shuffle_seed, lrr_result* out);
+/* The whole list over ndev devices of ONE process (the reference's outer loops, :2138 / :2230 / :2332, are one sequential program):
+ * ctx[d], moving_all[d], fixed_all[d] = replicas of the same volume pair on device d.  One host thread per device, runs of jobs
+ * drawn from one shared cursor (dynamic), two launches in flight per device, results written in place; job j is seeded with
+ * shuffle_seed + j whichever device runs it. */
+int  lrr_batch_run_multi(lrr_ctx** ctx, int ndev, lrr_fset** moving_all, lrr_fset** fixed_all, const lrr_job* jobs, int64_t njobs,
+                         int max_iter, uint64_t shuffle_seed, lrr_result* out);
 
 #ifdef __cplusplus
 }

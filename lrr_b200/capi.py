@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
-    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run",
+    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run", "batch_run_ids", "batch_run_multi",
 ]
 
 
@@ -129,6 +129,8 @@ class Lib:
             "objcov_eval": (i32, [vp, i32, pd, pd, pd]),
             "objcov_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32)]),
             "batch_run": (i32, [vp, vp, vp, vp, i64, i32, u64, vp]),
+            "batch_run_ids": (i32, [vp, vp, vp, vp, C.POINTER(C.c_int64), i64, i32, u64, vp]),
+            "batch_run_multi": (i32, [C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp), vp, i64, i32, u64, vp]),
         }
         for name, (res, args) in sig.items():
             if self.has(name):
@@ -138,6 +140,17 @@ class Lib:
     # ---- object-style helpers ------------------------------------------------------------------
     def context(self, device: int = 0) -> "Context":
         return Context(self, device)
+
+    def batch_run_multi(self, contexts, movings, fixeds, jobs: np.ndarray, max_iter: int = 70, seed: int = 0):
+        """The whole job list over several devices of this process (contexts[d], movings[d], fixeds[d] = replicas on device d)."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        n = len(contexts)
+        vp = C.c_void_p
+        ca = (vp * n)(*[c.h for c in contexts]); ma = (vp * n)(*[m.h for m in movings]); fa = (vp * n)(*[f.h for f in fixeds])
+        rc = self.fn("batch_run_multi")(ca, n, ma, fa, jobs.ctypes.data_as(vp), len(jobs), max_iter, seed, out.ctypes.data_as(vp))
+        contexts[0].check(rc, "batch_run_multi")
+        return out
 
 
 class Context:
@@ -180,11 +193,18 @@ class Context:
     def estimator(self, kind: str, moving: "FeatureSet", fixed: "FeatureSet", dof: int = 12, dim: int = 3) -> "Estimator":
         return Estimator(self, kind, moving, fixed, dof, dim)
 
-    def batch_run(self, moving: "FeatureSet", fixed: "FeatureSet", jobs: np.ndarray, max_iter: int = 70, seed: int = 0):
+    def batch_run(self, moving: "FeatureSet", fixed: "FeatureSet", jobs: np.ndarray, max_iter: int = 70, seed: int = 0, ids=None):
+        """ids: global indices of `jobs` in a larger list (a shard): job i is seeded with seed + ids[i]."""
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
-        rc = self.lib.fn("batch_run")(self.h, moving.h, fixed.h, jobs.ctypes.data_as(C.c_void_p), len(jobs), max_iter,
-                                      seed, out.ctypes.data_as(C.c_void_p))
+        if ids is None:
+            rc = self.lib.fn("batch_run")(self.h, moving.h, fixed.h, jobs.ctypes.data_as(C.c_void_p), len(jobs), max_iter,
+                                          seed, out.ctypes.data_as(C.c_void_p))
+        else:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            assert len(ids) == len(jobs)
+            rc = self.lib.fn("batch_run_ids")(self.h, moving.h, fixed.h, jobs.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              len(jobs), max_iter, seed, out.ctypes.data_as(C.c_void_p))
         self.check(rc, "batch_run")
         return out
 

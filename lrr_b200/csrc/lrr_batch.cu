@@ -33,6 +33,7 @@ struct BatchArgs {
   FsetDev all[2];                  // 0 = moving_all, 1 = fixed_all
   const lrr_job* jobs; lrr_result* out; long long njobs;
   int max_iter; unsigned long long shuffle_seed;
+  const long long* job_ids;          // global index of job j (null: j): the shuffle seed of a job is shuffle_seed + its GLOBAL index, however the list was sharded
   int* next_job;
   // workspace bases (strided by block)
   double* w_f; double* w_fP6; int* w_forig; int* w_sidx; double* w_pm; int* w_prev; int* w_hq; double* w_hqb;
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__
       // find_closest_euclidean, both directions: new permutation key, new stamp epoch
       if (threadIdx.x < 2) {
         const int d = threadIdx.x;
-        unsigned long long st = (B.shuffle_seed + (unsigned long long)j) + (unsigned long long)d * 0x632BE59BD9B4E019ULL + S.calls[d] * 0xD1342543DE82EF95ULL;
+        const unsigned long long gid = B.job_ids ? (unsigned long long)B.job_ids[j] : (unsigned long long)j;
+        unsigned long long st = (B.shuffle_seed + gid) + (unsigned long long)d * 0x632BE59BD9B4E019ULL + S.calls[d] * 0xD1342543DE82EF95ULL;
         S.calls[d] += 1;
         for (int r = 0; r < 4; ++r) S.d[d].perm_key[r] = (unsigned int)(bt_splitmix(st) >> 32);
         int bits = 2; while ((1ull << bits) < (unsigned long long)S.d[d].n_in) ++bits;
@@ -412,10 +414,11 @@ __global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__
 size_t lrr_batch_smem_bytes() { return ((sizeof(BatchShared) + 15) & ~size_t(15)) + (size_t)BATCH_CAP * sizeof(int); }
 
 cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
-                             int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
+                             const long long* job_ids_dev, int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
                              size_t workspace_bytes, cudaStream_t st, long long* launches) {
   BatchArgs B; memset(&B, 0, sizeof(B));
   B.all[0] = moving_all; B.all[1] = fixed_all; B.jobs = jobs_dev; B.out = out_dev; B.njobs = njobs; B.max_iter = max_iter; B.shuffle_seed = shuffle_seed;
+  B.job_ids = job_ids_dev;
   for (int i = 0; i < 4 * 32; ++i) B.muse_table[i] = muse_table[i];
   B.muse_rows = muse_rows;
   // carve the workspace

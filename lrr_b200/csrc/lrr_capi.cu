@@ -80,14 +80,14 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
   }
   ok = ok && dmalloc(&ctx->partials, (size_t)2 * LRR_MAX_BLOCKS * LRR_NRED) == cudaSuccess;
   ok = ok && dmalloc(&ctx->ticket, 8) == cudaSuccess;
-  ok = ok && cudaMemset(ctx->ticket, 0, 8 * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(ctx->ticket, 0, 8 * sizeof(unsigned int), ctx->own_stream) == cudaSuccess;
   // four selectors (G and S for two groups)
   const size_t sel_uints = (size_t)LRR_SEL_FINE + LRR_SEL_COARSE;
   ok = ok && dmalloc(&ctx->sel_hist, 4 * sel_uints) == cudaSuccess;
-  ok = ok && cudaMemset(ctx->sel_hist, 0, 4 * sel_uints * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(ctx->sel_hist, 0, 4 * sel_uints * sizeof(unsigned int), ctx->own_stream) == cudaSuccess;
   ok = ok && dmalloc(&ctx->sel_cand, (size_t)4 * LRR_SEL_CAP) == cudaSuccess;
   ok = ok && dmalloc(&ctx->sel_misc, (size_t)4 * 16) == cudaSuccess;   // 16 x 8 bytes per selector
-  ok = ok && cudaMemset(ctx->sel_misc, 0, 4 * 16 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(ctx->sel_misc, 0, 4 * 16 * sizeof(unsigned long long), ctx->own_stream) == cudaSuccess;
   ok = ok && dmalloc(&ctx->muse_table, 4 * 32) == cudaSuccess;
   ok = ok && dmalloc(&ctx->scratch_d, 1024) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&ctx->pinned, 2 * sizeof(Scal) + 4096) == cudaSuccess;
@@ -98,6 +98,7 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
     } else { ctx->mailbox = nullptr; cudaGetLastError(); }
   }
   ctx->sort.keys2 = nullptr; ctx->sort.hist = nullptr; ctx->sort.cap = 0; ctx->sort_keys = nullptr;
+  ok = ok && cudaStreamSynchronize(ctx->own_stream) == cudaSuccess;   // (allocations and clears are ordered on the context's own stream)
   if (!ok) { cudaGetLastError(); lrr_ctx_destroy(ctx); return LRR_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) {
     SelDev& s = ctx->sel[i];
@@ -1375,49 +1376,154 @@ static int batch_job_host(lrr_est* est, lrr_fset* moving_all, lrr_fset* fixed_al
 }
 
 cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
-                             int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
+                             const long long* job_ids_dev, int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
                              size_t workspace_bytes, cudaStream_t st, long long* launches);
 size_t lrr_batch_workspace_bytes(int nblocks, int n_moving, int n_fixed);
 int lrr_batch_blocks_per_sm();
 
+// One launch of the block-per-registration kernel over a run of jobs, with its own stream, workspace and staging buffers: the
+// single-device entry points use one slot on the context's stream, lrr_batch_run_multi keeps two in flight per device.
+struct BatchSlot {
+  cudaStream_t st = nullptr; bool own_stream = false;
+  void* work = nullptr; lrr_job* djobs = nullptr; lrr_result* dout = nullptr; long long* dids = nullptr;
+  int64_t a = 0, n = 0; bool busy = false;
+};
+static void slot_release(BatchSlot& s) {
+  if (s.work) cudaFreeAsync(s.work, s.st); if (s.djobs) cudaFreeAsync(s.djobs, s.st); if (s.dout) cudaFreeAsync(s.dout, s.st); if (s.dids) cudaFreeAsync(s.dids, s.st);
+  s.work = nullptr; s.djobs = nullptr; s.dout = nullptr; s.dids = nullptr;
+}
+static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t a, int64_t n,
+                            const int64_t* ids, int64_t id_base, int max_iter, uint64_t shuffle_seed, lrr_result* out);
+static int slot_launch(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t a, int64_t n,
+                       const int64_t* ids, int64_t id_base, int max_iter, uint64_t shuffle_seed, lrr_result* out) {
+  const int rc = slot_launch_impl(ctx, s, moving_all, fixed_all, jobs, a, n, ids, id_base, max_iter, shuffle_seed, out);
+  if (rc != LRR_OK) { cudaStreamSynchronize(s.st); slot_release(s); s.busy = false; }   // every early return of the body ends here: nothing leaks
+  return rc;
+}
+static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t a, int64_t n,
+                            const int64_t* ids, int64_t id_base, int max_iter, uint64_t shuffle_seed, lrr_result* out) {
+  const int nblocks = (int)std::min<int64_t>(n, (int64_t)lrr_num_sms() * lrr_batch_blocks_per_sm());
+  const size_t wbytes = lrr_batch_workspace_bytes(nblocks, (int)moving_all->n, (int)fixed_all->n);
+  cudaStream_t st = s.st;
+  CK(cudaMallocAsync(&s.work, wbytes, st));
+  CK(cudaMallocAsync((void**)&s.djobs, sizeof(lrr_job) * n, st)); CK(cudaMallocAsync((void**)&s.dout, sizeof(lrr_result) * n, st));
+  CK(cudaMallocAsync((void**)&s.dids, sizeof(long long) * n, st));
+  CK(cudaMemcpyAsync(s.djobs, jobs + a, sizeof(lrr_job) * n, cudaMemcpyHostToDevice, st));
+  std::vector<long long> hid((size_t)n);
+  for (int64_t i = 0; i < n; ++i) hid[(size_t)i] = ids ? (long long)ids[a + i] : (long long)(id_base + a + i);
+  CK(cudaMemcpyAsync(s.dids, hid.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // `hid` is a local buffer (and pageable copies are staged anyway)
+  double table[4 * 32] = {0};
+  const int rows = build_muse_table(1000u, table);
+  CK(lrr_batch_launch(moving_all->dev, fixed_all->dev, s.djobs, s.dout, n, s.dids, max_iter, shuffle_seed, table, rows, nblocks, s.work, wbytes, st, &ctx->launches));
+  CK(cudaMemcpyAsync(out + a, s.dout, sizeof(lrr_result) * n, cudaMemcpyDeviceToHost, st));
+  s.a = a; s.n = n; s.busy = true;
+  return LRR_OK;
+}
+static int slot_collect(lrr_ctx* ctx, BatchSlot& s) {
+  if (!s.busy) return LRR_OK;
+  s.busy = false;
+  cudaError_t e1 = cudaStreamSynchronize(s.st), e2 = cudaGetLastError();
+  slot_release(s);
+  CK(e1); CK(e2);
+  return LRR_OK;
+}
+
+// jobs the block kernel handed back (ROI above its capacity, selector overflow; status < 0) and the LRR_BATCH_MODE=host debugging
+// mode go through one reused estimator object and the per-iteration kernels
+static int batch_host_jobs(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, const std::vector<int64_t>& todo, const int64_t* ids,
+                           int64_t id_base, int max_iter, uint64_t shuffle_seed, lrr_result* out) {
+  if (todo.empty()) return LRR_OK;
+  lrr_est* est = nullptr;
+  int rc = lrr_est_create(ctx, LRR_RRL_SYM, 3, 12, moving_all, fixed_all, &est);
+  if (rc != LRR_OK) return rc;
+  std::vector<int32_t> mi, fi;
+  for (int64_t j : todo) if ((rc = batch_job_host(est, moving_all, fixed_all, jobs[j], ids ? ids[j] : id_base + j, max_iter, shuffle_seed, out[j], mi, fi)) != LRR_OK) break;
+  lrr_est_destroy(est);
+  return rc;
+}
+
 // Batched location registration: the outer loops of LocationRegistration::Run (rrl/itkLocationRegistration.cxx:2138,
-// 2230,2332) over one resident volume pair.  Device path: one persistent thread block per registration
-// (lrr_batch.cu).  Jobs the block kernel hands back (ROI above its capacity, selector overflow) and the
-// LRR_BATCH_MODE=host debugging mode go through one reused estimator object and the per-iteration kernels.
-// Jobs are independent; callers shard them across GPUs (one ctx each).
-extern "C" int lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int max_iter,
-                             uint64_t shuffle_seed, lrr_result* out) {
+// 2230,2332) over one resident volume pair.  Device path: one persistent thread block per registration (lrr_batch.cu).
+static int batch_run_impl(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, const int64_t* ids, int max_iter,
+                          uint64_t shuffle_seed, lrr_result* out) {
   if (!ctx || !moving_all || !fixed_all || njobs < 0 || (njobs > 0 && (!jobs || !out))) return LRR_ERR_INVALID;
+  if (moving_all->ctx != ctx || fixed_all->ctx != ctx) return LRR_ERR_INVALID;
   enter(ctx);
   if (njobs == 0) return LRR_OK;
   const char* mode = getenv("LRR_BATCH_MODE");
   const bool host_only = (mode && std::string(mode) == "host") || max_iter > 250;
   std::vector<int64_t> todo;
   if (!host_only) {
-    const int nblocks = (int)std::min<int64_t>(njobs, (int64_t)lrr_num_sms() * lrr_batch_blocks_per_sm());
-    const size_t wbytes = lrr_batch_workspace_bytes(nblocks, (int)moving_all->n, (int)fixed_all->n);
-    void* work = nullptr; lrr_job* djobs = nullptr; lrr_result* dout = nullptr;
-    CK(cudaMallocAsync(&work, wbytes, ctx->stream));
-    CK(dmalloc(&djobs, (size_t)njobs)); CK(dmalloc(&dout, (size_t)njobs));
-    CK(cudaMemcpyAsync(djobs, jobs, sizeof(lrr_job) * njobs, cudaMemcpyHostToDevice, ctx->stream));
-    double table[4 * 32] = {0};
-    const int rows = build_muse_table(1000u, table);
-    { PHASE(PH_BATCH);
-      CK(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, max_iter, shuffle_seed, table, rows, nblocks, work, wbytes, ctx->stream, &ctx->launches)); }
-    CK(cudaMemcpyAsync(out, dout, sizeof(lrr_result) * njobs, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    dfree(work); dfree(djobs); dfree(dout);
+    BatchSlot s; s.st = ctx->stream;
+    int rc;
+    { PHASE(PH_BATCH); rc = slot_launch(ctx, s, moving_all, fixed_all, jobs, 0, njobs, ids, 0, max_iter, shuffle_seed, out); }
+    const int rc2 = slot_collect(ctx, s);
+    if (rc != LRR_OK) return rc;
+    if (rc2 != LRR_OK) return rc2;
     for (int64_t j = 0; j < njobs; ++j) if (out[j].status < 0) todo.push_back(j);
   } else {
     for (int64_t j = 0; j < njobs; ++j) todo.push_back(j);
   }
-  if (todo.empty()) return LRR_OK;
-  lrr_est* est = nullptr;
-  int rc = lrr_est_create(ctx, LRR_RRL_SYM, 3, 12, moving_all, fixed_all, &est);
-  if (rc != LRR_OK) return rc;
-  std::vector<int32_t> mi, fi;
-  for (int64_t j : todo) if ((rc = batch_job_host(est, moving_all, fixed_all, jobs[j], j, max_iter, shuffle_seed, out[j], mi, fi)) != LRR_OK) break;
-  lrr_est_destroy(est);
-  return rc;
+  return batch_host_jobs(ctx, moving_all, fixed_all, jobs, todo, ids, 0, max_iter, shuffle_seed, out);
+}
+extern "C" int lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int max_iter,
+                             uint64_t shuffle_seed, lrr_result* out) {
+  return batch_run_impl(ctx, moving_all, fixed_all, jobs, njobs, nullptr, max_iter, shuffle_seed, out);
+}
+extern "C" int lrr_batch_run_ids(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, const int64_t* job_ids, int64_t njobs,
+                                 int max_iter, uint64_t shuffle_seed, lrr_result* out) {
+  if (njobs > 0 && !job_ids) return LRR_ERR_INVALID;
+  return batch_run_impl(ctx, moving_all, fixed_all, jobs, njobs, job_ids, max_iter, shuffle_seed, out);
+}
+
+// The whole job list over ndev devices of THIS process (the reference's outer loops are one sequential program: a host that links
+// the backend has no process per GPU).  One host thread per device; the threads draw runs of jobs from one shared cursor (dynamic:
+// job costs range from a rejected ROI to 70 iterations) and keep two launches in flight per device, so that the blocks of the next
+// run start as the blocks of the current one run out of jobs.  Results are written in place; job j is seeded with
+// shuffle_seed + j whichever device runs it, so the result does not depend on the number of devices.
+#include <thread>
+extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_all, lrr_fset** fixed_all, const lrr_job* jobs, int64_t njobs,
+                                   int max_iter, uint64_t shuffle_seed, lrr_result* out) {
+  if (!ctxs || ndev <= 0 || !moving_all || !fixed_all || njobs < 0 || (njobs > 0 && (!jobs || !out))) return LRR_ERR_INVALID;
+  for (int d = 0; d < ndev; ++d) {
+    if (!ctxs[d] || !moving_all[d] || !fixed_all[d] || moving_all[d]->ctx != ctxs[d] || fixed_all[d]->ctx != ctxs[d]) return LRR_ERR_INVALID;
+    if (moving_all[d]->n != moving_all[0]->n || fixed_all[d]->n != fixed_all[0]->n) return LRR_ERR_INVALID;   // replicas of one pair
+  }
+  if (njobs == 0) return LRR_OK;
+  if (max_iter > 250 || ndev == 1) return batch_run_impl(ctxs[0], moving_all[0], fixed_all[0], jobs, njobs, nullptr, max_iter, shuffle_seed, out);
+  std::atomic<int64_t> cursor{0};
+  std::vector<int> rcs((size_t)ndev, LRR_OK);
+  auto worker = [&](int d) {
+    lrr_ctx* ctx = ctxs[d];
+    enter(ctx);
+    const int64_t nblocks = (int64_t)lrr_num_sms() * lrr_batch_blocks_per_sm();
+    const int64_t run = std::max<int64_t>(nblocks, std::min<int64_t>(4 * nblocks, njobs / (8 * (int64_t)ndev)));
+    BatchSlot slot[2];
+    int rc = LRR_OK;
+    for (int k = 0; k < 2; ++k) {
+      if (cudaStreamCreateWithFlags(&slot[k].st, cudaStreamNonBlocking) != cudaSuccess) { rc = LRR_ERR_CUDA; ctx->err = "cudaStreamCreate"; }
+      else slot[k].own_stream = true;
+    }
+    cudaStreamSynchronize(ctx->stream);   // the uploads of the replicas are complete
+    for (int cur = 0; rc == LRR_OK; cur ^= 1) {
+      if ((rc = slot_collect(ctx, slot[cur])) != LRR_OK) break;
+      const int64_t a = cursor.fetch_add(run);
+      if (a >= njobs) break;
+      const cudaStream_t keep = g_alloc_stream;
+      rc = slot_launch(ctx, slot[cur], moving_all[d], fixed_all[d], jobs, a, std::min(run, njobs - a), nullptr, 0, max_iter, shuffle_seed, out);
+      g_alloc_stream = keep;
+    }
+    for (int k = 0; k < 2; ++k) { const int r2 = slot_collect(ctx, slot[k]); if (rc == LRR_OK) rc = r2; if (slot[k].own_stream) cudaStreamDestroy(slot[k].st); }
+    rcs[(size_t)d] = rc;
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < ndev; ++d) th.emplace_back(worker, d);
+  worker(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < ndev; ++d) if (rcs[(size_t)d] != LRR_OK) return rcs[(size_t)d];
+  std::vector<int64_t> todo;
+  for (int64_t j = 0; j < njobs; ++j) if (out[j].status < 0) todo.push_back(j);
+  enter(ctxs[0]);
+  return batch_host_jobs(ctxs[0], moving_all[0], fixed_all[0], jobs, todo, nullptr, 0, max_iter, shuffle_seed, out);
 }

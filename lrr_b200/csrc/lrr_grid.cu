@@ -9,14 +9,19 @@
 #include <math.h>
 #include <stdlib.h>
 
-static int g_num_sms = 0;
+// per-device facts are cached PER DEVICE (contexts on several devices may live in one process and be driven from several threads)
+#include <atomic>
+static std::atomic<int> g_num_sms[LRR_MAX_DEVICES];
+int lrr_current_device() { int dev = 0; cudaGetDevice(&dev); return (dev < 0 || dev >= LRR_MAX_DEVICES) ? 0 : dev; }
 int lrr_num_sms() {
-  if (!g_num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  const int dev = lrr_current_device();
+  int n = g_num_sms[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    g_num_sms[dev].store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
 
 // ---- bounding box -----------------------------------------------------------------------------

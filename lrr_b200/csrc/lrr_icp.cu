@@ -20,14 +20,16 @@ static inline int nblk_for(long long items) {
 // directions ran back to back, each with its own tail.
 template <class K>
 static inline int resident_width(K kernel, int threads, int ny, long long items) {
-  static std::unordered_map<const void*, int> cache;   // host calls on one context are serialised by the caller (lrr_gpu.h)
+  // (occupancy per (device, kernel); thread_local: contexts on different devices may be driven from different host threads)
+  static thread_local std::unordered_map<unsigned long long, int> cache;
+  const unsigned long long key = (unsigned long long)(uintptr_t)(const void*)kernel ^ ((unsigned long long)lrr_current_device() << 56);
   int per_sm;
-  auto it = cache.find((const void*)kernel);
+  auto it = cache.find(key);
   if (it != cache.end()) per_sm = it->second;
   else {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
-    cache[(const void*)kernel] = per_sm = n;
+    cache[key] = per_sm = n;
   }
   long long b = (items + threads - 1) / threads;
   long long cap = (long long)lrr_num_sms() * per_sm / (ny < 1 ? 1 : ny);

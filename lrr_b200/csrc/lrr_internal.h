@@ -197,14 +197,16 @@ struct EstArgs {
 #include <cstdlib>
 #include <utility>
 template <class... KArgs, class... Args>
-static inline void lrr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+static inline cudaError_t lrr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   static const bool off = getenv("LRR_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
-  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  // (a failed launch — e.g. a function attribute missing on this device — stays in the runtime's sticky last error, which every
+  //  entry point checks when it reads the scalars back; the status is returned for callers that want it at once)
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 #endif
 
@@ -218,7 +220,9 @@ struct FsetBuild {
 cudaError_t lrr_grid_build(FsetBuild* fb, cudaStream_t st, long long* launches);
 cudaError_t lrr_nn_query(const GridDev& g, int64_t nq, const double* qx, const double* qy, const double* qz,
                          int* out_orig, cudaStream_t st, long long* launches);
-int lrr_num_sms();
+#define LRR_MAX_DEVICES 64
+int lrr_num_sms();          // of the CURRENT device (cached per device)
+int lrr_current_device();   // clamped to [0, LRR_MAX_DEVICES)
 
 // ---- ICP kernels (lrr_icp.cu) ----------------------------------------------------------------------
 void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* mark /* from_all.n ints scratch */, int* proc, cudaStream_t st, long long* launches);

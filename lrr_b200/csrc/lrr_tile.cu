@@ -17,6 +17,7 @@
 // (rrl/rrl_estimation_ICP_matching_all.txx:530-543) for the iterations where all points are in use.
 #include "lrr_phases.cuh"
 #include <algorithm>
+#include <atomic>
 
 #define LRR_TILE_WARPS 4
 #define LRR_TILE_THREADS (32 * LRR_TILE_WARPS)
@@ -669,8 +670,12 @@ bool lrr_match_cert_usable(const EstArgs& a) {
 void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches, int mode, double* mbox, unsigned long long seq, int pull_mask, int nhead) {
   int maxM = a.d[0].M; if (a.ndir == 2 && a.d[1].M > maxM) maxM = a.d[1].M;
   int nb = (maxM / 32 + LRR_CERT_THREADS / 32 - 1) / (LRR_CERT_THREADS / 32) + 1;   // about one chunk per warp ...
-  static int per_sm = 0;
-  if (!per_sm) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_cert, LRR_CERT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1; }
+  static std::atomic<int> per_sm_dev[LRR_MAX_DEVICES];   // per device
+  int per_sm = per_sm_dev[lrr_current_device()].load(std::memory_order_relaxed);
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_cert, LRR_CERT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    per_sm_dev[lrr_current_device()].store(per_sm, std::memory_order_relaxed);
+  }
   nb = std::max(1, std::min(nb, per_sm * lrr_num_sms() / a.ndir));   // ... but every block resident at once (no second wave)
   dim3 grid(nb, a.ndir);
   lrr_launch_pdl(k_match_cert, grid, dim3(LRR_CERT_THREADS), 0, st, a, mode, mbox, seq, pull_mask, nhead); ++*launches;
@@ -681,9 +686,13 @@ bool lrr_match_tile_usable(const EstArgs& a) {
   return false;
 }
 void lrr_k_match_tile(const EstArgs& a, cudaStream_t st, long long* launches) {
-  static bool attr_set = false;
+  // (cudaFuncSetAttribute is per DEVICE: the 53 KB of dynamic shared memory have to be allowed on every device the library runs on)
+  static std::atomic<int> attr_set[LRR_MAX_DEVICES];
   const size_t smem = sizeof(TileWarp) * LRR_TILE_WARPS;
-  if (!attr_set) { cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  if (!attr_set[lrr_current_device()].load(std::memory_order_relaxed)) {
+    cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set[lrr_current_device()].store(1, std::memory_order_relaxed);
+  }
   // every block of both directions resident at once (4 blocks of 128 threads per SM): no second wave
   dim3 grid(std::max(1, (4 * lrr_num_sms()) / a.ndir), a.ndir);
   lrr_launch_pdl(k_match_tile, grid, dim3(LRR_TILE_THREADS), smem, st, a); ++*launches;

@@ -331,6 +331,18 @@ int lrro_batch_run_mt(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, co
 int lrro_batch_run(lrro_ctx* c, lrro_fset* m, lrro_fset* f, const lrr_job* jobs, int64_t njobs, int max_iter, uint64_t seed, lrr_result* out) {
   return lrro_batch_run_mt(c, m, f, jobs, njobs, max_iter, seed, out, 1);
 }
+// shard of a larger list: job i is seeded with seed + its global index
+int lrro_batch_run_ids(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, const lrr_job* jobs, const int64_t* ids, int64_t njobs, int max_iter,
+                       uint64_t seed, lrr_result* out) {
+  auto mall = clone_set(moving_all->base); auto fall = clone_set(fixed_all->base);
+  for (int64_t j = 0; j < njobs; ++j)
+    run_one_job(moving_all, fixed_all, mall, fall, fixed_all->kd, moving_all->kd, jobs[j], max_iter, seed + (uint64_t)ids[j], out[j]);
+  return LRR_OK;
+}
+// "devices" of the CPU checker = host threads over the first replica
+int lrro_batch_run_multi(lrro_ctx** c, int ndev, lrro_fset** m, lrro_fset** f, const lrr_job* jobs, int64_t njobs, int max_iter, uint64_t seed, lrr_result* out) {
+  return lrro_batch_run_mt(c[0], m[0], f[0], jobs, njobs, max_iter, seed, out, ndev);
+}
 
 // ---- test hooks -------------------------------------------------------------------------------
 double lrro_test_muse_scale(const double* r, int64_t n) { return muse_scale(std::vector<double>(r, r + n)); }

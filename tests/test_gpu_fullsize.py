@@ -90,17 +90,51 @@ def test_feature_order_invariance_100k(gpu_lib, pair100k):
 
 
 def test_batch_independent_of_sharding(gpu_lib):
+    """A job's result depends on its GLOBAL index only (shuffle seed), not on the shard it is run in: block-cyclic shards
+    (lrr_batch_run_ids, what bench.py --gpus N runs per rank) and contiguous runs reproduce the single launch."""
+    from lrr_b200.sharding import job_shard
     pair = synth.make_pair(4, N, N, size=160.0)
     jobs = synth.make_jobs(pair, 6, 4, seed=4)
     ctx = gpu_lib.context()
     fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
     full = ctx.batch_run(mv, fx, jobs, 70, 11)
+    cyc = np.zeros_like(full)
+    for r in range(3):
+        ids = job_shard(len(jobs), 3, r)
+        cyc[ids] = ctx.batch_run(mv, fx, jobs[ids], 70, 11, ids=ids)
     parts = []
     for r in range(3):
         a, b = job_block(len(jobs), 3, r)
         parts.append(ctx.batch_run(mv, fx, jobs[a:b], 70, 11 + a))
-    cat = np.concatenate(parts)
-    for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"):
-        assert np.array_equal(cat[k], full[k]), k
-    assert rel(cat["A"], full["A"]) < 1e-9 and rel(cat["cov"], full["cov"]) < 1e-9
+    for cat in (cyc, np.concatenate(parts)):
+        for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"):
+            assert np.array_equal(cat[k], full[k]), k
+        assert rel(cat["A"], full["A"]) < 1e-9 and rel(cat["cov"], full["cov"]) < 1e-9
     assert (full["status"] == 0).sum() >= 20 and full["converged"].sum() >= 12
+
+
+def test_two_contexts_in_one_process_and_multi_device_entry(gpu_lib):
+    """The ABI keeps no mutable global state: two contexts of one process (on two devices when the box has them, else both on
+    device 0) run the full-size path side by side, and lrr_batch_run_multi — one host thread per context, dynamic job cursor —
+    returns what the single-device call returns."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = [0, 1 if ndev > 1 else 0]
+    pair = synth.make_pair(4, N, N, size=160.0)
+    jobs = synth.make_jobs(pair, 12, 32, seed=4)
+    ctxs = [gpu_lib.context(d) for d in devs]
+    fxs = [c.upload(pair["fixed"]) for c in ctxs]; mvs = [c.upload(pair["moving"]) for c in ctxs]
+    # the finest-level kernels (dynamic shared memory above 48 KB: per-device function attributes) on both contexts
+    res = []
+    for c, mv, fx in zip(ctxs, mvs, fxs):
+        e = c.estimator("rrl_sym", mv, fx, 12)
+        e.set_transform(*pair["init"]); e.set_number_points(N, 0); e.set_number_points(N, 1)
+        for it in range(3):
+            e.one_iteration(it)
+        res.append(e.get_transform(0))
+    assert rel(res[1]["A"], res[0]["A"]) < 1e-12 and rel(res[1]["cov"], res[0]["cov"]) < 1e-10
+    single = ctxs[0].batch_run(mvs[0], fxs[0], jobs, 70, 7)
+    multi = gpu_lib.batch_run_multi(ctxs, mvs, fxs, jobs, 70, 7)
+    for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"):
+        assert np.array_equal(multi[k], single[k]), k
+    assert rel(multi["A"], single["A"]) < 1e-9 and rel(multi["cov"], single["cov"]) < 1e-9

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_job_block_partition():
-    from lrr_b200.sharding import job_block
+    from lrr_b200.sharding import job_block, job_shard
     for njobs in (0, 1, 7, 8192, 8193):
         for world in (1, 2, 3, 8):
             blocks = [job_block(njobs, world, r) for r in range(world)]
@@ -18,6 +18,12 @@ def test_job_block_partition():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+            # block-cyclic shards: a partition of the list, sizes within one, every location's candidates on every rank
+            shards = [job_shard(njobs, world, r) for r in range(world)]
+            assert sorted(np.concatenate(shards).tolist()) == list(range(njobs))
+            assert max(len(x) for x in shards) - min(len(x) for x in shards) <= 1
+            if njobs >= 32 * world:
+                assert all(len(set((x[x < 32 * world] // 32).tolist())) == world for x in shards) or world == 1
 
 
 def _worker(rank, world, port, outdir):
@@ -30,7 +36,7 @@ def _worker(rank, world, port, outdir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = Lib(os.path.join(ROOT, "oracle", "liblrr_oracle.so"), "lrro_")   # CPU stand-in for the device backend
     pair = synth.make_pair(4, 12000, 12000, size=80.0)
-    jobs = synth.make_jobs(pair, 3, 2, seed=4)
+    jobs = synth.make_jobs(pair, 3, 3, seed=4)
     ctx = lib.context()
     fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
     local = run_batch_sharded(ctx, mv, fx, jobs, 8, 5, rank, world)
