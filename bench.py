@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """bench.py — ICP iterations/s of the CDCL robust-ICP hot path on B200 (BASELINE.json metric).
 
-A "step" is one `one_iteration` call of the product-default estimator
-(rrl_estimation_symmetric_ICP_matching_all<3,12>) at the FINEST level (all points of both
-directions) on a synthetic lung-CT-sized pair with 100 000 shape features per volume,
-after the reference's own point-count ramp 1000 -> x2 -> all has been run and (untimed setup, like the ramp) the iteration has
-been continued until the transform stopped changing: the metric is the steady-state iteration; `config` carries
-the counts (`ramp_iterations`, `settle_iterations`).  The W warm-up steps come after that.
+A "step" is one `one_iteration` call of the product-default estimator (rrl_estimation_symmetric_ICP_matching_all<3,12>,
+SURVEY.md §3.2) at the FINEST level (all points of both directions) on a synthetic lung-CT-sized pair with 100 000 shape features
+per volume INSIDE a ramped registration: every registration starts from the initial transform, runs the
+reference's own point-count ramp 1000 -> x2 -> all and stops at the driver's convergence test
+(rrl/itkLocationRegistration.cxx:2418); the timed steps are its finest-level iterations — the transform still moves in every one of
+them, the first has no neighbour certificates at all — gathered over as many registrations as it takes (K steps after W untimed
+ones).  `value` = K / (sum of their CUDA-event times), L2 flushed before each.  The post-convergence fixed point that round 1
+reported as the headline (iterate on until the transform stops changing: every certificate holds, three launches per
+iteration) is kept as `value_fixed_point`: the driver loop never gets there.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-N > 1 (torchrun): the path shards only across independent registrations, so every rank runs
-its own replica of the registration on its own GPU, no data-path collective; `value` = all ranks' iterations
-divided by the max-over-ranks time ("weak" scaling).
+N > 1 (torchrun): the path shards only across independent registrations, so every rank runs its own replica of
+the single registration on its own GPU, no data-path collective; `value` = all ranks' iterations divided by the max-over-ranks
+time ("weak" scaling, replicas).  The batched workload C4 (`registrations`) is the FIXED list of 256 locations x 32
+initialisations sharded block-cyclically over the ranks (strong scaling), one result gather at the end.
 
-One JSON line on stdout (rank 0).  `value` = device-resident iterations/s with an L2 flush between timed
-iterations; `e2e` = the same metric through the C ABI with HOST buffers (upload of both volumes, estimator
-construction, full ramped run, result read-back inside the timed region).  `--impl reference` times the reference's own
-estimator code on the host (oracle/_ref: its sources compiled unmodified against oracle/vxl_shim; the oracle port if absent).
+One JSON line on stdout (rank 0).  `e2e` = the same metric through the C ABI with HOST buffers (upload of both volumes, estimator
+construction, full ramped run, result read-back inside the timed region).  `parity` compares the GPU registration with the CPU arm
+run on the same pair in the same process (iteration counts, neighbour index sets, transform, covariance) and the run FAILS
+(exit 3) when it is outside the north_star tolerance.  `c5` is config 5 (1 M features per side).  `--impl reference` times the
+reference's own estimator code on the host (oracle/_ref: its sources compiled unmodified against oracle/vxl_shim; the oracle port
+if absent).
 """
 import argparse
 import ctypes
@@ -35,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 N_FEATURES = 100_000
 SEED = 3
-WORKLOAD = "C3: rrl symmetric ICP matching-all <3,12>, 100k shape features per volume, finest level (all points)"
+WORKLOAD = "C3: rrl symmetric ICP matching-all <3,12>, 100k shape features per volume, finest-level iterations inside ramped registrations"
 METRIC = "icp_iterations_per_s_100k_features"
 UNIT = "iterations/s"
 # compulsory bytes per forward affine iteration = 124 B per match + 24 B per fixed feature
@@ -56,8 +62,13 @@ KERNEL_BYTES = {
     "collect": (16, 0),
     "accumulate": (24 + 4 + 8 + 8 + 8 + 24 + 48 + 8, 0),
     "resid": (24 + 4 + 24 + 48 + 8 + 8, 0),
-    # the whole iteration as one cooperative kernel: SURVEY.md §8(d) bytes per iteration (124 B per match + 24 B per to-feature)
-    "fused_iteration": (BYTES_PER_MATCH, BYTES_PER_FIXED),
+    # certificate pass = residual pass of the finished iteration + neighbour test of the next: x 24 + certificate 32 + previous neighbour 4 +
+    # q 24 + P 48 + w 8 (reads) + r2 8 (write)
+    "cert_resid": (24 + 32 + 4 + 24 + 48 + 8 + 8, 0),
+    "restamp": (4 + 8, 0),
+    # match completion: per RE-SEARCHED query (not per match): x 24 + q 24 + P 48 + idx 4 + r2 8 + certificate 32; the candidates read
+    # by the search itself are not compulsory traffic
+    "search": (140, 0), "queue": (140, 0),
 }
 
 
@@ -156,38 +167,54 @@ CPU_KIND_NOTE = {
 }
 
 
-def cpu_measure(pair, steps, warmup):
+def cpu_measure(pair, steps, warmup, keep=False):
     """CPU arm, single thread: the reference pins its estimators to one thread
-    (rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760) and one registration has no other parallel axis."""
+    (rrl/rrl_estimation_symmetric_ICP_matching_all.txx:760) and one registration has no other parallel axis.
+    Same metric as the b200 arm: the finest-level one_iteration calls INSIDE ramped registrations (every registration starts again
+    from the initial transform and stops at the driver's convergence test, rrl/itkLocationRegistration.cxx:2418), `steps` of them
+    timed after `warmup` untimed ones.  keep: also return the final state of the first registration (bench parity block)."""
     lib, kind = cpu_library()
     ctx = lib.context()
     t0 = time.perf_counter()
     fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
     est = ctx.estimator("rrl_sym", mv, fx, 12)
+    t_setup = time.perf_counter() - t0
     A, t, c = pair["init"]
-    est.set_transform(A, t, c)
-    iters, conv = ramp_to_finest(est)
-    est.get_transform(0)
-    t_reg = time.perf_counter() - t0
-    for i in range(warmup):
-        est.one_iteration(iters + i)
-    t0 = time.perf_counter()
-    for i in range(steps):
-        est.one_iteration(iters + warmup + i)
-    dt = time.perf_counter() - t0
-    return {"kind": kind, "finest_iters_per_s": steps / dt, "ms_per_step": 1e3 * dt / steps, "registration_s": t_reg,
-            "registration_iters": iters, "registration_iters_per_s": iters / t_reg, "converged": bool(conv)}
+    samples, seen, regs, first = [], 0, [], None
+    while len(samples) < steps:
+        t0 = time.perf_counter()
+        est.set_transform(A, t, c)
+        it, conv = 0, False
+        while not conv and it < 70:
+            finest = est.state().finest_level == 1
+            ta = time.perf_counter(); conv = est.one_iteration(it); dt = time.perf_counter() - ta
+            it += 1
+            if finest:
+                seen += 1
+                if seen > warmup and len(samples) < steps:
+                    samples.append(dt)
+        regs.append((time.perf_counter() - t0 + (t_setup if not regs else 0.0), it, bool(conv)))
+        if first is None and keep:
+            first = {"T": est.get_transform(0), "Tb": est.get_transform(1), "m0": est.get_matches(0), "m1": est.get_matches(1), "iters": it, "conv": bool(conv)}
+        if it == 0:
+            break
+    dt = float(np.sum(samples))
+    out = {"kind": kind, "finest_iters_per_s": len(samples) / dt, "ms_per_step": 1e3 * dt / len(samples), "samples": len(samples),
+           "registration_s": regs[0][0], "registration_iters": regs[0][1], "registration_iters_per_s": regs[0][1] / regs[0][0], "converged": regs[0][2]}
+    if keep:
+        out["first"] = first
+    return out
 
 
-BATCH_SEED, BATCH_SIZE_MM, BATCH_LOCATIONS_PER_GPU, BATCH_INITS = 4, 160.0, 32, 32
+BATCH_SEED, BATCH_SIZE_MM, BATCH_LOCATIONS, BATCH_INITS = 4, 160.0, 256, 32
 
 
 def make_batch_workload(world):
-    """C4, bounded: one 100k/100k pair, per GPU 32 locations x 32 initialisations (first near-correct,
-    the rest perturbed up to 30 deg / 20 mm), 50 mm ROI cubes, rrl symmetric <3,12>, <= 70 iterations each."""
+    """C4: one 100k/100k pair, the FIXED list of 256 locations x 32 initialisations (first near-correct, the
+    rest perturbed up to 30 deg / 20 mm) = 8192 jobs at every N, 50 mm ROI cubes, rrl symmetric <3,12>, <= 70 iterations each."""
     from lrr_b200 import synth
     pair = synth.make_pair(BATCH_SEED, N_FEATURES, N_FEATURES, size=BATCH_SIZE_MM)
-    jobs = synth.make_jobs(pair, BATCH_LOCATIONS_PER_GPU * world, BATCH_INITS, seed=BATCH_SEED)
+    jobs = synth.make_jobs(pair, BATCH_LOCATIONS, BATCH_INITS, seed=BATCH_SEED)
     return pair, jobs
 
 
@@ -221,8 +248,8 @@ def run_reference(args, rank):
     if rank != 0:
         return
     pair = make_workload()
-    steps = max(1, min(args.steps, 30))   # bounded sample: ~0.9 s of CPU per finest-level iteration
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 30))   # bounded sample: ~0.4 s of CPU per finest-level iteration, ~2.4 s per ramped registration
+    warm = max(0, min(args.warmup, 5))
     r = cpu_measure(pair, steps, warm)
     cores = 1
     line = {
@@ -231,7 +258,7 @@ def run_reference(args, rank):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_fixed": N_FEATURES, "n_moving": N_FEATURES, "seed": SEED, "l2": "host CPU run"},
         "cpu_baseline": {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": cores, "kind": r["kind"],
-                         "sample": f"{steps} one_iteration calls at the finest level after the full ramp; single thread = the "
+                         "sample": f"{steps} finest-level one_iteration calls inside ramped registrations ({warm} untimed first); single thread = the "
                                    "reference's execution model (its MultiThreader is pinned to 1 thread); " + CPU_KIND_NOTE[r["kind"]],
                          "host_cores_available": os.cpu_count()},
         # same definition as the b200 arm's e2e: iterations of one whole ramped registration / its wall time (setup included),
@@ -263,6 +290,79 @@ def pin(feats):
     return out
 
 
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def gpu_registration(est, pair, on_finest=None):
+    """One ramped registration from the initial transform to the driver's convergence test.  on_finest(call) wraps every
+    finest-level one_iteration call (timing); returns (iterations, converged, finest-level iterations)."""
+    A0, t0_, c0 = pair["init"]
+    est.set_transform(A0, t0_, c0)
+    it, conv, nf = 0, False, 0
+    while not conv and it < 70:
+        finest = est.state().finest_level == 1
+        if finest and on_finest is not None:
+            conv = on_finest(lambda: est.one_iteration(it))
+        else:
+            conv = est.one_iteration(it)
+        nf += int(finest)
+        it += 1
+    return it, conv, nf
+
+
+def run_c5(ctx, stream, peak, steps):
+    """Config 5: 1 M features per side, cdcl_estimation_ICP_matching_all<3,12> over every point to convergence,
+    then cdcl_obj_fun_cov<3,12> + L-BFGS (<= 5 evaluations) on the final matches.  The only configuration whose working set
+    (148 MB per iteration) does not fit the L2."""
+    import torch
+    from lrr_b200 import synth
+    n = 1_000_000
+    pair = synth.make_pair(5, n, n)
+    with torch.cuda.stream(stream):
+        fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+        est = ctx.estimator("cdcl_fwd", mv, fx, 12)
+        est.set_flags(True, True)
+        times = []
+        for rep in range(2):   # (the first run warms the memory pool and the order-statistic windows)
+            est.set_transform(*pair["init"]); est.set_number_points(n)
+            it, conv, times = 0, False, []
+            while not conv and it < 30:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream); conv = est.one_iteration(it); b.record(stream); b.synchronize()
+                times.append(a.elapsed_time(b)); it += 1
+        run_iters, run_conv = it, conv
+        ctx.set_profiling(True)
+        for k in range(steps):
+            est.one_iteration(it); it += 1
+        ph_it = ctx.phase_times()
+        cov = est.get_transform(0)["cov"]
+        U = np.linalg.cholesky(cov).T
+        x = np.concatenate([U[i, i:] for i in range(12)])
+        ctx.set_profiling(True)
+        for k in range(5):
+            f0, g0 = est.objcov_eval(x)
+        ph_obj = ctx.phase_times(); ctx.set_profiling(False)
+        t0 = time.perf_counter(); fs, fe, ev = est.objcov_refine(5); t_ref = time.perf_counter() - t0
+        est.close(); fx.close(); mv.close()
+    it_bytes = 124 * n + 24 * n
+    in_run_ms = float(np.mean(times[1:])) if len(times) > 1 else float(times[0])
+    steady_ms = float(sum(v[0] / v[1] for v in ph_it.values()))
+    obj_us = 1e3 * ph_obj["objcov"][0] / ph_obj["objcov"][1]
+    return {
+        "workload": "C5: whole-volume pair, 1M features per side, cdcl forward affine <3,12> over every point + cdcl_obj_fun_cov L-BFGS refinement",
+        "run": {"iterations": run_iters, "converged": bool(run_conv), "ms_per_iteration_in_run": in_run_ms, "ms_first_iteration": float(times[0])},
+        "iteration": {"algorithmic_bytes": it_bytes, "ms_in_run": in_run_ms, "gbs_in_run": it_bytes / (in_run_ms * 1e-3) / 1e9,
+                      "frac_in_run": it_bytes / (in_run_ms * 1e-3) / 1e9 / peak,
+                      "ms_after_convergence_sum_of_kernels": steady_ms, "frac_after_convergence": it_bytes / (steady_ms * 1e-3) / 1e9 / peak,
+                      "kernels_us": {k: 1e3 * v[0] / v[1] for k, v in ph_it.items()}},
+        "objcov_eval": {"algorithmic_bytes": 156 * n, "us": obj_us, "gbs": 156 * n / (obj_us * 1e-6) / 1e9, "frac": 156 * n / (obj_us * 1e-6) / 1e9 / peak,
+                        "f": float(f0)},
+        "objcov_refine": {"f_start": float(fs), "f_end": float(fe), "evaluations": int(ev), "seconds": t_ref},
+    }
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import lrr_b200
@@ -285,6 +385,7 @@ def run_b200(args, rank, world, local_rank):
     ctx = lib.context(local_rank)
     ctx.set_stream(stream.cuda_stream)
     A0, t0_, c0 = pair["init"]
+    K, W = args.steps, max(3, args.warmup)
 
     def barrier():
         if dist is not None:
@@ -294,70 +395,101 @@ def run_b200(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
         est = ctx.estimator("rrl_sym", mv, fx, 12)
-        est.set_transform(A0, t0_, c0)
-        ramp_iters, ramp_conv = ramp_to_finest(est)
-        st = est.state()
-        assert st.finest_level == 1 and st.number_points[0] == N_FEATURES and st.number_points[1] == N_FEATURES, "ramp did not reach the finest level"
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
-        # The metric is the STEADY-STATE iteration at the finest level.  The driver loop's convergence test fires
-        # while the transform still moves by ~1e-4 mm per iteration; part of the setup (untimed, like the ramp) is therefore to
-        # iterate on until the transform has stopped changing (at most 16 iterations; the count goes into `config`).
-        it_no = ramp_iters
+        # ---- warm-up: W finest-level iterations = whole untimed registrations; the first one is also the parity registration ----
+        seen = 0
+        reg_iters, reg_conv, reg_finest = gpu_registration(est, pair)
+        seen += reg_finest
+        par_gpu = {"T": est.get_transform(0), "Tb": est.get_transform(1), "m0": est.get_matches(0), "m1": est.get_matches(1),
+                   "iters": reg_iters, "conv": bool(reg_conv)}
+        st = est.state()
+        assert st.finest_level == 1 and st.number_points[0] == N_FEATURES and st.number_points[1] == N_FEATURES, "ramp did not reach the finest level"
+        while seen < W:
+            seen += gpu_registration(est, pair)[2]
+        sampler = ClockSampler(local_rank); sampler.start()
+
+        # ---- timed region 1 (headline): exactly K finest-level iterations inside ramped registrations, L2 flushed before each,
+        #      CUDA events on the launching stream ----
+        evs, warm_evs = [], []
+
+        def timed(call, store, do_flush):
+            if len(store) >= K:
+                return call()
+            if do_flush:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); r = call(); b.record(stream)
+            store.append((a, b))
+            return r
+
+        barrier()
+        launches0 = ctx.launch_count()
+        n_regs = 0
+        while len(evs) < K:
+            gpu_registration(est, pair, lambda call: timed(call, evs, True)); n_regs += 1
+        barrier()
+        launches = ctx.launch_count() - launches0
+        ms_iters = np.array([a.elapsed_time(b) for a, b in evs])
+        total_ms = float(ms_iters.sum())
+        # ---- the same without the flush (the production state: a 30 MB working set stays in the 126 MB L2) ----
+        barrier()
+        while len(warm_evs) < K:
+            gpu_registration(est, pair, lambda call: timed(call, warm_evs, False))
+        barrier()
+        warm_ms_iters = np.array([a.elapsed_time(b) for a, b in warm_evs])
+        warm_ms = float(warm_ms_iters.sum())
+        # ---- per-kernel CUDA-event times of the finest-level iterations inside registrations (L2 flushed) ----
+        def profiled(call):
+            flush.fill_(1); ctx.set_profiling_keep(True); r = call(); ctx.set_profiling_keep(False); return r
+        ctx.set_profiling(True); ctx.set_profiling_keep(False)
+        nprof = 0
+        while nprof < max(10, min(K, 20)):
+            nprof += gpu_registration(est, pair, profiled)[2]
+        phases = ctx.phase_times(); ctx.set_profiling(False)
+        stats_last = est.stats()
+
+        # ---- fixed point (round 1's headline): iterate past convergence until the transform has stopped changing ----
+        gpu_registration(est, pair)
+        it_no = 70
         settle_iters, prevT = 0, est.get_transform(0)
-        while settle_iters < 16:
+        while settle_iters < 24:
             est.one_iteration(it_no); it_no += 1; settle_iters += 1
             T = est.get_transform(0)
             moved = max(float(np.abs(T["A"] - prevT["A"]).max()), float(np.abs(T["t"] - prevT["t"]).max()))
             prevT = T
             if moved < 1e-12:
                 break
-        sampler = ClockSampler(local_rank); sampler.start()
-        for _ in range(max(3, args.warmup)):
+        for _ in range(3):
             est.one_iteration(it_no); it_no += 1
-
-        # ---- timed region 1: K iterations, L2 flushed between iterations, CUDA events on the launching stream ----
         barrier()
-        launches0 = ctx.launch_count()
-        evs = []
-        for _ in range(args.steps):
+        fp_evs = []
+        for _ in range(K):
             flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            est.one_iteration(it_no); it_no += 1
-            b.record(stream)
-            evs.append((a, b))
+            a.record(stream); est.one_iteration(it_no); it_no += 1; b.record(stream)
+            fp_evs.append((a, b))
         barrier()
-        launches = ctx.launch_count() - launches0
-        ms_iters = np.array([a.elapsed_time(b) for a, b in evs])
-        total_ms = float(ms_iters.sum())
-
-        # ---- timed region 2: L2-warm back-to-back iterations (the production steady state) ----
-        barrier()
+        fp_ms = float(sum(a.elapsed_time(b) for a, b in fp_evs))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        for _ in range(args.steps):
+        for _ in range(K):
             est.one_iteration(it_no); it_no += 1
         b.record(stream)
         barrier()
-        warm_ms = a.elapsed_time(b)
-
-        # ---- per-kernel CUDA-event times (same conditions as region 1) ----
+        fp_warm_ms = a.elapsed_time(b)
         ctx.set_profiling(True)
-        for _ in range(args.steps):
-            flush.fill_(1)
-            est.one_iteration(it_no); it_no += 1
-        phases = ctx.phase_times()
-        ctx.set_profiling(False)
-        clocks = sampler.stop()   # sampled across warm-up, both timed regions and the per-kernel pass
-        final = est.get_transform(0)
+        for _ in range(min(K, 20)):
+            flush.fill_(1); est.one_iteration(it_no); it_no += 1
+        fp_phases = ctx.phase_times(); ctx.set_profiling(False)
+        clocks = sampler.stop()   # sampled across both timed regions, the per-kernel passes and the fixed point
 
-    tm = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
+    tm = torch.tensor([total_ms, warm_ms, fp_ms, fp_warm_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms_max, warm_ms_max = float(tm[0]), float(tm[1])
-    value = world * args.steps / (total_ms_max * 1e-3)
-    value_warm = world * args.steps / (warm_ms_max * 1e-3)
+    total_ms_max, warm_ms_max, fp_ms_max, fp_warm_ms_max = (float(x) for x in tm)
+    value = world * K / (total_ms_max * 1e-3)
+    value_warm = world * K / (warm_ms_max * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (rank-local; max over ranks) ----
     e2e_steps = 0 if args.only_iterations else max(1, min(5, args.steps))
@@ -397,7 +529,7 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_iters / float(te[0]) if e2e_iters else None
 
-    # ---- batched location registration, sharded over the ranks ----
+    # ---- batched location registration: the fixed C4 list sharded block-cyclically over the ranks ----
     from lrr_b200.sharding import gather_results, run_batch_sharded
     bpair, bjobs = make_batch_workload(world)
     if args.only_iterations:
@@ -430,95 +562,143 @@ def run_b200(args, rank, world, local_rank):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     M, N = N_FEATURES, N_FEATURES
-    # dominant kernel by CUDA-event time
-    dom = max(phases.items(), key=lambda kv: kv[1][0])[0] if phases else "match"
-    per_phase = {}
-    for name, (ms, cnt) in phases.items():
-        pm_, pt_ = KERNEL_BYTES.get(name, (0, 0))
-        ndirs = 1 if name in ("norm1", "norm2", "resid") else 2
-        by = ndirs * (pm_ * M + pt_ * N)
-        us = 1e3 * ms / cnt
-        per_phase[name] = {"us_per_launch": us, "launches": cnt, "algorithmic_bytes": by, "gbs": by / (us * 1e-6) / 1e9 if us > 0 else None}
-        if name in ("norm1", "norm2") and os.environ.get("LRR_NO_NORM_SKIP") is None and os.environ.get("LRR_NO_PROOF") is None:
-            # steady state: every query is kept by its certificate, the match set — all the normalisation depends on — is unchanged,
-            # and the launch leaves at entry (Scal::norm_dirty): no bytes are moved, the time is the launch itself
-            per_phase[name].update({"algorithmic_bytes": 0, "gbs": None, "note": "leaves at entry while no match changed (steady state)"})
-    d = per_phase.get(dom, {"gbs": 0, "us_per_launch": 0, "algorithmic_bytes": 0})
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bench.py cannot run under a profiler)
+    researched = float(sum(stats_last["cert_failed"]))   # queries of the last profiled iteration's certificate pass that had to be searched again
+
+    def kernel_table(ph):
+        tab = {}
+        for name, (ms, cnt) in ph.items():
+            pm_, pt_ = KERNEL_BYTES.get(name, (0, 0))
+            ndirs = 1 if name in ("norm1", "norm2", "restamp") else 2
+            by = ndirs * (pm_ * M + pt_ * N)
+            if name in ("search", "queue"):
+                by = None   # re-searched queries only: a few thousand of 200 000, not a streaming kernel (est.stats() in `neighbour_search`)
+            us = 1e3 * ms / cnt
+            tab[name] = {"us_per_launch": us, "launches": cnt, "algorithmic_bytes": by, "gbs": (by / (us * 1e-6) / 1e9) if (by and us > 0) else None}
+        return tab
+    per_phase, fp_per_phase = kernel_table(phases), kernel_table(fp_phases)
+    KNAME = {"resid": "k_match_cert (residual pass of the iteration = certificate pass of the next find_closest)", "weight": "k_weight", "accumulate": "k_accumulate (+ solve)",
+             "search": "k_match_tile (staged search + sparse list)", "queue": "k_match_hard", "norm1": "k_norm1", "norm2": "k_norm2", "restamp": "k_restamp", "collect": "k_collect", "match": "k_match_cert + k_match_tile + k_match_hard"}
+    streaming = {k: v for k, v in per_phase.items() if v["gbs"]}
+    dom = max(streaming.items(), key=lambda kv: kv[1]["us_per_launch"])[0]
+    d = per_phase[dom]
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        names = {"match": ["k_match_cert", "k_match_tile", "k_match_hard"], "accumulate": ["k_accumulate"], "weight": ["k_weight"]}.get(dom, [])
+        names = {"accumulate": ["k_accumulate"], "weight": ["k_weight"], "resid": ["k_match_cert"]}.get(dom, [])
         if names and all(n in tj["dram_bytes_per_launch"] for n in names):
             traffic = sum(tj["dram_bytes_per_launch"][n] for n in names); traffic_src = tj["source"]
     except Exception:
         pass
     it_bytes = algorithmic_bytes_iteration(M, N, M, N)
-    ms_step = total_ms_max / args.steps
+    ms_step = total_ms_max / K
+    fp_ms_step, fp_warm_ms_step = fp_ms_max / K, fp_warm_ms_max / K
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_fixed": N, "n_moving": M, "seed": SEED, "parallelism": f"replicas x{world} (no data-path collective)",
-                   "l2": "flushed (256 MiB write) between timed iterations; working set ~30 MB is L2-resident otherwise",
-                   "ramp_iterations": ramp_iters, "ramp_converged": bool(ramp_conv), "settle_iterations": settle_iters},
-        "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_iteration (fused: match, normalise, weight, order statistics, accumulate, solve, residuals)" if dom == "fused_iteration" else ("k_match_cert + k_match_tile + k_match_hard (exact 1-NN: neighbour certificates, shared-memory-staged cells for the queries they do not cover, queued far queries)" if dom == "match" else "k_" + dom), "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+                   "l2": "flushed (256 MiB write) before every timed iteration; working set ~30 MB is L2-resident otherwise (value_l2_warm)",
+                   "registration_iterations": reg_iters, "finest_level_iterations_per_registration": reg_finest, "registrations_timed": n_regs,
+                   "timed_steps": "the finest-level one_iteration calls of ramped registrations up to the driver's convergence test (transform still moving; the first of each registration has no certificates)"},
+        "ms_per_step_median": float(np.median(ms_iters)), "ms_per_step_each": [round(float(x), 4) for x in ms_iters],
+        "value_l2_warm": value_warm, "ms_per_step_l2_warm": warm_ms_max / K, "ms_per_step_l2_warm_median": float(np.median(warm_ms_iters)),
+        "value_fixed_point": world * K / (fp_ms_max * 1e-3), "value_fixed_point_l2_warm": world * K / (fp_warm_ms_max * 1e-3),
+        "fixed_point": {"what": "round 1's headline: the registration iterated past convergence until the transform stopped changing (every neighbour certificate holds; "
+                                "certificate/residual pass -> weight -> accumulate+solve); the driver loop never reaches this state",
+                        "ms_per_step": fp_ms_step, "ms_per_step_l2_warm": fp_warm_ms_step, "settle_iterations": settle_iters,
+                        "roofline_iteration_frac": it_bytes / (fp_ms_step * 1e-3) / 1e9 / peak, "kernels": fp_per_phase},
+        "roofline": {"bound": "hbm", "kernel": KNAME.get(dom, "k_" + dom), "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": (d["gbs"] / peak) if d["gbs"] else None, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
-                     "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
+                     "us_per_launch": d["us_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes"],
+                     "note": "dominant streaming kernel of the in-registration finest-level iteration by CUDA-event time; per-kernel events serialise the "
+                             "programmatic-dependent-launch overlap, so their sum exceeds ms_per_step"},
         "roofline_iteration": {"algorithmic_bytes": it_bytes, "achieved_gbs": it_bytes / (ms_step * 1e-3) / 1e9,
                                "frac": it_bytes / (ms_step * 1e-3) / 1e9 / peak,
-                               "achieved_gbs_l2_warm": it_bytes / (warm_ms_max / args.steps * 1e-3) / 1e9},
+                               "achieved_gbs_l2_warm": it_bytes / (warm_ms_max / K * 1e-3) / 1e9},
         "kernels": per_phase,
+        "neighbour_search": {"queries_searched_again_last_profiled_iteration": researched, "of": 2 * M, "stats": stats_last},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "iterations": e2e_iters, "seconds": float(te[0]),
                 "what": "per step: upload both volumes (cdcl_feature_ICP arrays: locations, projectors, strengths, shapes, directions) from pinned host memory (grid build), construct estimator, set_transform, "
                         "ramped run to convergence (<=70 one_iteration calls), read back transform+covariance"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "registrations": {"value": len(bjobs) / batch_s, "unit": "registrations/s", "jobs": int(len(bjobs)), "seconds": batch_s,
+        "registrations": {"value": len(bjobs) / batch_s, "unit": "registrations/s", "jobs": int(len(bjobs)), "seconds": batch_s, "scaling": "strong (fixed list)",
                           "verified": verified_count(full), "verified_per_s": verified_count(full) / batch_s,
                           "rejected": int((full["status"] == 1).sum()), "mean_iterations": float(full["iterations"][full["status"] == 0].mean()),
-                          "what": f"C4 bounded: {BATCH_LOCATIONS_PER_GPU} locations x {BATCH_INITS} initialisations per GPU on one resident "
-                                  "100k/100k pair, 50 mm ROI, rrl symmetric <3,12>, <= 70 iterations, jobs sharded over the ranks, one result gather"},
+                          "what": f"C4: {BATCH_LOCATIONS} locations x {BATCH_INITS} initialisations = {len(bjobs)} jobs on one resident 100k/100k pair, 50 mm ROI, "
+                                  "rrl symmetric <3,12>, <= 70 iterations, block-cyclic shards over the ranks, one result gather"},
     }
-    if world == 1 and not args.only_iterations and os.environ.get("LRR_NO_PROOF") is None:
-        # the same timed loop with the neighbour certificates switched off (every finest-level query searched in every iteration):
-        # what an iteration costs when nothing can be kept, e.g. the first iteration at the finest level
-        try:
-            env = dict(os.environ, LRR_NO_PROOF="1")
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--only-iterations", "--steps", str(args.steps), "--warmup", str(args.warmup)],
-                                 env=env, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
-            sub = json.loads(out[-1])
-            line["certificates_off"] = {"value": sub["value"], "unit": UNIT, "ms_per_step": sub["ms_per_step"], "value_l2_warm": sub["value_l2_warm"],
-                                        "match_us": sub["kernels"]["match"]["us_per_launch"],
-                                        "what": "LRR_NO_PROOF=1: same loop, every query of both directions searched in every iteration (no neighbour certificates)"}
-        except Exception as ex:   # noqa: BLE001
-            line["certificates_off"] = {"error": repr(ex)}
+    rc_exit = 0
     if world == 1 and not args.no_cpu and not args.only_iterations:
-        r = cpu_measure(pair, 6, 1)
+        # ---- CPU arm on the same pair in the same process: baseline AND parity of the benchmarked registration ----
+        r = cpu_measure(pair, 6, 0, keep=True)
+        c = r.pop("first")
         line["cpu_baseline"] = {"value": r["finest_iters_per_s"], "unit": UNIT, "cores": 1, "kind": r["kind"],
-                                "sample": "full ramped registration + 6 one_iteration calls at the finest level, single thread "
+                                "sample": f"{r['samples']} finest-level one_iteration calls inside ramped registrations, single thread "
                                           "(the reference's execution model); " + CPU_KIND_NOTE[r["kind"]],
                                 "registration_iters_per_s": r["registration_iters_per_s"], "registration_s": r["registration_s"],
                                 "host_cores_available": os.cpu_count()}
+        g = par_gpu
+        par = {"iters_equal": g["iters"] == c["iters"] and g["conv"] == c["conv"], "iterations": [g["iters"], c["iters"]],
+               "idx_equal": bool(np.array_equal(g["m0"][1], c["m0"][1]) and np.array_equal(g["m1"][1], c["m1"][1]) and np.array_equal(g["m0"][0], c["m0"][0])),
+               "rel_A": relerr(g["T"]["A"], c["T"]["A"]), "rel_t": relerr(g["T"]["t"], c["T"]["t"]), "rel_cov": relerr(g["T"]["cov"], c["T"]["cov"]),
+               "rel_A_backward": relerr(g["Tb"]["A"], c["Tb"]["A"]), "rel_w": relerr(g["m0"][2], c["m0"][2]),
+               "against": r["kind"], "tolerance": 1e-5,
+               "what": "the first (untimed) GPU registration of this run against the CPU arm on the same pair: iteration count and convergence flag, neighbour index sets of both "
+                       "directions at the end (np.array_equal), forward / backward transform and 12 x 12 covariance"}
+        par["ok"] = bool(par["iters_equal"] and par["idx_equal"] and max(par["rel_A"], par["rel_t"], par["rel_cov"], par["rel_A_backward"]) <= 1e-5)
+        line["parity"] = par
+        if not par["ok"]:
+            rc_exit = 3
         line["cpu_baseline"]["registrations"] = cpu_batch_measure(bpair, bjobs)
+        # C4 `verified`, last clause of SURVEY.md §8(d): GPU theta / Sigma within 1e-5 of the CPU oracle — on a sample, outside the timed region
+        line["registrations"]["verified_vs_oracle"] = verify_batch_sample(bpair, bjobs, full)
+        if not line["registrations"]["verified_vs_oracle"]["ok"]:
+            rc_exit = 3
     else:
         line["cpu_baseline"] = None
-    line["final_A00"] = float(final["A"][0, 0])
+    if world == 1 and not args.only_iterations and not args.no_c5:
+        try:
+            line["c5"] = run_c5(ctx, stream, peak, 10)
+        except Exception as ex:   # noqa: BLE001
+            line["c5"] = {"error": repr(ex)}
     sys.stdout.flush()
     os.write(out_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
+    if rc_exit:
+        print("bench.py: PARITY FAILURE (see `parity` / `registrations.verified_vs_oracle` in the JSON line)", file=sys.stderr)
+        sys.exit(rc_exit)
+
+
+def verify_batch_sample(pair, jobs, gpu_results, n_sample=64):
+    """64 jobs spread over the list, re-run by the CPU oracle (all host cores) and compared with the GPU results."""
+    from lrr_b200.capi import Lib, RESULT_DTYPE
+    lib = Lib(os.path.join(ROOT, "oracle", "liblrr_oracle.so"), "lrro_")
+    ctx = lib.context()
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    ids = np.unique(np.linspace(0, len(jobs) - 1, n_sample).astype(np.int64))
+    ref = ctx.batch_run(mv, fx, jobs[ids], 70, BATCH_SEED, ids=ids)
+    g = gpu_results[ids]
+    same_int = all(np.array_equal(g[k], ref[k]) for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"))
+    ran = ref["status"] == 0
+    worst = 0.0
+    for k in ("A", "t", "cov"):
+        for a, b in zip(g[k][ran], ref[k][ran]):
+            worst = max(worst, relerr(a, b))
+    return {"jobs": int(len(ids)), "ran": int(ran.sum()), "integer_fields_equal": bool(same_int), "worst_rel_A_t_cov": worst, "tolerance": 1e-5,
+            "ok": bool(same_int and worst <= 1e-5), "what": "status, converged, oscillated, iteration count and ROI sizes identical; A, t and covariance of every job that ran within 1e-5 relative"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=50)   # finest-level iterations inside registrations (~5 per registration)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--only-iterations", action="store_true", help="skip the e2e / batch / cpu legs (short run for ncu launch lists)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 leg (1 M features per side)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

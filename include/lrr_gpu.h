@@ -109,7 +109,9 @@ int64_t lrr_ctx_launch_count(lrr_ctx* ctx);
 /* instrumentation (no reference counterpart; the reference prints vul_timer wall times per phase,
  * cdcl/cdcl_estimation_ICP_matching_all.txx:407-408,442-444): CUDA-event time per phase kernel.
  * phase index: 0 match, 1 norm1, 2 norm2, 3 weight, 4 collect, 5 accumulate+solve, 6 resid, 7 muse, 8 metric,
- * 9 objcov, 10 batch (one block per registration), 11 fused iteration (one cooperative kernel).  Enabling resets the counters. */
+ * 9 objcov, 10 batch (one block per registration), 11 restamp, 12 match completion: staged search / sparse list, 13 match
+ * completion: queued queries.  Phase 0 is a whole find_closest outside the pipelined finest level; there the certificate pass is
+ * the residual pass (6).  enable = 1 resets the counters and starts, 2 resumes without a reset, 0 pauses (counters kept). */
 int  lrr_ctx_set_profiling(lrr_ctx* ctx, int enable);
 int  lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count);
 

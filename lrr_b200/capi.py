@@ -177,14 +177,19 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.fn("ctx_launch_count")(self.h))
 
-    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "restamp"]
+    PHASES = ["match", "norm1", "norm2", "weight", "collect", "accumulate", "resid", "muse", "metric", "objcov", "batch", "restamp", "search", "queue"]
 
     def set_profiling(self, on: bool):
         self.check(self.lib.fn("ctx_set_profiling")(self.h, int(on)), "ctx_set_profiling")
 
+    def set_profiling_keep(self, on: bool):
+        """pause / resume the per-kernel timers without resetting the counters"""
+        self.check(self.lib.fn("ctx_set_profiling")(self.h, 2 if on else 0), "ctx_set_profiling")
+
     def phase_times(self) -> dict:
-        ms = np.zeros(12); cnt = np.zeros(12, dtype=np.int64)
-        self.check(self.lib.fn("ctx_phase_times")(self.h, 12, _dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))), "ctx_phase_times")
+        n = len(self.PHASES)
+        ms = np.zeros(n); cnt = np.zeros(n, dtype=np.int64)
+        self.check(self.lib.fn("ctx_phase_times")(self.h, n, _dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))), "ctx_phase_times")
         return {p: (float(ms[i]), int(cnt[i])) for i, p in enumerate(self.PHASES) if cnt[i]}
 
     def upload(self, feats: dict) -> "FeatureSet":

@@ -51,7 +51,7 @@ extern "C" int lrr_ctx_set_profiling(lrr_ctx* ctx, int enable) {
   enter(ctx);
   drain_spans(ctx);
   ctx->profiling = enable != 0;
-  for (int i = 0; i < LRR_NPHASE; ++i) { ctx->phase_ms[i] = 0; ctx->phase_count[i] = 0; }
+  if (enable == 1) for (int i = 0; i < LRR_NPHASE; ++i) { ctx->phase_ms[i] = 0; ctx->phase_count[i] = 0; }   // 1: reset and start; 2: resume; 0: pause (counters kept)
   return LRR_OK;
 }
 extern "C" int lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count) {
@@ -811,7 +811,7 @@ static int estimate_and_pull(lrr_est* e, int resid_mask, bool spec = false) {
       e->steady_hint = false;
       if ((rc = restore(LRR_ST_NOT_STEADY)) != LRR_OK) return rc;
       e->window_holdoff = holdoff0; ctx->sel_owner = owner0;
-      { EstArgs a = est_args(e); PHASE(PH_MATCH); lrr_k_match_rest(a, ctx->stream, &ctx->launches); }
+      { EstArgs a = est_args(e); { PHASE(PH_SEARCH); lrr_k_match_search(a, ctx->stream, &ctx->launches); } { PHASE(PH_QUEUE); lrr_k_match_queue(a, ctx->stream, &ctx->launches); } }
       return estimate_and_pull(e, resid_mask, false);
     }
   }
@@ -844,7 +844,7 @@ static int match_estimate_pull(lrr_est* e, int resid_mask) {
     e->pre_matched = false;
     spec = spec_ok(e);
     EstArgs a = est_args(e);
-    if (!spec) { PHASE(PH_MATCH); lrr_k_match_rest(a, ctx->stream, &ctx->launches); }
+    if (!spec) { { PHASE(PH_SEARCH); lrr_k_match_search(a, ctx->stream, &ctx->launches); } { PHASE(PH_QUEUE); lrr_k_match_queue(a, ctx->stream, &ctx->launches); } }
     finish_find_closest(e, a);
   } else {
     spec = spec_ok(e);
@@ -877,7 +877,8 @@ extern "C" int lrr_est_find_closest(lrr_est* e) {
   if (e->pre_matched) {   // the certificate pass has run already (trailing pass of the last iteration): complete the match
     e->pre_matched = false;
     EstArgs a = est_args(e);
-    { PHASE(PH_MATCH); lrr_k_match_rest(a, ctx->stream, &ctx->launches); }
+    { PHASE(PH_SEARCH); lrr_k_match_search(a, ctx->stream, &ctx->launches); }
+    { PHASE(PH_QUEUE); lrr_k_match_queue(a, ctx->stream, &ctx->launches); }
     finish_find_closest(e, a);
   } else {
     int rc = do_find_closest(e); if (rc != LRR_OK) return rc;

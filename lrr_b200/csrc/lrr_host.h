@@ -7,8 +7,8 @@
 #include "lrr_internal.h"
 #include "lrr_linalg.cuh"
 
-#define LRR_NPHASE 12
-enum { PH_MATCH = 0, PH_NORM1, PH_NORM2, PH_WEIGHT, PH_COLLECT, PH_ACCUM, PH_RESID, PH_MUSE, PH_METRIC, PH_OBJCOV, PH_BATCH, PH_RESTAMP };
+#define LRR_NPHASE 14
+enum { PH_MATCH = 0, PH_NORM1, PH_NORM2, PH_WEIGHT, PH_COLLECT, PH_ACCUM, PH_RESID, PH_MUSE, PH_METRIC, PH_OBJCOV, PH_BATCH, PH_RESTAMP, PH_SEARCH, PH_QUEUE };
 struct lrr_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;

@@ -229,6 +229,11 @@ void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches, bool ce
   lrr_k_match_rest(a, st, launches);
 }
 void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches) {
+  lrr_k_match_search(a, st, launches);
+  lrr_k_match_queue(a, st, launches);
+}
+// pass A: the staged search / sparse list of the finest level (lrr_tile.cu) or the thread-per-query ball scan of the ramp levels
+void lrr_k_match_search(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
   if (!lrr_no_tile() && lrr_match_tile_usable(a)) {   // finest level (lrr_tile.cu): shared-memory-staged cells for what the certificates did not keep
     lrr_k_match_tile(a, st, launches);
@@ -237,6 +242,9 @@ void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches) {
     dim3 grid(std::min(nblk_for(maxM(a)), 2 * lrr_num_sms()), a.ndir);
     lrr_launch_pdl(k_match, grid, dim3(LRR_THREADS), 0, st, a); ++*launches;
   }
+}
+// pass B: one warp per queued query
+void lrr_k_match_queue(const EstArgs& a, cudaStream_t st, long long* launches) {
   // queue length is only known on the device: a fixed grid of warps strides over it
   dim3 gridb(resident_width(k_match_hard, LRR_THREADS, 1, 32LL * maxM(a)));
   lrr_launch_pdl(k_match_hard, gridb, dim3(LRR_THREADS), 0, st, a); ++*launches;

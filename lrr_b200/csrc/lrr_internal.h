@@ -233,6 +233,8 @@ void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx,
                        cudaStream_t st, long long* launches);
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches, bool cert_only = false);   // certificate pass / pass A + pass B
 void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches);   // what a cert_only call left out: staged search + pass B
+void lrr_k_match_search(const EstArgs& a, cudaStream_t st, long long* launches);  // ... its first half: staged search / sparse list / ramp-level pass A
+void lrr_k_match_queue(const EstArgs& a, cudaStream_t st, long long* launches);   // ... its second half: pass B over the queue
 // lrr_tile.cu: tile construction and the shared-memory-staged pass A of the finest level
 void lrr_k_build_tiles(const double* fx, const double* fy, const double* fz, int n_in, const TileGeom& g, int* tile_cnt, int* tile_start,
                        int* chunk_start, int* tile_of, int* tmp, int2* chunk_tab, int* proc, cudaStream_t st, long long* launches);
