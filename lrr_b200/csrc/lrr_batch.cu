@@ -24,7 +24,7 @@ struct BatchWork {                 // per-block workspace in global memory
   int* forig[2];                   // CAP
   int* sidx[2]; double* pm[2];     // per match: sidx, 4 x CAP doubles (w r2 gkey skey)
   int* prev_s[2];
-  int* hq[2]; double* hq_best[2];  // 3 x CAP + 1 ints, CAP doubles
+  int* hq[2]; double* hq_best[2];  // 2 queues x (3 x CAP + 4) ints, 2 x CAP doubles
   unsigned long long* stamp[2];    // n_to
   Scal* sc[2];
 };
@@ -39,6 +39,7 @@ struct BatchArgs {
   double* w_f; double* w_fP6; int* w_forig; int* w_sidx; double* w_pm; int* w_prev; int* w_hq; double* w_hqb;
   unsigned long long* w_stamp0; unsigned long long* w_stamp1; Scal* w_sc;
   double muse_table[4 * 32]; int muse_rows;   // table for n = 1000
+  int ball_rows, g8;                            // pass A keeps balls of at most ball_rows rows; the rest: eight-lane groups (g8) / one warp per query
   long long* dbg;                               // optional: 16 cycle counters (block 0), phase profile
 };
 
@@ -209,6 +210,8 @@ struct BatchShared {
   double seg[40];
   int si[16]; double sd[4];
   int cnt;
+  DirArgs d2[2];                        // the same directions with the second queue (what the eight-lane groups pass on)
+  int rows[(BATCH_THREADS / 8) * 2 * LRR_G8_ROWS];   // row tables of the eight-lane groups
   // control state (thread 0 writes, everybody reads after a barrier)
   int converged, status, it, finest, osc, job;
   unsigned int number_matches;
@@ -221,7 +224,7 @@ struct BatchShared {
 extern __shared__ __align__(16) unsigned char batch_smem[];
 #define TPH(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); S.tph[i] += now_ - tmark; tmark = now_; } } while (0)
 
-__global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__ BatchArgs B) {
+__global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constant__ BatchArgs B) {
   BatchShared& S = *reinterpret_cast<BatchShared*>(batch_smem);
   int* list = reinterpret_cast<int*>(batch_smem + ((sizeof(BatchShared) + 15) & ~size_t(15)));   // BATCH_CAP ints
   const BlockScope scope;
@@ -278,14 +281,22 @@ __global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__
       a.sidx = B.w_sidx + (blk * 2 + d) * BATCH_CAP;
       double* pm = B.w_pm + (blk * 2 + d) * 4 * BATCH_CAP; a.w = pm; a.r2 = pm + BATCH_CAP; a.gkey = pm + 2 * BATCH_CAP; a.skey = pm + 3 * BATCH_CAP;
       a.stamp = (d == 0 ? B.w_stamp0 + blk * (size_t)B.all[1].n : B.w_stamp1 + blk * (size_t)B.all[0].n);
-      int* hq = B.w_hq + (blk * 2 + d) * (3 * BATCH_CAP + 4);
+      int* hq = B.w_hq + (blk * 2 + d) * 2 * (3 * BATCH_CAP + 4);
       a.hq_k = hq; a.hq_s = hq + BATCH_CAP; a.hq_o = hq + 2 * BATCH_CAP; a.hq_count = hq + 3 * BATCH_CAP;
-      a.hq_best = B.w_hqb + (blk * 2 + d) * BATCH_CAP;
+      a.hq_best = B.w_hqb + (blk * 2 + d) * 2 * BATCH_CAP;
+      a.ball_rows = B.ball_rows;
       a.prev_s = B.w_prev + (blk * 2 + d) * BATCH_CAP;
       a.sc = B.w_sc + blk * 2 + d;
       a.stamp_in_match = 1;   // (no certificates in batched mode: every finished match stamps its to-feature)
       *a.hq_count = 0;
       S.d[d] = a;
+      {   // second queue
+        int* hq2 = hq + (3 * BATCH_CAP + 4);
+        a.hq_k = hq2; a.hq_s = hq2 + BATCH_CAP; a.hq_o = hq2 + 2 * BATCH_CAP; a.hq_count = hq2 + 3 * BATCH_CAP;
+        a.hq_best = B.w_hqb + (blk * 2 + d) * 2 * BATCH_CAP + BATCH_CAP;
+        *a.hq_count = 0;
+        S.d2[d] = a;
+      }
       S.calls[d] = 0; S.number_points[d] = a.M; S.scale_estimated[d] = 0;
     }
     __syncthreads();
@@ -319,13 +330,19 @@ __global__ void __launch_bounds__(BATCH_THREADS) k_batch(const __grid_constant__
         if (bits & 1) ++bits;
         S.d[d].perm_half = bits / 2;
         S.d[d].M = min(S.number_points[d], S.d[d].n_in);
+        for (int r = 0; r < 4; ++r) S.d2[d].perm_key[r] = S.d[d].perm_key[r];
+        S.d2[d].perm_half = S.d[d].perm_half; S.d2[d].M = S.d[d].M;
         // epoch: job and iteration make it unique over the life of the workspace (stamps are never cleared)
         const unsigned long long epoch = ((unsigned long long)(j + 1) << 8) | (unsigned long long)(S.it + 1);
-        S.d[d].tag = (~epoch) << 32;
+        S.d[d].tag = (~epoch) << 32; S.d2[d].tag = S.d[d].tag;
       }
       __syncthreads();
       TPH(1);
-      for (int d = 0; d < 2; ++d) { lrr_phase_match(scope, S.d[d], flags, S.ph); TPH(2); lrr_phase_match_hard(scope, S.d[d], flags, S.ph); TPH(3); }
+      for (int d = 0; d < 2; ++d) {
+        lrr_phase_match(scope, S.d[d], flags, S.ph); TPH(2);
+        if (B.g8) lrr_phase_match_queue_g8(scope, S.d[d], S.d2[d], flags, S.ph, S.rows);
+        lrr_phase_match_hard(scope, B.g8 ? S.d2[d] : S.d[d], flags, S.ph); TPH(3);
+      }
       // estimate_LS: scales (MUSE on the first call), normalisation, weights, order statistics, normal equations, solve
       int mode[2] = {0, 0};
       for (int d = 0; d < 2; ++d) if (!S.scale_estimated[d]) {
@@ -419,6 +436,7 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
   BatchArgs B; memset(&B, 0, sizeof(B));
   B.all[0] = moving_all; B.all[1] = fixed_all; B.jobs = jobs_dev; B.out = out_dev; B.njobs = njobs; B.max_iter = max_iter; B.shuffle_seed = shuffle_seed;
   B.job_ids = job_ids_dev;
+  { const char* e = getenv("LRR_BATCH_G8"); B.g8 = e ? atoi(e) : 1; const char* r = getenv("LRR_BATCH_BALL_ROWS"); B.ball_rows = r ? atoi(r) : (B.g8 ? 16 : 0); }
   for (int i = 0; i < 4 * 32; ++i) B.muse_table[i] = muse_table[i];
   B.muse_rows = muse_rows;
   // carve the workspace
@@ -430,11 +448,11 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
   B.w_f = (double*)take(nb * 2 * 4 * BATCH_CAP * sizeof(double));
   B.w_fP6 = (double*)take(nb * 2 * 6 * BATCH_CAP * sizeof(double));
   B.w_pm = (double*)take(nb * 2 * 4 * BATCH_CAP * sizeof(double));
-  B.w_hqb = (double*)take(nb * 2 * BATCH_CAP * sizeof(double));
+  B.w_hqb = (double*)take(nb * 2 * 2 * BATCH_CAP * sizeof(double));
   B.w_forig = (int*)take(nb * 2 * BATCH_CAP * sizeof(int));
   B.w_sidx = (int*)take(nb * 2 * BATCH_CAP * sizeof(int));
   B.w_prev = (int*)take(nb * 2 * BATCH_CAP * sizeof(int));
-  B.w_hq = (int*)take(nb * 2 * (3 * BATCH_CAP + 4) * sizeof(int));
+  B.w_hq = (int*)take(nb * 2 * 2 * (3 * BATCH_CAP + 4) * sizeof(int));
   B.w_stamp0 = (unsigned long long*)take(nb * (size_t)fixed_all.n * 8);
   B.w_stamp1 = (unsigned long long*)take(nb * (size_t)moving_all.n * 8);
   if ((size_t)(p - (char*)workspace) > workspace_bytes) return cudaErrorMemoryAllocation;
@@ -458,8 +476,8 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
 size_t lrr_batch_workspace_bytes(int nblocks, int n_moving, int n_fixed) {
   const size_t nb = (size_t)nblocks;
   auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-  size_t t = up(256) + up(nb * 2 * sizeof(Scal)) + 2 * up(nb * 2 * 4 * BATCH_CAP * 8) + up(nb * 2 * 6 * BATCH_CAP * 8) + up(nb * 2 * BATCH_CAP * 8) +
-             3 * up(nb * 2 * BATCH_CAP * 4) + up(nb * 2 * (3 * BATCH_CAP + 4) * 4) + up(nb * (size_t)n_fixed * 8) + up(nb * (size_t)n_moving * 8);
+  size_t t = up(256) + up(nb * 2 * sizeof(Scal)) + 2 * up(nb * 2 * 4 * BATCH_CAP * 8) + up(nb * 2 * 6 * BATCH_CAP * 8) + up(nb * 2 * 2 * BATCH_CAP * 8) +
+             3 * up(nb * 2 * BATCH_CAP * 4) + up(nb * 2 * 2 * (3 * BATCH_CAP + 4) * 4) + up(nb * (size_t)n_fixed * 8) + up(nb * (size_t)n_moving * 8);
   return t + 4096;
 }
 int lrr_batch_blocks_per_sm() {

@@ -174,9 +174,10 @@ static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, cons
   fs->cell_start = fb.cell_start;
   FsetDev& d = fs->dev;
   d.n = (int)n; d.x = fs->xyz; d.y = fs->xyz + n; d.z = fs->xyz + 2 * n; d.s = fs->s; d.P6 = fs->P6; d.C6 = fs->C6; d.dirs = fs->dirs;
-  d.shape = fs->shape; d.grid = fb.grid; d.rec = fs->rec; d.sorted_of_orig = fs->sorted_of_orig;
+  if (fs->C6) FCK(dmalloc(&fs->crec, (size_t)8 * n));
+  d.shape = fs->shape; d.grid = fb.grid; d.rec = fs->rec; d.crec = fs->crec; d.sorted_of_orig = fs->sorted_of_orig;
   FCK(cudaStreamWaitEvent(st, ctx->copy_ev, 0));
-  lrr_k_fill_records(d, fs->rec, st, &ctx->launches);
+  lrr_k_fill_records(d, fs->rec, fs->crec, st, &ctx->launches);
   FCK(cudaStreamSynchronize(st));
   FCK(cudaGetLastError());
   dfree(cov2_d);
@@ -203,7 +204,7 @@ extern "C" void lrr_features_destroy(lrr_fset* fs) {
   if (!fs) return;
   enter(fs->ctx);
   dfree(fs->xyz); dfree(fs->s); dfree(fs->P6); dfree(fs->C6); dfree(fs->dirs); dfree(fs->shape);
-  dfree(fs->pos4); dfree(fs->rec); dfree(fs->sorted_of_orig); dfree(fs->cell_start);
+  dfree(fs->pos4); dfree(fs->rec); dfree(fs->crec); dfree(fs->sorted_of_orig); dfree(fs->cell_start);
   delete fs;
 }
 extern "C" int64_t lrr_features_size(const lrr_fset* fs) { return fs ? fs->n : 0; }

@@ -466,6 +466,88 @@ __device__ __forceinline__ int lrr_nn_ball_flat(const GridDev& g, double qx, dou
   return gs;
 }
 
+// The flattened ball scan at a quarter of a warp: a group of EIGHT lanes (gmask = its lanes, gl = lane in the group) takes one query
+// with a candidate (best, best_s, best_o on entry, identical in the group): run bounds of up to LRR_G8_ROWS rows in one round trip
+// (four per lane), a prefix sum over the group into the group's row table (`rowlo`, `rowbase`: LRR_G8_ROWS ints each, shared
+// memory), the points in a second round trip, group minimum.  Four queries per warp at a time.  Returns false — nothing changed —
+// when the ball touches more rows or points than that (far outliers: the caller gives the query a whole warp); true with the
+// exact neighbour (ties: lowest original index) and the certificate bound (0: none) otherwise.
+#define LRR_G8_ROWS 32
+#define LRR_G8_PTS 256
+__device__ __forceinline__ bool lrr_nn_ball_g8(const GridDev& g, double qx, double qy, double qz, double margin, int* rowlo, int* rowbase, unsigned int gmask,
+                                               int gl, double& best, int& best_s, int& best_o, double& bound) {
+  bound = 0.0;
+  const double slack = 1e-9 * g.h;
+  const double Rm = sqrt(best) * (1.0 + 1e-9) + slack + margin, Rm2 = Rm * Rm;
+  const int z0 = lrr_cell_clamp(qz - Rm, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + Rm, g.oz, g.inv_h, g.nz);
+  const int y0 = lrr_cell_clamp(qy - Rm, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + Rm, g.oy, g.inv_h, g.ny);
+  const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+  if (nrows > LRR_G8_ROWS) return false;
+  int lo4[4], sz4[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int rl = 8 * u + gl;
+    lo4[u] = 0; sz4[u] = 0;
+    if (rl < nrows) {
+      const int zz = z0 + rl / ny, yy = y0 + rl % ny;
+      const double dz = lrr_slab_dist(qz, g.oz, g.h, zz, slack), dy = lrr_slab_dist(qy, g.oy, g.h, yy, slack);
+      const double dyz2 = dz * dz + dy * dy;
+      if (dyz2 <= Rm2) {
+        const double rx = sqrt(Rm2 - dyz2) * (1.0 + 1e-9) + slack;
+        const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
+        const int row = (zz * g.ny + yy) * g.nx;
+        lo4[u] = __ldg(g.cell_start + row + xa); sz4[u] = __ldg(g.cell_start + row + xb + 1);
+      }
+    }
+  }
+  int total = 0;
+  __syncwarp(gmask);   // the group's previous query is done with the table
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (8 * u < nrows) {   // uniform in the group
+      const int rl = 8 * u + gl, sz = (rl < nrows) ? sz4[u] - lo4[u] : 0;
+      int inc = sz;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) { const int v = __shfl_up_sync(gmask, inc, o, 8); if (gl >= o) inc += v; }
+      if (rl < nrows) { rowlo[rl] = lo4[u]; rowbase[rl] = total + inc - sz; }
+      total += __shfl_sync(gmask, inc, 7, 8);
+    }
+  }
+  __syncwarp(gmask);
+  if (total > LRR_G8_PTS) return false;
+  double second = 1e300;
+  for (int p0 = 0; p0 < total; p0 += 32) {
+    double4 P[4]; int J[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + 8 * u + gl;
+      J[u] = -1;
+      if (p < total) {
+        int ra = 0, rb = nrows;   // last row with rowbase <= p
+        while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (rowbase[mid] <= p) ra = mid; else rb = mid; }
+        J[u] = rowlo[ra] + (p - rowbase[ra]);
+        P[u] = lrr_ld_pos4(g.pos4 + J[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (J[u] >= 0) lrr_nn_upd2(P[u], J[u], qx, qy, qz, best, best_s, best_o, second);
+  }
+  double gb = best; int gs = best_s, go = best_o;
+#pragma unroll
+  for (int o = 4; o; o >>= 1) {
+    const double ob = __shfl_xor_sync(gmask, gb, o, 8);
+    const int os = __shfl_xor_sync(gmask, gs, o, 8), oo = __shfl_xor_sync(gmask, go, o, 8);
+    if (ob < gb || (ob == gb && oo < go)) { gb = ob; gs = os; go = oo; }
+  }
+  double sec = (best_s == gs) ? second : best;
+#pragma unroll
+  for (int o = 4; o; o >>= 1) sec = fmin(sec, __shfl_xor_sync(gmask, sec, o, 8));
+  const double bd = fmin(sqrt(sec), sqrt(gb) + margin) * (1.0 - 1e-9) - slack;
+  bound = (sec > gb && bd > 0.0) ? bd : 0.0;
+  best = gb; best_s = gs; best_o = go;
+  return true;
+}
+
 // ---- reduction scopes ------------------------------------------------------------------------------
 // A phase body is written once against a Scope: `first()/stride()` drive the element loop, `reduce<K>`
 // sums K doubles per thread over the scope.  It returns true in every thread of the FINALIZER block with

@@ -39,7 +39,7 @@ struct lrr_fset {
   int dim = 3;   // 2: plain planar cdcl_feature<2> set (lrr_features_upload_cov), stored with z = 0
   double *xyz = nullptr, *s = nullptr, *P6 = nullptr, *C6 = nullptr, *dirs = nullptr;
   uint8_t* shape = nullptr;
-  double4* pos4 = nullptr; double* rec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
+  double4* pos4 = nullptr; double* rec = nullptr; double* crec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
   FsetDev dev;
   std::vector<double> host_xyz;   // 3 x n copy for host-side ROI selection (FeaturesInROIs); fetched from the device on first use
 };

@@ -69,7 +69,7 @@ __device__ __forceinline__ bool lrr_spec_bad(const EstArgs& a) {
 }
 
 // ---- upload-time helpers ---------------------------------------------------------------------------------
-__global__ void k_fill_records(FsetDev f, double* __restrict__ rec) {
+__global__ void k_fill_records(FsetDev f, double* __restrict__ rec, double* __restrict__ crec) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= f.n) return;
   const int o = lrr_pos4_orig(f.grid.pos4[j]);
@@ -78,10 +78,16 @@ __global__ void k_fill_records(FsetDev f, double* __restrict__ rec) {
   for (int p = 0; p < 6; ++p) r[p] = f.P6[(size_t)p * f.n + o];
   const double s = f.s[o];
   r[6] = s; r[7] = (double)(float)s;
+  if (crec && f.C6) {
+    double* c = crec + 8 * (size_t)j;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) c[p] = f.C6[(size_t)p * f.n + o];
+    c[6] = 0.0; c[7] = 0.0;
+  }
 }
-void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long long* launches) {
+void lrr_k_fill_records(const FsetDev& f, double* rec, double* crec, cudaStream_t st, long long* launches) {
   if (f.n == 0) return;
-  k_fill_records<<<(f.n + 255) / 256, 256, 0, st>>>(f, rec); ++*launches;
+  k_fill_records<<<(f.n + 255) / 256, 256, 0, st>>>(f, rec, crec); ++*launches;
 }
 
 // Error projector of a planar cdcl_feature: outer product of the eigenvector of the smallest eigenvalue of its 2x2 covariance = the

@@ -45,6 +45,7 @@ struct FsetDev {
   const uint8_t* shape;          // n
   GridDev grid;
   const double* rec;             // 8 x n interleaved, cell order
+  const double* crec;            // 8 x n interleaved, cell order: Cxx Cxy Cxz Cyy Cyz Czz 0 0 (null without covariances): one 64-byte gather per match for cdcl_obj_fun_cov
   const int* sorted_of_orig;     // n
 };
 
@@ -226,7 +227,7 @@ int lrr_current_device();   // clamped to [0, LRR_MAX_DEVICES)
 
 // ---- ICP kernels (lrr_icp.cu) ----------------------------------------------------------------------
 void lrr_k_build_proc(const FsetDev& from_all, const int* forig, int n_in, int* mark /* from_all.n ints scratch */, int* proc, cudaStream_t st, long long* launches);
-void lrr_k_fill_records(const FsetDev& f, double* rec, cudaStream_t st, long long* launches);
+void lrr_k_fill_records(const FsetDev& f, double* rec, double* crec, cudaStream_t st, long long* launches);
 // planar cdcl_feature<2> sets: P6 / C6 (3-D layout, z parts zero) from the 2x2 covariances (xx, xy, yy) x n
 void lrr_k_projector2_from_cov(const double* cov3, int n, double* P6, double* C6, cudaStream_t st, long long* launches);
 void lrr_k_gather_from(const FsetDev& src, const int* idx, int n_in, double* fx, double* fy, double* fz, double* fs, double* fP6,

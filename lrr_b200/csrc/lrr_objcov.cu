@@ -2,10 +2,13 @@
 //   Cij = Jp Cp Jp^T + Jt Sigma Jt^T + Cq ;  r = e^T Cij^-1 e ;  f += w (rho(r) + ln det Cij)
 //   kl += w ( Jt^T Cij^-1 Jt - rho'(r) t t^T ),  t = Jt^T Cij^-1 e
 // The affine Jacobian is J = x~^T (x) I3 (x~ = (x - c, 1)), so with v = Cij^-1 e and the symmetric 3x3
-// S = Cij^-1 - rho'(r) v v^T the gradient kernel is the Kronecker moment  kl[(d,a),(e,b)] = sum w x~_a x~_b S_de
-// — the same 4-lanes-per-match accumulation as the normal equations (24 + 1 accumulators per lane) instead of
-// the reference's dense 12x3 . 3x3 . 3x12 products per match; J Sigma J^T is 144 MACs split over the 4 lanes.
-// This keeps the evaluation HBM-bound: ~156 B and ~0.6 kflop per match.
+// S = Cij^-1 - rho'(r) v v^T the gradient kernel is the Kronecker moment  kl[(d,a),(e,b)] = sum w x~_a x~_b S_de,
+// and J Sigma J^T = sum_{a<=b} x~_a x~_b B_ab with the ten symmetric 3x3 blocks B_aa = Sigma_aa, B_ab = Sigma_ab + Sigma_ab^T
+// (60 multiply-adds per match from 60 broadcast shared-memory values) instead of the reference's dense 3x12 . 12x12 . 12x3.
+// ~0.3 kflop and 156 B per match: HBM-bound — provided the loads are: every LANE takes one match per trip
+// (coalesced streams for the from-side: location, covariance, weight, neighbour slot; two gathers of one sector pair each for the
+// neighbour: pos4 and the cell-ordered covariance record FsetDev::crec), the four lanes of a quad then pass (w, x~, S) round by
+// shuffle and each adds row x~_j of all four matches: 24 + 1 accumulators per lane.
 #include "lrr_phases.cuh"
 
 struct ObjArgs {
@@ -16,88 +19,117 @@ struct ObjArgs {
 
 __device__ __forceinline__ int obj_idx(int d, int a) { return a < 3 ? 3 * d + a : 9 + d; }
 
-__global__ void __launch_bounds__(LRR_THREADS) k_objcov(DirArgs a, ObjArgs o, double* partials, unsigned int* ticket) {
+#define LRR_OBJ_THREADS 256
+__global__ void __launch_bounds__(LRR_OBJ_THREADS, 2) k_objcov(const __grid_constant__ DirArgs a, const __grid_constant__ ObjArgs o, double* partials, unsigned int* ticket) {
   __shared__ PhaseShared sh;
-  __shared__ double Sg[144];
+  __shared__ double Bs[10][6];     // blocks B_ab (a <= b), symmetric 6: xx,xy,xz,yy,yz,zz
   GridScope scope; scope.partials = partials; scope.ticket = ticket;
-  for (int i = threadIdx.x; i < 144; i += blockDim.x) Sg[i] = o.Sigma[i];
+  if (threadIdx.x < 60) {
+    const int pair = threadIdx.x / 6, p = threadIdx.x % 6;
+    // pair -> (a, b), a <= b, in the order (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3)
+    int aa = 0, bb = 0, cnt = 0;
+    for (int i = 0; i < 4; ++i) for (int j2 = i; j2 < 4; ++j2) { if (cnt == pair) { aa = i; bb = j2; } ++cnt; }
+    const int d = p < 3 ? 0 : (p < 5 ? 1 : 2), e = p < 3 ? p : (p < 5 ? p - 2 : 2);
+    const double s1 = o.Sigma[obj_idx(d, aa) * 12 + obj_idx(e, bb)];
+    const double s2 = o.Sigma[obj_idx(e, aa) * 12 + obj_idx(d, bb)];   // (Sigma_ab^T)_de = (Sigma_ab)_ed
+    Bs[pair][p] = aa == bb ? s1 : s1 + s2;
+  }
   __syncthreads();
   Scal* sc = a.sc;
   const int mapped = sc->from_mapped;
-  const int j = threadIdx.x & 3;
+  const int lane = threadIdx.x & 31, j = lane & 3, qbase = lane & ~3;
   const FsetDev& F = a.from_all; const FsetDev& T = a.to;
-  const double irm2 = 1.0 / (o.rm * o.rm), irf2 = 1.0 / (o.rf * o.rf);
+  const double irm = 1.0 / o.rm, irf = 1.0 / o.rf, irm2 = irm * irm, irf2 = irf * irf;
   double acc[25];
 #pragma unroll
   for (int i = 0; i < 25; ++i) acc[i] = 0.0;
-  for (int k = scope.first() >> 2; k < a.M; k += scope.stride() >> 2) {
-    const int s = a.sidx[k];
-    if (s < 0) continue;
-    const int i = lrr_from_index(a, k);
-    const int po = a.forig ? a.forig[i] : i;
-    double px, py, pz; lrr_from_loc(a, sc, mapped, i, px, py, pz);
-    px = (px - o.cm[0]) / o.rm; py = (py - o.cm[1]) / o.rm; pz = (pz - o.cm[2]) / o.rm;
-    const double4 q4 = lrr_ld_pos4(T.grid.pos4 + s);
-    const int qo = lrr_pos4_orig(q4);
-    const double qx = (q4.x - o.cf[0]) / o.rf, qy = (q4.y - o.cf[1]) / o.rf, qz = (q4.z - o.cf[2]) / o.rf;
-    // covariances (symmetric 6: xx,xy,xz,yy,yz,zz)
-    double Cp[6], Cq[6];
-#pragma unroll
-    for (int p = 0; p < 6; ++p) { Cp[p] = F.C6[(size_t)p * F.n + po] * irm2; Cq[p] = T.C6[(size_t)p * T.n + qo] * irf2; }
-    const double xt[4] = {px - o.c[0], py - o.c[1], pz - o.c[2], 1.0};
-    // JCpJ = A Cp A^T
-    double M1[9];
-    {
-      const double C[9] = {Cp[0], Cp[1], Cp[2], Cp[1], Cp[3], Cp[4], Cp[2], Cp[4], Cp[5]};
-      double AC[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) AC[r * 3 + cc] = o.A[r * 3] * C[cc] + o.A[r * 3 + 1] * C[3 + cc] + o.A[r * 3 + 2] * C[6 + cc];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) M1[r * 3 + cc] = AC[r * 3] * o.A[cc * 3] + AC[r * 3 + 1] * o.A[cc * 3 + 1] + AC[r * 3 + 2] * o.A[cc * 3 + 2];
-    }
-    // J Sigma J^T: lane j sums the terms with a = j, then the 4 lanes add up
-    double JS[9];
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        double v = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) v += xt[b] * Sg[obj_idx(d, j) * 12 + obj_idx(e, b)];
-        JS[d * 3 + e] = xt[j] * v;
+  const int wfirst = scope.first() - lane, wstride = scope.stride();
+  for (int base = wfirst; base < a.M; base += wstride) {
+    const int k = base + lane;
+    double w = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, S[6] = {0, 0, 0, 0, 0, 0}, fterm = 0.0;
+    const int s = k < a.M ? a.sidx[k] : -1;
+    if (s >= 0) {
+      const int i = lrr_from_index(a, k);
+      const int po = a.forig ? a.forig[i] : i;
+      double px, py, pz; lrr_from_loc(a, sc, mapped, i, px, py, pz);
+      const double4 q4 = lrr_ld_pos4(T.grid.pos4 + s);
+      double Cq[6];
+      {
+        const double2* cr = reinterpret_cast<const double2*>(T.crec + 8 * (size_t)s);
+        const double2 c0 = __ldg(cr), c1 = __ldg(cr + 1), c2 = __ldg(cr + 2);
+        Cq[0] = c0.x * irf2; Cq[1] = c0.y * irf2; Cq[2] = c1.x * irf2; Cq[3] = c1.y * irf2; Cq[4] = c2.x * irf2; Cq[5] = c2.y * irf2;
       }
+      double Cp[6];
 #pragma unroll
-    for (int m = 0; m < 9; ++m) { JS[m] += __shfl_xor_sync(0xffffffffu, JS[m], 1); JS[m] += __shfl_xor_sync(0xffffffffu, JS[m], 2); }
-    double Cij[9];
-    {
-      const double Q[9] = {Cq[0], Cq[1], Cq[2], Cq[1], Cq[3], Cq[4], Cq[2], Cq[4], Cq[5]};
+      for (int p = 0; p < 6; ++p) Cp[p] = __ldg(F.C6 + (size_t)p * F.n + po) * irm2;
+      w = a.w[k];
+      px = (px - o.cm[0]) * irm; py = (py - o.cm[1]) * irm; pz = (pz - o.cm[2]) * irm;
+      const double qx = (q4.x - o.cf[0]) * irf, qy = (q4.y - o.cf[1]) * irf, qz = (q4.z - o.cf[2]) * irf;
+      x0 = px - o.c[0]; x1 = py - o.c[1]; x2 = pz - o.c[2];
+      // Cij (symmetric 6) = A Cp A^T + J Sigma J^T + Cq
+      double Cij[6];
+      {
+        // rows of A Cp
+        double AC[9];
 #pragma unroll
-      for (int m = 0; m < 9; ++m) Cij[m] = M1[m] + JS[m] + Q[m];
+        for (int r = 0; r < 3; ++r) {
+          const double a0 = o.A[3 * r], a1 = o.A[3 * r + 1], a2 = o.A[3 * r + 2];
+          AC[3 * r] = a0 * Cp[0] + a1 * Cp[1] + a2 * Cp[2];
+          AC[3 * r + 1] = a0 * Cp[1] + a1 * Cp[3] + a2 * Cp[4];
+          AC[3 * r + 2] = a0 * Cp[2] + a1 * Cp[4] + a2 * Cp[5];
+        }
+        Cij[0] = AC[0] * o.A[0] + AC[1] * o.A[1] + AC[2] * o.A[2] + Cq[0];
+        Cij[1] = AC[0] * o.A[3] + AC[1] * o.A[4] + AC[2] * o.A[5] + Cq[1];
+        Cij[2] = AC[0] * o.A[6] + AC[1] * o.A[7] + AC[2] * o.A[8] + Cq[2];
+        Cij[3] = AC[3] * o.A[3] + AC[4] * o.A[4] + AC[5] * o.A[5] + Cq[3];
+        Cij[4] = AC[3] * o.A[6] + AC[4] * o.A[7] + AC[5] * o.A[8] + Cq[4];
+        Cij[5] = AC[6] * o.A[6] + AC[7] * o.A[7] + AC[8] * o.A[8] + Cq[5];
+        const double xt[4] = {x0, x1, x2, 1.0};
+        int pair = 0;
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+          for (int bb = aa; bb < 4; ++bb) {
+            const double xx = xt[aa] * xt[bb];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) Cij[p] += xx * Bs[pair][p];
+            ++pair;
+          }
+      }
+      // inverse and determinant of the symmetric 3x3
+      const double c00 = Cij[3] * Cij[5] - Cij[4] * Cij[4], c01 = Cij[2] * Cij[4] - Cij[1] * Cij[5], c02 = Cij[1] * Cij[4] - Cij[2] * Cij[3];
+      const double det = Cij[0] * c00 + Cij[1] * c01 + Cij[2] * c02;
+      const double id = 1.0 / det;
+      const double Ci[6] = {c00 * id, c01 * id, c02 * id, (Cij[0] * Cij[5] - Cij[2] * Cij[2]) * id, (Cij[1] * Cij[2] - Cij[0] * Cij[4]) * id,
+                            (Cij[0] * Cij[3] - Cij[1] * Cij[1]) * id};
+      // err = q - T(p)   (cdcl_obj_fun_cov.txx:84-86)
+      const double yx = o.A[0] * x0 + o.A[1] * x1 + o.A[2] * x2 + o.t[0];
+      const double yy = o.A[3] * x0 + o.A[4] * x1 + o.A[5] * x2 + o.t[1];
+      const double yz = o.A[6] * x0 + o.A[7] * x1 + o.A[8] * x2 + o.t[2];
+      const double e0 = qx - yx, e1 = qy - yy, e2 = qz - yz;
+      const double v0 = Ci[0] * e0 + Ci[1] * e1 + Ci[2] * e2, v1 = Ci[1] * e0 + Ci[3] * e1 + Ci[4] * e2, v2 = Ci[2] * e0 + Ci[4] * e1 + Ci[5] * e2;
+      const double r = e0 * v0 + e1 * v1 + e2 * v2;
+      fterm = w * (lrr_rho(r) + log(det));
+      const double rp = lrr_rho_p(r);
+      S[0] = Ci[0] - rp * v0 * v0; S[1] = Ci[1] - rp * v0 * v1; S[2] = Ci[2] - rp * v0 * v2;
+      S[3] = Ci[3] - rp * v1 * v1; S[4] = Ci[4] - rp * v1 * v2; S[5] = Ci[5] - rp * v2 * v2;
     }
-    double Ci[9]; lrr_inv3(Cij, Ci);
-    const double det = lrr_det3(Cij);
-    // err = q - T(p)   (cdcl_obj_fun_cov.txx:84-86)
-    const double yx = o.A[0] * xt[0] + o.A[1] * xt[1] + o.A[2] * xt[2] + o.t[0];
-    const double yy = o.A[3] * xt[0] + o.A[4] * xt[1] + o.A[5] * xt[2] + o.t[1];
-    const double yz = o.A[6] * xt[0] + o.A[7] * xt[1] + o.A[8] * xt[2] + o.t[2];
-    const double e0 = qx - yx, e1 = qy - yy, e2 = qz - yz;
-    const double v0 = Ci[0] * e0 + Ci[1] * e1 + Ci[2] * e2, v1 = Ci[3] * e0 + Ci[4] * e1 + Ci[5] * e2, v2 = Ci[6] * e0 + Ci[7] * e1 + Ci[8] * e2;
-    const double r = e0 * v0 + e1 * v1 + e2 * v2;
-    const double w = a.w[k];
-    if (j == 0) acc[24] += w * (lrr_rho(r) + log(det));
-    const double rp = lrr_rho_p(r);
-    // S = Ci - rho' v v^T, symmetric part taken from the upper triangle (Ci is symmetric up to rounding)
-    const double S[6] = {Ci[0] - rp * v0 * v0, Ci[1] - rp * v0 * v1, Ci[2] - rp * v0 * v2, Ci[4] - rp * v1 * v1, Ci[5] - rp * v1 * v2, Ci[8] - rp * v2 * v2};
-    const double wxa = w * xt[j];
+    acc[24] += fterm;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const double tt = wxa * xt[b];
+    for (int m = 0; m < 4; ++m) {
+      const int src = qbase + m;
+      const double wm = __shfl_sync(0xffffffffu, w, src);
+      const double xm[4] = {__shfl_sync(0xffffffffu, x0, src), __shfl_sync(0xffffffffu, x1, src), __shfl_sync(0xffffffffu, x2, src), 1.0};
+      double Sm[6];
 #pragma unroll
-      for (int p = 0; p < 6; ++p) acc[b * 6 + p] += tt * S[p];
+      for (int p = 0; p < 6; ++p) Sm[p] = __shfl_sync(0xffffffffu, S[p], src);
+      const double wxa = wm * (j == 0 ? xm[0] : (j == 1 ? xm[1] : (j == 2 ? xm[2] : 1.0)));
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double tt = wxa * xm[b];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) acc[b * 6 + p] += tt * Sm[p];
+      }
     }
   }
   if (scope.reduce<25, 4>(acc, sh.out, sh.tmp)) {
@@ -111,8 +143,9 @@ void lrr_k_objcov_launch(const DirArgs& a, const double* A, const double* t, con
   for (int i = 0; i < 9; ++i) o.A[i] = A[i];
   for (int i = 0; i < 3; ++i) { o.t[i] = t[i]; o.c[i] = c[i]; o.cm[i] = norm8[i]; o.cf[i] = norm8[4 + i]; }
   o.rm = norm8[3]; o.rf = norm8[7]; o.Sigma = Sigma_dev;
-  long long b = (4LL * a.M + LRR_THREADS - 1) / LRR_THREADS, cap = (long long)lrr_num_sms() * 4;
+  // one match per lane and trip; at most two resident blocks per SM (LRR_MAX_BLOCKS rows of partial sums)
+  long long b = ((long long)a.M + LRR_OBJ_THREADS - 1) / LRR_OBJ_THREADS, cap = (long long)lrr_num_sms() * 2;
   if (cap > LRR_MAX_BLOCKS) cap = LRR_MAX_BLOCKS;
   if (b > cap) b = cap; if (b < 1) b = 1;
-  k_objcov<<<(int)b, LRR_THREADS, 0, st>>>(a, o, partials, ticket); ++*launches;
+  k_objcov<<<(int)b, LRR_OBJ_THREADS, 0, st>>>(a, o, partials, ticket); ++*launches;
 }

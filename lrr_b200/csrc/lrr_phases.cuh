@@ -255,6 +255,46 @@ __device__ void lrr_phase_match_hard(const Scope& scope, const DirArgs& a, int f
   scope.phase_end();
 }
 
+// Batched mode: the queue pass A leaves (queries whose ball touches more than DirArgs::ball_rows rows) is drained by GROUPS OF
+// EIGHT LANES (lrr_nn_ball_g8, lrr_dev.cuh): 64 queries of a 512-thread block in flight, two round trips each, instead of 16 warps
+// walking their rows lane by lane.  What a group cannot take (no candidate yet, a ball of more than 32 rows) moves on to the second
+// queue `a2` (same DirArgs with the hq_* members pointing at it) for the one-warp-per-query pass.  rows: 64 ints per group.
+template <class Scope, class SH>
+__device__ void lrr_phase_match_queue_g8(const Scope& scope, const DirArgs& a, const DirArgs& a2, int flags, SH& sh, int* rows) {
+  __shared__ double s_T[15];
+  lrr_stage_transform(a.sc, s_T);
+  const double* A = s_T; const double* t = s_T + 9; const double* c = s_T + 12;
+  const bool rigid = (flags & LRR_F_RIGID) != 0;
+  const GridDev& g = a.to.grid;
+  const int lane = threadIdx.x & 31, gl = lane & 7, gi = lane >> 3;
+  const unsigned int gmask = 0xffu << (8 * gi);
+  int* rowlo = rows + ((threadIdx.x >> 5) * 4 + gi) * 2 * LRR_G8_ROWS; int* rowbase = rowlo + LRR_G8_ROWS;
+  const int nq = *a.hq_count;
+  double acc[4] = {0, 0, 0, 0};
+  for (int qi = scope.first() >> 3; qi < nq; qi += scope.stride() >> 3) {
+    const int kq = a.hq_k[qi];
+    const int i = lrr_from_index(a, kq);
+    const double x = __ldg(a.fx + i), y = __ldg(a.fy + i), z = __ldg(a.fz + i);
+    double qx, qy, qz;
+    lrr_map_exact(A, t, c, x, y, z, qx, qy, qz);
+    const int cand = a.hq_s[qi]; const double cbest = a.hq_best[qi]; const int co = a.hq_o[qi];
+    double best = cbest, bound; int best_s = cand, best_o = co;
+    const bool ok = cand >= 0 && lrr_nn_ball_g8(g, qx, qy, qz, 0.0, rowlo, rowbase, gmask, gl, best, best_s, best_o, bound);
+    if (gl == 0) {
+      if (ok) lrr_match_finish(a, rigid, kq, i, x, y, z, qx, qy, qz, best_s, acc, 0, 0.0);
+      else { const int slot = atomicAdd(a2.hq_count, 1); a2.hq_k[slot] = kq; a2.hq_best[slot] = cbest; a2.hq_s[slot] = cand; a2.hq_o[slot] = co; }
+    }
+  }
+  if (scope.template reduce<4>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) {
+      Scal* sc = a.sc;
+      sc->sum_loc[0] += sh.out[0]; sc->sum_loc[1] += sh.out[1]; sc->sum_loc[2] += sh.out[2]; sc->sum_r2 += sh.out[3];
+      *a.hq_count = 0;
+    }
+  }
+  scope.phase_end();
+}
+
 // ---- NORM1 / NORM2: cdcl_normalize_matches (cdcl :1159-1240, rrl :864-943).  The std::set of matched
 // fixed features becomes "the match with the lowest position wins the stamp of its to-feature". ----------
 template <class Scope, class SH>

@@ -353,8 +353,6 @@ __device__ __forceinline__ void lrr_match_tile_body(const DirArgs& a, int flags,
 // sum over the group, the points in a second round trip, group minimum — the flattened ball scan of lrr_dev.cuh at a quarter of a
 // warp, four queries per warp at a time, every query of the list in (almost) one round.  Balls of more than LRR_G8_ROWS rows or
 // LRR_G8_PTS points (far outliers) are queued for the one-warp-per-query pass.  Exact, with a new certificate.
-#define LRR_G8_ROWS 32
-#define LRR_G8_PTS 256
 __device__ __forceinline__ void lrr_match_sparse_body(const DirArgs& a, int flags, const double* s_T, TileWarp& W, double (&acc)[4]) {
   const int nfq = *reinterpret_cast<volatile int*>(a.fq_count);
   if (nfq <= 0) return;
@@ -365,7 +363,6 @@ __device__ __forceinline__ void lrr_match_sparse_body(const DirArgs& a, int flag
   const unsigned int gmask = 0xffu << (8 * gi);
   int* rowlo = W.rowlo + LRR_G8_ROWS * gi; int* rowbase = W.rowbase + LRR_G8_ROWS * gi;
   const int ngroups = gridDim.x * LRR_TILE_WARPS * 4;
-  const double slack = 1e-9 * g.h, margin = 0.125 * g.h;
   __syncwarp();
   for (int qi = (blockIdx.x * LRR_TILE_WARPS + (threadIdx.x >> 5)) * 4 + gi; qi < nfq; qi += ngroups) {
     // the record the certificate pass left: match position, previous neighbour (slot, original index, squared distance under the
@@ -377,87 +374,12 @@ __device__ __forceinline__ void lrr_match_sparse_body(const DirArgs& a, int flag
     const double x = r1.x, y = r1.y, z = r2.x;
     double qx, qy, qz;
     lrr_map_exact(A, tt, cc, x, y, z, qx, qy, qz);
-    bool queue = cand < 0;
-    double best = 1e300, second = 1e300, bound = 0.0; int best_s = -1, best_o = 0x7fffffff;
-    if (!queue) {
-      best = r2.y; best_s = cand; best_o = ri.z;
-      const double cand_best = best;
-      const double Rm = sqrt(best) * (1.0 + 1e-9) + slack + margin, Rm2 = Rm * Rm;
-      const int z0 = lrr_cell_clamp(qz - Rm, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(qz + Rm, g.oz, g.inv_h, g.nz);
-      const int y0 = lrr_cell_clamp(qy - Rm, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(qy + Rm, g.oy, g.inv_h, g.ny);
-      const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
-      if (nrows > LRR_G8_ROWS) queue = true;
-      else {
-        int lo4[4], sz4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int rl = 8 * u + gl;
-          lo4[u] = 0; sz4[u] = 0;
-          if (rl < nrows) {
-            const int zz = z0 + rl / ny, yy = y0 + rl % ny;
-            const double dz = lrr_slab_dist(qz, g.oz, g.h, zz, slack), dy = lrr_slab_dist(qy, g.oy, g.h, yy, slack);
-            const double dyz2 = dz * dz + dy * dy;
-            if (dyz2 <= Rm2) {
-              const double rx = sqrt(Rm2 - dyz2) * (1.0 + 1e-9) + slack;
-              const int xa = lrr_cell_clamp(qx - rx, g.ox, g.inv_h, g.nx), xb = lrr_cell_clamp(qx + rx, g.ox, g.inv_h, g.nx);
-              const int row = (zz * g.ny + yy) * g.nx;
-              lo4[u] = __ldg(g.cell_start + row + xa); sz4[u] = __ldg(g.cell_start + row + xb + 1);
-            }
-          }
-        }
-        int total = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (8 * u < nrows) {   // uniform in the group
-            const int rl = 8 * u + gl, sz = (rl < nrows) ? sz4[u] - lo4[u] : 0;
-            int inc = sz;
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) { const int v = __shfl_up_sync(gmask, inc, o, 8); if (gl >= o) inc += v; }
-            if (rl < nrows) { rowlo[rl] = lo4[u]; rowbase[rl] = total + inc - sz; }
-            total += __shfl_sync(gmask, inc, 7, 8);
-          }
-        }
-        __syncwarp(gmask);
-        if (total > LRR_G8_PTS) queue = true;
-        else {
-          for (int p0 = 0; p0 < total; p0 += 32) {
-            double4 P[4]; int J[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int p = p0 + 8 * u + gl;
-              J[u] = -1;
-              if (p < total) {
-                int ra = 0, rb = nrows;   // last row with rowbase <= p
-                while (rb - ra > 1) { const int mid = (ra + rb) >> 1; if (rowbase[mid] <= p) ra = mid; else rb = mid; }
-                J[u] = rowlo[ra] + (p - rowbase[ra]);
-                P[u] = lrr_ld_pos4(g.pos4 + J[u]);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (J[u] >= 0) lrr_nn_upd2(P[u], J[u], qx, qy, qz, best, best_s, best_o, second);
-          }
-          double gb = best; int gs = best_s, go = best_o;
-#pragma unroll
-          for (int o = 4; o; o >>= 1) {
-            const double ob = __shfl_xor_sync(gmask, gb, o, 8);
-            const int os = __shfl_xor_sync(gmask, gs, o, 8), oo = __shfl_xor_sync(gmask, go, o, 8);
-            if (ob < gb || (ob == gb && oo < go)) { gb = ob; gs = os; go = oo; }
-          }
-          double sec = (best_s == gs) ? second : best;
-#pragma unroll
-          for (int o = 4; o; o >>= 1) sec = fmin(sec, __shfl_xor_sync(gmask, sec, o, 8));
-          const double bd = fmin(sqrt(sec), sqrt(gb) + margin) * (1.0 - 1e-9) - slack;
-          bound = (sec > gb && bd > 0.0) ? bd : 0.0;
-          best = gb; best_s = gs; best_o = go;
-        }
-        __syncwarp(gmask);   // the group is done with its row table
-        if (queue) { best = cand_best; best_s = cand; best_o = ri.z; }
-      }
-    }
+    double best = r2.y, bound = 0.0; int best_s = cand, best_o = ri.z;
+    const bool ok = cand >= 0 && lrr_nn_ball_g8(g, qx, qy, qz, 0.125 * g.h, rowlo, rowbase, gmask, gl, best, best_s, best_o, bound);
     if (gl == 0) {
-      if (queue) {
+      if (!ok) {
         const int slot = atomicAdd(a.hq_count, 1);
-        a.hq_k[slot] = k; a.hq_best[slot] = best_s >= 0 ? best : 1e300; a.hq_s[slot] = best_s; a.hq_o[slot] = best_s >= 0 ? best_o : 0x7fffffff;
+        a.hq_k[slot] = k; a.hq_best[slot] = cand >= 0 ? r2.y : 1e300; a.hq_s[slot] = cand; a.hq_o[slot] = cand >= 0 ? ri.z : 0x7fffffff;
       } else lrr_match_finish(a, rigid, k, k, x, y, z, qx, qy, qz, best_s, acc, (a.proof && bound > 0.0) ? 2 : 0, bound);
     }
   }
