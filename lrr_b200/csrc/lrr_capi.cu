@@ -716,6 +716,12 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   // last find_closest (a ramp step at the end of one_iteration, then estimate_LS_backward)
   for (int d = 0; d < nd; ++d) a.d[d].M = (int)e->d[d].matches;
   if (stale) { PHASE(PH_RESID); lrr_k_resid(a, stale, ctx->stream, &ctx->launches); a.flags |= LRR_F_USE_OLD_W; }
+  if (cdcl_backward && e->dof == 6) {
+    // rigid: make_incremental on matches whose from_ are mapped clones already (cdcl sym :708-731): mapped once more, through the
+    // current global transform (the residuals above are those of estimate_scale_and_assign_weight on exactly these clones)
+    lrr_k_map_clones_again(e->d[src].sc, ctx->stream, &ctx->launches);
+    if (estimate_parameters) a.flags |= LRR_F_INV_OF_INCREMENT;
+  }
   int mode[2] = {0, 0}; double sin[2] = {0, 0};
   for (int d = 0; d < nd; ++d) {
     lrr_dir& D = e->d[d];
@@ -1053,7 +1059,6 @@ extern "C" int lrr_est_estimate_ls_backward(lrr_est* e, int estimate_parameters)
   if (e->kind == LRR_CDCL_SYM) {
     // cdcl variant (cdcl sym :705-863): the backward matches plus the forward matches reversed, normalised as ONE list,
     // strength re-weighting over the merged list, no spatial weighting; only backward_->trans_ is (un)normalised.
-    if (e->dof != 12) { ctx->err = "estimate_LS_backward: cdcl symmetric rigid variant (doubly mapped clones) is not built"; return LRR_ERR_UNSUPPORTED; }
     int rc = do_estimate(e, 1, estimate_parameters, true, true); if (rc != LRR_OK) return rc;
     if ((rc = pull_scal(e, 3)) != LRR_OK) return rc;
     return check_status(e);

@@ -268,6 +268,17 @@ __global__ void __launch_bounds__(LRR_THREADS) k_restamp(const __grid_constant__
     if (s >= 0) atomicMin(d.stamp + s, d.tag | (unsigned long long)(unsigned int)k);
   }
 }
+// cdcl symmetric rigid estimate_LS_backward (cdcl sym :708-731): the matches' from_ — clones mapped through the transform of the
+// iteration's find_closest — are cloned and mapped AGAIN through the current global transform, which becomes the transform the
+// increment is recomposed onto.
+__global__ void k_map_clones_again(Scal* sc) {
+  const int t = threadIdx.x;
+  if (t < 9) sc->Ag2[t] = sc->A[t];
+  else if (t < 12) sc->tg2[t - 9] = sc->t[t - 9];
+  else if (t < 15) sc->cg2[t - 12] = sc->c[t - 12];
+  else if (t == 15) sc->from_mapped = 2;
+}
+void lrr_k_map_clones_again(Scal* sc, cudaStream_t st, long long* launches) { k_map_clones_again<<<1, 32, 0, st>>>(sc); ++*launches; }
 __global__ void k_fill_ones(double* __restrict__ w, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) w[i] = 1.0;

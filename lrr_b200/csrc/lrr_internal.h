@@ -100,6 +100,9 @@ struct Scal {
   // completes the match (k_match_tile's finalizer folds it in).
   double pm_sum_loc[3], pm_sum_r2;
   double used_sum_r2;   // sum_r2 of the match the last estimate was made from (RMS_error "before", cdcl :440): copied by the weight phase
+  // from_mapped == 2: the matches' from_ are clones of clones — mapped through (Ag, tg, cg) and then through this second transform
+  // (cdcl symmetric rigid estimate_LS_backward maps the already mapped clones once more, cdcl sym :708-731)
+  double Ag2[9], tg2[3], cg2[3];
   double cert_failed, passb_queries;   // instrumentation: queries the last certificate pass could not keep / queries finished by pass B in the last find_closest
   double wfac;          // fused estimate pass: the weights it stored are final up to this factor 1 / (G S), applied by the trailing pass
   double mom[LRR_NRED];
@@ -176,6 +179,7 @@ enum {
   LRR_F_NO_OTHER_RENORM = 2048,   // ... and only the estimated direction's transform goes through normalize / unnormalize
   LRR_F_ICP = 4096,       // cdcl_estimation_ICP: scale constant 2.0 (cdcl_estimation_ICP.txx:580), strength weights normalised by their SUM (:607-637)
   LRR_F_SIM2D = 8192,     // cdcl_trans_similarity2d<2,4>: J = [x -y 1 0; y x 0 1], parameters (s cos a, s sin a, tx, ty)
+  LRR_F_INV_OF_INCREMENT = 32768,   // cdcl symmetric rigid estimate_LS_backward(true): the other direction becomes the inverse of the INCREMENT (cdcl sym :849-851 runs before the recomposition :856-862)
   LRR_F_NOFLAT = 16384,   // A/B switch: lane-per-row ball scans instead of the flattened warp-cooperative one (lrr_dev.cuh)
   LRR_F_BRACKET = 512     // order statistics from the window around the previous iteration's values (no histogram atomics, no collect pass)
 };
@@ -248,7 +252,8 @@ bool lrr_match_cert_usable(const EstArgs& a);
 // weights are final up to Scal::wfac (fused estimate pass)
 void lrr_k_match_cert(const EstArgs& a, cudaStream_t st, long long* launches, int mode = 0, double* mbox = nullptr, unsigned long long seq = 0,
                       int pull_mask = 0, int nhead = 0);
-void lrr_k_restamp(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);   // stamps of the source direction's matches (DirArgs::stamp_in_match == 0)
+void lrr_k_restamp(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);
+void lrr_k_map_clones_again(Scal* sc, cudaStream_t st, long long* launches);   // from_mapped 1 -> 2: the clones are mapped through the current transform once more   // stamps of the source direction's matches (DirArgs::stamp_in_match == 0)
 void lrr_tile_set_timeline(unsigned long long* p);
 void lrr_k_norm1(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);
 void lrr_k_norm2(const EstArgs& a, cudaStream_t st, long long* launches, int skip_clean = 0);

@@ -70,6 +70,11 @@ __global__ void __launch_bounds__(LRR_THREADS) k_angles(DirArgs a, int flags, in
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int m = 0; m < 3; ++m) v += sc->Ag[r * 3 + m] * Cp[m * 3 + c]; Tm[r * 3 + c] = v; }
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int m = 0; m < 3; ++m) v += Tm[r * 3 + m] * sc->Ag[c * 3 + m]; Cn[r * 3 + c] = v; }
         for (int m = 0; m < 9; ++m) Cp[m] = Cn[m];
+        if (mapped == 2) {   // ... and once more for a clone of a clone
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int m = 0; m < 3; ++m) v += sc->Ag2[r * 3 + m] * Cp[m * 3 + c]; Tm[r * 3 + c] = v; }
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double v = 0; for (int m = 0; m < 3; ++m) v += Tm[r * 3 + m] * sc->Ag2[c * 3 + m]; Cn[r * 3 + c] = v; }
+          for (int m = 0; m < 9; ++m) Cp[m] = Cn[m];
+        }
       }
       lrr_sym_eig3(Cp, Vp, D); lrr_sym_eig3(Cq, Vq, D);
       const int col = which == 0 ? 0 : 2;   // smallest / largest eigenvalue

@@ -47,6 +47,7 @@ __device__ __forceinline__ void lrr_from_loc(const DirArgs& a, const Scal* __res
                                              double& z) {
   x = __ldg(a.fx + i); y = __ldg(a.fy + i); z = __ldg(a.fz + i);
   if (mapped) { double ox, oy, oz; lrr_map_exact(sc->Ag, sc->tg, sc->cg, x, y, z, ox, oy, oz); x = ox; y = oy; z = oz; }
+  if (mapped == 2) { double ox, oy, oz; lrr_map_exact(sc->Ag2, sc->tg2, sc->cg2, x, y, z, ox, oy, oz); x = ox; y = oy; z = oz; }
 }
 
 __device__ __forceinline__ void lrr_ld_P6(const double* __restrict__ rec, int s, double (&P)[6]) {
@@ -773,7 +774,8 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
   // instead of being read and written one by one by thread 0 (~40 dependent round trips on the critical path of every
   // iteration): sF/sB = A[9] t[3] c[3], sFg = Ag[9] tg[3] cg[3], sFn/sBn = cfrom[3] rfrom cto[3] rto.
   __shared__ double sF[15], sFg[15], sFn[8], sB[15], sBn[8];
-  if (tid < 15) { sF[tid] = __ldcg(&F->A[0] + tid); sFg[tid] = __ldcg(&F->Ag[0] + tid); if (B) sB[tid] = __ldcg(&B->A[0] + tid); }
+  // (the global transform an increment is recomposed onto is the LAST map the clones went through)
+  if (tid < 15) { sF[tid] = __ldcg(&F->A[0] + tid); sFg[tid] = F->from_mapped == 2 ? __ldcg(&F->Ag2[0] + tid) : __ldcg(&F->Ag[0] + tid); if (B) sB[tid] = __ldcg(&B->A[0] + tid); }
   else if (tid >= 32 && tid < 40) { sFn[tid - 32] = __ldcg(&F->cfrom[0] + (tid - 32)); if (B) sBn[tid - 32] = __ldcg(&B->cfrom[0] + (tid - 32)); }
   __syncthreads();
   lrr_tl(9, 1);
@@ -945,6 +947,14 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
           t[r] = acc + rfx * t[r] + cf[r];
         }
       }
+      if (B && (flags & LRR_F_INV_OF_INCREMENT)) {   // the other direction <- inverse() of the increment as it stands here (cdcl sym :849-851)
+        double invA[9]; lrr_inv3(A, invA);
+        for (int i = 0; i < 9; ++i) sB[i] = invA[i];
+        for (int i = 0; i < 3; ++i) {
+          double acc = (-invA[3 * i]) * t[0]; acc += (-invA[3 * i + 1]) * t[1]; acc += (-invA[3 * i + 2]) * t[2];
+          sB[9 + i] = acc + (normalize ? cm[i] : 0.0); sB[12 + i] = 0.0;   // (the increment's centre: unnormalize left center_moving_ = the normalisation centre, rigid3d.cxx:305)
+        }
+      }
       // recompose_increment (rigid3d.cxx:309-326): dR = U V^T, R <- R dR, t <- dR t + dt   (Q7)
       double dR[9]; lrr_orthogonalize3(A, dR);
       double Rn[9], tn[3];
@@ -984,7 +994,7 @@ static __device__ void lrr_solve(Scal* F, Scal* B, int flags, int dof, int estim
       for (int i = 0; i < 12; ++i) for (int jx = 0; jx < 12; ++jx) { double v = 0; for (int k = 0; k < 12; ++k) v += Tm[i * 12 + k] * K[jx * 12 + k]; B->cov[i * 12 + jx] = v; }
       for (int d = 0; d < 3; ++d) sB[12 + d] = bcm[d];
     }
-    if (B && estimate_parameters) {   // backward = forward->inverse()  (affine.txx:54-59, rigid3d.cxx:113-118)
+    if (B && estimate_parameters && !(rigid && (flags & LRR_F_INV_OF_INCREMENT))) {   // backward = forward->inverse()  (affine.txx:54-59, rigid3d.cxx:113-118)
       double invA[9]; lrr_inv3(sF, invA);
       for (int i = 0; i < 9; ++i) sB[i] = invA[i];
       for (int i = 0; i < 3; ++i) {

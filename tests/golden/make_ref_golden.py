@@ -73,13 +73,16 @@ def run_case(lib, pair, kind, dof, iters=ITERS, with_objcov=True):
         for tag, xx in (("x0", x), ("x1", x2)):
             f, g = est.objcov_eval(xx, 0)
             out[f"objcov_{tag}"], out[f"objcov_{tag}_f"], out[f"objcov_{tag}_g"] = xx, np.array([f]), g
-    if "sym" in kind and not (kind == "cdcl_sym" and dof == 6):
-        # estimate_LS_backward(false): decision-measurement path of the driver (rrl/itkLocationRegistration.cxx:1840)
+    if "sym" in kind:
+        # estimate_LS_backward(false): decision-measurement path of the driver (rrl/itkLocationRegistration.cxx:1840), followed by
+        # the metrics the driver reads next (:1842-1845).  cdcl symmetric <3,6>: the rigid branch (cdcl sym :708-731, :856-862) maps
+        # the already mapped clones once more, so these metrics see them through a third map.
         est.estimate_ls_backward(False)
         for d in dirs:
             T = est.get_transform(d)
             out[f"lsb_d{d}_cov"], out[f"lsb_d{d}_A"] = T["cov"], T["A"]
             out[f"lsb_d{d}_w"] = est.get_matches(d)[2]
+            out[f"lsb_d{d}_metrics"] = np.array([est.metric(m, d) for m in ("rms", "weighted", "sheet_angles", "tube_angles")])
     return out
 
 

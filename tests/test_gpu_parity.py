@@ -301,14 +301,20 @@ def test_speculative_plan_and_its_fallback():
         assert out.returncode == 0 and "spec ok" in out.stdout, str(env) + out.stdout + out.stderr
 
 
-def test_cdcl_estimate_ls_backward(gpu_lib, oracle_lib, pair):
-    """cdcl symmetric estimate_LS_backward (cdcl sym :705-863): merged list, merged normalisation, no spatial weighting."""
-    for ep in (False, True):
-        _, g = make_est(gpu_lib, pair, "cdcl_sym")
-        _, o = make_est(oracle_lib, pair, "cdcl_sym")
-        for it in range(4):
-            g.one_iteration(it); o.one_iteration(it)
-        g.estimate_ls_backward(ep); o.estimate_ls_backward(ep)
-        compare_state(g, o, dirs=(0, 1))
-        sg, so = g.state(), o.state()
-        assert abs(g.metric("weighted", 1) - o.metric("weighted", 1)) <= 1e-9 * max(1.0, abs(o.metric("weighted", 1)))
+def test_cdcl_estimate_ls_backward(gpu_lib, oracle_lib, pair, pair_rigid):
+    """cdcl symmetric estimate_LS_backward (cdcl sym :705-863): merged list, merged normalisation, no spatial weighting — affine
+    <3,12> and the rigid <3,6> branch (the already mapped clones are mapped once more, :708-731; recomposed onto the transform at
+    call time, :856-862; with estimate_parameters the forward transform becomes the inverse of the INCREMENT, :849-851), and the
+    metrics the driver reads afterwards (rrl/itkLocationRegistration.cxx:1842-1845)."""
+    for dof, pr in ((12, pair), (6, pair_rigid)):
+        for ep in (False, True):
+            _, g = make_est(gpu_lib, pr, "cdcl_sym", dof=dof)
+            _, o = make_est(oracle_lib, pr, "cdcl_sym", dof=dof)
+            for it in range(4):
+                g.one_iteration(it); o.one_iteration(it)
+            g.estimate_ls_backward(ep); o.estimate_ls_backward(ep)
+            compare_state(g, o, dirs=(0, 1))
+            for d in (0, 1):
+                for m in ("rms", "weighted", "sheet_angles", "tube_angles"):
+                    a, b = g.metric(m, d), o.metric(m, d)
+                    assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (dof, ep, d, m, a, b)
