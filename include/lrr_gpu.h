@@ -224,6 +224,29 @@ int  lrr_batch_run_ids(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, 
 int  lrr_batch_run_multi(lrr_ctx** ctx, int ndev, lrr_fset** moving_all, lrr_fset** fixed_all, const lrr_job* jobs, int64_t njobs,
                          int max_iter, uint64_t shuffle_seed, lrr_result* out);
 
+/* ---- the driver's candidate loop (rrl/itkLocationRegistration.cxx:2230-2332, 1816-1871) -----------------------------------------
+ * jobs[l * n_candidates + c] = candidate initialisation c of nodule location l.  For every candidate: SetupEstimation,
+ * find_closest_euclidean and the four angle measures -> ranking key = their mean (:2303-2326).  Then per location, best angle
+ * first: SetupEstimation, the <= max_iter one_iteration loop (:2418), and — when it converged and did not oscillate (:2495-2507) —
+ * ComputeDecisionMeasurements (:1816-1871: angles, weighted errors, estimate_LS_backward(false), the maximum trace of the transfer-
+ * error covariance J Sigma J^T over a 5 mm grid of the ROI, forward and backward, :2793-2858).  until_verified != 0: a location
+ * stops at its first verified candidate (:2332) — verified = converged, not oscillated, validTransform; the reference's libsvm
+ * model file is not in its repository — else every candidate is run.  All on the device, one launch for the ranking and one for
+ * the registrations; out / decisions are indexed like jobs. */
+typedef struct lrr_decision {
+  double  rank_angles[4];       /* sheet, tube, sheet backward, tube backward (degrees) at the initial transform   :2305-2311 */
+  double  rank_angle_average;   /* the ranking key                                                                 :2313      */
+  double  measurements[8];      /* max / min of {weighted error, maxTrace, sheet angles, tube angles}              :1853-1860 */
+  double  weighted_error[2], max_trace[2], sheet_angles[2], tube_angles[2];   /* [0] forward, [1] backward, before max / min */
+  int32_t rank;                 /* position among the location's candidates, best angle first; -1: ROI rejected    :2326      */
+  int32_t ran;                  /* the registration was run (until_verified: candidates after the verified one are not)       */
+  int32_t verified;             /* converged, not oscillated, validTransform                                                  */
+  int32_t measured;             /* measurements[] are valid (the driver computes them only for converged, non-oscillating runs) */
+} lrr_decision;
+int  lrr_batch_run_locations(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t n_locations,
+                             int32_t n_candidates, int max_iter, uint64_t shuffle_seed, int until_verified, double voxel_spacing,
+                             lrr_result* out, lrr_decision* decisions);
+
 #ifdef __cplusplus
 }
 #endif

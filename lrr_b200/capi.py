@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
-    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run", "batch_run_ids", "batch_run_multi",
+    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations",
 ]
 
 
@@ -65,7 +65,10 @@ JOB_DTYPE = np.dtype([("A", "f8", 9), ("t", "f8", 3), ("c", "f8", 3), ("roi_cent
 RESULT_DTYPE = np.dtype([("status", "i4"), ("converged", "i4"), ("oscillated", "i4"), ("iterations", "i4"),
                          ("n_moving_inside", "i4"), ("n_fixed_inside", "i4"), ("A", "f8", 9), ("t", "f8", 3),
                          ("c", "f8", 3), ("cov", "f8", 144), ("rms", "f8"), ("weighted_error", "f8")])
-assert JOB_DTYPE.itemsize == C.sizeof(Job) and RESULT_DTYPE.itemsize == C.sizeof(Result)
+DECISION_DTYPE = np.dtype([("rank_angles", "f8", 4), ("rank_angle_average", "f8"), ("measurements", "f8", 8), ("weighted_error", "f8", 2),
+                           ("max_trace", "f8", 2), ("sheet_angles", "f8", 2), ("tube_angles", "f8", 2), ("rank", "i4"), ("ran", "i4"),
+                           ("verified", "i4"), ("measured", "i4")])
+assert JOB_DTYPE.itemsize == C.sizeof(Job) and RESULT_DTYPE.itemsize == C.sizeof(Result) and DECISION_DTYPE.itemsize == 8 * 21 + 16
 
 
 class LrrError(RuntimeError):
@@ -130,6 +133,7 @@ class Lib:
             "objcov_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32)]),
             "batch_run": (i32, [vp, vp, vp, vp, i64, i32, u64, vp]),
             "batch_run_ids": (i32, [vp, vp, vp, vp, C.POINTER(C.c_int64), i64, i32, u64, vp]),
+            "batch_run_locations": (i32, [vp, vp, vp, vp, i64, C.c_int32, i32, u64, i32, dbl, vp, vp]),
             "batch_run_multi": (i32, [C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp), vp, i64, i32, u64, vp]),
         }
         for name, (res, args) in sig.items():
@@ -212,6 +216,18 @@ class Context:
                                               len(jobs), max_iter, seed, out.ctypes.data_as(C.c_void_p))
         self.check(rc, "batch_run")
         return out
+
+    def batch_run_locations(self, moving: "FeatureSet", fixed: "FeatureSet", jobs: np.ndarray, n_candidates: int, max_iter: int = 70, seed: int = 0,
+                            until_verified: bool = False, voxel_spacing: float = 1.0):
+        """The driver's candidate loop: jobs[l * n_candidates + c]; returns (results, decisions), indexed like jobs."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        assert len(jobs) % n_candidates == 0
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE); dec = np.zeros(len(jobs), dtype=DECISION_DTYPE)
+        rc = self.lib.fn("batch_run_locations")(self.h, moving.h, fixed.h, jobs.ctypes.data_as(C.c_void_p), len(jobs) // n_candidates, n_candidates,
+                                                max_iter, seed, int(until_verified), float(voxel_spacing), out.ctypes.data_as(C.c_void_p),
+                                                dec.ctypes.data_as(C.c_void_p))
+        self.check(rc, "batch_run_locations")
+        return out, dec
 
     def close(self):
         if self.h:

@@ -9,6 +9,7 @@
 // __syncthreads instead of kernel boundaries).  No host round trip per iteration, no launches per iteration.
 #include "lrr_phases.cuh"
 #include "../../include/lrr_gpu.h"
+#include "lrr_host.h"
 #include <cstdio>
 #include <cstdlib>
 
@@ -39,6 +40,10 @@ struct BatchArgs {
   double* w_f; double* w_fP6; int* w_forig; int* w_sidx; double* w_pm; int* w_prev; int* w_hq; double* w_hqb;
   unsigned long long* w_stamp0; unsigned long long* w_stamp1; Scal* w_sc;
   double muse_table[4 * 32]; int muse_rows;   // table for n = 1000
+  // the driver's candidate loop (lrr_batch_run_locations): mode 0 = registration only (lrr_batch_run), 1 = ranking angles only,
+  // 2 = registration + decision measurements; order != null: a unit of work is a LOCATION whose candidates (order[l * ncand + k], -1
+  // terminated) are run one after the other, until_verified stops at the first verified one
+  int mode, ncand, until_verified; const int* order; lrr_decision* dec; double spacing; long long nunits;
   int ball_rows, g8;                            // pass A keeps balls of at most ball_rows rows; the rest: eight-lane groups (g8) / one warp per query
   long long* dbg;                               // optional: 16 cycle counters (block 0), phase profile
 };
@@ -202,6 +207,42 @@ __device__ double block_muse(const DirArgs& a, const BatchArgs& B, double* buf /
   return r;
 }
 
+// ComputeTransferErrorCovariance (rrl/itkLocationRegistration.cxx:2793-2858): maximum over a 5 mm grid of the ROI of
+// trace( J(x) Sigma J(x)^T ), J the affine Jacobian at x (x~ = (x - centre, 1)): sum_d sum_ab x~_a x~_b Sigma[(d,a),(d,b)].
+// start = ROI centre - half, end = start + 2 half - voxel spacing; the grid counts follow the reference's floating loops.
+__device__ double block_max_trace(const Scal* sc, const double* centre, double half, double spacing, double* s_d /* >= 2 doubles */) {
+  __shared__ int s_n[3];
+  unsigned long long* mx = reinterpret_cast<unsigned long long*>(s_d);
+  if (threadIdx.x < 3) {
+    const double start = centre[threadIdx.x] - half, end = start + 2.0 * half - spacing;
+    int n = 0; for (double v = start; v <= end; v += 5.0) ++n;
+    s_n[threadIdx.x] = n;
+  }
+  if (threadIdx.x == 0) mx[0] = 0ull;
+  __syncthreads();
+  const int nx = s_n[0], ny = s_n[1], nz = s_n[2], total = nx * ny * nz;
+  double best = 0.0;
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    const int ix = p % nx, iy = (p / nx) % ny, iz = p / (nx * ny);
+    // (coordinates by repeated addition, as the reference's loops form them)
+    double x = centre[0] - half; for (int q = 0; q < ix; ++q) x += 5.0;
+    double y = centre[1] - half; for (int q = 0; q < iy; ++q) y += 5.0;
+    double z = centre[2] - half; for (int q = 0; q < iz; ++q) z += 5.0;
+    const double xt[4] = {x - sc->c[0], y - sc->c[1], z - sc->c[2], 1.0};
+    double tr = 0.0;
+    for (int d = 0; d < 3; ++d) for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
+      const int ia = a < 3 ? 3 * d + a : 9 + d, ib = b < 3 ? 3 * d + b : 9 + d;
+      tr += xt[a] * xt[b] * sc->cov[ia * 12 + ib];
+    }
+    best = fmax(best, tr);
+  }
+  if (best > 0.0) atomicMax(mx, (unsigned long long)__double_as_longlong(best));
+  __syncthreads();
+  const double r = __longlong_as_double((long long)mx[0]);
+  __syncthreads();
+  return r;
+}
+
 struct BatchShared {
   PhaseSharedT<BATCH_THREADS / 32> ph;
   DirArgs d[2];
@@ -214,6 +255,7 @@ struct BatchShared {
   int rows[(BATCH_THREADS / 8) * 2 * LRR_G8_ROWS];   // row tables of the eight-lane groups
   // control state (thread 0 writes, everybody reads after a barrier)
   int converged, status, it, finest, osc, job;
+  unsigned int seq;   // registrations this block has started: the stamp epochs must GROW over the life of its workspace (jobs may come in any order)
   unsigned int number_matches;
   double err_diff, werr_before;
   unsigned long long calls[2];
@@ -232,13 +274,19 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
   const size_t blk = blockIdx.x;
   SelDev nosel; nosel.fine = nullptr;
   long long tmark = clock64();
-  if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) S.tph[i] = 0;
+  if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) S.tph[i] = 0; S.seq = 0; }
 
   for (;;) {
     if (threadIdx.x == 0) S.job = atomicAdd(B.next_job, 1);
     __syncthreads();
-    const int j = S.job;
-    if (j >= B.njobs) break;
+    const int unit = S.job;
+    __syncthreads();
+    if (unit >= B.nunits) break;
+   int cpos = 0; bool unit_verified = false;
+   do {   // the candidates of a location, best angle first (rrl/itkLocationRegistration.cxx:2332); a plain job list has one "candidate" per unit
+    int j = unit;
+    if (B.order) { const int oc = B.order[(size_t)unit * B.ncand + cpos]; if (oc < 0) break; j = unit * B.ncand + oc; }
+    ++cpos;
     const lrr_job job = B.jobs[j];
     lrr_result* R = B.out + j;
     // ---- set_features: ROI selection for both directions (forward from = moving, backward from = fixed) ----
@@ -260,14 +308,16 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       }
       __syncthreads();
     }
+    lrr_decision* D = B.dec ? B.dec + j : nullptr;
     if (threadIdx.x == 0) {
       for (size_t i = 0; i < sizeof(lrr_result) / 8; ++i) reinterpret_cast<double*>(R)[i] = 0.0;
       R->n_moving_inside = overflow ? -1 : n_in[0]; R->n_fixed_inside = overflow ? -1 : n_in[1];
       R->status = overflow ? -1 : (reject ? 1 : 0);     // -1: ROI larger than BATCH_CAP, the host path takes the job
+      if (D && B.mode == 1) { for (size_t i = 0; i < sizeof(lrr_decision) / 8; ++i) reinterpret_cast<double*>(D)[i] = 0.0; D->rank = -1; }
     }
     __syncthreads();
     TPH(0);
-    if (overflow || reject) continue;
+    if (!(overflow || reject)) {
 
     // ---- direction descriptors ----
     if (threadIdx.x < 2) {
@@ -313,10 +363,40 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       }
       F->from_mapped = 0; Bk->from_mapped = 0; F->status = 0; Bk->status = 0;
       S.converged = 0; S.status = 0; S.it = 0; S.finest = 0; S.osc = 0; S.number_matches = 1000; S.err_diff = 0.0; S.werr_before = 0.0;
+      S.seq += 1;
     }
     for (int i = threadIdx.x; i < 144; i += blockDim.x) { F->cov[i] = 0.0; Bk->cov[i] = 0.0; }
     __syncthreads();
 
+    if (B.mode == 1) {
+      // ---- ranking (rrl/itkLocationRegistration.cxx:2303-2313): find_closest_euclidean at the initial transform (1000 points, its own
+      //      permutation stream), then sheet / tube angles forward and backward, in degrees ----
+      if (threadIdx.x < 2) {
+        const int d = threadIdx.x;
+        const unsigned long long gid = B.job_ids ? (unsigned long long)B.job_ids[j] : (unsigned long long)j;
+        unsigned long long st = (B.shuffle_seed + gid) + (unsigned long long)d * 0x632BE59BD9B4E019ULL + (1ULL << 40) * 0xD1342543DE82EF95ULL;
+        for (int r = 0; r < 4; ++r) { S.d[d].perm_key[r] = (unsigned int)(bt_splitmix(st) >> 32); S.d2[d].perm_key[r] = S.d[d].perm_key[r]; }
+        int bits = 2; while ((1ull << bits) < (unsigned long long)S.d[d].n_in) ++bits;
+        if (bits & 1) ++bits;
+        S.d[d].perm_half = bits / 2; S.d2[d].perm_half = bits / 2;
+        S.d[d].M = min(1000, S.d[d].n_in); S.d2[d].M = S.d[d].M;
+        const unsigned long long epoch = ((unsigned long long)S.seq << 8) | 255ull;
+        S.d[d].tag = (~epoch) << 32; S.d2[d].tag = S.d[d].tag;
+      }
+      __syncthreads();
+      for (int d = 0; d < 2; ++d) {
+        lrr_phase_match(scope, S.d[d], flags, S.ph);
+        if (B.g8) lrr_phase_match_queue_g8(scope, S.d[d], S.d2[d], flags, S.ph, S.rows);
+        lrr_phase_match_hard(scope, B.g8 ? S.d2[d] : S.d[d], flags, S.ph);
+      }
+      for (int d = 0; d < 2; ++d) for (int which = 0; which < 2; ++which) {
+        lrr_phase_angles_rrl(scope, S.d[d], which, S.ph);
+        if (threadIdx.x == 0 && D) D->rank_angles[2 * d + which] = (S.d[d].sc->ang_num / S.d[d].sc->ang_den) * (180.0 / 3.14159265358979323846);
+        __syncthreads();
+      }
+      if (threadIdx.x == 0 && D) D->rank_angle_average = (D->rank_angles[0] + D->rank_angles[1] + D->rank_angles[2] + D->rank_angles[3]) / 4;
+      __syncthreads();
+    } else {
     // ---- the driver loop (rrl/itkLocationRegistration.cxx:2418) ----
     while (!S.converged && S.it < B.max_iter && S.status == 0) {
       // find_closest_euclidean, both directions: new permutation key, new stamp epoch
@@ -332,8 +412,8 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
         S.d[d].M = min(S.number_points[d], S.d[d].n_in);
         for (int r = 0; r < 4; ++r) S.d2[d].perm_key[r] = S.d[d].perm_key[r];
         S.d2[d].perm_half = S.d[d].perm_half; S.d2[d].M = S.d[d].M;
-        // epoch: job and iteration make it unique over the life of the workspace (stamps are never cleared)
-        const unsigned long long epoch = ((unsigned long long)(j + 1) << 8) | (unsigned long long)(S.it + 1);
+        // epoch: (registration number of this block, iteration) — unique and growing over the life of the workspace (stamps are never cleared)
+        const unsigned long long epoch = ((unsigned long long)S.seq << 8) | (unsigned long long)(S.it + 1);
         S.d[d].tag = (~epoch) << 32; S.d2[d].tag = S.d[d].tag;
       }
       __syncthreads();
@@ -420,9 +500,61 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       for (int i = 0; i < 3; ++i) { R->t[i] = F->t[i]; R->c[i] = F->c[i]; }
       R->rms = F->res_sum_r2;                          // rrl RMS_error: the plain sum (Q1)
       R->weighted_error = F->res_sum_w != 0 ? F->res_sum_wr / F->res_sum_w : F->res_sum_wr;
+      if (D) { D->ran = 1; D->verified = (S.status == 0 && S.converged && !(S.osc > 10)) ? 1 : 0; }
     }
     __syncthreads();
+    if (S.status == 0 && S.converged && !(S.osc > 10)) unit_verified = true;
+    // ---- ComputeDecisionMeasurements (rrl/itkLocationRegistration.cxx:1816-1871), only for converged, non-oscillating runs (:2495-2507) ----
+    if (B.mode == 2 && D && S.status == 0 && S.converged && !(S.osc > 10)) {
+      const double deg = 180.0 / 3.14159265358979323846;
+      // forward: angles and weighted error of the final matches, then the sampled transfer-error covariance
+      for (int which = 0; which < 2; ++which) {
+        lrr_phase_angles_rrl(scope, S.d[0], which, S.ph);
+        if (threadIdx.x == 0) (which == 0 ? D->sheet_angles : D->tube_angles)[0] = (F->ang_num / F->ang_den) * deg;
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) D->weighted_error[0] = F->res_sum_w != 0 ? F->res_sum_wr / F->res_sum_w : F->res_sum_wr;
+      { const double mt = block_max_trace(F, job.roi_center_moving, job.roi_half_size, B.spacing, S.sd); if (threadIdx.x == 0) D->max_trace[0] = mt; }
+      // estimate_LS_backward( false ) = estimate_LS with forward_ / backward_ swapped (rrl sym :922-934): stale weights -> residuals
+      // under the current transforms first, scale from the current weights (cdcl :698-701), the backward direction defines the
+      // normalisation, its list is the "forward" one of the accumulation
+      for (int d = 0; d < 2; ++d) lrr_phase_resid(scope, S.d[d], S.ph);
+      lrr_phase_norm1(scope, S.d[1], S.ph);
+      lrr_phase_norm2(scope, S.d[1], F, S.ph);
+      for (int d = 0; d < 2; ++d) { lrr_phase_weight(scope, S.d[d], flags | LRR_F_USE_OLD_W, 0, nosel, nosel, 0, 0.0, S.ph); scope.phase_end(); }
+      for (int d = 0; d < 2; ++d) {
+        int ok = 1;
+        const double G = block_mad(S.d[d].gkey, S.d[d].M, (double)BATCH_SEL_BINS / LRR_STRENGTH_CAP, S.hist, S.cand, S.si, S.sd, &ok);
+        const double Sp = block_mad(S.d[d].skey, S.d[d].M, (double)BATCH_SEL_BINS, S.hist, S.cand, S.si, S.sd, &ok);
+        if (threadIdx.x == 0) { S.d[d].sc->G = G; S.d[d].sc->S = Sp; if (!ok) S.status = 3; }
+      }
+      __syncthreads();
+      const double jc0[3] = {0, 0, 0};
+      for (int d = 0; d < 2; ++d) lrr_phase_accumulate(scope, S.d[d], flags, d == 0, 0, S.d[d].sc->G, S.d[d].sc->S, jc0, S.ph);
+      __syncthreads();
+      lrr_solve(Bk, F, flags, 12, 0);
+      scope.phase_end();
+      { const double mt = block_max_trace(Bk, job.roi_center_fixed, job.roi_half_size, B.spacing, S.sd); if (threadIdx.x == 0) D->max_trace[1] = mt; }
+      for (int which = 0; which < 2; ++which) {
+        lrr_phase_angles_rrl(scope, S.d[1], which, S.ph);
+        if (threadIdx.x == 0) (which == 0 ? D->sheet_angles : D->tube_angles)[1] = (Bk->ang_num / Bk->ang_den) * deg;
+        __syncthreads();
+      }
+      lrr_phase_resid(scope, S.d[1], S.ph);
+      if (threadIdx.x == 0) {
+        D->weighted_error[1] = Bk->res_sum_w != 0 ? Bk->res_sum_wr / Bk->res_sum_w : Bk->res_sum_wr;
+        const double* q[4] = {D->weighted_error, D->max_trace, D->sheet_angles, D->tube_angles};
+        for (int k = 0; k < 4; ++k) { D->measurements[k] = fmax(q[k][0], q[k][1]); D->measurements[4 + k] = fmin(q[k][0], q[k][1]); }
+        D->measured = S.status == 0 ? 1 : 0;
+        if (S.status == 3) R->status = -2;
+      }
+      __syncthreads();
+    }
+    }   // mode
+    }   // ROI accepted
+    __syncthreads();
     TPH(11);
+   } while (B.order && cpos < B.ncand && !(B.until_verified && unit_verified));
   }
   if (B.dbg && blockIdx.x == 0 && threadIdx.x == 0) for (int i = 0; i < 16; ++i) B.dbg[i] = S.tph[i];
 }
@@ -430,12 +562,21 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
 // ---- host side -------------------------------------------------------------------------------------------------
 size_t lrr_batch_smem_bytes() { return ((sizeof(BatchShared) + 15) & ~size_t(15)) + (size_t)BATCH_CAP * sizeof(int); }
 
+// extra arguments of the candidate-loop launches (lrr_batch_run_locations); mode == 0: a plain job list.  thread_local: one host
+// thread drives one context
+thread_local BatchLocArgs lrr_batch_loc_args = {0, 1, 0, nullptr, nullptr, 1.0};
 cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
                              const long long* job_ids_dev, int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
                              size_t workspace_bytes, cudaStream_t st, long long* launches) {
   BatchArgs B; memset(&B, 0, sizeof(B));
   B.all[0] = moving_all; B.all[1] = fixed_all; B.jobs = jobs_dev; B.out = out_dev; B.njobs = njobs; B.max_iter = max_iter; B.shuffle_seed = shuffle_seed;
   B.job_ids = job_ids_dev;
+  B.mode = 0; B.ncand = 1; B.until_verified = 0; B.order = nullptr; B.dec = nullptr; B.spacing = 1.0; B.nunits = njobs;
+  if (lrr_batch_loc_args.mode) {
+    B.mode = lrr_batch_loc_args.mode; B.ncand = lrr_batch_loc_args.ncand; B.until_verified = lrr_batch_loc_args.until_verified;
+    B.order = lrr_batch_loc_args.order; B.dec = lrr_batch_loc_args.dec; B.spacing = lrr_batch_loc_args.spacing;
+    if (B.order) B.nunits = njobs / B.ncand;
+  }
   { const char* e = getenv("LRR_BATCH_G8"); B.g8 = e ? atoi(e) : 1; const char* r = getenv("LRR_BATCH_BALL_ROWS"); B.ball_rows = r ? atoi(r) : (B.g8 ? 16 : 0); }
   for (int i = 0; i < 4 * 32; ++i) B.muse_table[i] = muse_table[i];
   B.muse_rows = muse_rows;

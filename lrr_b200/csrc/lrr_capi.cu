@@ -1534,3 +1534,71 @@ extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_a
   enter(ctxs[0]);
   return batch_host_jobs(ctxs[0], moving_all[0], fixed_all[0], jobs, todo, nullptr, 0, max_iter, shuffle_seed, out);
 }
+
+// The driver's candidate loop on the device (include/lrr_gpu.h): one launch ranks every candidate (find_closest_euclidean + four
+// angle measures), the host orders each location's candidates by the mean angle (std::sort of rrl/itkLocationRegistration.cxx:2326;
+// ties keep the candidate order), a second launch runs one LOCATION per thread block, best angle first, with the decision
+// measurements of every converged, non-oscillating registration.
+extern "C" int lrr_batch_run_locations(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t n_locations, int32_t n_candidates,
+                                       int max_iter, uint64_t shuffle_seed, int until_verified, double voxel_spacing, lrr_result* out, lrr_decision* decisions) {
+  if (!ctx || !moving_all || !fixed_all || n_locations < 0 || n_candidates <= 0 || max_iter > 250) return LRR_ERR_INVALID;
+  if (moving_all->ctx != ctx || fixed_all->ctx != ctx) return LRR_ERR_INVALID;
+  const int64_t njobs = n_locations * (int64_t)n_candidates;
+  if (njobs > 0 && (!jobs || !out || !decisions)) return LRR_ERR_INVALID;
+  if (njobs == 0) return LRR_OK;
+  if (!(voxel_spacing > 0.0)) voxel_spacing = 1.0;
+  enter(ctx);
+  cudaStream_t st = ctx->stream;
+  const int per_sm = lrr_batch_blocks_per_sm();
+  const int nb_rank = (int)std::min<int64_t>(njobs, (int64_t)lrr_num_sms() * per_sm), nb_run = (int)std::min<int64_t>(n_locations, (int64_t)lrr_num_sms() * per_sm);
+  const size_t wbytes = lrr_batch_workspace_bytes(std::max(nb_rank, nb_run), (int)moving_all->n, (int)fixed_all->n);
+  void* work = nullptr; lrr_job* djobs = nullptr; lrr_result* dout = nullptr; lrr_decision* ddec = nullptr; int* dorder = nullptr;
+  int rc = LRR_OK;
+  auto fail = [&](int code, const char* what) { if (rc == LRR_OK) { rc = code; if (what) ctx->err = what; } };
+  auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == LRR_OK) { rc = LRR_ERR_CUDA; ctx->err = std::string(what) + ": " + cudaGetErrorString(e); } };
+  cu(cudaMallocAsync(&work, wbytes, st), "workspace");
+  cu(cudaMallocAsync((void**)&djobs, sizeof(lrr_job) * njobs, st), "jobs"); cu(cudaMallocAsync((void**)&dout, sizeof(lrr_result) * njobs, st), "results");
+  cu(cudaMallocAsync((void**)&ddec, sizeof(lrr_decision) * njobs, st), "decisions"); cu(cudaMallocAsync((void**)&dorder, sizeof(int) * njobs, st), "order");
+  double table[4 * 32] = {0};
+  const int rows = build_muse_table(1000u, table);
+  if (rc == LRR_OK) {
+    cu(cudaMemcpyAsync(djobs, jobs, sizeof(lrr_job) * njobs, cudaMemcpyHostToDevice, st), "jobs H2D");
+    // ---- stage 1: ranking ----
+    lrr_batch_loc_args = BatchLocArgs{1, n_candidates, 0, nullptr, ddec, voxel_spacing};
+    { PHASE(PH_BATCH); cu(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, nullptr, max_iter, shuffle_seed, table, rows, nb_rank, work, wbytes, st, &ctx->launches), "ranking launch"); }
+    lrr_batch_loc_args.mode = 0;
+    cu(cudaMemcpyAsync(out, dout, sizeof(lrr_result) * njobs, cudaMemcpyDeviceToHost, st), "results D2H");
+    cu(cudaMemcpyAsync(decisions, ddec, sizeof(lrr_decision) * njobs, cudaMemcpyDeviceToHost, st), "decisions D2H");
+    cu(cudaStreamSynchronize(st), "ranking");
+  }
+  std::vector<int> order((size_t)njobs, -1);
+  if (rc == LRR_OK) {
+    for (int64_t l = 0; l < n_locations && rc == LRR_OK; ++l) {
+      std::vector<std::pair<double, int> > cand;
+      for (int c = 0; c < n_candidates; ++c) {
+        const int64_t j = l * n_candidates + c;
+        if (out[j].status < 0) fail(LRR_ERR_UNSUPPORTED, "lrr_batch_run_locations: an ROI holds more features than the block kernel takes (16384)");
+        if (out[j].status == 0) cand.push_back(std::make_pair(decisions[j].rank_angle_average, c));
+      }
+      std::stable_sort(cand.begin(), cand.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+      for (size_t k = 0; k < cand.size(); ++k) { order[(size_t)(l * n_candidates) + k] = cand[k].second; decisions[l * n_candidates + cand[k].second].rank = (int32_t)k; }
+    }
+  }
+  if (rc == LRR_OK) {
+    // ---- stage 2: one location per block, best angle first ----
+    cu(cudaMemcpyAsync(dorder, order.data(), sizeof(int) * njobs, cudaMemcpyHostToDevice, st), "order H2D");
+    cu(cudaMemcpyAsync(ddec, decisions, sizeof(lrr_decision) * njobs, cudaMemcpyHostToDevice, st), "decisions H2D");
+    lrr_batch_loc_args = BatchLocArgs{2, n_candidates, until_verified ? 1 : 0, dorder, ddec, voxel_spacing};
+    { PHASE(PH_BATCH); cu(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, nullptr, max_iter, shuffle_seed, table, rows, nb_run, work, wbytes, st, &ctx->launches), "registration launch"); }
+    lrr_batch_loc_args.mode = 0;
+    cu(cudaMemcpyAsync(out, dout, sizeof(lrr_result) * njobs, cudaMemcpyDeviceToHost, st), "results D2H");
+    cu(cudaMemcpyAsync(decisions, ddec, sizeof(lrr_decision) * njobs, cudaMemcpyDeviceToHost, st), "decisions D2H");
+    cu(cudaStreamSynchronize(st), "registrations");
+    cu(cudaGetLastError(), "registrations");
+    for (int64_t j = 0; j < njobs && rc == LRR_OK; ++j) if (out[j].status < 0) fail(LRR_ERR_STATE, "lrr_batch_run_locations: order-statistic selector overflow in the block kernel");
+  }
+  lrr_batch_loc_args.mode = 0;
+  cudaStreamSynchronize(st);
+  if (work) cudaFreeAsync(work, st); if (djobs) cudaFreeAsync(djobs, st); if (dout) cudaFreeAsync(dout, st); if (ddec) cudaFreeAsync(ddec, st); if (dorder) cudaFreeAsync(dorder, st);
+  return rc;
+}

@@ -91,3 +91,7 @@ struct lrr_est {
 
 // kernels with host-visible extras (lrr_icp.cu / lrr_metrics.cu)
 void lrr_k_weight_ex(const EstArgs& a, const int* scale_mode, const double* scale_in, cudaStream_t st, long long* launches, int spec = 0);
+
+// extra arguments of the block-per-registration launches issued by lrr_batch_run_locations (lrr_batch.cu)
+struct BatchLocArgs { int mode, ncand, until_verified; const int* order; lrr_decision* dec; double spacing; };
+extern thread_local BatchLocArgs lrr_batch_loc_args;

@@ -296,6 +296,54 @@ __device__ void lrr_phase_match_queue_g8(const Scope& scope, const DirArgs& a, c
   scope.phase_end();
 }
 
+// ---- sheet_angles / tube_angles of the rrl estimators (rrl/rrl_estimation_ICP_matching_all.txx:281-375): weighted mean over the
+// SHEET-SHEET (which = 0) / TUBE-TUBE (1) matches of acos |< T-mapped normal / tangent of p, normal / tangent of q >| folded to
+// [0, pi/2].  Scope form for the batched mode (the single-registration path has its own kernel, lrr_metrics.cu).  Result in
+// sc->ang_num / sc->ang_den.
+template <class Scope, class SH>
+__device__ void lrr_phase_angles_rrl(const Scope& scope, const DirArgs& a, int which, SH& sh) {
+  Scal* sc = a.sc;
+  const int want = which == 0 ? 2 : 1;
+  const int mapped = sc->from_mapped;
+  const FsetDev& F = a.from_all; const FsetDev& T = a.to;
+  double acc[2] = {0, 0};
+  if (F.dirs && T.dirs) for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int s = a.sidx[k];
+    if (s < 0) continue;
+    const int i = lrr_from_index(a, k);
+    const int po = a.forig ? a.forig[i] : i;
+    const int qo = lrr_pos4_orig(lrr_ld_pos4(T.grid.pos4 + s));
+    if (F.shape[po] != want || T.shape[qo] != want) continue;
+    double pd[3], qd[3];
+    if (which == 0) {
+      for (int d = 0; d < 3; ++d) { pd[d] = F.dirs[(size_t)d * F.n + po]; qd[d] = T.dirs[(size_t)d * T.n + qo]; }
+    } else {   // tangent = d0 x d1
+      double p0[3], p1[3], q0[3], q1[3];
+      for (int d = 0; d < 3; ++d) {
+        p0[d] = F.dirs[(size_t)d * F.n + po]; p1[d] = F.dirs[(size_t)(3 + d) * F.n + po];
+        q0[d] = T.dirs[(size_t)d * T.n + qo]; q1[d] = T.dirs[(size_t)(3 + d) * T.n + qo];
+      }
+      pd[0] = p0[1] * p1[2] - p0[2] * p1[1]; pd[1] = p0[2] * p1[0] - p0[0] * p1[2]; pd[2] = p0[0] * p1[1] - p0[1] * p1[0];
+      qd[0] = q0[1] * q1[2] - q0[2] * q1[1]; qd[1] = q0[2] * q1[0] - q0[0] * q1[2]; qd[2] = q0[0] * q1[1] - q0[1] * q1[0];
+    }
+    double x, y, z; lrr_from_loc(a, sc, mapped, i, x, y, z);
+    double y0, y1, y2, n0, n1, n2;
+    lrr_map_exact(sc->A, sc->t, sc->c, x, y, z, y0, y1, y2);
+    lrr_map_exact(sc->A, sc->t, sc->c, x + pd[0], y + pd[1], z + pd[2], n0, n1, n2);
+    double d0 = n0 - y0, d1 = n1 - y1, d2 = n2 - y2;
+    const double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    d0 /= nrm; d1 /= nrm; d2 /= nrm;
+    double ang = acos(d0 * qd[0] + d1 * qd[1] + d2 * qd[2]);
+    if (ang > 3.14159265358979323846 / 2) ang = 3.14159265358979323846 - ang;
+    const double w = a.w[k];
+    acc[0] += w * ang; acc[1] += w;
+  }
+  if (scope.template reduce<2>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x == 0) { sc->ang_num = sh.out[0]; sc->ang_den = sh.out[1]; }
+  }
+  scope.phase_end();
+}
+
 // ---- NORM1 / NORM2: cdcl_normalize_matches (cdcl :1159-1240, rrl :864-943).  The std::set of matched
 // fixed features becomes "the match with the lowest position wins the stamp of its to-feature". ----------
 template <class Scope, class SH>

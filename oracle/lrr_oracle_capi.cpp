@@ -309,6 +309,108 @@ static void run_one_job(const lrro_fset* moving_all, const lrro_fset* fixed_all,
   r.rms = est.forward_->RMS_error(); r.weighted_error = est.forward_->weighted_error();
 }
 
+// ---- the driver's candidate loop (rrl/itkLocationRegistration.cxx:2230-2332, 1816-1871) -----------------------------------------
+// ComputeTransferErrorCovariance (:2793-2858): max over a 5 mm grid of the ROI of trace( J(x) Sigma J(x)^T ).  The ROI region of the
+// driver is an image region; here start = centre - half, size = 2 half, end = start + size - spacing.
+static double transfer_max_trace(const Trans& tr, const double* centre, double half, double spacing) {
+  const int dof = tr.dof;
+  const double interval = 5.0;
+  double start[3], end[3];
+  for (int d = 0; d < 3; ++d) { start[d] = centre[d] - half; end[d] = start[d] + 2.0 * half - spacing; }
+  double maxTrace = 0.0;
+  std::vector<double> J(3 * dof);
+  for (double k = start[2]; k <= end[2]; k += interval)
+    for (double j = start[1]; j <= end[1]; j += interval)
+      for (double i = start[0]; i <= end[0]; i += interval) {
+        const double p[3] = {i, j, k};
+        tr.jacobian_wrt_par(p, J.data());
+        double trc = 0.0;
+        for (int d = 0; d < 3; ++d) {
+          double s = 0.0;
+          for (int a = 0; a < dof; ++a) { double v = 0.0; for (int b = 0; b < dof; ++b) v += tr.covar[a * dof + b] * J[d * dof + b]; s += J[d * dof + a] * v; }
+          trc += s;
+        }
+        if (trc > maxTrace) maxTrace = trc;
+      }
+  return maxTrace;
+}
+static const uint64_t kRankStream = 1ULL << 40;   // the ranking find_closest draws its permutation from its own stream (Q4)
+
+// stage 0: ranking angles only; stage 1: the registration (+ decision measurements)
+static void run_candidate(const lrro_fset* moving_all, const lrro_fset* fixed_all, const std::vector<FeatureP>& mall, const std::vector<FeatureP>& fall,
+                          const lrr_job& job, int max_iter, uint64_t seed, double spacing, int stage, lrr_result& r, lrr_decision& dec) {
+  auto in_cube = [&](const Feature& f, const double* c) {
+    for (int d = 0; d < 3; ++d) if (c[d] - job.roi_half_size > f.loc[d] || f.loc[d] > c[d] + job.roi_half_size) return false;
+    return true;
+  };
+  std::vector<FeatureP> mi, fi;
+  for (auto& f : fixed_all->base) if (in_cube(f, job.roi_center_fixed)) fi.push_back(std::make_shared<Feature>(f));
+  for (auto& f : moving_all->base) if (in_cube(f, job.roi_center_moving)) mi.push_back(std::make_shared<Feature>(f));
+  if (stage == 0) { std::memset(&r, 0, sizeof(r)); std::memset(&dec, 0, sizeof(dec)); dec.rank = -1; }
+  r.n_moving_inside = (int)mi.size(); r.n_fixed_inside = (int)fi.size();
+  if (mi.size() < 1000 || fi.size() < 1000) { r.status = 1; return; }
+  auto t = std::make_shared<Trans>(TRANS_AFFINE);
+  std::memcpy(t->A, job.A, 72); std::memcpy(t->t, job.t, 24); std::memcpy(t->c, job.c, 24);
+  SymEst est(FLAVOR_RRL, mall, fall, t, t->inverse(), mi, fi, fixed_all->kd, moving_all->kd);
+  est.forward_->shuffle_mode = est.backward_->shuffle_mode = 1;
+  est.forward_->shuffle_seed = est.backward_->shuffle_seed = seed; est.forward_->shuffle_dir = 0; est.backward_->shuffle_dir = 1;
+  est.set_transform(t);
+  const double deg = 180.0 / 3.14159265358979323846;
+  if (stage == 0) {   // :2303-2313
+    est.forward_->shuffle_calls = est.backward_->shuffle_calls = kRankStream;
+    est.find_closest_euclidean();
+    dec.rank_angles[0] = est.forward_->sheet_angles() * deg; dec.rank_angles[1] = est.forward_->tube_angles() * deg;
+    dec.rank_angles[2] = est.backward_->sheet_angles() * deg; dec.rank_angles[3] = est.backward_->tube_angles() * deg;
+    dec.rank_angle_average = (dec.rank_angles[0] + dec.rank_angles[1] + dec.rank_angles[2] + dec.rank_angles[3]) / 4;
+    return;
+  }
+  bool converged = false; int it = 0;
+  while (!converged && it < max_iter) {
+    converged = est.one_iteration((unsigned)it); ++it;
+    if (!valid_transform(*est.forward_->trans_)) { r.status = 2; break; }
+  }
+  const Trans& T = *est.forward_->trans_;
+  r.converged = converged; r.oscillated = est.oscillated(); r.iterations = it;
+  std::memcpy(r.A, T.A, 72); std::memcpy(r.t, T.t, 24); std::memcpy(r.c, T.c, 24);
+  std::memcpy(r.cov, T.covar.data(), sizeof(double) * 144);
+  r.rms = est.forward_->RMS_error(); r.weighted_error = est.forward_->weighted_error();
+  dec.ran = 1; dec.verified = (r.status == 0 && r.converged && !r.oscillated) ? 1 : 0;
+  if (r.status == 0 && converged && !est.oscillated()) {   // :2495-2507 -> ComputeDecisionMeasurements :1828-1860
+    dec.sheet_angles[0] = est.forward_->sheet_angles() * deg; dec.tube_angles[0] = est.forward_->tube_angles() * deg;
+    dec.weighted_error[0] = est.forward_->weighted_error();
+    dec.max_trace[0] = transfer_max_trace(*est.forward_->trans_, job.roi_center_moving, job.roi_half_size, spacing);
+    est.estimate_LS_backward(false);
+    dec.max_trace[1] = transfer_max_trace(*est.backward_->trans_, job.roi_center_fixed, job.roi_half_size, spacing);
+    dec.sheet_angles[1] = est.backward_->sheet_angles() * deg; dec.tube_angles[1] = est.backward_->tube_angles() * deg;
+    dec.weighted_error[1] = est.backward_->weighted_error();
+    const double* q[4] = {dec.weighted_error, dec.max_trace, dec.sheet_angles, dec.tube_angles};
+    for (int k = 0; k < 4; ++k) { dec.measurements[k] = std::max(q[k][0], q[k][1]); dec.measurements[4 + k] = std::min(q[k][0], q[k][1]); }
+    dec.measured = 1;
+  }
+}
+int lrro_batch_run_locations(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, const lrr_job* jobs, int64_t n_locations, int32_t n_candidates,
+                             int max_iter, uint64_t shuffle_seed, int until_verified, double voxel_spacing, lrr_result* out, lrr_decision* dec) {
+  auto mall = clone_set(moving_all->base); auto fall = clone_set(fixed_all->base);
+  for (int64_t l = 0; l < n_locations; ++l) {
+    std::vector<std::pair<double, int> > cand;
+    for (int c = 0; c < n_candidates; ++c) {
+      const int64_t j = l * n_candidates + c;
+      run_candidate(moving_all, fixed_all, mall, fall, jobs[j], max_iter, shuffle_seed + (uint64_t)j, voxel_spacing, 0, out[j], dec[j]);
+      if (out[j].status == 0) cand.push_back(std::make_pair(dec[j].rank_angle_average, c));
+    }
+    std::stable_sort(cand.begin(), cand.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });   // :2326 (ties: candidate order)
+    bool verified = false;
+    for (size_t k = 0; k < cand.size(); ++k) {
+      const int64_t j = l * n_candidates + cand[k].second;
+      dec[j].rank = (int)k;
+      if (until_verified && verified) continue;   // :2332
+      run_candidate(moving_all, fixed_all, mall, fall, jobs[j], max_iter, shuffle_seed + (uint64_t)j, voxel_spacing, 1, out[j], dec[j]);
+      verified = verified || dec[j].verified;
+    }
+  }
+  return LRR_OK;
+}
+
 // Batched location registration on the CPU.  nthreads <= 0 -> 1 (the reference's execution model).
 int lrro_batch_run_mt(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, const lrr_job* jobs, int64_t njobs,
                       int max_iter, uint64_t shuffle_seed, lrr_result* out, int nthreads) {
