@@ -133,6 +133,16 @@ int64_t lrr_features_size(const lrr_fset* fs);
  * Replaces rsdl_kd_tree::n_nearest(n=1) (cdcl :572) and the Voronoi lookup (rrl :530-543, Q5). */
 int  lrr_features_nearest(lrr_fset* fs, int64_t n_query, const double* q_xyz, int32_t* idx_out);
 
+/* FeaturesInRegions (rrl/itkLocationRegistration.cxx:1363-1522) for one volume, on the device.  labels[i] = region label of feature i:
+ * the caller's watershed over-segmentation looked up at the feature's location (:1407).  From the features inside the cube
+ * [x0, x1], sorted by distance from reference_point (:1297-1311; ties: lowest index), regions are taken in the order of their
+ * nearest feature and all features of a region are added, region after region, until at least min_count (1500, :1487) are in
+ * the set.  idx_out (capacity cap) receives the indices in the reference's order (region after region, nearest first inside a
+ * region), n_out their number.  The complement of FeaturesInROIs, which lrr_est_set_subsets / lrr_batch_run already cover. */
+int  lrr_features_set_labels(lrr_fset* fs, const int32_t* labels);
+int  lrr_features_in_regions(lrr_fset* fs, const double* x0, const double* x1, const double* reference_point, int64_t min_count,
+                             int64_t cap, int32_t* idx_out, int64_t* n_out);
+
 /* ---- estimators ------------------------------------------------------------------------------ */
 /* ctor #3 semantics (cdcl sym .txx:144-164, rrl sym .txx:198-220): forward_ = (moving_inside -> fixed_all),
  * backward_ = (fixed_inside -> moving_all).  Until lrr_est_set_subsets is called the inside sets are

@@ -24,7 +24,7 @@ METRIC = {"rms": 0, "weighted": 1, "median": 2, "sheet_angles": 3, "tube_angles"
 ABI_SYMBOLS = [
     "ctx_create", "ctx_destroy", "ctx_set_stream", "ctx_synchronize", "ctx_last_error", "ctx_launch_count",
     "ctx_set_profiling", "ctx_phase_times",
-    "features_upload", "features_upload_cov", "features_destroy", "features_size", "features_nearest",
+    "features_upload", "features_upload_cov", "features_destroy", "features_size", "features_nearest", "features_set_labels", "features_in_regions",
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
@@ -116,6 +116,7 @@ class Lib:
             "features_upload_cov": (i32, [vp, i32, i64, pd, pd, pd, C.POINTER(vp)]),
             "features_destroy": (None, [vp]), "features_size": (i64, [vp]),
             "features_nearest": (i32, [vp, i64, pd, pi32]),
+            "features_set_labels": (i32, [vp, pi32]), "features_in_regions": (i32, [vp, pd, pd, pd, i64, i64, pi32, C.POINTER(i64)]),
             "est_create": (i32, [vp, i32, i32, i32, vp, vp, C.POINTER(vp)]), "est_destroy": (None, [vp]),
             "est_set_subsets": (i32, [vp, pi32, i64, pi32, i64]),
             "est_set_transform": (i32, [vp, i32, pd, pd, pd, pd]),
@@ -268,6 +269,20 @@ class FeatureSet:
         self.ctx.check(self.ctx.lib.fn("features_nearest")(self.h, nq, _dp(q), out.ctypes.data_as(C.POINTER(C.c_int32))),
                        "features_nearest")
         return out
+
+    def set_labels(self, labels):
+        """region label of every feature (the watershed over-segmentation looked up at its location)"""
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        self._labels = lab
+        self.ctx.check(self.ctx.lib.fn("features_set_labels")(self.h, lab.ctypes.data_as(C.POINTER(C.c_int32))), "features_set_labels")
+
+    def in_regions(self, x0, x1, reference_point, min_count: int = 1500, cap: int = 8192) -> np.ndarray:
+        """FeaturesInRegions for this volume: indices in the reference's order (region after region, nearest first)."""
+        out = np.empty(cap, dtype=np.int32); n = C.c_int64(0)
+        x0 = _f64(x0, (3,)); x1 = _f64(x1, (3,)); rp = _f64(reference_point, (3,))
+        self.ctx.check(self.ctx.lib.fn("features_in_regions")(self.h, _dp(x0), _dp(x1), _dp(rp), min_count, cap, out.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                               C.byref(n)), "features_in_regions")
+        return out[: min(int(n.value), cap)].copy()
 
     def close(self):
         if self.h:

@@ -204,7 +204,7 @@ extern "C" void lrr_features_destroy(lrr_fset* fs) {
   if (!fs) return;
   enter(fs->ctx);
   dfree(fs->xyz); dfree(fs->s); dfree(fs->P6); dfree(fs->C6); dfree(fs->dirs); dfree(fs->shape);
-  dfree(fs->pos4); dfree(fs->rec); dfree(fs->crec); dfree(fs->sorted_of_orig); dfree(fs->cell_start);
+  dfree(fs->labels); dfree(fs->pos4); dfree(fs->rec); dfree(fs->crec); dfree(fs->sorted_of_orig); dfree(fs->cell_start);
   delete fs;
 }
 extern "C" int64_t lrr_features_size(const lrr_fset* fs) { return fs ? fs->n : 0; }

@@ -41,6 +41,7 @@ struct lrr_fset {
   uint8_t* shape = nullptr;
   double4* pos4 = nullptr; double* rec = nullptr; double* crec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
   FsetDev dev;
+  int* labels = nullptr;          // n region labels (watershed over-segmentation at the feature locations) for lrr_features_in_regions, or null
   std::vector<double> host_xyz;   // 3 x n copy for host-side ROI selection (FeaturesInROIs); fetched from the device on first use
 };
 

@@ -6,6 +6,7 @@
 #include <string>
 #include <thread>
 #include <atomic>
+#include <set>
 #include "../include/lrr_gpu.h"
 #include "lrr_oracle_core.hpp"
 
@@ -18,6 +19,7 @@ struct lrro_fset {
   std::shared_ptr<KdTree> kd;
   bool has_cov = false, has_dirs = false;
   int dim = 3;
+  std::vector<int32_t> labels;   // region label per feature (FeaturesInRegions)
 };
 struct lrro_est {
   lrro_ctx* ctx; int kind, dof; lrro_fset *moving_all, *fixed_all;
@@ -102,6 +104,36 @@ void lrro_features_destroy(lrro_fset* fs) { delete fs; }
 int64_t lrro_features_size(const lrro_fset* fs) { return (int64_t)fs->base.size(); }
 int lrro_features_nearest(lrro_fset* fs, int64_t nq, const double* q, int32_t* idx) {
   for (int64_t i = 0; i < nq; ++i) { double p[3] = {q[i], q[nq + i], q[2 * nq + i]}; idx[i] = fs->kd->nearest(p); }
+  return LRR_OK;
+}
+// FeaturesInRegions for one volume (rrl/itkLocationRegistration.cxx:1363-1522), restated literally: features inside the cube with their
+// region labels (:1398-1412), std::sort by distance from the reference point (:1297-1311,1460-1464; ties: lowest index — the
+// reference leaves them to std::sort), labels in the order of their first appearance (:1478-1483), all features of a label added,
+// label after label, while the set holds fewer than min_count (:1487-1495).
+int lrro_features_set_labels(lrro_fset* fs, const int32_t* labels) { fs->labels.assign(labels, labels + fs->base.size()); return LRR_OK; }
+int lrro_features_in_regions(lrro_fset* fs, const double* x0, const double* x1, const double* ref, int64_t min_count, int64_t cap, int32_t* idx_out, int64_t* n_out) {
+  if (fs->labels.size() != fs->base.size()) return LRR_ERR_STATE;
+  struct Item { double d2; int32_t idx; int32_t label; };
+  std::vector<Item> in_roi;
+  for (size_t i = 0; i < fs->base.size(); ++i) {
+    const double* c = fs->base[i].loc;
+    bool inside = true;
+    for (int d = 0; d < 3; ++d) if (x0[d] > c[d] || c[d] > x1[d]) inside = false;
+    if (!inside) continue;
+    const double dx = c[0] - ref[0], dy = c[1] - ref[1], dz = c[2] - ref[2];
+    in_roi.push_back(Item{dx * dx + dy * dy + dz * dz, (int32_t)i, fs->labels[i]});
+  }
+  std::sort(in_roi.begin(), in_roi.end(), [](const Item& a, const Item& b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx); });
+  std::set<int32_t> labels_set; std::vector<int32_t> labels;
+  for (auto& it : in_roi) if (labels_set.insert(it.label).second) labels.push_back(it.label);
+  std::vector<int32_t> inside;
+  auto label_it = labels.begin();
+  while ((int64_t)inside.size() < min_count && label_it != labels.end()) {
+    for (auto& it : in_roi) if (it.label == *label_it) inside.push_back(it.idx);
+    ++label_it;
+  }
+  *n_out = (int64_t)inside.size();
+  for (int64_t i = 0; i < (int64_t)inside.size() && i < cap; ++i) idx_out[i] = inside[(size_t)i];
   return LRR_OK;
 }
 // test hook: brute-force NN (cross-check of the kd-tree, K-f)
