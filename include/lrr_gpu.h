@@ -200,6 +200,15 @@ int  lrr_objcov_eval(lrr_est* est, int dir, const double* x, double* f, double* 
  * by more than 5 %: cdcl/cdcl_lbfgs.h:30-36), Sigma <- U^T U, unnormalise (cdcl/cdcl_estimation.txx:264-337). */
 int  lrr_objcov_refine(lrr_est* est, int dir, int max_evals, double* f_start, double* f_end, int* n_evals);
 
+/* ---- parameter objective of the CDC M-step (cdcl_obj_fun_par<3,12>::compute, cdcl/cdcl_obj_fun_par.txx:46-144) ------------------------
+ * theta = (A row-major, t) (cdcl_trans_affine.txx:65-106); f and g (12 entries) may be NULL.  Evaluated over the current matches /
+ * weights of `dir`; the transfer-error covariances J Sigma J^T are frozen at the direction's current transform and covariance
+ * (the objective's constructor, :27-38); the transform itself is left unchanged. */
+int  lrr_objpar_eval(lrr_est* est, int dir, const double* theta, double* f, double* g);
+/* estimate_parameters(): normalise, L-BFGS over theta (<= max_evals evaluations, 5 % early stop), set_parameterization, unnormalise;
+ * *converged = (f_start - f_end) < 1e-4 (cdcl/cdcl_estimation.txx:207-262). */
+int  lrr_objpar_refine(lrr_est* est, int dir, int max_evals, double* f_start, double* f_end, int* n_evals, int* converged);
+
 /* ---- batched location registration (outer loops of LocationRegistration::Run,
  * rrl/itkLocationRegistration.cxx:2138,2230,2332) ------------------------------------- */
 typedef struct lrr_job {

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
-    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations",
+    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "objpar_eval", "objpar_refine", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations",
 ]
 
 
@@ -132,6 +132,8 @@ class Lib:
             "est_oscillated": (i32, [vp, C.POINTER(i32)]), "est_get_stats": (i32, [vp, C.POINTER(EstStats)]),
             "objcov_eval": (i32, [vp, i32, pd, pd, pd]),
             "objcov_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32)]),
+            "objpar_eval": (i32, [vp, i32, pd, pd, pd]),
+            "objpar_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32), C.POINTER(i32)]),
             "batch_run": (i32, [vp, vp, vp, vp, i64, i32, u64, vp]),
             "batch_run_ids": (i32, [vp, vp, vp, vp, C.POINTER(C.c_int64), i64, i32, u64, vp]),
             "batch_run_locations": (i32, [vp, vp, vp, vp, i64, C.c_int32, i32, u64, i32, dbl, vp, vp]),
@@ -404,6 +406,17 @@ class Estimator:
         fs, fe = np.zeros(1), np.zeros(1); ne = C.c_int(0)
         self._c(self.lib.fn("objcov_refine")(self.h, direction, max_evals, _dp(fs), _dp(fe), C.byref(ne)), "objcov_refine")
         return float(fs[0]), float(fe[0]), int(ne.value)
+
+    def objpar_eval(self, theta, direction=0, want_g=True):
+        """cdcl_obj_fun_par::compute at theta = (A row-major, t): f and the 12 gradient entries"""
+        x = _f64(theta); f = np.zeros(1); g = np.zeros_like(x) if want_g else None
+        self._c(self.lib.fn("objpar_eval")(self.h, direction, _dp(x), _dp(f), _dp(g)), "objpar_eval")
+        return float(f[0]), g
+
+    def objpar_refine(self, max_evals=5, direction=0):
+        fs, fe = np.zeros(1), np.zeros(1); ne = C.c_int(0); cv = C.c_int(0)
+        self._c(self.lib.fn("objpar_refine")(self.h, direction, max_evals, _dp(fs), _dp(fe), C.byref(ne), C.byref(cv)), "objpar_refine")
+        return float(fs[0]), float(fe[0]), int(ne.value), bool(cv.value)
 
     def close(self):
         if self.h:

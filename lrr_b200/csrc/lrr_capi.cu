@@ -1336,6 +1336,78 @@ extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_s
   return LRR_OK;
 }
 
+// ---- parameter objective of the CDC M-step (cdcl_obj_fun_par<3,12>, cdcl/cdcl_obj_fun_par.txx:46-144) --------------------------------
+void lrr_k_objpar_launch(const DirArgs& a, const double* A, const double* t, const double* c, const double* norm8, const double* Sigma_dev,
+                         double* partials, unsigned int* ticket, cudaStream_t st, long long* launches);
+// one evaluation at theta = (A row-major, t) in the frame of T (its centre, its covariance = the frozen Sigma_theta) / norm8
+static int objpar_device_eval(lrr_est* e, int dir, const HostTrans& T, const double* norm8, const double* theta, double* f, double* g) {
+  lrr_ctx* ctx = e->ctx;
+  lrr_dir& d = e->d[dir];
+  double* pin = (double*)ctx->pinned;
+  memcpy(pin, T.cov, sizeof(T.cov));
+  CK(cudaMemcpyAsync(ctx->scratch_d, pin, sizeof(T.cov), cudaMemcpyHostToDevice, ctx->stream));
+  EstArgs a = est_args(e);
+  a.d[dir].M = (int)d.matches;
+  { PHASE(PH_OBJCOV); lrr_k_objpar_launch(a.d[dir], theta, theta + 9, T.c, norm8, ctx->scratch_d, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches); }
+  CK(cudaMemcpyAsync(pin + 256, d.sc->mom, 13 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  const double* mom = pin + 256;
+  const double n = (double)d.matches;
+  if (f) *f = mom[12] / n;
+  if (g) for (int k = 0; k < 12; ++k) g[k] = mom[k] * (1.0 / n);
+  return LRR_OK;
+}
+extern "C" int lrr_objpar_eval(lrr_est* e, int dir, const double* theta, double* f, double* g) {
+  touch(e);
+  int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
+  if (!theta) return LRR_ERR_INVALID;
+  enter(e->ctx);
+  if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;
+  HostTrans T; memcpy(T.A, e->h[dir].A, 72); memcpy(T.t, e->h[dir].t, 24); memcpy(T.c, e->h[dir].c, 24); memcpy(T.cov, e->h[dir].cov, sizeof(T.cov));
+  const double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
+  return objpar_device_eval(e, dir, T, norm8, theta, f, g);
+}
+// estimate_parameters (cdcl/cdcl_estimation.txx:207-262) on the ICP matches of direction `dir`: normalise, L-BFGS over theta
+// (<= max_evals evaluations, the 5 % early stop of cdcl_lbfgs), set_parameterization, unnormalise
+extern "C" int lrr_objpar_refine(lrr_est* e, int dir, int max_evals, double* f_start, double* f_end, int* n_evals, int* converged) {
+  touch(e);
+  int rc = objcov_check(e, dir); if (rc != LRR_OK) return rc;
+  lrr_ctx* ctx = e->ctx; enter(ctx);
+  lrr_dir& d = e->d[dir];
+  double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
+  if (e->normalize) {   // cdcl_normalize_matches over the current matches (:214-217)
+    if ((rc = bump_epoch(e, dir)) != LRR_OK) return rc;
+    EstArgs a = est_args(e, dir);
+    a.d[dir].M = (int)d.matches;
+    a.ndir = 1; if (dir == 1) { a.d[0] = a.d[1]; a.src = 0; }
+    lrr_k_restamp(a, ctx->stream, &ctx->launches);
+    lrr_k_norm1(a, ctx->stream, &ctx->launches); lrr_k_norm2(a, ctx->stream, &ctx->launches);
+  }
+  if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;
+  Scal& h = e->h[dir];
+  HostTrans T; memcpy(T.A, h.A, 72); memcpy(T.t, h.t, 24); memcpy(T.c, h.c, 24); memcpy(T.cov, h.cov, sizeof(T.cov));
+  if (e->normalize) {
+    for (int k = 0; k < 3; ++k) { norm8[k] = h.cfrom[k]; norm8[4 + k] = h.cto[k]; }
+    norm8[3] = h.rfrom; norm8[7] = h.rto;
+    affine_normalize(T, norm8[3], norm8[7], norm8, norm8 + 4);
+  }
+  std::vector<double> x(12);
+  for (int i = 0; i < 9; ++i) x[i] = T.A[i];
+  for (int i = 0; i < 3; ++i) x[9 + i] = T.t[i];
+  double fs = 0, fe = 0; int ev = 0;
+  rc = lbfgs_minimize([&](const double* xx, double* f, double* g) { return objpar_device_eval(e, dir, T, norm8, xx, f, g); }, x, max_evals, &fs, &fe, &ev);
+  if (rc != LRR_OK) return rc;
+  for (int i = 0; i < 9; ++i) T.A[i] = x[i];
+  for (int i = 0; i < 3; ++i) T.t[i] = x[9 + i];
+  if (e->normalize) affine_unnormalize(T, norm8[3], norm8[7], norm8, norm8 + 4);
+  memcpy(h.A, T.A, 72); memcpy(h.t, T.t, 24); memcpy(h.c, T.c, 24); memcpy(h.cov, T.cov, sizeof(T.cov));
+  if ((rc = push_scal(e, dir)) != LRR_OK) return rc;
+  e->werr_cache_valid = false;
+  if (f_start) *f_start = fs; if (f_end) *f_end = fe; if (n_evals) *n_evals = ev; if (converged) *converged = (fs - fe) < 1e-4;
+  return LRR_OK;
+}
+
 // validTransform (rrl/itkLocationRegistration.cxx:2914-2926): singular values of A inside [0.1, 10]
 static bool valid_transform(const double* A) {
   double U[9], V[9], w[3];

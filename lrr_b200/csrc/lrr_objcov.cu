@@ -149,3 +149,121 @@ void lrr_k_objcov_launch(const DirArgs& a, const double* A, const double* t, con
   if (b > cap) b = cap; if (b < 1) b = 1;
   k_objcov<<<(int)b, LRR_OBJ_THREADS, 0, st>>>(a, o, partials, ticket); ++*launches;
 }
+
+// ---- cdcl_obj_fun_par<3,12>::compute (cdcl/cdcl_obj_fun_par.txx:46-144): the parameter objective of the CDC M-step -------------------
+// Same streams, same Cij as above except that the transfer-error covariance J Sigma J^T is frozen at the transform the objective was
+// built with (o.Sigma, :27-38) while A, t are the parameters being evaluated.  With v = Cij^-1 e and the unit-element matrices
+// Mkl = dJp/dth_(3k+l) (cdcl_trans_affine.txx:199-214) the correction terms collapse to rank-one forms:
+//   dCij/dth_(3k+l) = (A Cp)[:,l] e_k^T + e_k (A Cp)[:,l]^T
+//   correct_(3k+l) = -v^T dCij v = -2 v_k (Cp A^T v)_l          correctS_(3k+l) = tr(Cij^-1 dCij) = 2 (Cij^-1 A Cp)_(kl)
+//   g_(3k+l) += w ( rho' (2 x~_l v_k - 2 v_k (Cp A^T v)_l) + 2 (Cij^-1 A Cp)_(kl) ),   g_(9+k) += w rho' 2 v_k      (inliers only, :97)
+// 12 + 1 sums per lane, no exchange between lanes.
+__global__ void __launch_bounds__(LRR_OBJ_THREADS, 2) k_objpar(const __grid_constant__ DirArgs a, const __grid_constant__ ObjArgs o, double* partials, unsigned int* ticket) {
+  __shared__ PhaseShared sh;
+  __shared__ double Bs[10][6];
+  GridScope scope; scope.partials = partials; scope.ticket = ticket;
+  if (threadIdx.x < 60) {
+    const int pair = threadIdx.x / 6, p = threadIdx.x % 6;
+    int aa = 0, bb = 0, cnt = 0;
+    for (int i = 0; i < 4; ++i) for (int j2 = i; j2 < 4; ++j2) { if (cnt == pair) { aa = i; bb = j2; } ++cnt; }
+    const int d = p < 3 ? 0 : (p < 5 ? 1 : 2), e = p < 3 ? p : (p < 5 ? p - 2 : 2);
+    const double s1 = o.Sigma[obj_idx(d, aa) * 12 + obj_idx(e, bb)], s2 = o.Sigma[obj_idx(e, aa) * 12 + obj_idx(d, bb)];
+    Bs[pair][p] = aa == bb ? s1 : s1 + s2;
+  }
+  __syncthreads();
+  Scal* sc = a.sc;
+  const int mapped = sc->from_mapped;
+  const FsetDev& F = a.from_all; const FsetDev& T = a.to;
+  const double irm = 1.0 / o.rm, irf = 1.0 / o.rf, irm2 = irm * irm, irf2 = irf * irf;
+  double acc[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) acc[i] = 0.0;
+  for (int k = scope.first(); k < a.M; k += scope.stride()) {
+    const int s = a.sidx[k];
+    if (s < 0) continue;
+    const int i = lrr_from_index(a, k);
+    const int po = a.forig ? a.forig[i] : i;
+    double px, py, pz; lrr_from_loc(a, sc, mapped, i, px, py, pz);
+    const double4 q4 = lrr_ld_pos4(T.grid.pos4 + s);
+    double Cq[6];
+    {
+      const double2* cr = reinterpret_cast<const double2*>(T.crec + 8 * (size_t)s);
+      const double2 c0 = __ldg(cr), c1 = __ldg(cr + 1), c2 = __ldg(cr + 2);
+      Cq[0] = c0.x * irf2; Cq[1] = c0.y * irf2; Cq[2] = c1.x * irf2; Cq[3] = c1.y * irf2; Cq[4] = c2.x * irf2; Cq[5] = c2.y * irf2;
+    }
+    double Cp[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) Cp[p] = __ldg(F.C6 + (size_t)p * F.n + po) * irm2;
+    const double w = a.w[k];
+    px = (px - o.cm[0]) * irm; py = (py - o.cm[1]) * irm; pz = (pz - o.cm[2]) * irm;
+    const double qx = (q4.x - o.cf[0]) * irf, qy = (q4.y - o.cf[1]) * irf, qz = (q4.z - o.cf[2]) * irf;
+    const double xt[4] = {px - o.c[0], py - o.c[1], pz - o.c[2], 1.0};
+    double AC[9], Cij[6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double a0 = o.A[3 * r], a1 = o.A[3 * r + 1], a2 = o.A[3 * r + 2];
+      AC[3 * r] = a0 * Cp[0] + a1 * Cp[1] + a2 * Cp[2];
+      AC[3 * r + 1] = a0 * Cp[1] + a1 * Cp[3] + a2 * Cp[4];
+      AC[3 * r + 2] = a0 * Cp[2] + a1 * Cp[4] + a2 * Cp[5];
+    }
+    Cij[0] = AC[0] * o.A[0] + AC[1] * o.A[1] + AC[2] * o.A[2] + Cq[0];
+    Cij[1] = AC[0] * o.A[3] + AC[1] * o.A[4] + AC[2] * o.A[5] + Cq[1];
+    Cij[2] = AC[0] * o.A[6] + AC[1] * o.A[7] + AC[2] * o.A[8] + Cq[2];
+    Cij[3] = AC[3] * o.A[3] + AC[4] * o.A[4] + AC[5] * o.A[5] + Cq[3];
+    Cij[4] = AC[3] * o.A[6] + AC[4] * o.A[7] + AC[5] * o.A[8] + Cq[4];
+    Cij[5] = AC[6] * o.A[6] + AC[7] * o.A[7] + AC[8] * o.A[8] + Cq[5];
+    {
+      int pair = 0;
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = aa; bb < 4; ++bb) {
+          const double xx = xt[aa] * xt[bb];
+#pragma unroll
+          for (int p = 0; p < 6; ++p) Cij[p] += xx * Bs[pair][p];
+          ++pair;
+        }
+    }
+    const double c00 = Cij[3] * Cij[5] - Cij[4] * Cij[4], c01 = Cij[2] * Cij[4] - Cij[1] * Cij[5], c02 = Cij[1] * Cij[4] - Cij[2] * Cij[3];
+    const double det = Cij[0] * c00 + Cij[1] * c01 + Cij[2] * c02;
+    const double id = 1.0 / det;
+    const double Ci[6] = {c00 * id, c01 * id, c02 * id, (Cij[0] * Cij[5] - Cij[2] * Cij[2]) * id, (Cij[1] * Cij[2] - Cij[0] * Cij[4]) * id,
+                          (Cij[0] * Cij[3] - Cij[1] * Cij[1]) * id};
+    // err = T(p) - q   (cdcl_obj_fun_par.txx:84)
+    const double e0 = o.A[0] * xt[0] + o.A[1] * xt[1] + o.A[2] * xt[2] + o.t[0] - qx;
+    const double e1 = o.A[3] * xt[0] + o.A[4] * xt[1] + o.A[5] * xt[2] + o.t[1] - qy;
+    const double e2 = o.A[6] * xt[0] + o.A[7] * xt[1] + o.A[8] * xt[2] + o.t[2] - qz;
+    const double v[3] = {Ci[0] * e0 + Ci[1] * e1 + Ci[2] * e2, Ci[1] * e0 + Ci[3] * e1 + Ci[4] * e2, Ci[2] * e0 + Ci[4] * e1 + Ci[5] * e2};
+    const double r = e0 * v[0] + e1 * v[1] + e2 * v[2];
+    const double rp = lrr_rho_p(r);
+    if (!(rp > 0)) continue;   // inliers only: a point may become an outlier during the parameter search (:94-97)
+    acc[12] += w * (lrr_rho(r) + log(det));
+    // u = Cp A^T v = (A Cp)^T v
+    const double u[3] = {AC[0] * v[0] + AC[3] * v[1] + AC[6] * v[2], AC[1] * v[0] + AC[4] * v[1] + AC[7] * v[2], AC[2] * v[0] + AC[5] * v[1] + AC[8] * v[2]};
+    const double Cif[9] = {Ci[0], Ci[1], Ci[2], Ci[1], Ci[3], Ci[4], Ci[2], Ci[4], Ci[5]};
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double Mkl = Cif[3 * kk] * AC[l] + Cif[3 * kk + 1] * AC[3 + l] + Cif[3 * kk + 2] * AC[6 + l];   // (Cij^-1 A Cp)_(kl)
+        acc[3 * kk + l] += w * (rp * (2.0 * xt[l] * v[kk] - 2.0 * v[kk] * u[l]) + 2.0 * Mkl);
+      }
+      acc[9 + kk] += w * rp * 2.0 * v[kk];
+    }
+  }
+  if (scope.reduce<13>(acc, sh.out, sh.tmp)) {
+    if (threadIdx.x < 13) sc->mom[threadIdx.x] = sh.out[threadIdx.x];
+  }
+}
+
+void lrr_k_objpar_launch(const DirArgs& a, const double* A, const double* t, const double* c, const double* norm8, const double* Sigma_dev,
+                         double* partials, unsigned int* ticket, cudaStream_t st, long long* launches) {
+  ObjArgs o;
+  for (int i = 0; i < 9; ++i) o.A[i] = A[i];
+  for (int i = 0; i < 3; ++i) { o.t[i] = t[i]; o.c[i] = c[i]; o.cm[i] = norm8[i]; o.cf[i] = norm8[4 + i]; }
+  o.rm = norm8[3]; o.rf = norm8[7]; o.Sigma = Sigma_dev;
+  long long b = ((long long)a.M + LRR_OBJ_THREADS - 1) / LRR_OBJ_THREADS, cap = (long long)lrr_num_sms() * 2;
+  if (cap > LRR_MAX_BLOCKS) cap = LRR_MAX_BLOCKS;
+  if (b > cap) b = cap; if (b < 1) b = 1;
+  k_objpar<<<(int)b, LRR_OBJ_THREADS, 0, st>>>(a, o, partials, ticket); ++*launches;
+}

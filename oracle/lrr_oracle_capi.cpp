@@ -302,6 +302,36 @@ int lrro_objcov_refine(lrro_est* e, int d, int max_evals, double* f_start, doubl
   return LRR_OK;
 }
 
+// cdcl_obj_fun_par<3,12>::compute over the current matches / weights of direction d, at the parameter vector theta (row-major A, then
+// t; cdcl_trans_affine.txx:65-106), with the transfer-error covariances frozen at the direction's current transform.  The transform
+// itself is left as it was.
+int lrro_objpar_eval(lrro_est* e, int d, const double* theta, double* f, double* g) {
+  FwdEst* fe = e->dir(d); if (!fe || fe->trans_->dof != 12) return LRR_ERR_UNSUPPORTED;
+  Trans saved = *fe->trans_;
+  ObjFunPar obj(fe->matches_, *fe->trans_);
+  obj.compute(theta, f, g);
+  *fe->trans_ = saved;
+  return LRR_OK;
+}
+// estimate_parameters (cdcl/cdcl_estimation.txx:207-262) on the ICP matches of direction d: normalise, L-BFGS over theta (<= max_evals
+// evaluations, 5 % early stop of cdcl_lbfgs), set_parameterization, unnormalise.  converged = (f_start - f_end) < 1e-4 (:239).
+int lrro_objpar_refine(lrro_est* e, int d, int max_evals, double* f_start, double* f_end, int* n_evals, int* converged) {
+  FwdEst* fe = e->dir(d); if (!fe || fe->trans_->dof != 12) return LRR_ERR_UNSUPPORTED;
+  Trans& tr = *fe->trans_;
+  double cm[3] = {0, 0, 0}, cf[3] = {0, 0, 0}, rm = 0, rf = 0;
+  if (fe->normalize_matches_) { fe->normalize_matches_fn(cm, rm, cf, rf); tr.normalize(rm, rf, cm, cf); }
+  ObjFunPar obj(fe->matches_, tr);
+  std::vector<double> x(12);
+  for (int i = 0; i < 9; ++i) x[i] = tr.A[i];
+  for (int i = 0; i < 3; ++i) x[9 + i] = tr.t[i];
+  double fs = 0, fe_ = 0;
+  int ev = lbfgs_minimize([&](const double* xx, double* f, double* g) { obj.compute(xx, f, g); }, x, max_evals, &fs, &fe_);
+  tr.set_parameterization(x.data());
+  if (fe->normalize_matches_) { tr.unnormalize(rm, rf, cm, cf); fe->unnormalize_matches_fn(cm, rm, cf, rf); }
+  if (f_start) *f_start = fs; if (f_end) *f_end = fe_; if (n_evals) *n_evals = ev; if (converged) *converged = (fs - fe_) < 1e-4;
+  return LRR_OK;
+}
+
 // validTransform (rrl/itkLocationRegistration.cxx:2914-2926)
 static bool valid_transform(const Trans& t) {
   double w[3]; svd_singular_values(3, t.A, w);

@@ -1119,6 +1119,70 @@ struct ObjFunCov {
 };
 
 // ----------------------------------------------------------------------------------------------
+// cdcl_obj_fun_par<3,12>::compute (cdcl/cdcl_obj_fun_par.txx:20-144): the parameter objective of the CDC M-step, dense and literal.
+// The transfer-error covariances J Sigma_theta J^T are frozen at construction (:27-38); compute() sets the parameters (:52), then
+// for every match  Cij = JCthJ + Jp Cp Jp^T + Cq,  r = e^T Cij^-1 e,  and only for inliers (rho'(r) > 0, :97)
+//   f += w (rho(r) + ln det Cij)
+//   g += w ( rho'(r) (2 Jth^T Cij^-1 e + correct) + correctS ),  correct_f = -v^T dCij/dth_f v,  correctS_f = tr(Cij^-1 dCij/dth_f),
+//   dCij/dth_f = Jp Cp Mkl^T + Mkl Cp Jp^T,  Mkl = d Jp / d th_f = unit matrix element (k,l), f = 3k + l  (affine.txx:199-214).
+struct ObjFunPar {
+  const std::vector<Match>& matches_;
+  Trans& trans_;
+  std::vector<double> JCthJ_;   // 9 per match
+  ObjFunPar(const std::vector<Match>& matches, Trans& trans) : matches_(matches), trans_(trans) {
+    const int dof = trans_.dof;
+    std::vector<double> J(3 * dof), T(3 * dof);
+    JCthJ_.resize(matches_.size() * 9);
+    for (size_t i = 0; i < matches_.size(); ++i) {
+      trans_.jacobian_wrt_par(matches_[i].from->loc, J.data());
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < dof; ++b) { double s = 0; for (int k = 0; k < dof; ++k) s += J[a * dof + k] * trans_.covar[k * dof + b]; T[a * dof + b] = s; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < dof; ++k) s += T[a * dof + k] * J[b * dof + k]; JCthJ_[i * 9 + a * 3 + b] = s; }
+    }
+  }
+  void compute(const double* x, double* f, double* g) {
+    const int dof = trans_.dof;
+    trans_.set_parameterization(x);
+    const double* Jp = trans_.A;
+    double fv = 0.0;
+    std::vector<double> gv(dof, 0.0), J(3 * dof);
+    for (size_t i = 0; i < matches_.size(); ++i) {
+      const Feature& p = *matches_[i].from; const Feature& q = *matches_[i].to;
+      trans_.jacobian_wrt_par(p.loc, J.data());
+      double JC[9], Cij[9];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += Jp[a * 3 + k] * p.cov[k * 3 + b]; JC[a * 3 + b] = s; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += JC[a * 3 + k] * Jp[b * 3 + k]; Cij[a * 3 + b] = JCthJ_[i * 9 + a * 3 + b] + s + q.cov[a * 3 + b]; }
+      double Ci[9]; inv3(Cij, Ci);
+      double y[3]; trans_.map_loc(p.loc, y);
+      const double err[3] = {y[0] - q.loc[0], y[1] - q.loc[1], y[2] - q.loc[2]};
+      double v[3]; for (int a = 0; a < 3; ++a) v[a] = Ci[a * 3] * err[0] + Ci[a * 3 + 1] * err[1] + Ci[a * 3 + 2] * err[2];
+      const double residual = err[0] * v[0] + err[1] * v[1] + err[2] * v[2];
+      const double w = matches_[i].w;
+      const double rp = rho_p(residual);
+      const bool inlier = rp > 0;
+      if (f && inlier) fv += w * (rho(residual) + std::log(det3(Cij)));
+      if (g && inlier) {
+        for (int fi = 0; fi < dof; ++fi) {
+          double corr = 0.0, corrS = 0.0;
+          if (fi < dof - 3) {
+            const int k = fi / 3, l = fi % 3;
+            double dC[9];   // Jp Cp Mkl^T + Mkl Cp Jp^T : (Jp Cp)[:, l] e_k^T + e_k (Jp Cp)[:, l]^T
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) dC[a * 3 + b] = (b == k ? JC[a * 3 + l] : 0.0) + (a == k ? JC[b * 3 + l] : 0.0);
+            double vdv = 0.0, tr = 0.0;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { vdv += v[a] * dC[a * 3 + b] * v[b]; tr += Ci[a * 3 + b] * dC[b * 3 + a]; }
+            corr = -vdv; corrS = tr;
+          }
+          const double jtv = J[0 * dof + fi] * v[0] + J[1 * dof + fi] * v[1] + J[2 * dof + fi] * v[2];
+          gv[fi] += w * (rp * (jtv * 2.0 + corr) + corrS);
+        }
+      }
+    }
+    const double n = (double)matches_.size();
+    if (f) *f = fv / n;
+    if (g) for (int k = 0; k < dof; ++k) g[k] = gv[k] * (1.0 / n);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
 // L-BFGS (stands in for vnl_lbfgs = v3p netlib lbfgs, Nocedal; m = 5, backtracking Armijo/Wolfe line
 // search) with cdcl_lbfgs::report_iter's early stop: finish as soon as |f_start - f| > 5 % |f_start|
 // (cdcl/cdcl_lbfgs.h:30-36) and at most max_evals evaluations (cdcl/cdcl_estimation.txx:299).

@@ -102,6 +102,7 @@ int lrrr_est_transfer_cov(lrrr_est* e, int d, double* S9) { return e->impl->tran
 int lrrr_est_get_state(lrrr_est* e, lrr_est_state* s) { e->impl->get_state(s); return LRR_OK; }
 int lrrr_est_oscillated(lrrr_est* e, int* out) { *out = e->impl->oscillated(); return LRR_OK; }
 int lrrr_objcov_eval(lrrr_est* e, int d, const double* x, double* f, double* g) { return e->impl->objcov_eval(d, x, f, g) ? LRR_OK : LRR_ERR_UNSUPPORTED; }
+int lrrr_objpar_eval(lrrr_est* e, int d, const double* x, double* f, double* g) { return e->impl->objpar_eval(d, x, f, g) ? LRR_OK : LRR_ERR_UNSUPPORTED; }
 
 double lrrr_test_weight_BT(double u) { return lrr_ref_weight_BT(u); }
 double lrrr_test_rho(double u) { return lrr_ref_rho(u); }

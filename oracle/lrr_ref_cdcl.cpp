@@ -1,6 +1,6 @@
 // lrr_ref_cdcl.cpp — compiles the reference's cdcl estimators UNMODIFIED from /root/reference.  TEST INFRASTRUCTURE ONLY.
 // Reference sources pulled in by #include (never copied): cdcl/cdcl_trans.txx, cdcl_trans_affine.txx, cdcl_trans_rigid3d.cxx,
-// cdcl_estimation_ICP_matching_all.txx, cdcl_estimation_symmetric_ICP_matching_all.txx, cdcl_obj_fun_cov.txx (+ their headers).
+// cdcl_estimation_ICP_matching_all.txx, cdcl_estimation_symmetric_ICP_matching_all.txx, cdcl_obj_fun_cov.txx, cdcl_obj_fun_par.txx (+ their headers).
 #include "vxl_shim/vcl_shim_all.h"
 #include "vxl_shim/vnl/algo/vnl_shim_algo.h"
 #include "vxl_shim/rsdl/rsdl_kd_tree.h"
@@ -14,6 +14,7 @@
 #include <cdcl/cdcl_estimation_ICP_matching_all.txx>
 #include <cdcl/cdcl_estimation_symmetric_ICP_matching_all.txx>
 #include <cdcl/cdcl_obj_fun_cov.txx>
+#include <cdcl/cdcl_obj_fun_par.txx>
 #undef protected
 #undef private
 #include "lrr_ref_impl.hpp"
@@ -56,6 +57,28 @@ struct CdclPolicy {
     obj.compute(xv, &fv, &gv);
     if (f) *f = fv;
     if (g) for (unsigned k = 0; k < n; ++k) g[k] = gv[k];
+    return true;
+  }
+  // cdcl_obj_fun_par<3,dof>::compute over the same matches (the objective of the CDC M-step, cdcl/cdcl_obj_fun_par.txx:46-144)
+  template <unsigned dof, class F> static bool objpar(F& fe, const double* x, double* f, double* g) {
+    typedef cdcl_feature<3> bf; typedef cdcl_match<3> bm;
+    std::vector<bm::sptr> ms;
+    for (size_t i = 0; i < fe.matches_.size(); ++i) {
+      bm::sptr m = new bm;
+      m->from_ = new bf(fe.matches_[i]->from_->location_, fe.matches_[i]->from_->strength_, fe.matches_[i]->from_->covariance_);
+      for (size_t j = 0; j < fe.matches_[i]->to_.size(); ++j) {
+        m->to_.push_back(new bf(fe.matches_[i]->to_[j]->location_, fe.matches_[i]->to_[j]->strength_, fe.matches_[i]->to_[j]->covariance_));
+        m->w_.push_back(fe.matches_[i]->w_[j]);
+      }
+      ms.push_back(m);
+    }
+    typename cdcl_trans<3, dof>::sptr t = fe.get_transform()->clone();
+    cdcl_obj_fun_par<3, dof> obj(ms, t);
+    vnl_vector<double> xv(x, dof), gv(dof, 0.0);
+    double fv = 0;
+    obj.compute(xv, &fv, &gv);
+    if (f) *f = fv;
+    if (g) for (unsigned k = 0; k < dof; ++k) g[k] = gv[k];
     return true;
   }
 };

@@ -123,6 +123,7 @@ struct RefIcp2d : RefEst {
   }
   int oscillated() override { return 0; }
   bool objcov_eval(int, const double*, double*, double*) override { return false; }
+  bool objpar_eval(int, const double*, double*, double*) override { return false; }
 };
 }  // namespace
 

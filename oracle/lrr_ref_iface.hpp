@@ -31,6 +31,7 @@ struct RefEst {
   virtual void get_state(lrr_est_state* s) = 0;
   virtual int oscillated() = 0;
   virtual bool objcov_eval(int dir, const double* x, double* f, double* g) = 0;
+  virtual bool objpar_eval(int dir, const double* theta, double* f, double* g) = 0;
 };
 
 RefEst* lrr_ref_make_cdcl(int kind, int dof, const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);

@@ -153,5 +153,9 @@ struct RefEstImpl : RefEst {
     fwd_type* fe = dir(d); if (!fe) return false;
     return P::template objcov<dof>(*fe, x, f, g);
   }
+  bool objpar_eval(int d, const double* x, double* f, double* g) override {
+    fwd_type* fe = dir(d); if (!fe) return false;
+    return P::template objpar<dof>(*fe, x, f, g);
+  }
 };
 #endif

@@ -55,6 +55,7 @@ struct RrlPolicy {
     s.set_voronoi_maps(x.map_moving, x.map_fixed);
   }
   template <unsigned dof, class F> static bool objcov(F&, const double*, double*, double*) { return false; }
+  template <unsigned dof, class F> static bool objpar(F&, const double*, double*, double*) { return false; }
 };
 
 RefEst* lrr_ref_make_rrl(int kind, int dof, const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed) {

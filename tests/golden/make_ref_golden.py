@@ -73,6 +73,13 @@ def run_case(lib, pair, kind, dof, iters=ITERS, with_objcov=True):
         for tag, xx in (("x0", x), ("x1", x2)):
             f, g = est.objcov_eval(xx, 0)
             out[f"objcov_{tag}"], out[f"objcov_{tag}_f"], out[f"objcov_{tag}_g"] = xx, np.array([f]), g
+        # cdcl_obj_fun_par<3,12>::compute at the estimated parameters and at perturbed ones (some matches turn into outliers)
+        T = est.get_transform(0)
+        th = np.concatenate([T["A"].reshape(9), T["t"]])
+        th2 = th + np.concatenate([0.002 * rng.standard_normal(9), 0.5 * rng.standard_normal(3)])
+        for tag, xx in (("x0", th), ("x1", th2)):
+            f, g = est.objpar_eval(xx, 0)
+            out[f"objpar_{tag}"], out[f"objpar_{tag}_f"], out[f"objpar_{tag}_g"] = xx, np.array([f]), g
     if "sym" in kind:
         # estimate_LS_backward(false): decision-measurement path of the driver (rrl/itkLocationRegistration.cxx:1840), followed by
         # the metrics the driver reads next (:1842-1845).  cdcl symmetric <3,6>: the rigid branch (cdcl sym :708-731, :856-862) maps

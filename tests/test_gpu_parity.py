@@ -195,6 +195,30 @@ def test_objcov(gpu_lib, oracle_lib, pair):
     assert rel(Tg["cov"], To["cov"]) < TOL_PARAM and rel(Tg["A"], To["A"]) < 1e-12 and rel(Tg["t"], To["t"]) < 1e-12
 
 
+def test_objpar(gpu_lib, oracle_lib, pair):
+    """cdcl_obj_fun_par<3,12>::compute (cdcl/cdcl_obj_fun_par.txx:46-144) and estimate_parameters (cdcl/cdcl_estimation.txx:207-262)
+    on the device: f 1e-9, the 12 gradient entries 1e-8, refined parameters 1e-5 against the oracle (itself pinned to the compiled
+    reference, tests/test_reference_pin.py::test_objpar_matches_reference)."""
+    _, g = make_est(gpu_lib, pair, "cdcl_fwd", number_points=5000)
+    _, o = make_est(oracle_lib, pair, "cdcl_fwd", number_points=5000)
+    for it in range(3):
+        g.one_iteration(it); o.one_iteration(it)
+    T = o.get_transform(0)
+    th = np.concatenate([T["A"].reshape(9), T["t"]])
+    rng = np.random.default_rng(4)
+    for trial in range(3):
+        xx = th + (np.concatenate([0.002 * rng.normal(size=9), 0.5 * rng.normal(size=3)]) if trial else 0.0)
+        fg_, gg = g.objpar_eval(xx); fo, go = o.objpar_eval(xx)
+        assert abs(fg_ - fo) <= 1e-9 * max(1.0, abs(fo)), (fg_, fo)
+        assert rel(gg, go) < 1e-8, rel(gg, go)
+    Tb = g.get_transform(0)
+    assert rel(Tb["A"], T["A"]) < 1e-12   # evaluation leaves the transform alone
+    rg, ro = g.objpar_refine(5), o.objpar_refine(5)
+    assert rg[2] == ro[2] and rg[3] == ro[3] and abs(rg[0] - ro[0]) <= 1e-9 * max(1.0, abs(ro[0])) and abs(rg[1] - ro[1]) <= 1e-7 * max(1.0, abs(ro[1])), (rg, ro)
+    Tg, To = g.get_transform(0), o.get_transform(0)
+    assert rel(Tg["A"], To["A"]) < TOL_PARAM and rel(Tg["t"], To["t"]) < TOL_PARAM and rel(Tg["cov"], To["cov"]) < TOL_PARAM
+
+
 def test_cpp_host_api():
     """The header-only C++ mirror of the reference template API (include/lrr/lrr_estimators.h) drives the C ABI."""
     import os, subprocess

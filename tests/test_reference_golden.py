@@ -45,7 +45,7 @@ def check(lib, kind, dof, rigid, tol_param, tol_tight):
                 assert np.allclose(o, g, rtol=1e-6, atol=1e-9), (k, o, g)      # error_difference is a difference of near-equal values
             else:
                 assert rel(o, g) < tol_tight, (k, rel(o, g))
-        elif k.startswith("objcov_x"):
+        elif k.startswith("objcov_x") or k.startswith("objpar_x"):
             pass   # inputs of the objective, derived from the covariance checked above
         else:
             raise AssertionError(f"unclassified golden key {k}")

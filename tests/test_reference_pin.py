@@ -133,6 +133,30 @@ def test_objcov_matches_reference(oracle_lib, ref_lib):
         assert rel(go, gr) < 1e-9
 
 
+def test_objpar_matches_reference(oracle_lib, ref_lib):
+    """cdcl_obj_fun_par<3,12>::compute (cdcl/cdcl_obj_fun_par.txx:46-144): f and all 12 gradient entries, at the current parameters
+    and at perturbed ones (some matches become outliers: the `inlier` branch, :97)."""
+    pair = synth.make_pair(63, 2500, 2200)
+    o, r = make(oracle_lib, pair, "cdcl_fwd", 12), make(ref_lib, pair, "cdcl_fwd", 12)
+    for it in range(3):
+        o.one_iteration(it); r.one_iteration(it)
+    T = r.get_transform(0)
+    x = np.concatenate([T["A"].reshape(9), T["t"]])
+    rng = np.random.default_rng(2)
+    for xx in (x, x + np.concatenate([0.002 * rng.standard_normal(9), 0.5 * rng.standard_normal(3)])):
+        fo, go = o.objpar_eval(xx, 0)
+        fr, gr = r.objpar_eval(xx, 0)
+        assert fo == pytest.approx(fr, rel=1e-10)
+        assert rel(go, gr) < 1e-9
+    # finite differences of the oracle's f (the gradient omits the inlier-set boundary, so a small step on a smooth stretch)
+    f0, g0 = o.objpar_eval(x, 0)
+    for k in (0, 4, 9, 11):
+        h = 1e-6 * max(1.0, abs(x[k]))
+        xp, xm = x.copy(), x.copy(); xp[k] += h; xm[k] -= h
+        fd = (o.objpar_eval(xp, 0, want_g=False)[0] - o.objpar_eval(xm, 0, want_g=False)[0]) / (2 * h)
+        assert abs(fd - g0[k]) <= 1e-4 * max(1.0, abs(g0[k])), (k, fd, g0[k])
+
+
 @pytest.mark.parametrize("u", [0.0, 0.5, 1.0, 4.0, 15.99, 16.0, 16.01, 100.0])
 def test_robust_kernels_match_reference(oracle_lib, ref_lib, u):
     """weight_BT / rho / rho_p (cdcl/cdcl_utils.h:142-204)."""
