@@ -15,6 +15,20 @@ est.set_transform(A, t, c)
 if "fwd" in kind:
     est.set_flags(True, True); est.set_number_points(n)
 it, conv = 0, False
+inreg = os.environ.get("LRR_PROF_INREG")   # ncu --profile-from-start off: capture the finest-level iterations INSIDE the registration (2nd onwards)
+if inreg:
+    import torch
+    started = False
+    while not conv and it < 70:
+        fin = bool(est.state().finest_level)
+        if fin and not started and int(inreg) <= 1:       # LRR_PROF_INREG=1: from the first finest-level iteration (no certificates yet)
+            ctx.synchronize(); torch.cuda.cudart().cudaProfilerStart(); started = True
+        conv = est.one_iteration(it); it += 1
+        if fin and not started:                           # LRR_PROF_INREG=2: from the second one (certificates in place, transform moving)
+            ctx.synchronize(); torch.cuda.cudart().cudaProfilerStart(); started = True
+    ctx.synchronize(); torch.cuda.cudart().cudaProfilerStop()
+    print("in-registration capture: iterations", it, "converged", conv, "launches", ctx.launch_count())
+    sys.exit(0)
 while not conv and it < 70:
     conv = est.one_iteration(it); it += 1
 print("ramp iterations", it, "converged", conv, "launches", ctx.launch_count())
