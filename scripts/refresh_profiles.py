@@ -3,11 +3,12 @@ ncu --set full summary (selected metrics per kernel) and the DRAM bytes per laun
 import csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 T = sys.argv[1]
+R = sys.argv[2] if len(sys.argv) > 2 else T[:2]   # round prefix of the files under profiles/ (r1, r2, ...)
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-shutil.copy(f"{G}/{T}_bench.json", f"{P}/r1_bench_line.json")
-shutil.copy(f"{G}/{T}_ref.json", f"{P}/r1_bench_line_reference_arm.json")
-shutil.copy(f"{G}/{T}_launches.csv", f"{P}/r1_launches_bench.csv")
-open(f"{P}/r1_launch_list_bench.txt", "w").write(subprocess.run([sys.executable, f"{ROOT}/scripts/launch_list.py", f"{G}/{T}_launches.csv"], capture_output=True, text=True).stdout)
+shutil.copy(f"{G}/{T}_bench.json", f"{P}/{R}_bench_line.json")
+shutil.copy(f"{G}/{T}_ref.json", f"{P}/{R}_bench_line_reference_arm.json")
+shutil.copy(f"{G}/{T}_launches.csv", f"{P}/{R}_launches_bench.csv")
+open(f"{P}/{R}_launch_list_bench.txt", "w").write(subprocess.run([sys.executable, f"{ROOT}/scripts/launch_list.py", f"{G}/{T}_launches.csv"], capture_output=True, text=True).stdout)
 raw = subprocess.run(["ncu", "-i", f"{G}/prof_{T}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(raw.splitlines())); h, u = r[0], r[1]
 want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "smsp__inst_executed.sum",
@@ -17,7 +18,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
 idx = [h.index(w) for w in want]
 scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Gbyte": 1e9}
 tr = {}
-with open(f"{P}/r1_ncu_full_top_kernels.csv", "w", newline="") as f:
+with open(f"{P}/{R}_ncu_full_top_kernels.csv", "w", newline="") as f:
     w = csv.writer(f); w.writerow(want); w.writerow([u[i] for i in idx])
     for row in r[2:]:
         w.writerow([row[i] for i in idx])
@@ -26,6 +27,27 @@ with open(f"{P}/r1_ncu_full_top_kernels.csv", "w", newline="") as f:
         tr[name] = by
         print(name, row[h.index("gpu__time_duration.sum")], "us", row[h.index("launch__registers_per_thread")], "regs", round(by / 1e6, 2), "MB",
               row[h.index("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")], "% dram")
-json.dump({"source": "ncu --set full --clock-control none of scripts/prof_iter.py 100000 1 (LRR_PROF_RANGE, LRR_PROF_SETTLE=15: one steady-state "
-           "finest-level iteration), profiles/r1_ncu_full_top_kernels.csv; cold caches under ncu replay", "dram_bytes_per_launch": tr},
+tr_fixed = dict(tr)
+# the in-registration capture (LRR_PROF_INREG=2: finest-level iterations 2.. of the ramped registration, transform still moving)
+inreg = f"{G}/prof_{T}_inreg.ncu-rep"
+tr_in = {}
+if os.path.exists(inreg):
+    raw = subprocess.run(["ncu", "-i", inreg, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(raw.splitlines())); h, u = r[0], r[1]
+    idx = [h.index(w) for w in want]
+    agg = {}
+    with open(f"{P}/{R}_ncu_full_inreg_kernels.csv", "w", newline="") as f:
+        w = csv.writer(f); w.writerow(want); w.writerow([u[i] for i in idx])
+        for row in r[2:]:
+            w.writerow([row[i] for i in idx])
+            name = row[h.index("Kernel Name")].split("(")[0]
+            by = sum(float(row[h.index(m)]) * scale[u[h.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            a = agg.setdefault(name, [0, 0.0, 0.0]); a[0] += 1; a[1] += by; a[2] += float(row[h.index("gpu__time_duration.sum")])
+    print("in-registration capture:")
+    for name, (cnt, by, us) in agg.items():
+        tr_in[name] = by / cnt
+        print(f"  {name}: {cnt} launches, {us / cnt:.1f} us, {by / cnt / 1e6:.2f} MB per launch")
+json.dump({"source": f"ncu --set full --clock-control none of scripts/prof_iter.py 100000 1; cold caches under ncu replay. in_registration: LRR_PROF_INREG=2, "
+           f"finest-level iterations 2.. of the ramped registration (profiles/{R}_ncu_full_inreg_kernels.csv); fixed_point: LRR_PROF_RANGE, LRR_PROF_SETTLE=15 "
+           f"(profiles/{R}_ncu_full_top_kernels.csv)", "dram_bytes_per_launch": tr_in or tr_fixed, "dram_bytes_per_launch_fixed_point": tr_fixed},
           open(f"{P}/ncu_traffic.json", "w"), indent=1)
