@@ -10,6 +10,8 @@
 #include "vxl_shim/rrel/rrel_muset_obj.h"
 #include "vxl_shim/itk/itkMultiThreader.h"
 #include <unordered_map>
+#include <cstdlib>
+#include <thread>
 #define protected public
 #define private public
 #include <cdcl/cdcl_trans.txx>
@@ -19,6 +21,10 @@
 #undef protected
 #undef private
 #include "lrr_ref_impl.hpp"
+
+#include <chrono>
+static double g_raster_seconds = 0.0;   // wall time spent building rasterised Voronoi maps (bench.py subtracts it: an input file upstream)
+extern "C" double lrrr_voronoi_raster_seconds() { return g_raster_seconds; }
 
 struct RrlPolicy {
   typedef cdcl_feature_ICP<3> feature_type;
@@ -38,6 +44,33 @@ struct RrlPolicy {
     kd = new rsdl_kd_tree(pts);
     rsdl_kd_tree* tree = kd.as_pointer();
     map_type::Pointer m = map_type::New();
+    if (const char* mode = std::getenv("LRR_REF_VORONOI"); mode && std::string(mode) == "raster") {
+      // TIMING ONLY (bench.py's second cpu_baseline figure): the stock reference's O(1) lookup in a rasterised 1 mm label volume
+      // (rrl/examples/compute_distance_map.cxx builds it offline; here every voxel gets the exact nearest feature of its centre,
+      // all host threads, untimed set-up like the reference's input file)
+      const auto t_begin = std::chrono::steady_clock::now();
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (size_t i = 0; i < set.size(); ++i) for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], set[i]->location_[d]); hi[d] = std::max(hi[d], set[i]->location_[d]); }
+      unsigned long dims[3]; double org[3];
+      for (int d = 0; d < 3; ++d) { org[d] = std::floor(lo[d]) - 8.0; dims[d] = (unsigned long)(std::ceil(hi[d]) + 8.0 - org[d]) + 1; }
+      m->SetRaster(dims, org, 1.0);
+      std::vector<unsigned int>& data = m->Data();
+      unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+        rsdl_kd_tree own(pts);   // (the stand-in's search keeps its scratch in the tree object: one tree per thread)
+        rsdl_kd_tree* tree = &own;
+        rsdl_point q(3, 0); std::vector<rsdl_point> cp; std::vector<int> ci; double p[3];
+        for (unsigned long z = t; z < dims[2]; z += nt) for (unsigned long y = 0; y < dims[1]; ++y) for (unsigned long x = 0; x < dims[0]; ++x) {
+          p[0] = org[0] + (double)x; p[1] = org[1] + (double)y; p[2] = org[2] + (double)z;
+          q.set_cartesian(p); tree->n_nearest(q, 1, cp, ci);
+          data[(z * dims[1] + y) * dims[0] + x] = (unsigned int)ci[0];
+        }
+      });
+      for (auto& x : th) x.join();
+      g_raster_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+      return m;
+    }
     m->SetLookup([tree](const double* p) -> unsigned int {
       rsdl_point q(3, 0); q.set_cartesian(p);
       std::vector<rsdl_point> cp; std::vector<int> ci;

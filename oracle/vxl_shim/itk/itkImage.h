@@ -8,11 +8,17 @@
 // (north_star item 2).  This stand-in therefore models an *ideal* Voronoi map: an unbounded image whose pixel at a
 // physical point is the index of that point's exact nearest feature.  TransformPhysicalPointToIndex keeps the
 // continuous point alongside the (never clamped) integer index and GetPixel evaluates the lookup function.
+//
+// TIMING-ONLY second mode (SetRaster): a real rasterised 1 mm label volume with an O(1) voxel lookup, which is what the stock
+// reference runs (rrl/rrl_estimation_ICP_matching_all.txx:530-543; USE_KD_TREE is never defined, Q5) — so that the CPU baseline
+// bench.py reports is not slower than the stock path.  Its match sets differ from the exact neighbour where a
+// 1 mm voxel straddles a Voronoi face, so it is never used for parity.
 #ifndef itkImage_shim_h_
 #define itkImage_shim_h_
 #include <cstddef>
 #include <functional>
 #include <memory>
+#include <vector>
 namespace itk {
 
 template <class T> class SmartPointer {
@@ -71,17 +77,37 @@ template <class TPixel, unsigned N> class Image {
   typedef std::function<TPixel(const double*)> LookupType;
   static Pointer New() { return Pointer(new Self); }
   void SetLookup(LookupType f) { lookup_ = f; }
+  // rasterised mode: `dims` voxels of `spacing` mm from `origin` (voxel centres), x fastest; the caller fills Data()
+  void SetRaster(const unsigned long* dims, const double* origin, double spacing) {
+    raster_ = true; spacing_ = spacing;
+    size_t n = 1;
+    for (unsigned d = 0; d < N; ++d) { region_.size[d] = dims[d]; origin_[d] = origin[d]; n *= dims[d]; }
+    data_.assign(n, TPixel());
+  }
+  std::vector<TPixel>& Data() { return data_; }
   const RegionType& GetLargestPossibleRegion() const { return region_; }
   template <class TCoord> bool TransformPhysicalPointToIndex(const itk::Point<TCoord, N>& p, IndexType& idx) const {
+    if (raster_) {   // itk::Image: index = round((p - origin) / spacing); the caller clamps it to the region (:537-540)
+      bool inside = true;
+      for (unsigned d = 0; d < N; ++d) {
+        idx.physical[d] = p[d]; idx[d] = (IndexValueType)std::floor((p[d] - origin_[d]) / spacing_ + 0.5);
+        inside = inside && idx[d] >= 0 && idx[d] < (IndexValueType)region_.size[d];
+      }
+      return inside;
+    }
     for (unsigned d = 0; d < N; ++d) { idx.physical[d] = p[d]; idx[d] = half_ + (IndexValueType)std::llround(p[d]); }
     return true;
   }
-  TPixel GetPixel(const IndexType& idx) const { return lookup_(idx.physical); }
+  TPixel GetPixel(const IndexType& idx) const {
+    if (raster_) { size_t o = 0; for (unsigned d = N; d-- > 0;) o = o * region_.size[d] + (size_t)idx[d]; return data_[o]; }
+    return lookup_(idx.physical);
+  }
  private:
   Image() { for (unsigned d = 0; d < N; ++d) { region_.size[d] = 2ul * (unsigned long)half_; region_.index[d] = 0; } }
   static const long half_ = 1l << 40;   // unbounded for every practical coordinate: the clamp at :537-540 never triggers
   RegionType region_;
   LookupType lookup_;
+  bool raster_ = false; double spacing_ = 1.0; double origin_[N] = {}; std::vector<TPixel> data_;
 };
 }  // namespace itk
 #endif
