@@ -495,14 +495,12 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
       const int tq = qq.x + lane;
       const bool valid = tq < qq.y;
       bool kept = false;
-      int fk = 0, fsp = -1, fo = 0x7fffffff; double fx_ = 0, fy_ = 0, fz_ = 0, fbest = 1e300;   // what a sparse-list record needs
       if (valid) {
         const int k = __ldg(d.proc + tq);
         const int sp = d.cprev[tq];
         const double2* pr = reinterpret_cast<const double2*>(d.proof + tq);
         const double2 p0 = __ldcg(pr), p1 = __ldcg(pr + 1);
         const double x = __ldg(d.tfx + tq), y = __ldg(d.tfy + tq), z = __ldg(d.tfz + tq);
-        fk = k; fx_ = x; fy_ = y; fz_ = z;
         if (sp >= 0 && (resid || p1.y > 0.0)) {
           const double4 q = lrr_ld_pos4(g.pos4 + sp);
           double P[6]; lrr_ld_P6(d.to.rec, sp, P);
@@ -516,9 +514,8 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
             d.r2[k] = r2;
             acc[4] += r2; acc[5] += w * r2; acc[6] += w; acc[7] += sqrt(r2) * w; acc[8] += 1.0;
           }
-          fsp = sp; fo = lrr_pos4_orig(q); fbest = lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z);
           if (p1.y > 0.0) {
-            const double dq = sqrt(fbest);
+            const double dq = sqrt(lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z));
             const double ex = yx - p0.x, ey = yy - p0.y, ez = yz - p1.x;
             const double dm = sqrt(ex * ex + ey * ey + ez * ez);
             // (1e-9 relative + slack covers the rounding of the square roots and sums; B itself was rounded down when written)
@@ -552,7 +549,15 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
           if (lane == 0) base = atomicAdd(d.fq_count, nrest);
           base = __shfl_sync(0xffffffffu, base, 0);
           if (valid && !kept) {
-            FqRec r; r.k = fk; r.cand = fsp; r.cand_o = fo; r.tq = tq; r.x = fx_; r.y = fy_; r.z = fz_; r.best = fbest;
+            // (the record is put together again from the caches here, on the rare path, instead of being carried in registers through the
+            //  common one: that cost the kernel 76 bytes of spills and ~6 us per launch)
+            FqRec r; r.k = __ldg(d.proc + tq); r.cand = d.cprev[tq]; r.cand_o = 0x7fffffff; r.tq = tq;
+            r.x = __ldg(d.tfx + tq); r.y = __ldg(d.tfy + tq); r.z = __ldg(d.tfz + tq); r.best = 1e300;
+            if (r.cand >= 0) {
+              const double4 q = lrr_ld_pos4(g.pos4 + r.cand);
+              double yx, yy, yz; lrr_map_exact(A, tt, cc, r.x, r.y, r.z, yx, yy, yz);
+              r.cand_o = lrr_pos4_orig(q); r.best = lrr_dist2_exact(yx, yy, yz, q.x, q.y, q.z);
+            }
             d.fq[base + __popc(rest & ((1u << lane) - 1u))] = r;
           }
         } else if (lane == 0) { const int slot = atomicAdd(d.todo_count, 1); d.todo[slot] = make_int2(ch, (int)rest); }
