@@ -683,11 +683,28 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
   const int mapped = sc->from_mapped;
   const bool sym = (flags & LRR_F_SYM) != 0, strength = (flags & LRR_F_STRENGTH) != 0, spatial = LRR_SPATIAL(flags);
   const bool skip_small = sym && (flags & LRR_F_RRL);
-  const double invG = 1.0 / G, invS = 1.0 / S;
   // normalised coordinates (x - c) / r as a multiplication by 1/r: one rounding apart from the reference's
-  // division, far inside the 1e-5 gate, and it removes six fp64 divisions (~40 instructions each) per match
-  const double cf0 = sc->cfrom[0], cf1 = sc->cfrom[1], cf2 = sc->cfrom[2], irf = 1.0 / sc->rfrom;
-  const double ct0 = sc->cto[0], ct1 = sc->cto[1], ct2 = sc->cto[2], irt = 1.0 / sc->rto;
+  // division, far inside the 1e-5 gate, and it removes six fp64 divisions (~40 instructions each) per match.
+  // The thirteen uniform scalars of the loop live in shared memory (broadcast reads): as registers they pushed the 27 accumulators
+  // of every lane into local memory (ncu: 21 MB of spill traffic per launch next to 26 MB of algorithmic bytes).
+  __shared__ double s_u[13];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_u[0] = sc->cfrom[0]; s_u[1] = sc->cfrom[1]; s_u[2] = sc->cfrom[2]; s_u[3] = 1.0 / sc->rfrom;
+    s_u[4] = sc->cto[0]; s_u[5] = sc->cto[1]; s_u[6] = sc->cto[2]; s_u[7] = 1.0 / sc->rto;
+    s_u[8] = 1.0 / G; s_u[9] = 1.0 / S; s_u[10] = jc[0]; s_u[11] = jc[1]; s_u[12] = jc[2];
+  }
+  __syncthreads();
+#define cf0 s_u[0]
+#define cf1 s_u[1]
+#define cf2 s_u[2]
+#define irf s_u[3]
+#define ct0 s_u[4]
+#define ct1 s_u[5]
+#define ct2 s_u[6]
+#define irt s_u[7]
+#define invG s_u[8]
+#define invS s_u[9]
   const int lane = threadIdx.x & 31, j = lane & 3, qbase = lane & ~3;
   double acc[27];
 #pragma unroll
@@ -724,11 +741,11 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
         double b0, b1, b2;
         if (!reversed) {
           lrr_ld_P6(a.to.rec, s, P);
-          x0 = px - jc[0]; x1 = py - jc[1]; x2 = pz - jc[2]; b0 = qx; b1 = qy; b2 = qz;
+          x0 = px - s_u[10]; x1 = py - s_u[11]; x2 = pz - s_u[12]; b0 = qx; b1 = qy; b2 = qz;
         } else {   // J at the to_ location, projector and right-hand side of the from_ feature
 #pragma unroll
           for (int p = 0; p < 6; ++p) P[p] = __ldg(a.fP6 + (size_t)p * a.n_in + i);
-          x0 = qx - jc[0]; x1 = qy - jc[1]; x2 = qz - jc[2]; b0 = px; b1 = py; b2 = pz;
+          x0 = qx - s_u[10]; x1 = qy - s_u[11]; x2 = qz - s_u[12]; b0 = px; b1 = py; b2 = pz;
         }
         pb0 = P[0] * b0 + P[1] * b1 + P[2] * b2;
         pb1 = P[1] * b0 + P[3] * b1 + P[4] * b2;
@@ -754,6 +771,16 @@ __device__ bool lrr_phase_accumulate(const Scope& scope, const DirArgs& a, int f
       acc[24] += wxa * c0; acc[25] += wxa * c1; acc[26] += wxa * c2;
     }
   }
+#undef cf0
+#undef cf1
+#undef cf2
+#undef irf
+#undef ct0
+#undef ct1
+#undef ct2
+#undef irt
+#undef invG
+#undef invS
   lrr_tl(2, 1);
   const bool fin = scope.template reduce<27, 4>(acc, sh.out, sh.tmp);
   lrr_tl(2, 2);
