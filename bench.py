@@ -517,6 +517,10 @@ def run_b200(args, rank, world, local_rank):
     pf, pm = pin(e2e_fixed), pin(e2e_moving)
     h2d = feature_bytes(e2e_fixed) + feature_bytes(e2e_moving)
     d2h = (9 + 3 + 3 + 144) * 8
+    # asynchronous upload (lrr_ctx_set_async_upload): the direction arrays — 47 % of the bytes, read by the angle metrics only — cross PCIe
+    # while the registration already runs; the copy is complete before the step ends (lrr_features_destroy waits for it), so every byte of
+    # h2d_bytes_per_step is moved inside the timed region
+    ctx.set_async_upload(True)
     with torch.cuda.stream(stream):
         e2e_iters = 0
         t_start = time.perf_counter()
@@ -541,6 +545,7 @@ def run_b200(args, rank, world, local_rank):
             print(f"[e2e] upload {tb - ta:.4f} est {tc - tb:.4f} run {td - tc:.4f} ({n_it} its) close {te_ - td:.4f}", file=sys.stderr)
         barrier()
         e2e_s = time.perf_counter() - t_start
+    ctx.set_async_upload(False)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -635,7 +640,7 @@ def run_b200(args, rank, world, local_rank):
         "neighbour_search": {"queries_searched_again_last_profiled_iteration": researched, "of": 2 * M, "stats": stats_last},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "iterations": e2e_iters, "seconds": float(te[0]),
-                "what": "per step: upload both volumes (cdcl_feature_ICP arrays: locations, projectors, strengths, shapes, directions) from pinned host memory (grid build), construct estimator, set_transform, "
+                "what": "per step: upload both volumes (cdcl_feature_ICP arrays: locations, projectors, strengths, shapes, directions) from pinned host memory (grid build; the directions asynchronously, lrr_ctx_set_async_upload, complete before the step ends), construct estimator, set_transform, "
                         "ramped run to convergence (<=70 one_iteration calls), read back transform+covariance"},
         "gpu_launches": int(launches),
         "clocks": clocks,

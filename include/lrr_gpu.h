@@ -121,6 +121,12 @@ int  lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count);
  * rrl/examples/compute_distance_map.cxx:55-151: the upload also builds the exact-NN uniform grid. */
 int  lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6,
                          const double* strength, const uint8_t* shape, const double* dirs, lrr_fset** out);
+/* Asynchronous upload (off by default; no reference counterpart — the reference builds its k-d trees / reads its Voronoi volumes before
+ * the first estimator exists, rrl/itkLocationRegistration.cxx:2035-2047).  on = 1: lrr_features_upload returns as soon as the search grid and
+ * the cell-ordered records exist; the `dirs` array — 47 % of a feature set's bytes, read by the sheet / tube angle metrics only — may still
+ * be on its way over PCIe while the registration already runs.  The caller keeps the `dirs` host buffer (pinned, for a truly asynchronous
+ * copy) valid until lrr_features_destroy or the next lrr_ctx_synchronize; every consumer of the directions waits for the copy on the device. */
+int  lrr_ctx_set_async_upload(lrr_ctx* ctx, int on);
 /* Plain cdcl_feature<dim> sets (location, strength, covariance; cdcl/cdcl_feature.h:17-64) for LRR_CDCL_ICP.  loc = dim x n SoA,
  * cov = dim(dim+1)/2 x n SoA (xx, xy, yy).  The error projector the reference re-derives at every use from the fixed feature's
  * covariance — outer product of the eigenvector of the smallest eigenvalue, cdcl/cdcl_estimation_ICP.txx:470-477,686-696 — is

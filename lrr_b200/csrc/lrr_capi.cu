@@ -122,11 +122,17 @@ extern "C" void lrr_ctx_destroy(lrr_ctx* ctx) {
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   if (ctx->copy_ev) cudaEventDestroy(ctx->copy_ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->dirs_stream) cudaStreamDestroy(ctx->dirs_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 extern "C" int lrr_ctx_set_stream(lrr_ctx* ctx, void* s) { if (!ctx) return LRR_ERR_INVALID; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return LRR_OK; }
-extern "C" int lrr_ctx_synchronize(lrr_ctx* ctx) { if (!ctx) return LRR_ERR_INVALID; enter(ctx); CK(cudaStreamSynchronize(ctx->stream)); return LRR_OK; }
+extern "C" int lrr_ctx_synchronize(lrr_ctx* ctx) {
+  if (!ctx) return LRR_ERR_INVALID;
+  enter(ctx); CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->dirs_stream) CK(cudaStreamSynchronize(ctx->dirs_stream));   // asynchronous uploads: the callers' `dirs` buffers are free again
+  return LRR_OK;
+}
 extern "C" const char* lrr_ctx_last_error(lrr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int64_t lrr_ctx_launch_count(lrr_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
 
@@ -165,8 +171,19 @@ static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, cons
   FCK(cudaMemcpyAsync(fs->s, strength, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
   FCK(cudaMemcpyAsync(fs->shape, shape, (size_t)n, cudaMemcpyHostToDevice, cs));
   if (C6 && !cov2) { FCK(dmalloc(&fs->C6, (size_t)6 * n)); FCK(cudaMemcpyAsync(fs->C6, C6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, cs)); }
-  if (dirs) { FCK(dmalloc(&fs->dirs, (size_t)9 * n)); FCK(cudaMemcpyAsync(fs->dirs, dirs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, cs)); }
   FCK(cudaEventRecord(ctx->copy_ev, cs));
+  // the directions (47 % of a cdcl_feature_ICP set's bytes) are read by the angle metrics only: last, on their own stream, and in
+  // asynchronous mode not waited for at all (lrr_ctx_set_async_upload; fset_wait_dirs)
+  if (dirs) {
+    FCK(dmalloc(&fs->dirs, (size_t)9 * n));
+    if (ctx->async_upload && !ctx->dirs_stream) FCK(cudaStreamCreateWithFlags(&ctx->dirs_stream, cudaStreamNonBlocking));
+    cudaStream_t ds = ctx->async_upload ? ctx->dirs_stream : cs;
+    if (ctx->async_upload) FCK(cudaStreamWaitEvent(ds, ctx->copy_ev, 0));   // behind this set's own projectors, not in front of them
+    FCK(cudaMemcpyAsync(fs->dirs, dirs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, ds));
+    if (ctx->async_upload) {
+      FCK(cudaEventCreateWithFlags(&fs->dirs_ev, cudaEventDisableTiming)); FCK(cudaEventRecord(fs->dirs_ev, ds)); fs->dirs_pending = true;
+    }
+  }
   FCK(dmalloc(&fs->pos4, (size_t)n)); FCK(dmalloc(&fs->rec, (size_t)8 * n)); FCK(dmalloc(&fs->sorted_of_orig, (size_t)n));
   FsetBuild fb; memset(&fb, 0, sizeof(fb));
   fb.n = n; fb.x = fs->xyz; fb.y = fs->xyz + n; fb.z = fs->xyz + 2 * n; fb.pos4 = fs->pos4; fb.sorted_of_orig = fs->sorted_of_orig;
@@ -179,6 +196,7 @@ static int features_upload_impl(lrr_ctx* ctx, int64_t n, const double* xyz, cons
   FCK(cudaStreamWaitEvent(st, ctx->copy_ev, 0));
   lrr_k_fill_records(d, fs->rec, fs->crec, st, &ctx->launches);
   FCK(cudaStreamSynchronize(st));
+  if (!fs->dirs_pending) FCK(cudaStreamSynchronize(cs));   // synchronous contract: every host buffer has been read when the call returns
   FCK(cudaGetLastError());
   dfree(cov2_d);
 #undef FCK
@@ -200,9 +218,13 @@ extern "C" int lrr_features_upload_cov(lrr_ctx* ctx, int dim, int64_t n, const d
   static const double dummy = 0.0;
   return features_upload_impl(ctx, n, xyz.data(), nullptr, nullptr, strength, nullptr, nullptr, n ? cov : &dummy, out);
 }
+// consumers of the direction arrays: wait (on the device, stream-ordered) for an asynchronous upload still in flight
+static void fset_wait_dirs(lrr_fset* fs, cudaStream_t st) { if (fs && fs->dirs_pending) cudaStreamWaitEvent(st, fs->dirs_ev, 0); }
+extern "C" int lrr_ctx_set_async_upload(lrr_ctx* ctx, int on) { if (!ctx) return LRR_ERR_INVALID; ctx->async_upload = on != 0; return LRR_OK; }
 extern "C" void lrr_features_destroy(lrr_fset* fs) {
   if (!fs) return;
   enter(fs->ctx);
+  if (fs->dirs_ev) { cudaEventSynchronize(fs->dirs_ev); cudaEventDestroy(fs->dirs_ev); }
   dfree(fs->xyz); dfree(fs->s); dfree(fs->P6); dfree(fs->C6); dfree(fs->dirs); dfree(fs->shape);
   dfree(fs->labels); dfree(fs->pos4); dfree(fs->rec); dfree(fs->crec); dfree(fs->sorted_of_orig); dfree(fs->cell_start);
   delete fs;
@@ -1041,6 +1063,7 @@ extern "C" int lrr_est_metric(lrr_est* e, int which, int dir, double* out) {
     case LRR_METRIC_SHEET_ANGLES:
     case LRR_METRIC_TUBE_ANGLES: {
       if (d.matches <= 0) { ctx->err = "angles without matches"; return LRR_ERR_STATE; }
+      fset_wait_dirs(e->d[dir].from_all, ctx->stream); fset_wait_dirs(e->d[dir].to_all, ctx->stream);
       lrr_k_angles(a.d[dir], a.flags, which == LRR_METRIC_SHEET_ANGLES ? 0 : 1, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches);
       CK(cudaMemcpyAsync(ctx->pinned, &d.sc->ang_num, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
@@ -1494,6 +1517,7 @@ static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lr
   CK(cudaStreamSynchronize(st));   // `hid` is a local buffer (and pageable copies are staged anyway)
   double table[4 * 32] = {0};
   const int rows = build_muse_table(1000u, table);
+  fset_wait_dirs(moving_all, st); fset_wait_dirs(fixed_all, st);
   CK(lrr_batch_launch(moving_all->dev, fixed_all->dev, s.djobs, s.dout, n, s.dids, max_iter, shuffle_seed, table, rows, nblocks, s.work, wbytes, st, &ctx->launches));
   CK(cudaMemcpyAsync(out + a, s.dout, sizeof(lrr_result) * n, cudaMemcpyDeviceToHost, st));
   s.a = a; s.n = n; s.busy = true;
@@ -1637,6 +1661,7 @@ extern "C" int lrr_batch_run_locations(lrr_ctx* ctx, lrr_fset* moving_all, lrr_f
     cu(cudaMemcpyAsync(djobs, jobs, sizeof(lrr_job) * njobs, cudaMemcpyHostToDevice, st), "jobs H2D");
     // ---- stage 1: ranking ----
     lrr_batch_loc_args = BatchLocArgs{1, n_candidates, 0, nullptr, ddec, voxel_spacing};
+    fset_wait_dirs(moving_all, st); fset_wait_dirs(fixed_all, st);
     { PHASE(PH_BATCH); cu(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, nullptr, max_iter, shuffle_seed, table, rows, nb_rank, work, wbytes, st, &ctx->launches), "ranking launch"); }
     lrr_batch_loc_args.mode = 0;
     cu(cudaMemcpyAsync(out, dout, sizeof(lrr_result) * njobs, cudaMemcpyDeviceToHost, st), "results D2H");

@@ -20,6 +20,7 @@ struct lrr_ctx {
   unsigned int* ticket = nullptr;
   unsigned int* sel_hist = nullptr; double* sel_cand = nullptr; unsigned long long* sel_misc = nullptr;
   SelDev sel[4];
+  bool async_upload = false; cudaStream_t dirs_stream = nullptr;
   unsigned long long sel_owner = 0; long long window_misses = 0;   // signature of the last estimate that left valid search windows in the selectors
   SortScratch sort; double* sort_keys = nullptr;
   double* muse_table = nullptr;
@@ -41,6 +42,9 @@ struct lrr_fset {
   uint8_t* shape = nullptr;
   double4* pos4 = nullptr; double* rec = nullptr; double* crec = nullptr; int* sorted_of_orig = nullptr; int* cell_start = nullptr;
   FsetDev dev;
+  // asynchronous upload (lrr_ctx_set_async_upload): the direction arrays — half the bytes, read by the angle metrics only — may still be on
+  // their way when lrr_features_upload returns; their consumers wait for this event on their stream (fset_wait_dirs)
+  cudaEvent_t dirs_ev = nullptr; bool dirs_pending = false;
   int* labels = nullptr;          // n region labels (watershed over-segmentation at the feature locations) for lrr_features_in_regions, or null
   std::vector<double> host_xyz;   // 3 x n copy for host-side ROI selection (FeaturesInROIs); fetched from the device on first use
 };

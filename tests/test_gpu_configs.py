@@ -149,3 +149,34 @@ def test_c5_one_million(gpu_lib, oracle_lib):
     fg_, gg = g.objcov_eval(x); fo, go = o.objcov_eval(x)
     assert abs(fg_ - fo) <= 1e-9 * abs(fo), (fg_, fo)
     assert rel(gg, go) < 1e-8, rel(gg, go)
+
+
+def test_async_upload_of_directions(gpu_lib):
+    """lrr_ctx_set_async_upload: the direction arrays arrive while the registration runs; the angle metrics (their only readers) wait for
+    them on the device and give bit for bit what the synchronous upload gives"""
+    import torch
+    pair = synth.make_pair(41, 30000, 30000)
+    res = []
+    for mode in (False, True):
+        ctx = gpu_lib.context()
+        ctx.set_async_upload(mode)
+        sets = []
+        for side in ("fixed", "moving"):
+            f = dict(pair[side]); f["C6"] = None
+            if mode:   # pinned host memory: the copy is truly asynchronous
+                keep = torch.from_numpy(np.ascontiguousarray(f["dirs"])).pin_memory(); f["dirs"] = keep.numpy(); f["_keep"] = keep
+            sets.append((ctx.upload({k: v for k, v in f.items() if k != "_keep"}), f))
+        (fx, _), (mv, _) = sets
+        est = ctx.estimator("rrl_sym", mv, fx, 12)
+        est.set_transform(*pair["init"])
+        est.find_closest()
+        a0 = [est.metric(m, d) for m in ("sheet_angles", "tube_angles") for d in (0, 1)]     # straight after the upload
+        for it in range(4):
+            est.one_iteration(it)
+        a1 = [est.metric(m, d) for m in ("sheet_angles", "tube_angles") for d in (0, 1)]
+        ctx.synchronize()
+        res.append((a0, a1, est.get_transform(0)["A"].copy()))
+        est.close(); fx.close(); mv.close()
+    assert res[0][0] == res[1][0]      # same matches, same directions: bit for bit
+    # (after iterations the sums of the work-queue passes are added in queue order, which differs from run to run by rounding)
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-11, atol=0) and np.allclose(res[0][2], res[1][2], rtol=1e-11, atol=1e-13)
