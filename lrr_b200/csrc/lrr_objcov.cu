@@ -44,10 +44,13 @@ __global__ void __launch_bounds__(LRR_OBJ_THREADS, 2) k_objcov(const __grid_cons
 #pragma unroll
   for (int i = 0; i < 25; ++i) acc[i] = 0.0;
   const int wfirst = scope.first() - lane, wstride = scope.stride();
+  // (the neighbour slot is fetched a trip ahead: the two gathers behind it start with the trip instead of a round trip into it)
+  int s_next = (wfirst + lane) < a.M ? a.sidx[wfirst + lane] : -1;
   for (int base = wfirst; base < a.M; base += wstride) {
     const int k = base + lane;
     double w = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, S[6] = {0, 0, 0, 0, 0, 0}, fterm = 0.0;
-    const int s = k < a.M ? a.sidx[k] : -1;
+    const int s = s_next;
+    s_next = (k + wstride) < a.M ? a.sidx[k + wstride] : -1;
     if (s >= 0) {
       const int i = lrr_from_index(a, k);
       const int po = a.forig ? a.forig[i] : i;
