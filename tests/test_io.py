@@ -342,9 +342,10 @@ def test_features_from_disk_through_the_backend(tmp_path):
             conv = est.one_iteration(it); it += 1
         res.append((it, est.get_transform(0), est.get_matches(0)[1], est.metric("sheet_angles"), est.metric("tube_angles")))
     assert res[0][0] == res[1][0] and np.array_equal(res[0][2], res[1][2])
+    # (same bits in, same matches out; the sums of the work-queue passes are added in queue order, which differs from run to run by rounding)
     for k in ("A", "t", "cov"):
-        assert np.array_equal(res[0][1][k], res[1][1][k]), k
-    assert res[0][3] == res[1][3] and res[0][4] == res[1][4]
+        assert np.allclose(res[0][1][k], res[1][1][k], rtol=1e-10, atol=1e-14), k
+    assert np.isclose(res[0][3], res[1][3], rtol=1e-10) and np.isclose(res[0][4], res[1][4], rtol=1e-10)
     tr = res[1][1]
     p = str(tmp_path / "transform000000_00.vtk"); lio.write_transform(p, tr["A"], tr["t"], tr["c"])
     A2, t2, c2 = lio.read_transform(p)
