@@ -357,7 +357,12 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
   if (e->dof == 4) f |= LRR_F_SIM2D;
   { static const bool noflat = getenv("LRR_NO_FLAT") != nullptr; if (noflat) f |= LRR_F_NOFLAT; }
   a.flags = f; a.dof = e->dof; a.src = src; a.estimate_parameters = 1;
-  { static const int ts = getenv("LRR_TILE_SPARSE") ? atoi(getenv("LRR_TILE_SPARSE")) : 8; a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : ts; }
+  // chunks with at most tile_sparse failed certificates put their queries on the per-query sparse list, the others are staged whole.
+  // While few certificates fail (sparse_hint: under a quarter of the queries in the last certificate pass — inside a registration
+  // 2-6 %, near ties) EVERY failed query goes to the list: a single staged chunk costs ~25 us of one warp's latency and set the
+  // duration of k_match_tile (43-61 -> 32-37 us per in-registration iteration; config 5 after convergence 309 -> 128 us)
+  { static const int ts = getenv("LRR_TILE_SPARSE") ? atoi(getenv("LRR_TILE_SPARSE")) : -1;
+    a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : (ts >= 0 ? ts : (e->sparse_hint ? 32 : 8)); }
   a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
   a.partials = ctx->partials; a.ticket = ctx->ticket;
   return a;
@@ -459,7 +464,7 @@ extern "C" void lrr_est_destroy(lrr_est* e) {
 // pass of the last iteration) is dropped together with the work list it may have left.
 static void touch(lrr_est* e) {
   if (!e) return;
-  e->norm_token = false; e->steady_hint = false;
+  e->norm_token = false; e->steady_hint = false; e->sparse_hint = false;
   if (e->pre_matched) {
     enter(e->ctx);
     for (int d = 0; d < (e->sym() ? 2 : 1); ++d) cudaMemsetAsync(e->d[d].todo_count, 0, 2 * sizeof(int), e->ctx->stream);
@@ -858,6 +863,8 @@ static int estimate_and_pull(lrr_est* e, int resid_mask, bool spec = false) {
   // pipelined: match_left is that of the NEXT find_closest (its certificate pass has just run); otherwise that of this iteration's,
   // the bet of the speculative plan
   e->steady_hint = all_kept;
+  { double failed = 0, total = 0; for (int d = 0; d < nd; ++d) { failed += e->h[d].cert_failed; total += (double)e->d[d].n_in; }
+    e->sparse_hint = used_cert && failed < 0.25 * total; }
   e->pre_matched = pipe;
   return LRR_OK;
 }

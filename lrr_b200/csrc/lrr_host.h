@@ -87,6 +87,9 @@ struct lrr_est {
   // every query of every direction was kept by its certificate in the last iteration (Scal::match_left == 0): the next iteration is
   // launched without the staged search, pass B and the normalisation (speculative plan; verified on the device, see estimate_and_pull)
   bool steady_hint = false;
+  // under a quarter of the queries lost their certificate in the last certificate pass: the next one routes every failed query to the
+  // per-query sparse list instead of staging whole chunks (est_args, lrr_capi.cu)
+  bool sparse_hint = false;
   // the certificate pass of the NEXT find_closest has already run, as the trailing (residual) pass of the last one_iteration (lrr_tile.cu)
   bool pre_matched = false;
   bool sym() const { return kind == LRR_CDCL_SYM || kind == LRR_RRL_SYM; }
