@@ -362,10 +362,10 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
   // 2-6 %, near ties) EVERY failed query goes to the list: a single staged chunk costs ~25 us of one warp's latency and set the
   // duration of k_match_tile (43-61 -> 32-37 us per in-registration iteration; config 5 after convergence 309 -> 128 us)
   { static const int ts = getenv("LRR_TILE_SPARSE") ? atoi(getenv("LRR_TILE_SPARSE")) : -1;
-    // (up to ~300 000 features per side the per-query list also wins when every certificate fails — first finest-level iteration,
-    //  whole find_closest 110/160/355 -> 90/140/300 us at 50k/100k/250k per side, equal at 500k, slower at 1 M: profiles/r2_summary.md)
-    int64_t total_in = 0; for (int d = 0; d < a.ndir; ++d) total_in += e->d[d].n_in;
-    a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : (ts >= 0 ? ts : ((e->sparse_hint || total_in <= 600000) ? 32 : 8)); }
+    // (without the hint — a level's first find_closest — whole chunks are staged: with candidates for every query the list would win
+    //  up to ~300k features per side, 160 -> 140 us at 100k, but in a fresh estimator the 36 % of the queries that have no previous
+    //  neighbour yet make it lose, 0.36 -> 0.54 ms: profiles/r2_summary.md)
+    a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : (ts >= 0 ? ts : (e->sparse_hint ? 32 : 8)); }
   a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
   a.partials = ctx->partials; a.ticket = ctx->ticket;
   return a;
