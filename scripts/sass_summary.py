@@ -13,7 +13,7 @@ for line in txt.splitlines():
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
         kern = name; rows[kern] = collections.Counter(); continue
-    if kern and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+    if kern and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         ins = line.split("*/", 1)[1]
         rows[kern]["total"] += 1
         matched_ldg = False
