@@ -121,6 +121,13 @@ int  lrr_ctx_phase_times(lrr_ctx* ctx, int cap, double* ms, int64_t* count);
  * rrl/examples/compute_distance_map.cxx:55-151: the upload also builds the exact-NN uniform grid. */
 int  lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const double* P6, const double* C6,
                          const double* strength, const uint8_t* shape, const double* dirs, lrr_fset** out);
+/* Behaviour switches of a context (measurement A/B and fall-backs; every default is the product path).  No reference counterpart.
+ * keys: "certificates" 0/1 (neighbour certificates), "tile" 0/1 (staged search, certificate pass and sparse list of the finest level),
+ * "speculative" 0 never / 1 after an iteration that kept every query / 2 in every finest-level iteration (the device refuses a lost bet),
+ * "pipeline" 0/1 (trailing residual pass = certificate pass of the next find_closest), "norm_skip" 0/1, "flat_scan" 0/1,
+ * "tile_sparse" -1 (by the host hint) or 0..32.  The environment variables listed in README.md only set the initial values.
+ * Estimators created before the call see the new value from their next call on. */
+int  lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value);
 /* Asynchronous upload (off by default; no reference counterpart — the reference builds its k-d trees / reads its Voronoi volumes before
  * the first estimator exists, rrl/itkLocationRegistration.cxx:2035-2047).  on = 1: lrr_features_upload returns as soon as the search grid and
  * the cell-ordered records exist; the `dirs` array — 47 % of a feature set's bytes, read by the sheet / tube angle metrics only — may still

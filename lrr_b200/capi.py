@@ -23,7 +23,7 @@ METRIC = {"rms": 0, "weighted": 1, "median": 2, "sheet_angles": 3, "tube_angles"
 # every symbol include/lrr_gpu.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = [
     "ctx_create", "ctx_destroy", "ctx_set_stream", "ctx_synchronize", "ctx_last_error", "ctx_launch_count",
-    "ctx_set_profiling", "ctx_phase_times", "ctx_set_async_upload",
+    "ctx_set_profiling", "ctx_phase_times", "ctx_set_async_upload", "ctx_set_option",
     "features_upload", "features_upload_cov", "features_destroy", "features_size", "features_nearest", "features_set_labels", "features_in_regions",
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
@@ -109,7 +109,7 @@ class Lib:
         pd, pi32 = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         sig = {
             "ctx_create": (i32, [i32, C.POINTER(vp)]), "ctx_destroy": (None, [vp]),
-            "ctx_set_stream": (i32, [vp, vp]), "ctx_synchronize": (i32, [vp]), "ctx_set_async_upload": (i32, [vp, i32]),
+            "ctx_set_stream": (i32, [vp, vp]), "ctx_synchronize": (i32, [vp]), "ctx_set_async_upload": (i32, [vp, i32]), "ctx_set_option": (i32, [vp, C.c_char_p, i32]),
             "ctx_last_error": (C.c_char_p, [vp]), "ctx_launch_count": (i64, [vp]),
             "ctx_set_profiling": (i32, [vp, i32]), "ctx_phase_times": (i32, [vp, i32, pd, C.POINTER(C.c_int64)]),
             "features_upload": (i32, [vp, i64, pd, pd, pd, pd, C.POINTER(C.c_uint8), pd, C.POINTER(vp)]),
@@ -177,6 +177,10 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.fn("ctx_synchronize")(self.h), "ctx_synchronize")
+
+    def set_option(self, key: str, value: int):
+        """behaviour switch of the context (include/lrr_gpu.h: certificates, tile, speculative, pipeline, norm_skip, flat_scan, tile_sparse)"""
+        self.check(self.lib.fn("ctx_set_option")(self.h, key.encode(), int(value)), "ctx_set_option")
 
     def set_async_upload(self, on: bool):
         """the direction arrays of later uploads are copied while the registration already runs (host buffers must stay valid)"""

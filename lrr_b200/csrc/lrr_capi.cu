@@ -98,6 +98,16 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
     } else { ctx->mailbox = nullptr; cudaGetLastError(); }
   }
   ctx->sort.keys2 = nullptr; ctx->sort.hist = nullptr; ctx->sort.cap = 0; ctx->sort_keys = nullptr;
+  {   // initial values of the behaviour switches (A/B measurements): environment, then lrr_ctx_set_option
+    lrr_ctx::Options& o = ctx->opt;
+    if (getenv("LRR_NO_PROOF")) o.certificates = 0;
+    if (getenv("LRR_NO_TILE")) o.tile = 0;
+    if (getenv("LRR_NO_SPEC")) o.spec = 0; else if (getenv("LRR_SPEC_FORCE")) o.spec = 2;
+    if (getenv("LRR_NO_PIPE")) o.pipe = 0;
+    if (getenv("LRR_NO_NORM_SKIP")) o.norm_skip = 0;
+    if (getenv("LRR_NO_FLAT")) o.flat = 0;
+    if (const char* ts = getenv("LRR_TILE_SPARSE")) o.tile_sparse = atoi(ts);
+  }
   ok = ok && cudaStreamSynchronize(ctx->own_stream) == cudaSuccess;   // (allocations and clears are ordered on the context's own stream)
   if (!ok) { cudaGetLastError(); lrr_ctx_destroy(ctx); return LRR_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) {
@@ -220,6 +230,20 @@ extern "C" int lrr_features_upload_cov(lrr_ctx* ctx, int dim, int64_t n, const d
 }
 // consumers of the direction arrays: wait (on the device, stream-ordered) for an asynchronous upload still in flight
 static void fset_wait_dirs(lrr_fset* fs, cudaStream_t st) { if (fs && fs->dirs_pending) cudaStreamWaitEvent(st, fs->dirs_ev, 0); }
+extern "C" int lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return LRR_ERR_INVALID;
+  lrr_ctx::Options& o = ctx->opt;
+  const std::string k(key);
+  if (k == "certificates") o.certificates = value != 0;
+  else if (k == "tile") o.tile = value != 0;
+  else if (k == "speculative") { if (value < 0 || value > 2) return LRR_ERR_INVALID; o.spec = value; }
+  else if (k == "pipeline") o.pipe = value != 0;
+  else if (k == "norm_skip") o.norm_skip = value != 0;
+  else if (k == "flat_scan") o.flat = value != 0;
+  else if (k == "tile_sparse") { if (value < -1 || value > 32) return LRR_ERR_INVALID; o.tile_sparse = value; }
+  else { ctx->err = "lrr_ctx_set_option: unknown key " + k; return LRR_ERR_INVALID; }
+  return LRR_OK;
+}
 extern "C" int lrr_ctx_set_async_upload(lrr_ctx* ctx, int on) { if (!ctx) return LRR_ERR_INVALID; ctx->async_upload = on != 0; return LRR_OK; }
 extern "C" void lrr_features_destroy(lrr_fset* fs) {
   if (!fs) return;
@@ -331,10 +355,11 @@ static DirArgs dir_args(const lrr_dir& d) {
   a.to = d.to_all->dev; a.from_all = d.from_all->dev;
   a.sidx = d.sidx; a.w = d.w; a.r2 = d.r2; a.gkey = d.gkey; a.skey = d.skey;
   a.stamp = d.stamp; a.tag = (~(unsigned long long)d.epoch) << 32;
-  static const bool no_proof = getenv("LRR_NO_PROOF") != nullptr;   // A/B switch for measurements
+  const lrr_ctx::Options& opt = d.from_all->ctx->opt;
+  const bool no_proof = !opt.certificates;
   a.proof = no_proof ? nullptr : d.proof; a.todo = no_proof ? nullptr : d.todo; a.todo_count = d.todo_count; a.fq = d.fq; a.fq_count = d.todo_count + 1;
   if (a.proof) { a.pos_of = d.pos_of; a.cprev = d.cprev; a.tfx = d.tf; a.tfy = d.tf + n; a.tfz = d.tf + 2 * n; }
-  a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.chunk_tab = (a.proc && d.n_in > 0) ? d.chunk_tab : nullptr; a.nchunks = d.chunk_start; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
+  a.prev_s = d.prev_s; a.proc = (d.has_order || d.perm_half) ? nullptr : d.proc; a.chunk_tab = (a.proc && d.n_in > 0 && opt.tile) ? d.chunk_tab : nullptr; a.nchunks = d.chunk_start; a.hq_k = d.hq_k; a.hq_best = d.hq_best; a.hq_s = d.hq_s; a.hq_o = d.hq_o; a.hq_count = d.hq_count;
   a.sc = d.sc;
   // certified finest level (lrr_dir_certified, lrr_tile.cu): kept matches are not touched, the stamps come from k_restamp
   a.stamp_in_match = !(a.proof && a.todo && a.chunk_tab && a.proc && a.M == a.n_in);
@@ -355,13 +380,13 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
   if (e->kind == LRR_CDCL_SYM) f |= LRR_F_MERGED;
   if (e->icp()) f |= LRR_F_ICP;
   if (e->dof == 4) f |= LRR_F_SIM2D;
-  { static const bool noflat = getenv("LRR_NO_FLAT") != nullptr; if (noflat) f |= LRR_F_NOFLAT; }
+  if (!ctx->opt.flat) f |= LRR_F_NOFLAT;
   a.flags = f; a.dof = e->dof; a.src = src; a.estimate_parameters = 1;
   // chunks with at most tile_sparse failed certificates put their queries on the per-query sparse list, the others are staged whole.
   // While few certificates fail (sparse_hint: under a quarter of the queries in the last certificate pass — inside a registration
   // 2-6 %, near ties) EVERY failed query goes to the list: a single staged chunk costs ~25 us of one warp's latency and set the
   // duration of k_match_tile (43-61 -> 32-37 us per in-registration iteration; config 5 after convergence 309 -> 128 us)
-  { static const int ts = getenv("LRR_TILE_SPARSE") ? atoi(getenv("LRR_TILE_SPARSE")) : -1;
+  { const int ts = ctx->opt.tile_sparse;
     // (without the hint — a level's first find_closest — whole chunks are staged: with candidates for every query the list would win
     //  up to ~300k features per side, 160 -> 140 us at 100k, but in a fresh estimator the 36 % of the queries that have no previous
     //  neighbour yet make it lose, 0.36 -> 0.54 ms: profiles/r2_summary.md)
@@ -687,7 +712,7 @@ static int do_find_closest(lrr_est* e, bool cert_only = false) {
 // Every direction of the next find_closest goes through the certificate pass (finest level, identity order, certificates on):
 // the condition under which Scal::match_left means "queries not kept", and the structural half of the speculative plan.
 static bool cert_path(const lrr_est* e) {
-  static const bool no_proof = getenv("LRR_NO_PROOF") != nullptr, no_tile = getenv("LRR_NO_TILE") != nullptr;
+  const bool no_proof = !e->ctx->opt.certificates, no_tile = !e->ctx->opt.tile;
   if (no_proof || no_tile || e->icp() || e->shuffle_mode == LRR_ORDER_RESHUFFLE) return false;
   for (int d = 0; d < (e->sym() ? 2 : 1); ++d) {
     const lrr_dir& D = e->d[d];
@@ -703,7 +728,7 @@ static bool cert_path(const lrr_est* e) {
 // LRR_SPEC_FORCE=1 bets in every iteration the certificate pass can run (tests: the fallback in every non-steady iteration),
 // LRR_NO_SPEC=1 never.
 static bool spec_ok(const lrr_est* e) {
-  static const bool off = getenv("LRR_NO_SPEC") != nullptr, force = getenv("LRR_SPEC_FORCE") != nullptr;
+  const bool off = e->ctx->opt.spec == 0, force = e->ctx->opt.spec == 2;
   if (off || !e->ctx->mailbox_dev || !e->normalize || e->dof == 6 || !e->norm_token || !cert_path(e)) return false;
   for (int d = 0; d < (e->sym() ? 2 : 1); ++d) if (!e->d[d].scale_estimated || e->d[d].matches <= 0) return false;
   return force || e->steady_hint;
@@ -767,7 +792,7 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
   }
   else if (e->normalize && !spec) {   // (speculative plan: the normalisation is clean or the kernels below refuse)
     // (rigid increments normalise mapped clones of the from-features, which move with the transform: never skipped)
-    static const bool no_skip = getenv("LRR_NO_NORM_SKIP") != nullptr;   // A/B switch for measurements
+    const bool no_skip = !ctx->opt.norm_skip;
     const int skip_clean = (e->norm_token && src == 0 && e->dof != 6 && !stale && !no_skip) ? 1 : 0;
     if (restamp) { PHASE(PH_RESTAMP); lrr_k_restamp(a, ctx->stream, &ctx->launches, skip_clean); }
     { PHASE(PH_NORM1); lrr_k_norm1(a, ctx->stream, &ctx->launches, skip_clean); }
@@ -801,7 +826,7 @@ static int do_estimate(lrr_est* e, int src, int estimate_parameters, bool force_
 // (steady state: certificate/residual pass -> weight -> accumulate+solve, three launches) or the match has to be completed first
 // (staged search + pass B, then the normalisation).  LRR_NO_PIPE=1 switches it off (A/B).
 static bool pipe_ok(const lrr_est* e) {
-  static const bool off = getenv("LRR_NO_PIPE") != nullptr;
+  const bool off = !e->ctx->opt.pipe;
   if (off || e->dof != 12 || !cert_path(e)) return false;
   for (int d = 0; d < (e->sym() ? 2 : 1); ++d) if (e->d[d].matches != e->d[d].n_in) return false;   // the finished iteration matched every point
   return true;

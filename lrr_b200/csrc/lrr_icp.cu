@@ -228,10 +228,10 @@ __global__ void __launch_bounds__(LRR_THREADS, LRR_HARD_MINBLK) k_match_hard(con
   }
   lrr_tl(1, 3);
 }
-static bool lrr_no_tile() { static const bool v = getenv("LRR_NO_TILE") != nullptr; return v; }   // A/B switch for measurements
+// (the "tile" switch lives in lrr_ctx::Options: with it off dir_args withholds the chunk table and the tile path is not usable)
 void lrr_k_match(const EstArgs& a, cudaStream_t st, long long* launches, bool cert_only) {
   if (cert_only) { lrr_k_match_cert(a, st, launches); return; }   // the caller has checked that every direction is certified
-  if (!lrr_no_tile() && lrr_match_tile_usable(a) && lrr_match_cert_usable(a)) lrr_k_match_cert(a, st, launches);
+  if (lrr_match_tile_usable(a) && lrr_match_cert_usable(a)) lrr_k_match_cert(a, st, launches);
   lrr_k_match_rest(a, st, launches);
 }
 void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches) {
@@ -241,7 +241,7 @@ void lrr_k_match_rest(const EstArgs& a, cudaStream_t st, long long* launches) {
 // pass A: the staged search / sparse list of the finest level (lrr_tile.cu) or the thread-per-query ball scan of the ramp levels
 void lrr_k_match_search(const EstArgs& a, cudaStream_t st, long long* launches) {
   // persistent-style grid: every resident warp pulls 32-query chunks until the direction's queries are exhausted
-  if (!lrr_no_tile() && lrr_match_tile_usable(a)) {   // finest level (lrr_tile.cu): shared-memory-staged cells for what the certificates did not keep
+  if (lrr_match_tile_usable(a)) {   // finest level (lrr_tile.cu): shared-memory-staged cells for what the certificates did not keep
     lrr_k_match_tile(a, st, launches);
   }
   else {

@@ -54,7 +54,8 @@ extern "C" {
 int lrro_ctx_create(int, lrro_ctx** out) { *out = new lrro_ctx(); return LRR_OK; }
 void lrro_ctx_destroy(lrro_ctx* c) { delete c; }
 int lrro_ctx_set_stream(lrro_ctx*, void*) { return LRR_OK; }
-int lrro_ctx_set_async_upload(lrro_ctx*, int) { return LRR_OK; }   // (host memory: nothing to overlap)
+int lrro_ctx_set_async_upload(lrro_ctx*, int) { return LRR_OK; }
+int lrro_ctx_set_option(lrro_ctx*, const char*, int) { return LRR_OK; }   // (switches of the CUDA path: nothing to switch here)   // (host memory: nothing to overlap)
 int lrro_ctx_synchronize(lrro_ctx*) { return LRR_OK; }
 const char* lrro_ctx_last_error(lrro_ctx* c) { return c->err.c_str(); }
 int64_t lrro_ctx_launch_count(lrro_ctx*) { return 0; }

@@ -180,3 +180,33 @@ def test_async_upload_of_directions(gpu_lib):
     assert res[0][0] == res[1][0]      # same matches, same directions: bit for bit
     # (after iterations the sums of the work-queue passes are added in queue order, which differs from run to run by rounding)
     assert np.allclose(res[0][1], res[1][1], rtol=1e-11, atol=0) and np.allclose(res[0][2], res[1][2], rtol=1e-11, atol=1e-13)
+
+
+def test_context_options_switch_paths_without_changing_results(gpu_lib):
+    """lrr_ctx_set_option: certificates / tile / speculative / pipeline / tile_sparse select launch plans, never results (index sets
+    bit-exact, transforms to rounding)"""
+    pair = synth.make_pair(43, 20000, 20000)
+    ref = None
+    for opts in ({}, {"certificates": 0}, {"tile": 0}, {"speculative": 2}, {"pipeline": 0}, {"tile_sparse": 0}, {"tile_sparse": 32}, {"norm_skip": 0, "flat_scan": 0}):
+        ctx = gpu_lib.context()
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+        est = ctx.estimator("rrl_sym", mv, fx, 12)
+        est.set_transform(*pair["init"])
+        it, conv = 0, False
+        while not conv and it < 40:
+            conv = est.one_iteration(it); it += 1
+        for k in range(3):
+            est.one_iteration(it + k)
+        out = (it, est.get_matches(0)[1].copy(), est.get_matches(1)[1].copy(), est.get_transform(0)["A"].copy(), est.get_transform(0)["cov"].copy())
+        if ref is None:
+            ref = out
+        else:
+            assert out[0] == ref[0], opts
+            assert np.array_equal(out[1], ref[1]) and np.array_equal(out[2], ref[2]), opts
+            assert np.allclose(out[3], ref[3], rtol=1e-10, atol=1e-13) and np.allclose(out[4], ref[4], rtol=1e-8, atol=1e-18), opts
+        est.close(); fx.close(); mv.close()
+    import pytest as _pt
+    with _pt.raises(Exception):
+        gpu_lib.context().set_option("no_such_switch", 1)
