@@ -222,6 +222,34 @@ int  lrr_objpar_eval(lrr_est* est, int dir, const double* theta, double* f, doub
  * *converged = (f_start - f_end) < 1e-4 (cdcl/cdcl_estimation.txx:207-262). */
 int  lrr_objpar_refine(lrr_est* est, int dir, int max_evals, double* f_start, double* f_end, int* n_evals, int* converged);
 
+/* ---- E-step of the full CDC estimator: covariance-driven radius matching
+ * (cdcl_estimation<3,12>::compute_weights, cdcl/cdcl_estimation.txx:342-545) -------------------------------------------------------------
+ * For every from-feature p of `dir` under the direction's current transform and covariance: Cij_p = Jth Sigma Jth^T + Jp Cp Jp^T,
+ * search radius eval_multiplier (5.0) * sqrt(lambda_max(Cij_p)), every to-feature within the radius (rsdl points_in_radius) but at most
+ * max_matches (100) of them — the reference takes the first 100 of a random shuffle (:396-398; Q4, unpinned: the backend takes the
+ * lowest original indices) —, w0 = weight(e^T (Cij_p + Cq)^-1 e) kept when > 0, finally w = w0^2 / (row sum * to-feature sum).
+ * The many-to-many set then REPLACES the 1-NN matches as the set lrr_objcov_* and lrr_objpar_* run over (f over entries,
+ * cdcl_obj_fun_cov.txx:124; over rows, cdcl_obj_fun_par.txx:136; normalisation as cdcl_estimation_ICP.txx:751-832) until the next
+ * find_closest / one_iteration.  entries == 0: the covariance is too small for any match, the caller falls back to
+ * find_closest_euclidean as :544 does. */
+typedef struct lrr_cdc_summary {
+  int64_t rows;              /* matches_.size(): from-features with at least one kept to-feature                     */
+  int64_t entries;           /* sum of to_.size()                                                                    */
+  int32_t min_matches, max_matches;   /* smallest / largest row (:465-466)                                          */
+  double  avg_largest_eval;  /* sum over ALL from-features of sqrt(lambda_max(Jth Sigma Jth^T)) / rows (:375, :480)  */
+} lrr_cdc_summary;
+int  lrr_cdc_compute_weights(lrr_est* est, int dir, int max_matches, double eval_multiplier, lrr_cdc_summary* out);
+/* CSR export for display / tests: rows ascending by from position (row_from = index in the parent set), entries of a row ascending by
+ * to index.  Sizes through n_rows / n_entries (the arrays may be NULL to query them). */
+int  lrr_cdc_get_matches(lrr_est* est, int dir, int64_t cap_rows, int64_t cap_entries, int64_t* n_rows, int64_t* n_entries,
+                         int32_t* row_from, int64_t* row_start, int32_t* to_idx, double* w);
+/* the resolution switch compute_weights ends with (:494-508): one level finer when avg_largest_eval < 2 spacing[res], else one level
+ * coarser when it exceeds 2 spacing[res + 1]; the caller re-invokes set_subsets with that level's feature sets and matches again. */
+int  lrr_cdc_resolution_switch(double avg_largest_eval, const double* fixed_spacing, int res, int max_res, int allowed, int* new_res);
+/* cdcl_estimation<3,12>::one_iteration (:88-186) at one resolution: weights; for iteration > 5 estimate_parameters and weights again;
+ * estimate_covariance.  *converged = parameters && covariance && |Sigma_theta|_F < 1e-3. */
+int  lrr_cdc_one_iteration(lrr_est* est, int dir, unsigned iteration, int max_matches, double eval_multiplier, int* converged, lrr_cdc_summary* out);
+
 /* ---- batched location registration (outer loops of LocationRegistration::Run,
  * rrl/itkLocationRegistration.cxx:2138,2230,2332) ------------------------------------- */
 typedef struct lrr_job {

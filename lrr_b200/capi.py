@@ -28,7 +28,8 @@ ABI_SYMBOLS = [
     "est_create", "est_destroy", "est_set_subsets", "est_set_transform", "est_set_flags", "est_set_order",
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
-    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "objpar_eval", "objpar_refine", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations",
+    "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "objpar_eval", "objpar_refine",
+    "cdc_compute_weights", "cdc_get_matches", "cdc_resolution_switch", "cdc_one_iteration", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations",
 ]
 
 
@@ -45,6 +46,11 @@ class EstState(C.Structure):
 class EstStats(C.Structure):
     _fields_ = [("cert_failed", C.c_int64 * 2), ("passb_queries", C.c_int64 * 2), ("work_list_entries", C.c_int64 * 2),
                 ("window_misses", C.c_int64), ("spec_misses", C.c_int64)]
+
+
+class CdcSummary(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("entries", C.c_int64), ("min_matches", C.c_int32), ("max_matches", C.c_int32),
+                ("avg_largest_eval", C.c_double)]
 
 
 class Job(C.Structure):
@@ -134,6 +140,11 @@ class Lib:
             "objcov_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32)]),
             "objpar_eval": (i32, [vp, i32, pd, pd, pd]),
             "objpar_refine": (i32, [vp, i32, i32, pd, pd, C.POINTER(i32), C.POINTER(i32)]),
+            "cdc_compute_weights": (i32, [vp, i32, i32, dbl, C.POINTER(CdcSummary)]),
+            "cdc_get_matches": (i32, [vp, i32, i64, i64, C.POINTER(i64), C.POINTER(i64), pi32, C.POINTER(i64), pi32, pd]),
+            "cdc_resolution_switch": (i32, [dbl, pd, i32, i32, i32, C.POINTER(i32)]),
+            "cdc_one_iteration": (i32, [vp, i32, C.c_uint, i32, dbl, C.POINTER(i32), C.POINTER(CdcSummary)]),
+            "test_cdc_normalisation": (i32, [vp, pd]),
             "batch_run": (i32, [vp, vp, vp, vp, i64, i32, u64, vp]),
             "batch_run_ids": (i32, [vp, vp, vp, vp, C.POINTER(C.c_int64), i64, i32, u64, vp]),
             "batch_run_locations": (i32, [vp, vp, vp, vp, i64, C.c_int32, i32, u64, i32, dbl, vp, vp]),
@@ -426,6 +437,32 @@ class Estimator:
         fs, fe = np.zeros(1), np.zeros(1); ne = C.c_int(0); cv = C.c_int(0)
         self._c(self.lib.fn("objpar_refine")(self.h, direction, max_evals, _dp(fs), _dp(fe), C.byref(ne), C.byref(cv)), "objpar_refine")
         return float(fs[0]), float(fe[0]), int(ne.value), bool(cv.value)
+
+    # ---- E-step of the full CDC estimator (cdcl_estimation::compute_weights, cdcl/cdcl_estimation.txx:342-545) ----
+    @staticmethod
+    def _cdc_dict(s):
+        return {"rows": int(s.rows), "entries": int(s.entries), "min_matches": int(s.min_matches), "max_matches": int(s.max_matches),
+                "avg_largest_eval": float(s.avg_largest_eval)}
+
+    def cdc_compute_weights(self, max_matches=100, eval_multiplier=5.0, direction=0):
+        s = CdcSummary()
+        self._c(self.lib.fn("cdc_compute_weights")(self.h, direction, max_matches, eval_multiplier, C.byref(s)), "cdc_compute_weights")
+        return self._cdc_dict(s)
+
+    def cdc_get_matches(self, direction=0):
+        """(row_from[rows], row_start[rows + 1], to_idx[entries], w[entries]): the many-to-many match set in CSR form"""
+        nr, ne = C.c_int64(0), C.c_int64(0)
+        fn = self.lib.fn("cdc_get_matches")
+        self._c(fn(self.h, direction, 0, 0, C.byref(nr), C.byref(ne), None, None, None, None), "cdc_get_matches")
+        rf = np.zeros(nr.value, np.int32); rs = np.zeros(nr.value + 1, np.int64); ti = np.zeros(ne.value, np.int32); w = np.zeros(ne.value)
+        self._c(fn(self.h, direction, nr.value, ne.value, None, None, rf.ctypes.data_as(C.POINTER(C.c_int32)),
+                   rs.ctypes.data_as(C.POINTER(C.c_int64)), ti.ctypes.data_as(C.POINTER(C.c_int32)), _dp(w)), "cdc_get_matches")
+        return rf, rs, ti, w
+
+    def cdc_one_iteration(self, iteration, max_matches=100, eval_multiplier=5.0, direction=0):
+        s = CdcSummary(); cv = C.c_int(0)
+        self._c(self.lib.fn("cdc_one_iteration")(self.h, direction, iteration, max_matches, eval_multiplier, C.byref(cv), C.byref(s)), "cdc_one_iteration")
+        return bool(cv.value), self._cdc_dict(s)
 
     def close(self):
         if self.h:

@@ -315,6 +315,7 @@ static int dir_alloc(lrr_ctx* ctx, lrr_dir& d, lrr_fset* from_all, lrr_fset* to_
 static void dir_free(lrr_dir& d) {
   dfree(d.fx); dfree(d.fP6); dfree(d.forig); dfree(d.order); dfree(d.sidx); dfree(d.w); dfree(d.stamp); dfree(d.sc); dfree(d.hq_k); dfree(d.hq_best); dfree(d.prev_s); dfree(d.proc); dfree(d.proc_mark); dfree(d.proof); dfree(d.pos_of); dfree(d.cprev); dfree(d.tf);
   dfree(d.tile_cnt); dfree(d.tile_start); dfree(d.chunk_start); dfree(d.tile_of); dfree(d.chunk_tab); dfree(d.todo); dfree(d.todo_count); dfree(d.fq);
+  dfree(d.cdc_efrom); dfree(d.cdc_eslot); dfree(d.cdc_ew); dfree(d.cdc_rowcnt); dfree(d.cdc_roww); dfree(d.cdc_tow); dfree(d.cdc_cand); dfree(d.cdc_candw); dfree(d.cdc_cursor);
 }
 static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t n) {
   if (n < 0 || (size_t)n > d.cap) return LRR_ERR_INVALID;
@@ -330,7 +331,7 @@ static int dir_set_subset(lrr_ctx* ctx, lrr_dir& d, const int32_t* idx, int64_t 
     lrr_k_gather_from(d.from_all->dev, nullptr, (int)n, d.fx, d.fy, d.fz, d.fs, d.fP6, st, &ctx->launches);
     d.subset = false;
   }
-  d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false;
+  d.n_in = n; d.has_order = false; d.matches = 0; d.weights_fresh = false; d.cdc_active = false;
   CK(cudaMemsetAsync(d.prev_s, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));   // no search candidates yet
   CK(cudaMemsetAsync(d.proof, 0, sizeof(double4) * (size_t)(n ? n : 1), st));   // ... and no neighbour certificates
   CK(cudaMemsetAsync(d.cprev, 0xFF, sizeof(int) * (size_t)(n ? n : 1), st));
@@ -692,6 +693,7 @@ static int prepare_find_closest(lrr_est* e) {
     if (e->d[d].to_all->n == 0 || e->d[d].n_in == 0) { ctx->err = "find_closest_euclidean: empty feature set"; return LRR_ERR_STATE; }
     int rc = apply_shuffle(e, d); if (rc != LRR_OK) return rc;
     if ((rc = bump_epoch(e, d)) != LRR_OK) return rc;
+    e->d[d].cdc_active = false;   // a new 1-NN match replaces the many-to-many set of the CDC E-step
   }
   return LRR_OK;
 }
@@ -1250,6 +1252,23 @@ static bool cholesky_upper12(const double* C, double* U) {   // C = U^T U  (vnl_
   return true;
 }
 
+// the flat many-to-many set of the CDC E-step as the match arrays the objective kernels stream (position -> from index, slot, weight)
+static void cdc_dir_args(const lrr_dir& d, DirArgs& a) {
+  a.order = d.cdc_efrom; a.perm_half = 0; a.sidx = d.cdc_eslot; a.w = d.cdc_ew; a.M = (int)d.cdc_entries;
+}
+// cdcl_normalize_matches over the many-to-many set (cdcl/cdcl_estimation_ICP.txx:751-832) -> norm8 = (cm, rm, cf, rf)
+static int cdc_normalisation(lrr_est* e, int dir, double* norm8) {
+  lrr_ctx* ctx = e->ctx; lrr_dir& d = e->d[dir];
+  double* out = ctx->scratch_d + 160;
+  lrr_k_cdc_norm((int)d.n_in, (int)d.to_all->n, d.fx, d.fy, d.fz, d.cdc_rowcnt, d.cdc_tow, d.to_all->dev.grid.pos4, out, ctx->stream, &ctx->launches);
+  double* pin = (double*)ctx->pinned + 512;
+  CK(cudaMemcpyAsync(pin, out, 10 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 3; ++k) { norm8[k] = pin[k] / pin[3]; norm8[4 + k] = pin[4 + k] / pin[7]; }
+  norm8[3] = pin[8] / pin[3]; norm8[7] = pin[9] / pin[7];
+  return LRR_OK;
+}
+
 // one evaluation of f and g at x (length 78) for direction `dir`, transform / normalisation given by the caller
 static int objcov_device_eval(lrr_est* e, int dir, const HostTrans& T, const double* norm8, const double* x, double* f, double* g) {
   lrr_ctx* ctx = e->ctx;
@@ -1263,12 +1282,13 @@ static int objcov_device_eval(lrr_est* e, int dir, const HostTrans& T, const dou
   CK(cudaMemcpyAsync(ctx->scratch_d, pin, sizeof(Sg), cudaMemcpyHostToDevice, ctx->stream));
   EstArgs a = est_args(e);
   a.d[dir].M = (int)d.matches;
+  if (d.cdc_active) cdc_dir_args(d, a.d[dir]);
   { PHASE(PH_OBJCOV); lrr_k_objcov_launch(a.d[dir], T.A, T.t, T.c, norm8, ctx->scratch_d, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches); }
   CK(cudaMemcpyAsync(pin + 256, d.sc->mom, 100 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   const double* mom = pin + 256;
-  const double n = (double)d.matches;
+  const double n = d.cdc_active ? (double)d.cdc_entries : (double)d.matches;   // num_of_all_matches (cdcl_obj_fun_cov.txx:76,124)
   static const int sym6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
   if (f) { double fv = 0; for (int j = 0; j < 4; ++j) fv += mom[j * 25 + 24]; *f = fv / n; }
   if (g) {
@@ -1292,7 +1312,7 @@ static int objcov_check(lrr_est* e, int dir) {
   if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
   lrr_ctx* ctx = e->ctx;
   if (e->dof != 12) { ctx->err = "cdcl_obj_fun_cov: only the affine <3,12> instantiation is built"; return LRR_ERR_UNSUPPORTED; }
-  if (e->d[dir].matches <= 0) { ctx->err = "objcov without matches"; return LRR_ERR_STATE; }
+  if (e->d[dir].matches <= 0 && !e->d[dir].cdc_active) { ctx->err = "objcov without matches"; return LRR_ERR_STATE; }
   if (!e->d[dir].from_all->C6 || !e->d[dir].to_all->C6) { ctx->err = "objcov needs feature covariances (C6)"; return LRR_ERR_STATE; }
   return LRR_OK;
 }
@@ -1360,7 +1380,9 @@ extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_s
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
-  if (e->normalize) {   // cdcl_normalize_matches over the current matches (:271-277)
+  bool cdc_norm = false;
+  if (e->normalize && d.cdc_active) { if ((rc = cdc_normalisation(e, dir, norm8)) != LRR_OK) return rc; cdc_norm = true; }
+  else if (e->normalize) {   // cdcl_normalize_matches over the current matches (:271-277)
     if ((rc = bump_epoch(e, dir)) != LRR_OK) return rc;
     EstArgs a = est_args(e, dir);
     a.d[dir].M = (int)d.matches;
@@ -1372,8 +1394,13 @@ extern "C" int lrr_objcov_refine(lrr_est* e, int dir, int max_evals, double* f_s
   Scal& h = e->h[dir];
   HostTrans T; memcpy(T.A, h.A, 72); memcpy(T.t, h.t, 24); memcpy(T.c, h.c, 24); memcpy(T.cov, h.cov, sizeof(T.cov));
   if (e->normalize) {
-    for (int k = 0; k < 3; ++k) { norm8[k] = h.cfrom[k]; norm8[4 + k] = h.cto[k]; }
-    norm8[3] = h.rfrom; norm8[7] = h.rto;
+    if (!cdc_norm) {
+      for (int k = 0; k < 3; ++k) { norm8[k] = h.cfrom[k]; norm8[4 + k] = h.cto[k]; }
+      norm8[3] = h.rfrom; norm8[7] = h.rto;
+    } else {   // (reported by lrr_est_get_state like the normalisation of any other estimate)
+      for (int k = 0; k < 3; ++k) { h.cfrom[k] = norm8[k]; h.cto[k] = norm8[4 + k]; }
+      h.rfrom = norm8[3]; h.rto = norm8[7];
+    }
     affine_normalize(T, norm8[3], norm8[7], norm8, norm8 + 4);
   }
   double U[144];
@@ -1406,12 +1433,13 @@ static int objpar_device_eval(lrr_est* e, int dir, const HostTrans& T, const dou
   CK(cudaMemcpyAsync(ctx->scratch_d, pin, sizeof(T.cov), cudaMemcpyHostToDevice, ctx->stream));
   EstArgs a = est_args(e);
   a.d[dir].M = (int)d.matches;
+  if (d.cdc_active) cdc_dir_args(d, a.d[dir]);
   { PHASE(PH_OBJCOV); lrr_k_objpar_launch(a.d[dir], theta, theta + 9, T.c, norm8, ctx->scratch_d, ctx->partials, ctx->ticket, ctx->stream, &ctx->launches); }
   CK(cudaMemcpyAsync(pin + 256, d.sc->mom, 13 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   const double* mom = pin + 256;
-  const double n = (double)d.matches;
+  const double n = d.cdc_active ? (double)d.cdc_rows : (double)d.matches;   // matches_.size() (cdcl_obj_fun_par.txx:131-137)
   if (f) *f = mom[12] / n;
   if (g) for (int k = 0; k < 12; ++k) g[k] = mom[k] * (1.0 / n);
   return LRR_OK;
@@ -1434,7 +1462,9 @@ extern "C" int lrr_objpar_refine(lrr_est* e, int dir, int max_evals, double* f_s
   lrr_ctx* ctx = e->ctx; enter(ctx);
   lrr_dir& d = e->d[dir];
   double norm8[8] = {0, 0, 0, 1, 0, 0, 0, 1};
-  if (e->normalize) {   // cdcl_normalize_matches over the current matches (:214-217)
+  bool cdc_norm = false;
+  if (e->normalize && d.cdc_active) { if ((rc = cdc_normalisation(e, dir, norm8)) != LRR_OK) return rc; cdc_norm = true; }
+  else if (e->normalize) {   // cdcl_normalize_matches over the current matches (:214-217)
     if ((rc = bump_epoch(e, dir)) != LRR_OK) return rc;
     EstArgs a = est_args(e, dir);
     a.d[dir].M = (int)d.matches;
@@ -1446,8 +1476,13 @@ extern "C" int lrr_objpar_refine(lrr_est* e, int dir, int max_evals, double* f_s
   Scal& h = e->h[dir];
   HostTrans T; memcpy(T.A, h.A, 72); memcpy(T.t, h.t, 24); memcpy(T.c, h.c, 24); memcpy(T.cov, h.cov, sizeof(T.cov));
   if (e->normalize) {
-    for (int k = 0; k < 3; ++k) { norm8[k] = h.cfrom[k]; norm8[4 + k] = h.cto[k]; }
-    norm8[3] = h.rfrom; norm8[7] = h.rto;
+    if (!cdc_norm) {
+      for (int k = 0; k < 3; ++k) { norm8[k] = h.cfrom[k]; norm8[4 + k] = h.cto[k]; }
+      norm8[3] = h.rfrom; norm8[7] = h.rto;
+    } else {   // (reported by lrr_est_get_state like the normalisation of any other estimate)
+      for (int k = 0; k < 3; ++k) { h.cfrom[k] = norm8[k]; h.cto[k] = norm8[4 + k]; }
+      h.rfrom = norm8[3]; h.rto = norm8[7];
+    }
     affine_normalize(T, norm8[3], norm8[7], norm8, norm8 + 4);
   }
   std::vector<double> x(12);
@@ -1463,6 +1498,145 @@ extern "C" int lrr_objpar_refine(lrr_est* e, int dir, int max_evals, double* f_s
   if ((rc = push_scal(e, dir)) != LRR_OK) return rc;
   e->werr_cache_valid = false;
   if (f_start) *f_start = fs; if (f_end) *f_end = fe; if (n_evals) *n_evals = ev; if (converged) *converged = (fs - fe) < 1e-4;
+  return LRR_OK;
+}
+
+// ---- CDC E-step: covariance-driven radius matching (cdcl_estimation<3,12>::compute_weights, cdcl/cdcl_estimation.txx:342-545) ---------
+static int cdc_check(lrr_est* e, int dir) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx;
+  if (e->dof != 12 || e->dim != 3) { ctx->err = "cdcl_estimation::compute_weights: only the affine <3,12> instantiation is built"; return LRR_ERR_UNSUPPORTED; }
+  if (!e->d[dir].from_all->C6 || !e->d[dir].to_all->C6) { ctx->err = "compute_weights needs feature covariances (C6)"; return LRR_ERR_STATE; }
+  if (e->d[dir].n_in <= 0 || e->d[dir].to_all->n <= 0) { ctx->err = "compute_weights: empty feature set"; return LRR_ERR_STATE; }
+  return LRR_OK;
+}
+extern "C" int lrr_cdc_compute_weights(lrr_est* e, int dir, int max_matches, double eval_multiplier, lrr_cdc_summary* out) {
+  touch(e);
+  int rc = cdc_check(e, dir); if (rc != LRR_OK) return rc;
+  if (max_matches <= 0 || !(eval_multiplier > 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; enter(ctx);
+  lrr_dir& d = e->d[dir];
+  cudaStream_t st = ctx->stream;
+  if ((rc = pull_scal(e, 1 << dir)) != LRR_OK) return rc;
+  const Scal& h = e->h[dir];
+  double* pin = (double*)ctx->pinned;
+  memcpy(pin, h.cov, 144 * sizeof(double));
+  CK(cudaMemcpyAsync(ctx->scratch_d, pin, 144 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int M = (int)d.n_in; const size_t nto = (size_t)d.to_all->n;
+  if (!d.cdc_rowcnt) {
+    CK(dmalloc(&d.cdc_rowcnt, 2 * d.cap + 4)); d.cdc_rowstart = d.cdc_rowcnt + d.cap; d.cdc_istat = d.cdc_rowcnt + 2 * d.cap;
+    CK(dmalloc(&d.cdc_roww, d.cap)); CK(dmalloc(&d.cdc_tow, nto + 1)); d.cdc_dsum = d.cdc_tow + nto;
+    CK(dmalloc(&d.cdc_cursor, 1));
+  }
+  const int blocks = lrr_cdc_blocks(M);
+  const size_t scratch = lrr_cdc_scratch_entries(blocks);
+  if (scratch > d.cdc_scratch) {
+    dfree(d.cdc_cand); dfree(d.cdc_candw); d.cdc_cand = nullptr; d.cdc_candw = nullptr; d.cdc_scratch = 0;
+    CK(dmalloc(&d.cdc_cand, scratch)); CK(dmalloc(&d.cdc_candw, scratch)); d.cdc_scratch = scratch;
+  }
+  int64_t want = (int64_t)M * std::min(max_matches, 48);
+  d.cdc_active = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (want > d.cdc_ecap) {
+      dfree(d.cdc_efrom); dfree(d.cdc_eslot); dfree(d.cdc_ew); d.cdc_efrom = d.cdc_eslot = nullptr; d.cdc_ew = nullptr; d.cdc_ecap = 0;
+      if (want > 0x7fffffffLL) { ctx->err = "compute_weights: more than 2^31 match entries"; return LRR_ERR_UNSUPPORTED; }
+      CK(dmalloc(&d.cdc_efrom, (size_t)want)); CK(dmalloc(&d.cdc_eslot, (size_t)want)); CK(dmalloc(&d.cdc_ew, (size_t)want)); d.cdc_ecap = want;
+    }
+    CK(cudaMemsetAsync(d.cdc_cursor, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(d.cdc_tow, 0, (nto + 1) * sizeof(double), st));
+    { int* ip = (int*)(pin + 256); ip[0] = 0; ip[1] = 0x7fffffff; ip[2] = 0; ip[3] = 0;
+      CK(cudaMemcpyAsync(d.cdc_istat, ip, 4 * sizeof(int), cudaMemcpyHostToDevice, st)); }
+    CdcLaunch L;
+    L.A = h.A; L.t = h.t; L.c = h.c; L.Sigma_dev = ctx->scratch_d; L.eval_mult = eval_multiplier; L.max_matches = max_matches; L.M = M;
+    L.fx = d.fx; L.fy = d.fy; L.fz = d.fz; L.forig = d.subset ? d.forig : nullptr; L.to = d.to_all->dev; L.from_all = d.from_all->dev;
+    L.efrom = d.cdc_efrom; L.eslot = d.cdc_eslot; L.ew = d.cdc_ew; L.ecap = d.cdc_ecap; L.cursor = d.cdc_cursor;
+    L.rowcnt = d.cdc_rowcnt; L.rowstart = d.cdc_rowstart; L.roww = d.cdc_roww; L.tow = d.cdc_tow; L.dsum = d.cdc_dsum; L.istat = d.cdc_istat;
+    L.cand = d.cdc_cand; L.candw = d.cdc_candw; L.blocks = blocks;
+    { PHASE(PH_MATCH); lrr_k_cdc_match(L, st, &ctx->launches); }
+    CK(cudaMemcpyAsync(pin + 260, d.cdc_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pin + 261, d.cdc_dsum, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pin + 262, d.cdc_istat, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const int64_t entries = (int64_t) * (unsigned long long*)(pin + 260);
+    const int* is = (const int*)(pin + 262);
+    if (is[3]) { ctx->err = "compute_weights: a search ball holds more than 4096 fixed features"; return LRR_ERR_UNSUPPORTED; }
+    if (entries > d.cdc_ecap) { want = entries; continue; }   // the flat set did not fit: once more with the size the cursor reports
+    d.cdc_entries = entries; d.cdc_rows = is[0];
+    lrr_k_cdc_normalise((int)entries, d.cdc_efrom, d.cdc_eslot, d.cdc_ew, d.cdc_roww, d.cdc_tow, st, &ctx->launches);
+    d.cdc_active = entries > 0;   // no match at all: the caller falls back to find_closest_euclidean (:544)
+    if (out) {
+      out->rows = d.cdc_rows; out->entries = entries; out->min_matches = is[0] ? is[1] : 0; out->max_matches = is[2];
+      out->avg_largest_eval = pin[261] / (double)d.cdc_rows;   // divided by matches_.size(), summed over every from-feature (:375, :480)
+    }
+    return LRR_OK;
+  }
+  ctx->err = "compute_weights: the match set grew between two passes"; return LRR_ERR_STATE;
+}
+extern "C" int lrr_cdc_get_matches(lrr_est* e, int dir, int64_t cap_rows, int64_t cap_entries, int64_t* n_rows, int64_t* n_entries, int32_t* row_from,
+                                   int64_t* row_start, int32_t* to_idx, double* w) {
+  if (!e || dir < 0 || dir > (e->sym() ? 1 : 0)) return LRR_ERR_INVALID;
+  lrr_ctx* ctx = e->ctx; enter(ctx);
+  lrr_dir& d = e->d[dir];
+  if (!d.cdc_active) { ctx->err = "lrr_cdc_get_matches: no CDC match set"; return LRR_ERR_STATE; }
+  if (n_rows) *n_rows = d.cdc_rows; if (n_entries) *n_entries = d.cdc_entries;
+  if (!row_from && !row_start && !to_idx && !w) return LRR_OK;
+  if (cap_rows < d.cdc_rows || cap_entries < d.cdc_entries) return LRR_ERR_INVALID;
+  const size_t M = (size_t)d.n_in, E = (size_t)d.cdc_entries;
+  std::vector<int> rowcnt(M), rowstart(M), eslot(E), orig(d.to_all->n), forig;
+  std::vector<double> ew(E); std::vector<double4> pos(d.to_all->n);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(rowcnt.data(), d.cdc_rowcnt, M * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rowstart.data(), d.cdc_rowstart, M * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(eslot.data(), d.cdc_eslot, E * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ew.data(), d.cdc_ew, E * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pos.data(), d.to_all->pos4, pos.size() * sizeof(double4), cudaMemcpyDeviceToHost, st));
+  if (d.subset) { forig.resize(M); CK(cudaMemcpyAsync(forig.data(), d.forig, M * sizeof(int), cudaMemcpyDeviceToHost, st)); }
+  CK(cudaStreamSynchronize(st));
+  int64_t r = 0, pos_out = 0;
+  std::vector<std::pair<int, double>> row;
+  for (size_t i = 0; i < M; ++i) {
+    if (rowcnt[i] <= 0) continue;
+    row.clear();
+    for (int k = 0; k < rowcnt[i]; ++k) { const int sl = eslot[rowstart[i] + k]; long long ob; memcpy(&ob, &pos[sl].w, 8); row.push_back({(int)ob, ew[rowstart[i] + k]}); }
+    std::sort(row.begin(), row.end());
+    if (row_from) row_from[r] = d.subset ? forig[i] : (int32_t)i;
+    if (row_start) row_start[r] = pos_out;
+    for (auto& pr : row) { if (to_idx) to_idx[pos_out] = pr.first; if (w) w[pos_out] = pr.second; ++pos_out; }
+    ++r;
+  }
+  if (row_start) row_start[r] = pos_out;
+  return LRR_OK;
+}
+// the resolution switch at the end of the matching pass (cdcl/cdcl_estimation.txx:494-508); bitwise `&` of the reference kept as logic
+extern "C" int lrr_cdc_resolution_switch(double avg_largest_eval, const double* fixed_spacing, int res, int max_res, int allowed, int* new_res) {
+  if (!fixed_spacing || !new_res || res < 0 || res > max_res) return LRR_ERR_INVALID;
+  int r = res; bool not_restarted = true;
+  if (avg_largest_eval < 2.0 * fixed_spacing[r] && allowed && not_restarted) { if (r > 0) { --r; not_restarted = false; } }
+  if (r + 1 <= max_res && avg_largest_eval > 2.0 * fixed_spacing[r + 1] && allowed && not_restarted) { ++r; }
+  *new_res = r;
+  return LRR_OK;
+}
+// one EM iteration of cdcl_estimation<3,12>::one_iteration (cdcl/cdcl_estimation.txx:88-186) at a single resolution: weights; past
+// iteration startEM = 5 parameters and weights again; covariance.  converged = parameters && covariance && |Sigma|_F < 1e-3 (:185).
+extern "C" int lrr_cdc_one_iteration(lrr_est* e, int dir, unsigned iteration, int max_matches, double eval_multiplier, int* converged, lrr_cdc_summary* out) {
+  int rc = cdc_check(e, dir); if (rc != LRR_OK) return rc;
+  const unsigned startEM = 5;
+  lrr_cdc_summary s; memset(&s, 0, sizeof(s));
+  if ((rc = lrr_cdc_compute_weights(e, dir, max_matches, eval_multiplier, &s)) != LRR_OK) return rc;
+  if (s.entries == 0) { e->ctx->err = "cdc one_iteration: the covariance is too small for any match (fall back to find_closest_euclidean, :544)"; return LRR_ERR_STATE; }
+  int par_conv = 0, cov_conv = 0;
+  double fs = 0, fe = 0; int ev = 0;
+  if (iteration > startEM) {
+    if ((rc = lrr_objpar_refine(e, dir, 5, &fs, &fe, &ev, &par_conv)) != LRR_OK) return rc;
+    if ((rc = lrr_cdc_compute_weights(e, dir, max_matches, eval_multiplier, &s)) != LRR_OK) return rc;
+    if (s.entries == 0) { e->ctx->err = "cdc one_iteration: no match after the parameter step"; return LRR_ERR_STATE; }
+  }
+  if ((rc = lrr_objcov_refine(e, dir, 5, &fs, &fe, &ev)) != LRR_OK) return rc;
+  cov_conv = (fs - fe) < 1e-5;   // (:300)
+  double fro = 0; for (int i = 0; i < 144; ++i) fro += e->h[dir].cov[i] * e->h[dir].cov[i];
+  if (converged) *converged = par_conv && cov_conv && std::sqrt(fro) < 1e-3;
+  if (out) *out = s;
   return LRR_OK;
 }
 

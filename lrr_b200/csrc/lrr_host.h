@@ -69,6 +69,13 @@ struct lrr_dir {
   double initial_scale = 0;
   uint64_t shuffle_calls = 0;        // RESHUFFLE: find_closest calls so far (selects the permutation key)
   unsigned int perm_key[4] = {0, 0, 0, 0}; int perm_half = 0;
+  // many-to-many match set of the CDC E-step (lrr_cdc_compute_weights, lrr_cdc.cu): flat entries (compact from index, neighbour slot,
+  // weight), per-from-feature rows, per-to-feature weight sums.  While cdc_active the objective entry points (lrr_objcov_*,
+  // lrr_objpar_*) run over this set instead of the 1-NN matches; any new 1-NN match drops it.
+  int *cdc_efrom = nullptr, *cdc_eslot = nullptr, *cdc_rowcnt = nullptr, *cdc_rowstart = nullptr, *cdc_istat = nullptr;
+  double *cdc_ew = nullptr, *cdc_roww = nullptr, *cdc_tow = nullptr, *cdc_dsum = nullptr, *cdc_candw = nullptr;
+  int2* cdc_cand = nullptr; unsigned long long* cdc_cursor = nullptr;
+  int64_t cdc_ecap = 0, cdc_entries = 0, cdc_rows = 0; size_t cdc_scratch = 0; bool cdc_active = false;
 };
 
 struct lrr_est {

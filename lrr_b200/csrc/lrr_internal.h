@@ -270,6 +270,20 @@ void lrr_k_export_matches(const DirArgs& a, int* from_idx, int* to_idx, cudaStre
 void lrr_k_objcov(const DirArgs& a, int dof, const double* U /*dof x dof upper, device*/, int want_g, double* partials,
                   unsigned int* ticket, cudaStream_t st, long long* launches);
 
+// ---- CDC E-step: covariance-driven radius matching (lrr_cdc.cu) -----------------------------------------
+struct CdcLaunch {
+  const double *A, *t, *c, *Sigma_dev; double eval_mult; int max_matches, M;
+  const double *fx, *fy, *fz; const int* forig; FsetDev to, from_all;
+  int *efrom, *eslot; double* ew; long long ecap; unsigned long long* cursor; int *rowcnt, *rowstart; double *roww, *tow, *dsum; int* istat;
+  int2* cand; double* candw; int blocks;
+};
+int lrr_cdc_blocks(int M);
+size_t lrr_cdc_scratch_entries(int blocks);
+void lrr_k_cdc_match(const CdcLaunch& L, cudaStream_t st, long long* launches);
+void lrr_k_cdc_normalise(int n, const int* efrom, const int* eslot, double* ew, const double* roww, const double* tow, cudaStream_t st, long long* launches);
+void lrr_k_cdc_norm(int M, int nto, const double* fx, const double* fy, const double* fz, const int* rowcnt, const double* tow, const double4* pos4,
+                    double* out10, cudaStream_t st, long long* launches);
+
 // ---- sort / MUSE (lrr_select.cu) -------------------------------------------------------------------
 struct SortScratch { double* keys2; unsigned int* hist; size_t cap; };
 cudaError_t lrr_sort_alloc(SortScratch* s, size_t cap);

@@ -310,7 +310,7 @@ int lrro_objcov_refine(lrro_est* e, int d, int max_evals, double* f_start, doubl
 int lrro_objpar_eval(lrro_est* e, int d, const double* theta, double* f, double* g) {
   FwdEst* fe = e->dir(d); if (!fe || fe->trans_->dof != 12) return LRR_ERR_UNSUPPORTED;
   Trans saved = *fe->trans_;
-  ObjFunPar obj(fe->matches_, *fe->trans_);
+  ObjFunPar obj(fe->matches_, *fe->trans_); obj.n_objects = (double)fe->cdc_rows;
   obj.compute(theta, f, g);
   *fe->trans_ = saved;
   return LRR_OK;
@@ -322,7 +322,7 @@ int lrro_objpar_refine(lrro_est* e, int d, int max_evals, double* f_start, doubl
   Trans& tr = *fe->trans_;
   double cm[3] = {0, 0, 0}, cf[3] = {0, 0, 0}, rm = 0, rf = 0;
   if (fe->normalize_matches_) { fe->normalize_matches_fn(cm, rm, cf, rf); tr.normalize(rm, rf, cm, cf); }
-  ObjFunPar obj(fe->matches_, tr);
+  ObjFunPar obj(fe->matches_, tr); obj.n_objects = (double)fe->cdc_rows;
   std::vector<double> x(12);
   for (int i = 0; i < 9; ++i) x[i] = tr.A[i];
   for (int i = 0; i < 3; ++i) x[9 + i] = tr.t[i];
@@ -331,6 +331,55 @@ int lrro_objpar_refine(lrro_est* e, int d, int max_evals, double* f_start, doubl
   tr.set_parameterization(x.data());
   if (fe->normalize_matches_) { tr.unnormalize(rm, rf, cm, cf); fe->unnormalize_matches_fn(cm, rm, cf, rf); }
   if (f_start) *f_start = fs; if (f_end) *f_end = fe_; if (n_evals) *n_evals = ev; if (converged) *converged = (fs - fe_) < 1e-4;
+  return LRR_OK;
+}
+
+// ---- CDC E-step (cdcl_estimation<3,12>::compute_weights, cdcl/cdcl_estimation.txx:342-545) ----------------------------------------------
+int lrro_cdc_compute_weights(lrro_est* e, int d, int max_matches, double eval_multiplier, lrr_cdc_summary* out) {
+  FwdEst* fe = e->dir(d); if (!fe || fe->trans_->dof != 12) return LRR_ERR_UNSUPPORTED;
+  if (max_matches <= 0 || !(eval_multiplier > 0)) return LRR_ERR_INVALID;
+  FwdEst::CdcSummary s = fe->cdc_compute_weights((unsigned)max_matches, eval_multiplier);
+  if (out) { out->rows = (int64_t)s.rows; out->entries = (int64_t)s.entries; out->min_matches = (int32_t)s.min_matches; out->max_matches = (int32_t)s.max_matches; out->avg_largest_eval = s.avg_largest_eval; }
+  return LRR_OK;
+}
+int lrro_cdc_get_matches(lrro_est* e, int d, int64_t cap_rows, int64_t cap_entries, int64_t* n_rows, int64_t* n_entries, int32_t* row_from,
+                         int64_t* row_start, int32_t* to_idx, double* w) {
+  FwdEst* fe = e->dir(d); if (!fe) return LRR_ERR_INVALID;
+  if (fe->cdc_row_of.empty()) return LRR_ERR_STATE;
+  if (n_rows) *n_rows = (int64_t)fe->cdc_rows; if (n_entries) *n_entries = (int64_t)fe->matches_.size();
+  if (!row_from && !row_start && !to_idx && !w) return LRR_OK;
+  if (cap_rows < (int64_t)fe->cdc_rows || cap_entries < (int64_t)fe->matches_.size()) return LRR_ERR_INVALID;
+  for (size_t k = 0; k < fe->matches_.size(); ++k) {
+    if (fe->first_of_row(k)) { const int r = fe->cdc_row_of[k]; if (row_from) row_from[r] = fe->matches_[k].from->id; if (row_start) row_start[r] = (int64_t)k; }
+    if (to_idx) to_idx[k] = fe->matches_[k].to->id;
+    if (w) w[k] = fe->matches_[k].w;
+  }
+  if (row_start) row_start[fe->cdc_rows] = (int64_t)fe->matches_.size();
+  return LRR_OK;
+}
+int lrro_cdc_resolution_switch(double avg_largest_eval, const double* fixed_spacing, int res, int max_res, int allowed, int* new_res) {
+  if (!fixed_spacing || !new_res || res < 0 || res > max_res) return LRR_ERR_INVALID;
+  int r = res; bool not_restarted = true;
+  if (avg_largest_eval < 2.0 * fixed_spacing[r] && allowed && not_restarted) { if (r > 0) { --r; not_restarted = false; } }
+  if (r + 1 <= max_res && avg_largest_eval > 2.0 * fixed_spacing[r + 1] && allowed && not_restarted) { ++r; }
+  *new_res = r; return LRR_OK;
+}
+int lrro_cdc_one_iteration(lrro_est* e, int d, unsigned iteration, int max_matches, double eval_multiplier, int* converged, lrr_cdc_summary* out) {
+  FwdEst* fe = e->dir(d); if (!fe || fe->trans_->dof != 12) return LRR_ERR_UNSUPPORTED;
+  lrr_cdc_summary s; int rc;
+  if ((rc = lrro_cdc_compute_weights(e, d, max_matches, eval_multiplier, &s)) != LRR_OK) return rc;
+  if (s.entries == 0) return LRR_ERR_STATE;
+  int par_conv = 0; double fs = 0, fe_ = 0; int ev = 0;
+  if (iteration > 5) {
+    if ((rc = lrro_objpar_refine(e, d, 5, &fs, &fe_, &ev, &par_conv)) != LRR_OK) return rc;
+    if ((rc = lrro_cdc_compute_weights(e, d, max_matches, eval_multiplier, &s)) != LRR_OK) return rc;
+    if (s.entries == 0) return LRR_ERR_STATE;
+  }
+  if ((rc = lrro_objcov_refine(e, d, 5, &fs, &fe_, &ev)) != LRR_OK) return rc;
+  const int cov_conv = (fs - fe_) < 1e-5;
+  double fro = 0; for (double v : fe->trans_->covar) fro += v * v;
+  if (converged) *converged = par_conv && cov_conv && std::sqrt(fro) < 1e-3;
+  if (out) *out = s;
   return LRR_OK;
 }
 

@@ -35,6 +35,7 @@
 #include <limits>
 #include <memory>
 #include <set>
+#include <map>
 #include <vector>
 #include <algorithm>
 #include <numeric>
@@ -221,6 +222,19 @@ struct KdTree {
     double best = std::numeric_limits<double>::infinity(); int bi = -1;
     if (n > 0) search(0, q, best, bi);
     return bi;
+  }
+  // rsdl_kd_tree::points_in_radius: every point with |q - p|^2 <= r2, returned in ascending index order (the order is the
+  // library's own and unpinned; the caller shuffles it anyway, cdcl/cdcl_estimation.txx:396)
+  void radius_rec(int ni, const double* q, double r2, std::vector<int>& out) const {
+    const Node& nd = nodes[ni];
+    if (box_d2(nd, q) * (1.0 - 1e-12) > r2) return;
+    if (nd.left < 0) { for (int i = nd.lo; i < nd.hi; ++i) { int j = perm[i]; if (dist2(q, &pts[3 * j]) <= r2) out.push_back(j); } return; }
+    radius_rec(nd.left, q, r2, out); radius_rec(nd.right, q, r2, out);
+  }
+  void points_in_radius(const double* q, double radius, std::vector<int>& out) const {
+    out.clear();
+    if (n > 0) radius_rec(0, q, radius * radius, out);
+    std::sort(out.begin(), out.end());
   }
   int nearest_brute(const double* q) const {
     double best = std::numeric_limits<double>::infinity(); int bi = -1;
@@ -471,6 +485,11 @@ struct FwdEst {
   double initial_scale = std::numeric_limits<double>::quiet_NaN();
   double last_scale = 0;
   double last_norm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cm[3], rm, cf[3], rf
+  // many-to-many matches of the CDC E-step (cdc_compute_weights): matches_ then holds one entry per (from, to) pair, row after row,
+  // and cdc_row_of[k] is the row (cdcl_match object) entry k belongs to.  Empty: the ordinary one-to-one matches.
+  std::vector<int> cdc_row_of; size_t cdc_rows = 0;
+  bool first_of_row(size_t k) const { return cdc_row_of.empty() || k == 0 || cdc_row_of[k] != cdc_row_of[k - 1]; }
+  size_t match_objects() const { return cdc_row_of.empty() ? matches_.size() : cdc_rows; }
 
   // ctor #2 (cdcl :73-91, rrl :89-113)
   FwdEst(int flavor_, const std::vector<FeatureP>& moving, const std::vector<FeatureP>& fixed, TransP trans,
@@ -618,7 +637,7 @@ struct FwdEst {
       FeistelPerm perm(shuffle_seed, shuffle_dir, shuffle_calls++, (uint32_t)moving_base_.size());
       for (size_t k = 0; k < moving_base_.size(); ++k) moving_[k] = moving_base_[perm((uint32_t)k)];
     }
-    matches_.clear();
+    matches_.clear(); cdc_row_of.clear(); cdc_rows = 0;
     for (size_t i = 0; i < number_points_; ++i) {
       FeatureP p = moving_[i];
       double y[3]; trans_->map_loc(p->loc, y);
@@ -697,22 +716,28 @@ struct FwdEst {
   void normalize_matches_fn(double* cm, double& rm, double* cf, double& rf) {
     cm[0] = cm[1] = cm[2] = 0; cf[0] = cf[1] = cf[2] = 0; rm = 0; rf = 0;
     std::set<Feature*> fixed_matched;
-    for (auto& m : matches_) {
-      for (int d = 0; d < 3; ++d) cm[d] += m.from->loc[d];
+    const double nobj = double(match_objects());   // matches_.size() of the reference: one cdcl_match per from-feature
+    for (size_t k = 0; k < matches_.size(); ++k) {
+      auto& m = matches_[k];
+      if (first_of_row(k)) for (int d = 0; d < 3; ++d) cm[d] += m.from->loc[d];
       if (fixed_matched.insert(m.to.get()).second) for (int d = 0; d < 3; ++d) cf[d] += m.to->loc[d];
     }
-    for (int d = 0; d < 3; ++d) { cm[d] /= double(matches_.size()); cf[d] /= double(fixed_matched.size()); }
+    for (int d = 0; d < 3; ++d) { cm[d] /= nobj; cf[d] /= double(fixed_matched.size()); }
     auto mag = [](const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
-    for (auto& m : matches_) {
+    for (size_t k = 0; k < matches_.size(); ++k) {
+      if (!first_of_row(k)) continue;
+      auto& m = matches_[k];
       for (int d = 0; d < 3; ++d) m.from->loc[d] -= cm[d];
       rm += mag(m.from->loc);
     }
-    rm /= double(matches_.size());
+    rm /= nobj;
     for (Feature* q : fixed_matched) { for (int d = 0; d < 3; ++d) q->loc[d] -= cf[d]; rf += mag(q->loc); }
     rf /= double(fixed_matched.size());
-    for (auto& m : matches_) {
+    for (size_t k = 0; k < matches_.size(); ++k) {
+      if (!first_of_row(k)) continue;
+      auto& m = matches_[k];
       for (int d = 0; d < 3; ++d) m.from->loc[d] /= rm;
-      if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) m.from->cov[k] /= (rm * rm);
+      if (flavor != FLAVOR_RRL) for (int i = 0; i < 9; ++i) m.from->cov[i] /= (rm * rm);
     }
     for (Feature* q : fixed_matched) {
       for (int d = 0; d < 3; ++d) q->loc[d] /= rf;
@@ -724,14 +749,85 @@ struct FwdEst {
   // cdcl_unnormalize_matches (cdcl :1245-1286, rrl :948-986)
   void unnormalize_matches_fn(const double* cm, double rm, const double* cf, double rf) {
     std::set<Feature*> fixed_matched;
-    for (auto& m : matches_) {
-      for (int d = 0; d < 3; ++d) { m.from->loc[d] *= rm; m.from->loc[d] += cm[d]; }
-      if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) m.from->cov[k] *= (rm * rm);
+    for (size_t k = 0; k < matches_.size(); ++k) {
+      auto& m = matches_[k];
+      if (first_of_row(k)) {
+        for (int d = 0; d < 3; ++d) { m.from->loc[d] *= rm; m.from->loc[d] += cm[d]; }
+        if (flavor != FLAVOR_RRL) for (int i = 0; i < 9; ++i) m.from->cov[i] *= (rm * rm);
+      }
       if (fixed_matched.insert(m.to.get()).second) {
         for (int d = 0; d < 3; ++d) { m.to->loc[d] *= rf; m.to->loc[d] += cf[d]; }
-        if (flavor != FLAVOR_RRL) for (int k = 0; k < 9; ++k) m.to->cov[k] *= (rf * rf);
+        if (flavor != FLAVOR_RRL) for (int i = 0; i < 9; ++i) m.to->cov[i] *= (rf * rf);
       }
     }
+  }
+
+  // cdcl_estimation<dim,dof>::compute_weights (cdcl/cdcl_estimation.txx:342-545) at one resolution, shuffle = identity (Q4):
+  // covariance-driven radius search, Mahalanobis Beaton-Tukey weights, normalisation by the row and to-feature sums.
+  struct CdcSummary { size_t rows = 0, entries = 0; unsigned min_matches = 0, max_matches = 0; double avg_largest_eval = 0; };
+  static double largest_evalue3(const double* C) { double V[9], D[3]; sym_eig3(C, V, D); return D[2]; }   // cdcl_utils.h:284-292
+  CdcSummary cdc_compute_weights(unsigned max_matches_allowed, double eval_multiplier) {
+    const int dof = trans_->dof;
+    const double* Jp = trans_->A;   // jacobian_wrt_loc
+    std::map<Feature*, double> to_weights; std::vector<double> from_weights;
+    std::vector<double> J(3 * dof), T(3 * dof);
+    unsigned min_matches = 99999, max_matches = 0;
+    double avg_largest_eval = 0.0;
+    matches_.clear(); cdc_row_of.clear(); cdc_rows = 0;
+    std::vector<int> indices;
+    for (size_t i = 0; i < moving_.size(); ++i) {
+      FeatureP p = moving_[i];
+      double y[3]; trans_->map_loc(p->loc, y);
+      trans_->jacobian_wrt_par(p->loc, J.data());
+      double Cij_p[9];   // transfer_covar( Jth ) = Jth covar Jth^T
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < dof; ++b) { double s = 0; for (int k = 0; k < dof; ++k) s += J[a * dof + k] * trans_->covar[k * dof + b]; T[a * dof + b] = s; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < dof; ++k) s += T[a * dof + k] * J[b * dof + k]; Cij_p[a * 3 + b] = s; }
+      avg_largest_eval += std::sqrt(largest_evalue3(Cij_p));
+      double JC[9];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += Jp[a * 3 + k] * p->cov[k * 3 + b]; JC[a * 3 + b] = s; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += JC[a * 3 + k] * Jp[b * 3 + k]; Cij_p[a * 3 + b] += s; }
+      const double radius = eval_multiplier * std::sqrt(largest_evalue3(Cij_p));
+      kd_->points_in_radius(y, radius, indices);
+      double sum_w = 0.0;
+      if (!indices.empty()) {
+        const size_t possible = std::min<size_t>(max_matches_allowed, indices.size());
+        size_t kept = 0;
+        for (size_t j = 0; j < possible; ++j) {
+          FeatureP q = fixed_[indices[j]];
+          const double err[3] = {y[0] - q->loc[0], y[1] - q->loc[1], y[2] - q->loc[2]};
+          double Cij[9], Ci[9];
+          for (int k = 0; k < 9; ++k) Cij[k] = Cij_p[k] + q->cov[k];
+          inv3(Cij, Ci);
+          double v[3]; for (int a = 0; a < 3; ++a) v[a] = Ci[a * 3] * err[0] + Ci[a * 3 + 1] * err[1] + Ci[a * 3 + 2] * err[2];
+          const double residual = err[0] * v[0] + err[1] * v[1] + err[2] * v[2];
+          const double w0 = cdc_weight(residual);
+          if (w0 > 0.0) {
+            matches_.push_back(Match{p, q, w0}); cdc_row_of.push_back((int)cdc_rows);
+            to_weights[q.get()] += w0;
+            sum_w += w0; ++kept;
+          }
+        }
+        if (kept > 0) {
+          from_weights.push_back(sum_w); ++cdc_rows;
+          if (kept < min_matches) min_matches = (unsigned)kept;
+          if (kept > max_matches) max_matches = (unsigned)kept;
+        }
+      }
+    }
+    avg_largest_eval /= double(cdc_rows);
+    for (size_t k = 0; k < matches_.size(); ++k) {   // :523-536
+      const double wi = from_weights[cdc_row_of[k]], wj = to_weights[matches_[k].to.get()];
+      matches_[k].w = matches_[k].w * matches_[k].w / (wi * wj);
+    }
+    CdcSummary s; s.rows = cdc_rows; s.entries = matches_.size(); s.min_matches = cdc_rows ? min_matches : 0; s.max_matches = max_matches; s.avg_largest_eval = avg_largest_eval;
+    if (matches_.empty()) { cdc_row_of.clear(); cdc_rows = 0; }   // (:544: the caller falls back to find_closest_euclidean)
+    return s;
+  }
+  // weight(): Beaton-Tukey with b = 4 times f = 2.9872 (cdcl/cdcl_utils.h:209-224)
+  static double cdc_weight(double residual) {
+    const double b_2 = 16.0, f = 2.9872;
+    if (residual <= b_2) return f * (1 - residual / b_2) * (1 - residual / b_2);
+    return 0;
   }
 
   // AtA += J^T P J w ; Atb += J^T P q_loc w   (cdcl :1061-1062), dense like the vnl products.
@@ -1129,6 +1225,7 @@ struct ObjFunPar {
   const std::vector<Match>& matches_;
   Trans& trans_;
   std::vector<double> JCthJ_;   // 9 per match
+  double n_objects = 0;         // > 0: the entries are the flattened rows of a many-to-many set with this many cdcl_match objects
   ObjFunPar(const std::vector<Match>& matches, Trans& trans) : matches_(matches), trans_(trans) {
     const int dof = trans_.dof;
     std::vector<double> J(3 * dof), T(3 * dof);
@@ -1176,7 +1273,7 @@ struct ObjFunPar {
         }
       }
     }
-    const double n = (double)matches_.size();
+    const double n = n_objects > 0 ? n_objects : (double)matches_.size();   // matches_.size() = cdcl_match objects (rows of a many-to-many set)
     if (f) *f = fv / n;
     if (g) for (int k = 0; k < dof; ++k) g[k] = gv[k] * (1.0 / n);
   }

@@ -7,7 +7,12 @@
 
 struct lrrr_ctx { std::string err; };
 struct lrrr_fset { lrrr_ctx* ctx; std::vector<RefFeat> base; int dim = 3; };
-struct lrrr_est { lrrr_ctx* ctx; int kind, dof; RefEst* impl; };
+struct lrrr_est {
+  lrrr_ctx* ctx; int kind, dof; RefEst* impl;
+  // for the CDC E-step (lrrr_cdc_*): the parent sets, the moving subset and the many-to-many estimator built on demand
+  lrrr_fset *moving_all = nullptr, *fixed_all = nullptr; std::vector<int32_t> msub; bool has_sub = false; RefCdc* cdc = nullptr;
+  void drop_cdc() { delete cdc; cdc = nullptr; }
+};
 
 extern "C" {
 int lrrr_ctx_create(int, lrrr_ctx** out) { *out = new lrrr_ctx(); return LRR_OK; }
@@ -62,24 +67,28 @@ int lrrr_est_create(lrrr_ctx* ctx, int kind, int dim, int dof, lrrr_fset* moving
   RefEst* impl = (kind == LRR_CDCL_FWD || kind == LRR_CDCL_SYM) ? lrr_ref_make_cdcl(kind, dof, moving_all->base, fixed_all->base)
                                                                  : lrr_ref_make_rrl(kind, dof, moving_all->base, fixed_all->base);
   if (!impl) return LRR_ERR_UNSUPPORTED;
-  lrrr_est* e = new lrrr_est(); e->ctx = ctx; e->kind = kind; e->dof = dof; e->impl = impl;
+  lrrr_est* e = new lrrr_est(); e->ctx = ctx; e->kind = kind; e->dof = dof; e->impl = impl; e->moving_all = moving_all; e->fixed_all = fixed_all;
   *out = e; return LRR_OK;
 }
-void lrrr_est_destroy(lrrr_est* e) { if (e) { delete e->impl; delete e; } }
-int lrrr_est_set_subsets(lrrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) { e->impl->set_subsets(mi, nm, fi, nf); return LRR_OK; }
+void lrrr_est_destroy(lrrr_est* e) { if (e) { delete e->cdc; delete e->impl; delete e; } }
+int lrrr_est_set_subsets(lrrr_est* e, const int32_t* mi, int64_t nm, const int32_t* fi, int64_t nf) {
+  e->impl->set_subsets(mi, nm, fi, nf); e->drop_cdc();
+  e->has_sub = mi != nullptr; e->msub.assign(mi ? mi : nullptr, mi ? mi + nm : nullptr);
+  return LRR_OK;
+}
 int lrrr_est_set_transform(lrrr_est* e, int tk, const double* A9, const double* t3, const double* c3, const double* cov) {
   if ((tk == LRR_TRANS_AFFINE) != (e->dof == 12) || (tk == LRR_TRANS_SIMILARITY2D) != (e->dof == 4)) return LRR_ERR_INVALID;
   RefTrans t; t.kind = tk; std::memcpy(t.A, A9, 72); std::memcpy(t.t, t3, 24);
   if (c3) std::memcpy(t.c, c3, 24); else std::memset(t.c, 0, 24);
   if (cov) t.cov.assign(cov, cov + e->dof * e->dof);
-  e->impl->set_transform(t); return LRR_OK;
+  e->impl->set_transform(t); e->drop_cdc(); return LRR_OK;
 }
 int lrrr_est_set_flags(lrrr_est* e, int normalize, int wbs) { e->impl->set_flags(normalize, wbs); return LRR_OK; }
 // the reference's order policy is vcl_random_shuffle (Q4); the stand-in routes it through a hook: mode 0 = keep the given order
 int lrrr_est_set_shuffle(lrrr_est*, int mode, uint64_t seed) { lrr_ref_set_shuffle(mode, seed); return LRR_OK; }
 int lrrr_est_set_number_points(lrrr_est* e, int d, int64_t m, int* at_max) { return e->impl->set_number_points(d, m, at_max) ? LRR_OK : LRR_ERR_INVALID; }
-int lrrr_est_find_closest(lrrr_est* e) { e->impl->find_closest(); return LRR_OK; }
-int lrrr_est_one_iteration(lrrr_est* e, unsigned it, int* conv) { bool c = e->impl->one_iteration(it); if (conv) *conv = c; return LRR_OK; }
+int lrrr_est_find_closest(lrrr_est* e) { e->drop_cdc(); e->impl->find_closest(); return LRR_OK; }
+int lrrr_est_one_iteration(lrrr_est* e, unsigned it, int* conv) { e->drop_cdc(); bool c = e->impl->one_iteration(it); if (conv) *conv = c; return LRR_OK; }
 int lrrr_est_run(lrrr_est* e, int max_iter, int* conv, int* iters) {
   bool c = false; int it = 0;
   while (!c && it < max_iter) { c = e->impl->one_iteration((unsigned)it); ++it; }   // cdcl :413-428 / driver loop rrl/itkLocationRegistration.cxx:2418
@@ -101,8 +110,36 @@ int lrrr_est_estimate_ls_backward(lrrr_est* e, int ep) { return e->impl->estimat
 int lrrr_est_transfer_cov(lrrr_est* e, int d, double* S9) { return e->impl->transfer_cov(d, S9) ? LRR_OK : LRR_ERR_INVALID; }
 int lrrr_est_get_state(lrrr_est* e, lrr_est_state* s) { e->impl->get_state(s); return LRR_OK; }
 int lrrr_est_oscillated(lrrr_est* e, int* out) { *out = e->impl->oscillated(); return LRR_OK; }
-int lrrr_objcov_eval(lrrr_est* e, int d, const double* x, double* f, double* g) { return e->impl->objcov_eval(d, x, f, g) ? LRR_OK : LRR_ERR_UNSUPPORTED; }
-int lrrr_objpar_eval(lrrr_est* e, int d, const double* x, double* f, double* g) { return e->impl->objpar_eval(d, x, f, g) ? LRR_OK : LRR_ERR_UNSUPPORTED; }
+int lrrr_objcov_eval(lrrr_est* e, int d, const double* x, double* f, double* g) {
+  if (e->cdc && d == 0) return e->cdc->objcov(x, f, g) ? LRR_OK : LRR_ERR_STATE;
+  return e->impl->objcov_eval(d, x, f, g) ? LRR_OK : LRR_ERR_UNSUPPORTED;
+}
+int lrrr_objpar_eval(lrrr_est* e, int d, const double* x, double* f, double* g) {
+  if (e->cdc && d == 0) return e->cdc->objpar(x, f, g) ? LRR_OK : LRR_ERR_STATE;
+  return e->impl->objpar_eval(d, x, f, g) ? LRR_OK : LRR_ERR_UNSUPPORTED;
+}
+// cdcl_estimation<3,12>::compute_weights of the REFERENCE (lrr_ref_cdc.cpp) on the estimator's moving subset / fixed set under its
+// current transform and covariance.  The cap of 100 and the multiplier 5.0 are constants of the reference's source (:356-359).
+int lrrr_cdc_compute_weights(lrrr_est* e, int d, int max_matches, double eval_multiplier, lrr_cdc_summary* out) {
+  if (d != 0 || e->dof != 12 || e->kind == LRR_CDCL_ICP) return LRR_ERR_UNSUPPORTED;
+  if (max_matches != 100 || eval_multiplier != 5.0) return LRR_ERR_UNSUPPORTED;
+  RefTrans t; if (!e->impl->get_transform(0, t)) return LRR_ERR_INVALID;
+  e->drop_cdc();
+  e->cdc = lrr_ref_make_cdc(e->moving_all->base, e->has_sub ? e->msub.data() : nullptr, (int64_t)e->msub.size(), e->fixed_all->base);
+  e->cdc->set_transform(t);
+  return e->cdc->compute_weights(out) ? LRR_OK : LRR_ERR_STATE;
+}
+int lrrr_cdc_get_matches(lrrr_est* e, int d, int64_t cap_rows, int64_t cap_entries, int64_t* n_rows, int64_t* n_entries, int32_t* row_from,
+                         int64_t* row_start, int32_t* to_idx, double* w) {
+  if (d != 0 || !e->cdc) return LRR_ERR_STATE;
+  if (n_rows) *n_rows = e->cdc->rows(); if (n_entries) *n_entries = e->cdc->entries();
+  if (!row_from && !row_start && !to_idx && !w) return LRR_OK;
+  if (cap_rows < e->cdc->rows() || cap_entries < e->cdc->entries()) return LRR_ERR_INVALID;
+  e->cdc->get_matches(row_from, row_start, to_idx, w);
+  return LRR_OK;
+}
+// cdcl_normalize_matches of the reference over its many-to-many set: (cm, rm, cf, rf)
+int lrrr_test_cdc_normalisation(lrrr_est* e, double* norm8) { if (!e->cdc) return LRR_ERR_STATE; e->cdc->normalisation(norm8); return LRR_OK; }
 
 double lrrr_test_weight_BT(double u) { return lrr_ref_weight_BT(u); }
 double lrrr_test_rho(double u) { return lrr_ref_rho(u); }

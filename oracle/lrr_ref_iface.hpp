@@ -34,6 +34,20 @@ struct RefEst {
   virtual bool objpar_eval(int dir, const double* theta, double* f, double* g) = 0;
 };
 
+// the full CDC estimator's E-step (cdcl_estimation<3,12>::compute_weights, lrr_ref_cdc.cpp)
+struct RefCdc {
+  virtual ~RefCdc() {}
+  virtual void set_transform(const RefTrans& t) = 0;
+  virtual bool compute_weights(lrr_cdc_summary* out) = 0;
+  virtual int64_t rows() const = 0;
+  virtual int64_t entries() const = 0;
+  virtual void get_matches(int32_t* row_from, int64_t* row_start, int32_t* to_idx, double* w) = 0;
+  virtual bool objcov(const double* x, double* f, double* g) = 0;
+  virtual bool objpar(const double* theta, double* f, double* g) = 0;
+  virtual void normalisation(double* norm8) = 0;
+};
+RefCdc* lrr_ref_make_cdc(const std::vector<RefFeat>& moving, const int32_t* mi, int64_t nm, const std::vector<RefFeat>& fixed);
+
 RefEst* lrr_ref_make_cdcl(int kind, int dof, const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);
 RefEst* lrr_ref_make_rrl(int kind, int dof, const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);
 RefEst* lrr_ref_make_icp2d(const std::vector<RefFeat>& moving, const std::vector<RefFeat>& fixed);   // cdcl_estimation_ICP<2,4> (lrr_ref_icp2d.cpp)
