@@ -553,7 +553,7 @@ def run_b200(args, rank, world, local_rank):
     e2e_value = world * e2e_iters / float(te[0]) if e2e_iters else None
 
     # ---- batched location registration: the fixed C4 list sharded block-cyclically over the ranks ----
-    from lrr_b200.sharding import gather_results, run_batch_sharded
+    from lrr_b200.sharding import expected_costs, gather_results, run_batch_sharded
     bpair, bjobs = make_batch_workload(world)
     if args.only_iterations:
         bjobs = bjobs[:world]
@@ -562,10 +562,13 @@ def run_b200(args, rank, world, local_rank):
         run_batch_sharded(ctx, bmv, bfx, bjobs[: min(len(bjobs), 512 * world)], 70, BATCH_SEED, rank, world)   # warm-up (workspace allocation)
         barrier()
         tb0 = time.perf_counter()
-        local = run_batch_sharded(ctx, bmv, bfx, bjobs, 70, BATCH_SEED, rank, world)
+        # (N > 1: the shares are dealt over the jobs sorted by expected cost — lrr_batch_expected_cost, inside the timed region; within
+        #  a rank the backend hands its jobs out longest-expected-first either way)
+        bcosts = expected_costs(ctx, bmv, bfx, bjobs, world)
+        local = run_batch_sharded(ctx, bmv, bfx, bjobs, 70, BATCH_SEED, rank, world, costs=bcosts)
         torch.cuda.synchronize()
         tb_local = time.perf_counter() - tb0
-        full = gather_results(local, len(bjobs), rank, world, device=torch.device("cuda", local_rank) if world > 1 else None)
+        full = gather_results(local, len(bjobs), rank, world, device=torch.device("cuda", local_rank) if world > 1 else None, costs=bcosts)
         barrier()
     tb = torch.tensor([tb_local], dtype=torch.float64, device="cuda")
     if dist is not None:

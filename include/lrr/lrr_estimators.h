@@ -246,6 +246,63 @@ template <unsigned int dim, unsigned int dof> using cdcl_estimation_symmetric_IC
 template <unsigned int dim, unsigned int dof> using rrl_estimation_ICP_matching_all = estimation_impl<dim, dof, LRR_RRL_FWD>;
 template <unsigned int dim, unsigned int dof> using rrl_estimation_symmetric_ICP_matching_all = estimation_impl<dim, dof, LRR_RRL_SYM>;
 
+// ---- the full CDC estimator (cdcl/cdcl_estimation.h:20-100, .txx:66-545): EM over many-to-many matches ---------------------------------
+// cdcl_estimation<dim,dof> derives from the ICP estimator, which supplies its initialisation; here it sits on the matching-all forward
+// estimator of the path.  compute_weights = the E-step on the device (lrr_cdc_compute_weights), estimate_parameters / estimate_covariance
+// = L-BFGS over cdcl_obj_fun_par / cdcl_obj_fun_cov evaluated on the device over the many-to-many set.  One resolution level per
+// object: compute_weights reports avg_largest_eval, switch_resolution() gives the reference's decision (:494-508) and the caller
+// re-invokes set_moving_data with that level's features, as the driver of a multi-resolution run does.  <3,12> only.
+template <unsigned int dim, unsigned int dof>
+class cdcl_estimation : public estimation_impl<dim, dof, LRR_CDCL_FWD> {
+ public:
+  typedef estimation_impl<dim, dof, LRR_CDCL_FWD> icp;
+  typedef typename icp::feature_sptr_type feature_sptr_type;
+  typedef typename icp::trans_sptr_type trans_sptr_type;
+  typedef typename icp::display_callback_type display_callback_type;
+  cdcl_estimation(device_context& ctx, std::vector<feature_sptr_type> const& moving, std::vector<feature_sptr_type> const& fixed, trans_sptr_type const& trans)
+      : icp(ctx, moving, fixed, trans), cctx_(ctx) {}
+  // initialize(): initial weights by find_closest_euclidean, initial covariance by estimate_LS  (:69-84)
+  void initialize() override { icp::one_iteration(0, 0, 0); }
+  // compute_weights( resolution_switch_allowed )  (:342-545); returns false when the covariance is too small for any match — the
+  // reference then falls back to find_closest_euclidean (:544), and so does this
+  bool compute_weights(bool /*resolution_switch_allowed*/ = false) {
+    cctx_.check(lrr_cdc_compute_weights(this->handle(), LRR_DIR_FORWARD, 100, 5.0, &last_), "lrr_cdc_compute_weights");
+    if (last_.entries == 0) { this->find_closest_euclidean(); return false; }
+    return true;
+  }
+  lrr_cdc_summary const& last_weights() const { return last_; }
+  int switch_resolution(std::vector<double> const& fixed_spacing, int res, bool allowed) const {
+    int r = res;
+    lrr_cdc_resolution_switch(last_.avg_largest_eval, fixed_spacing.data(), res, (int)fixed_spacing.size() - 1, allowed, &r);
+    return r;
+  }
+  bool estimate_parameters() {   // (:207-262)
+    double fs = 0, fe = 0; int ev = 0, conv = 0;
+    cctx_.check(lrr_objpar_refine(this->handle(), LRR_DIR_FORWARD, 5, &fs, &fe, &ev, &conv), "lrr_objpar_refine");
+    return conv != 0;
+  }
+  bool estimate_covariance() {   // (:264-337)
+    double fs = 0, fe = 0; int ev = 0;
+    cctx_.check(lrr_objcov_refine(this->handle(), LRR_DIR_FORWARD, 5, &fs, &fe, &ev), "lrr_objcov_refine");
+    return (fs - fe) < 1e-5;
+  }
+  // one EM iteration: weights; past startEM = 5 parameters and weights again; covariance  (:88-186)
+  bool one_iteration(void* /*caller*/, display_callback_type /*display_points*/, unsigned int iteration) {
+    int conv = 0;
+    cctx_.check(lrr_cdc_one_iteration(this->handle(), LRR_DIR_FORWARD, iteration, 100, 5.0, &conv, &last_), "lrr_cdc_one_iteration");
+    return conv != 0;
+  }
+  bool run(void* caller = 0, display_callback_type display_points = 0) override {   // (:190-204): initialize, then at most 85 iterations
+    initialize();
+    bool converged = false; unsigned int iteration = 0;
+    while (!converged && iteration < 85) { converged = one_iteration(caller, display_points, iteration); ++iteration; }
+    return converged;
+  }
+ private:
+  device_context& cctx_;
+  lrr_cdc_summary last_ = lrr_cdc_summary();
+};
+
 // ---- planar demo estimator (BASELINE.json configs[0]) -----------------------------------------------------------
 typedef std::array<double, 2> vec2;
 typedef std::array<double, 4> mat2;   // row-major

@@ -284,6 +284,12 @@ int  lrr_batch_run_ids(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, 
 int  lrr_batch_run_multi(lrr_ctx** ctx, int ndev, lrr_fset** moving_all, lrr_fset** fixed_all, const lrr_job* jobs, int64_t njobs,
                          int max_iter, uint64_t shuffle_seed, lrr_result* out);
 
+/* Expected cost of every job before it runs: the features covered by its two ROI cubes (whole grid cells), 0 when a cube cannot
+ * reach the 1000-feature gate (:1632).  The batched entry points above hand their jobs out longest-expected-first by this figure
+ * (a job's time is iterations x ROI points; the makespan is set by the jobs still running when the queue is empty; switch:
+ * lrr_ctx_set_option "batch_sort"); a host that shards the list over processes balances the shares with it (lrr_b200/sharding.py). */
+int  lrr_batch_expected_cost(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int32_t* cost);
+
 /* ---- the driver's candidate loop (rrl/itkLocationRegistration.cxx:2230-2332, 1816-1871) -----------------------------------------
  * jobs[l * n_candidates + c] = candidate initialisation c of nodule location l.  For every candidate: SetupEstimation,
  * find_closest_euclidean and the four angle measures -> ranking key = their mean (:2303-2326).  Then per location, best angle

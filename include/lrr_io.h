@@ -92,6 +92,29 @@ int  lrr_io_results_name(char* out, int outlen, const char* dir, const char* pre
 int  lrr_io_write_transform(const char* path, const double* A9, const double* t3, const double* c3, char* err, int errlen);
 int  lrr_io_read_transform(const char* path, double* A9, double* t3, double* c3, char* err, int errlen);
 
+/* ---- verification of a candidate by the trained classifier (rrl/itkLocationRegistration.cxx:2087-2109, 2508-2528 through
+ * libsvm/svm_interface.cpp:18-102) -------------------------------------------------------------------------------------------------
+ * The driver loads a LIBSVM model (`training_data_all.model`, not part of the repository: the caller supplies the file), scales the
+ * eight decision measurements of a converged, non-oscillating candidate (lrr_decision::measurements, include/lrr_gpu.h) to [-1, 1] and
+ * accepts the registration when the probability of the first class exceeds 0.5.  LIBSVM itself is third-party code carried by the
+ * reference tree (libsvm/svm.cpp): restated here from its published model format and methods, pinned against that source compiled in
+ * oracle/_ref (tests/test_svm.py).  C-SVC / nu-SVC (any number of classes, with or without probability information), one-class and
+ * regression models; linear, polynomial, rbf and sigmoid kernels. */
+typedef struct lrr_svm_model lrr_svm_model;
+int  lrr_svm_load(const char* path, lrr_svm_model** out, char* err, int errlen);   /* svm_load_model (load_model, svm_interface.cpp:79-102) */
+void lrr_svm_free(lrr_svm_model* m);
+int  lrr_svm_nr_class(const lrr_svm_model* m);
+int  lrr_svm_has_probability(const lrr_svm_model* m);
+int  lrr_svm_labels(const lrr_svm_model* m, int32_t* labels);
+/* predict() (svm_interface.cpp:18-76): x[i] -> -1 + 2 (x[i] - feature_min[i]) / (feature_max[i] - feature_min[i]) (both NULL: no
+ * scaling), node indices index_base + i (the driver uses 0, LIBSVM data files 1), then svm_predict_probability when asked and the
+ * model supports it (prob[nr_class]), else svm_predict.  *label = the predicted class label (or value, for regression). */
+int  lrr_svm_predict(const lrr_svm_model* m, const double* x, int size, const double* feature_min, const double* feature_max, int index_base,
+                     int predict_probability, double* label, double* prob);
+/* the driver's acceptance test: its scaling ranges (:2108-2109), indices from 0 (:2099), *verified = probability_estimates[0] > 0.5
+ * (:2528).  Returns 2 for a model that is not a two-class probability model (the driver exits on those, svm_interface.cpp:82-86). */
+int  lrr_svm_verify(const lrr_svm_model* m, const double* measurements8, int* verified, double* probability_good, double* label);
+
 #ifdef __cplusplus
 }
 #endif

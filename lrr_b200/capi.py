@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "est_set_shuffle", "est_set_initial_scale", "est_set_number_points", "est_find_closest", "est_one_iteration",
     "est_run", "est_get_transform", "est_get_matches", "est_metric", "est_estimate_ls_backward", "est_transfer_cov",
     "est_get_state", "est_get_stats", "est_oscillated", "objcov_eval", "objcov_refine", "objpar_eval", "objpar_refine",
-    "cdc_compute_weights", "cdc_get_matches", "cdc_resolution_switch", "cdc_one_iteration", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations",
+    "cdc_compute_weights", "cdc_get_matches", "cdc_resolution_switch", "cdc_one_iteration", "batch_run", "batch_run_ids", "batch_run_multi", "batch_run_locations", "batch_expected_cost",
 ]
 
 
@@ -149,6 +149,7 @@ class Lib:
             "batch_run_ids": (i32, [vp, vp, vp, vp, C.POINTER(C.c_int64), i64, i32, u64, vp]),
             "batch_run_locations": (i32, [vp, vp, vp, vp, i64, C.c_int32, i32, u64, i32, dbl, vp, vp]),
             "batch_run_multi": (i32, [C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp), vp, i64, i32, u64, vp]),
+            "batch_expected_cost": (i32, [vp, vp, vp, vp, i64, pi32]),
         }
         for name, (res, args) in sig.items():
             if self.has(name):
@@ -238,6 +239,15 @@ class Context:
                                               len(jobs), max_iter, seed, out.ctypes.data_as(C.c_void_p))
         self.check(rc, "batch_run")
         return out
+
+    def batch_expected_cost(self, moving: "FeatureSet", fixed: "FeatureSet", jobs: np.ndarray) -> np.ndarray:
+        """features covered by the two ROI cubes of every job (0: an ROI cannot pass the 1000-feature gate)"""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        cost = np.zeros(len(jobs), dtype=np.int32)
+        rc = self.lib.fn("batch_expected_cost")(self.h, moving.h, fixed.h, jobs.ctypes.data_as(C.c_void_p), len(jobs),
+                                                cost.ctypes.data_as(C.POINTER(C.c_int32)))
+        self.check(rc, "batch_expected_cost")
+        return cost
 
     def batch_run_locations(self, moving: "FeatureSet", fixed: "FeatureSet", jobs: np.ndarray, n_candidates: int, max_iter: int = 70, seed: int = 0,
                             until_verified: bool = False, voxel_spacing: float = 1.0):

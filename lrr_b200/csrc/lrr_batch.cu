@@ -565,6 +565,37 @@ size_t lrr_batch_smem_bytes() { return ((sizeof(BatchShared) + 15) & ~size_t(15)
 // extra arguments of the candidate-loop launches (lrr_batch_run_locations); mode == 0: a plain job list.  thread_local: one host
 // thread drives one context
 thread_local BatchLocArgs lrr_batch_loc_args = {0, 1, 0, nullptr, nullptr, 1.0};
+// Expected cost of a job before it runs = the features its two ROI cubes cover, counted by whole grid cells (run bounds of the
+// cell-sorted arrays: one pair of loads per grid row, no point is touched); a cube that cannot reach the 1000-feature gate costs
+// nothing.  One warp per job.  Used to hand the jobs out longest-expected-first (lrr_capi.cu): the makespan of a run is set by the
+// jobs that are still running when the queue is empty, and a job's time is (iterations) x (ROI points).
+__device__ __forceinline__ int warp_roi_cells(const GridDev& g, const double* c, double half) {
+  const int x0 = lrr_cell_clamp(c[0] - half, g.ox, g.inv_h, g.nx), x1 = lrr_cell_clamp(c[0] + half, g.ox, g.inv_h, g.nx);
+  const int y0 = lrr_cell_clamp(c[1] - half, g.oy, g.inv_h, g.ny), y1 = lrr_cell_clamp(c[1] + half, g.oy, g.inv_h, g.ny);
+  const int z0 = lrr_cell_clamp(c[2] - half, g.oz, g.inv_h, g.nz), z1 = lrr_cell_clamp(c[2] + half, g.oz, g.inv_h, g.nz);
+  const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+  int cnt = 0;
+  for (int r = threadIdx.x & 31; r < nrows; r += 32) {
+    const int row = ((z0 + r / ny) * g.ny + (y0 + r % ny)) * g.nx;
+    cnt += __ldg(g.cell_start + row + x1 + 1) - __ldg(g.cell_start + row + x0);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  return cnt;
+}
+__global__ void k_roi_cost(const FsetDev moving_all, const FsetDev fixed_all, const lrr_job* __restrict__ jobs, long long njobs, int* __restrict__ cost) {
+  const long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= njobs) return;
+  const lrr_job& job = jobs[j];
+  const int cm = warp_roi_cells(moving_all.grid, job.roi_center_moving, job.roi_half_size);
+  const int cf = warp_roi_cells(fixed_all.grid, job.roi_center_fixed, job.roi_half_size);
+  if ((threadIdx.x & 31) == 0) cost[j] = (cm < 1000 || cf < 1000) ? 0 : cm + cf;
+}
+void lrr_batch_roi_cost(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, long long njobs, int* cost_dev, cudaStream_t st, long long* launches) {
+  if (njobs <= 0) return;
+  k_roi_cost<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(moving_all, fixed_all, jobs_dev, njobs, cost_dev); ++*launches;
+}
+
 cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
                              const long long* job_ids_dev, int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
                              size_t workspace_bytes, cudaStream_t st, long long* launches) {

@@ -107,6 +107,7 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
     if (getenv("LRR_NO_NORM_SKIP")) o.norm_skip = 0;
     if (getenv("LRR_NO_FLAT")) o.flat = 0;
     if (const char* ts = getenv("LRR_TILE_SPARSE")) o.tile_sparse = atoi(ts);
+    if (getenv("LRR_NO_BATCH_SORT")) o.batch_sort = 0;
   }
   ok = ok && cudaStreamSynchronize(ctx->own_stream) == cudaSuccess;   // (allocations and clears are ordered on the context's own stream)
   if (!ok) { cudaGetLastError(); lrr_ctx_destroy(ctx); return LRR_ERR_CUDA; }
@@ -241,6 +242,7 @@ extern "C" int lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value) {
   else if (k == "norm_skip") o.norm_skip = value != 0;
   else if (k == "flat_scan") o.flat = value != 0;
   else if (k == "tile_sparse") { if (value < -1 || value > 32) return LRR_ERR_INVALID; o.tile_sparse = value; }
+  else if (k == "batch_sort") o.batch_sort = value != 0;
   else { ctx->err = "lrr_ctx_set_option: unknown key " + k; return LRR_ERR_INVALID; }
   return LRR_OK;
 }
@@ -1560,7 +1562,7 @@ extern "C" int lrr_cdc_compute_weights(lrr_est* e, int dir, int max_matches, dou
     CK(cudaGetLastError());
     const int64_t entries = (int64_t) * (unsigned long long*)(pin + 260);
     const int* is = (const int*)(pin + 262);
-    if (is[3]) { ctx->err = "compute_weights: a search ball holds more than 4096 fixed features"; return LRR_ERR_UNSUPPORTED; }
+    if (is[3]) { ctx->err = "compute_weights: max_matches does not fit the per-warp candidate list (4064)"; return LRR_ERR_UNSUPPORTED; }
     if (entries > d.cdc_ecap) { want = entries; continue; }   // the flat set did not fit: once more with the size the cursor reports
     d.cdc_entries = entries; d.cdc_rows = is[0];
     lrr_k_cdc_normalise((int)entries, d.cdc_efrom, d.cdc_eslot, d.cdc_ew, d.cdc_roww, d.cdc_tow, st, &ctx->launches);
@@ -1755,6 +1757,36 @@ static int batch_host_jobs(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_a
   return rc;
 }
 
+void lrr_batch_roi_cost(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, long long njobs, int* cost_dev, cudaStream_t st, long long* launches);
+// Expected cost of every job (features covered by its two ROI cubes; 0 when an ROI cannot pass the 1000-feature gate): what the
+// batched entry points order their queue by, and what a host that shards the list over processes can balance the shares with.
+extern "C" int lrr_batch_expected_cost(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int32_t* cost) {
+  if (!ctx || !moving_all || !fixed_all || njobs < 0 || (njobs > 0 && (!jobs || !cost))) return LRR_ERR_INVALID;
+  if (moving_all->ctx != ctx || fixed_all->ctx != ctx) return LRR_ERR_INVALID;
+  if (njobs == 0) return LRR_OK;
+  enter(ctx);
+  cudaStream_t st = ctx->stream;
+  lrr_job* dj = nullptr; int* dc = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&dj, sizeof(lrr_job) * njobs, st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&dc, sizeof(int) * njobs, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dj, jobs, sizeof(lrr_job) * njobs, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) { lrr_batch_roi_cost(moving_all->dev, fixed_all->dev, dj, njobs, dc, st, &ctx->launches); e = cudaMemcpyAsync(cost, dc, sizeof(int) * njobs, cudaMemcpyDeviceToHost, st); }
+  const cudaError_t e2 = cudaStreamSynchronize(st);
+  if (dj) cudaFreeAsync(dj, st); if (dc) cudaFreeAsync(dc, st);
+  CK(e); CK(e2); CK(cudaGetLastError());
+  return LRR_OK;
+}
+// queue order of a batched run: longest expected first (stable, so equal costs keep the list order)
+static int batch_queue_order(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, std::vector<int64_t>& perm) {
+  perm.resize((size_t)njobs);
+  for (int64_t j = 0; j < njobs; ++j) perm[(size_t)j] = j;
+  if (!ctx->opt.batch_sort || njobs < 2) return LRR_OK;
+  std::vector<int32_t> cost((size_t)njobs);
+  int rc = lrr_batch_expected_cost(ctx, moving_all, fixed_all, jobs, njobs, cost.data()); if (rc != LRR_OK) return rc;
+  std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+  return LRR_OK;
+}
+
 // Batched location registration: the outer loops of LocationRegistration::Run (rrl/itkLocationRegistration.cxx:2138,
 // 2230,2332) over one resident volume pair.  Device path: one persistent thread block per registration (lrr_batch.cu).
 static int batch_run_impl(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t njobs, const int64_t* ids, int max_iter,
@@ -1767,12 +1799,18 @@ static int batch_run_impl(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_al
   const bool host_only = (mode && std::string(mode) == "host") || max_iter > 250;
   std::vector<int64_t> todo;
   if (!host_only) {
+    // the queue in the order longest-expected-first: permuted copies of the jobs and of their ids (the id seeds a job's shuffle and
+    // must stay the job's own), results scattered back to the list order afterwards
+    std::vector<int64_t> perm;
+    int rc = batch_queue_order(ctx, moving_all, fixed_all, jobs, njobs, perm); if (rc != LRR_OK) return rc;
+    std::vector<lrr_job> pj((size_t)njobs); std::vector<int64_t> pid((size_t)njobs); std::vector<lrr_result> pout((size_t)njobs);
+    for (int64_t i = 0; i < njobs; ++i) { const int64_t j = perm[(size_t)i]; pj[(size_t)i] = jobs[j]; pid[(size_t)i] = ids ? ids[j] : j; }
     BatchSlot s; s.st = ctx->stream;
-    int rc;
-    { PHASE(PH_BATCH); rc = slot_launch(ctx, s, moving_all, fixed_all, jobs, 0, njobs, ids, 0, max_iter, shuffle_seed, out); }
+    { PHASE(PH_BATCH); rc = slot_launch(ctx, s, moving_all, fixed_all, pj.data(), 0, njobs, pid.data(), 0, max_iter, shuffle_seed, pout.data()); }
     const int rc2 = slot_collect(ctx, s);
     if (rc != LRR_OK) return rc;
     if (rc2 != LRR_OK) return rc2;
+    for (int64_t i = 0; i < njobs; ++i) out[perm[(size_t)i]] = pout[(size_t)i];
     for (int64_t j = 0; j < njobs; ++j) if (out[j].status < 0) todo.push_back(j);
   } else {
     for (int64_t j = 0; j < njobs; ++j) todo.push_back(j);
@@ -1804,6 +1842,10 @@ extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_a
   }
   if (njobs == 0) return LRR_OK;
   if (max_iter > 250 || ndev == 1) return batch_run_impl(ctxs[0], moving_all[0], fixed_all[0], jobs, njobs, nullptr, max_iter, shuffle_seed, out);
+  std::vector<int64_t> perm;
+  { enter(ctxs[0]); const int rc = batch_queue_order(ctxs[0], moving_all[0], fixed_all[0], jobs, njobs, perm); if (rc != LRR_OK) return rc; }
+  std::vector<lrr_job> pj((size_t)njobs); std::vector<lrr_result> pout((size_t)njobs);
+  for (int64_t i = 0; i < njobs; ++i) pj[(size_t)i] = jobs[perm[(size_t)i]];
   std::atomic<int64_t> cursor{0};
   std::vector<int> rcs((size_t)ndev, LRR_OK);
   auto worker = [&](int d) {
@@ -1823,7 +1865,7 @@ extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_a
       const int64_t a = cursor.fetch_add(run);
       if (a >= njobs) break;
       const cudaStream_t keep = g_alloc_stream;
-      rc = slot_launch(ctx, slot[cur], moving_all[d], fixed_all[d], jobs, a, std::min(run, njobs - a), nullptr, 0, max_iter, shuffle_seed, out);
+      rc = slot_launch(ctx, slot[cur], moving_all[d], fixed_all[d], pj.data(), a, std::min(run, njobs - a), perm.data(), 0, max_iter, shuffle_seed, pout.data());
       g_alloc_stream = keep;
     }
     for (int k = 0; k < 2; ++k) { const int r2 = slot_collect(ctx, slot[k]); if (rc == LRR_OK) rc = r2; if (slot[k].own_stream) cudaStreamDestroy(slot[k].st); }
@@ -1834,6 +1876,7 @@ extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_a
   worker(0);
   for (auto& t : th) t.join();
   for (int d = 0; d < ndev; ++d) if (rcs[(size_t)d] != LRR_OK) return rcs[(size_t)d];
+  for (int64_t i = 0; i < njobs; ++i) out[perm[(size_t)i]] = pout[(size_t)i];
   std::vector<int64_t> todo;
   for (int64_t j = 0; j < njobs; ++j) if (out[j].status < 0) todo.push_back(j);
   enter(ctxs[0]);

@@ -45,6 +45,40 @@ __device__ __forceinline__ double lrr_sym3_lmax(const double (&C)[6]) {
   return q + 2.0 * p * cos(acos(r) / 3.0);
 }
 
+// smallest v with #{candidates of index <= v} >= want  (the list holds more than `want` candidates)
+__device__ __forceinline__ int cdc_index_threshold(const int2* cand, int cnt, int want, int nto, int lane) {
+  int lo = 0, hi = nto - 1;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+    for (int k = lane; k < cnt; k += 32) c += cand[k].x <= mid ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (c >= want) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+// The warp's candidate list is full (a very large search ball): only the max_matches lowest original indices of the WHOLE ball can
+// survive the cap, so everything above the max_matches-th smallest index seen so far is dropped (in place, order kept) and the scan
+// goes on.  Exact whatever the size of the ball; returns the new length (<= max_matches).
+__device__ __forceinline__ int cdc_prune(int2* cand, int cnt, int max_matches, int nto, int lane) {
+  __syncwarp();
+  if (cnt <= max_matches) return cnt;
+  const int tau = cdc_index_threshold(cand, cnt, max_matches, nto, lane);
+  int nk = 0;
+  for (int k0 = 0; k0 < cnt; k0 += 32) {
+    const int k = k0 + lane;
+    int2 cd = make_int2(0, 0); bool keep = false;
+    if (k < cnt) { cd = cand[k]; keep = cd.x <= tau; }
+    const unsigned int m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) cand[nk + __popc(m & ((1u << lane) - 1u))] = cd;
+    nk += __popc(m);
+  }
+  __syncwarp();
+  return nk;
+}
+
 __global__ void __launch_bounds__(LRR_CDC_THREADS) k_cdc_match(const __grid_constant__ CdcArgs a) {
   __shared__ double Bs[10][6];
   __shared__ int rowlo_s[LRR_CDC_WARPS][LRR_FLAT_ROWS + 1], rowbase_s[LRR_CDC_WARPS][LRR_FLAT_ROWS + 1];
@@ -159,6 +193,7 @@ __global__ void __launch_bounds__(LRR_CDC_THREADS) k_cdc_match(const __grid_cons
             o = lrr_pos4_orig(P);
           }
           const unsigned int m = __ballot_sync(full, in);
+          if (m && cnt + 32 > LRR_CDC_CAND) cnt = cdc_prune(cand, cnt, a.max_matches, a.to.n, lane);   // (warp-uniform)
           if (in) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); if (pos < LRR_CDC_CAND) cand[pos] = make_int2(o, J); }
           cnt += __popc(m);
         }
@@ -166,22 +201,11 @@ __global__ void __launch_bounds__(LRR_CDC_THREADS) k_cdc_match(const __grid_cons
     }
     __syncwarp();
     int nk = 0; double sum_w = 0.0;
-    if (cnt > LRR_CDC_CAND) { if (lane == 0) atomicExch(a.istat + 3, 1); cnt = 0; }
+    if (cnt > LRR_CDC_CAND) { if (lane == 0) atomicExch(a.istat + 3, 1); cnt = 0; }   // (only when max_matches itself does not fit the list)
     if (cnt > 0) {
       // cap: the max_matches lowest original indices (bisection on the index: smallest v with #{o <= v} >= max_matches)
       int tau = 0x7fffffff;
-      if (cnt > a.max_matches) {
-        int lo = 0, hi = a.to.n - 1;
-        while (lo < hi) {
-          const int mid = lo + ((hi - lo) >> 1);
-          int c = 0;
-          for (int k = lane; k < cnt; k += 32) c += cand[k].x <= mid ? 1 : 0;
-#pragma unroll
-          for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(full, c, o);
-          if (c >= a.max_matches) hi = mid; else lo = mid + 1;
-        }
-        tau = lo;
-      }
+      if (cnt > a.max_matches) tau = cdc_index_threshold(cand, cnt, a.max_matches, a.to.n, lane);
       // evaluate the candidates, one per lane; kept entries are compacted in place (the write position never passes the chunk read)
       for (int k0 = 0; k0 < cnt; k0 += 32) {
         const int k = k0 + lane;
@@ -284,7 +308,9 @@ __global__ void k_cdc_norm(int pass, int M, int nto, const double* __restrict__ 
 
 size_t lrr_cdc_scratch_entries(int blocks) { return (size_t)blocks * LRR_CDC_WARPS * LRR_CDC_CAND; }
 int lrr_cdc_blocks(int M) {
-  long long b = ((long long)M + LRR_CDC_WARPS - 1) / LRR_CDC_WARPS, cap = (long long)lrr_num_sms() * 2;
+  // 80 registers per thread: six blocks of four warps per SM — the kernel is bound by the latency of its dependent phases (run bounds ->
+  // points -> covariance records), not by bandwidth: the fixed set is L2-resident (0.96 -> see profiles/r2_summary.md)
+  long long b = ((long long)M + LRR_CDC_WARPS - 1) / LRR_CDC_WARPS, cap = (long long)lrr_num_sms() * 6;
   if (b > cap) b = cap; if (b < 1) b = 1;
   return (int)b;
 }

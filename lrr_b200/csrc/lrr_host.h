@@ -22,7 +22,8 @@ struct lrr_ctx {
   SelDev sel[4];
   // behaviour switches (lrr_ctx_set_option; the environment variables of README.md only set their initial values)
   struct Options { int certificates = 1, tile = 1, spec = 1 /* 0 never, 1 when the last iteration kept every query, 2 always */, pipe = 1, norm_skip = 1,
-                       tile_sparse = -1 /* -1: by the host hint */, flat = 1; } opt;
+                       tile_sparse = -1 /* -1: by the host hint */, flat = 1,
+                       batch_sort = 1 /* batched mode: jobs handed out longest-expected-first */; } opt;
   bool async_upload = false; cudaStream_t dirs_stream = nullptr;
   unsigned long long sel_owner = 0; long long window_misses = 0;   // signature of the last estimate that left valid search windows in the selectors
   SortScratch sort; double* sort_keys = nullptr;

@@ -25,7 +25,8 @@ SYMBOLS = ["lrr_io_read_features_vtp", "lrr_io_features_free", "lrr_io_features_
            "lrr_io_features_C6", "lrr_io_features_strength", "lrr_io_features_shape", "lrr_io_features_dirs", "lrr_io_features_shape_counts",
            "lrr_io_write_features_vtp", "lrr_io_read_mhd", "lrr_io_volume_free", "lrr_io_volume_geometry", "lrr_io_volume_data",
            "lrr_io_labels_at", "lrr_io_write_mhd", "lrr_io_results_t_centered", "lrr_io_write_results", "lrr_io_read_results",
-           "lrr_io_results_name", "lrr_io_write_transform", "lrr_io_read_transform"]
+           "lrr_io_results_name", "lrr_io_write_transform", "lrr_io_read_transform",
+           "lrr_svm_load", "lrr_svm_free", "lrr_svm_nr_class", "lrr_svm_has_probability", "lrr_svm_labels", "lrr_svm_predict", "lrr_svm_verify"]
 
 
 def lib():
@@ -56,6 +57,12 @@ def lib():
         L.lrr_io_results_name.argtypes = [cp, C.c_int, cp, cp, cp, C.c_uint, C.c_uint, cp]
         L.lrr_io_write_transform.argtypes = [cp, dp, dp, dp, cp, C.c_int]
         L.lrr_io_read_transform.argtypes = [cp, dp, dp, dp, cp, C.c_int]
+        L.lrr_svm_load.argtypes = [cp, C.POINTER(vp), cp, C.c_int]
+        L.lrr_svm_free.argtypes = [vp]; L.lrr_svm_free.restype = None
+        L.lrr_svm_nr_class.argtypes = [vp]; L.lrr_svm_has_probability.argtypes = [vp]
+        L.lrr_svm_labels.argtypes = [vp, C.POINTER(C.c_int32)]
+        L.lrr_svm_predict.argtypes = [vp, dp, C.c_int, dp, dp, C.c_int, C.c_int, dp, dp]
+        L.lrr_svm_verify.argtypes = [vp, dp, C.POINTER(C.c_int), dp, dp]
         _lib = L
     return _lib
 
@@ -179,3 +186,39 @@ def read_transform(path: str):
     A, t, c = np.zeros(9), np.zeros(3), np.zeros(3)
     _call(lib().lrr_io_read_transform, os.fsencode(path), _dp(A), _dp(t), _dp(c))
     return A.reshape(3, 3), t, c
+
+
+class SvmModel:
+    """A LIBSVM model file behind lrr_svm_* (the driver's verification step, rrl/itkLocationRegistration.cxx:2087-2109, 2508-2528)."""
+
+    def __init__(self, path: str):
+        L = lib(); h = C.c_void_p(); err = C.create_string_buffer(512)
+        if L.lrr_svm_load(path.encode(), C.byref(h), err, 512) != 0:
+            raise IoError(err.value.decode())
+        self.h = h
+        self.nr_class = L.lrr_svm_nr_class(h); self.has_probability = bool(L.lrr_svm_has_probability(h))
+        lab = np.zeros(max(self.nr_class, 1), np.int32); L.lrr_svm_labels(h, lab.ctypes.data_as(C.POINTER(C.c_int32))); self.labels = lab[: self.nr_class]
+
+    def predict(self, x, feature_min=None, feature_max=None, index_base: int = 1, probability: bool = True):
+        """(label, probabilities or None)"""
+        x = np.ascontiguousarray(x, np.float64); lab = np.zeros(1); prob = np.zeros(max(self.nr_class, 1))
+        fmin = None if feature_min is None else np.ascontiguousarray(feature_min, np.float64)
+        fmax = None if feature_max is None else np.ascontiguousarray(feature_max, np.float64)
+        rc = lib().lrr_svm_predict(self.h, _dp(x), len(x), None if fmin is None else _dp(fmin), None if fmax is None else _dp(fmax), index_base,
+                                   int(probability), _dp(lab), _dp(prob))
+        if rc != 0:
+            raise IoError(f"lrr_svm_predict -> {rc}")
+        return float(lab[0]), (prob[: self.nr_class].copy() if (probability and self.has_probability) else None)
+
+    def verify(self, measurements8):
+        """(verified, probability of the first class, label) for the eight decision measurements of one candidate"""
+        m = np.ascontiguousarray(measurements8, np.float64); assert m.size == 8
+        v = C.c_int(0); p = np.zeros(1); lab = np.zeros(1)
+        rc = lib().lrr_svm_verify(self.h, _dp(m), C.byref(v), _dp(p), _dp(lab))
+        if rc != 0:
+            raise IoError(f"lrr_svm_verify -> {rc} (2: not a two-class probability model)")
+        return bool(v.value), float(p[0]), float(lab[0])
+
+    def close(self):
+        if self.h:
+            lib().lrr_svm_free(self.h); self.h = None

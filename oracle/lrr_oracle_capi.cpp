@@ -554,6 +554,20 @@ int lrro_batch_run_ids(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, c
     run_one_job(moving_all, fixed_all, mall, fall, fixed_all->kd, moving_all->kd, jobs[j], max_iter, seed + (uint64_t)ids[j], out[j]);
   return LRR_OK;
 }
+// expected cost of a job = the features inside its two ROI cubes (FeaturesInROIs, rrl/itkLocationRegistration.cxx:1324-1360), 0 when
+// a cube fails the 1000-feature gate (:1632).  (The CUDA backend counts by whole grid cells: a scheduling heuristic, not a result.)
+int lrro_batch_expected_cost(lrro_ctx*, lrro_fset* moving_all, lrro_fset* fixed_all, const lrr_job* jobs, int64_t njobs, int32_t* cost) {
+  auto inside = [](const std::vector<Feature>& v, const double* c, double h) {
+    int n = 0;
+    for (const Feature& f : v) if (!(c[0] - h > f.loc[0] || f.loc[0] > c[0] + h || c[1] - h > f.loc[1] || f.loc[1] > c[1] + h || c[2] - h > f.loc[2] || f.loc[2] > c[2] + h)) ++n;
+    return n;
+  };
+  for (int64_t j = 0; j < njobs; ++j) {
+    const int cm = inside(moving_all->base, jobs[j].roi_center_moving, jobs[j].roi_half_size), cf = inside(fixed_all->base, jobs[j].roi_center_fixed, jobs[j].roi_half_size);
+    cost[j] = (cm < 1000 || cf < 1000) ? 0 : cm + cf;
+  }
+  return LRR_OK;
+}
 // "devices" of the CPU checker = host threads over the first replica
 int lrro_batch_run_multi(lrro_ctx** c, int ndev, lrro_fset** m, lrro_fset** f, const lrr_job* jobs, int64_t njobs, int max_iter, uint64_t seed, lrr_result* out) {
   return lrro_batch_run_mt(c[0], m[0], f[0], jobs, njobs, max_iter, seed, out, ndev);

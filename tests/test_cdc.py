@@ -180,6 +180,20 @@ def test_gpu_cap_and_multiplier_arguments(gpu_lib, oracle_lib):
 
 
 @pytest.mark.gpu
+def test_gpu_search_balls_larger_than_the_candidate_list(gpu_lib, oracle_lib):
+    """6000 fixed features inside a 20 mm cube: every search ball (radius >= 5 sigma) holds most of them, more than the 4096 entries of a
+    warp's candidate list — the list is pruned to the lowest indices while the scan goes on, exactly"""
+    pair = synth.make_pair(81, 6000, 600, size=20.0)
+    g, o = make(gpu_lib, pair, icp=2), make(oracle_lib, pair, icp=2)
+    s = compare_sets(g, o)
+    assert s["max_matches"] > 50
+    sg, so = g.cdc_compute_weights(1000, 5.0), o.cdc_compute_weights(1000, 5.0)
+    assert (sg["rows"], sg["entries"], sg["max_matches"]) == (so["rows"], so["entries"], so["max_matches"])
+    mg, mo = g.cdc_get_matches(), o.cdc_get_matches()
+    assert all(np.array_equal(x, y) for x, y in zip(mg[:3], mo[:3])) and rel(mg[3], mo[3]) < TOL
+
+
+@pytest.mark.gpu
 def test_gpu_refinements_and_em_iterations(gpu_lib, oracle_lib):
     """estimate_parameters / estimate_covariance over the many-to-many set (normalised as cdcl_estimation_ICP.txx:751-832) and
     cdcl_estimation::one_iteration for iterations 4..9 (the parameter step starts after startEM = 5)"""

@@ -308,7 +308,7 @@ def test_transform_file(tmp_path):
 def test_io_abi_exports_every_declared_symbol():
     import ctypes
     hdr = open(os.path.join(ROOT, "include", "lrr_io.h")).read()
-    names = sorted(set(re.findall(r"\b(lrr_io_[A-Za-z0-9_]+)\s*\(", hdr)))
+    names = sorted(set(re.findall(r"\b(lrr_(?:io|svm)_[A-Za-z0-9_]+)\s*\(", hdr)))
     assert len(names) >= 20 and set(names) == set(lio.SYMBOLS)
     L = ctypes.CDLL(os.path.join(ROOT, "lrr_b200", "liblrr_io.so"))
     for n in names:

@@ -26,12 +26,25 @@ def test_job_block_partition():
                 assert all(len(set((x[x < 32 * world] // 32).tolist())) == world for x in shards) or world == 1
 
 
+def test_cost_balanced_shards_are_a_partition():
+    from lrr_b200.sharding import job_shard
+    rng = np.random.default_rng(0)
+    for njobs, world in ((1, 2), (97, 2), (8192, 8)):
+        costs = rng.integers(0, 20000, size=njobs)
+        shards = [job_shard(njobs, world, r, costs) for r in range(world)]
+        assert sorted(np.concatenate(shards).tolist()) == list(range(njobs))
+        assert max(len(x) for x in shards) - min(len(x) for x in shards) <= 1
+        if njobs >= 64 * world:   # every rank gets the same share of the expected work, to a few jobs' worth
+            tot = [int(costs[x].sum()) for x in shards]
+            assert max(tot) - min(tot) <= 4 * int(costs.max())
+
+
 def _worker(rank, world, port, outdir):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from lrr_b200 import synth
     from lrr_b200.capi import Lib
-    from lrr_b200.sharding import gather_results, run_batch_sharded
+    from lrr_b200.sharding import expected_costs, gather_results, run_batch_sharded
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = Lib(os.path.join(ROOT, "oracle", "liblrr_oracle.so"), "lrro_")   # CPU stand-in for the device backend
@@ -41,7 +54,17 @@ def _worker(rank, world, port, outdir):
     fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
     local = run_batch_sharded(ctx, mv, fx, jobs, 8, 5, rank, world)
     full = gather_results(local, len(jobs), rank, world)
+    # ... and with the shares dealt over the jobs sorted by expected cost (what bench.py does at N > 1)
+    costs = expected_costs(ctx, mv, fx, jobs, world)
+    assert costs is not None and len(costs) == len(jobs)
+    local_c = run_batch_sharded(ctx, mv, fx, jobs, 8, 5, rank, world, costs=costs)
+    full_c = gather_results(local_c, len(jobs), rank, world, costs=costs)
     if rank == 0:
+        same = all(np.array_equal(full_c[k], full[k]) for k in ("status", "converged", "iterations", "n_moving_inside", "n_fixed_inside"))
+        same = same and all(np.allclose(full_c[k], full[k], rtol=1e-9, atol=1e-12) for k in ("A", "t", "cov"))
+        if not same:
+            open(os.path.join(outdir, "result.txt"), "w").write("MISMATCH (cost-balanced shards)")
+            dist.barrier(); dist.destroy_process_group(); return
         ref = ctx.batch_run(mv, fx, jobs, 8, 5)
         # the oracle normalises shared feature objects in place (Q10), so results drift by O(ulp) with the job history:
         # integer fields exact, floating-point fields to 1e-9
