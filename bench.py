@@ -381,6 +381,48 @@ def run_c5(ctx, stream, peak, steps):
     }
 
 
+def run_cdc(ctx, stream, peak):
+    """The E-step of the full CDC estimator at C3 size (SURVEY.md §8(f)3): cdcl_estimation<3,12>::compute_weights over 100k / 100k features
+    under the transform and covariance of three ICP iterations, then cdcl_obj_fun_cov / cdcl_obj_fun_par over the many-to-many set."""
+    import torch
+    from lrr_b200 import synth
+    n = N_FEATURES
+    pair = synth.make_pair(SEED, n, n)
+    with torch.cuda.stream(stream):
+        fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+        est = ctx.estimator("cdcl_fwd", mv, fx, 12)
+        est.set_flags(True, True); est.set_transform(*pair["init"])
+        for it in range(3):
+            est.one_iteration(it)
+        s = est.cdc_compute_weights()   # untimed: allocates the flat set and the scratch lists
+        ctx.set_profiling(True)
+        for k in range(5):
+            est.cdc_compute_weights()
+        ph = ctx.phase_times()
+        T = est.get_transform(0)
+        U = np.linalg.cholesky(T["cov"]).T
+        x = np.concatenate([U[i, i:] for i in range(12)]); th = np.concatenate([T["A"].reshape(9), T["t"]])
+        est.objcov_eval(x); est.objpar_eval(th)
+        ctx.set_profiling(True)
+        for k in range(5):
+            est.objcov_eval(x)
+        ph_cov = ctx.phase_times()
+        ctx.set_profiling(True)
+        for k in range(5):
+            est.objpar_eval(th)
+        ph_par = ctx.phase_times(); ctx.set_profiling(False)
+        est.close(); fx.close(); mv.close()
+    us_match = 1e3 * ph["match"][0] / ph["match"][1]
+    us_cov = 1e3 * ph_cov["objcov"][0] / ph_cov["objcov"][1]; us_par = 1e3 * ph_par["objcov"][0] / ph_par["objcov"][1]
+    e = s["entries"]
+    return {"workload": "cdcl_estimation<3,12>::compute_weights (covariance-driven radius matching, cap 100, radius 5 sqrt(lambda_max)), 100k features per side",
+            "rows": s["rows"], "entries": e, "max_matches": s["max_matches"], "avg_largest_eval": s["avg_largest_eval"],
+            "compute_weights": {"kernel": "k_cdc_match", "us": us_match, "entries_per_s": e / (us_match * 1e-6),
+                                "note": "latency / instruction bound: the fixed set is L2-resident (profiles/r2_ncu_full_k_cdc_match.csv: 34 MB of DRAM traffic, FP64 pipe 27 %)"},
+            "objcov_eval": {"us": us_cov, "algorithmic_bytes": 156 * e, "gbs": 156 * e / (us_cov * 1e-6) / 1e9, "frac": 156 * e / (us_cov * 1e-6) / 1e9 / peak},
+            "objpar_eval": {"us": us_par, "algorithmic_bytes": 156 * e, "gbs": 156 * e / (us_par * 1e-6) / 1e9, "frac": 156 * e / (us_par * 1e-6) / 1e9 / peak}}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import lrr_b200
@@ -693,6 +735,10 @@ def run_b200(args, rank, world, local_rank):
             line["c5"] = run_c5(ctx, stream, peak, 10)
         except Exception as ex:   # noqa: BLE001
             line["c5"] = {"error": repr(ex)}
+        try:
+            line["cdc_e_step"] = run_cdc(ctx, stream, peak)
+        except Exception as ex:   # noqa: BLE001
+            line["cdc_e_step"] = {"error": repr(ex)}
     sys.stdout.flush()
     os.write(out_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:

@@ -5,7 +5,7 @@
 // published formats and methods: the LIBSVM model text format (header keywords, then one line per support vector
 // "coef ... index:value ..."), the one-against-one decision function of C-SVC / nu-SVC (sum of coef K(x, sv) - rho per class
 // pair, majority vote), Platt's sigmoid on the decision value and the pairwise coupling of Wu, Lin and Weng (JMLR 2004, second
-// method) for class probabilities.  Pinned against the reference's own libsvm compiled in oracle/_ref (tests/test_svm.py).
+// method) for class probabilities.  Checked against the libsvm sources of the reference tree (tests/test_svm.py).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
