@@ -601,7 +601,9 @@ def run_b200(args, rank, world, local_rank):
         bjobs = bjobs[:world]
     with torch.cuda.stream(stream):
         bfx, bmv = ctx.upload(bpair["fixed"]), ctx.upload(bpair["moving"])
-        run_batch_sharded(ctx, bmv, bfx, bjobs[: min(len(bjobs), 512 * world)], 70, BATCH_SEED, rank, world)   # warm-up (workspace allocation)
+        # warm-up: a rank's share of at least 1024 jobs, so that the workspace (a slot per job in flight, up to 1024: gigabytes, kept by the
+        # context between calls) has its full size before the timed run
+        run_batch_sharded(ctx, bmv, bfx, bjobs[: min(len(bjobs), 1024 * world)], 70, BATCH_SEED, rank, world)
         barrier()
         tb0 = time.perf_counter()
         # (N > 1: the shares are dealt over the jobs sorted by expected cost — lrr_batch_expected_cost, inside the timed region; within

@@ -12,6 +12,9 @@
 #include "lrr_host.h"
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
+#include <chrono>
+#include <algorithm>
 
 #define BATCH_CAP 16384            // max features of one ROI (larger ROIs are returned to the host path)
 #define BATCH_SEL_BINS 2048
@@ -46,7 +49,28 @@ struct BatchArgs {
   int mode, ncand, until_verified; const int* order; lrr_decision* dec; double spacing; long long nunits;
   int ball_rows, g8;                            // pass A keeps balls of at most ball_rows rows; the rest: eight-lane groups (g8) / one warp per query
   long long* dbg;                               // optional: 16 cycle counters (block 0), phase profile
+  // TIME SLICING (plain job lists only).  A job's time is iterations x ROI points and the iteration count (1 ... 70) is not known before
+  // it runs: with run-to-completion the jobs that hit the cap late in the queue are the tail of the launch (0.74 of ideal on an
+  // eighth of the C4 list).  Here the workspace is a pool of SLOTS (one per job in flight, more slots than blocks), a block runs a job
+  // for at most `quantum` iterations, parks it — control state into the slot's BatchCtl, everything else already lives in the slot —
+  // and takes the next unit: fresh jobs first while slots are free (every job is started early), then parked jobs in FIFO order.
+  // quantum == 0: one slot per block, run to completion (the candidate loop of lrr_batch_run_locations).
+  int quantum, nslots;
+  int* sched;                                   // [0] lock, [1] next fresh unit, [2] free slots, [3] queue head, [4] queue length, then free[nslots], queue[nslots]
+  struct BatchCtl* ctl;                         // per slot
 };
+struct BatchCtl {
+  int job, n_in[2];
+  int converged, status, it, finest, osc;
+  unsigned int number_matches, seq;             // seq: registrations this SLOT has started — the stamp epochs must grow over the life of its workspace
+  double err_diff, werr_before;
+  unsigned long long calls[2];
+  int number_points[2], scale_estimated[2];
+  // instrumentation (LRR_BATCH_DEBUG=2 prints the latest finishers): first start / last end of the slot's current job (globaltimer ns), its
+  // slices, the time it spent parked
+  unsigned long long t_first, t_last, t_parked_at, t_waited; int slices, done_job, done_it, pad;
+};
+__device__ __forceinline__ unsigned long long batch_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ unsigned long long bt_splitmix(unsigned long long& s) {
   unsigned long long z = (s += 0x9E3779B97F4A7C15ULL);
@@ -255,13 +279,41 @@ struct BatchShared {
   int rows[(BATCH_THREADS / 8) * 2 * LRR_G8_ROWS];   // row tables of the eight-lane groups
   // control state (thread 0 writes, everybody reads after a barrier)
   int converged, status, it, finest, osc, job;
-  unsigned int seq;   // registrations this block has started: the stamp epochs must GROW over the life of its workspace (jobs may come in any order)
+  int slot, resume;   // workspace slot of the unit in hand; 1: a parked job is taken up again
+  unsigned int seq;   // registrations the slot has started (BatchCtl::seq): the stamp epochs must GROW over the life of its workspace (jobs may come in any order)
   unsigned int number_matches;
   double err_diff, werr_before;
   unsigned long long calls[2];
   int number_points[2], scale_estimated[2];
   long long tph[16];
 };
+
+// ---- slot pool and FIFO of parked jobs (one thread per block calls these; a spin lock in global memory: a few thousand operations
+//      per launch) ----
+__device__ __forceinline__ void sched_lock(int* sched) { while (atomicCAS(sched, 0, 1) != 0) { __nanosleep(64); } __threadfence(); }
+__device__ __forceinline__ void sched_unlock(int* sched) { __threadfence(); atomicExch(sched, 0); }
+// next unit of work: job >= 0 fresh (slot reserved), job == -2 a parked job (slot = its slot), job == -1 nothing left for this block
+__device__ void sched_take(const BatchArgs& B, int& job, int& slot) {
+  int* sc = B.sched; int* fr = sc + 8; int* q = fr + B.nslots;
+  volatile int* v = sc;
+  for (;;) {
+    sched_lock(sc);
+    if (v[1] < (int)B.nunits && v[2] > 0) { job = v[1]; sc[1] = job + 1; slot = fr[v[2] - 1]; sc[2] = v[2] - 1; sched_unlock(sc); return; }
+    if (v[4] > 0) { slot = q[v[3]]; sc[3] = (v[3] + 1) % B.nslots; sc[4] = v[4] - 1; job = -2; sched_unlock(sc); return; }
+    const bool fresh_left = v[1] < (int)B.nunits;
+    sched_unlock(sc);
+    if (!fresh_left) { job = -1; slot = -1; return; }   // parked jobs that appear later are taken up by the block that parks them
+    __nanosleep(2000);                                  // every slot is held by a RUNNING block (nslots >= blocks keeps this from happening)
+  }
+}
+__device__ void sched_release(const BatchArgs& B, int slot) {
+  int* sc = B.sched; int* fr = sc + 8; volatile int* v = sc;
+  sched_lock(sc); fr[v[2]] = slot; sc[2] = v[2] + 1; sched_unlock(sc);
+}
+__device__ void sched_park(const BatchArgs& B, int slot) {
+  int* sc = B.sched; int* q = sc + 8 + B.nslots; volatile int* v = sc;
+  sched_lock(sc); q[(v[3] + v[4]) % B.nslots] = slot; sc[4] = v[4] + 1; sched_unlock(sc);
+}
 
 extern __shared__ __align__(16) unsigned char batch_smem[];
 #define TPH(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); S.tph[i] += now_ - tmark; tmark = now_; } } while (0)
@@ -271,17 +323,23 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
   int* list = reinterpret_cast<int*>(batch_smem + ((sizeof(BatchShared) + 15) & ~size_t(15)));   // BATCH_CAP ints
   const BlockScope scope;
   const int flags = LRR_F_RRL | LRR_F_NORMALIZE | LRR_F_SYM | LRR_F_STRENGTH;
-  const size_t blk = blockIdx.x;
   SelDev nosel; nosel.fine = nullptr;
   long long tmark = clock64();
   if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) S.tph[i] = 0; S.seq = 0; }
 
   for (;;) {
-    if (threadIdx.x == 0) S.job = atomicAdd(B.next_job, 1);
+    if (threadIdx.x == 0) {
+      if (B.quantum > 0) { int jb, sl; sched_take(B, jb, sl); S.resume = jb == -2; S.slot = sl; S.job = jb == -2 ? B.ctl[sl].job : jb; }
+      else { const int jb = atomicAdd(B.next_job, 1); S.job = jb < B.nunits ? jb : -1; S.slot = blockIdx.x; S.resume = 0; }
+    }
     __syncthreads();
-    const int unit = S.job;
+    const int unit = S.job; const bool resume = S.resume != 0;
+    const size_t blk = (size_t)(S.slot < 0 ? 0 : S.slot);   // the workspace slot (quantum == 0: the block's own)
     __syncthreads();
-    if (unit >= B.nunits) break;
+    if (unit < 0) break;
+    // a slot's contents may have been written by another SM (the block that parked the job, or an earlier tenant of the slot): acquire
+    // at device scope in every thread before anything of the slot is read (the fence also drops this SM's L1 lines)
+    if (B.quantum > 0) __threadfence();
    int cpos = 0; bool unit_verified = false;
    do {   // the candidates of a location, best angle first (rrl/itkLocationRegistration.cxx:2332); a plain job list has one "candidate" per unit
     int j = unit;
@@ -289,9 +347,12 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
     ++cpos;
     const lrr_job job = B.jobs[j];
     lrr_result* R = B.out + j;
+    BatchCtl* C = B.ctl + blk;
+    bool parked = false;
     // ---- set_features: ROI selection for both directions (forward from = moving, backward from = fixed) ----
     int n_in[2]; bool reject = false, overflow = false;
-    for (int d = 0; d < 2; ++d) {
+    if (resume) { n_in[0] = C->n_in[0]; n_in[1] = C->n_in[1]; }
+    else for (int d = 0; d < 2; ++d) {
       const FsetDev& fa = B.all[d];
       const int n = block_roi(fa, d == 0 ? job.roi_center_moving : job.roi_center_fixed, job.roi_half_size, list, &S.cnt);
       n_in[d] = n;
@@ -309,7 +370,7 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       __syncthreads();
     }
     lrr_decision* D = B.dec ? B.dec + j : nullptr;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !resume) {
       for (size_t i = 0; i < sizeof(lrr_result) / 8; ++i) reinterpret_cast<double*>(R)[i] = 0.0;
       R->n_moving_inside = overflow ? -1 : n_in[0]; R->n_fixed_inside = overflow ? -1 : n_in[1];
       R->status = overflow ? -1 : (reject ? 1 : 0);     // -1: ROI larger than BATCH_CAP, the host path takes the job
@@ -338,20 +399,28 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       a.prev_s = B.w_prev + (blk * 2 + d) * BATCH_CAP;
       a.sc = B.w_sc + blk * 2 + d;
       a.stamp_in_match = 1;   // (no certificates in batched mode: every finished match stamps its to-feature)
-      *a.hq_count = 0;
+      if (!resume) *a.hq_count = 0;
       S.d[d] = a;
       {   // second queue
         int* hq2 = hq + (3 * BATCH_CAP + 4);
         a.hq_k = hq2; a.hq_s = hq2 + BATCH_CAP; a.hq_o = hq2 + 2 * BATCH_CAP; a.hq_count = hq2 + 3 * BATCH_CAP;
         a.hq_best = B.w_hqb + (blk * 2 + d) * 2 * BATCH_CAP + BATCH_CAP;
-        *a.hq_count = 0;
+        if (!resume) *a.hq_count = 0;
         S.d2[d] = a;
       }
-      S.calls[d] = 0; S.number_points[d] = a.M; S.scale_estimated[d] = 0;
+      if (!resume) { S.calls[d] = 0; S.number_points[d] = a.M; S.scale_estimated[d] = 0; }
+      else { S.calls[d] = C->calls[d]; S.number_points[d] = C->number_points[d]; S.scale_estimated[d] = C->scale_estimated[d]; }
     }
     __syncthreads();
     Scal* F = S.d[0].sc; Scal* Bk = S.d[1].sc;
     // ---- set_transform (cdcl sym :231-242): forward <- job transform, backward <- inverse ----
+    if (resume) {
+      if (threadIdx.x == 0) {   // the parked job's control state; transforms, scales and matches never left the slot
+        S.converged = C->converged; S.status = C->status; S.it = C->it; S.finest = C->finest; S.osc = C->osc; S.number_matches = C->number_matches;
+        S.err_diff = C->err_diff; S.werr_before = C->werr_before; S.seq = C->seq;
+        C->t_waited += batch_now() - C->t_parked_at;
+      }
+    } else {
     if (threadIdx.x == 0) {
       for (int i = 0; i < 9; ++i) F->A[i] = job.A[i];
       for (int i = 0; i < 3; ++i) { F->t[i] = job.t[i]; F->c[i] = job.c[i]; }
@@ -363,9 +432,11 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       }
       F->from_mapped = 0; Bk->from_mapped = 0; F->status = 0; Bk->status = 0;
       S.converged = 0; S.status = 0; S.it = 0; S.finest = 0; S.osc = 0; S.number_matches = 1000; S.err_diff = 0.0; S.werr_before = 0.0;
-      S.seq += 1;
+      C->seq += 1; S.seq = C->seq;
+      C->t_first = batch_now(); C->slices = 0; C->t_waited = 0;
     }
     for (int i = threadIdx.x; i < 144; i += blockDim.x) { F->cov[i] = 0.0; Bk->cov[i] = 0.0; }
+    }
     __syncthreads();
 
     if (B.mode == 1) {
@@ -398,7 +469,8 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       __syncthreads();
     } else {
     // ---- the driver loop (rrl/itkLocationRegistration.cxx:2418) ----
-    while (!S.converged && S.it < B.max_iter && S.status == 0) {
+    int slice = B.quantum > 0 ? B.quantum : 0x7fffffff;
+    while (!S.converged && S.it < B.max_iter && S.status == 0 && slice-- > 0) {
       // find_closest_euclidean, both directions: new permutation key, new stamp epoch
       if (threadIdx.x < 2) {
         const int d = threadIdx.x;
@@ -491,11 +563,28 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       }
       __syncthreads();
     }
+    // ---- out of iterations for this slice and not finished: park the job ----
+    parked = B.quantum > 0 && !S.converged && S.it < B.max_iter && S.status == 0;
+    if (parked) {
+      __threadfence();    // every thread's writes into the slot are visible device-wide before the slot goes on the queue
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        C->job = j; C->n_in[0] = n_in[0]; C->n_in[1] = n_in[1];
+        C->converged = S.converged; C->status = S.status; C->it = S.it; C->finest = S.finest; C->osc = S.osc; C->number_matches = S.number_matches;
+        C->err_diff = S.err_diff; C->werr_before = S.werr_before;
+        for (int d = 0; d < 2; ++d) { C->calls[d] = S.calls[d]; C->number_points[d] = S.number_points[d]; C->scale_estimated[d] = S.scale_estimated[d]; }
+        C->slices += 1; C->t_parked_at = batch_now();
+        __threadfence();
+        sched_park(B, (int)blk);
+      }
+      __syncthreads();
+    } else {
     // ---- result ----
     for (int i = threadIdx.x; i < 144; i += blockDim.x) R->cov[i] = F->cov[i];
     if (threadIdx.x == 0) {
       R->status = S.status == 3 ? -2 : S.status;      // -2: selector overflow, the host path takes the job
       R->converged = S.converged; R->oscillated = S.osc > 10; R->iterations = S.it;
+      C->slices += 1; C->t_last = batch_now(); C->done_job = j; C->done_it = S.it;
       for (int i = 0; i < 9; ++i) R->A[i] = F->A[i];
       for (int i = 0; i < 3; ++i) { R->t[i] = F->t[i]; R->c[i] = F->c[i]; }
       R->rms = F->res_sum_r2;                          // rrl RMS_error: the plain sum (Q1)
@@ -550,8 +639,11 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constan
       }
       __syncthreads();
     }
+    }   // not parked
     }   // mode
     }   // ROI accepted
+    __syncthreads();
+    if (B.quantum > 0 && !parked) { __threadfence(); if (threadIdx.x == 0) sched_release(B, (int)blk); }   // the job is done (or was rejected): its slot is free again
     __syncthreads();
     TPH(11);
    } while (B.order && cpos < B.ncand && !(B.until_verified && unit_verified));
@@ -598,7 +690,8 @@ void lrr_batch_roi_cost(const FsetDev& moving_all, const FsetDev& fixed_all, con
 
 cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
                              const long long* job_ids_dev, int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
-                             size_t workspace_bytes, cudaStream_t st, long long* launches) {
+                             size_t workspace_bytes, cudaStream_t st, long long* launches, int nslots, int quantum) {
+  if (nslots < nblocks) nslots = nblocks;
   BatchArgs B; memset(&B, 0, sizeof(B));
   B.all[0] = moving_all; B.all[1] = fixed_all; B.jobs = jobs_dev; B.out = out_dev; B.njobs = njobs; B.max_iter = max_iter; B.shuffle_seed = shuffle_seed;
   B.job_ids = job_ids_dev;
@@ -612,7 +705,7 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
   for (int i = 0; i < 4 * 32; ++i) B.muse_table[i] = muse_table[i];
   B.muse_rows = muse_rows;
   // carve the workspace
-  char* p = (char*)workspace; const size_t nb = (size_t)nblocks;
+  char* p = (char*)workspace; const size_t nb = (size_t)nslots;   // workspace slots (>= blocks)
   auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~size_t(255); return r; };
   B.next_job = (int*)take(256);
   B.dbg = getenv("LRR_BATCH_DEBUG") ? (long long*)((char*)B.next_job + 64) : nullptr;
@@ -627,8 +720,19 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
   B.w_hq = (int*)take(nb * 2 * 2 * (3 * BATCH_CAP + 4) * sizeof(int));
   B.w_stamp0 = (unsigned long long*)take(nb * (size_t)fixed_all.n * 8);
   B.w_stamp1 = (unsigned long long*)take(nb * (size_t)moving_all.n * 8);
+  B.ctl = (BatchCtl*)take(nb * sizeof(BatchCtl));
+  B.sched = (int*)take((8 + 2 * nb) * sizeof(int));
   if ((size_t)(p - (char*)workspace) > workspace_bytes) return cudaErrorMemoryAllocation;
+  // time slicing: plain job lists with more slots than blocks (nslots = the workspace slots the caller sized the workspace for)
+  B.nslots = nslots; B.quantum = (B.mode == 0 && !B.order && nslots > nblocks) ? quantum : 0;
   cudaError_t e;
+  if ((e = cudaMemsetAsync(B.ctl, 0, nb * sizeof(BatchCtl), st)) != cudaSuccess) return e;
+  {   // scheduler state: unlocked, first fresh unit 0, every slot free, empty queue
+    std::vector<int> h(8 + 2 * nb, 0);
+    h[2] = nslots; for (int i = 0; i < nslots; ++i) h[8 + i] = nslots - 1 - i;
+    if ((e = cudaMemcpyAsync(B.sched, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;   // (h is a local buffer)
+  }
   if ((e = cudaMemsetAsync(B.next_job, 0, 256, st)) != cudaSuccess) return e;
   // stamps: all ones = "older than any epoch"
   if ((e = cudaMemsetAsync(B.w_stamp0, 0xFF, nb * (size_t)fixed_all.n * 8, st)) != cudaSuccess) return e;
@@ -636,7 +740,25 @@ cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all
   if ((e = cudaMemsetAsync(B.w_sc, 0, nb * 2 * sizeof(Scal), st)) != cudaSuccess) return e;
   const size_t smem = lrr_batch_smem_bytes();
   if ((e = cudaFuncSetAttribute(k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const bool dbg_time = getenv("LRR_BATCH_DEBUG") != nullptr;
+  if (dbg_time) {
+    const auto c0 = std::chrono::steady_clock::now(); cudaStreamSynchronize(st);
+    fprintf(stderr, "[batch] clears of the workspace drained in %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count());
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st);
+  }
   k_batch<<<nblocks, BATCH_THREADS, smem, st>>>(B); ++*launches;
+  if (dbg_time) { cudaEventRecord(ev1, st); cudaEventSynchronize(ev1); float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); fprintf(stderr, "[batch] k_batch %.2f ms (events), %d blocks, %d slots, quantum %d\n", ms, nblocks, nslots, B.quantum); cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+  if (getenv("LRR_BATCH_DEBUG") && atoi(getenv("LRR_BATCH_DEBUG")) == 2) {   // the jobs that finished last: when they started, how long they waited parked
+    cudaStreamSynchronize(st);
+    std::vector<BatchCtl> hc((size_t)nslots); cudaMemcpy(hc.data(), B.ctl, hc.size() * sizeof(BatchCtl), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull, t1 = 0; for (auto& c : hc) if (c.t_first) { t0 = std::min(t0, c.t_first); t1 = std::max(t1, c.t_last); }
+    std::vector<int> idx; for (int i = 0; i < nslots; ++i) if (hc[(size_t)i].t_last) idx.push_back(i);
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return hc[(size_t)a].t_last > hc[(size_t)b].t_last; });
+    fprintf(stderr, "[batch] quantum %d slots %d makespan %.1f ms; last finishers (last tenant of the slot):\n", B.quantum, nslots, (t1 - t0) * 1e-6);
+    for (size_t k = 0; k < idx.size() && k < 6; ++k) { const BatchCtl& c = hc[(size_t)idx[k]];
+      fprintf(stderr, "  job %d its %d start %.1f end %.1f ms slices %d parked %.1f ms\n", c.done_job, c.done_it, (c.t_first - t0) * 1e-6, (c.t_last - t0) * 1e-6, c.slices, c.t_waited * 1e-6); }
+  }
   if (B.dbg) {
     long long h[16]; cudaStreamSynchronize(st); cudaMemcpy(h, B.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const char* nm[12] = {"roi", "ctl", "matchA", "matchB", "muse", "norm", "weight", "mad", "accum", "solve", "resid", "result"};
@@ -649,7 +771,8 @@ size_t lrr_batch_workspace_bytes(int nblocks, int n_moving, int n_fixed) {
   const size_t nb = (size_t)nblocks;
   auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
   size_t t = up(256) + up(nb * 2 * sizeof(Scal)) + 2 * up(nb * 2 * 4 * BATCH_CAP * 8) + up(nb * 2 * 6 * BATCH_CAP * 8) + up(nb * 2 * 2 * BATCH_CAP * 8) +
-             3 * up(nb * 2 * BATCH_CAP * 4) + up(nb * 2 * 2 * (3 * BATCH_CAP + 4) * 4) + up(nb * (size_t)n_fixed * 8) + up(nb * (size_t)n_moving * 8);
+             3 * up(nb * 2 * BATCH_CAP * 4) + up(nb * 2 * 2 * (3 * BATCH_CAP + 4) * 4) + up(nb * (size_t)n_fixed * 8) + up(nb * (size_t)n_moving * 8) +
+             up(nb * sizeof(BatchCtl)) + up((8 + 2 * nb) * sizeof(int));
   return t + 4096;
 }
 int lrr_batch_blocks_per_sm() {

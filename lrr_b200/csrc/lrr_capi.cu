@@ -3,6 +3,7 @@
 // kernels of lrr_grid.cu, lrr_icp.cu, lrr_select.cu, lrr_metrics.cu and lrr_batch.cu.
 // There is NO CPU fallback: every entry point that computes needs a CUDA device.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -108,6 +109,7 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
     if (getenv("LRR_NO_FLAT")) o.flat = 0;
     if (const char* ts = getenv("LRR_TILE_SPARSE")) o.tile_sparse = atoi(ts);
     if (getenv("LRR_NO_BATCH_SORT")) o.batch_sort = 0;
+    if (const char* q = getenv("LRR_BATCH_QUANTUM")) o.batch_quantum = atoi(q);
   }
   ok = ok && cudaStreamSynchronize(ctx->own_stream) == cudaSuccess;   // (allocations and clears are ordered on the context's own stream)
   if (!ok) { cudaGetLastError(); lrr_ctx_destroy(ctx); return LRR_ERR_CUDA; }
@@ -128,6 +130,8 @@ extern "C" void lrr_ctx_destroy(lrr_ctx* ctx) {
   enter(ctx);
   dfree(ctx->partials); dfree(ctx->ticket); dfree(ctx->sel_hist); dfree(ctx->sel_cand); dfree(ctx->sel_misc);
   dfree(ctx->muse_table); dfree(ctx->scratch_d); dfree(ctx->sort_keys);
+  for (auto& w : ctx->batch_ws) dfree(w.p);
+  ctx->batch_ws.clear();
   if (ctx->sort.keys2) lrr_sort_free(&ctx->sort);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
@@ -243,6 +247,7 @@ extern "C" int lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value) {
   else if (k == "flat_scan") o.flat = value != 0;
   else if (k == "tile_sparse") { if (value < -1 || value > 32) return LRR_ERR_INVALID; o.tile_sparse = value; }
   else if (k == "batch_sort") o.batch_sort = value != 0;
+  else if (k == "batch_quantum") { if (value < 0 || value > 250) return LRR_ERR_INVALID; o.batch_quantum = value; }
   else { ctx->err = "lrr_ctx_set_option: unknown key " + k; return LRR_ERR_INVALID; }
   return LRR_OK;
 }
@@ -1690,7 +1695,7 @@ static int batch_job_host(lrr_est* est, lrr_fset* moving_all, lrr_fset* fixed_al
 
 cudaError_t lrr_batch_launch(const FsetDev& moving_all, const FsetDev& fixed_all, const lrr_job* jobs_dev, lrr_result* out_dev, long long njobs,
                              const long long* job_ids_dev, int max_iter, unsigned long long shuffle_seed, const double* muse_table, int muse_rows, int nblocks, void* workspace,
-                             size_t workspace_bytes, cudaStream_t st, long long* launches);
+                             size_t workspace_bytes, cudaStream_t st, long long* launches, int nslots = 0, int quantum = 0);
 size_t lrr_batch_workspace_bytes(int nblocks, int n_moving, int n_fixed);
 int lrr_batch_blocks_per_sm();
 
@@ -1700,9 +1705,25 @@ struct BatchSlot {
   cudaStream_t st = nullptr; bool own_stream = false;
   void* work = nullptr; lrr_job* djobs = nullptr; lrr_result* dout = nullptr; long long* dids = nullptr;
   int64_t a = 0, n = 0; bool busy = false;
+  lrr_ctx* ctx = nullptr; size_t work_bytes = 0;   // the workspace goes back to the context's cache
 };
+// workspace cache of the context (released workspaces are idle: slot_collect has synchronised their stream)
+static cudaError_t ws_acquire(lrr_ctx* ctx, size_t bytes, cudaStream_t st, void** out, size_t* got) {
+  int best = -1;
+  for (size_t i = 0; i < ctx->batch_ws.size(); ++i) if (ctx->batch_ws[i].bytes >= bytes && (best < 0 || ctx->batch_ws[i].bytes < ctx->batch_ws[(size_t)best].bytes)) best = (int)i;
+  if (best >= 0) { *out = ctx->batch_ws[(size_t)best].p; *got = ctx->batch_ws[(size_t)best].bytes; ctx->batch_ws.erase(ctx->batch_ws.begin() + best); return cudaSuccess; }
+  *got = bytes;
+  return cudaMallocAsync(out, bytes, st);
+}
+static void ws_release(lrr_ctx* ctx, void* p, size_t bytes, cudaStream_t st) {
+  if (!p) return;
+  if (ctx->batch_ws.size() < 2) { ctx->batch_ws.push_back({p, bytes}); return; }
+  size_t small = 0; for (size_t i = 1; i < ctx->batch_ws.size(); ++i) if (ctx->batch_ws[i].bytes < ctx->batch_ws[small].bytes) small = i;
+  if (ctx->batch_ws[small].bytes < bytes) { cudaFreeAsync(ctx->batch_ws[small].p, st); ctx->batch_ws[small] = {p, bytes}; }
+  else cudaFreeAsync(p, st);
+}
 static void slot_release(BatchSlot& s) {
-  if (s.work) cudaFreeAsync(s.work, s.st); if (s.djobs) cudaFreeAsync(s.djobs, s.st); if (s.dout) cudaFreeAsync(s.dout, s.st); if (s.dids) cudaFreeAsync(s.dids, s.st);
+  if (s.work) { if (s.ctx) ws_release(s.ctx, s.work, s.work_bytes, s.st); else cudaFreeAsync(s.work, s.st); } if (s.djobs) cudaFreeAsync(s.djobs, s.st); if (s.dout) cudaFreeAsync(s.dout, s.st); if (s.dids) cudaFreeAsync(s.dids, s.st);
   s.work = nullptr; s.djobs = nullptr; s.dout = nullptr; s.dids = nullptr;
 }
 static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t a, int64_t n,
@@ -1716,9 +1737,31 @@ static int slot_launch(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lrr_fse
 static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, int64_t a, int64_t n,
                             const int64_t* ids, int64_t id_base, int max_iter, uint64_t shuffle_seed, lrr_result* out) {
   const int nblocks = (int)std::min<int64_t>(n, (int64_t)lrr_num_sms() * lrr_batch_blocks_per_sm());
-  const size_t wbytes = lrr_batch_workspace_bytes(nblocks, (int)moving_all->n, (int)fixed_all->n);
+  // time slicing (lrr_batch.cu): more workspace slots than blocks, a job is parked after `batch_quantum` iterations and the block takes
+  // the next unit — every job is started early, so the jobs that run into the iteration cap no longer start late and end the launch
+  // alone.  Slots: up to 1024 (one per job in flight) within an eighth of the free device memory.
+  int nslots = nblocks;
+  const int quantum = ctx->opt.batch_quantum;
+  if (quantum > 0 && n > nblocks) {
+    const size_t per_slot = lrr_batch_workspace_bytes(2, (int)moving_all->n, (int)fixed_all->n) - lrr_batch_workspace_bytes(1, (int)moving_all->n, (int)fixed_all->n);
+    // (the budget is fixed per context, from the device's total memory: cudaMemGetInfo per launch was measured at 0.1 ... 50 ms)
+    if (!ctx->batch_budget) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+      ctx->batch_budget = std::max<size_t>(std::min<size_t>(total_b / 16, (size_t)16 << 30), 1);
+    }
+    const size_t budget = ctx->batch_budget;
+    const int64_t fit = per_slot ? (int64_t)(budget / per_slot) : 0;
+    nslots = (int)std::max<int64_t>(nblocks, std::min<int64_t>(std::min<int64_t>(n, 1024), fit));
+  }
+  const size_t wbytes = lrr_batch_workspace_bytes(nslots, (int)moving_all->n, (int)fixed_all->n);
   cudaStream_t st = s.st;
-  CK(cudaMallocAsync(&s.work, wbytes, st));
+  s.ctx = ctx;
+  const bool dbg_time = getenv("LRR_BATCH_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tl0 = now();
+  CK(ws_acquire(ctx, wbytes, st, &s.work, &s.work_bytes));
+  const double tl1 = now();
   CK(cudaMallocAsync((void**)&s.djobs, sizeof(lrr_job) * n, st)); CK(cudaMallocAsync((void**)&s.dout, sizeof(lrr_result) * n, st));
   CK(cudaMallocAsync((void**)&s.dids, sizeof(long long) * n, st));
   CK(cudaMemcpyAsync(s.djobs, jobs + a, sizeof(lrr_job) * n, cudaMemcpyHostToDevice, st));
@@ -1729,7 +1772,8 @@ static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lr
   double table[4 * 32] = {0};
   const int rows = build_muse_table(1000u, table);
   fset_wait_dirs(moving_all, st); fset_wait_dirs(fixed_all, st);
-  CK(lrr_batch_launch(moving_all->dev, fixed_all->dev, s.djobs, s.dout, n, s.dids, max_iter, shuffle_seed, table, rows, nblocks, s.work, wbytes, st, &ctx->launches));
+  if (dbg_time) { cudaStreamSynchronize(st); fprintf(stderr, "[batch host] workspace %.2f ms, job copies %.2f ms\n", tl1 - tl0, now() - tl1); }
+  CK(lrr_batch_launch(moving_all->dev, fixed_all->dev, s.djobs, s.dout, n, s.dids, max_iter, shuffle_seed, table, rows, nblocks, s.work, s.work_bytes, st, &ctx->launches, nslots, quantum));
   CK(cudaMemcpyAsync(out + a, s.dout, sizeof(lrr_result) * n, cudaMemcpyDeviceToHost, st));
   s.a = a; s.n = n; s.busy = true;
   return LRR_OK;
@@ -1802,12 +1846,18 @@ static int batch_run_impl(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_al
     // the queue in the order longest-expected-first: permuted copies of the jobs and of their ids (the id seeds a job's shuffle and
     // must stay the job's own), results scattered back to the list order afterwards
     std::vector<int64_t> perm;
+    const bool dbg_time = getenv("LRR_BATCH_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double th0 = now();
     int rc = batch_queue_order(ctx, moving_all, fixed_all, jobs, njobs, perm); if (rc != LRR_OK) return rc;
+    const double th1 = now();
     std::vector<lrr_job> pj((size_t)njobs); std::vector<int64_t> pid((size_t)njobs); std::vector<lrr_result> pout((size_t)njobs);
     for (int64_t i = 0; i < njobs; ++i) { const int64_t j = perm[(size_t)i]; pj[(size_t)i] = jobs[j]; pid[(size_t)i] = ids ? ids[j] : j; }
     BatchSlot s; s.st = ctx->stream;
     { PHASE(PH_BATCH); rc = slot_launch(ctx, s, moving_all, fixed_all, pj.data(), 0, njobs, pid.data(), 0, max_iter, shuffle_seed, pout.data()); }
+    const double th2 = now();
     const int rc2 = slot_collect(ctx, s);
+    if (dbg_time) fprintf(stderr, "[batch host] order %.2f ms, launch (workspace, copies, clears, kernel enqueue) %.2f ms, collect %.2f ms\n", th1 - th0, th2 - th1, now() - th2);
     if (rc != LRR_OK) return rc;
     if (rc2 != LRR_OK) return rc2;
     for (int64_t i = 0; i < njobs; ++i) out[perm[(size_t)i]] = pout[(size_t)i];

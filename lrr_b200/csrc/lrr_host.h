@@ -23,7 +23,8 @@ struct lrr_ctx {
   // behaviour switches (lrr_ctx_set_option; the environment variables of README.md only set their initial values)
   struct Options { int certificates = 1, tile = 1, spec = 1 /* 0 never, 1 when the last iteration kept every query, 2 always */, pipe = 1, norm_skip = 1,
                        tile_sparse = -1 /* -1: by the host hint */, flat = 1,
-                       batch_sort = 1 /* batched mode: jobs handed out longest-expected-first */; } opt;
+                       batch_sort = 1 /* batched mode: jobs handed out longest-expected-first */,
+                       batch_quantum = 8 /* batched mode: iterations a job runs before it is parked for the next unit (0: run to completion) */; } opt;
   bool async_upload = false; cudaStream_t dirs_stream = nullptr;
   unsigned long long sel_owner = 0; long long window_misses = 0;   // signature of the last estimate that left valid search windows in the selectors
   SortScratch sort; double* sort_keys = nullptr;
@@ -31,6 +32,9 @@ struct lrr_ctx {
   double* scratch_d = nullptr;
   void* pinned = nullptr;
   double* mailbox = nullptr; double* mailbox_dev = nullptr; unsigned long long mailbox_seq = 0; long long spec_misses = 0;   // result mailbox (mapped pinned, lrr_icp.cu)
+  // workspaces of the batched mode kept between calls (up to two: lrr_batch_run_multi has two launches in flight per device): with the
+  // slot pool of the time-sliced kernel a workspace is gigabytes, and a fresh allocation of that size from the driver costs tens of ms
+  struct Ws { void* p; size_t bytes; }; std::vector<Ws> batch_ws; size_t batch_budget = 0;
   // instrumentation: CUDA-event timing per phase kernel (lrr_ctx_set_profiling)
   bool profiling = false;
   struct Span { int phase; cudaEvent_t a, b; };

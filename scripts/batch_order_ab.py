@@ -17,6 +17,7 @@ ctx.batch_run(mv, fx, jobs[:512], 70, bench.BATCH_SEED)
 def timed(j, ids=None):
     ctx.synchronize(); t0 = time.perf_counter(); out = ctx.batch_run(mv, fx, j, 70, bench.BATCH_SEED, ids=ids); ctx.synchronize(); return time.perf_counter() - t0, out
 res = {}
+ctx.set_option("batch_quantum", 0)
 for sort in (0, 1, 0, 1):
     ctx.set_option("batch_sort", sort)
     dt, out = timed(jobs)
@@ -39,3 +40,20 @@ for name, sort, use_costs in (("block-cyclic, list order", 0, False), ("block-cy
         dt, _ = timed(jobs[ids], ids)
         ts.append(dt)
     print(f"N=8 emulated, {name}: shares {min(ts):.4f} .. {max(ts):.4f} s  -> {len(jobs) / max(ts):.0f} registrations/s  (ideal from the whole-list time would be 8 x)")
+
+# time slicing (suspend / resume): a job is parked after `batch_quantum` iterations and the block takes the next unit
+ctx.set_option("batch_sort", 1)
+for q in (0, 4, 8, 16, 8):
+    ctx.set_option("batch_quantum", q)
+    dt, out = timed(jobs)
+    for k in ("status", "converged", "iterations", "n_moving_inside", "n_fixed_inside"):
+        assert np.array_equal(out[k], res[1][k]), (q, k)
+    for k in ("A", "t", "cov"):
+        assert np.allclose(out[k], res[1][k], rtol=1e-9, atol=1e-12), (q, k)
+    ts = []
+    for r in range(W):
+        ids = job_shard(len(jobs), W, r, costs)
+        dts, o2 = timed(jobs[ids], ids)
+        assert np.array_equal(o2["iterations"], res[1]["iterations"][ids])
+        ts.append(dts)
+    print(f"batch_quantum={q}: whole list {dt:.4f} s {len(jobs) / dt:.0f} registrations/s; N=8 emulated shares {min(ts):.4f} .. {max(ts):.4f} s -> {len(jobs) / max(ts):.0f} registrations/s")
