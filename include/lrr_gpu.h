@@ -127,7 +127,8 @@ int  lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const doubl
  * "pipeline" 0/1 (trailing residual pass = certificate pass of the next find_closest), "norm_skip" 0/1, "flat_scan" 0/1,
  * "tile_sparse" -1 (by the host hint) or 0..32; batched mode: "batch_sort" 0/1 (jobs handed out longest-expected-first),
  * "batch_quantum" 0..250 (iterations a job runs before it is parked and the block takes the next unit; 0 = run to completion; default 8:
- * the workspace then holds a slot per job in flight, up to 1024 slots within 1/16 of the device memory, and is kept by the context).
+ * the workspace then holds a slot per job in flight, up to "batch_slots" (default 1024) within 1/16 of the device memory, and is kept by
+ * the context).
  * The environment variables listed in README.md only set the initial values.
  * Estimators created before the call see the new value from their next call on. */
 int  lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value);

@@ -248,6 +248,7 @@ extern "C" int lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value) {
   else if (k == "tile_sparse") { if (value < -1 || value > 32) return LRR_ERR_INVALID; o.tile_sparse = value; }
   else if (k == "batch_sort") o.batch_sort = value != 0;
   else if (k == "batch_quantum") { if (value < 0 || value > 250) return LRR_ERR_INVALID; o.batch_quantum = value; }
+  else if (k == "batch_slots") { if (value < 1 || value > 65536) return LRR_ERR_INVALID; o.batch_slots = value; }
   else { ctx->err = "lrr_ctx_set_option: unknown key " + k; return LRR_ERR_INVALID; }
   return LRR_OK;
 }
@@ -1752,7 +1753,7 @@ static int slot_launch_impl(lrr_ctx* ctx, BatchSlot& s, lrr_fset* moving_all, lr
     }
     const size_t budget = ctx->batch_budget;
     const int64_t fit = per_slot ? (int64_t)(budget / per_slot) : 0;
-    nslots = (int)std::max<int64_t>(nblocks, std::min<int64_t>(std::min<int64_t>(n, 1024), fit));
+    nslots = (int)std::max<int64_t>(nblocks, std::min<int64_t>(std::min<int64_t>(n, ctx->opt.batch_slots), fit));
   }
   const size_t wbytes = lrr_batch_workspace_bytes(nslots, (int)moving_all->n, (int)fixed_all->n);
   cudaStream_t st = s.st;

@@ -24,7 +24,8 @@ struct lrr_ctx {
   struct Options { int certificates = 1, tile = 1, spec = 1 /* 0 never, 1 when the last iteration kept every query, 2 always */, pipe = 1, norm_skip = 1,
                        tile_sparse = -1 /* -1: by the host hint */, flat = 1,
                        batch_sort = 1 /* batched mode: jobs handed out longest-expected-first */,
-                       batch_quantum = 8 /* batched mode: iterations a job runs before it is parked for the next unit (0: run to completion) */; } opt;
+                       batch_quantum = 8 /* batched mode: iterations a job runs before it is parked for the next unit (0: run to completion) */,
+                       batch_slots = 1024 /* ... and the most workspace slots (jobs in flight) it may use */; } opt;
   bool async_upload = false; cudaStream_t dirs_stream = nullptr;
   unsigned long long sel_owner = 0; long long window_misses = 0;   // signature of the last estimate that left valid search windows in the selectors
   SortScratch sort; double* sort_keys = nullptr;

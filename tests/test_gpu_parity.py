@@ -174,6 +174,42 @@ def test_batch_run(gpu_lib, oracle_lib):
         assert abs(g["rms"][j] - o["rms"][j]) <= 1e-8 * max(1.0, o["rms"][j])
 
 
+def test_batch_time_slicing(gpu_lib, oracle_lib):
+    """More jobs than thread blocks: the batched mode parks a job after `batch_quantum` iterations and any block takes it up again
+    (slot pool, FIFO of parked jobs).  Every quantum — and a pool with fewer slots than jobs, so that slots change tenants — gives the
+    results of run-to-completion (integer fields exact, transforms to rounding: the work-queue order of pass A enters a job's sums), and
+    those are the oracle's."""
+    pair = synth.make_pair(4, 30000, 30000, size=110.0)
+    jobs = synth.make_jobs(pair, 40, 8, seed=6)
+    jobs[7]["roi_half_size"] = 3.0
+    ctx = gpu_lib.context()
+    fx, mv = ctx.upload(pair["fixed"]), ctx.upload(pair["moving"])
+    runs = {}
+    try:
+        for q, slots in ((0, 1024), (8, 1024), (1, 1024), (3, 160), (70, 200)):
+            ctx.set_option("batch_quantum", q); ctx.set_option("batch_slots", slots)
+            runs[(q, slots)] = ctx.batch_run(mv, fx, jobs, 40, 99)
+    finally:
+        ctx.set_option("batch_quantum", 8); ctx.set_option("batch_slots", 1024)
+    base = runs[(0, 1024)]
+    assert (base["status"] == 0).sum() > 250 and base["status"][7] == 1
+    assert len(set(base["iterations"][base["status"] == 0].tolist())) > 5      # jobs of very different lengths
+    for key, r in runs.items():
+        for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"):
+            assert np.array_equal(r[k], base[k]), (key, k)
+        for k in ("A", "t", "cov", "rms", "weighted_error"):
+            assert np.allclose(r[k], base[k], rtol=1e-9, atol=1e-12), (key, k)
+    octx = oracle_lib.context()
+    ofx, omv = octx.upload(pair["fixed"]), octx.upload(pair["moving"])
+    sample = np.arange(0, len(jobs), 27)
+    o = octx.batch_run(omv, ofx, jobs[sample], 40, 99, ids=sample)
+    g = runs[(3, 160)][sample]
+    for k in ("status", "converged", "oscillated", "iterations", "n_moving_inside", "n_fixed_inside"):
+        assert np.array_equal(g[k], o[k]), (k, g[k], o[k])
+    for j in np.nonzero(g["status"] == 0)[0]:
+        assert rel(g["A"][j], o["A"][j]) < TOL_PARAM and rel(g["t"][j], o["t"][j]) < TOL_PARAM and rel(g["cov"][j], o["cov"][j]) < TOL_PARAM
+
+
 def test_objcov(gpu_lib, oracle_lib, pair):
     """A13: cdcl_obj_fun_cov f/g on the ICP matches, and the LBFGS covariance refinement built on it (config 5 in miniature)."""
     _, g = make_est(gpu_lib, pair, "cdcl_fwd", number_points=5000)
