@@ -19,7 +19,10 @@
 #define BATCH_CAP 16384            // max features of one ROI (larger ROIs are returned to the host path)
 #define BATCH_SEL_BINS 2048
 #define BATCH_SEL_CAND 1024
+#ifndef BATCH_THREADS
 #define BATCH_THREADS 512           // one block of 16 warps per SM: half the per-registration latency of 2 x 256
+#endif
+#define BATCH_MIN_BLOCKS (512 / BATCH_THREADS)
 
 struct BatchWork {                 // per-block workspace in global memory
   // per direction
@@ -318,7 +321,7 @@ __device__ void sched_park(const BatchArgs& B, int slot) {
 extern __shared__ __align__(16) unsigned char batch_smem[];
 #define TPH(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); S.tph[i] += now_ - tmark; tmark = now_; } } while (0)
 
-__global__ void __launch_bounds__(BATCH_THREADS, 1) k_batch(const __grid_constant__ BatchArgs B) {
+__global__ void __launch_bounds__(BATCH_THREADS, BATCH_MIN_BLOCKS) k_batch(const __grid_constant__ BatchArgs B) {
   BatchShared& S = *reinterpret_cast<BatchShared*>(batch_smem);
   int* list = reinterpret_cast<int*>(batch_smem + ((sizeof(BatchShared) + 15) & ~size_t(15)));   // BATCH_CAP ints
   const BlockScope scope;

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../lrr_b200/csrc"
 name=$1; shift
 out=build/variants/$name; mkdir -p $out
-for f in lrr_grid lrr_icp lrr_tile lrr_select lrr_metrics lrr_objcov lrr_batch lrr_regions lrr_capi; do
+for f in lrr_grid lrr_icp lrr_tile lrr_select lrr_metrics lrr_objcov lrr_cdc lrr_batch lrr_regions lrr_capi; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcudafe --diag_suppress=550 -Xcudafe --diag_suppress=177 "$@" -c $f.cu -o $out/$f.o &
 done
 wait
