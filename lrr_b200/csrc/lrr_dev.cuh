@@ -391,7 +391,9 @@ __device__ __forceinline__ int lrr_nn_pass_b_cert(const GridDev& g, double qx, d
 // The radius is fixed by the candidate (the neighbour of the previous iteration): every point within sqrt(st.best) + margin of the
 // query lies in a scanned run — the exactness argument of lrr_nn_pass_b_cert with no pruning at all.  Returns the sorted slot of
 // the exact neighbour (ties: lowest original index) and the certificate bound (0: none).
+#ifndef LRR_FLAT_ROWS
 #define LRR_FLAT_ROWS 128
+#endif
 __device__ __forceinline__ int lrr_nn_ball_flat(const GridDev& g, double qx, double qy, double qz, NNState st, double margin, double* bound_out,
                                                 int* rowlo, int* rowbase) {
   *bound_out = 0.0;
