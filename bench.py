@@ -657,6 +657,11 @@ def run_b200(args, rank, world, local_rank):
         names = {"accumulate": ["k_accumulate"], "weight": ["k_weight"], "resid": ["k_match_cert"]}.get(dom, [])
         if names and all(n in tj["dram_bytes_per_launch"] for n in names):
             traffic = sum(tj["dram_bytes_per_launch"][n] for n in names); traffic_src = tj["source"]
+        first = tj.get("dram_bytes_per_launch_first_finest_iteration", {})
+        if dom == "match" and all(n in first for n in ("k_match_cert", "k_match_tile", "k_match_hard")):
+            # the `match` phase is timed only in the first finest-level iteration of a registration (afterwards the certificate pass is
+            # the trailing pass of the previous iteration): its three launches together, from the capture of exactly that iteration
+            traffic = sum(first[n] for n in ("k_match_cert", "k_match_tile", "k_match_hard")); traffic_src = tj["source"]
     except Exception:
         pass
     it_bytes = algorithmic_bytes_iteration(M, N, M, N)
