@@ -125,7 +125,7 @@ int  lrr_features_upload(lrr_ctx* ctx, int64_t n, const double* xyz, const doubl
  * keys: "certificates" 0/1 (neighbour certificates), "tile" 0/1 (staged search, certificate pass and sparse list of the finest level),
  * "speculative" 0 never / 1 after an iteration that kept every query / 2 in every finest-level iteration (the device refuses a lost bet),
  * "pipeline" 0/1 (trailing residual pass = certificate pass of the next find_closest), "norm_skip" 0/1, "flat_scan" 0/1,
- * "tile_sparse" -1 (by the host hint) or 0..32; batched mode: "batch_sort" 0/1 (jobs handed out longest-expected-first),
+ * "tile_sparse" -1 (by the host hint) or 0..32, "first_sparse" 0/1 (a level's first find_closest on the per-query list); batched mode: "batch_sort" 0/1 (jobs handed out longest-expected-first),
  * "batch_quantum" 0..250 (iterations a job runs before it is parked and the block takes the next unit; 0 = run to completion; default 8:
  * the workspace then holds a slot per job in flight, up to "batch_slots" (default 1024) within 1/16 of the device memory, and is kept by
  * the context).

@@ -108,6 +108,7 @@ extern "C" int lrr_ctx_create(int device, lrr_ctx** out) {
     if (getenv("LRR_NO_NORM_SKIP")) o.norm_skip = 0;
     if (getenv("LRR_NO_FLAT")) o.flat = 0;
     if (const char* ts = getenv("LRR_TILE_SPARSE")) o.tile_sparse = atoi(ts);
+    if (getenv("LRR_NO_FIRST_SPARSE")) o.first_sparse = 0;
     if (getenv("LRR_NO_BATCH_SORT")) o.batch_sort = 0;
     if (const char* q = getenv("LRR_BATCH_QUANTUM")) o.batch_quantum = atoi(q);
   }
@@ -246,6 +247,7 @@ extern "C" int lrr_ctx_set_option(lrr_ctx* ctx, const char* key, int value) {
   else if (k == "norm_skip") o.norm_skip = value != 0;
   else if (k == "flat_scan") o.flat = value != 0;
   else if (k == "tile_sparse") { if (value < -1 || value > 32) return LRR_ERR_INVALID; o.tile_sparse = value; }
+  else if (k == "first_sparse") o.first_sparse = value != 0;
   else if (k == "batch_sort") o.batch_sort = value != 0;
   else if (k == "batch_quantum") { if (value < 0 || value > 250) return LRR_ERR_INVALID; o.batch_quantum = value; }
   else if (k == "batch_slots") { if (value < 1 || value > 65536) return LRR_ERR_INVALID; o.batch_slots = value; }
@@ -399,7 +401,11 @@ static EstArgs est_args(lrr_est* e, int src = 0) {
     // (without the hint — a level's first find_closest — whole chunks are staged: with candidates for every query the list would win
     //  up to ~300k features per side, 160 -> 140 us at 100k, but in a fresh estimator the 36 % of the queries that have no previous
     //  neighbour yet make it lose, 0.36 -> 0.54 ms: profiles/r2_summary.md)
-    a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : (ts >= 0 ? ts : (e->sparse_hint ? 32 : 8)); }
+    // (round 2, later: queries without a previous neighbour borrow the candidate of a neighbouring lane of their chunk, k_match_cert;
+    //  with that the list is tried for a level's first find_closest again up to 300k features per side: opt.first_sparse)
+    int64_t total_in = 0; for (int d = 0; d < a.ndir; ++d) total_in += e->d[d].n_in;
+    const bool first_list = ctx->opt.first_sparse && total_in <= 300000 * (int64_t)a.ndir;
+    a.tile_sparse = (f & LRR_F_NOFLAT) ? 0 : (ts >= 0 ? ts : ((e->sparse_hint || first_list) ? 32 : 8)); }
   a.selG[0] = ctx->sel[0]; a.selG[1] = ctx->sel[1]; a.selS[0] = ctx->sel[2]; a.selS[1] = ctx->sel[3];
   a.partials = ctx->partials; a.ticket = ctx->ticket;
   return a;

@@ -22,7 +22,7 @@ struct lrr_ctx {
   SelDev sel[4];
   // behaviour switches (lrr_ctx_set_option; the environment variables of README.md only set their initial values)
   struct Options { int certificates = 1, tile = 1, spec = 1 /* 0 never, 1 when the last iteration kept every query, 2 always */, pipe = 1, norm_skip = 1,
-                       tile_sparse = -1 /* -1: by the host hint */, flat = 1,
+                       tile_sparse = -1 /* -1: by the host hint */, flat = 1, first_sparse = 1 /* a level's first find_closest also goes to the per-query list */,
                        batch_sort = 1 /* batched mode: jobs handed out longest-expected-first */,
                        batch_quantum = 8 /* batched mode: iterations a job runs before it is parked for the next unit (0: run to completion) */,
                        batch_slots = 1024 /* ... and the most workspace slots (jobs in flight) it may use */; } opt;

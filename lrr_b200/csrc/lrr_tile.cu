@@ -548,10 +548,23 @@ __global__ void __launch_bounds__(LRR_CERT_THREADS, LRR_CERT_MINBLK) k_match_cer
           int base = 0;
           if (lane == 0) base = atomicAdd(d.fq_count, nrest);
           base = __shfl_sync(0xffffffffu, base, 0);
+          // A query WITHOUT a previous neighbour (a from-feature the point-count ramp has just added) borrows the candidate of the nearest
+          // lane that has one: the 32 queries of a chunk lie in one sub-cell of a tile, so a neighbouring query's neighbour is a few
+          // millimetres away and bounds the ball scan of the eight-lane groups; without a candidate the query would go to the
+          // one-warp-per-query pass and its shell search.  Any to-feature is a valid candidate: the search is exact whatever it starts from.
+          const int sp_mine = valid ? d.cprev[tq] : -1;
+          const unsigned int have = __ballot_sync(0xffffffffu, sp_mine >= 0);
+          int donor = lane;
+          if (sp_mine < 0 && have) {
+            const unsigned int below = have & ((1u << lane) - 1u), above = lane < 31 ? (have & ~((2u << lane) - 1u)) : 0u;
+            const int lb = below ? 31 - __clz(below) : -1, la = above ? __ffs(above) - 1 : -1;
+            donor = (lb >= 0 && (la < 0 || lane - lb <= la - lane)) ? lb : la;
+          }
+          const int sp_cand = __shfl_sync(0xffffffffu, sp_mine, donor);
           if (valid && !kept) {
             // (the record is put together again from the caches here, on the rare path, instead of being carried in registers through the
             //  common one: that cost the kernel 76 bytes of spills and ~6 us per launch)
-            FqRec r; r.k = __ldg(d.proc + tq); r.cand = d.cprev[tq]; r.cand_o = 0x7fffffff; r.tq = tq;
+            FqRec r; r.k = __ldg(d.proc + tq); r.cand = sp_cand; r.cand_o = 0x7fffffff; r.tq = tq;
             r.x = __ldg(d.tfx + tq); r.y = __ldg(d.tfy + tq); r.z = __ldg(d.tfz + tq); r.best = 1e300;
             if (r.cand >= 0) {
               const double4 q = lrr_ld_pos4(g.pos4 + r.cand);
