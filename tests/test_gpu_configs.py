@@ -183,11 +183,11 @@ def test_async_upload_of_directions(gpu_lib):
 
 
 def test_context_options_switch_paths_without_changing_results(gpu_lib):
-    """lrr_ctx_set_option: certificates / tile / speculative / pipeline / tile_sparse select launch plans, never results (index sets
+    """lrr_ctx_set_option: certificates / tile / speculative / pipeline / tile_sparse / first_sparse select launch plans, never results (index sets
     bit-exact, transforms to rounding)"""
     pair = synth.make_pair(43, 20000, 20000)
     ref = None
-    for opts in ({}, {"certificates": 0}, {"tile": 0}, {"speculative": 2}, {"pipeline": 0}, {"tile_sparse": 0}, {"tile_sparse": 32}, {"norm_skip": 0, "flat_scan": 0}):
+    for opts in ({}, {"certificates": 0}, {"tile": 0}, {"speculative": 2}, {"pipeline": 0}, {"tile_sparse": 0}, {"tile_sparse": 32}, {"norm_skip": 0, "flat_scan": 0}, {"first_sparse": 0}):
         ctx = gpu_lib.context()
         for k, v in opts.items():
             ctx.set_option(k, v)
