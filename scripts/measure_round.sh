@@ -6,6 +6,8 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${T}_ref.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 5 --warmup 3 --only-iterations > gpurun_out/${T}_ncu_launch.log 2>&1
 # in-registration finest-level iterations (2nd onwards: certificates in place, transform still moving) — the state `value` is quoted on
 LRR_PROF_INREG=2 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_${T}_inreg -f python scripts/prof_iter.py 100000 1 > gpurun_out/${T}_ncu_inreg.log 2>&1
+# the FIRST finest-level iteration of the registration (no certificates yet: the whole find_closest the bench line's `roofline` names)
+LRR_PROF_INREG=1 ncu --set full --clock-control none --profile-from-start off -c 10 -o gpurun_out/prof_${T}_first -f python scripts/prof_iter.py 100000 1 > gpurun_out/${T}_ncu_first.log 2>&1
 # one fixed-point iteration (round 1's state, kept for comparison)
 LRR_PROF_SETTLE=15 LRR_PROF_RANGE=1 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_${T} -f python scripts/prof_iter.py 100000 1 > gpurun_out/${T}_ncu_full.log 2>&1
 tail -3 gpurun_out/${T}_ncu_full.log gpurun_out/${T}_ncu_inreg.log

@@ -47,7 +47,23 @@ if os.path.exists(inreg):
     for name, (cnt, by, us) in agg.items():
         tr_in[name] = by / cnt
         print(f"  {name}: {cnt} launches, {us / cnt:.1f} us, {by / cnt / 1e6:.2f} MB per launch")
+first = f"{G}/prof_{T}_first.ncu-rep"
+tr_first = {}
+if os.path.exists(first):   # the first finest-level iteration of the registration (LRR_PROF_INREG=1 -c 10): first launch of every kernel
+    raw = subprocess.run(["ncu", "-i", first, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(raw.splitlines())); h, u = r[0], r[1]
+    idx = [h.index(w) for w in want]
+    with open(f"{P}/{R}_ncu_full_first_finest_iteration.csv", "w", newline="") as f:
+        w = csv.writer(f); w.writerow(want); w.writerow([u[i] for i in idx])
+        for row in r[2:]:
+            w.writerow([row[i] for i in idx])
+            name = row[h.index("Kernel Name")].split("(")[0]
+            if name not in tr_first:
+                tr_first[name] = sum(float(row[h.index(m)]) * scale[u[h.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                print(f"  first finest-level iteration: {name} {row[h.index('gpu__time_duration.sum')]} us, {tr_first[name] / 1e6:.2f} MB")
 json.dump({"source": f"ncu --set full --clock-control none of scripts/prof_iter.py 100000 1; cold caches under ncu replay. in_registration: LRR_PROF_INREG=2, "
            f"finest-level iterations 2.. of the ramped registration (profiles/{R}_ncu_full_inreg_kernels.csv); fixed_point: LRR_PROF_RANGE, LRR_PROF_SETTLE=15 "
-           f"(profiles/{R}_ncu_full_top_kernels.csv)", "dram_bytes_per_launch": tr_in or tr_fixed, "dram_bytes_per_launch_fixed_point": tr_fixed},
+           f"(profiles/{R}_ncu_full_top_kernels.csv); first_finest_iteration: LRR_PROF_INREG=1 -c 10, the first finest-level iteration of the registration, no "
+           f"certificates yet (profiles/{R}_ncu_full_first_finest_iteration.csv)",
+           "dram_bytes_per_launch": tr_in or tr_fixed, "dram_bytes_per_launch_fixed_point": tr_fixed, "dram_bytes_per_launch_first_finest_iteration": tr_first},
           open(f"{P}/ncu_traffic.json", "w"), indent=1)
