@@ -282,9 +282,9 @@ int  lrr_batch_run(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, cons
 int  lrr_batch_run_ids(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* fixed_all, const lrr_job* jobs, const int64_t* job_ids,
                        int64_t njobs, int max_iter, uint64_t shuffle_seed, lrr_result* out);
 /* The whole list over ndev devices of ONE process (the reference's outer loops, :2138 / :2230 / :2332, are one sequential program):
- * ctx[d], moving_all[d], fixed_all[d] = replicas of the same volume pair on device d.  One host thread per device, runs of jobs
- * drawn from one shared cursor (dynamic), two launches in flight per device, results written in place; job j is seeded with
- * shuffle_seed + j whichever device runs it. */
+ * ctx[d], moving_all[d], fixed_all[d] = replicas of the same volume pair on device d.  One host thread per device, one launch per device
+ * over its share of the list (dealt from the jobs sorted by expected cost, so every device gets the same mix; the kernel schedules
+ * inside a launch), results written in place; job j is seeded with shuffle_seed + j whichever device runs it. */
 int  lrr_batch_run_multi(lrr_ctx** ctx, int ndev, lrr_fset** moving_all, lrr_fset** fixed_all, const lrr_job* jobs, int64_t njobs,
                          int max_iter, uint64_t shuffle_seed, lrr_result* out);
 

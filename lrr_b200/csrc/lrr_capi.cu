@@ -1885,10 +1885,9 @@ extern "C" int lrr_batch_run_ids(lrr_ctx* ctx, lrr_fset* moving_all, lrr_fset* f
 }
 
 // The whole job list over ndev devices of THIS process (the reference's outer loops are one sequential program: a host that links
-// the backend has no process per GPU).  One host thread per device; the threads draw runs of jobs from one shared cursor (dynamic:
-// job costs range from a rejected ROI to 70 iterations) and keep two launches in flight per device, so that the blocks of the next
-// run start as the blocks of the current one run out of jobs.  Results are written in place; job j is seeded with
-// shuffle_seed + j whichever device runs it, so the result does not depend on the number of devices.
+// the backend has no process per GPU).  One host thread per device, one launch per device over its share of the list (dealt from the
+// jobs sorted by expected cost); the kernel schedules inside a launch (job cursor, time slices).  Results are written in place; job j is
+// seeded with shuffle_seed + j whichever device runs it, so the result does not depend on the number of devices.
 #include <thread>
 extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_all, lrr_fset** fixed_all, const lrr_job* jobs, int64_t njobs,
                                    int max_iter, uint64_t shuffle_seed, lrr_result* out) {
@@ -1901,31 +1900,29 @@ extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_a
   if (max_iter > 250 || ndev == 1) return batch_run_impl(ctxs[0], moving_all[0], fixed_all[0], jobs, njobs, nullptr, max_iter, shuffle_seed, out);
   std::vector<int64_t> perm;
   { enter(ctxs[0]); const int rc = batch_queue_order(ctxs[0], moving_all[0], fixed_all[0], jobs, njobs, perm); if (rc != LRR_OK) return rc; }
-  std::vector<lrr_job> pj((size_t)njobs); std::vector<lrr_result> pout((size_t)njobs);
-  for (int64_t i = 0; i < njobs; ++i) pj[(size_t)i] = jobs[perm[(size_t)i]];
-  std::atomic<int64_t> cursor{0};
+  // One launch per device over a share dealt from the list sorted by expected cost (device d takes positions d, d + ndev, ... : every
+  // device gets the same mix of large and small ROIs); inside a launch the time-sliced kernel does the dynamic scheduling.  (A first
+  // version drew runs of a few hundred jobs from a shared cursor, two launches in flight per device: every launch ends in a sparse tail
+  // of long jobs, and sixteen of them cost more than they balanced — 0.64 of 2 x the one-device rate on two B200, 0.45 with time slicing.)
+  std::vector<std::vector<lrr_job> > pj((size_t)ndev); std::vector<std::vector<int64_t> > pid((size_t)ndev); std::vector<std::vector<lrr_result> > pout((size_t)ndev);
+  for (int64_t i = 0; i < njobs; ++i) { const size_t d = (size_t)(i % ndev); pj[d].push_back(jobs[perm[(size_t)i]]); pid[d].push_back(perm[(size_t)i]); }
+  for (int d = 0; d < ndev; ++d) pout[(size_t)d].resize(pj[(size_t)d].size());
   std::vector<int> rcs((size_t)ndev, LRR_OK);
   auto worker = [&](int d) {
     lrr_ctx* ctx = ctxs[d];
     enter(ctx);
-    const int64_t nblocks = (int64_t)lrr_num_sms() * lrr_batch_blocks_per_sm();
-    const int64_t run = std::max<int64_t>(nblocks, std::min<int64_t>(4 * nblocks, njobs / (8 * (int64_t)ndev)));
-    BatchSlot slot[2];
+    const int64_t n = (int64_t)pj[(size_t)d].size();
+    if (n == 0) { rcs[(size_t)d] = LRR_OK; return; }
+    BatchSlot slot;
     int rc = LRR_OK;
-    for (int k = 0; k < 2; ++k) {
-      if (cudaStreamCreateWithFlags(&slot[k].st, cudaStreamNonBlocking) != cudaSuccess) { rc = LRR_ERR_CUDA; ctx->err = "cudaStreamCreate"; }
-      else slot[k].own_stream = true;
-    }
+    if (cudaStreamCreateWithFlags(&slot.st, cudaStreamNonBlocking) != cudaSuccess) { rcs[(size_t)d] = LRR_ERR_CUDA; ctx->err = "cudaStreamCreate"; return; }
+    slot.own_stream = true;
     cudaStreamSynchronize(ctx->stream);   // the uploads of the replicas are complete
-    for (int cur = 0; rc == LRR_OK; cur ^= 1) {
-      if ((rc = slot_collect(ctx, slot[cur])) != LRR_OK) break;
-      const int64_t a = cursor.fetch_add(run);
-      if (a >= njobs) break;
-      const cudaStream_t keep = g_alloc_stream;
-      rc = slot_launch(ctx, slot[cur], moving_all[d], fixed_all[d], pj.data(), a, std::min(run, njobs - a), perm.data(), 0, max_iter, shuffle_seed, pout.data());
-      g_alloc_stream = keep;
-    }
-    for (int k = 0; k < 2; ++k) { const int r2 = slot_collect(ctx, slot[k]); if (rc == LRR_OK) rc = r2; if (slot[k].own_stream) cudaStreamDestroy(slot[k].st); }
+    const cudaStream_t keep = g_alloc_stream;
+    rc = slot_launch(ctx, slot, moving_all[d], fixed_all[d], pj[(size_t)d].data(), 0, n, pid[(size_t)d].data(), 0, max_iter, shuffle_seed, pout[(size_t)d].data());
+    g_alloc_stream = keep;
+    { const int r2 = slot_collect(ctx, slot); if (rc == LRR_OK) rc = r2; }
+    cudaStreamDestroy(slot.st);
     rcs[(size_t)d] = rc;
   };
   std::vector<std::thread> th;
@@ -1933,7 +1930,7 @@ extern "C" int lrr_batch_run_multi(lrr_ctx** ctxs, int ndev, lrr_fset** moving_a
   worker(0);
   for (auto& t : th) t.join();
   for (int d = 0; d < ndev; ++d) if (rcs[(size_t)d] != LRR_OK) return rcs[(size_t)d];
-  for (int64_t i = 0; i < njobs; ++i) out[perm[(size_t)i]] = pout[(size_t)i];
+  for (int d = 0; d < ndev; ++d) for (size_t i = 0; i < pid[(size_t)d].size(); ++i) out[pid[(size_t)d][i]] = pout[(size_t)d][i];
   std::vector<int64_t> todo;
   for (int64_t j = 0; j < njobs; ++j) if (out[j].status < 0) todo.push_back(j);
   enter(ctxs[0]);
