@@ -1991,8 +1991,12 @@ extern "C" int lrr_batch_run_locations(lrr_ctx* ctx, lrr_fset* moving_all, lrr_f
     // ---- stage 2: one location per block, best angle first ----
     cu(cudaMemcpyAsync(dorder, order.data(), sizeof(int) * njobs, cudaMemcpyHostToDevice, st), "order H2D");
     cu(cudaMemcpyAsync(ddec, decisions, sizeof(lrr_decision) * njobs, cudaMemcpyHostToDevice, st), "decisions H2D");
-    lrr_batch_loc_args = BatchLocArgs{2, n_candidates, until_verified ? 1 : 0, dorder, ddec, voxel_spacing};
-    { PHASE(PH_BATCH); cu(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, nullptr, max_iter, shuffle_seed, table, rows, nb_run, work, wbytes, st, &ctx->launches), "registration launch"); }
+    // until verified: a unit of work is a LOCATION (its candidates one after the other, best angle first, stop at the first verified one).
+    // All candidates: nothing orders the registrations of a location, so every candidate is its own unit — 8192 units on 148 blocks instead
+    // of 256 (1.7 waves of 32-registration units: 2.32 s for the C4 list against 1.43 s for the plain list)
+    const bool per_job = !until_verified;
+    lrr_batch_loc_args = BatchLocArgs{2, per_job ? 1 : n_candidates, until_verified ? 1 : 0, per_job ? nullptr : dorder, ddec, voxel_spacing};
+    { PHASE(PH_BATCH); cu(lrr_batch_launch(moving_all->dev, fixed_all->dev, djobs, dout, njobs, nullptr, max_iter, shuffle_seed, table, rows, per_job ? nb_rank : nb_run, work, wbytes, st, &ctx->launches), "registration launch"); }
     lrr_batch_loc_args.mode = 0;
     cu(cudaMemcpyAsync(out, dout, sizeof(lrr_result) * njobs, cudaMemcpyDeviceToHost, st), "results D2H");
     cu(cudaMemcpyAsync(decisions, ddec, sizeof(lrr_decision) * njobs, cudaMemcpyDeviceToHost, st), "decisions D2H");
