@@ -79,7 +79,7 @@ __device__ __forceinline__ int cdc_prune(int2* cand, int cnt, int max_matches, i
   return nk;
 }
 
-__global__ void __launch_bounds__(LRR_CDC_THREADS) k_cdc_match(const __grid_constant__ CdcArgs a) {
+__global__ void __launch_bounds__(LRR_CDC_THREADS, 6) k_cdc_match(const __grid_constant__ CdcArgs a) {
   __shared__ double Bs[10][6];
   __shared__ int rowlo_s[LRR_CDC_WARPS][LRR_FLAT_ROWS + 1], rowbase_s[LRR_CDC_WARPS][LRR_FLAT_ROWS + 1];
   if (threadIdx.x < 60) {
@@ -310,7 +310,12 @@ size_t lrr_cdc_scratch_entries(int blocks) { return (size_t)blocks * LRR_CDC_WAR
 int lrr_cdc_blocks(int M) {
   // 80 registers per thread: six blocks of four warps per SM — the kernel is bound by the latency of its dependent phases (run bounds ->
   // points -> covariance records), not by bandwidth: the fixed set is L2-resident (0.96 -> see profiles/r2_summary.md)
-  long long b = ((long long)M + LRR_CDC_WARPS - 1) / LRR_CDC_WARPS, cap = (long long)lrr_num_sms() * 6;
+  // (the grid is what is resident at once: a seventh block per SM would run as a second wave behind the other six — measured 466 -> 695 us
+  //  when the kernel had grown to 96 registers and only five blocks fitted)
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cdc_match, LRR_CDC_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  if (per_sm > 6) per_sm = 6;
+  long long b = ((long long)M + LRR_CDC_WARPS - 1) / LRR_CDC_WARPS, cap = (long long)lrr_num_sms() * per_sm;
   if (b > cap) b = cap; if (b < 1) b = 1;
   return (int)b;
 }
