@@ -33,7 +33,7 @@ struct lrr_ctx {
   double* scratch_d = nullptr;
   void* pinned = nullptr;
   double* mailbox = nullptr; double* mailbox_dev = nullptr; unsigned long long mailbox_seq = 0; long long spec_misses = 0;   // result mailbox (mapped pinned, lrr_icp.cu)
-  // workspaces of the batched mode kept between calls (up to two: lrr_batch_run_multi has two launches in flight per device): with the
+  // workspaces of the batched mode kept between calls (up to two sizes: a warm-up and a full-size call alternate in practice): with the
   // slot pool of the time-sliced kernel a workspace is gigabytes, and a fresh allocation of that size from the driver costs tens of ms
   struct Ws { void* p; size_t bytes; }; std::vector<Ws> batch_ws; size_t batch_budget = 0;
   // instrumentation: CUDA-event timing per phase kernel (lrr_ctx_set_profiling)
