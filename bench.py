@@ -439,6 +439,15 @@ def run_b200(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one process per GPU on one host: every rank spins on its result mailbox and feeds its own launch queue, so each gets its own
+        # share of the host cores (a rank that lands on another rank's core was measured 20 % slower per iteration at N = 8)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 2:
+                os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+        except (AttributeError, OSError):
+            pass
     lib = lrr_b200.lib()
     pair = make_workload()
     stream = torch.cuda.Stream()
