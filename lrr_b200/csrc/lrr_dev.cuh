@@ -616,10 +616,24 @@ struct GridScope {
       double s[KL];
 #pragma unroll
       for (int j = 0; j < KL; ++j) s[j] = 0;
-#pragma unroll 8
-      for (unsigned int b = wid; b < gridDim.x; b += nw) {
+      // (the loads of RB rows are issued before the first add — one L2 round trip per RB rows instead of one per row, which was most
+      //  of a finalizer's time at two blocks per SM; the adds keep the ascending-row order, so the sums are bitwise the plain loop's)
+      constexpr int RB = KL >= 3 ? 4 : 8;
+      for (unsigned int b0 = wid; b0 < gridDim.x; b0 += RB * nw) {
+        double v[RB][KL];
 #pragma unroll
-        for (int j = 0; j < KL; ++j) { const int k = lane + 32 * j; if (k < KG) s[j] += __ldcg(&partials[(size_t)b * LRR_NRED + k]); }
+        for (int u = 0; u < RB; ++u) {
+          const unsigned int b = b0 + u * nw;
+#pragma unroll
+          for (int j = 0; j < KL; ++j) { const int k = lane + 32 * j; v[u][j] = (b < gridDim.x && k < KG) ? __ldcg(&partials[(size_t)b * LRR_NRED + k]) : 0.0; }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          if (b0 + u * nw < gridDim.x) {
+#pragma unroll
+            for (int j = 0; j < KL; ++j) s[j] += v[u][j];
+          }
+        }
       }
       __syncthreads();   // sh_tmp is free again
 #pragma unroll
