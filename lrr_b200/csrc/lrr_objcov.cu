@@ -14,6 +14,7 @@
 // log() each end in a slow-path branch); one 256-thread block per SM at ~200 registers beats two at 128 (fewer rows for the finalizer, no
 // register-starved schedule); keeping the NEXT trip's loads in flight as well (LRR_OBJ_PIPE = 2) was measured slower (73 us).
 #include "lrr_phases.cuh"
+#include <math_constants.h>
 
 struct ObjArgs {
   double A[9], t[3], c[3];          // transform in the frame the objective is evaluated in
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(LRR_OBJ_THREADS, LRR_OBJ_MINB) k_objcov(const 
   //  and sits in the same basic block, so the scheduler fills the chain's FP64 latency with it; lanes without a match run the chain on
   //  a clamped index with weight 0 and + I on their Cij, so that it stays finite)
   double pw = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0, pS[6] = {0, 0, 0, 0, 0, 0};
+  bool det_bad = false;
   const int k0 = -(j == 0), k1 = -(j == 1), k2 = -(j == 2);
   auto accumulate = [&]() {
 #pragma unroll
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(LRR_OBJ_THREADS, LRR_OBJ_MINB) k_objcov(const 
       // inverse and determinant of the symmetric 3x3
       const double c00 = Cij[3] * Cij[5] - Cij[4] * Cij[4], c01 = Cij[2] * Cij[4] - Cij[1] * Cij[5], c02 = Cij[1] * Cij[4] - Cij[2] * Cij[3];
       const double det = Cij[0] * c00 + Cij[1] * c01 + Cij[2] * c02;
+      det_bad |= !(det > 0.0 && det < CUDART_INF);   // indefinite / singular Cij: f is poisoned after the loop, as vcl_log would (no select in the chain)
       const double id = obj_rcp(det);
       const double Ci[6] = {c00 * id, c01 * id, c02 * id, (Cij[0] * Cij[5] - Cij[2] * Cij[2]) * id, (Cij[1] * Cij[2] - Cij[0] * Cij[4]) * id,
                             (Cij[0] * Cij[3] - Cij[1] * Cij[1]) * id};
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(LRR_OBJ_THREADS, LRR_OBJ_MINB) k_objcov(const 
     for (int p = 0; p < 6; ++p) pS[p] = S[p];
   }
   accumulate();
+  if (det_bad) acc[24] = CUDART_NAN;
 #else
   int s_next = (wfirst + lane) < a.M ? a.sidx[wfirst + lane] : -1;
   for (int base = wfirst; base < a.M; base += wstride) {
