@@ -332,10 +332,13 @@ void lrr_k_objcov_launch(const DirArgs& a, const double* A, const double* t, con
   for (int i = 0; i < 3; ++i) { o.t[i] = t[i]; o.c[i] = c[i]; o.cm[i] = norm8[i]; o.cf[i] = norm8[4 + i]; }
   o.rm = norm8[3]; o.rf = norm8[7]; o.Sigma = Sigma_dev;
   // one match per lane and trip; LRR_OBJ_MINB resident blocks per SM (LRR_MAX_BLOCKS rows of partial sums)
-  long long b = ((long long)a.M + LRR_OBJ_THREADS - 1) / LRR_OBJ_THREADS, cap = (long long)lrr_num_sms() * LRR_OBJ_MINB;
+  // (the pipelined loop lets a lane without a match load entry 0 of both sets: an empty set means no match, so no trip at all)
+  DirArgs aa = a;
+  if (a.to.n <= 0 || a.from_all.n <= 0) aa.M = 0;
+  long long b = ((long long)aa.M + LRR_OBJ_THREADS - 1) / LRR_OBJ_THREADS, cap = (long long)lrr_num_sms() * LRR_OBJ_MINB;
   if (cap > LRR_MAX_BLOCKS) cap = LRR_MAX_BLOCKS;
   if (b > cap) b = cap; if (b < 1) b = 1;
-  k_objcov<<<(int)b, LRR_OBJ_THREADS, 0, st>>>(a, o, partials, ticket); ++*launches;
+  k_objcov<<<(int)b, LRR_OBJ_THREADS, 0, st>>>(aa, o, partials, ticket); ++*launches;
 }
 
 // ---- cdcl_obj_fun_par<3,12>::compute (cdcl/cdcl_obj_fun_par.txx:46-144): the parameter objective of the CDC M-step -------------------
